@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- canonical k-mers counted per second at k=32 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C1] [--scale s]
+
+A "step" is one complete pass of the hot path over one batch of synthetic reads: fresh table ->
+pack (ASCII -> 2-bit) -> rolling canonical k-mer extraction + table insert -> clamp + occurrence
+histogram (+ hash-range exchange and histogram all-reduce when N > 1).
+
+  value  whole-job k-mer instances/s with the reads already resident in HBM (pbk_push_reads_device)
+  e2e    the same through the reference-facing C ABI with HOST buffers: H2D of the reads from pinned
+         memory and D2H of the histogram inside the timed region (pbk_push_reads + pbk_finalize)
+
+N = 1 runs BASELINE config C1 (4.6 Mb genome, 2x150 bp, 100x, k=32).  N > 1 is weak scaling: every
+rank gets a C1-sized slice of the C4 metagenome mix (20 genomes), keys are owned by hash range and
+(k-mer, count) records move with one NCCL all-to-all per step.
+
+`--impl reference` times the unmodified reference (`oracle/_ref/platanus_b assemble -kmer_occ_only`,
+OpenMP, all host cores) on a bounded sample of the same workload; the same run is embedded as
+`cpu_baseline` in the default arm at N = 1.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 32
+METRIC = "canonical k-mers counted/sec at k=32"
+UNIT = "k-mers/s"
+BYTES_PER_INSTANCE = {150: 65.26, 250: 65.14}          # SURVEY.md section 8d (k=32)
+CPU_SAMPLE_DIV = 16                                     # reference arm: 1/16 of the N=1 workload
+
+
+def algorithmic_bytes_per_instance(read_len: int, k: int) -> float:
+    return read_len / (read_len - k + 1.0) + 64.0
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference arm / cpu_baseline
+# ------------------------------------------------------------------------------------------------
+
+def reference_sample(workload: str, scale: float):
+    from platanus_b_b200 import synth
+    spec = synth.config(workload, scale=scale)
+    max_pairs = max(1, spec.n_pairs // CPU_SAMPLE_DIV)
+    rs = synth.make_reads(spec, max_pairs=max_pairs)
+    return spec, rs, f"first 1/{CPU_SAMPLE_DIV} of the {workload} read pairs ({rs.n_reads} reads x {rs.read_len} bp)"
+
+
+def count_instances(rs, k: int) -> int:
+    is_n = rs.reads == ord("N")
+    n = rs.reads.shape[0]
+    csum = np.concatenate([np.zeros((n, 1), np.int32), np.cumsum(is_n, axis=1, dtype=np.int32)], axis=1)
+    return int(((csum[:, k:] - csum[:, :-k]) == 0).sum())
+
+
+def run_reference_once(files, workdir, threads, mem_gb):
+    from oracle import oracle as O
+    r = O.run_reference(files, K, workdir, threads=threads, mem_gb=mem_gb, parse_bin=False)
+    if r.returncode != 0:
+        raise RuntimeError("reference failed: " + r.stderr[-400:])
+    return r.wall_s
+
+
+def cpu_baseline(workload: str, scale: float, steps: int, warmup: int):
+    """The unmodified reference on the host cores of this box; a reported baseline, not the target."""
+    from oracle import oracle as O
+    from platanus_b_b200 import synth
+    if not O.have_ref_binary():
+        return None
+    spec, rs, sample = reference_sample(workload, scale)
+    n_inst = count_instances(rs, K)
+    cores = os.cpu_count() or 1
+    tmp = tempfile.mkdtemp(prefix="pbk_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        files = synth.write_fastq(rs, os.path.join(tmp, "r_1.fq"), os.path.join(tmp, "r_2.fq"))
+        for _ in range(warmup):
+            run_reference_once(files, tmp, cores, 2)
+        t = [run_reference_once(files, tmp, cores, 2) for _ in range(max(1, steps))]
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    wall = float(np.mean(t))
+    return {"value": n_inst / wall, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": sample + f"; platanus_b assemble -kmer_occ_only -k {K} -t {cores} -m 2, whole-process wall clock "
+                               f"{wall:.2f} s incl. FASTQ parse and kmer_occ.bin write",
+            "n_instances": n_inst, "ms_per_step": wall * 1e3}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    base = cpu_baseline(args.workload, args.scale, args.steps, args.warmup)
+    if base is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/platanus_b has not been built"}))
+        return 0
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": args.workload, "k": K, "scale": args.scale, "sample": base["sample"]},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from platanus_b_b200 import KmerCounter, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- workload -------------------------------------------------------------------------------
+    if world == 1:
+        spec = synth.config(args.workload, scale=args.scale)
+        rs = synth.make_reads(spec)
+        workload = f"{args.workload}: {spec.total_genome} bp genome, 2x{spec.read_len} bp PE, {spec.coverage:g}x, k={K}"
+    else:
+        c1 = synth.config("C1", scale=args.scale)
+        spec = synth.config("C4", scale=args.scale)
+        rs = synth.make_reads(spec, pair_slice=(rank, max(world, int(round(spec.n_pairs / c1.n_pairs)))))
+        workload = (f"C4 metagenome mix (20 genomes, {spec.total_genome} bp), 2x{spec.read_len} bp PE: one C1-sized "
+                    f"slice of {rs.n_reads} reads per GPU, k={K}, keys owned by hash range")
+    bases, offsets = rs.flat()
+    n_reads, n_bases, L = rs.n_reads, int(bases.shape[0]), rs.read_len
+    n_inst_local = count_instances(rs, K)
+
+    h_bases = torch.from_numpy(bases.copy()).pin_memory()
+    h_offs = torch.from_numpy(offsets.astype(np.int64)).pin_memory()
+    d_bases = h_bases.cuda()
+    d_offs = h_offs.cuda()
+    torch.cuda.synchronize()
+
+    kc = KmerCounter(K, device=local_rank, n_shards=world, shard_rank=rank, timing=True)
+    W = kc.words
+    send_buf = recv_buf = None
+    hist_dev = torch.zeros(65535, dtype=torch.int64, device="cuda")
+
+    def exchange():
+        """hash-range all-to-all of pre-aggregated (k-mer, count) records + histogram all-reduce"""
+        nonlocal send_buf, recv_buf
+        cnt = kc.shard_send_counts(world).astype(np.int64)
+        send_counts = torch.from_numpy(cnt).cuda()
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts)
+        rc = recv_counts.cpu().numpy()
+        n_send, n_recv = int(cnt.sum()), int(rc.sum())
+        if send_buf is None or send_buf.shape[0] < n_send + 1:
+            send_buf = torch.empty((int(n_send * 1.2) + 1024, W + 1), dtype=torch.int64, device="cuda")
+        if recv_buf is None or recv_buf.shape[0] < n_recv + 1:
+            recv_buf = torch.empty((int(n_recv * 1.2) + 1024, W + 1), dtype=torch.int64, device="cuda")
+        kc.shard_pack_device(send_buf.data_ptr(), send_buf.shape[0])
+        dist.all_to_all_single(recv_buf[:n_recv], send_buf[:n_send], rc.tolist(), cnt.tolist())
+        torch.cuda.current_stream().synchronize()
+        kc.shard_insert_device(recv_buf.data_ptr(), n_recv)
+        return n_send * (W + 1) * 8
+
+    def step(resident: bool):
+        kc.reset()
+        if resident:
+            kc.push_reads_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, n_bases)
+        else:
+            kc.push_reads_ptr(h_bases.data_ptr(), h_offs.data_ptr(), n_reads)
+        sent = exchange() if world > 1 else 0
+        kc.finalize_light()                     # D2H of the occurrence histogram: the step's result
+        if world > 1:
+            hist_dev.copy_(torch.from_numpy(kc.occ_hist.astype(np.int64)), non_blocking=False)
+            dist.all_reduce(hist_dev)
+            torch.cuda.current_stream().synchronize()
+        return sent
+
+    def timed(resident: bool, steps: int, warmup: int):
+        for _ in range(warmup):
+            step(resident)
+        s0 = kc.stats()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        kc.timer_mark(0)
+        t0 = time.perf_counter()
+        sent = 0
+        for _ in range(steps):
+            sent += step(resident)
+        kc.timer_mark(1)
+        ms_dev = kc.timer_elapsed_ms(0, 1)
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        clocks = sampler.stop() if rank == 0 else None
+        ms = max(ms_dev, 0.0)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        s1 = kc.stats()
+        delta = {k: s1[k] - s0[k] for k in s1 if isinstance(s1[k], (int, float))}
+        return ms, wall_ms, delta, clocks, sent
+
+    total_inst = n_inst_local
+    if world > 1:
+        t = torch.tensor([n_inst_local], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        total_inst = int(t.item())
+
+    ms_res, wall_res, d_res, clocks, sent_res = timed(True, args.steps, args.warmup)
+    ms_e2e, wall_e2e, d_e2e, clocks_e2e, _ = timed(False, args.steps, max(1, args.warmup // 2))
+
+    # sanity: the counter saw exactly the windows we expect
+    assert kc.n_instances == n_inst_local or world > 1, (kc.n_instances, n_inst_local)
+
+    value = total_inst * args.steps / (ms_res * 1e-3)
+    e2e = total_inst * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (count_kernel: extraction + table insert) ----------------
+    peak, peak_src = measured_peaks()
+    bpi = algorithmic_bytes_per_instance(L, K)
+    launches = max(1, int(d_res["launches_count"]))
+    inst_per_launch = n_inst_local * args.steps / launches
+    ms_per_launch = d_res["ms_count"] / launches
+    achieved = bpi * inst_per_launch / (ms_per_launch * 1e-3) / 1e9 if ms_per_launch > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "count_kernel<1> (rolling canonical k-mers + table insert)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_instance": bpi,
+                "instances_per_launch": inst_per_launch, "ms_per_launch": ms_per_launch,
+                "kernel_share_of_step": d_res["ms_count"] / max(ms_res, 1e-9)}
+
+    line = None
+    if rank == 0:
+        base = cpu_baseline(args.workload, args.scale, 1, 0) if (world == 1 and not args.no_cpu_baseline) else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload, "k": K, "instances_per_step": total_inst,
+                       "reads_per_gpu": n_reads, "input_bytes_per_gpu": n_bases + (n_reads + 1) * 8,
+                       "l2": "inputs (>= 460 MB per GPU) and table are larger than the 126 MB L2; no explicit flush",
+                       "timed_region": "reset + push (pack, count) + finalize (clamp + histogram), device stopwatch "
+                                       "on the library's compute stream, max over ranks"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(d_e2e["h2d_bytes"] / args.steps),
+                    "d2h_bytes_per_step": int(d_e2e["d2h_bytes"] / args.steps), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(d_res["launches_pack"] + d_res["launches_count"] + d_res["launches_other"]),
+            "roofline": roofline,
+            "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
+            "kernel_ms_per_step": {"pack": d_res["ms_pack"] / args.steps, "count": d_res["ms_count"] / args.steps,
+                                   "other": d_res["ms_other"] / args.steps},
+            "wall_ms_per_step": wall_res / args.steps,
+            "table": {"slots": int(kc.stats()["table_slots"]), "bytes": int(kc.stats()["table_bytes"]),
+                      "distinct_local": int(kc.n_distinct), "grows_in_timed_region": int(d_res["n_grow"])},
+        }
+        if world > 1:
+            line["exchange_bytes_sent_per_gpu_per_step"] = int(sent_res / args.steps)
+        if base is not None:
+            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    kc.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C1")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

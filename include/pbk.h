@@ -1,0 +1,197 @@
+/*
+ * pbk.h -- C ABI of libpbk.so: B200-native (sm_100a) k-mer occurrence counting for Platanus_B.
+ *
+ * This is the drop-in boundary for ONE path of the reference: what
+ *     Counter<KMER>::makeKmerReadDistributionMT            (reference counter.h:276-383)
+ * and the functions it drives (countKmerPerThreadFirst counter.h:391-434, countKmerOrWriteTemporary
+ * counter.h:459-476, writeKmerDistribution counter.h:483-507) compute, plus the consumers of its
+ * result that run before the `-kmer_occ_only` return: getLeftLocalMinimalValue (counter.h:245-267),
+ * sortedKeyFromKmerFile (counter.h:917-951), loadKmer (counter.h:600-640) and
+ * outputOccurrenceTableBinary / DoubleHash::writeTable (counter.h:955-963, doubleHash.h:266-278).
+ *
+ * The reference has no FFI layer: the seam is the header-only template
+ * Counter<KMER>.  The host C++ shim that re-implements those member functions on top of this ABI
+ * is platanus_b_b200/host/pbk_counter_shim.h; INTEGRATION.md shows how a maintainer wires it in.
+ *
+ * Conventions: plain C types only; every function returns 0 (PBK_OK) or a negative pbk_status;
+ * no exceptions cross the boundary; the caller owns every host buffer it passes in; the context
+ * owns all device memory and streams.  A context is used from one host thread at a time.
+ * There is NO CPU fallback: without a usable CUDA device pbk_create fails with PBK_E_NO_DEVICE.
+ */
+#ifndef PBK_H
+#define PBK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBK_ABI_VERSION   1
+#define PBK_OCC_BINS      65535u    /* counter.h:336: occurrenceDistribution.resize(UINT16_MAX)      */
+#define PBK_LEN_BINS      500001u   /* counter.h:328: lengthDistribution, MAX_READ_LEN + 1 bins      */
+#define PBK_COUNT_SAT     65534u    /* counter.h:468: counts saturate at UINT16_MAX - 1              */
+#define PBK_MAX_K         256u      /* keys of up to 8 x 64-bit words (reference: unbounded binstr_t) */
+
+typedef enum pbk_status {
+    PBK_OK              =  0,
+    PBK_E_ARG           = -1,   /* bad argument                                                    */
+    PBK_E_NO_DEVICE     = -2,   /* no CUDA device / driver: there is no CPU fallback                */
+    PBK_E_CUDA          = -3,   /* a CUDA call failed; pbk_last_error() has the text                */
+    PBK_E_NOMEM         = -4,   /* device (HBM budget) or host memory exhausted                     */
+    PBK_E_READ_TOO_LONG = -5,   /* a read has >= 500000 bases: platanus::ReadError (common.h:465)   */
+    PBK_E_BAD_BASE      = -6,   /* a character whose Char2Bin code (common.h:256) is undefined      */
+    PBK_E_KMER_DIST     = -7,   /* empty distribution: platanus::KmerDistError (counter.h:225-237)  */
+    PBK_E_STATE         = -8,   /* call out of order (e.g. export before finalize)                  */
+    PBK_E_IO            = -9,   /* file could not be written: platanus::FILEError                   */
+    PBK_E_UNSUPPORTED_K = -10   /* k == 0 or k > PBK_MAX_K                                          */
+} pbk_status;
+
+typedef struct pbk_ctx pbk_ctx;
+
+enum {
+    PBK_ENC_ASCII    = 0,  /* raw characters as the parser hands them to SEQ::convertFromString     */
+    PBK_ENC_PLATANUS = 1   /* SEQ temp-file form (common.h:426-448): bytes 0..3, N positions listed */
+};
+
+enum {
+    PBK_F_TIMING = 1u << 0  /* bracket every kernel launch with CUDA events (see pbk_get_stats)      */
+};
+
+typedef struct pbk_config {
+    uint32_t struct_size;        /* sizeof(pbk_config), for ABI evolution                           */
+    uint32_t k;                  /* k-mer length, 1..PBK_MAX_K                                      */
+    int32_t  device;             /* CUDA device ordinal, -1 = current device                        */
+    uint32_t flags;              /* PBK_F_*                                                         */
+    uint32_t n_shards;           /* 0/1 = unsharded; >1: this context owns hash range `shard_rank`  */
+    uint32_t shard_rank;
+    uint64_t table_slots_hint;   /* initial table capacity in slots, 0 = derive from the first push */
+    uint64_t hbm_budget_bytes;   /* cap on device memory used by the context, 0 = 85% of free HBM   */
+} pbk_config;
+
+/* counters of the work done so far; durations are CUDA-event times on the context's own streams */
+typedef struct pbk_stats {
+    uint64_t n_reads;
+    uint64_t n_bases;
+    uint64_t n_instances;        /* k-mer windows inserted                                          */
+    uint64_t n_distinct;
+    uint64_t table_slots;
+    uint64_t table_bytes;
+    uint64_t n_grow;             /* table rebuilds                                                  */
+    uint64_t launches_pack;      /* kernel launches by class                                        */
+    uint64_t launches_count;
+    uint64_t launches_other;
+    double   ms_pack;            /* only filled with PBK_F_TIMING                                   */
+    double   ms_count;
+    double   ms_other;
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+} pbk_stats;
+
+const char *pbk_strerror(int status);
+/* text of the last failure on this context (valid until the next call on it) */
+const char *pbk_last_error(const pbk_ctx *ctx);
+int  pbk_abi_version(void);
+
+int  pbk_create(pbk_ctx **out, const pbk_config *cfg);
+void pbk_destroy(pbk_ctx *ctx);
+
+/* Pinned host memory for callers that want the H2D copies to run at full PCIe speed. */
+int  pbk_host_alloc(void **out, size_t bytes);
+void pbk_host_free(void *p);
+
+/*
+ * Count the k-mers of a batch of reads (may be called repeatedly before pbk_finalize).
+ *   bases         concatenated reads, read_offsets[n_reads] bytes, no separators
+ *   read_offsets  n_reads + 1 ascending byte offsets into `bases`
+ *   encoding      PBK_ENC_ASCII: characters (upper or lower case ACGTN, Char2Bin semantics).
+ *                 PBK_ENC_PLATANUS: codes 0..3; N positions in n_pos[n_pos_offsets[r] ..
+ *                 n_pos_offsets[r+1]) (read-relative, as SEQ::positionUnknown); the byte under an N
+ *                 is ignored exactly like the reference (common.h:468-476).
+ * Replaces the per-thread loops of counter.h:322-325 over the read temp files.
+ * Host pointers.  Returns after the batch has been queued and its inputs consumed.
+ */
+int  pbk_push_reads(pbk_ctx *ctx, const uint8_t *bases, const uint64_t *read_offsets, uint64_t n_reads,
+                    int encoding, const int32_t *n_pos, const uint64_t *n_pos_offsets);
+
+/* Same with `bases` and `read_offsets` already resident in device memory (PBK_ENC_ASCII only). */
+int  pbk_push_reads_device(pbk_ctx *ctx, const void *d_bases, const void *d_read_offsets,
+                           uint64_t n_reads, uint64_t n_bases);
+
+/*
+ * Finish counting: clamp counts to 65534 and build the distributions
+ * (writeKmerDistribution counter.h:483-507, counter.h:328-333, 371-376).
+ *   occ_hist   PBK_OCC_BINS u64, [c] = number of distinct k-mers with clamped count c
+ *   len_hist   PBK_LEN_BINS u64 read-length histogram over all reads; may be NULL
+ * Any output pointer may be NULL.
+ */
+int  pbk_finalize(pbk_ctx *ctx, uint64_t *occ_hist, uint64_t *len_hist,
+                  uint64_t *n_distinct, uint64_t *n_instances, uint64_t *max_occurrence);
+
+/*
+ * Dump the table: every distinct canonical k-mer with clamped count >= min_count.
+ *   keys    n x ceil(k/32) u64, word 0 (the LAST 32 bases, kmer.h:119/237 order) first
+ *   counts  n u16
+ *   sorted  non-zero: ascending in the reference's numeric order (top word first,
+ *           binstr.h:460-466) -- what sortedKeyFromKmerFile (counter.h:917-951) produces
+ * With capacity == 0 only *n_out is written (size query).  Needs pbk_finalize first.
+ */
+int  pbk_export(pbk_ctx *ctx, uint32_t min_count, int sorted, uint64_t *keys, uint16_t *counts,
+                uint64_t capacity, uint64_t *n_out);
+
+int  pbk_get_stats(const pbk_ctx *ctx, pbk_stats *out);
+
+/* Device-side stopwatch on the context's own compute stream (the stream every kernel of this context
+ * is launched on, and that waits for every H2D copy): pbk_timer_mark records CUDA event `slot`
+ * (0..7); pbk_timer_elapsed_ms waits for event `stop` and returns the time between two marks. */
+int  pbk_timer_mark(pbk_ctx *ctx, int slot);
+int  pbk_timer_elapsed_ms(pbk_ctx *ctx, int start, int stop, double *ms);
+
+/* Forget all counts but keep device buffers; optionally change k (k sweep over the same process). */
+int  pbk_reset(pbk_ctx *ctx, uint32_t k);
+
+/* ---- hash-range sharding across GPUs (one context per GPU) --------------
+ * With cfg.n_shards > 1, pbk_push_reads inserts the k-mers this shard owns and stages the others,
+ * pre-aggregated, per destination.  The caller moves them with its collective of choice
+ * (torch.distributed / NCCL all-to-all) and feeds what it received to pbk_shard_insert.        */
+/* bytes of one staged record: ceil(k/32) u64 key words + one u64 count                            */
+uint32_t pbk_shard_record_bytes(const pbk_ctx *ctx);
+/* number of staged records per destination shard (n_shards entries; own entry is 0)               */
+int  pbk_shard_send_counts(pbk_ctx *ctx, uint64_t *counts);
+/* copy the staged records, grouped by destination in shard order, into a device buffer of the
+ * caller (device pointer, capacity in records) and clear the staging area                        */
+int  pbk_shard_pack_device(pbk_ctx *ctx, void *d_records, uint64_t capacity_records);
+/* insert n records (device pointer) received from other shards                                    */
+int  pbk_shard_insert_device(pbk_ctx *ctx, const void *d_records, uint64_t n_records);
+/* owner shard of a key (host helper, same function as on the device)                              */
+uint32_t pbk_shard_of_key(const uint64_t *key_words, uint32_t k, uint32_t n_shards);
+
+/* ---- host-side pieces of the path that stay on the CPU (negligible cost) --- */
+/* Counter::getLeftLocalMinimalValue (counter.h:245-267) */
+uint64_t pbk_left_local_min(const uint64_t *occ_hist, uint64_t max_occurrence, uint64_t window);
+/* cutoff rule of Assemble::initialKmerAssemble (assemble.cpp:318-321); n_opt = -n, repeat = -repeat */
+uint64_t pbk_coverage_cutoff(const uint64_t *occ_hist, uint64_t max_occurrence, int n_opt, int repeat);
+/* Counter::calcDistributionAverage (counter.h:221-238); PBK_E_KMER_DIST when empty */
+int  pbk_distribution_average(const uint64_t *dist, uint64_t n_bins, uint64_t start, uint64_t end, double *out);
+/* doubleHashSize returned by makeKmerReadDistributionMT (counter.h:300-309) for -m `memory_bytes` */
+uint64_t pbk_double_hash_size(uint64_t memory_bytes, uint32_t k);
+/* Counter::outputOccurrenceDistribution (counter.h:1000-1007): PREFIX_<k>merFrq.tsv */
+int  pbk_write_frq_tsv(const char *path, const uint64_t *occ_hist, uint64_t max_occurrence);
+/* loadKmer + outputOccurrenceTableBinary (counter.h:600-640, 955-963; doubleHash.h:266-278):
+ * PREFIX_kmer_occ.bin from n (key, count) entries, all of which are written.  Records are placed
+ * by DoubleHash probing so that the reference's readTable/find_any (doubleHash.h:280-293, 170-184)
+ * finds them.  *load_size_out (may be NULL) receives loadKmer's return value. */
+int  pbk_write_kmer_occ_bin(const char *path, uint32_t k, const uint64_t *keys, const uint16_t *counts,
+                            uint64_t n, uint64_t double_hash_size, uint64_t *load_size_out);
+
+/* ---- measurement helper: random read-modify-write rate of this GPU's memory system -------------
+ * Uniform-random 64-bit key probe + 32-bit atomic add on a table of `table_bytes` (SURVEY.md 8d:
+ * R_atomic).  mode 0: red.add only; 1: ld key + red.add (steady-state hit path); 2: CAS-claim
+ * inserts of distinct keys.  Returns operations per second in *ops_per_s. */
+int  pbk_microbench_atomics(int device, uint64_t table_bytes, uint64_t n_ops, int mode, double *ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBK_H */

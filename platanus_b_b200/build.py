@@ -1,0 +1,55 @@
+"""Build libpbk.so in-tree (nvcc, sm_100a only).  Usable as `python -m platanus_b_b200.build`."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "_lib")
+LIB = os.path.join(OUT_DIR, "libpbk.so")
+
+NVCC = os.environ.get("PBK_NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
+UNITS = ["pbk_kernels.cu", "pbk_api.cu", "pbk_host.cpp"]
+HEADERS = ["pbk_device.cuh", "pbk_kernels.cuh", os.path.join("..", "..", "include", "pbk.h")]
+
+
+def _stale(target: str, deps: list) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OUT_DIR, exist_ok=True)
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS]
+    env = dict(os.environ)
+    env.pop("CXX", None)        # the image exports a wrapper CXX that breaks host linking
+    env.pop("CC", None)
+
+    def compile_one(unit: str) -> str:
+        src = os.path.join(CSRC, unit)
+        obj = os.path.join(OUT_DIR, os.path.splitext(unit)[0] + ".o")
+        if force or _stale(obj, [src] + hdrs):
+            cmd = [NVCC, *ARCH, *CFLAGS, "-ccbin", "g++", "-c", src, "-o", obj]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd), file=sys.stderr)
+            subprocess.run(cmd, check=True, env=env)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
+        objs = list(ex.map(compile_one, UNITS))
+    if force or _stale(LIB, objs):
+        subprocess.run([NVCC, *ARCH, "-ccbin", "g++", "-shared", "-o", LIB, *objs, "-cudart", "static"],
+                       check=True, env=env)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))

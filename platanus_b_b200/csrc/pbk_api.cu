@@ -1,0 +1,757 @@
+// pbk_api.cu -- the C ABI of libpbk.so (include/pbk.h): context, streams, batching, table growth.
+//
+// One context drives one GPU.  Reads arrive in batches (pbk_push_reads); each batch is cut into
+// chunks of CHUNK_BASES bases that flow  H2D copy (copy stream, double-buffered)  ->  pack kernel
+// ->  count kernel (compute stream).  After every chunk the host reads a 48-byte counter block to
+// decide whether the table has to grow; nothing else crosses PCIe until pbk_finalize/pbk_export.
+#include "../../include/pbk.h"
+#include "pbk_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace pbk;
+
+namespace {
+
+constexpr u64 CHUNK_BASES = 1ull << 25;          // 32 Mi bases per pipeline stage (multiple of 32)
+constexpr u64 MIN_SLOTS = 1ull << 16;
+constexpr double MAX_LOAD = 0.5;
+constexpr u64 U32_HEADROOM = (1ull << 32) - 65536 - 2;
+
+enum LaunchClass { LC_PACK = 0, LC_COUNT = 1, LC_OTHER = 2 };
+
+struct TimedSpan { cudaEvent_t a, b; int cls; };
+
+}  // namespace
+
+struct pbk_ctx {
+    int device = 0, sm_count = 148;
+    u32 k = 0; int W = 0; u32 flags = 0;
+    ShardInfo shard{1, 0};
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    u64 budget = 0, used = 0;
+
+    // batch buffers (grow-only)
+    u64 *d_stream_raw = nullptr; u32 *d_nflag_raw = nullptr, *d_rflag_raw = nullptr; u64 stream_cap_words = 0;
+    u64 *d_offsets = nullptr; u64 offsets_cap = 0;
+    uint8_t *d_stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0;
+    cudaEvent_t ev_copy_done[2] = {nullptr, nullptr}, ev_stage_free[2] = {nullptr, nullptr};
+
+    TableView table{nullptr, 0, 0}, remote{nullptr, 0, 0};
+    u64 occupied = 0, occupied_remote = 0;
+    u64 table_hint = 0;
+    Counters *d_ctr = nullptr, *h_ctr = nullptr;
+    Counters last{};                 // cumulative counters at the last read-back
+    u64 *d_ovf = nullptr; u64 ovf_cap = 0;
+    u64 *d_len_hist = nullptr, *d_occ_hist = nullptr, *d_shard_counts = nullptr;
+    std::vector<u64> h_occ_hist, h_shard_counts;
+
+    bool finalized = false;
+    u64 n_reads = 0, n_bases = 0, inst_since_clamp = 0, n_grow = 0;
+    double new_ratio = 0.20;         // new keys per window, adapted from what the data shows
+    u64 launches[3] = {0, 0, 0};
+    double ms[3] = {0, 0, 0};
+    std::vector<TimedSpan> spans;
+    cudaEvent_t timer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    u64 h2d_bytes = 0, d2h_bytes = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(pbk_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(c, e__ == cudaErrorMemoryAllocation ? PBK_E_NOMEM : PBK_E_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                                \
+    } while (0)
+
+#define TRY(call) do { int rc__ = (call); if (rc__ != PBK_OK) return rc__; } while (0)
+
+int dev_alloc(pbk_ctx *c, void **p, size_t bytes)
+{
+    if (bytes == 0) bytes = 8;
+    if (c->used + bytes > c->budget)
+        return fail(c, PBK_E_NOMEM, "HBM budget exceeded: %.1f MB in use + %.1f MB requested > %.1f MB",
+                    c->used / 1e6, bytes / 1e6, c->budget / 1e6);
+    CK(cudaMalloc(p, bytes));
+    c->used += bytes;
+    return PBK_OK;
+}
+
+void dev_free(pbk_ctx *c, void *p, size_t bytes)
+{
+    if (!p) return;
+    cudaFree(p);
+    if (bytes == 0) bytes = 8;
+    c->used -= std::min<u64>(c->used, bytes);
+}
+
+struct Span {
+    pbk_ctx *c; int cls; TimedSpan t{nullptr, nullptr, 0}; bool on;
+    Span(pbk_ctx *c_, int cls_) : c(c_), cls(cls_), on((c_->flags & PBK_F_TIMING) != 0)
+    {
+        c->launches[cls] += 1;
+        if (on) {
+            cudaEventCreate(&t.a); cudaEventCreate(&t.b); t.cls = cls;
+            cudaEventRecord(t.a, c->s_compute);
+        }
+    }
+    ~Span() { if (on) { cudaEventRecord(t.b, c->s_compute); c->spans.push_back(t); } }
+};
+
+void resolve_spans(pbk_ctx *c)
+{
+    for (auto &s : c->spans) {
+        float ms = 0;
+        if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) c->ms[s.cls] += ms;
+        cudaEventDestroy(s.a); cudaEventDestroy(s.b);
+    }
+    c->spans.clear();
+}
+
+u64 round_slots(u64 want) { return std::max<u64>(MIN_SLOTS, (want + 1023) & ~1023ull); }
+
+int table_alloc(pbk_ctx *c, TableView *t, u64 slots)
+{
+    t->words = c->W; t->cap = slots; t->slots = nullptr;
+    TRY(dev_alloc(c, &t->slots, t->bytes()));
+    { Span sp(c, LC_OTHER); launch_table_init(*t, c->s_compute); }
+    CK(cudaGetLastError());
+    return PBK_OK;
+}
+
+int read_counters(pbk_ctx *c)
+{
+    CK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));
+    c->d2h_bytes += sizeof(Counters);
+    const Counters &n = *c->h_ctr;
+    c->occupied += n.new_keys - c->last.new_keys;
+    c->occupied_remote += n.new_keys_remote - c->last.new_keys_remote;
+    c->inst_since_clamp += n.instances - c->last.instances;
+    c->last = n;
+    if (n.error_flags & ERR_READ_TOO_LONG) return fail(c, PBK_E_READ_TOO_LONG, "a read has >= 500000 bases");
+    if (n.error_flags & ERR_BAD_BASE) return fail(c, PBK_E_BAD_BASE, "input contains a character with no Char2Bin code (only ACGTN, any case)");
+    if (n.error_flags & ERR_OVERFLOW_LOST) return fail(c, PBK_E_CUDA, "internal: overflow list exhausted");
+    return PBK_OK;
+}
+
+int grow_table(pbk_ctx *c, TableView *t, u64 occupied, u64 want_slots)
+{
+    const u64 ns = round_slots(std::max<u64>(t->cap + t->cap / 2, want_slots));
+    TableView nt{nullptr, ns, c->W};
+    TRY(table_alloc(c, &nt, ns));
+    { Span sp(c, LC_OTHER); launch_table_rehash(*t, nt, c->d_ctr, c->s_compute); }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->s_compute));
+    dev_free(c, t->slots, t->bytes());
+    *t = nt;
+    c->n_grow += 1;
+    (void)occupied;
+    return PBK_OK;
+}
+
+// make room for `expect_new` more keys in the main (and, when sharded, the remote) table
+int ensure_room(pbk_ctx *c, u64 expect_new)
+{
+    u64 local_new = expect_new, remote_new = 0;
+    if (c->shard.n_shards > 1) {
+        local_new = expect_new / c->shard.n_shards + 1;
+        remote_new = expect_new - local_new + 1;
+    }
+    if ((double)(c->occupied + local_new) > MAX_LOAD * (double)c->table.capacity())
+        TRY(grow_table(c, &c->table, c->occupied, (u64)((c->occupied + local_new) / MAX_LOAD) + 1));
+    if (c->shard.n_shards > 1 && (double)(c->occupied_remote + remote_new) > MAX_LOAD * (double)c->remote.capacity())
+        TRY(grow_table(c, &c->remote, c->occupied_remote, (u64)((c->occupied_remote + remote_new) / MAX_LOAD) + 1));
+    return PBK_OK;
+}
+
+int ensure_overflow(pbk_ctx *c, u64 records)
+{
+    if (records <= c->ovf_cap) return PBK_OK;
+    if (c->d_ovf) { CK(cudaStreamSynchronize(c->s_compute)); dev_free(c, c->d_ovf, c->ovf_cap * (c->W + 1) * 8); c->d_ovf = nullptr; c->ovf_cap = 0; }
+    TRY(dev_alloc(c, (void **)&c->d_ovf, records * (c->W + 1) * 8));
+    c->ovf_cap = records;
+    return PBK_OK;
+}
+
+// keys that found no slot within MAX_PROBE: grow, then insert them from a private copy
+int drain_overflow(pbk_ctx *c)
+{
+    while (c->h_ctr->overflow_n > 0) {
+        const u64 n = std::min<u64>(c->h_ctr->overflow_n, c->ovf_cap);
+        const size_t bytes = n * (c->W + 1) * 8;
+        u64 *tmp = nullptr;
+        TRY(dev_alloc(c, (void **)&tmp, bytes));
+        CK(cudaMemcpyAsync(tmp, c->d_ovf, bytes, cudaMemcpyDeviceToDevice, c->s_compute));
+        CK(cudaMemsetAsync(&c->d_ctr->overflow_n, 0, sizeof(u64), c->s_compute));
+        c->last.overflow_n = 0;
+        int rc = grow_table(c, &c->table, c->occupied, (u64)((c->occupied + n) / MAX_LOAD) * 2 + 1);
+        if (rc == PBK_OK && c->shard.n_shards > 1)
+            rc = grow_table(c, &c->remote, c->occupied_remote, (u64)((c->occupied_remote + n) / MAX_LOAD) * 2 + 1);
+        if (rc == PBK_OK) {
+            Span sp(c, LC_COUNT);
+            launch_insert_records(tmp, n, true, c->table, c->remote, c->shard, c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+        }
+        if (rc == PBK_OK) rc = read_counters(c);
+        else cudaStreamSynchronize(c->s_compute);
+        dev_free(c, tmp, bytes);
+        TRY(rc);
+    }
+    return PBK_OK;
+}
+
+int maybe_clamp(pbk_ctx *c, u64 upcoming)
+{
+    if (c->inst_since_clamp + upcoming < U32_HEADROOM) return PBK_OK;
+    { Span sp(c, LC_OTHER); launch_table_clamp(c->table, c->s_compute); }
+    if (c->shard.n_shards > 1) { Span sp(c, LC_OTHER); launch_table_clamp(c->remote, c->s_compute); }
+    CK(cudaGetLastError());
+    c->inst_since_clamp = 0;
+    return PBK_OK;
+}
+
+int ensure_tables(pbk_ctx *c, u64 first_batch_windows)
+{
+    if (c->table.slots) return PBK_OK;
+    u64 want = c->table_hint ? c->table_hint : (u64)(first_batch_windows * c->new_ratio / MAX_LOAD) + 1;
+    if (c->shard.n_shards > 1) {
+        TRY(table_alloc(c, &c->remote, round_slots(want)));     // remote-staging table holds (n-1)/n of the keys
+        want = want / c->shard.n_shards + 1;
+    }
+    TRY(table_alloc(c, &c->table, round_slots(want)));
+    return PBK_OK;
+}
+
+int ensure_batch_buffers(pbk_ctx *c, u64 n_bases, u64 n_reads)
+{
+    const u64 words = (n_bases + 31) / 32;
+    if (words > c->stream_cap_words) {
+        CK(cudaStreamSynchronize(c->s_compute));
+        const u64 old = c->stream_cap_words ? c->stream_cap_words + STREAM_PAD_WORDS : 0;
+        dev_free(c, c->d_stream_raw, old * 8); dev_free(c, c->d_nflag_raw, old * 4); dev_free(c, c->d_rflag_raw, old * 4);
+        c->d_stream_raw = nullptr; c->d_nflag_raw = c->d_rflag_raw = nullptr; c->stream_cap_words = 0;
+        const u64 cap = words + words / 8 + 1024, tot = cap + STREAM_PAD_WORDS;
+        TRY(dev_alloc(c, (void **)&c->d_stream_raw, tot * 8));
+        TRY(dev_alloc(c, (void **)&c->d_nflag_raw, tot * 4));
+        TRY(dev_alloc(c, (void **)&c->d_rflag_raw, tot * 4));
+        CK(cudaMemsetAsync(c->d_stream_raw, 0, STREAM_PAD_WORDS * 8, c->s_compute));
+        CK(cudaMemsetAsync(c->d_nflag_raw, 0, STREAM_PAD_WORDS * 4, c->s_compute));
+        CK(cudaMemsetAsync(c->d_rflag_raw, 0, STREAM_PAD_WORDS * 4, c->s_compute));
+        c->stream_cap_words = cap;
+    }
+    if (n_reads + 1 > c->offsets_cap) {
+        CK(cudaStreamSynchronize(c->s_compute));
+        dev_free(c, c->d_offsets, c->offsets_cap * 8);
+        c->d_offsets = nullptr; c->offsets_cap = 0;
+        const u64 cap = n_reads + n_reads / 8 + 1024;
+        TRY(dev_alloc(c, (void **)&c->d_offsets, cap * 8));
+        c->offsets_cap = cap;
+    }
+    return PBK_OK;
+}
+
+// count the windows ending in stream words [w0, w1) of the current batch; grows the table as needed
+int count_range(pbk_ctx *c, u64 w0, u64 w1)
+{
+    if (w1 <= w0) return PBK_OK;
+    const u64 windows = (w1 - w0) * 32;
+    TRY(maybe_clamp(c, windows));
+    TRY(ensure_room(c, (u64)(windows * std::min(1.0, c->new_ratio * 1.25))));
+    TRY(ensure_overflow(c, windows));
+    const u64 before_new = c->occupied + c->occupied_remote, before_inst = c->last.instances;
+    {
+        Span sp(c, LC_COUNT);
+        launch_count(c->d_stream_raw + STREAM_PAD_WORDS, c->d_nflag_raw + STREAM_PAD_WORDS, c->d_rflag_raw + STREAM_PAD_WORDS,
+                     w0, w1, (int)c->k, c->table, c->remote, c->shard, c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+    }
+    CK(cudaGetLastError());
+    TRY(read_counters(c));
+    TRY(drain_overflow(c));
+    const u64 inst = c->last.instances - before_inst, newk = c->occupied + c->occupied_remote - before_new;
+    if (inst > 4096) c->new_ratio = std::max(0.01, std::min(1.0, (double)newk / (double)inst));
+    return PBK_OK;
+}
+
+int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, const u64 *h_offsets,
+                const u64 *d_offsets_in, u64 n_reads, u64 n_bases, int encoding, const int32_t *n_pos,
+                const u64 *n_pos_offsets)
+{
+    if (c->finalized) return fail(c, PBK_E_STATE, "pbk_push_reads after pbk_finalize (call pbk_reset first)");
+    if (n_reads == 0) return PBK_OK;
+    CK(cudaSetDevice(c->device));
+    TRY(ensure_batch_buffers(c, n_bases, n_reads));
+    const u64 windows_ub = n_bases > (u64)n_reads * (c->k - 1) ? n_bases - (u64)n_reads * (c->k - 1) : 0;
+    TRY(ensure_tables(c, std::max<u64>(windows_ub, 1024)));
+
+    u64 *stream = c->d_stream_raw + STREAM_PAD_WORDS;
+    u32 *nflag = c->d_nflag_raw + STREAM_PAD_WORDS, *rflag = c->d_rflag_raw + STREAM_PAD_WORDS;
+    const u64 words = (n_bases + 31) / 32;
+
+    // read starts + length histogram
+    const u64 *d_off = d_offsets_in;
+    if (!d_off) {
+        CK(cudaMemcpyAsync(c->d_offsets, h_offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->s_compute));
+        c->h2d_bytes += (n_reads + 1) * 8;
+        d_off = c->d_offsets;
+    }
+    CK(cudaMemsetAsync(rflag, 0, words * 4, c->s_compute));
+    { Span sp(c, LC_OTHER); launch_read_marks(d_off, n_reads, c->d_len_hist, rflag, c->d_ctr, c->s_compute); }
+    CK(cudaGetLastError());
+
+    const bool deferred_count = (encoding == PBK_ENC_PLATANUS);     // N flags arrive after all packs
+    if (d_bases_in) {
+        // inputs already in HBM: pack chunk by chunk so the chunk's stream words are still in L2 when counted
+        for (u64 b0 = 0; b0 < n_bases; b0 += CHUNK_BASES) {
+            const u64 nb = std::min(CHUNK_BASES, n_bases - b0), w0 = b0 / 32, nw = (nb + 31) / 32;
+            { Span sp(c, LC_PACK); launch_pack(d_bases_in + b0, nb, nw, encoding, stream, nflag, w0, c->d_ctr, c->s_compute); }
+            CK(cudaGetLastError());
+            TRY(count_range(c, w0, w0 + nw));
+        }
+    } else {
+        if (!c->d_stage[0]) {
+            for (int i = 0; i < 2; ++i) {
+                TRY(dev_alloc(c, (void **)&c->d_stage[i], CHUNK_BASES));
+                CK(cudaEventCreateWithFlags(&c->ev_copy_done[i], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&c->ev_stage_free[i], cudaEventDisableTiming));
+            }
+            c->stage_bytes = CHUNK_BASES;
+        }
+        const u64 n_chunks = (n_bases + CHUNK_BASES - 1) / CHUNK_BASES;
+        auto enqueue_copy = [&](u64 ci) -> int {
+            const int buf = (int)(ci & 1);
+            const u64 b0 = ci * CHUNK_BASES, nb = std::min(CHUNK_BASES, n_bases - b0);
+            CK(cudaStreamWaitEvent(c->s_copy, c->ev_stage_free[buf], 0));
+            CK(cudaMemcpyAsync(c->d_stage[buf], h_bases + b0, nb, cudaMemcpyHostToDevice, c->s_copy));
+            CK(cudaEventRecord(c->ev_copy_done[buf], c->s_copy));
+            c->h2d_bytes += nb;
+            return PBK_OK;
+        };
+        if (n_chunks) TRY(enqueue_copy(0));
+        for (u64 ci = 0; ci < n_chunks; ++ci) {
+            const int buf = (int)(ci & 1);
+            const u64 b0 = ci * CHUNK_BASES, nb = std::min(CHUNK_BASES, n_bases - b0), w0 = b0 / 32, nw = (nb + 31) / 32;
+            if (ci + 1 < n_chunks) TRY(enqueue_copy(ci + 1));       // next copy overlaps this chunk's kernels
+            CK(cudaStreamWaitEvent(c->s_compute, c->ev_copy_done[buf], 0));
+            { Span sp(c, LC_PACK); launch_pack(c->d_stage[buf], nb, nw, encoding, stream, nflag, w0, c->d_ctr, c->s_compute); }
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(c->ev_stage_free[buf], c->s_compute));
+            if (!deferred_count) TRY(count_range(c, w0, w0 + nw));
+        }
+    }
+    if (deferred_count) {
+        if (!n_pos || !n_pos_offsets) return fail(c, PBK_E_ARG, "PBK_ENC_PLATANUS needs n_pos and n_pos_offsets");
+        const u64 total_n = n_pos_offsets[n_reads];
+        int32_t *d_np = nullptr; u64 *d_npo = nullptr;
+        TRY(dev_alloc(c, (void **)&d_np, total_n * 4));
+        int rc = dev_alloc(c, (void **)&d_npo, (n_reads + 1) * 8);
+        if (rc == PBK_OK) {
+            cudaMemcpyAsync(d_np, n_pos, total_n * 4, cudaMemcpyHostToDevice, c->s_compute);
+            cudaMemcpyAsync(d_npo, n_pos_offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->s_compute);
+            c->h2d_bytes += total_n * 4 + (n_reads + 1) * 8;
+            { Span sp(c, LC_OTHER); launch_npos_scatter(d_off, d_np, d_npo, n_reads, nflag, c->s_compute); }
+            for (u64 w0 = 0; w0 < words && rc == PBK_OK; w0 += CHUNK_BASES / 32)
+                rc = count_range(c, w0, std::min(words, w0 + CHUNK_BASES / 32));
+        }
+        cudaStreamSynchronize(c->s_compute);
+        dev_free(c, d_np, total_n * 4); dev_free(c, d_npo, (n_reads + 1) * 8);
+        TRY(rc);
+    }
+    c->n_reads += n_reads;
+    c->n_bases += n_bases;
+    return PBK_OK;
+}
+
+void release_all(pbk_ctx *c)
+{
+    cudaSetDevice(c->device);
+    if (c->s_compute) cudaStreamSynchronize(c->s_compute);
+    if (c->s_copy) cudaStreamSynchronize(c->s_copy);
+    resolve_spans(c);
+    cudaFree(c->d_stream_raw); cudaFree(c->d_nflag_raw); cudaFree(c->d_rflag_raw); cudaFree(c->d_offsets);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->d_stage[i]);
+        if (c->ev_copy_done[i]) cudaEventDestroy(c->ev_copy_done[i]);
+        if (c->ev_stage_free[i]) cudaEventDestroy(c->ev_stage_free[i]);
+    }
+    cudaFree(c->table.slots); cudaFree(c->remote.slots); cudaFree(c->d_ctr); cudaFree(c->d_ovf);
+    cudaFree(c->d_len_hist); cudaFree(c->d_occ_hist); cudaFree(c->d_shard_counts);
+    if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    for (auto &e : c->timer) if (e) cudaEventDestroy(e);
+    if (c->s_compute) cudaStreamDestroy(c->s_compute);
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
+}
+
+}  // namespace
+
+// =================================================================================================
+// exported functions
+// =================================================================================================
+
+extern "C" {
+
+int pbk_abi_version(void) { return PBK_ABI_VERSION; }
+
+const char *pbk_strerror(int s)
+{
+    switch (s) {
+    case PBK_OK: return "ok";
+    case PBK_E_ARG: return "bad argument";
+    case PBK_E_NO_DEVICE: return "no usable CUDA device (libpbk has no CPU fallback)";
+    case PBK_E_CUDA: return "CUDA error";
+    case PBK_E_NOMEM: return "out of memory (HBM budget or host)";
+    case PBK_E_READ_TOO_LONG: return "read length >= 500000 (platanus::ReadError)";
+    case PBK_E_BAD_BASE: return "character without a Char2Bin code in the input";
+    case PBK_E_KMER_DIST: return "empty k-mer distribution (platanus::KmerDistError)";
+    case PBK_E_STATE: return "call out of order";
+    case PBK_E_IO: return "file error (platanus::FILEError)";
+    case PBK_E_UNSUPPORTED_K: return "k must be in 1..256";
+    default: return "unknown status";
+    }
+}
+
+const char *pbk_last_error(const pbk_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+int pbk_create(pbk_ctx **out, const pbk_config *cfg)
+{
+    if (!out || !cfg || cfg->struct_size < sizeof(pbk_config)) return PBK_E_ARG;
+    *out = nullptr;
+    if (cfg->k == 0 || cfg->k > PBK_MAX_K) return PBK_E_UNSUPPORTED_K;
+    if (cfg->n_shards > 1 && cfg->shard_rank >= cfg->n_shards) return PBK_E_ARG;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return PBK_E_NO_DEVICE; }
+    pbk_ctx *c = new (std::nothrow) pbk_ctx();
+    if (!c) return PBK_E_NOMEM;
+    int dev = cfg->device;
+    if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) { delete c; return PBK_E_NO_DEVICE; }
+    if (dev >= n_dev || cudaSetDevice(dev) != cudaSuccess) { delete c; return PBK_E_NO_DEVICE; }
+    c->device = dev;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { delete c; return PBK_E_NO_DEVICE; }
+    c->sm_count = prop.multiProcessorCount;
+    c->k = cfg->k; c->W = (int)((cfg->k + 31) / 32); c->flags = cfg->flags;
+    c->shard.n_shards = cfg->n_shards > 1 ? cfg->n_shards : 1;
+    c->shard.rank = cfg->n_shards > 1 ? cfg->shard_rank : 0;
+    c->table_hint = cfg->table_slots_hint;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    c->budget = cfg->hbm_budget_bytes ? cfg->hbm_budget_bytes : (u64)(free_b * 0.85);
+    auto bail = [&](int code) { release_all(c); delete c; return code; };
+    if (cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking) != cudaSuccess) return bail(PBK_E_CUDA);
+    if (cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking) != cudaSuccess) return bail(PBK_E_CUDA);
+    if (cudaMallocHost((void **)&c->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(PBK_E_NOMEM);
+    memset(c->h_ctr, 0, sizeof(Counters));
+    if (dev_alloc(c, (void **)&c->d_ctr, sizeof(Counters)) || dev_alloc(c, (void **)&c->d_len_hist, PBK_LEN_BINS * 8) ||
+        dev_alloc(c, (void **)&c->d_occ_hist, PBK_OCC_BINS * 8) || dev_alloc(c, (void **)&c->d_shard_counts, (c->shard.n_shards + 1) * 8))
+        return bail(PBK_E_NOMEM);
+    cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), c->s_compute);
+    cudaMemsetAsync(c->d_len_hist, 0, PBK_LEN_BINS * 8, c->s_compute);
+    if (cudaStreamSynchronize(c->s_compute) != cudaSuccess) return bail(PBK_E_CUDA);
+    *out = c;
+    return PBK_OK;
+}
+
+void pbk_destroy(pbk_ctx *c)
+{
+    if (!c) return;
+    release_all(c);
+    delete c;
+}
+
+int pbk_host_alloc(void **out, size_t bytes)
+{
+    if (!out) return PBK_E_ARG;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorMemoryAllocation ? PBK_E_NOMEM : PBK_E_NO_DEVICE; }
+    return PBK_OK;
+}
+
+void pbk_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int pbk_push_reads(pbk_ctx *c, const uint8_t *bases, const uint64_t *read_offsets, uint64_t n_reads,
+                   int encoding, const int32_t *n_pos, const uint64_t *n_pos_offsets)
+{
+    if (!c) return PBK_E_ARG;
+    if (n_reads == 0) return PBK_OK;
+    if (!read_offsets || (encoding != PBK_ENC_ASCII && encoding != PBK_ENC_PLATANUS)) return fail(c, PBK_E_ARG, "bad arguments");
+    if (read_offsets[0] != 0) return fail(c, PBK_E_ARG, "read_offsets[0] must be 0");
+    const u64 n_bases = read_offsets[n_reads];
+    if (n_bases && !bases) return fail(c, PBK_E_ARG, "bases is NULL");
+    return push_common(c, bases, nullptr, (const u64 *)read_offsets, nullptr, n_reads, n_bases, encoding, n_pos, (const u64 *)n_pos_offsets);
+}
+
+int pbk_push_reads_device(pbk_ctx *c, const void *d_bases, const void *d_read_offsets, uint64_t n_reads, uint64_t n_bases)
+{
+    if (!c) return PBK_E_ARG;
+    if (n_reads == 0) return PBK_OK;
+    if (!d_read_offsets || (n_bases && !d_bases)) return fail(c, PBK_E_ARG, "NULL device pointer");
+    return push_common(c, nullptr, (const uint8_t *)d_bases, nullptr, (const u64 *)d_read_offsets, n_reads, n_bases,
+                       PBK_ENC_ASCII, nullptr, nullptr);
+}
+
+int pbk_finalize(pbk_ctx *c, uint64_t *occ_hist, uint64_t *len_hist, uint64_t *n_distinct,
+                 uint64_t *n_instances, uint64_t *max_occurrence)
+{
+    if (!c) return PBK_E_ARG;
+    CK(cudaSetDevice(c->device));
+    if (c->shard.n_shards > 1 && c->occupied_remote > 0)
+        return fail(c, PBK_E_STATE, "%llu staged records have not been exchanged (pbk_shard_pack_device)", (unsigned long long)c->occupied_remote);
+    c->h_occ_hist.assign(PBK_OCC_BINS, 0);
+    if (c->table.slots) {
+        CK(cudaMemsetAsync(c->d_occ_hist, 0, PBK_OCC_BINS * 8, c->s_compute));
+        { Span sp(c, LC_OTHER); launch_table_histogram(c->table, c->d_occ_hist, c->s_compute); }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(c->h_occ_hist.data(), c->d_occ_hist, PBK_OCC_BINS * 8, cudaMemcpyDeviceToHost, c->s_compute));
+        c->d2h_bytes += PBK_OCC_BINS * 8;
+    }
+    if (len_hist) {
+        CK(cudaMemcpyAsync(len_hist, c->d_len_hist, PBK_LEN_BINS * 8, cudaMemcpyDeviceToHost, c->s_compute));
+        c->d2h_bytes += PBK_LEN_BINS * 8;
+    }
+    CK(cudaStreamSynchronize(c->s_compute));
+    c->inst_since_clamp = 0;
+    u64 nd = 0, mx = 0;
+    for (u64 i = 1; i < PBK_OCC_BINS; ++i) { nd += c->h_occ_hist[i]; if (c->h_occ_hist[i]) mx = i; }
+    if (nd != c->occupied)
+        return fail(c, PBK_E_CUDA, "internal: histogram holds %llu keys, table tracked %llu", (unsigned long long)nd, (unsigned long long)c->occupied);
+    if (occ_hist) memcpy(occ_hist, c->h_occ_hist.data(), PBK_OCC_BINS * 8);
+    if (n_distinct) *n_distinct = nd;
+    if (n_instances) *n_instances = c->last.instances;
+    if (max_occurrence) *max_occurrence = mx;
+    c->finalized = true;
+    return PBK_OK;
+}
+
+int pbk_export(pbk_ctx *c, uint32_t min_count, int sorted, uint64_t *keys, uint16_t *counts, uint64_t capacity, uint64_t *n_out)
+{
+    if (!c) return PBK_E_ARG;
+    if (!c->finalized) return fail(c, PBK_E_STATE, "pbk_export before pbk_finalize");
+    CK(cudaSetDevice(c->device));
+    u64 n = 0;
+    for (u64 i = std::max<u64>(min_count, 1); i < PBK_OCC_BINS; ++i) n += c->h_occ_hist[i];
+    if (n_out) *n_out = n;
+    if (capacity == 0) return PBK_OK;
+    if (capacity < n || !keys || !counts) return fail(c, PBK_E_ARG, "export needs room for %llu entries", (unsigned long long)n);
+    if (n == 0) return PBK_OK;
+    u64 *d_keys = nullptr, *d_n = nullptr; uint16_t *d_counts = nullptr;
+    const size_t kb = n * 8 * c->W, cb = n * 2;
+    TRY(dev_alloc(c, (void **)&d_keys, kb));
+    int rc = dev_alloc(c, (void **)&d_counts, cb);
+    if (rc == PBK_OK) rc = dev_alloc(c, (void **)&d_n, 8);
+    if (rc == PBK_OK) {
+        cudaMemsetAsync(d_n, 0, 8, c->s_compute);
+        { Span sp(c, LC_OTHER); launch_table_export(c->table, std::max<u32>(min_count, 1), d_keys, d_counts, n, d_n, c->s_compute); }
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess && sorted) { c->launches[LC_OTHER] += 1; e = sort_export(d_keys, d_counts, n, c->W, (int)c->k, c->s_compute); }
+        u64 got = 0;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&got, d_n, 8, cudaMemcpyDeviceToHost, c->s_compute);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(keys, d_keys, kb, cudaMemcpyDeviceToHost, c->s_compute);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(counts, d_counts, cb, cudaMemcpyDeviceToHost, c->s_compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_compute);
+        c->d2h_bytes += kb + cb + 8;
+        if (e != cudaSuccess) rc = fail(c, PBK_E_CUDA, "export: %s", cudaGetErrorString(e));
+        else if (got != n) rc = fail(c, PBK_E_CUDA, "internal: export found %llu entries, histogram says %llu", (unsigned long long)got, (unsigned long long)n);
+    }
+    cudaStreamSynchronize(c->s_compute);
+    dev_free(c, d_keys, kb); dev_free(c, d_counts, cb); dev_free(c, d_n, 8);
+    return rc;
+}
+
+int pbk_get_stats(const pbk_ctx *cc, pbk_stats *out)
+{
+    if (!cc || !out) return PBK_E_ARG;
+    pbk_ctx *c = const_cast<pbk_ctx *>(cc);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->s_compute);
+    resolve_spans(c);
+    memset(out, 0, sizeof(*out));
+    out->n_reads = c->n_reads; out->n_bases = c->n_bases; out->n_instances = c->last.instances;
+    out->n_distinct = c->occupied; out->table_slots = c->table.slots ? c->table.capacity() : 0;
+    out->table_bytes = c->table.slots ? c->table.bytes() : 0; out->n_grow = c->n_grow;
+    out->launches_pack = c->launches[LC_PACK]; out->launches_count = c->launches[LC_COUNT]; out->launches_other = c->launches[LC_OTHER];
+    out->ms_pack = c->ms[LC_PACK]; out->ms_count = c->ms[LC_COUNT]; out->ms_other = c->ms[LC_OTHER];
+    out->h2d_bytes = c->h2d_bytes; out->d2h_bytes = c->d2h_bytes;
+    return PBK_OK;
+}
+
+int pbk_timer_mark(pbk_ctx *c, int slot)
+{
+    if (!c || slot < 0 || slot >= 8) return PBK_E_ARG;
+    CK(cudaSetDevice(c->device));
+    if (!c->timer[slot]) CK(cudaEventCreate(&c->timer[slot]));
+    CK(cudaEventRecord(c->timer[slot], c->s_compute));
+    return PBK_OK;
+}
+
+int pbk_timer_elapsed_ms(pbk_ctx *c, int start, int stop, double *ms)
+{
+    if (!c || !ms || start < 0 || start >= 8 || stop < 0 || stop >= 8 || !c->timer[start] || !c->timer[stop]) return PBK_E_ARG;
+    float f = 0;
+    CK(cudaEventSynchronize(c->timer[stop]));
+    CK(cudaEventElapsedTime(&f, c->timer[start], c->timer[stop]));
+    *ms = f;
+    return PBK_OK;
+}
+
+int pbk_reset(pbk_ctx *c, uint32_t k)
+{
+    if (!c) return PBK_E_ARG;
+    if (k == 0) k = c->k;
+    if (k > PBK_MAX_K) return PBK_E_UNSUPPORTED_K;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->s_compute));
+    const int W = (int)((k + 31) / 32);
+    if (W != c->W) {                                   // slot size changes: tables are re-created lazily
+        if (c->table.slots) dev_free(c, c->table.slots, c->table.bytes());
+        if (c->remote.slots) dev_free(c, c->remote.slots, c->remote.bytes());
+        if (c->d_ovf) dev_free(c, c->d_ovf, c->ovf_cap * (c->W + 1) * 8);
+        c->table = TableView{nullptr, 0, 0}; c->remote = TableView{nullptr, 0, 0}; c->d_ovf = nullptr; c->ovf_cap = 0;
+    } else {
+        if (c->table.slots) { Span sp(c, LC_OTHER); launch_table_init(c->table, c->s_compute); }
+        if (c->remote.slots) { Span sp(c, LC_OTHER); launch_table_init(c->remote, c->s_compute); }
+    }
+    c->k = k; c->W = W;
+    CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), c->s_compute));
+    CK(cudaMemsetAsync(c->d_len_hist, 0, PBK_LEN_BINS * 8, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));
+    c->last = Counters{}; c->occupied = c->occupied_remote = 0; c->inst_since_clamp = 0;
+    c->n_reads = c->n_bases = 0; c->finalized = false; c->h_occ_hist.clear();
+    return PBK_OK;
+}
+
+// ---- sharding ---------------------------------------------------------------------------------
+
+uint32_t pbk_shard_record_bytes(const pbk_ctx *c) { return c ? (uint32_t)((c->W + 1) * 8) : 0; }
+
+int pbk_shard_send_counts(pbk_ctx *c, uint64_t *counts)
+{
+    if (!c || !counts) return PBK_E_ARG;
+    const u32 n = c->shard.n_shards;
+    c->h_shard_counts.assign(n, 0);
+    if (n > 1 && c->remote.slots && c->occupied_remote) {
+        CK(cudaSetDevice(c->device));
+        CK(cudaMemsetAsync(c->d_shard_counts, 0, n * 8, c->s_compute));
+        { Span sp(c, LC_OTHER); launch_shard_count(c->remote, n, c->d_shard_counts, c->s_compute); }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(c->h_shard_counts.data(), c->d_shard_counts, n * 8, cudaMemcpyDeviceToHost, c->s_compute));
+        CK(cudaStreamSynchronize(c->s_compute));
+        c->d2h_bytes += n * 8;
+    }
+    memcpy(counts, c->h_shard_counts.data(), n * 8);
+    return PBK_OK;
+}
+
+int pbk_shard_pack_device(pbk_ctx *c, void *d_records, uint64_t capacity_records)
+{
+    if (!c) return PBK_E_ARG;
+    const u32 n = c->shard.n_shards;
+    if (n <= 1 || !c->remote.slots || c->occupied_remote == 0) return PBK_OK;
+    std::vector<uint64_t> cnt(n);
+    TRY(pbk_shard_send_counts(c, cnt.data()));
+    std::vector<u64> cur(n);
+    u64 total = 0;
+    for (u32 i = 0; i < n; ++i) { cur[i] = total; total += cnt[i]; }
+    if (total != c->occupied_remote) return fail(c, PBK_E_CUDA, "internal: staged %llu records, tracked %llu", (unsigned long long)total, (unsigned long long)c->occupied_remote);
+    if (total > capacity_records || !d_records) return fail(c, PBK_E_ARG, "exchange buffer too small: need %llu records", (unsigned long long)total);
+    CK(cudaMemcpyAsync(c->d_shard_counts, cur.data(), n * 8, cudaMemcpyHostToDevice, c->s_compute));
+    { Span sp(c, LC_OTHER); launch_shard_pack(c->remote, n, c->d_shard_counts, (u64 *)d_records, c->s_compute); }
+    { Span sp(c, LC_OTHER); launch_table_init(c->remote, c->s_compute); }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->s_compute));
+    c->occupied_remote = 0;
+    return PBK_OK;
+}
+
+int pbk_shard_insert_device(pbk_ctx *c, const void *d_records, uint64_t n_records)
+{
+    if (!c) return PBK_E_ARG;
+    if (n_records == 0) return PBK_OK;
+    if (!d_records) return PBK_E_ARG;
+    if (c->finalized) return fail(c, PBK_E_STATE, "insert after finalize");
+    CK(cudaSetDevice(c->device));
+    TRY(ensure_tables(c, n_records));
+    const ShardInfo local{1, 0};                      // received records are owned by this shard
+    for (u64 at = 0; at < n_records; at += CHUNK_BASES) {
+        const u64 n = std::min<u64>(CHUNK_BASES, n_records - at);
+        TRY(maybe_clamp(c, (u64)c->shard.n_shards * COUNT_SAT));
+        if ((double)(c->occupied + n) > MAX_LOAD * (double)c->table.capacity())
+            TRY(grow_table(c, &c->table, c->occupied, (u64)((c->occupied + n) / MAX_LOAD) + 1));
+        TRY(ensure_overflow(c, n));
+        {
+            Span sp(c, LC_COUNT);
+            launch_insert_records((const u64 *)d_records + at * (c->W + 1), n, true, c->table, c->remote, local, c->d_ctr,
+                                  c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+        }
+        CK(cudaGetLastError());
+        TRY(read_counters(c));
+        TRY(drain_overflow(c));
+    }
+    return PBK_OK;
+}
+
+uint32_t pbk_shard_of_key(const uint64_t *key_words, uint32_t k, uint32_t n_shards)
+{
+    if (!key_words || n_shards <= 1) return 0;
+    u64 h = 0;
+    switch ((k + 31) / 32) {
+    case 1: h = hash_key<1>((const u64 *)key_words); break;
+    case 2: h = hash_key<2>((const u64 *)key_words); break;
+    case 3: h = hash_key<3>((const u64 *)key_words); break;
+    case 4: h = hash_key<4>((const u64 *)key_words); break;
+    case 5: h = hash_key<5>((const u64 *)key_words); break;
+    case 6: h = hash_key<6>((const u64 *)key_words); break;
+    case 7: h = hash_key<7>((const u64 *)key_words); break;
+    case 8: h = hash_key<8>((const u64 *)key_words); break;
+    default: return 0;
+    }
+    return shard_of_hash(h, n_shards);
+}
+
+// ---- microbenchmark ---------------------------------------------------------------------------
+
+int pbk_microbench_atomics(int device, uint64_t table_bytes, uint64_t n_ops, int mode, double *ops_per_s)
+{
+    if (!ops_per_s || table_bytes < 4096 || n_ops == 0 || mode < 0 || mode > 2) return PBK_E_ARG;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return PBK_E_NO_DEVICE; }
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return PBK_E_NO_DEVICE;
+    cudaDeviceProp prop; int dev = 0;
+    cudaGetDevice(&dev); cudaGetDeviceProperties(&prop, dev);
+    int log2slots = 0;
+    while ((32ull << log2slots) <= table_bytes) ++log2slots;     // 16-byte slots, largest power of two that fits
+    TableView t{nullptr, 1ull << log2slots, 1};
+    if (cudaMalloc(&t.slots, t.bytes()) != cudaSuccess) { cudaGetLastError(); return PBK_E_NOMEM; }
+    cudaStream_t st; cudaStreamCreate(&st);
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {                            // rep 0 warms up
+        if (mode == 2 || rep == 0) launch_table_init(t, st);
+        cudaEventRecord(a, st);
+        launch_microbench(t.slots, log2slots, n_ops, mode, 0x9E3779B97F4A7C15ull * (rep + 1), prop.multiProcessorCount, st);
+        cudaEventRecord(b, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(t.slots); return PBK_E_CUDA; }
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *ops_per_s = (double)n_ops / (best * 1e-3);
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaStreamDestroy(st); cudaFree(t.slots);
+    return PBK_OK;
+}
+
+}  // extern "C"

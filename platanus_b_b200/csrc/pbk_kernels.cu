@@ -1,0 +1,252 @@
+// pbk_kernels.cu -- hand-written sm_100a kernels of the k-mer counting path.
+//
+// None of this is GEMM-shaped: it is byte/integer streaming plus scattered read-modify-write, so
+// there is deliberately no tensor-core code.  What matters here is coalesced 128-bit loads, one HBM
+// sector per table access, enough resident warps to cover DRAM latency, and grids sized from the
+// SM count (148 on B200).
+#include "pbk_kernels.cuh"
+#include "pbk_kernels_impl.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace pbk {
+
+static inline int grid_for(u64 n_threads, int block, int sm_count, int blocks_per_sm)
+{
+    u64 need = (n_threads + block - 1) / block;
+    u64 cap = (u64)sm_count * blocks_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+void launch_pack(const uint8_t *bases, u64 n_valid, u64 n_words, int encoding,
+                 u64 *stream, u32 *nflag, u64 word0, Counters *ctr, cudaStream_t st)
+{
+    if (n_words == 0) return;
+    int grid = grid_for(n_words, 256, 148, 16);
+    bool aligned = (reinterpret_cast<uintptr_t>(bases) & 15) == 0;
+    if (aligned) pack_kernel<true><<<grid, 256, 0, st>>>(bases, n_valid, n_words, encoding, stream, nflag, word0, ctr);
+    else pack_kernel<false><<<grid, 256, 0, st>>>(bases, n_valid, n_words, encoding, stream, nflag, word0, ctr);
+}
+
+void launch_read_marks(const u64 *offsets, u64 n_reads, u64 *len_hist, u32 *rflag, Counters *ctr, cudaStream_t st)
+{
+    if (n_reads == 0) return;
+    read_marks_kernel<<<grid_for(n_reads, 256, 148, 8), 256, 0, st>>>(offsets, n_reads, len_hist, rflag, ctr);
+}
+
+void launch_npos_scatter(const u64 *offsets, const int32_t *n_pos, const u64 *n_pos_offsets, u64 n_reads,
+                         u32 *nflag, cudaStream_t st)
+{
+    if (n_reads == 0) return;
+    npos_scatter_kernel<<<grid_for(n_reads, 256, 148, 8), 256, 0, st>>>(offsets, n_pos, n_pos_offsets, n_reads, nflag);
+}
+
+// =================================================================================================
+// dispatch on W = ceil(k/32)
+// =================================================================================================
+
+#define PBK_DISPATCH_W(words, CALL)                                                                  \
+    switch (words) {                                                                                \
+    case 1: { constexpr int W = 1; CALL; } break;                                                    \
+    case 2: { constexpr int W = 2; CALL; } break;                                                    \
+    case 3: { constexpr int W = 3; CALL; } break;                                                    \
+    case 4: { constexpr int W = 4; CALL; } break;                                                    \
+    case 5: { constexpr int W = 5; CALL; } break;                                                    \
+    case 6: { constexpr int W = 6; CALL; } break;                                                    \
+    case 7: { constexpr int W = 7; CALL; } break;                                                    \
+    case 8: { constexpr int W = 8; CALL; } break;                                                    \
+    default: break;                                                                                  \
+    }
+
+void launch_count(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
+                  TableView table, TableView remote, ShardInfo shard, Counters *ctr,
+                  u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st)
+{
+    if (word_end <= word_begin) return;
+    const int grid = grid_for(word_end - word_begin, 256, sm_count, 8);
+    PBK_DISPATCH_W(table.words,
+        (count_kernel<W><<<grid, 256, 0, st>>>(stream, nflag, rflag, word_begin, word_end, k,
+            (Slot<W> *)table.slots, table.cap, (Slot<W> *)remote.slots, remote.cap,
+            shard.n_shards, shard.rank, ctr, overflow_keys, overflow_cap)));
+}
+
+void launch_insert_records(const u64 *records, u64 n, bool weighted, TableView table, TableView remote,
+                           ShardInfo shard, Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count,
+                           cudaStream_t st)
+{
+    if (n == 0) return;
+    const int grid = grid_for(n, 256, sm_count, 8);
+    PBK_DISPATCH_W(table.words,
+        (insert_records_kernel<W><<<grid, 256, 0, st>>>(records, n, weighted ? 1 : 0, (Slot<W> *)table.slots,
+            table.cap, (Slot<W> *)remote.slots, remote.cap, shard.n_shards, shard.rank,
+            ctr, overflow_keys, overflow_cap)));
+}
+
+void launch_table_init(TableView t, cudaStream_t st)
+{
+    if (t.words == 1) {
+        table_init1_kernel<<<grid_for(t.capacity(), 256, 148, 16), 256, 0, st>>>((uint4 *)t.slots, t.capacity());
+    } else {
+        cudaMemsetAsync(t.slots, 0, t.bytes(), st);
+    }
+}
+
+void launch_table_rehash(TableView from, TableView to, Counters *ctr, cudaStream_t st)
+{
+    const int grid = grid_for(from.capacity(), 256, 148, 8);
+    PBK_DISPATCH_W(from.words,
+        (rehash_kernel<W><<<grid, 256, 0, st>>>((const Slot<W> *)from.slots, from.capacity(), (Slot<W> *)to.slots,
+            to.cap, ctr)));
+}
+
+void launch_table_clamp(TableView t, cudaStream_t st)
+{
+    const int grid = grid_for(t.capacity(), 256, 148, 8);
+    PBK_DISPATCH_W(t.words, (clamp_kernel<W><<<grid, 256, 0, st>>>((Slot<W> *)t.slots, t.capacity())));
+}
+
+void launch_table_histogram(TableView t, u64 *occ_hist, cudaStream_t st)
+{
+    const int grid = grid_for(t.capacity(), 256, 148, 4);
+    PBK_DISPATCH_W(t.words, (histogram_kernel<W><<<grid, 256, 0, st>>>((Slot<W> *)t.slots, t.capacity(), occ_hist)));
+}
+
+void launch_table_export(TableView t, u32 min_count, u64 *keys_out, uint16_t *counts_out, u64 capacity,
+                         u64 *d_n_out, cudaStream_t st)
+{
+    const int grid = grid_for(t.capacity(), 256, 148, 8);
+    PBK_DISPATCH_W(t.words,
+        (export_kernel<W><<<grid, 256, 0, st>>>((const Slot<W> *)t.slots, t.capacity(), min_count, keys_out,
+            counts_out, capacity, d_n_out)));
+}
+
+void launch_shard_count(TableView remote, u32 n_shards, u64 *d_counts, cudaStream_t st)
+{
+    const int grid = grid_for(remote.capacity(), 256, 148, 8);
+    PBK_DISPATCH_W(remote.words,
+        (shard_count_kernel<W><<<grid, 256, 0, st>>>((const Slot<W> *)remote.slots, remote.capacity(), n_shards, d_counts)));
+}
+
+void launch_shard_pack(TableView remote, u32 n_shards, u64 *d_cursors, u64 *records_out, cudaStream_t st)
+{
+    const int grid = grid_for(remote.capacity(), 256, 148, 8);
+    PBK_DISPATCH_W(remote.words,
+        (shard_pack_kernel<W><<<grid, 256, 0, st>>>((const Slot<W> *)remote.slots, remote.capacity(), n_shards,
+            d_cursors, records_out)));
+}
+
+// =================================================================================================
+// sorted export (sortedKeyFromKmerFile, counter.h:917-951): LSD radix sort, least significant word
+// first, with a permutation carried along for multi-word keys.  Radix sort itself is library code
+// (CUB); it is not on the counting hot path.
+// =================================================================================================
+
+__global__ void iota_kernel(u32 *p, u64 n)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) p[i] = (u32)i;
+}
+__global__ void gather_word_kernel(const u64 *keys, const u32 *perm, u64 n, int words, int w, u64 *out)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        out[i] = keys[(u64)perm[i] * words + w];
+}
+__global__ void gather_rows_kernel(const u64 *keys, const uint16_t *counts, const u32 *perm, u64 n, int words,
+                                   u64 *keys_out, uint16_t *counts_out)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u64 src = perm[i];
+        for (int j = 0; j < words; ++j) keys_out[i * words + j] = keys[src * words + j];
+        counts_out[i] = counts[src];
+    }
+}
+
+cudaError_t sort_export(u64 *keys, uint16_t *counts, u64 n, int words, int k, cudaStream_t st)
+{
+    if (n < 2) return cudaSuccess;
+    if (n >= (1ull << 32)) return cudaErrorInvalidValue;
+    cudaError_t e;
+    const int grid = grid_for(n, 256, 148, 8);
+    if (words == 1) {
+        u64 *k2 = nullptr; uint16_t *c2 = nullptr; void *tmp = nullptr; size_t tmp_bytes = 0;
+        if ((e = cudaMalloc(&k2, n * 8))) return e;
+        if ((e = cudaMalloc(&c2, n * 2))) { cudaFree(k2); return e; }
+        cub::DoubleBuffer<u64> dk(keys, k2);
+        cub::DoubleBuffer<uint16_t> dc(counts, c2);
+        const int end_bit = 2 * k > 64 ? 64 : 2 * k;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dc, (int)n, 0, end_bit, st);
+        if ((e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1))) { cudaFree(k2); cudaFree(c2); return e; }
+        e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dc, (int)n, 0, end_bit, st);
+        if (!e && dk.Current() != keys) {
+            cudaMemcpyAsync(keys, dk.Current(), n * 8, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(counts, dc.Current(), n * 2, cudaMemcpyDeviceToDevice, st);
+        }
+        cudaError_t e2 = cudaStreamSynchronize(st);
+        cudaFree(k2); cudaFree(c2); cudaFree(tmp);
+        return e ? e : e2;
+    }
+    u32 *perm = nullptr, *perm2 = nullptr; u64 *kw = nullptr, *kw2 = nullptr, *keys_tmp = nullptr; uint16_t *counts_tmp = nullptr;
+    void *tmp = nullptr; size_t tmp_bytes = 0;
+    e = cudaMalloc(&perm, n * 4);
+    if (!e) e = cudaMalloc(&perm2, n * 4);
+    if (!e) e = cudaMalloc(&kw, n * 8);
+    if (!e) e = cudaMalloc(&kw2, n * 8);
+    if (!e) e = cudaMalloc(&keys_tmp, n * 8 * words);
+    if (!e) e = cudaMalloc(&counts_tmp, n * 2);
+    if (!e) {
+        cub::DoubleBuffer<u64> dk(kw, kw2);
+        cub::DoubleBuffer<u32> dp(perm, perm2);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dp, (int)n, 0, 64, st);
+        e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
+        if (!e) {
+            iota_kernel<<<grid, 256, 0, st>>>(perm, n);
+            for (int w = 0; w < words && !e; ++w) {
+                gather_word_kernel<<<grid, 256, 0, st>>>(keys, dp.Current(), n, words, w, dk.Current());
+                int end_bit = 64;
+                if (w == words - 1 && (k & 31)) end_bit = 2 * (k & 31);
+                e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dp, (int)n, 0, end_bit, st);
+            }
+            if (!e) {
+                gather_rows_kernel<<<grid, 256, 0, st>>>(keys, counts, dp.Current(), n, words, keys_tmp, counts_tmp);
+                cudaMemcpyAsync(keys, keys_tmp, n * 8 * words, cudaMemcpyDeviceToDevice, st);
+                cudaMemcpyAsync(counts, counts_tmp, n * 2, cudaMemcpyDeviceToDevice, st);
+            }
+        }
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(perm); cudaFree(perm2); cudaFree(kw); cudaFree(kw2); cudaFree(keys_tmp); cudaFree(counts_tmp); cudaFree(tmp);
+    return e ? e : e2;
+}
+
+// =================================================================================================
+// microbenchmark: random read-modify-write rate (R_atomic of SURVEY.md section 8d)
+// =================================================================================================
+
+__global__ void __launch_bounds__(256)
+microbench_kernel(Slot<1> *t, int log2slots, u64 n_ops, int mode, u64 seed)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    u32 sink = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_ops; i += stride) {
+        const u64 h = fmix64(i + seed);
+        if (mode == 0) {
+            red_add_u32(&t[h >> (64 - log2slots)].cs, 1u);
+        } else if (mode == 1) {
+            Slot<1> *s = t + (h >> (64 - log2slots));
+            const u64 cur = ld_cg_u64(&s->key[0]);
+            if (cur != 0x123456789ull) red_add_u32(&s->cs, 1u);
+            else ++sink;
+        } else {
+            u64 key = h >> 1;                        // never KEY_EMPTY
+            sink += (u32)table_insert<1>(t, 1ull << log2slots, &key, h, 1u);
+        }
+    }
+    if (sink == 0xFFFFFFFFu) t[0].pad = sink;
+}
+
+void launch_microbench(void *table, int log2slots, u64 n_ops, int mode, u64 seed, int sm_count, cudaStream_t st)
+{
+    microbench_kernel<<<grid_for(n_ops, 256, sm_count, 8), 256, 0, st>>>((Slot<1> *)table, log2slots, n_ops, mode, seed);
+}
+
+}  // namespace pbk

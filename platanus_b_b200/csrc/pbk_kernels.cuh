@@ -1,0 +1,67 @@
+// pbk_kernels.cuh -- launch wrappers of the hand-written sm_100a kernels (defined in pbk_kernels.cu)
+#pragma once
+
+#include "pbk_device.cuh"
+
+namespace pbk {
+
+struct TableView {
+    void *slots;       // Slot<W>[cap]
+    u64   cap;         // number of slots (any value >= 1)
+    int   words;       // W
+    u64   capacity() const { return cap; }
+    size_t slot_bytes() const { return 8 * (size_t)words + 8; }
+    size_t bytes() const { return slot_bytes() * cap; }
+};
+
+struct ShardInfo {
+    u32 n_shards;      // <= 1: everything is local
+    u32 rank;
+};
+
+// ---- ingest -----------------------------------------------------------------------------------
+// ASCII (or platanus code bytes) -> 2-bit stream words + N flags for stream words [word0, word0 + n_words).
+// `bases` points at the byte of stream position word0 * 32; n_valid = number of real bases from there.
+void launch_pack(const uint8_t *bases, u64 n_valid, u64 n_words, int encoding,
+                 u64 *stream, u32 *nflag, u64 word0, Counters *ctr, cudaStream_t st);
+// per read: length histogram, read-start flags, MAX_READ_LEN check
+void launch_read_marks(const u64 *offsets, u64 n_reads, u64 *len_hist, u32 *rflag, Counters *ctr, cudaStream_t st);
+// PBK_ENC_PLATANUS: scatter the N position lists into nflag
+void launch_npos_scatter(const u64 *offsets, const int32_t *n_pos, const u64 *n_pos_offsets, u64 n_reads,
+                         u32 *nflag, cudaStream_t st);
+
+// ---- counting ---------------------------------------------------------------------------------
+// windows that END in stream words [word_begin, word_end) are canonicalised and inserted
+void launch_count(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
+                  TableView table, TableView remote, ShardInfo shard, Counters *ctr,
+                  u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st);
+// insert n (key words..., weight) records; a record has W + 1 words when weighted, W otherwise.
+// Overflow-list records always have W + 1 words.
+void launch_insert_records(const u64 *records, u64 n, bool weighted, TableView table, TableView remote,
+                           ShardInfo shard, Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count,
+                           cudaStream_t st);
+
+// ---- table ------------------------------------------------------------------------------------
+void launch_table_init(TableView t, cudaStream_t st);
+// move every entry of `from` into `to` (capacity change)
+void launch_table_rehash(TableView from, TableView to, Counters *ctr, cudaStream_t st);
+// clamp counts to 65534 (keeps the 32-bit counters far from overflow on > 4G-instance inputs)
+void launch_table_clamp(TableView t, cudaStream_t st);
+// clamp + occurrence histogram (writeKmerDistribution, counter.h:483-507)
+void launch_table_histogram(TableView t, u64 *occ_hist, cudaStream_t st);
+// compact entries with count >= min_count: keys (n x W, word 0 first), counts u16; *d_n_out += n
+void launch_table_export(TableView t, u32 min_count, u64 *keys_out, uint16_t *counts_out, u64 capacity,
+                         u64 *d_n_out, cudaStream_t st);
+// sort exported entries ascending in reference order (top word first); temp storage managed inside
+cudaError_t sort_export(u64 *keys, uint16_t *counts, u64 n, int words, int k, cudaStream_t st);
+
+// ---- sharding ---------------------------------------------------------------------------------
+// per-destination number of entries in the remote-staging table
+void launch_shard_count(TableView remote, u32 n_shards, u64 *d_counts, cudaStream_t st);
+// write (key words, count) records grouped by destination; d_cursors = exclusive prefix of counts
+void launch_shard_pack(TableView remote, u32 n_shards, u64 *d_cursors, u64 *records_out, cudaStream_t st);
+
+// ---- microbenchmark ---------------------------------------------------------------------------
+void launch_microbench(void *table, int log2slots, u64 n_ops, int mode, u64 seed, int sm_count, cudaStream_t st);
+
+}  // namespace pbk

@@ -1,0 +1,408 @@
+// pbk_kernels_impl.cuh -- the kernels themselves (no launch syntax), so that tests/cpu_emul can
+// run the very same source sequentially on the host as a logic check.  Launch wrappers: pbk_kernels.cu.
+#pragma once
+#include "pbk_device.cuh"
+
+namespace pbk {
+
+// =================================================================================================
+// ingest: ASCII -> 2-bit stream (SEQ::convertFromString + Char2Bin, common.h:256, 460-477)
+// =================================================================================================
+
+// four characters per 32-bit lane.  Char2Bin only looks at the low nibble: 1->A 3->C 7->G 4->T
+// 14->N 15->0(A); every other nibble has no defined code in the reference.
+__device__ __forceinline__ void pack4(u32 v, bool platanus, u32 &byte_out, u32 &nflag4, u32 &bad)
+{
+    if (platanus) {
+        u32 codes = v & 0x03030303u;
+        byte_out = (codes * 0x40100401u) >> 24;
+        nflag4 = 0;
+        return;
+    }
+    u32 codes = ((v >> 1) ^ (v >> 2)) & 0x03030303u;
+    byte_out = (codes * 0x40100401u) >> 24;                  // c0<<6 | c1<<4 | c2<<2 | c3
+    u32 eq = (v & 0x0F0F0F0Fu) ^ 0x0E0E0E0Eu;                // zero byte <=> nibble 14 ('N','n')
+    u32 z = ~(eq + 0x7F7F7F7Fu) & 0x80808080u;
+    nflag4 = (((z >> 7) * 0x01020408u) >> 24) & 0xFu;        // bit i <=> byte i
+    u32 b0 = v, b1 = v >> 1, b2 = v >> 2, b3 = v >> 3;
+    u32 ok = (~b3 & ~b2 & b0) | (~b3 & b2 & ~(b1 ^ b0)) | (b3 & b2 & b1);
+    bad |= (~ok) & 0x01010101u;
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256)
+pack_kernel(const uint8_t *__restrict__ bases, u64 n_valid, u64 n_words, int platanus,
+            u64 *__restrict__ stream, u32 *__restrict__ nflag, u64 word0, Counters *ctr)
+{
+    u32 bad = 0;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+        const u64 b0 = w * 32;
+        u32 x[8];
+        u32 tail_flags = 0;
+        if (ALIGNED && b0 + 32 <= n_valid) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(bases + b0);
+            uint4 lo = __ldg(p), hi = __ldg(p + 1);
+            x[0] = lo.x; x[1] = lo.y; x[2] = lo.z; x[3] = lo.w;
+            x[4] = hi.x; x[5] = hi.y; x[6] = hi.z; x[7] = hi.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                u32 v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    u64 pos = b0 + 4 * j + b;
+                    u32 c;
+                    if (pos < n_valid) c = bases[pos];
+                    else { c = platanus ? 0u : (u32)'A'; tail_flags |= 1u << (4 * j + b); }
+                    v |= c << (8 * b);
+                }
+                x[j] = v;
+            }
+        }
+        u64 word = 0;
+        u32 nf = tail_flags;        // positions past the end can never be inside a window
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            u32 byte, f4;
+            pack4(x[j], platanus != 0, byte, f4, bad);
+            word |= (u64)byte << (56 - 8 * j);
+            nf |= f4 << (4 * j);
+        }
+        stream[word0 + w] = word;
+        nflag[word0 + w] = nf;
+    }
+    if (__any_sync(0xffffffffu, bad != 0) && (threadIdx.x & 31) == 0)
+        atomicOr(&ctr->error_flags, ERR_BAD_BASE);
+}
+
+
+// per read: ++lengthDistribution[len] (counter.h:406), ReadError (common.h:465), first-base flag
+__global__ void __launch_bounds__(256)
+read_marks_kernel(const u64 *__restrict__ off, u64 n_reads, u64 *len_hist, u32 *rflag, Counters *ctr)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const u64 n_round = (n_reads + 31) & ~31ull;
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_round; r += stride) {
+        const bool active = r < n_reads;
+        u64 start = 0, len = 0;
+        if (active) { start = off[r]; len = off[r + 1] - start; }
+        if (active && len >= 500000ull) { atomicOr(&ctr->error_flags, ERR_READ_TOO_LONG); len = 500000ull; }
+        const unsigned act = __ballot_sync(0xffffffffu, active);
+        if (active) {
+            const unsigned peers = __match_any_sync(act, len);
+            if (lane == __ffs(peers) - 1) atomicAdd(&len_hist[len], (u64)__popc(peers));
+            if (len > 0) atomicOr(&rflag[start >> 5], 1u << (start & 31));
+        }
+    }
+}
+
+
+__global__ void __launch_bounds__(256)
+npos_scatter_kernel(const u64 *__restrict__ off, const int32_t *__restrict__ n_pos,
+                    const u64 *__restrict__ n_pos_off, u64 n_reads, u32 *nflag)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += stride) {
+        const u64 base = off[r], len = off[r + 1] - base;
+        for (u64 i = n_pos_off[r]; i < n_pos_off[r + 1]; ++i) {
+            const int32_t rel = n_pos[i];
+            if (rel < 0 || (u64)rel >= len) continue;
+            const u64 p = base + (u64)rel;
+            atomicOr(&nflag[p >> 5], 1u << (p & 31));
+        }
+    }
+}
+
+
+// =================================================================================================
+// counting: rolling canonical k-mers (counter.h:413-429) + table insert (counter.h:459-476)
+// =================================================================================================
+
+template <int W>
+__device__ __forceinline__ void spill_key(const u64 *key, Counters *ctr, u64 *ovf, u64 ovf_cap)
+{
+    u64 at = atomicAdd(&ctr->overflow_n, 1ull);
+    if (at < ovf_cap) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) ovf[at * (W + 1) + j] = key[j];
+        ovf[at * (W + 1) + W] = 1;
+    } else {
+        atomicOr(&ctr->error_flags, ERR_OVERFLOW_LOST);
+    }
+}
+
+// One thread owns one stream word: the 32 windows that END at its 32 positions.  Because the stream
+// is packed MSB-first and the word boundary is a window end, the k-1 bases before the word are simply
+// the previous W stream words -- the rolling state is primed without a single shift.
+template <int W>
+__global__ void __launch_bounds__(256)
+count_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, const u32 *__restrict__ rflag,
+             u64 word_begin, u64 word_end, int k, Slot<W> *table, u64 cap, Slot<W> *remote, u64 rcap,
+             u32 n_shards, u32 rank, Counters *ctr, u64 *ovf, u64 ovf_cap)
+{
+    const int top_shift = 2 * ((k - 1) & 31);
+    const u64 top_mask = (k & 31) ? ((1ull << (2 * (k & 31))) - 1ull) : ~0ull;
+    const int s = 2 * (32 * W - k);                   // 0..62
+    const int nb = (k + 30) >> 5;                     // flag words that cover the k-1 previous positions
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    u64 inst = 0;
+    u32 newk = 0, newr = 0;
+
+    for (u64 wi = word_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; wi < word_end; wi += stride) {
+        const u64 cur = stream[wi];
+        const u32 nf = nflag[wi], rf = rflag[wi];
+
+        // run = number of consecutive usable bases (same read, no N) ending just before this word
+        int run = k;
+        for (int j = 1; j <= nb; ++j) {
+            const u32 a = nflag[wi - j], b = rflag[wi - j];
+            if (a | b) {
+                const int pn = a ? 32 - __clz(a) : 0;  // first position after the last N
+                const int pr = b ? 31 - __clz(b) : 0;  // the last read start itself is usable
+                run = 32 * j - max(pn, pr);
+                break;
+            }
+        }
+
+        u64 fwd[W], rev[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) fwd[j] = stream[wi - 1 - j];
+        {
+            u64 y[W + 1];
+#pragma unroll
+            for (int j = 0; j < W; ++j) y[j] = pair_reverse64(~fwd[W - 1 - j]);
+            y[W] = 0;
+#pragma unroll
+            for (int j = 0; j < W; ++j) rev[j] = s ? ((y[j] >> s) | (y[j + 1] << (64 - s))) : y[j];
+        }
+
+#pragma unroll 2
+        for (int i = 0; i < 32; ++i) {
+            const u32 b = (u32)(cur >> (62 - 2 * i)) & 3u;
+            if ((rf >> i) & 1u) run = 0;
+            run = ((nf >> i) & 1u) ? 0 : run + 1;
+#pragma unroll
+            for (int j = W - 1; j > 0; --j) fwd[j] = (fwd[j] << 2) | (fwd[j - 1] >> 62);
+            fwd[0] = (fwd[0] << 2) | b;
+            fwd[W - 1] &= top_mask;
+#pragma unroll
+            for (int j = 0; j < W - 1; ++j) rev[j] = (rev[j] >> 2) | (rev[j + 1] << 62);
+            rev[W - 1] = (rev[W - 1] >> 2) | ((u64)(3u - b) << top_shift);
+
+            if (run >= k) {
+                const bool use_rev = key_less<W>(rev, fwd);        // key = min(forward, reverse), counter.h:429
+                u64 key[W];
+#pragma unroll
+                for (int j = 0; j < W; ++j) key[j] = use_rev ? rev[j] : fwd[j];
+                const u64 h = hash_key<W>(key);
+                ++inst;
+                int r;
+                if (n_shards > 1 && shard_of_hash(h, n_shards) != rank) {
+                    r = table_insert<W>(remote, rcap, key, h, 1u);
+                    newr += (r > 0);
+                } else {
+                    r = table_insert<W>(table, cap, key, h, 1u);
+                    newk += (r > 0);
+                }
+                if (r < 0) spill_key<W>(key, ctr, ovf, ovf_cap);
+            }
+        }
+    }
+    inst = warp_sum_u64(inst);
+    newk = warp_sum_u32(newk);
+    newr = warp_sum_u32(newr);
+    if ((threadIdx.x & 31) == 0) {
+        if (inst) atomicAdd(&ctr->instances, inst);
+        if (newk) atomicAdd(&ctr->new_keys, (u64)newk);
+        if (newr) atomicAdd(&ctr->new_keys_remote, (u64)newr);
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+insert_records_kernel(const u64 *__restrict__ rec, u64 n, int weighted, Slot<W> *table, u64 cap,
+                      Slot<W> *remote, u64 rcap, u32 n_shards, u32 rank,
+                      Counters *ctr, u64 *ovf, u64 ovf_cap)
+{
+    const int rw = weighted ? W + 1 : W;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    u32 newk = 0, newr = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        u64 key[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) key[j] = rec[i * rw + j];
+        u64 wgt = weighted ? rec[i * rw + W] : 1ull;
+        if (wgt == 0) continue;
+        const u32 add = wgt > COUNT_SAT ? COUNT_SAT : (u32)wgt;
+        const u64 h = hash_key<W>(key);
+        int r;
+        if (n_shards > 1 && shard_of_hash(h, n_shards) != rank) {
+            r = table_insert<W>(remote, rcap, key, h, add);
+            newr += (r > 0);
+        } else {
+            r = table_insert<W>(table, cap, key, h, add);
+            newk += (r > 0);
+        }
+        if (r < 0) {
+            u64 at = atomicAdd(&ctr->overflow_n, 1ull);
+            if (at < ovf_cap) {
+#pragma unroll
+                for (int j = 0; j < W; ++j) ovf[at * (W + 1) + j] = key[j];
+                ovf[at * (W + 1) + W] = add;
+            } else {
+                atomicOr(&ctr->error_flags, ERR_OVERFLOW_LOST);
+            }
+        }
+    }
+    newk = warp_sum_u32(newk);
+    newr = warp_sum_u32(newr);
+    if ((threadIdx.x & 31) == 0) {
+        if (newk) atomicAdd(&ctr->new_keys, (u64)newk);
+        if (newr) atomicAdd(&ctr->new_keys_remote, (u64)newr);
+    }
+}
+
+// =================================================================================================
+// table maintenance
+// =================================================================================================
+
+__global__ void __launch_bounds__(256) table_init1_kernel(uint4 *slots, u64 n)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const uint4 empty = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) slots[i] = empty;
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+rehash_kernel(const Slot<W> *__restrict__ from, u64 n_from, Slot<W> *to, u64 cap, Counters *ctr)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_from; i += stride) {
+        Slot<W> sl = from[i];
+        if (!slot_occupied<W>(sl)) continue;
+        const u64 h = hash_key<W>(sl.key);
+        if (table_insert<W>(to, cap, sl.key, h, sl.cs) < 0) atomicOr(&ctr->error_flags, ERR_OVERFLOW_LOST);
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) clamp_kernel(Slot<W> *t, u64 n)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (t[i].cs > COUNT_SAT) t[i].cs = COUNT_SAT;
+}
+
+// clamp + ++occurrenceDistribution[count] (counter.h:496).  Low counts go through a shared-memory
+// histogram, the long tail straight to global atomics.
+constexpr int HIST_SMEM_BINS = 4096;
+template <int W>
+__global__ void __launch_bounds__(256) histogram_kernel(Slot<W> *t, u64 n, u64 *occ_hist)
+{
+    __shared__ u32 sh[HIST_SMEM_BINS];
+    for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Slot<W> sl = t[i];
+        if (!slot_occupied<W>(sl)) continue;
+        u32 c = sl.cs;
+        if (c > COUNT_SAT) { c = COUNT_SAT; t[i].cs = c; }
+        if (c < HIST_SMEM_BINS) atomicAdd(&sh[c], 1u);
+        else atomicAdd(&occ_hist[c], 1ull);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&occ_hist[i], (u64)sh[i]);
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+export_kernel(const Slot<W> *__restrict__ t, u64 n, u32 min_count, u64 *keys_out, uint16_t *counts_out,
+              u64 capacity, u64 *d_n_out)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const u64 n_round = (n + 31) & ~31ull;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        Slot<W> sl;
+        bool keep = false;
+        if (i < n) {
+            sl = t[i];
+            keep = slot_occupied<W>(sl) && sl.cs >= min_count;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m == 0) continue;
+        const int leader = __ffs(m) - 1;
+        u64 base = 0;
+        if (lane == leader) base = atomicAdd(d_n_out, (u64)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (keep) {
+            const u64 at = base + __popc(m & ((1u << lane) - 1u));
+            if (at < capacity) {
+#pragma unroll
+                for (int j = 0; j < W; ++j) keys_out[at * W + j] = sl.key[j];
+                counts_out[at] = (uint16_t)(sl.cs > COUNT_SAT ? COUNT_SAT : sl.cs);
+            }
+        }
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+shard_count_kernel(const Slot<W> *__restrict__ t, u64 n, u32 n_shards, u64 *d_counts)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const u64 n_round = (n + 31) & ~31ull;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool occ = false;
+        u32 dest = 0;
+        if (i < n) {
+            Slot<W> sl = t[i];
+            occ = slot_occupied<W>(sl);
+            if (occ) dest = shard_of_hash(hash_key<W>(sl.key), n_shards);
+        }
+        const unsigned act = __ballot_sync(0xffffffffu, occ);
+        if (occ) {
+            const unsigned peers = __match_any_sync(act, dest);
+            if (lane == __ffs(peers) - 1) atomicAdd(&d_counts[dest], (u64)__popc(peers));
+        }
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+shard_pack_kernel(const Slot<W> *__restrict__ t, u64 n, u32 n_shards, u64 *d_cursors, u64 *rec_out)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const u64 n_round = (n + 31) & ~31ull;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool occ = false;
+        u32 dest = 0;
+        Slot<W> sl;
+        if (i < n) {
+            sl = t[i];
+            occ = slot_occupied<W>(sl);
+            if (occ) dest = shard_of_hash(hash_key<W>(sl.key), n_shards);
+        }
+        const unsigned act = __ballot_sync(0xffffffffu, occ);
+        if (occ) {
+            const unsigned peers = __match_any_sync(act, dest);
+            const int leader = __ffs(peers) - 1;
+            u64 base = 0;
+            if (lane == leader) base = atomicAdd(&d_cursors[dest], (u64)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            const u64 at = base + __popc(peers & ((1u << lane) - 1u));
+#pragma unroll
+            for (int j = 0; j < W; ++j) rec_out[at * (W + 1) + j] = sl.key[j];
+            rec_out[at * (W + 1) + W] = sl.cs > COUNT_SAT ? COUNT_SAT : sl.cs;
+        }
+    }
+}
+
+}  // namespace pbk

@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""Random read-modify-write microbenchmark (R_atomic) -> gpurun_out/atomics.json"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from platanus_b_b200 import microbench_atomics  # noqa: E402
+
+out = []
+MB = 1 << 20
+for mb in (16, 32, 48 * 0 + 64, 128, 256, 1024, 4096, 16384):
+    for mode in (0, 1, 2):
+        slots = (mb * MB) // 16
+        n_ops = 1 << 28 if mode < 2 else slots // 2
+        try:
+            r = microbench_atomics(mb * MB, n_ops, mode)
+        except Exception as e:  # noqa: BLE001
+            r = None
+            print("failed", mb, mode, e, flush=True)
+        rec = {"table_mb": mb, "mode": ["red", "ld+red", "cas-insert"][mode], "n_ops": n_ops, "gops": None if r is None else r / 1e9}
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/atomics.json", "w"), indent=1)

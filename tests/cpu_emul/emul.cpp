@@ -1,0 +1,94 @@
+// emul.cpp -- TEST ONLY: drives the product kernels (pbk_kernels_impl.cuh) sequentially on the host
+// through the same stages pbk_api.cu launches on the GPU: read_marks -> pack -> count -> histogram ->
+// export.  Used by tests/test_kernel_logic_cpu.py to compare the kernel logic with the oracle.
+#include "cuda_shim.h"
+#include "../../platanus_b_b200/csrc/pbk_kernels_impl.cuh"
+
+#include <vector>
+
+using namespace pbk;
+
+template <int W>
+static int run(const uint8_t *bases, const u64 *off, u64 n_reads, int k, int encoding, const int32_t *n_pos,
+               const u64 *n_pos_off, u64 table_slots, u32 n_shards, u32 rank, u32 min_count,
+               u64 *keys_out, uint16_t *counts_out, u64 cap_out, u64 *n_out, u64 *occ_hist, u64 *len_hist,
+               u64 *n_inst, u32 *err_flags, u64 *remote_records, u64 *n_remote)
+{
+    const u64 n_bases = off[n_reads], words = (n_bases + 31) / 32;
+    std::vector<u64> stream(words + STREAM_PAD_WORDS + 1, 0);
+    std::vector<u32> nflag(words + STREAM_PAD_WORDS + 1, 0), rflag(words + STREAM_PAD_WORDS + 1, 0);
+    Counters ctr{};
+    std::vector<Slot<W>> table(table_slots), remote(n_shards > 1 ? table_slots : 1);
+    for (auto *t : {&table, &remote})
+        for (auto &s : *t) { for (int j = 0; j < W; ++j) s.key[j] = (W == 1) ? KEY_EMPTY : 0; s.cs = 0; s.pad = 0; }
+    std::vector<u64> ovf((W + 1) * 1024);
+
+    read_marks_kernel(off, n_reads, len_hist, rflag.data() + STREAM_PAD_WORDS, &ctr);
+    // two chunks with an odd split to exercise word0 offsets (chunk boundaries are multiples of 32 bases)
+    const u64 w_split = words / 3;
+    pack_kernel<false>(bases, std::min<u64>(n_bases, w_split * 32), w_split, encoding, stream.data() + STREAM_PAD_WORDS,
+                       nflag.data() + STREAM_PAD_WORDS, 0, &ctr);
+    pack_kernel<false>(bases + w_split * 32, n_bases - w_split * 32, words - w_split, encoding,
+                       stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, w_split, &ctr);
+    if (encoding == 1) npos_scatter_kernel(off, n_pos, n_pos_off, n_reads, nflag.data() + STREAM_PAD_WORDS);
+    count_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
+                    0, w_split, k, table.data(), table_slots, remote.data(), table_slots, n_shards, rank, &ctr,
+                    ovf.data(), 1024);
+    count_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
+                    w_split, words, k, table.data(), table_slots, remote.data(), table_slots, n_shards, rank, &ctr,
+                    ovf.data(), 1024);
+    if (ctr.overflow_n) {          // grow + rehash + re-insert, as pbk_api.cu does
+        std::vector<Slot<W>> bigger(table_slots * 4);
+        for (auto &s : bigger) { for (int j = 0; j < W; ++j) s.key[j] = (W == 1) ? KEY_EMPTY : 0; s.cs = 0; s.pad = 0; }
+        rehash_kernel<W>(table.data(), table_slots, bigger.data(), table_slots * 4, &ctr);
+        table.swap(bigger);
+        table_slots *= 4;
+        std::vector<u64> copy(ovf.begin(), ovf.begin() + std::min<u64>(ctr.overflow_n, 1024) * (W + 1));
+        const u64 n = std::min<u64>(ctr.overflow_n, 1024);
+        ctr.overflow_n = 0;
+        insert_records_kernel<W>(copy.data(), n, 1, table.data(), table_slots, remote.data(), remote.size(), 1, 0, &ctr,
+                                 ovf.data(), 1024);
+    }
+    histogram_kernel<W>(table.data(), table_slots, occ_hist);
+    *n_out = 0;
+    export_kernel<W>(table.data(), table_slots, min_count, keys_out, counts_out, cap_out, n_out);
+    *n_inst = ctr.instances;
+    *err_flags = ctr.error_flags;
+    *n_remote = 0;
+    if (n_shards > 1 && remote_records) {
+        std::vector<u64> cnt(n_shards, 0), cur(n_shards, 0);
+        shard_count_kernel<W>(remote.data(), remote.size(), n_shards, cnt.data());
+        u64 tot = 0;
+        for (u32 i = 0; i < n_shards; ++i) { cur[i] = tot; tot += cnt[i]; }
+        shard_pack_kernel<W>(remote.data(), remote.size(), n_shards, cur.data(), remote_records);
+        *n_remote = tot;
+    }
+    return 0;
+}
+
+extern "C" int emul_count(const uint8_t *bases, const u64 *off, u64 n_reads, int k, int encoding,
+                          const int32_t *n_pos, const u64 *n_pos_off, u64 table_slots, u32 n_shards, u32 rank,
+                          u32 min_count, u64 *keys_out, uint16_t *counts_out, u64 cap_out, u64 *n_out,
+                          u64 *occ_hist, u64 *len_hist, u64 *n_inst, u32 *err_flags, u64 *remote_records,
+                          u64 *n_remote)
+{
+#define GO(Wv) case Wv: return run<Wv>(bases, off, n_reads, k, encoding, n_pos, n_pos_off, table_slots, n_shards, rank, \
+                                      min_count, keys_out, counts_out, cap_out, n_out, occ_hist, len_hist, n_inst, \
+                                      err_flags, remote_records, n_remote);
+    switch ((k + 31) / 32) { GO(1) GO(2) GO(3) GO(4) GO(5) GO(6) GO(7) GO(8) default: return -1; }
+}
+
+// insert weighted records (the receive side of the shard exchange) into a fresh table and dump it
+extern "C" int emul_insert_records(const u64 *records, u64 n, int k, u64 table_slots, u64 *keys_out,
+                                   uint16_t *counts_out, u64 cap_out, u64 *n_out)
+{
+    const int Wd = (k + 31) / 32;
+    Counters ctr{};
+    std::vector<u64> ovf(16 * 9);
+#define INS(Wv) case Wv: { std::vector<Slot<Wv>> t(table_slots);                                                   \
+        for (auto &s : t) { for (int j = 0; j < Wv; ++j) s.key[j] = (Wv == 1) ? KEY_EMPTY : 0; s.cs = 0; s.pad = 0; } \
+        insert_records_kernel<Wv>(records, n, 1, t.data(), table_slots, t.data(), table_slots, 1, 0, &ctr, ovf.data(), 16); \
+        *n_out = 0; export_kernel<Wv>(t.data(), table_slots, 1, keys_out, counts_out, cap_out, n_out);               \
+        return ctr.overflow_n ? -2 : 0; }
+    switch (Wd) { INS(1) INS(2) INS(3) INS(4) INS(5) INS(6) INS(7) INS(8) default: return -1; }
+}

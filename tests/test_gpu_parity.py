@@ -1,0 +1,286 @@
+"""Parity tests proper: the CUDA path through the C ABI (libpbk.so) against the oracle, the committed
+reference-binary golden vectors and -- at full BASELINE sizes -- size-independent properties.
+Run on a B200 with `pytest -m gpu`.  Bar: bit-exact (integer work)."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_cases as G
+from platanus_b_b200 import KmerCounter, PbkError, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _reads(O, case, tmp_path):
+    rd = O.Reads()
+    for f in G.materialise(case, str(tmp_path)):
+        rd.add_file(f)
+    return rd
+
+
+def _oracle_reads_from_set(O, rs):
+    rd = O.Reads()
+    b, o = rs.flat()
+    rd.add_array(b, o)
+    return rd
+
+
+@pytest.mark.parametrize("case", [c for c in G.CASES if not c.expect_fail], ids=lambda c: c.name)
+def test_golden_cases_bit_exact(oracle, case, tmp_path):
+    """Every committed output of the reference binary: .tsv text, cutoff, header sizes and the sorted
+    (key, count) dump of kmer_occ.bin, reproduced by the GPU path end to end (incl. our .bin writer)."""
+    O = oracle
+    g = np.load(G.golden_path(case), allow_pickle=False)
+    rd = _reads(O, case, tmp_path)
+    bases, offs = rd.arrays()
+    with KmerCounter(case.k) as kc:
+        dh = kc.make_kmer_read_distribution(bases, offs, 10 ** 9)
+        cutoff = kc.coverage_cutoff(case.n_opt, case.repeat)
+        assert cutoff == int(g["cutoff"])
+        tsv = str(tmp_path / "g.tsv")
+        kc.output_occurrence_distribution(tsv)
+        assert open(tsv).read() == str(g["tsv"])
+        ave_len = kc.calc_length_distribution_average()
+        assert "%g" % ave_len == str(g["ave_read_len"])
+        ave_cov = kc.calc_occurrence_distribution_average(cutoff, kc.get_max_occurrence())
+        ave_cov = ave_cov * ave_len / (ave_len - case.k + 1.0)
+        assert "%g" % (ave_cov * (ave_len - case.k + 1.0) / ave_len) == str(g["kmer_coverage"])
+        keys, counts = kc.sorted_key_from_kmer_file(cutoff)
+        assert np.array_equal(keys, g["keys"]) and np.array_equal(counts, g["counts"])
+        path = str(tmp_path / "g_kmer_occ.bin")
+        kc.output_occurrence_table_binary(path, cutoff, dh)
+        t = O.read_bin(path)
+        assert t.reachable and t.k == case.k and t.index_size == int(g["index_size"])
+        k2, c2 = t.sorted_dump()
+        assert np.array_equal(k2, g["keys"]) and np.array_equal(c2, g["counts"])
+        # and the full table against the oracle (golden only holds entries >= cutoff)
+        want = O.count(rd, case.k)
+        allk, allc = kc.export(1, sorted=True)
+        assert np.array_equal(allk, want.keys) and np.array_equal(allc, want.counts)
+        assert kc.n_instances == want.n_instances
+        assert np.array_equal(kc.len_hist, want.len_hist)
+
+
+def test_empty_distribution_raises_kmer_dist_error(oracle, tmp_path):
+    """reference: KmerDistError from calcDistributionAverage (counter.h:225-237), exit code 6"""
+    O = oracle
+    case = G.CASE_BY_NAME["empty_k8"]
+    rd = _reads(O, case, tmp_path)
+    bases, offs = rd.arrays()
+    with KmerCounter(case.k) as kc:
+        kc.make_kmer_read_distribution(bases, offs, 10 ** 9)
+        assert kc.n_distinct == 0 and kc.get_max_occurrence() == 0
+        with pytest.raises(PbkError) as e:
+            kc.calc_occurrence_distribution_average(kc.coverage_cutoff(), kc.get_max_occurrence())
+        assert e.value.status == -7
+
+
+@pytest.mark.parametrize("k", [32, 42, 52, 62, 72, 75])
+def test_c2_k_sweep_scaled_vs_oracle(oracle, k):
+    """BASELINE config 2 (k sweep 32..75, 1-3 word keys) on a 1/40-scale genome."""
+    O = oracle
+    rs = synth.make_reads(synth.config("C2", scale=1 / 40))
+    want = O.count(_oracle_reads_from_set(O, rs), k)
+    b, o = rs.flat()
+    with KmerCounter(k) as kc:
+        kc.push_reads(b, o)
+        kc.finalize()
+        keys, counts = kc.export(1, sorted=True)
+        assert np.array_equal(keys, want.keys) and np.array_equal(counts, want.counts)
+        assert np.array_equal(kc.occ_hist, want.occ_hist)
+        assert kc.coverage_cutoff() == O.coverage_cutoff(want.occ_hist, want.max_occ)
+
+
+@pytest.mark.parametrize("name,scale", [("C3", 1 / 100), ("C4", 1 / 200), ("C5", 1 / 20)])
+def test_other_configs_scaled_vs_oracle(oracle, name, scale):
+    O = oracle
+    spec = synth.config(name, scale=scale)
+    rs = synth.make_reads(spec)
+    want = O.count(_oracle_reads_from_set(O, rs), spec.k)
+    b, o = rs.flat()
+    with KmerCounter(spec.k) as kc:
+        kc.push_reads(b, o)
+        kc.finalize()
+        keys, counts = kc.export(1, sorted=True)
+        assert np.array_equal(keys, want.keys) and np.array_equal(counts, want.counts)
+        assert kc.coverage_cutoff(0, spec.repeat_mode) == O.coverage_cutoff(want.occ_hist, want.max_occ, 0, spec.repeat_mode)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "platanus_b")), reason="reference binary not built")
+@pytest.mark.parametrize("k,repeat", [(32, False), (75, False), (32, True)])
+def test_against_the_reference_binary_on_the_box(oracle, k, repeat, tmp_path):
+    """The unmodified reference (`platanus_b assemble -kmer_occ_only`, OpenMP, all its threads) and the
+    GPU path on the same FASTQ files: .tsv bytes, auto cutoff and sorted table dump."""
+    O = oracle
+    rs = synth.make_reads(synth.config("C1", scale=1 / 20))
+    files = synth.write_fastq(rs, str(tmp_path / "r_1.fq"), str(tmp_path / "r_2.fq"))
+    ref = O.run_reference(files, k, str(tmp_path), threads=min(8, os.cpu_count() or 1), mem_gb=1, repeat=repeat)
+    assert ref.returncode == 0, ref.stderr
+    b, o = rs.flat()
+    with KmerCounter(k) as kc:
+        dh = kc.make_kmer_read_distribution(b, o, 10 ** 9)
+        cutoff = kc.coverage_cutoff(0, repeat)
+        assert cutoff == ref.cutoff
+        tsv = str(tmp_path / "g.tsv")
+        kc.output_occurrence_distribution(tsv)
+        assert open(tsv).read() == ref.tsv
+        keys, counts = kc.sorted_key_from_kmer_file(cutoff)
+        rk, rc = ref.table.sorted_dump()
+        assert np.array_equal(keys, rk) and np.array_equal(counts, rc)
+        assert "%g" % kc.calc_length_distribution_average() == ref.ave_read_len
+        path = str(tmp_path / "g_kmer_occ.bin")
+        kc.output_occurrence_table_binary(path, cutoff, dh)
+        t = O.read_bin(path)
+        assert t.reachable and t.index_size == ref.table.index_size
+
+
+def test_c1_full_size_properties():
+    """BASELINE config 1 at full size (4.6 Mb, 2x150 bp, 100x): too big for the oracle in a test, so
+    check what must hold at any size."""
+    spec = synth.config("C1")
+    rs = synth.make_reads(spec)
+    b, o = rs.flat()
+    n, L = rs.reads.shape
+    with KmerCounter(32, timing=True) as kc:
+        kc.push_reads(b, o)
+        kc.finalize()
+        occ = kc.occ_hist.astype(np.int64)
+        # every window without an N is counted exactly once (nothing saturates at 100x)
+        is_n = (rs.reads == ord("N"))
+        csum = np.concatenate([np.zeros((n, 1), np.int32), np.cumsum(is_n, axis=1, dtype=np.int32)], axis=1)
+        clean = int(((csum[:, 32:] - csum[:, :-32]) == 0).sum())
+        assert kc.n_instances == clean
+        assert int((np.arange(65535) * occ).sum()) == clean
+        assert int(occ.sum()) == kc.n_distinct
+        assert int(kc.len_hist[L]) == n and int(kc.len_hist.sum()) == n
+        cutoff = kc.coverage_cutoff()
+        keys, counts = kc.export(cutoff, sorted=True)
+        assert len(counts) == int(occ[cutoff:].sum())
+        assert np.all(keys[1:, 0] > keys[:-1, 0])                      # strictly ascending, distinct
+        assert int(counts.min()) >= cutoff
+        # genome-sized solid set: kept k-mers ~ genome length (both strands collapse to one key)
+        assert 0.95 * spec.total_genome < len(counts) < 1.10 * spec.total_genome
+        first = (keys.copy(), counts.copy(), kc.occ_hist.copy())
+        # idempotence: reset + recount in two pushes of different sizes gives the identical table
+        kc.reset()
+        cut = (n // 3) * L
+        kc.push_reads(b[:cut], o[: n // 3 + 1])
+        kc.push_reads(b[cut:], o[n // 3:] - o[n // 3])
+        kc.finalize()
+        k2, c2 = kc.export(cutoff, sorted=True)
+        assert np.array_equal(first[0], k2) and np.array_equal(first[1], c2) and np.array_equal(first[2], kc.occ_hist)
+
+
+def test_device_resident_push_equals_host_push(oracle):
+    import torch
+    O = oracle
+    rs = synth.make_reads(synth.config("C1", scale=1 / 50))
+    b, o = rs.flat()
+    want = O.count(_oracle_reads_from_set(O, rs), 32)
+    db = torch.from_numpy(b.copy()).cuda()
+    do = torch.from_numpy(o.astype(np.int64)).cuda()
+    torch.cuda.synchronize()
+    with KmerCounter(32) as kc:
+        kc.push_reads_device(db.data_ptr(), do.data_ptr(), len(o) - 1, len(b))
+        kc.finalize()
+        keys, counts = kc.export(1, sorted=True)
+    assert np.array_equal(keys, want.keys) and np.array_equal(counts, want.counts)
+
+
+def test_unsorted_export_is_a_permutation_of_sorted(oracle):
+    rs = synth.make_reads(synth.config("C1", scale=1 / 100))
+    b, o = rs.flat()
+    with KmerCounter(52) as kc:
+        kc.push_reads(b, o)
+        kc.finalize()
+        ks, cs = kc.export(2, sorted=True)
+        ku, cu = kc.export(2, sorted=False)
+    order = np.lexsort((ku[:, 0], ku[:, 1]))
+    assert np.array_equal(ku[order], ks) and np.array_equal(cu[order], cs)
+
+
+@pytest.mark.parametrize("k,n_shards", [(32, 2), (75, 3), (32, 8)])
+def test_logical_shards_on_one_gpu_match_unsharded(oracle, k, n_shards):
+    """with fewer physical GPUs than shards, run G logical shards sequentially on
+    one device -- same partition function, the all-to-all replaced by local copies -- and compare
+    with G = 1.  Exercises pbk_shard_send_counts / pack_device / insert_device."""
+    import torch
+    O = oracle
+    rs = synth.make_reads(synth.config("C1", scale=1 / 60))
+    b, o = rs.flat()
+    want = O.count(_oracle_reads_from_set(O, rs), k)
+    n = len(o) - 1
+    W = (k + 31) // 32
+    ctxs = [KmerCounter(k, n_shards=n_shards, shard_rank=r) for r in range(n_shards)]
+    try:
+        sends, counts = [], []
+        for r, kc in enumerate(ctxs):
+            lo, hi = n * r // n_shards, n * (r + 1) // n_shards
+            kc.push_reads(b[int(o[lo]):int(o[hi])], o[lo:hi + 1] - o[lo])
+            cnt = kc.shard_send_counts(n_shards)
+            assert cnt[r] == 0
+            buf = torch.zeros((int(cnt.sum()) + 1, W + 1), dtype=torch.int64, device="cuda")
+            kc.shard_pack_device(buf.data_ptr(), int(cnt.sum()) + 1)
+            sends.append(buf)
+            counts.append(cnt)
+        torch.cuda.synchronize()
+        for dest, kc in enumerate(ctxs):
+            for src in range(n_shards):
+                if src == dest or counts[src][dest] == 0:
+                    continue
+                start = int(counts[src][:dest].sum())
+                part = sends[src][start:start + int(counts[src][dest])].contiguous()
+                kc.shard_insert_device(part.data_ptr(), part.shape[0])
+        keys, cts, inst, hist = [], [], 0, np.zeros(65535, np.uint64)
+        for kc in ctxs:
+            kc.finalize()
+            kk, cc = kc.export(1, sorted=True)
+            keys.append(kk); cts.append(cc); inst += kc.n_instances; hist += kc.occ_hist
+        keys = np.concatenate(keys); cts = np.concatenate(cts)
+        order = np.lexsort(tuple(keys[:, w] for w in range(W)))
+        assert np.array_equal(keys[order], want.keys) and np.array_equal(cts[order], want.counts)
+        assert inst == want.n_instances and np.array_equal(hist, want.occ_hist)
+        sizes = [len(c) for c in cts] if False else [int(kc.n_distinct) for kc in ctxs]
+        assert max(sizes) < 1.2 * (sum(sizes) / n_shards) + 64            # the mixed hash balances owners
+    finally:
+        for kc in ctxs:
+            kc.close()
+
+
+def test_table_growth_from_a_tiny_hint(oracle):
+    O = oracle
+    rs = synth.make_reads(synth.config("C3", scale=1 / 200))
+    b, o = rs.flat()
+    want = O.count(_oracle_reads_from_set(O, rs), 32)
+    with KmerCounter(32, table_slots_hint=1024) as kc:
+        kc.push_reads(b, o)
+        kc.finalize()
+        keys, counts = kc.export(1, sorted=True)
+        assert kc.stats()["n_grow"] >= 1
+    assert np.array_equal(keys, want.keys) and np.array_equal(counts, want.counts)
+
+
+def test_error_behaviour():
+    bad = np.frombuffer(b"ACGTACGTACGTACGTRYACGTACGTACGTACGTACGTACGTACGT", dtype=np.uint8)
+    with KmerCounter(8) as kc:
+        with pytest.raises(PbkError) as e:
+            kc.push_reads(bad, np.array([0, len(bad)], np.uint64))
+        assert e.value.status == -6                                    # PBK_E_BAD_BASE
+    long_read = np.full(500000, ord("A"), np.uint8)
+    with KmerCounter(8) as kc:
+        with pytest.raises(PbkError) as e:
+            kc.push_reads(long_read, np.array([0, 500000], np.uint64))
+        assert e.value.status == -5                                    # platanus::ReadError, common.h:465
+    ok = np.full(499999, ord("A"), np.uint8)
+    with KmerCounter(8) as kc:
+        with pytest.raises(PbkError) as e:
+            kc.export(1)
+        assert e.value.status == -8                                    # export before finalize
+        kc.push_reads(ok, np.array([0, 499999], np.uint64))
+        kc.finalize()
+        keys, counts = kc.export(1)
+        assert len(counts) == 1 and int(counts[0]) == 65534 and int(keys[0, 0]) == 0   # saturated poly-A
+        with pytest.raises(PbkError):
+            kc.push_reads(ok, np.array([0, 10], np.uint64))            # push after finalize
