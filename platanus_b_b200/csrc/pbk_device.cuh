@@ -92,12 +92,17 @@ __device__ __forceinline__ void st_cg_u64(u64 *p, u64 v)
 {
     asm volatile("st.global.cg.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_release_u32(u32 *p, u32 v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
 
 #else   // tests/cpu_emul: same source run sequentially on the host, see tests/cpu_emul/cuda_shim.h
 inline u64 ld_cg_u64(const u64 *p) { return *p; }
 inline u32 ld_cg_u32(const u32 *p) { return *p; }
 inline void red_add_u32(u32 *p, u32 v) { *p += v; }
 inline void st_cg_u64(u64 *p, u64 v) { *p = v; }
+inline void st_release_u32(u32 *p, u32 v) { *p = v; }
 #endif
 
 // reverse the order of the 32 2-bit groups of a word
@@ -139,26 +144,31 @@ __device__ __forceinline__ int table_insert(Slot<W> *table, u64 cap, const u64 *
         }
         return -1;
     } else {
+        int probe = 0;
 #pragma unroll 1
-        for (int probe = 0; probe < MAX_PROBE; ++probe, idx = (idx + 1 == cap) ? 0 : idx + 1) {
+        while (probe < MAX_PROBE) {
             Slot<W> *s = table + idx;
             u32 cs = ld_cg_u32(&s->cs);
             if (cs == 0) {
-                u32 old = atomicCAS(&s->cs, 0u, CS_LOCKED);
+                const u32 old = atomicCAS(&s->cs, 0u, CS_LOCKED);
                 if (old == 0) {
 #pragma unroll
                     for (int j = 0; j < W; ++j) st_cg_u64(&s->key[j], key[j]);
-                    __threadfence();                      // key words visible before the slot is published
-                    atomicExch(&s->cs, add);
+                    st_release_u32(&s->cs, add);          // key words become visible before the count
                     return 1;
                 }
                 cs = old;
             }
-            while (cs == CS_LOCKED) cs = ld_cg_u32(&s->cs);   // the claimer publishes within a few stores
+            // Claimed but not yet published: look at the SAME slot again.  (Written as a re-probe and not
+            // as an inner `while (cs == LOCKED)` spin: nvcc deleted that loop because nothing after it
+            // used `cs`, and threads then compared half-written keys.)
+            if (cs == CS_LOCKED) continue;
             bool eq = true;
 #pragma unroll
             for (int j = 0; j < W; ++j) eq &= (ld_cg_u64(&s->key[j]) == key[j]);
             if (eq) { red_add_u32(&s->cs, add); return 0; }
+            ++probe;
+            idx = (idx + 1 == cap) ? 0 : idx + 1;
         }
         return -1;
     }
