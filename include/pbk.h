@@ -56,7 +56,9 @@ enum {
 };
 
 enum {
-    PBK_F_TIMING = 1u << 0  /* bracket every kernel launch with CUDA events (see pbk_get_stats)      */
+    PBK_F_TIMING = 1u << 0,       /* bracket every kernel launch with CUDA events (see pbk_get_stats) */
+    PBK_F_NO_PARTITION = 1u << 1, /* always insert straight into the table (no hash-range bucket pass)  */
+    PBK_F_FORCE_PARTITION = 1u << 2 /* use the bucket pass even for tiny batches (tests)               */
 };
 
 typedef struct pbk_config {

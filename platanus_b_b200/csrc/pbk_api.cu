@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -23,6 +24,8 @@ constexpr u64 CHUNK_BASES = 1ull << 25;          // 32 Mi bases per pipeline sta
 constexpr u64 MIN_SLOTS = 1ull << 16;
 constexpr double MAX_LOAD = 0.5;
 constexpr u64 U32_HEADROOM = (1ull << 32) - 65536 - 2;
+constexpr u64 PART_MIN_WINDOWS = 1ull << 22;    // smaller batches go straight to the table
+constexpr u32 PART_CHECK_EVERY = 16;             // buckets between counter read-backs in Pass B
 
 enum LaunchClass { LC_PACK = 0, LC_COUNT = 1, LC_OTHER = 2 };
 
@@ -49,6 +52,11 @@ struct pbk_ctx {
     Counters *d_ctr = nullptr, *h_ctr = nullptr;
     Counters last{};                 // cumulative counters at the last read-back
     u64 *d_ovf = nullptr; u64 ovf_cap = 0;
+    // partitioned counting: bucket store filled by Pass A, drained by Pass B
+    PartitionPlan plan{};
+    u64 *d_bkt_keys = nullptr; size_t bkt_bytes = 0;
+    u64 *d_bkt_cursor = nullptr, *h_bkt_cursor = nullptr;
+    bool partition_enabled = true, partition_forced = false;
     u64 *d_len_hist = nullptr, *d_occ_hist = nullptr, *d_shard_counts = nullptr;
     std::vector<u64> h_occ_hist, h_shard_counts;
 
@@ -289,6 +297,69 @@ int count_range(pbk_ctx *c, u64 w0, u64 w1)
     return PBK_OK;
 }
 
+// ---- partitioned path ---------------------------------------------------------------------------
+
+int prepare_partition(pbk_ctx *c, u64 windows_ub)
+{
+    const u64 est_slots = std::max<u64>(c->table.slots ? c->table.cap : 0,
+                                        (u64)((c->occupied + windows_ub * c->new_ratio) / MAX_LOAD));
+    c->plan = plan_partition(est_slots * (8 * (u64)c->W + 8), windows_ub, c->W);
+    const size_t need = (size_t)c->plan.n_buckets * c->plan.seg_cap * c->W * 8;
+    if (need > c->bkt_bytes) {
+        CK(cudaStreamSynchronize(c->s_compute));
+        dev_free(c, c->d_bkt_keys, c->bkt_bytes);
+        c->d_bkt_keys = nullptr; c->bkt_bytes = 0;
+        TRY(dev_alloc(c, (void **)&c->d_bkt_keys, need));
+        c->bkt_bytes = need;
+    }
+    if (!c->d_bkt_cursor) {
+        TRY(dev_alloc(c, (void **)&c->d_bkt_cursor, PART_MAX_BUCKETS * 8));
+        if (cudaMallocHost((void **)&c->h_bkt_cursor, PART_MAX_BUCKETS * 8) != cudaSuccess) return fail(c, PBK_E_NOMEM, "pinned host memory");
+    }
+    CK(cudaMemsetAsync(c->d_bkt_cursor, 0, PART_MAX_BUCKETS * 8, c->s_compute));
+    // a spilled key (bucket segment or bin full) is rare; the list is also used by Pass B
+    TRY(ensure_overflow(c, std::max<u64>(1ull << 20, PART_CHECK_EVERY * (c->plan.seg_cap + 1))));
+    return PBK_OK;
+}
+
+// Pass B: drain the bucket store into the table, one L2-sized hash range at a time
+int flush_buckets(pbk_ctx *c)
+{
+    const u32 P = c->plan.n_buckets;
+    CK(cudaMemcpyAsync(c->h_bkt_cursor, c->d_bkt_cursor, P * 8, cudaMemcpyDeviceToHost, c->s_compute));
+    TRY(read_counters(c));                          // also picks up instances counted by Pass A
+    TRY(drain_overflow(c));
+    c->d2h_bytes += P * 8;
+    u64 total = 0;
+    for (u32 b = 0; b < P; ++b) { c->h_bkt_cursor[b] = std::min<u64>(c->h_bkt_cursor[b], c->plan.seg_cap); total += c->h_bkt_cursor[b]; }
+    if (total == 0) return PBK_OK;
+    TRY(maybe_clamp(c, total));
+    const u64 occ_before = c->occupied + c->occupied_remote;
+    u64 done = 0;
+    for (u32 b = 0; b < P; ++b) {
+        const u64 n = c->h_bkt_cursor[b];
+        if (b == 0) TRY(ensure_room(c, (u64)(n * std::min(1.0, c->new_ratio * 1.25))));
+        {
+            Span sp(c, LC_COUNT);
+            launch_bucket_insert(c->d_bkt_keys + (size_t)b * c->plan.seg_cap * c->W, n, b, P, c->table, c->remote, c->shard,
+                                 c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+        }
+        CK(cudaGetLastError());
+        done += n;
+        const bool pilot = (b == 0), check = pilot || ((b + 1) % PART_CHECK_EVERY == 0) || b + 1 == P;
+        if (!check) continue;
+        TRY(read_counters(c));
+        TRY(drain_overflow(c));
+        // buckets are statistically identical hash ranges: what the finished ones added predicts the rest
+        const u64 added = c->occupied + c->occupied_remote - occ_before;
+        const double per_key = done ? (double)added / (double)done : c->new_ratio;
+        if (b + 1 < P) TRY(ensure_room(c, (u64)((double)(total - done) * std::min(1.0, per_key * 1.05)) + 4096));
+        if (b + 1 == P && done > 4096) c->new_ratio = std::max(0.01, std::min(1.0, per_key));
+    }
+    CK(cudaMemsetAsync(c->d_bkt_cursor, 0, PART_MAX_BUCKETS * 8, c->s_compute));
+    return PBK_OK;
+}
+
 int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, const u64 *h_offsets,
                 const u64 *d_offsets_in, u64 n_reads, u64 n_bases, int encoding, const int32_t *n_pos,
                 const u64 *n_pos_offsets)
@@ -316,13 +387,23 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
     CK(cudaGetLastError());
 
     const bool deferred_count = (encoding == PBK_ENC_PLATANUS);     // N flags arrive after all packs
+    const bool partitioned = c->partition_enabled && (windows_ub >= PART_MIN_WINDOWS || (c->partition_forced && windows_ub > 0));
+    if (partitioned) TRY(prepare_partition(c, windows_ub));
+    // large batches: Pass A per chunk (no host sync), Pass B once at the end.  Small ones: straight to the table.
+    auto count_words = [&](u64 w0, u64 w1) -> int {
+        if (!partitioned) return count_range(c, w0, w1);
+        Span sp(c, LC_COUNT);
+        launch_partition(stream, nflag, rflag, w0, w1, (int)c->k, c->W, c->plan, c->d_bkt_keys, c->d_bkt_cursor, c->d_ctr,
+                         c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+        return PBK_OK;
+    };
     if (d_bases_in) {
         // inputs already in HBM: pack chunk by chunk so the chunk's stream words are still in L2 when counted
         for (u64 b0 = 0; b0 < n_bases; b0 += CHUNK_BASES) {
             const u64 nb = std::min(CHUNK_BASES, n_bases - b0), w0 = b0 / 32, nw = (nb + 31) / 32;
             { Span sp(c, LC_PACK); launch_pack(d_bases_in + b0, nb, nw, encoding, stream, nflag, w0, c->d_ctr, c->s_compute); }
             CK(cudaGetLastError());
-            TRY(count_range(c, w0, w0 + nw));
+            TRY(count_words(w0, w0 + nw));
         }
     } else {
         if (!c->d_stage[0]) {
@@ -352,7 +433,7 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
             { Span sp(c, LC_PACK); launch_pack(c->d_stage[buf], nb, nw, encoding, stream, nflag, w0, c->d_ctr, c->s_compute); }
             CK(cudaGetLastError());
             CK(cudaEventRecord(c->ev_stage_free[buf], c->s_compute));
-            if (!deferred_count) TRY(count_range(c, w0, w0 + nw));
+            if (!deferred_count) TRY(count_words(w0, w0 + nw));
         }
     }
     if (deferred_count) {
@@ -367,11 +448,15 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
             c->h2d_bytes += total_n * 4 + (n_reads + 1) * 8;
             { Span sp(c, LC_OTHER); launch_npos_scatter(d_off, d_np, d_npo, n_reads, nflag, c->s_compute); }
             for (u64 w0 = 0; w0 < words && rc == PBK_OK; w0 += CHUNK_BASES / 32)
-                rc = count_range(c, w0, std::min(words, w0 + CHUNK_BASES / 32));
+                rc = count_words(w0, std::min(words, w0 + CHUNK_BASES / 32));
         }
         cudaStreamSynchronize(c->s_compute);
         dev_free(c, d_np, total_n * 4); dev_free(c, d_npo, (n_reads + 1) * 8);
         TRY(rc);
+    }
+    if (partitioned) {
+        CK(cudaGetLastError());
+        TRY(flush_buckets(c));
     }
     c->n_reads += n_reads;
     c->n_bases += n_bases;
@@ -390,6 +475,7 @@ void release_all(pbk_ctx *c)
         if (c->ev_copy_done[i]) cudaEventDestroy(c->ev_copy_done[i]);
         if (c->ev_stage_free[i]) cudaEventDestroy(c->ev_stage_free[i]);
     }
+    cudaFree(c->d_bkt_keys); cudaFree(c->d_bkt_cursor); if (c->h_bkt_cursor) cudaFreeHost(c->h_bkt_cursor);
     cudaFree(c->table.slots); cudaFree(c->remote.slots); cudaFree(c->d_ctr); cudaFree(c->d_ovf);
     cudaFree(c->d_len_hist); cudaFree(c->d_occ_hist); cudaFree(c->d_shard_counts);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
@@ -449,6 +535,8 @@ int pbk_create(pbk_ctx **out, const pbk_config *cfg)
     c->shard.n_shards = cfg->n_shards > 1 ? cfg->n_shards : 1;
     c->shard.rank = cfg->n_shards > 1 ? cfg->shard_rank : 0;
     c->table_hint = cfg->table_slots_hint;
+    c->partition_enabled = !(cfg->flags & PBK_F_NO_PARTITION) && getenv("PBK_NO_PARTITION") == nullptr;
+    c->partition_forced = (cfg->flags & PBK_F_FORCE_PARTITION) != 0;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     c->budget = cfg->hbm_budget_bytes ? cfg->hbm_budget_bytes : (u64)(free_b * 0.85);

@@ -29,6 +29,7 @@ constexpr u32 CS_LOCKED = 0xFFFFFFFFu;    // W >= 2: slot claimed, key words bei
 constexpr u32 COUNT_SAT = 65534u;         // counter.h:468
 constexpr int MAX_PROBE = 192;            // longer probe runs go to the overflow list
 constexpr int STREAM_PAD_WORDS = 16;      // zero words in front of stream / flag arrays
+constexpr int PART_MAX_BUCKETS = 512;     // hash-range buckets of the partitioned path
 
 template <int W>
 struct alignas(8) Slot {

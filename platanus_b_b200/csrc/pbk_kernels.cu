@@ -7,6 +7,7 @@
 #include "pbk_kernels.cuh"
 #include "pbk_kernels_impl.cuh"
 
+#include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
 
 namespace pbk {
@@ -18,6 +19,19 @@ static inline int grid_for(u64 n_threads, int block, int sm_count, int blocks_pe
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
 }
+
+#define PBK_DISPATCH_W(words, CALL)                                                                  \
+    switch (words) {                                                                                \
+    case 1: { constexpr int W = 1; CALL; } break;                                                    \
+    case 2: { constexpr int W = 2; CALL; } break;                                                    \
+    case 3: { constexpr int W = 3; CALL; } break;                                                    \
+    case 4: { constexpr int W = 4; CALL; } break;                                                    \
+    case 5: { constexpr int W = 5; CALL; } break;                                                    \
+    case 6: { constexpr int W = 6; CALL; } break;                                                    \
+    case 7: { constexpr int W = 7; CALL; } break;                                                    \
+    case 8: { constexpr int W = 8; CALL; } break;                                                    \
+    default: break;                                                                                  \
+    }
 
 void launch_pack(const uint8_t *bases, u64 n_valid, u64 n_words, int encoding,
                  u64 *stream, u32 *nflag, u64 word0, Counters *ctr, cudaStream_t st)
@@ -46,18 +60,6 @@ void launch_npos_scatter(const u64 *offsets, const int32_t *n_pos, const u64 *n_
 // dispatch on W = ceil(k/32)
 // =================================================================================================
 
-#define PBK_DISPATCH_W(words, CALL)                                                                  \
-    switch (words) {                                                                                \
-    case 1: { constexpr int W = 1; CALL; } break;                                                    \
-    case 2: { constexpr int W = 2; CALL; } break;                                                    \
-    case 3: { constexpr int W = 3; CALL; } break;                                                    \
-    case 4: { constexpr int W = 4; CALL; } break;                                                    \
-    case 5: { constexpr int W = 5; CALL; } break;                                                    \
-    case 6: { constexpr int W = 6; CALL; } break;                                                    \
-    case 7: { constexpr int W = 7; CALL; } break;                                                    \
-    case 8: { constexpr int W = 8; CALL; } break;                                                    \
-    default: break;                                                                                  \
-    }
 
 void launch_count(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
                   TableView table, TableView remote, ShardInfo shard, Counters *ctr,
@@ -81,6 +83,74 @@ void launch_insert_records(const u64 *records, u64 n, bool weighted, TableView t
         (insert_records_kernel<W><<<grid, 256, 0, st>>>(records, n, weighted ? 1 : 0, (Slot<W> *)table.slots,
             table.cap, (Slot<W> *)remote.slots, remote.cap, shard.n_shards, shard.rank,
             ctr, overflow_keys, overflow_cap)));
+}
+
+// ---- partitioned counting -------------------------------------------------------------------------
+constexpr size_t PART_SMEM_BUDGET = 192 * 1024;      // bins; the B200 SM has 227 KB per CTA
+constexpr u64 PART_REGION_BYTES = 16ull << 20;       // table bytes per bucket: two regions + key stream << L2
+
+PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words)
+{
+    PartitionPlan p{};
+    const u64 entries = PART_SMEM_BUDGET / (8 * (size_t)words);
+    u64 P = (est_table_bytes + PART_REGION_BYTES - 1) / PART_REGION_BYTES;
+    P = std::max<u64>(P, 8);
+    P = std::min<u64>(P, std::min<u64>((u64)PART_MAX_BUCKETS, entries / 24));
+    p.n_buckets = (u32)P;
+    p.bin_cap = (u32)(entries / P);
+    // one tile = threads * 32 window ends, ~85 % of them valid; keep the mean bin fill at 60 % of the bin
+    u64 threads = (u64)(p.bin_cap * 0.6 * (double)P / (32.0 * 0.85));
+    threads = std::min<u64>(512, threads / 32 * 32);
+    p.threads = (int)std::max<u64>(64, threads);
+    p.smem = (size_t)p.n_buckets * p.bin_cap * 8 * words;
+    p.seg_cap = windows_ub / P + windows_ub / (P * 16) + 8192;
+    return p;
+}
+
+template <int W>
+static void partition_launch_w(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
+                               const PartitionPlan &plan, u64 *bkt_keys, u64 *bkt_cursor, Counters *ctr,
+                               u64 *overflow_keys, u64 overflow_cap, int grid, cudaStream_t st)
+{
+    cudaFuncSetAttribute(partition_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    partition_kernel<W><<<grid, plan.threads, plan.smem, st>>>(stream, nflag, rflag, word_begin, word_end, k,
+        plan.n_buckets, plan.bin_cap, bkt_keys, plan.seg_cap, bkt_cursor, ctr, overflow_keys, overflow_cap);
+}
+
+void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
+                      int words, const PartitionPlan &plan, u64 *bkt_keys, u64 *bkt_cursor, Counters *ctr,
+                      u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st)
+{
+    if (word_end <= word_begin) return;
+    const u64 tiles = (word_end - word_begin + plan.threads - 1) / plan.threads;
+    const int grid = (int)std::min<u64>(tiles, (u64)sm_count * 2);
+    PBK_DISPATCH_W(words,
+        (partition_launch_w<W>(stream, nflag, rflag, word_begin, word_end, k, plan, bkt_keys, bkt_cursor, ctr,
+                               overflow_keys, overflow_cap, grid, st)));
+}
+
+static void region_of(const TableView &t, u32 b, u32 n_buckets, const char **lo, const char **hi)
+{
+    if (!t.slots || b >= n_buckets) { *lo = *hi = nullptr; return; }
+    const unsigned __int128 cap = t.cap;
+    u64 s0 = (u64)((cap * b) / n_buckets), s1 = (u64)((cap * (b + 1)) / n_buckets) + 64;
+    if (s1 > t.cap) s1 = t.cap;
+    *lo = (const char *)t.slots + s0 * t.slot_bytes();
+    *hi = (const char *)t.slots + s1 * t.slot_bytes();
+}
+
+void launch_bucket_insert(const u64 *keys, u64 n, u32 b, u32 n_buckets, TableView table, TableView remote,
+                          ShardInfo shard, Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count,
+                          cudaStream_t st)
+{
+    const char *lo, *hi, *lo2 = nullptr, *hi2 = nullptr;
+    region_of(table, b + 1, n_buckets, &lo, &hi);
+    if (shard.n_shards > 1) region_of(remote, b + 1, n_buckets, &lo2, &hi2);
+    const int grid = grid_for(std::max<u64>(n, 1), 256, sm_count, 8);
+    PBK_DISPATCH_W(table.words,
+        (bucket_insert_kernel<W><<<grid, 256, 0, st>>>(keys, n, (Slot<W> *)table.slots, table.cap,
+            (Slot<W> *)remote.slots, remote.cap, shard.n_shards, shard.rank, lo, hi, lo2, hi2, ctr, overflow_keys,
+            overflow_cap)));
 }
 
 void launch_table_init(TableView t, cudaStream_t st)

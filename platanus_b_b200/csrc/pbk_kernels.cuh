@@ -41,6 +41,25 @@ void launch_insert_records(const u64 *records, u64 n, bool weighted, TableView t
                            ShardInfo shard, Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count,
                            cudaStream_t st);
 
+// ---- partitioned counting (large batches) -------------------------------------------------------
+struct PartitionPlan {
+    u32    n_buckets;   // P hash-range buckets == P contiguous table regions
+    u32    bin_cap;     // entries per shared-memory bin
+    int    threads;     // CTA size of the partition kernel (one stream word per thread and tile)
+    size_t smem;        // dynamic shared memory of the partition kernel
+    u64    seg_cap;     // entries per bucket segment in the bucket store
+};
+// shared-memory budget -> bucket count / bin size / CTA size for keys of `words` words
+PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words);
+// Pass A over stream words [word_begin, word_end): keys go to bkt_keys (P segments of seg_cap entries)
+void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
+                      int words, const PartitionPlan &plan, u64 *bkt_keys, u64 *bkt_cursor, Counters *ctr,
+                      u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st);
+// Pass B for bucket `b` holding n keys; prefetches the table region(s) of bucket b + 1 into L2
+void launch_bucket_insert(const u64 *keys, u64 n, u32 b, u32 n_buckets, TableView table, TableView remote,
+                          ShardInfo shard, Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count,
+                          cudaStream_t st);
+
 // ---- table ------------------------------------------------------------------------------------
 void launch_table_init(TableView t, cudaStream_t st);
 // move every entry of `from` into `to` (capacity change)

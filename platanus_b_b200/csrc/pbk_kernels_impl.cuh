@@ -265,6 +265,172 @@ insert_records_kernel(const u64 *__restrict__ rec, u64 n, int weighted, Slot<W> 
 }
 
 // =================================================================================================
+// partitioned counting: Pass A scatters canonical k-mers into P hash-range buckets, Pass B inserts one
+// bucket at a time.  home slot = mulhi(hash, capacity) and bucket = mulhi(hash, P) are both monotone in
+// the hash, so bucket b only touches the contiguous table region [b, b+1) * capacity / P, which is
+// small enough to stay in the 126 MB L2 while the bucket is processed: DRAM sees two sequential
+// streams (keys in, table region in/out) instead of one random sector per k-mer.
+// =================================================================================================
+
+#ifndef PBK_CPU_EMUL
+#define PBK_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#else
+#define PBK_DYN_SMEM(type, name) static type name[32768]
+#endif
+
+
+template <int W>
+__device__ __forceinline__ void bucket_append_direct(const u64 *key, u32 b, u64 *bkt_keys, u64 seg_cap,
+                                                     u64 *bkt_cursor, u64 *ovf, u64 ovf_cap, Counters *ctr)
+{
+    const u64 at = atomicAdd(&bkt_cursor[b], 1ull);
+    if (at < seg_cap) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) bkt_keys[((u64)b * seg_cap + at) * W + j] = key[j];
+    } else {
+        spill_key<W>(key, ctr, ovf, ovf_cap);       // bucket segment full: goes through the overflow list
+    }
+}
+
+// Pass A.  One thread owns one stream word (32 window ends), exactly like count_kernel, but instead of
+// touching the table it drops the canonical key into its bucket's shared-memory bin; full tiles are
+// then flushed warp-per-bucket with coalesced stores.
+template <int W>
+__global__ void __launch_bounds__(512)
+partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, const u32 *__restrict__ rflag,
+                 u64 word_begin, u64 word_end, int k, u32 n_buckets, u32 bin_cap, u64 *bkt_keys, u64 seg_cap,
+                 u64 *bkt_cursor, Counters *ctr, u64 *ovf, u64 ovf_cap)
+{
+    PBK_DYN_SMEM(u64, bins);                          // n_buckets * bin_cap * W words
+    __shared__ u32 scount[PART_MAX_BUCKETS];
+    const int top_shift = 2 * ((k - 1) & 31);
+    const u64 top_mask = (k & 31) ? ((1ull << (2 * (k & 31))) - 1ull) : ~0ull;
+    const int s = 2 * (32 * W - k);
+    const int nb = (k + 30) >> 5;
+    // (wsize is 32 on the GPU; tests/cpu_emul runs the kernel as a single one-lane "warp")
+    const int wsize = blockDim.x < 32 ? (int)blockDim.x : 32;
+    const int lane = threadIdx.x % wsize, warp = threadIdx.x / wsize, n_warps = blockDim.x / wsize;
+    u64 inst = 0;
+
+    for (u64 tile = word_begin + (u64)blockIdx.x * blockDim.x; tile < word_end; tile += (u64)gridDim.x * blockDim.x) {
+        for (u32 b = threadIdx.x; b < n_buckets; b += blockDim.x) scount[b] = 0;
+        __syncthreads();
+        const u64 wi = tile + threadIdx.x;
+        if (wi < word_end) {
+            const u64 cur = stream[wi];
+            const u32 nf = nflag[wi], rf = rflag[wi];
+            int run = k;
+            for (int j = 1; j <= nb; ++j) {
+                const u32 a = nflag[wi - j], b = rflag[wi - j];
+                if (a | b) {
+                    const int pn = a ? 32 - __clz(a) : 0;
+                    const int pr = b ? 31 - __clz(b) : 0;
+                    run = 32 * j - max(pn, pr);
+                    break;
+                }
+            }
+            u64 fwd[W], rev[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) fwd[j] = stream[wi - 1 - j];
+            {
+                u64 y[W + 1];
+#pragma unroll
+                for (int j = 0; j < W; ++j) y[j] = pair_reverse64(~fwd[W - 1 - j]);
+                y[W] = 0;
+#pragma unroll
+                for (int j = 0; j < W; ++j) rev[j] = s ? ((y[j] >> s) | (y[j + 1] << (64 - s))) : y[j];
+            }
+#pragma unroll 2
+            for (int i = 0; i < 32; ++i) {
+                const u32 b = (u32)(cur >> (62 - 2 * i)) & 3u;
+                if ((rf >> i) & 1u) run = 0;
+                run = ((nf >> i) & 1u) ? 0 : run + 1;
+#pragma unroll
+                for (int j = W - 1; j > 0; --j) fwd[j] = (fwd[j] << 2) | (fwd[j - 1] >> 62);
+                fwd[0] = (fwd[0] << 2) | b;
+                fwd[W - 1] &= top_mask;
+#pragma unroll
+                for (int j = 0; j < W - 1; ++j) rev[j] = (rev[j] >> 2) | (rev[j + 1] << 62);
+                rev[W - 1] = (rev[W - 1] >> 2) | ((u64)(3u - b) << top_shift);
+                if (run >= k) {
+                    const bool use_rev = key_less<W>(rev, fwd);
+                    u64 key[W];
+#pragma unroll
+                    for (int j = 0; j < W; ++j) key[j] = use_rev ? rev[j] : fwd[j];
+                    const u32 bkt = (u32)__umul64hi(hash_key<W>(key), (u64)n_buckets);
+                    ++inst;
+                    const u32 pos = atomicAdd(&scount[bkt], 1u);
+                    if (pos < bin_cap) {
+#pragma unroll
+                        for (int j = 0; j < W; ++j) bins[((u64)bkt * bin_cap + pos) * W + j] = key[j];
+                    } else {
+                        bucket_append_direct<W>(key, bkt, bkt_keys, seg_cap, bkt_cursor, ovf, ovf_cap, ctr);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (u32 b = warp; b < n_buckets; b += n_warps) {
+            const u32 n = min(scount[b], bin_cap);
+            if (n == 0) continue;
+            u64 g = 0;
+            if (lane == 0) g = atomicAdd(&bkt_cursor[b], (u64)n);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            for (u32 i = lane; i < n * W; i += wsize) {
+                const u64 e = g + i / W;                 // entry index inside the bucket segment
+                if (e < seg_cap) bkt_keys[((u64)b * seg_cap) * W + (g * W + i)] = bins[(u64)b * bin_cap * W + i];
+                else if (i % W == 0) {
+                    u64 key[W];
+#pragma unroll
+                    for (int j = 0; j < W; ++j) key[j] = bins[(u64)b * bin_cap * W + i + j];
+                    spill_key<W>(key, ctr, ovf, ovf_cap);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    inst = warp_sum_u64(inst);
+    if (lane == 0 && inst) atomicAdd(&ctr->instances, inst);
+}
+
+// Pass B for one bucket: pull the NEXT bucket's table region into L2 with line prefetches (a sequential
+// HBM stream), then insert this bucket's keys; their probes hit the region prefetched one launch ago.
+template <int W>
+__global__ void __launch_bounds__(256)
+bucket_insert_kernel(const u64 *__restrict__ keys, u64 n, Slot<W> *table, u64 cap, Slot<W> *remote, u64 rcap,
+                     u32 n_shards, u32 rank, const char *pf_lo, const char *pf_hi, const char *pf2_lo,
+                     const char *pf2_hi, Counters *ctr, u64 *ovf, u64 ovf_cap)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x, gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+#ifndef PBK_CPU_EMUL
+    for (const char *p = pf_lo + gtid * 128; p < pf_hi; p += stride * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+    for (const char *p = pf2_lo + gtid * 128; p < pf2_hi; p += stride * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#endif
+    u32 newk = 0, newr = 0;
+    for (u64 i = gtid; i < n; i += stride) {
+        u64 key[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) key[j] = keys[i * W + j];
+        const u64 h = hash_key<W>(key);
+        int r;
+        if (n_shards > 1 && shard_of_hash(h, n_shards) != rank) {
+            r = table_insert<W>(remote, rcap, key, h, 1u);
+            newr += (r > 0);
+        } else {
+            r = table_insert<W>(table, cap, key, h, 1u);
+            newk += (r > 0);
+        }
+        if (r < 0) spill_key<W>(key, ctr, ovf, ovf_cap);
+    }
+    newk = warp_sum_u32(newk);
+    newr = warp_sum_u32(newr);
+    if ((threadIdx.x & 31) == 0) {
+        if (newk) atomicAdd(&ctr->new_keys, (u64)newk);
+        if (newr) atomicAdd(&ctr->new_keys_remote, (u64)newr);
+    }
+}
+
+// =================================================================================================
 // table maintenance
 // =================================================================================================
 

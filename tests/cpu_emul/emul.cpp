@@ -8,6 +8,9 @@
 
 using namespace pbk;
 
+static int g_partition = 0;
+extern "C" void emul_set_partition(int on) { g_partition = on; }
+
 template <int W>
 static int run(const uint8_t *bases, const u64 *off, u64 n_reads, int k, int encoding, const int32_t *n_pos,
                const u64 *n_pos_off, u64 table_slots, u32 n_shards, u32 rank, u32 min_count,
@@ -21,7 +24,8 @@ static int run(const uint8_t *bases, const u64 *off, u64 n_reads, int k, int enc
     std::vector<Slot<W>> table(table_slots), remote(n_shards > 1 ? table_slots : 1);
     for (auto *t : {&table, &remote})
         for (auto &s : *t) { for (int j = 0; j < W; ++j) s.key[j] = (W == 1) ? KEY_EMPTY : 0; s.cs = 0; s.pad = 0; }
-    std::vector<u64> ovf((W + 1) * 1024);
+    const u64 OVF = 1 << 16;
+    std::vector<u64> ovf((W + 1) * OVF);
 
     read_marks_kernel(off, n_reads, len_hist, rflag.data() + STREAM_PAD_WORDS, &ctr);
     // two chunks with an odd split to exercise word0 offsets (chunk boundaries are multiples of 32 bases)
@@ -31,23 +35,38 @@ static int run(const uint8_t *bases, const u64 *off, u64 n_reads, int k, int enc
     pack_kernel<false>(bases + w_split * 32, n_bases - w_split * 32, words - w_split, encoding,
                        stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, w_split, &ctr);
     if (encoding == 1) npos_scatter_kernel(off, n_pos, n_pos_off, n_reads, nflag.data() + STREAM_PAD_WORDS);
-    count_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
-                    0, w_split, k, table.data(), table_slots, remote.data(), table_slots, n_shards, rank, &ctr,
-                    ovf.data(), 1024);
-    count_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
-                    w_split, words, k, table.data(), table_slots, remote.data(), table_slots, n_shards, rank, &ctr,
-                    ovf.data(), 1024);
+    if (!g_partition) {
+        count_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
+                        0, w_split, k, table.data(), table_slots, remote.data(), table_slots, n_shards, rank, &ctr,
+                        ovf.data(), OVF);
+        count_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
+                        w_split, words, k, table.data(), table_slots, remote.data(), table_slots, n_shards, rank, &ctr,
+                        ovf.data(), OVF);
+    } else {
+        // Pass A into P buckets with deliberately tiny bins/segments so the direct-append and spill paths run too
+        const u32 P = 7, bin_cap = 3;
+        const u64 seg_cap = std::max<u64>(4, n_bases / P * 3 / 4);
+        std::vector<u64> bkt((u64)P * seg_cap * W, 0), cursor(P, 0);
+        partition_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
+                            0, w_split, k, P, bin_cap, bkt.data(), seg_cap, cursor.data(), &ctr, ovf.data(), OVF);
+        partition_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
+                            w_split, words, k, P, bin_cap, bkt.data(), seg_cap, cursor.data(), &ctr, ovf.data(), OVF);
+        for (u32 b = 0; b < P; ++b)
+            bucket_insert_kernel<W>(bkt.data() + (u64)b * seg_cap * W, std::min<u64>(cursor[b], seg_cap), table.data(), table_slots,
+                                    remote.data(), table_slots, n_shards, rank, nullptr, nullptr, nullptr, nullptr, &ctr,
+                                    ovf.data(), OVF);
+    }
     if (ctr.overflow_n) {          // grow + rehash + re-insert, as pbk_api.cu does
         std::vector<Slot<W>> bigger(table_slots * 4);
         for (auto &s : bigger) { for (int j = 0; j < W; ++j) s.key[j] = (W == 1) ? KEY_EMPTY : 0; s.cs = 0; s.pad = 0; }
         rehash_kernel<W>(table.data(), table_slots, bigger.data(), table_slots * 4, &ctr);
         table.swap(bigger);
         table_slots *= 4;
-        std::vector<u64> copy(ovf.begin(), ovf.begin() + std::min<u64>(ctr.overflow_n, 1024) * (W + 1));
-        const u64 n = std::min<u64>(ctr.overflow_n, 1024);
+        std::vector<u64> copy(ovf.begin(), ovf.begin() + std::min<u64>(ctr.overflow_n, OVF) * (W + 1));
+        const u64 n = std::min<u64>(ctr.overflow_n, OVF);
         ctr.overflow_n = 0;
-        insert_records_kernel<W>(copy.data(), n, 1, table.data(), table_slots, remote.data(), remote.size(), 1, 0, &ctr,
-                                 ovf.data(), 1024);
+        insert_records_kernel<W>(copy.data(), n, 1, table.data(), table_slots, remote.data(), remote.size(), n_shards, rank, &ctr,
+                                 ovf.data(), OVF);
     }
     histogram_kernel<W>(table.data(), table_slots, occ_hist);
     *n_out = 0;

@@ -30,7 +30,8 @@ def lib():
 
 
 def emul_count(bases: np.ndarray, offsets: np.ndarray, k: int, encoding: int = 0, n_pos=None, n_pos_off=None,
-               table_slots: int | None = None, n_shards: int = 1, rank: int = 0, min_count: int = 1):
+               table_slots: int | None = None, n_shards: int = 1, rank: int = 0, min_count: int = 1,
+               partition: bool = False):
     W = (k + 31) // 32
     bases = np.ascontiguousarray(bases, dtype=np.uint8)
     pad = np.zeros(64, np.uint8)
@@ -53,6 +54,7 @@ def emul_count(bases: np.ndarray, offsets: np.ndarray, k: int, encoding: int = 0
     n_pos = np.ascontiguousarray(n_pos, dtype=np.int32)
     n_pos_off = np.ascontiguousarray(n_pos_off, dtype=np.uint64)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib().emul_set_partition(int(partition))
     rc = lib().emul_count(p(bases_p), p(offsets), C.c_uint64(n_reads), k, encoding, p(n_pos), p(n_pos_off),
                           C.c_uint64(slots), n_shards, rank, min_count, p(keys), p(counts), C.c_uint64(windows),
                           C.byref(n_out), p(occ), p(lh), C.byref(n_inst), C.byref(err), p(remote), C.byref(n_remote))

@@ -63,6 +63,39 @@ def test_golden_cases_bit_exact(oracle, case, tmp_path):
         assert np.array_equal(kc.len_hist, want.len_hist)
 
 
+@pytest.mark.parametrize("name", ["kat_k4", "smallfq_k32", "smallfq_k65", "smallfa_k129", "sat_k32", "multi_k32_n2"])
+def test_forced_partition_path_on_golden_cases(oracle, name, tmp_path):
+    """The hash-range bucket pass (normally used for batches >= 4M windows) forced on small inputs."""
+    O = oracle
+    case = G.CASE_BY_NAME[name]
+    rd = _reads(O, case, tmp_path)
+    bases, offs = rd.arrays()
+    want = O.count(rd, case.k)
+    with KmerCounter(case.k, partition="force") as kc:
+        half = (len(offs) - 1) // 2
+        kc.push_reads(bases[:int(offs[half])], offs[:half + 1])               # two pushes: two Pass A/Pass B rounds
+        kc.push_reads(bases[int(offs[half]):], offs[half:] - offs[half])
+        kc.finalize()
+        keys, counts = kc.export(1, sorted=True)
+        assert kc.n_instances == want.n_instances
+        assert np.array_equal(keys, want.keys) and np.array_equal(counts, want.counts)
+        assert np.array_equal(kc.occ_hist, want.occ_hist) and np.array_equal(kc.len_hist, want.len_hist)
+
+
+def test_direct_and_partitioned_paths_agree(oracle):
+    O = oracle
+    rs = synth.make_reads(synth.config("C1", scale=1 / 40))
+    b, o = rs.flat()
+    out = []
+    for mode in (True, False):
+        with KmerCounter(32, partition=mode) as kc:
+            kc.push_reads(b, o)
+            kc.finalize()
+            out.append(kc.export(1, sorted=True) + (kc.occ_hist.copy(), kc.n_instances))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][2], out[1][2]) and out[0][3] == out[1][3]
+
+
 def test_empty_distribution_raises_kmer_dist_error(oracle, tmp_path):
     """reference: KmerDistError from calcDistributionAverage (counter.h:225-237), exit code 6"""
     O = oracle

@@ -20,14 +20,15 @@ NAMES = ["kat_k4", "smallfq_k21", "smallfq_k31", "smallfq_k32", "smallfq_k33", "
          "smallfa_k161", "smallfa_k200", "tailhdr_k8", "multi_k32_n2"]
 
 
+@pytest.mark.parametrize("partition", [False, True], ids=["direct", "partitioned"])
 @pytest.mark.parametrize("name", NAMES)
-def test_kernels_match_oracle(oracle, name, tmp_path):
+def test_kernels_match_oracle(oracle, name, partition, tmp_path):
     O = oracle
     case = G.CASE_BY_NAME[name]
     rd = _reads(O, case, tmp_path)
     want = O.count(rd, case.k)
     bases, offs = rd.arrays()
-    got = emul_count(bases, offs, case.k)
+    got = emul_count(bases, offs, case.k, partition=partition)
     assert got["err"] == 0
     assert got["n_instances"] == want.n_instances
     assert np.array_equal(got["keys"], want.keys)
