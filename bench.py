@@ -328,7 +328,9 @@ def main_ours(args):
             "roofline": roofline,
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
             "kernel_ms_per_step": {"pack": d_res["ms_pack"] / args.steps, "count": d_res["ms_count"] / args.steps,
-                                   "other": d_res["ms_other"] / args.steps},
+                                   "other": d_res["ms_other"] / args.steps,
+                                   "count_partition_pass": d_res["ms_partition"] / args.steps,
+                                   "count_insert_pass": d_res["ms_insert"] / args.steps},
             "wall_ms_per_step": wall_res / args.steps,
             "table": {"slots": int(kc.stats()["table_slots"]), "bytes": int(kc.stats()["table_bytes"]),
                       "distinct_local": int(kc.n_distinct), "grows_in_timed_region": int(d_res["n_grow"])},

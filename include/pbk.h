@@ -89,6 +89,10 @@ typedef struct pbk_stats {
     double   ms_other;
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
+    uint64_t launches_partition; /* Pass A (hash-range bucket scatter) launches, also counted in launches_count */
+    uint64_t launches_insert;    /* Pass B (bucket -> table) launches, also counted in launches_count           */
+    double   ms_partition;       /* parts of ms_count                                                          */
+    double   ms_insert;
 } pbk_stats;
 
 const char *pbk_strerror(int status);

@@ -51,7 +51,9 @@ class PbkStats(C.Structure):
                 ("n_distinct", C.c_uint64), ("table_slots", C.c_uint64), ("table_bytes", C.c_uint64),
                 ("n_grow", C.c_uint64), ("launches_pack", C.c_uint64), ("launches_count", C.c_uint64),
                 ("launches_other", C.c_uint64), ("ms_pack", C.c_double), ("ms_count", C.c_double),
-                ("ms_other", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("ms_other", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("launches_partition", C.c_uint64), ("launches_insert", C.c_uint64),
+                ("ms_partition", C.c_double), ("ms_insert", C.c_double)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -22,12 +22,12 @@ namespace {
 
 constexpr u64 CHUNK_BASES = 1ull << 25;          // 32 Mi bases per pipeline stage (multiple of 32)
 constexpr u64 MIN_SLOTS = 1ull << 16;
-constexpr double MAX_LOAD = 0.5;
+constexpr double MAX_LOAD = 0.5;                  // k > 32 (16+ byte slots, any capacity)
+constexpr double MAX_LOAD_COMPACT = 0.6;          // k <= 32: capacity is a power of two, real load ends up 0.3-0.6
 constexpr u64 U32_HEADROOM = (1ull << 32) - 65536 - 2;
 constexpr u64 PART_MIN_WINDOWS = 1ull << 22;    // smaller batches go straight to the table
-constexpr u32 PART_CHECK_EVERY = 16;             // buckets between counter read-backs in Pass B
 
-enum LaunchClass { LC_PACK = 0, LC_COUNT = 1, LC_OTHER = 2 };
+enum LaunchClass { LC_PACK = 0, LC_COUNT = 1, LC_OTHER = 2, LC_PART = 3, LC_INSERT = 4, LC_N = 5 };
 
 struct TimedSpan { cudaEvent_t a, b; int cls; };
 
@@ -56,6 +56,7 @@ struct pbk_ctx {
     PartitionPlan plan{};
     u64 *d_bkt_keys = nullptr; size_t bkt_bytes = 0;
     u64 *d_bkt_cursor = nullptr, *h_bkt_cursor = nullptr;
+    u64 *d_passb = nullptr, *h_passb = nullptr;     // [ticket][tile_start: P+1][count: P]
     bool partition_enabled = true, partition_forced = false;
     u64 *d_len_hist = nullptr, *d_occ_hist = nullptr, *d_shard_counts = nullptr;
     std::vector<u64> h_occ_hist, h_shard_counts;
@@ -63,8 +64,8 @@ struct pbk_ctx {
     bool finalized = false;
     u64 n_reads = 0, n_bases = 0, inst_since_clamp = 0, n_grow = 0;
     double new_ratio = 0.20;         // new keys per window, adapted from what the data shows
-    u64 launches[3] = {0, 0, 0};
-    double ms[3] = {0, 0, 0};
+    u64 launches[LC_N] = {0, 0, 0, 0, 0};
+    double ms[LC_N] = {0, 0, 0, 0, 0};
     std::vector<TimedSpan> spans;
     cudaEvent_t timer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     u64 h2d_bytes = 0, d2h_bytes = 0;
@@ -72,6 +73,11 @@ struct pbk_ctx {
 };
 
 namespace {
+
+const bool g_debug = getenv("PBK_DEBUG") != nullptr;
+#define DBG(...) do { if (g_debug) { fprintf(stderr, "[pbk] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
+
+double max_load(const pbk_ctx *c) { return c->W == 1 ? MAX_LOAD_COMPACT : MAX_LOAD; }
 
 int fail(pbk_ctx *c, int code, const char *fmt, ...)
 {
@@ -133,7 +139,16 @@ void resolve_spans(pbk_ctx *c)
     c->spans.clear();
 }
 
-u64 round_slots(u64 want) { return std::max<u64>(MIN_SLOTS, (want + 1023) & ~1023ull); }
+// k <= 32: power of two >= 2^27 (compact slots need the count-field headroom); k > 32: any multiple of 1024
+u64 round_slots(const pbk_ctx *c, u64 want)
+{
+    if (c->W == 1) {
+        u64 s = 1ull << CT_MIN_QBITS;
+        while (s < want) s <<= 1;
+        return s;
+    }
+    return std::max<u64>(MIN_SLOTS, (want + 1023) & ~1023ull);
+}
 
 int table_alloc(pbk_ctx *c, TableView *t, u64 slots)
 {
@@ -162,7 +177,8 @@ int read_counters(pbk_ctx *c)
 
 int grow_table(pbk_ctx *c, TableView *t, u64 occupied, u64 want_slots)
 {
-    const u64 ns = round_slots(std::max<u64>(t->cap + t->cap / 2, want_slots));
+    const u64 ns = round_slots(c, std::max<u64>(t->cap + t->cap / 2, want_slots));
+    DBG("grow table %llu -> %llu slots (occupied %llu)", t->cap, ns, occupied);
     TableView nt{nullptr, ns, c->W};
     TRY(table_alloc(c, &nt, ns));
     { Span sp(c, LC_OTHER); launch_table_rehash(*t, nt, c->d_ctr, c->s_compute); }
@@ -183,10 +199,10 @@ int ensure_room(pbk_ctx *c, u64 expect_new)
         local_new = expect_new / c->shard.n_shards + 1;
         remote_new = expect_new - local_new + 1;
     }
-    if ((double)(c->occupied + local_new) > MAX_LOAD * (double)c->table.capacity())
-        TRY(grow_table(c, &c->table, c->occupied, (u64)((c->occupied + local_new) / MAX_LOAD) + 1));
-    if (c->shard.n_shards > 1 && (double)(c->occupied_remote + remote_new) > MAX_LOAD * (double)c->remote.capacity())
-        TRY(grow_table(c, &c->remote, c->occupied_remote, (u64)((c->occupied_remote + remote_new) / MAX_LOAD) + 1));
+    if ((double)(c->occupied + local_new) > max_load(c) * (double)c->table.capacity())
+        TRY(grow_table(c, &c->table, c->occupied, (u64)((c->occupied + local_new) / max_load(c)) + 1));
+    if (c->shard.n_shards > 1 && (double)(c->occupied_remote + remote_new) > max_load(c) * (double)c->remote.capacity())
+        TRY(grow_table(c, &c->remote, c->occupied_remote, (u64)((c->occupied_remote + remote_new) / max_load(c)) + 1));
     return PBK_OK;
 }
 
@@ -199,20 +215,26 @@ int ensure_overflow(pbk_ctx *c, u64 records)
     return PBK_OK;
 }
 
-// keys that found no slot within MAX_PROBE: grow, then insert them from a private copy
+// Spilled keys (no slot within the probe limit, or a full bucket segment in Pass A): insert them from
+// a private copy of the list.  The table only grows if it is really loaded, or if a plain retry
+// spilled again.
 int drain_overflow(pbk_ctx *c)
 {
-    while (c->h_ctr->overflow_n > 0) {
+    for (int attempt = 0; c->h_ctr->overflow_n > 0; ++attempt) {
         const u64 n = std::min<u64>(c->h_ctr->overflow_n, c->ovf_cap);
+        DBG("drain overflow: %llu records (cap %llu), attempt %d", c->h_ctr->overflow_n, c->ovf_cap, attempt);
         const size_t bytes = n * (c->W + 1) * 8;
         u64 *tmp = nullptr;
         TRY(dev_alloc(c, (void **)&tmp, bytes));
         CK(cudaMemcpyAsync(tmp, c->d_ovf, bytes, cudaMemcpyDeviceToDevice, c->s_compute));
         CK(cudaMemsetAsync(&c->d_ctr->overflow_n, 0, sizeof(u64), c->s_compute));
         c->last.overflow_n = 0;
-        int rc = grow_table(c, &c->table, c->occupied, (u64)((c->occupied + n) / MAX_LOAD) * 2 + 1);
-        if (rc == PBK_OK && c->shard.n_shards > 1)
-            rc = grow_table(c, &c->remote, c->occupied_remote, (u64)((c->occupied_remote + n) / MAX_LOAD) * 2 + 1);
+        int rc = PBK_OK;
+        const bool loaded = (double)(c->occupied + n) > max_load(c) * (double)c->table.capacity();
+        const bool rloaded = c->shard.n_shards > 1 && (double)(c->occupied_remote + n) > max_load(c) * (double)c->remote.capacity();
+        if (loaded || attempt > 0) rc = grow_table(c, &c->table, c->occupied, (u64)((c->occupied + n) / max_load(c)) * 2 + 1);
+        if (rc == PBK_OK && (rloaded || (attempt > 0 && c->shard.n_shards > 1)))
+            rc = grow_table(c, &c->remote, c->occupied_remote, (u64)((c->occupied_remote + n) / max_load(c)) * 2 + 1);
         if (rc == PBK_OK) {
             Span sp(c, LC_COUNT);
             launch_insert_records(tmp, n, true, c->table, c->remote, c->shard, c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
@@ -238,12 +260,12 @@ int maybe_clamp(pbk_ctx *c, u64 upcoming)
 int ensure_tables(pbk_ctx *c, u64 first_batch_windows)
 {
     if (c->table.slots) return PBK_OK;
-    u64 want = c->table_hint ? c->table_hint : (u64)(first_batch_windows * c->new_ratio / MAX_LOAD) + 1;
+    u64 want = c->table_hint ? c->table_hint : (u64)(first_batch_windows * c->new_ratio / max_load(c)) + 1;
     if (c->shard.n_shards > 1) {
-        TRY(table_alloc(c, &c->remote, round_slots(want)));     // remote-staging table holds (n-1)/n of the keys
+        TRY(table_alloc(c, &c->remote, round_slots(c, want)));     // remote-staging table holds (n-1)/n of the keys
         want = want / c->shard.n_shards + 1;
     }
-    TRY(table_alloc(c, &c->table, round_slots(want)));
+    TRY(table_alloc(c, &c->table, round_slots(c, want)));
     return PBK_OK;
 }
 
@@ -301,9 +323,10 @@ int count_range(pbk_ctx *c, u64 w0, u64 w1)
 
 int prepare_partition(pbk_ctx *c, u64 windows_ub)
 {
-    const u64 est_slots = std::max<u64>(c->table.slots ? c->table.cap : 0,
-                                        (u64)((c->occupied + windows_ub * c->new_ratio) / MAX_LOAD));
-    c->plan = plan_partition(est_slots * (8 * (u64)c->W + 8), windows_ub, c->W);
+    const u64 est_slots = round_slots(c, std::max<u64>(c->table.slots ? c->table.cap : 0,
+                                                       (u64)((c->occupied + windows_ub * c->new_ratio) / max_load(c))));
+    TableView tv{nullptr, est_slots, c->W};
+    c->plan = plan_partition(tv.bytes(), windows_ub, c->W);
     const size_t need = (size_t)c->plan.n_buckets * c->plan.seg_cap * c->W * 8;
     if (need > c->bkt_bytes) {
         CK(cudaStreamSynchronize(c->s_compute));
@@ -315,10 +338,36 @@ int prepare_partition(pbk_ctx *c, u64 windows_ub)
     if (!c->d_bkt_cursor) {
         TRY(dev_alloc(c, (void **)&c->d_bkt_cursor, PART_MAX_BUCKETS * 8));
         if (cudaMallocHost((void **)&c->h_bkt_cursor, PART_MAX_BUCKETS * 8) != cudaSuccess) return fail(c, PBK_E_NOMEM, "pinned host memory");
+        TRY(dev_alloc(c, (void **)&c->d_passb, (2 * PART_MAX_BUCKETS + 2) * 8));
+        if (cudaMallocHost((void **)&c->h_passb, (2 * PART_MAX_BUCKETS + 2) * 8) != cudaSuccess) return fail(c, PBK_E_NOMEM, "pinned host memory");
     }
     CK(cudaMemsetAsync(c->d_bkt_cursor, 0, PART_MAX_BUCKETS * 8, c->s_compute));
     // a spilled key (bucket segment or bin full) is rare; the list is also used by Pass B
-    TRY(ensure_overflow(c, std::max<u64>(1ull << 20, PART_CHECK_EVERY * (c->plan.seg_cap + 1))));
+    TRY(ensure_overflow(c, 1ull << 22));
+    return PBK_OK;
+}
+
+// one persistent Pass B launch over buckets [b0, b1)
+int passb_launch(pbk_ctx *c, u32 b0, u32 b1)
+{
+    const u32 P = c->plan.n_buckets, nb = b1 - b0, tk = passb_tile_keys();
+    u64 *h = c->h_passb;
+    h[0] = 0;                                        // ticket
+    u64 tiles = 0;
+    for (u32 i = 0; i < nb; ++i) { h[1 + i] = tiles; tiles += (c->h_bkt_cursor[b0 + i] + tk - 1) / tk; }
+    h[1 + nb] = tiles;
+    DBG("pass B buckets [%u,%u) of %u: %llu tiles, table %llu slots, occupied %llu", b0, b1, P, tiles, c->table.cap, c->occupied);
+    for (u32 i = 0; i < P; ++i) h[2 + nb + i] = c->h_bkt_cursor[i];
+    CK(cudaMemcpyAsync(c->d_passb, h, (2 + nb + P) * 8, cudaMemcpyHostToDevice, c->s_compute));
+    c->h2d_bytes += (2 + nb + P) * 8;
+    if (tiles) {
+        Span sp(c, LC_INSERT);
+        launch_bucket_insert(c->d_bkt_keys, c->plan.seg_cap, c->d_passb + 2 + nb, c->d_passb + 1, b0, b1, P, c->d_passb,
+                             c->table, c->remote, c->shard, c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+    }
+    CK(cudaGetLastError());
+    TRY(read_counters(c));                          // also makes h_passb reusable
+    TRY(drain_overflow(c));
     return PBK_OK;
 }
 
@@ -332,30 +381,24 @@ int flush_buckets(pbk_ctx *c)
     c->d2h_bytes += P * 8;
     u64 total = 0;
     for (u32 b = 0; b < P; ++b) { c->h_bkt_cursor[b] = std::min<u64>(c->h_bkt_cursor[b], c->plan.seg_cap); total += c->h_bkt_cursor[b]; }
+    DBG("pass A done: %llu keys in %u buckets (seg_cap %llu, bin_cap %u, threads %d), instances %llu", total, P, c->plan.seg_cap, c->plan.bin_cap, c->plan.threads, c->last.instances);
     if (total == 0) return PBK_OK;
     TRY(maybe_clamp(c, total));
     const u64 occ_before = c->occupied + c->occupied_remote;
-    u64 done = 0;
-    for (u32 b = 0; b < P; ++b) {
-        const u64 n = c->h_bkt_cursor[b];
-        if (b == 0) TRY(ensure_room(c, (u64)(n * std::min(1.0, c->new_ratio * 1.25))));
-        {
-            Span sp(c, LC_COUNT);
-            launch_bucket_insert(c->d_bkt_keys + (size_t)b * c->plan.seg_cap * c->W, n, b, P, c->table, c->remote, c->shard,
-                                 c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
-        }
-        CK(cudaGetLastError());
-        done += n;
-        const bool pilot = (b == 0), check = pilot || ((b + 1) % PART_CHECK_EVERY == 0) || b + 1 == P;
-        if (!check) continue;
-        TRY(read_counters(c));
-        TRY(drain_overflow(c));
-        // buckets are statistically identical hash ranges: what the finished ones added predicts the rest
-        const u64 added = c->occupied + c->occupied_remote - occ_before;
-        const double per_key = done ? (double)added / (double)done : c->new_ratio;
-        if (b + 1 < P) TRY(ensure_room(c, (u64)((double)(total - done) * std::min(1.0, per_key * 1.05)) + 4096));
-        if (b + 1 == P && done > 4096) c->new_ratio = std::max(0.01, std::min(1.0, per_key));
+    // pilot: buckets are statistically identical hash ranges, so what the first 1/16 of them adds
+    // predicts the rest; size the table once, then run everything else in a single launch
+    const u32 pilot = std::max<u32>(1, P / 16);
+    u64 pilot_keys = 0;
+    for (u32 b = 0; b < pilot; ++b) pilot_keys += c->h_bkt_cursor[b];
+    // the pilot fills only its own hash ranges, so the table must already have the size the whole batch needs
+    TRY(ensure_room(c, (u64)(total * std::min(1.0, c->new_ratio))));
+    TRY(passb_launch(c, 0, pilot));
+    double per_key = pilot_keys ? (double)(c->occupied + c->occupied_remote - occ_before) / (double)pilot_keys : c->new_ratio;
+    if (pilot < P) {
+        TRY(ensure_room(c, (u64)((double)(total - pilot_keys) * std::min(1.0, per_key * 1.05)) + 4096));
+        TRY(passb_launch(c, pilot, P));
     }
+    if (total > 4096) c->new_ratio = std::max(0.01, std::min(1.0, (double)(c->occupied + c->occupied_remote - occ_before) / (double)total));
     CK(cudaMemsetAsync(c->d_bkt_cursor, 0, PART_MAX_BUCKETS * 8, c->s_compute));
     return PBK_OK;
 }
@@ -392,7 +435,7 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
     // large batches: Pass A per chunk (no host sync), Pass B once at the end.  Small ones: straight to the table.
     auto count_words = [&](u64 w0, u64 w1) -> int {
         if (!partitioned) return count_range(c, w0, w1);
-        Span sp(c, LC_COUNT);
+        Span sp(c, LC_PART);
         launch_partition(stream, nflag, rflag, w0, w1, (int)c->k, c->W, c->plan, c->d_bkt_keys, c->d_bkt_cursor, c->d_ctr,
                          c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
         return PBK_OK;
@@ -476,6 +519,7 @@ void release_all(pbk_ctx *c)
         if (c->ev_stage_free[i]) cudaEventDestroy(c->ev_stage_free[i]);
     }
     cudaFree(c->d_bkt_keys); cudaFree(c->d_bkt_cursor); if (c->h_bkt_cursor) cudaFreeHost(c->h_bkt_cursor);
+    cudaFree(c->d_passb); if (c->h_passb) cudaFreeHost(c->h_passb);
     cudaFree(c->table.slots); cudaFree(c->remote.slots); cudaFree(c->d_ctr); cudaFree(c->d_ovf);
     cudaFree(c->d_len_hist); cudaFree(c->d_occ_hist); cudaFree(c->d_shard_counts);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
@@ -672,8 +716,12 @@ int pbk_get_stats(const pbk_ctx *cc, pbk_stats *out)
     out->n_reads = c->n_reads; out->n_bases = c->n_bases; out->n_instances = c->last.instances;
     out->n_distinct = c->occupied; out->table_slots = c->table.slots ? c->table.capacity() : 0;
     out->table_bytes = c->table.slots ? c->table.bytes() : 0; out->n_grow = c->n_grow;
-    out->launches_pack = c->launches[LC_PACK]; out->launches_count = c->launches[LC_COUNT]; out->launches_other = c->launches[LC_OTHER];
-    out->ms_pack = c->ms[LC_PACK]; out->ms_count = c->ms[LC_COUNT]; out->ms_other = c->ms[LC_OTHER];
+    out->launches_pack = c->launches[LC_PACK]; out->launches_other = c->launches[LC_OTHER];
+    out->launches_partition = c->launches[LC_PART]; out->launches_insert = c->launches[LC_INSERT];
+    out->launches_count = c->launches[LC_COUNT] + c->launches[LC_PART] + c->launches[LC_INSERT];
+    out->ms_pack = c->ms[LC_PACK]; out->ms_other = c->ms[LC_OTHER];
+    out->ms_partition = c->ms[LC_PART]; out->ms_insert = c->ms[LC_INSERT];
+    out->ms_count = c->ms[LC_COUNT] + c->ms[LC_PART] + c->ms[LC_INSERT];
     out->h2d_bytes = c->h2d_bytes; out->d2h_bytes = c->d2h_bytes;
     return PBK_OK;
 }
@@ -778,8 +826,8 @@ int pbk_shard_insert_device(pbk_ctx *c, const void *d_records, uint64_t n_record
     for (u64 at = 0; at < n_records; at += CHUNK_BASES) {
         const u64 n = std::min<u64>(CHUNK_BASES, n_records - at);
         TRY(maybe_clamp(c, (u64)c->shard.n_shards * COUNT_SAT));
-        if ((double)(c->occupied + n) > MAX_LOAD * (double)c->table.capacity())
-            TRY(grow_table(c, &c->table, c->occupied, (u64)((c->occupied + n) / MAX_LOAD) + 1));
+        if ((double)(c->occupied + n) > max_load(c) * (double)c->table.capacity())
+            TRY(grow_table(c, &c->table, c->occupied, (u64)((c->occupied + n) / max_load(c)) + 1));
         TRY(ensure_overflow(c, n));
         {
             Span sp(c, LC_COUNT);
@@ -815,7 +863,7 @@ uint32_t pbk_shard_of_key(const uint64_t *key_words, uint32_t k, uint32_t n_shar
 
 int pbk_microbench_atomics(int device, uint64_t table_bytes, uint64_t n_ops, int mode, double *ops_per_s)
 {
-    if (!ops_per_s || table_bytes < 4096 || n_ops == 0 || mode < 0 || mode > 2) return PBK_E_ARG;
+    if (!ops_per_s || table_bytes < 4096 || n_ops == 0 || mode < 0 || mode > 4) return PBK_E_ARG;
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return PBK_E_NO_DEVICE; }
     if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return PBK_E_NO_DEVICE;
@@ -823,7 +871,8 @@ int pbk_microbench_atomics(int device, uint64_t table_bytes, uint64_t n_ops, int
     cudaGetDevice(&dev); cudaGetDeviceProperties(&prop, dev);
     int log2slots = 0;
     while ((32ull << log2slots) <= table_bytes) ++log2slots;     // 16-byte slots, largest power of two that fits
-    TableView t{nullptr, 1ull << log2slots, 1};
+    TableView t{nullptr, 2ull << log2slots, 1};                 // bytes = 16 << log2slots
+    if (getenv("PBK_L2_FETCH32")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     if (cudaMalloc(&t.slots, t.bytes()) != cudaSuccess) { cudaGetLastError(); return PBK_E_NOMEM; }
     cudaStream_t st; cudaStreamCreate(&st);
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);

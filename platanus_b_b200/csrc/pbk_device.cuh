@@ -9,9 +9,13 @@
 //   * nflag/rflag : one bit per stream position (LSB-first in u32 words): "is N" and "first base
 //                   of a read".  They replace SEQ::positionUnknown (common.h:468-476) and the per-read
 //                   loop structure of countKmerPerThreadFirst (counter.h:405-432).
-//   * table       : open addressing, linear probing, home = mulhi(hash, capacity), slot = key words +
-//                   32-bit count/state.  Replaces the 1024 lock-striped DoubleHash sub-tables
-//                   (counter.h:280-314, doubleHash.h:202-218).
+//   * table       : open addressing with linear probing, replacing the 1024 lock-striped DoubleHash
+//                   sub-tables (counter.h:280-314, doubleHash.h:202-218).  Two slot formats:
+//                     k <= 32 : ONE 64-bit word per slot = [remainder | displacement+1 | count]; the
+//                               hash is a bijection of the key, the slot position supplies its top
+//                               bits, so the key is recoverable and insert-or-increment is a single
+//                               64-bit atomic add (see ct_insert_unit);
+//                     k  > 32 : key words + 32-bit count/state word (claim, publish, increment).
 #pragma once
 
 #include <cstdint>
@@ -24,19 +28,31 @@ namespace pbk {
 typedef unsigned long long u64;
 typedef uint32_t u32;
 
-constexpr u64 KEY_EMPTY = ~0ull;          // W == 1: never a canonical k-mer (T^32 > A^32 = its revcomp)
 constexpr u32 CS_LOCKED = 0xFFFFFFFFu;    // W >= 2: slot claimed, key words being written
 constexpr u32 COUNT_SAT = 65534u;         // counter.h:468
-constexpr int MAX_PROBE = 192;            // longer probe runs go to the overflow list
+constexpr int MAX_PROBE = 192;            // W >= 2: longer probe runs go to the overflow list
 constexpr int STREAM_PAD_WORDS = 16;      // zero words in front of stream / flag arrays
 constexpr int PART_MAX_BUCKETS = 512;     // hash-range buckets of the partitioned path
+
+// compact (k <= 32) slot format
+constexpr int CT_DISP_BITS = 7;           // displacement + 1 in 1..127, 0 = slot not (yet) owned
+constexpr int CT_MAX_DISP = 126;
+constexpr int CT_MIN_QBITS = 27;          // >= 2^27 slots (1 GiB): leaves a 20-bit count field
+#ifndef PBK_CPU_EMUL
+constexpr u64 CT_NOISE = 1ull << 19;      // > number of resident threads (148 SMs x 2048): bound on in-flight +1s
+#else
+constexpr u64 CT_NOISE = 16;              // sequential emulation: nothing is ever in flight, small tables suffice
+#endif
 
 template <int W>
 struct alignas(8) Slot {
     u64 key[W];
-    u32 cs;      // W == 1: count.  W >= 2: 0 = empty, CS_LOCKED = being written, else count
+    u32 cs;      // 0 = empty, CS_LOCKED = being written, else count
     u32 pad;
 };
+
+template <int W> struct SlotType { typedef Slot<W> type; };
+template <> struct SlotType<1> { typedef u64 type; };
 
 struct Counters {
     u64 instances;       // windows inserted (locally owned or staged)
@@ -53,6 +69,15 @@ __host__ __device__ __forceinline__ u64 fmix64(u64 x)
 {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
     x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+// fmix64 is a bijection on 64 bits (xor-shifts by >= 32 are involutions, the multipliers are odd)
+__host__ __device__ __forceinline__ u64 fmix64_inverse(u64 x)
+{
+    x ^= x >> 33; x *= 0x9cb4b2f8129337dbULL;
+    x ^= x >> 33; x *= 0x4f74430c22a54005ULL;
     x ^= x >> 33;
     return x;
 }
@@ -89,6 +114,10 @@ __device__ __forceinline__ void red_add_u32(u32 *p, u32 v)
 {
     asm volatile("red.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_add_u64(u64 *p, u64 v)
+{
+    asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void st_cg_u64(u64 *p, u64 v)
 {
     asm volatile("st.global.cg.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
@@ -97,11 +126,11 @@ __device__ __forceinline__ void st_release_u32(u32 *p, u32 v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
-
 #else   // tests/cpu_emul: same source run sequentially on the host, see tests/cpu_emul/cuda_shim.h
 inline u64 ld_cg_u64(const u64 *p) { return *p; }
 inline u32 ld_cg_u32(const u32 *p) { return *p; }
 inline void red_add_u32(u32 *p, u32 v) { *p += v; }
+inline void red_add_u64(u64 *p, u64 v) { *p += v; }
 inline void st_cg_u64(u64 *p, u64 v) { *p = v; }
 inline void st_release_u32(u32 *p, u32 v) { *p = v; }
 #endif
@@ -123,64 +152,206 @@ __device__ __forceinline__ bool key_less(const u64 *a, const u64 *b)
     return a[0] < b[0];
 }
 
-// Insert `key` with weight `add` (>= 1).  Returns 1 if a new slot was claimed, 0 if an existing key was
-// incremented, -1 if MAX_PROBE slots were tried without success (caller spills the key).
-// Replaces countKmerOrWriteTemporary (counter.h:459-476): lock + find_times_any + insert/++/spill.
-template <int W>
-__device__ __forceinline__ int table_insert(Slot<W> *table, u64 cap, const u64 *key, u64 h, u32 add)
+// -------------------------------------------------------------------------------------------------
+// compact table, k <= 32.  capacity = 2^q slots, h = fmix64(key):
+//     home = h >> (64 - q)            r = low (64 - q) bits of h
+//     slot word = [ r : 64-q bits | d+1 : 7 bits | count : q-7 bits ]      (0 = empty)
+// -------------------------------------------------------------------------------------------------
+struct CtGeom {
+    int rbits, cbits;
+    u64 capmask, cmask, dz;
+};
+__host__ __device__ __forceinline__ CtGeom ct_geom(u64 cap)
 {
-    u64 idx = __umul64hi(h, cap);          // capacity need not be a power of two
-    if constexpr (W == 1) {
-        const u64 k0 = key[0];
+    CtGeom g;
+    int q = 0;
+    while ((1ull << q) < cap) ++q;
+    g.rbits = 64 - q;
+    g.cbits = q - CT_DISP_BITS;
+    g.capmask = cap - 1;
+    g.cmask = (1ull << g.cbits) - 1;
+    g.dz = (1ull << g.cbits) - CT_NOISE;          // counts this large are saturated for sure; stop adding
+    return g;
+}
+
+// decode an owned slot (high bits != 0, no insert kernel running): key and raw count
+__host__ __device__ __forceinline__ bool ct_decode(u64 v, u64 index, const CtGeom &g, u64 *key, u64 *count)
+{
+    const u64 hi = v >> g.cbits;
+    if (hi == 0) return false;
+    const u64 d = (hi & ((1u << CT_DISP_BITS) - 1)) - 1, r = hi >> CT_DISP_BITS;
+    const u64 home = (index - d) & g.capmask;
+    *key = fmix64_inverse((home << g.rbits) | r);
+    *count = v & g.cmask;
+    return true;
+}
+
+// Insert-or-increment by ONE (the hot path, replaces countKmerOrWriteTemporary, counter.h:459-476).
+// Each probe is a single 64-bit atomic add of 1 whose return value tells whether the slot is ours:
+//   * old tag == our tag      -> done, the add already counted the k-mer;
+//   * old == 0                -> we are the one thread that saw the slot empty: publish our tag with a
+//                                second add (tag and count bits are disjoint, so concurrent +1s cannot
+//                                disturb it), our +1 stays as the first count;
+//   * old has no tag yet      -> the claimer is between its two adds: wait for the tag, then decide;
+//   * another key             -> take the +1 back (fire-and-forget reduction) and probe the next slot.
+// Counts are exact once all kernels have drained; they may exceed 65534 (clamped when read) but never
+// leave the count field: at `dz` further adds are taken back, and at most CT_NOISE +1s are in flight.
+// Returns 1 = new key, 0 = existing key, -1 = no slot within CT_MAX_DISP (caller spills the key).
+// continue an insert whose probe at displacement d returned `old`
+__device__ __forceinline__ int ct_resolve(u64 *tab, const CtGeom &g, u64 h, u32 d, u64 *s, u64 old)
+{
+    const u64 home = h >> g.rbits;
+    const u64 r_hi = ((h << (64 - g.rbits)) >> (64 - g.rbits)) << CT_DISP_BITS;   // remainder above the disp field
 #pragma unroll 1
-        for (int probe = 0; probe < MAX_PROBE; ++probe, idx = (idx + 1 == cap) ? 0 : idx + 1) {
-            Slot<1> *s = table + idx;
-            u64 cur = ld_cg_u64(&s->key[0]);
-            if (cur == k0) { red_add_u32(&s->cs, add); return 0; }
-            if (cur == KEY_EMPTY) {
-                u64 old = atomicCAS(&s->key[0], KEY_EMPTY, k0);
-                if (old == KEY_EMPTY) { red_add_u32(&s->cs, add); return 1; }
-                if (old == k0) { red_add_u32(&s->cs, add); return 0; }
-            }
+    for (;;) {
+        const u64 tag_hi = r_hi | (u64)(d + 1);
+        if (old == 0) {
+            red_add_u64(s, tag_hi << g.cbits);
+            return 1;
         }
-        return -1;
-    } else {
-        int probe = 0;
-#pragma unroll 1
-        while (probe < MAX_PROBE) {
-            Slot<W> *s = table + idx;
-            u32 cs = ld_cg_u32(&s->cs);
-            if (cs == 0) {
-                const u32 old = atomicCAS(&s->cs, 0u, CS_LOCKED);
-                if (old == 0) {
-#pragma unroll
-                    for (int j = 0; j < W; ++j) st_cg_u64(&s->key[j], key[j]);
-                    st_release_u32(&s->cs, add);          // key words become visible before the count
-                    return 1;
-                }
-                cs = old;
-            }
-            // Claimed but not yet published: look at the SAME slot again.  (Written as a re-probe and not
-            // as an inner `while (cs == LOCKED)` spin: nvcc deleted that loop because nothing after it
-            // used `cs`, and threads then compared half-written keys.)
-            if (cs == CS_LOCKED) continue;
-            bool eq = true;
-#pragma unroll
-            for (int j = 0; j < W; ++j) eq &= (ld_cg_u64(&s->key[j]) == key[j]);
-            if (eq) { red_add_u32(&s->cs, add); return 0; }
-            ++probe;
-            idx = (idx + 1 == cap) ? 0 : idx + 1;
+        u64 hi = old >> g.cbits;
+        while (hi == 0) {                              // claimed, tag not published yet
+            // volatile access on purpose: nvcc collapsed the same loop written with an inline-asm load
+            // into a single iteration, and threads then misjudged half-published slots
+            old = *reinterpret_cast<volatile u64 *>(s);
+            hi = old >> g.cbits;
         }
-        return -1;
+        if (hi == tag_hi) {
+            if ((old & g.cmask) >= g.dz) red_add_u64(s, ~0ull);
+            return 0;
+        }
+        red_add_u64(s, ~0ull);                         // not ours: take the +1 back
+        if (++d > (u32)CT_MAX_DISP) return -1;
+        s = tab + ((home + d) & g.capmask);
+        old = atomicAdd(s, 1ull);
     }
 }
 
-template <int W>
-__device__ __forceinline__ bool slot_occupied(const Slot<W> &s)
+__device__ __forceinline__ int ct_insert_unit(u64 *tab, const CtGeom &g, u64 h)
 {
-    if constexpr (W == 1) return s.key[0] != KEY_EMPTY;
-    else return s.cs != 0;
+    u64 *s = tab + (h >> g.rbits);
+    return ct_resolve(tab, g, h, 0, s, atomicAdd(s, 1ull));
 }
+
+// Weighted insert (table rebuild, records received from other shards, overflow re-insert).  Compare-
+// and-swap protocol: exact saturation at 65534 and no transient values.  Never runs concurrently with
+// ct_insert_unit (different kernels on one stream).
+__device__ __forceinline__ int ct_insert_weighted(u64 *tab, const CtGeom &g, u64 h, u64 w)
+{
+    const u64 home = h >> g.rbits;
+    const u64 r_hi = ((h << (64 - g.rbits)) >> (64 - g.rbits)) << CT_DISP_BITS;
+    if (w > COUNT_SAT) w = COUNT_SAT;
+#pragma unroll 1
+    for (u32 d = 0; d <= (u32)CT_MAX_DISP; ++d) {
+        u64 *s = tab + ((home + d) & g.capmask);
+        const u64 tag = (r_hi | (u64)(d + 1)) << g.cbits;
+        u64 cur = ld_cg_u64(s);
+        if (cur == 0) {
+            const u64 prev = atomicCAS(s, 0ull, tag | w);
+            if (prev == 0) return 1;
+            cur = prev;
+        }
+        if ((cur >> g.cbits) == (tag >> g.cbits)) {
+            for (;;) {
+                u64 c = (cur & g.cmask) + w;
+                if (c > COUNT_SAT) c = COUNT_SAT;
+                const u64 prev = atomicCAS(s, cur, tag | c);
+                if (prev == cur) return 0;
+                cur = prev;
+            }
+        }
+    }
+    return -1;
+}
+
+// -------------------------------------------------------------------------------------------------
+// generic table, k > 32
+// -------------------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ int wide_insert(Slot<W> *table, u64 cap, const u64 *key, u64 h, u32 add)
+{
+    u64 idx = __umul64hi(h, cap);          // capacity need not be a power of two
+    int probe = 0;
+#pragma unroll 1
+    while (probe < MAX_PROBE) {
+        Slot<W> *s = table + idx;
+        u32 cs = ld_cg_u32(&s->cs);
+        if (cs == 0) {
+            const u32 old = atomicCAS(&s->cs, 0u, CS_LOCKED);
+            if (old == 0) {
+#pragma unroll
+                for (int j = 0; j < W; ++j) st_cg_u64(&s->key[j], key[j]);
+                st_release_u32(&s->cs, add);          // key words become visible before the count
+                return 1;
+            }
+            cs = old;
+        }
+        // Claimed but not yet published: look at the SAME slot again.  (Written as a re-probe and not
+        // as an inner `while (cs == LOCKED)` spin: nvcc deleted that loop because nothing after it
+        // used `cs`, and threads then compared half-written keys.)
+        if (cs == CS_LOCKED) continue;
+        bool eq = true;
+#pragma unroll
+        for (int j = 0; j < W; ++j) eq &= (ld_cg_u64(&s->key[j]) == key[j]);
+        if (eq) { red_add_u32(&s->cs, add); return 0; }
+        ++probe;
+        idx = (idx + 1 == cap) ? 0 : idx + 1;
+    }
+    return -1;
+}
+
+// -------------------------------------------------------------------------------------------------
+// uniform view used by every kernel: Table<W> wraps either format
+// -------------------------------------------------------------------------------------------------
+template <int W>
+struct Table {
+    typedef typename SlotType<W>::type slot_t;
+    slot_t *slots;
+    u64 cap;
+    CtGeom g;          // only meaningful for W == 1
+
+    __host__ __device__ Table(void *p, u64 c) : slots((slot_t *)p), cap(c), g()
+    {
+        if (W == 1 && c) g = ct_geom(c);
+    }
+
+    // add `w` occurrences of `key`; unit adds take the single-atomic path
+    __device__ __forceinline__ int insert(const u64 *key, u64 h, u32 w, bool unit) const
+    {
+        if constexpr (W == 1) {
+            return unit ? ct_insert_unit(slots, g, h) : ct_insert_weighted(slots, g, h, w);
+        } else {
+            return wide_insert<W>(slots, cap, key, h, w > COUNT_SAT ? COUNT_SAT : w);
+        }
+    }
+    // read slot i once all inserts have drained: false if empty
+    __device__ __forceinline__ bool load(u64 i, u64 *key, u32 *count) const
+    {
+        if constexpr (W == 1) {
+            u64 c;
+            if (!ct_decode(slots[i], i, g, key, &c)) return false;
+            *count = c > COUNT_SAT ? COUNT_SAT : (u32)c;
+            return true;
+        } else {
+            const Slot<W> sl = slots[i];
+            if (sl.cs == 0) return false;
+#pragma unroll
+            for (int j = 0; j < W; ++j) key[j] = sl.key[j];
+            *count = sl.cs > COUNT_SAT ? COUNT_SAT : sl.cs;
+            return true;
+        }
+    }
+    // clamp the stored count to 65534 (keeps the 32-bit counters of wide slots away from overflow)
+    __device__ __forceinline__ void clamp(u64 i) const
+    {
+        if constexpr (W == 1) {
+            const u64 v = slots[i];
+            if ((v & g.cmask) > COUNT_SAT) slots[i] = (v & ~g.cmask) | COUNT_SAT;
+        } else {
+            if (slots[i].cs > COUNT_SAT) slots[i].cs = COUNT_SAT;
+        }
+    }
+};
 
 __device__ __forceinline__ u64 warp_sum_u64(u64 v)
 {

@@ -8,6 +8,7 @@
 #include "pbk_kernels_impl.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 
 namespace pbk {
@@ -69,7 +70,7 @@ void launch_count(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 wor
     const int grid = grid_for(word_end - word_begin, 256, sm_count, 8);
     PBK_DISPATCH_W(table.words,
         (count_kernel<W><<<grid, 256, 0, st>>>(stream, nflag, rflag, word_begin, word_end, k,
-            (Slot<W> *)table.slots, table.cap, (Slot<W> *)remote.slots, remote.cap,
+            Table<W>(table.slots, table.cap), Table<W>(remote.slots, remote.cap),
             shard.n_shards, shard.rank, ctr, overflow_keys, overflow_cap)));
 }
 
@@ -80,13 +81,13 @@ void launch_insert_records(const u64 *records, u64 n, bool weighted, TableView t
     if (n == 0) return;
     const int grid = grid_for(n, 256, sm_count, 8);
     PBK_DISPATCH_W(table.words,
-        (insert_records_kernel<W><<<grid, 256, 0, st>>>(records, n, weighted ? 1 : 0, (Slot<W> *)table.slots,
-            table.cap, (Slot<W> *)remote.slots, remote.cap, shard.n_shards, shard.rank,
+        (insert_records_kernel<W><<<grid, 256, 0, st>>>(records, n, weighted ? 1 : 0, Table<W>(table.slots, table.cap),
+            Table<W>(remote.slots, remote.cap), shard.n_shards, shard.rank,
             ctr, overflow_keys, overflow_cap)));
 }
 
 // ---- partitioned counting -------------------------------------------------------------------------
-constexpr size_t PART_SMEM_BUDGET = 192 * 1024;      // bins; the B200 SM has 227 KB per CTA
+constexpr size_t PART_SMEM_BUDGET = 100 * 1024;      // bins; two CTAs per SM (227 KB) so one computes while one flushes
 constexpr u64 PART_REGION_BYTES = 16ull << 20;       // table bytes per bucket: two regions + key stream << L2
 
 PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words)
@@ -129,57 +130,42 @@ void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64
                                overflow_keys, overflow_cap, grid, st)));
 }
 
-static void region_of(const TableView &t, u32 b, u32 n_buckets, const char **lo, const char **hi)
-{
-    if (!t.slots || b >= n_buckets) { *lo = *hi = nullptr; return; }
-    const unsigned __int128 cap = t.cap;
-    u64 s0 = (u64)((cap * b) / n_buckets), s1 = (u64)((cap * (b + 1)) / n_buckets) + 64;
-    if (s1 > t.cap) s1 = t.cap;
-    *lo = (const char *)t.slots + s0 * t.slot_bytes();
-    *hi = (const char *)t.slots + s1 * t.slot_bytes();
-}
+u32 passb_tile_keys() { return PASSB_TILE_KEYS; }
 
-void launch_bucket_insert(const u64 *keys, u64 n, u32 b, u32 n_buckets, TableView table, TableView remote,
-                          ShardInfo shard, Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count,
-                          cudaStream_t st)
+void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *d_count, const u64 *d_tile_start, u32 b_first,
+                          u32 b_end, u32 n_buckets, u64 *d_ticket, TableView table, TableView remote, ShardInfo shard,
+                          Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st)
 {
-    const char *lo, *hi, *lo2 = nullptr, *hi2 = nullptr;
-    region_of(table, b + 1, n_buckets, &lo, &hi);
-    if (shard.n_shards > 1) region_of(remote, b + 1, n_buckets, &lo2, &hi2);
-    const int grid = grid_for(std::max<u64>(n, 1), 256, sm_count, 8);
+    if (b_end <= b_first) return;
+    const int grid = sm_count * 8;                      // persistent: 8 CTAs of 256 threads per SM
     PBK_DISPATCH_W(table.words,
-        (bucket_insert_kernel<W><<<grid, 256, 0, st>>>(keys, n, (Slot<W> *)table.slots, table.cap,
-            (Slot<W> *)remote.slots, remote.cap, shard.n_shards, shard.rank, lo, hi, lo2, hi2, ctr, overflow_keys,
-            overflow_cap)));
+        (bucket_insert_kernel<W><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_count, d_tile_start, b_first, b_end,
+            n_buckets, d_ticket, Table<W>(table.slots, table.cap), Table<W>(remote.slots, remote.cap), shard.n_shards,
+            shard.rank, ctr, overflow_keys, overflow_cap, getenv("PBK_PASSB_SEQ") ? 1 : 0)));
 }
 
 void launch_table_init(TableView t, cudaStream_t st)
 {
-    if (t.words == 1) {
-        table_init1_kernel<<<grid_for(t.capacity(), 256, 148, 16), 256, 0, st>>>((uint4 *)t.slots, t.capacity());
-    } else {
-        cudaMemsetAsync(t.slots, 0, t.bytes(), st);
-    }
+    cudaMemsetAsync(t.slots, 0, t.bytes(), st);        // both slot formats use all-zero for "empty"
 }
 
 void launch_table_rehash(TableView from, TableView to, Counters *ctr, cudaStream_t st)
 {
     const int grid = grid_for(from.capacity(), 256, 148, 8);
     PBK_DISPATCH_W(from.words,
-        (rehash_kernel<W><<<grid, 256, 0, st>>>((const Slot<W> *)from.slots, from.capacity(), (Slot<W> *)to.slots,
-            to.cap, ctr)));
+        (rehash_kernel<W><<<grid, 256, 0, st>>>(Table<W>(from.slots, from.cap), Table<W>(to.slots, to.cap), ctr)));
 }
 
 void launch_table_clamp(TableView t, cudaStream_t st)
 {
     const int grid = grid_for(t.capacity(), 256, 148, 8);
-    PBK_DISPATCH_W(t.words, (clamp_kernel<W><<<grid, 256, 0, st>>>((Slot<W> *)t.slots, t.capacity())));
+    PBK_DISPATCH_W(t.words, (clamp_kernel<W><<<grid, 256, 0, st>>>(Table<W>(t.slots, t.cap))));
 }
 
 void launch_table_histogram(TableView t, u64 *occ_hist, cudaStream_t st)
 {
     const int grid = grid_for(t.capacity(), 256, 148, 4);
-    PBK_DISPATCH_W(t.words, (histogram_kernel<W><<<grid, 256, 0, st>>>((Slot<W> *)t.slots, t.capacity(), occ_hist)));
+    PBK_DISPATCH_W(t.words, (histogram_kernel<W><<<grid, 256, 0, st>>>(Table<W>(t.slots, t.cap), occ_hist)));
 }
 
 void launch_table_export(TableView t, u32 min_count, u64 *keys_out, uint16_t *counts_out, u64 capacity,
@@ -187,7 +173,7 @@ void launch_table_export(TableView t, u32 min_count, u64 *keys_out, uint16_t *co
 {
     const int grid = grid_for(t.capacity(), 256, 148, 8);
     PBK_DISPATCH_W(t.words,
-        (export_kernel<W><<<grid, 256, 0, st>>>((const Slot<W> *)t.slots, t.capacity(), min_count, keys_out,
+        (export_kernel<W><<<grid, 256, 0, st>>>(Table<W>(t.slots, t.cap), min_count, keys_out,
             counts_out, capacity, d_n_out)));
 }
 
@@ -195,14 +181,14 @@ void launch_shard_count(TableView remote, u32 n_shards, u64 *d_counts, cudaStrea
 {
     const int grid = grid_for(remote.capacity(), 256, 148, 8);
     PBK_DISPATCH_W(remote.words,
-        (shard_count_kernel<W><<<grid, 256, 0, st>>>((const Slot<W> *)remote.slots, remote.capacity(), n_shards, d_counts)));
+        (shard_count_kernel<W><<<grid, 256, 0, st>>>(Table<W>(remote.slots, remote.cap), n_shards, d_counts)));
 }
 
 void launch_shard_pack(TableView remote, u32 n_shards, u64 *d_cursors, u64 *records_out, cudaStream_t st)
 {
     const int grid = grid_for(remote.capacity(), 256, 148, 8);
     PBK_DISPATCH_W(remote.words,
-        (shard_pack_kernel<W><<<grid, 256, 0, st>>>((const Slot<W> *)remote.slots, remote.capacity(), n_shards,
+        (shard_pack_kernel<W><<<grid, 256, 0, st>>>(Table<W>(remote.slots, remote.cap), n_shards,
             d_cursors, records_out)));
 }
 
@@ -292,23 +278,35 @@ cudaError_t sort_export(u64 *keys, uint16_t *counts, u64 n, int words, int k, cu
 // microbenchmark: random read-modify-write rate (R_atomic of SURVEY.md section 8d)
 // =================================================================================================
 
+struct MbSlot { u64 key; u32 cs; u32 pad; };     // 16-byte key + count slot of the first table design
+
 __global__ void __launch_bounds__(256)
-microbench_kernel(Slot<1> *t, int log2slots, u64 n_ops, int mode, u64 seed)
+microbench_kernel(MbSlot *t, int log2slots, u64 n_ops, int mode, u64 seed)
 {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     u32 sink = 0;
+    const CtGeom g = ct_geom(2ull << log2slots);      // modes 2-4 see the buffer as 2^(log2slots+1) 8-byte slots
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_ops; i += stride) {
         const u64 h = fmix64(i + seed);
         if (mode == 0) {
             red_add_u32(&t[h >> (64 - log2slots)].cs, 1u);
         } else if (mode == 1) {
-            Slot<1> *s = t + (h >> (64 - log2slots));
-            const u64 cur = ld_cg_u64(&s->key[0]);
+            MbSlot *s = t + (h >> (64 - log2slots));
+            const u64 cur = ld_cg_u64(&s->key);
             if (cur != 0x123456789ull) red_add_u32(&s->cs, 1u);
             else ++sink;
-        } else {
-            u64 key = h >> 1;                        // never KEY_EMPTY
-            sink += (u32)table_insert<1>(t, 1ull << log2slots, &key, h, 1u);
+        } else if (mode == 2) {                      // compact-table inserts of distinct keys (claims)
+            sink += (u32)ct_insert_unit(reinterpret_cast<u64 *>(t), g, h);
+        } else if (mode == 3) {                      // 8-byte slots: one atomic with return per op
+            u64 *s8 = reinterpret_cast<u64 *>(t);
+            const u64 old = atomicAdd(&s8[h >> (63 - log2slots)], 1ull);
+            sink += (u32)(old >> 40);
+        } else {                                     // 8-byte slots: load, then reduction
+            u64 *s8 = reinterpret_cast<u64 *>(t);
+            u64 *q = &s8[h >> (63 - log2slots)];
+            const u64 cur = ld_cg_u64(q);
+            if (cur != 0x123456789ull) red_add_u64(q, 1ull);
+            else ++sink;
         }
     }
     if (sink == 0xFFFFFFFFu) t[0].pad = sink;
@@ -316,7 +314,7 @@ microbench_kernel(Slot<1> *t, int log2slots, u64 n_ops, int mode, u64 seed)
 
 void launch_microbench(void *table, int log2slots, u64 n_ops, int mode, u64 seed, int sm_count, cudaStream_t st)
 {
-    microbench_kernel<<<grid_for(n_ops, 256, sm_count, 8), 256, 0, st>>>((Slot<1> *)table, log2slots, n_ops, mode, seed);
+    microbench_kernel<<<grid_for(n_ops, 256, sm_count, 8), 256, 0, st>>>((MbSlot *)table, log2slots, n_ops, mode, seed);
 }
 
 }  // namespace pbk

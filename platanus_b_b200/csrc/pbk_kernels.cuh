@@ -6,11 +6,11 @@
 namespace pbk {
 
 struct TableView {
-    void *slots;       // Slot<W>[cap]
-    u64   cap;         // number of slots (any value >= 1)
+    void *slots;       // u64[cap] (k <= 32, cap a power of two >= 2^27) or Slot<W>[cap] (k > 32, any cap)
+    u64   cap;         // number of slots
     int   words;       // W
     u64   capacity() const { return cap; }
-    size_t slot_bytes() const { return 8 * (size_t)words + 8; }
+    size_t slot_bytes() const { return words == 1 ? 8 : 8 * (size_t)words + 8; }   // compact vs wide slots
     size_t bytes() const { return slot_bytes() * cap; }
 };
 
@@ -55,10 +55,12 @@ PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words);
 void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
                       int words, const PartitionPlan &plan, u64 *bkt_keys, u64 *bkt_cursor, Counters *ctr,
                       u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st);
-// Pass B for bucket `b` holding n keys; prefetches the table region(s) of bucket b + 1 into L2
-void launch_bucket_insert(const u64 *keys, u64 n, u32 b, u32 n_buckets, TableView table, TableView remote,
-                          ShardInfo shard, Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count,
-                          cudaStream_t st);
+// Pass B over buckets [b_first, b_end): one persistent launch.  d_count[b] = keys in bucket b,
+// d_tile_start[b - b_first] = first tile ticket of bucket b (b_end - b_first + 1 entries), *d_ticket = 0.
+u32 passb_tile_keys();
+void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *d_count, const u64 *d_tile_start, u32 b_first,
+                          u32 b_end, u32 n_buckets, u64 *d_ticket, TableView table, TableView remote, ShardInfo shard,
+                          Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st);
 
 // ---- table ------------------------------------------------------------------------------------
 void launch_table_init(TableView t, cudaStream_t st);

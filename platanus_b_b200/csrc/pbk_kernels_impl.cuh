@@ -77,27 +77,47 @@ pack_kernel(const uint8_t *__restrict__ bases, u64 n_valid, u64 n_words, int pla
 }
 
 
-// per read: ++lengthDistribution[len] (counter.h:406), ReadError (common.h:465), first-base flag
+// per read: ++lengthDistribution[len] (counter.h:406), ReadError (common.h:465), first-base flag.
+// Fixed-length read sets put every increment on ONE histogram bin, so lengths are aggregated per warp
+// (match_any) and then per CTA before touching global memory.
 __global__ void __launch_bounds__(256)
 read_marks_kernel(const u64 *__restrict__ off, u64 n_reads, u64 *len_hist, u32 *rflag, Counters *ctr)
 {
+    __shared__ u64 w_len[8];
+    __shared__ u32 w_cnt[8];
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31;
-    const u64 n_round = (n_reads + 31) & ~31ull;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 n_round = (n_reads + blockDim.x - 1) / blockDim.x * blockDim.x;
     for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_round; r += stride) {
         const bool active = r < n_reads;
         u64 start = 0, len = 0;
         if (active) { start = off[r]; len = off[r + 1] - start; }
         if (active && len >= 500000ull) { atomicOr(&ctr->error_flags, ERR_READ_TOO_LONG); len = 500000ull; }
         const unsigned act = __ballot_sync(0xffffffffu, active);
+        if (threadIdx.x < 8) w_cnt[threadIdx.x] = 0;
+        __syncthreads();
         if (active) {
             const unsigned peers = __match_any_sync(act, len);
-            if (lane == __ffs(peers) - 1) atomicAdd(&len_hist[len], (u64)__popc(peers));
+            if (lane == __ffs(peers) - 1) {
+                if (lane == __ffs(act) - 1 && warp < 8) { w_len[warp] = len; w_cnt[warp] = (u32)__popc(peers); }
+                else atomicAdd(&len_hist[len], (u64)__popc(peers));
+            }
             if (len > 0) atomicOr(&rflag[start >> 5], 1u << (start & 31));
         }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int nw = min((int)((blockDim.x + 31) >> 5), 8);
+            for (int a = 0; a < nw; ++a) {
+                if (!w_cnt[a]) continue;
+                u64 total = w_cnt[a];
+                for (int b = a + 1; b < nw; ++b)
+                    if (w_cnt[b] && w_len[b] == w_len[a]) { total += w_cnt[b]; w_cnt[b] = 0; }
+                atomicAdd(&len_hist[w_len[a]], total);
+            }
+        }
+        __syncthreads();
     }
 }
-
 
 __global__ void __launch_bounds__(256)
 npos_scatter_kernel(const u64 *__restrict__ off, const int32_t *__restrict__ n_pos,
@@ -139,7 +159,7 @@ __device__ __forceinline__ void spill_key(const u64 *key, Counters *ctr, u64 *ov
 template <int W>
 __global__ void __launch_bounds__(256)
 count_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, const u32 *__restrict__ rflag,
-             u64 word_begin, u64 word_end, int k, Slot<W> *table, u64 cap, Slot<W> *remote, u64 rcap,
+             u64 word_begin, u64 word_end, int k, Table<W> table, Table<W> remote,
              u32 n_shards, u32 rank, Counters *ctr, u64 *ovf, u64 ovf_cap)
 {
     const int top_shift = 2 * ((k - 1) & 31);
@@ -200,10 +220,10 @@ count_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, cons
                 ++inst;
                 int r;
                 if (n_shards > 1 && shard_of_hash(h, n_shards) != rank) {
-                    r = table_insert<W>(remote, rcap, key, h, 1u);
+                    r = remote.insert(key, h, 1u, true);
                     newr += (r > 0);
                 } else {
-                    r = table_insert<W>(table, cap, key, h, 1u);
+                    r = table.insert(key, h, 1u, true);
                     newk += (r > 0);
                 }
                 if (r < 0) spill_key<W>(key, ctr, ovf, ovf_cap);
@@ -222,9 +242,8 @@ count_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, cons
 
 template <int W>
 __global__ void __launch_bounds__(256)
-insert_records_kernel(const u64 *__restrict__ rec, u64 n, int weighted, Slot<W> *table, u64 cap,
-                      Slot<W> *remote, u64 rcap, u32 n_shards, u32 rank,
-                      Counters *ctr, u64 *ovf, u64 ovf_cap)
+insert_records_kernel(const u64 *__restrict__ rec, u64 n, int weighted, Table<W> table, Table<W> remote,
+                      u32 n_shards, u32 rank, Counters *ctr, u64 *ovf, u64 ovf_cap)
 {
     const int rw = weighted ? W + 1 : W;
     const u64 stride = (u64)gridDim.x * blockDim.x;
@@ -239,10 +258,10 @@ insert_records_kernel(const u64 *__restrict__ rec, u64 n, int weighted, Slot<W> 
         const u64 h = hash_key<W>(key);
         int r;
         if (n_shards > 1 && shard_of_hash(h, n_shards) != rank) {
-            r = table_insert<W>(remote, rcap, key, h, add);
+            r = remote.insert(key, h, add, false);
             newr += (r > 0);
         } else {
-            r = table_insert<W>(table, cap, key, h, add);
+            r = table.insert(key, h, add, false);
             newk += (r > 0);
         }
         if (r < 0) {
@@ -370,20 +389,29 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
             }
         }
         __syncthreads();
-        for (u32 b = warp; b < n_buckets; b += n_warps) {
-            const u32 n = min(scount[b], bin_cap);
-            if (n == 0) continue;
-            u64 g = 0;
-            if (lane == 0) g = atomicAdd(&bkt_cursor[b], (u64)n);
-            g = __shfl_sync(0xffffffffu, g, 0);
-            for (u32 i = lane; i < n * W; i += wsize) {
-                const u64 e = g + i / W;                 // entry index inside the bucket segment
-                if (e < seg_cap) bkt_keys[((u64)b * seg_cap) * W + (g * W + i)] = bins[(u64)b * bin_cap * W + i];
-                else if (i % W == 0) {
-                    u64 key[W];
+        // flush: a warp takes wsize buckets at a time, reserves all their segments with one atomic per
+        // lane (all in flight together), then copies bin after bin with coalesced stores
+        for (u32 b0 = warp * wsize; b0 < n_buckets; b0 += n_warps * wsize) {
+            const u32 mine = b0 + lane;
+            u32 n_mine = 0;
+            u64 g_mine = 0;
+            if (mine < n_buckets) {
+                n_mine = min(scount[mine], bin_cap);
+                if (n_mine) g_mine = atomicAdd(&bkt_cursor[mine], (u64)n_mine);
+            }
+            for (int t = 0; t < wsize && b0 + t < n_buckets; ++t) {
+                const u32 n = __shfl_sync(0xffffffffu, n_mine, t);
+                const u64 g = __shfl_sync(0xffffffffu, g_mine, t);
+                const u32 b = b0 + t;
+                for (u32 i = lane; i < n * W; i += wsize) {
+                    const u64 e = g + i / W;                 // entry index inside the bucket segment
+                    if (e < seg_cap) bkt_keys[((u64)b * seg_cap) * W + (g * W + i)] = bins[(u64)b * bin_cap * W + i];
+                    else if (i % W == 0) {
+                        u64 key[W];
 #pragma unroll
-                    for (int j = 0; j < W; ++j) key[j] = bins[(u64)b * bin_cap * W + i + j];
-                    spill_key<W>(key, ctr, ovf, ovf_cap);
+                        for (int j = 0; j < W; ++j) key[j] = bins[(u64)b * bin_cap * W + i + j];
+                        spill_key<W>(key, ctr, ovf, ovf_cap);
+                    }
                 }
             }
         }
@@ -393,34 +421,121 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
     if (lane == 0 && inst) atomicAdd(&ctr->instances, inst);
 }
 
-// Pass B for one bucket: pull the NEXT bucket's table region into L2 with line prefetches (a sequential
-// HBM stream), then insert this bucket's keys; their probes hit the region prefetched one launch ago.
+// Pass B, ONE persistent launch for all buckets.  Tiles of TILE_KEYS keys are handed out in bucket order
+// through an atomic ticket, so at any moment every CTA works inside the same one or two hash ranges and
+// the table region they touch stays in L2.  Tile j of bucket b also prefetches its share of the table
+// region of bucket b + 2, which turns the table's HBM traffic into one sequential pass.
+constexpr int PASSB_THREADS = 256;
+constexpr int PASSB_KEYS_PER_THREAD = 8;
+constexpr int PASSB_TILE_KEYS = PASSB_THREADS * PASSB_KEYS_PER_THREAD;
+
 template <int W>
-__global__ void __launch_bounds__(256)
-bucket_insert_kernel(const u64 *__restrict__ keys, u64 n, Slot<W> *table, u64 cap, Slot<W> *remote, u64 rcap,
-                     u32 n_shards, u32 rank, const char *pf_lo, const char *pf_hi, const char *pf2_lo,
-                     const char *pf2_hi, Counters *ctr, u64 *ovf, u64 ovf_cap)
+__global__ void __launch_bounds__(PASSB_THREADS)
+bucket_insert_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const u64 *__restrict__ bkt_count,
+                     const u64 *__restrict__ tile_start, u32 b_first, u32 b_end, u32 n_buckets, u64 *ticket,
+                     Table<W> table, Table<W> remote, u32 n_shards, u32 rank, Counters *ctr, u64 *ovf, u64 ovf_cap,
+                     int mode)
 {
-    const u64 stride = (u64)gridDim.x * blockDim.x, gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-#ifndef PBK_CPU_EMUL
-    for (const char *p = pf_lo + gtid * 128; p < pf_hi; p += stride * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-    for (const char *p = pf2_lo + gtid * 128; p < pf2_hi; p += stride * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-#endif
+    // buckets [b_first, b_end) of n_buckets; tile_start[b - b_first] = first ticket of bucket b
+    __shared__ u64 s_tile;
+    const u64 n_tiles = tile_start[b_end - b_first];
+    const u32 nthreads = blockDim.x, tile_keys = blockDim.x * PASSB_KEYS_PER_THREAD;
     u32 newk = 0, newr = 0;
-    for (u64 i = gtid; i < n; i += stride) {
-        u64 key[W];
-#pragma unroll
-        for (int j = 0; j < W; ++j) key[j] = keys[i * W + j];
-        const u64 h = hash_key<W>(key);
-        int r;
-        if (n_shards > 1 && shard_of_hash(h, n_shards) != rank) {
-            r = table_insert<W>(remote, rcap, key, h, 1u);
-            newr += (r > 0);
-        } else {
-            r = table_insert<W>(table, cap, key, h, 1u);
-            newk += (r > 0);
+    u32 b = b_first;
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1ull);
+        __syncthreads();
+        const u64 t = s_tile;
+        __syncthreads();
+        if (t >= n_tiles) break;
+        while (tile_start[b + 1 - b_first] <= t) ++b;            // tickets only grow: b only moves forward
+        const u64 j = t - tile_start[b - b_first], nt = tile_start[b + 1 - b_first] - tile_start[b - b_first];
+        const u64 n = bkt_count[b];
+        const u64 *keys = bkt_keys + (u64)b * seg_cap * W;
+
+#ifndef PBK_CPU_EMUL
+        if (b + 2 < n_buckets) {                                 // region of bucket b+2, slice j of nt
+            const u32 pb = b + 2;
+            const size_t sb = sizeof(typename SlotType<W>::type);
+            {
+                const u64 s0 = (u64)(((unsigned __int128)table.cap * pb) / n_buckets);
+                const u64 s1 = min((u64)(((unsigned __int128)table.cap * (pb + 1)) / n_buckets) + 128, table.cap);
+                const u64 bytes = (s1 - s0) * sb, lo = bytes * j / nt, hi = bytes * (j + 1) / nt;
+                const char *base = (const char *)(table.slots + s0);
+                for (u64 o = (lo & ~127ull) + (u64)threadIdx.x * 128; o < hi; o += (u64)nthreads * 128)
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(base + o));
+            }
+            if (n_shards > 1) {
+                const u64 s0 = (u64)(((unsigned __int128)remote.cap * pb) / n_buckets);
+                const u64 s1 = min((u64)(((unsigned __int128)remote.cap * (pb + 1)) / n_buckets) + 128, remote.cap);
+                const u64 bytes = (s1 - s0) * sb, lo = bytes * j / nt, hi = bytes * (j + 1) / nt;
+                const char *base = (const char *)(remote.slots + s0);
+                for (u64 o = (lo & ~127ull) + (u64)threadIdx.x * 128; o < hi; o += (u64)nthreads * 128)
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(base + o));
+            }
         }
-        if (r < 0) spill_key<W>(key, ctr, ovf, ovf_cap);
+#endif
+        const u64 base_i = j * tile_keys;
+        if (W == 1 && mode == 0) {
+          if constexpr (W == 1) {
+            // all loads, then all first-probe atomics, then the (rare) follow-ups: 8 independent
+            // memory operations in flight per thread
+            u64 hh[PASSB_KEYS_PER_THREAD], old[PASSB_KEYS_PER_THREAD];
+            bool own[PASSB_KEYS_PER_THREAD];
+#pragma unroll
+            for (int q = 0; q < PASSB_KEYS_PER_THREAD; ++q) {
+                const u64 i = base_i + (u64)q * nthreads + threadIdx.x;
+                hh[q] = i < n ? fmix64(keys[i]) : 0;
+                own[q] = !(n_shards > 1 && shard_of_hash(hh[q], n_shards) != rank);
+            }
+#pragma unroll
+            for (int q = 0; q < PASSB_KEYS_PER_THREAD; ++q) {
+                const u64 i = base_i + (u64)q * nthreads + threadIdx.x;
+                const Table<W> &tb = own[q] ? table : remote;
+                if (i < n) old[q] = atomicAdd(tb.slots + (hh[q] >> tb.g.rbits), 1ull);
+            }
+            // A thread must never wait for another thread's tag while it still owes tags of its own
+            // (two threads could wait for each other): publish every claim first, then resolve the rest.
+            bool done[PASSB_KEYS_PER_THREAD];
+#pragma unroll
+            for (int q = 0; q < PASSB_KEYS_PER_THREAD; ++q) {
+                const u64 i = base_i + (u64)q * nthreads + threadIdx.x;
+                done[q] = i >= n;
+                if (!done[q] && old[q] == 0) {
+                    const Table<W> &tb = own[q] ? table : remote;
+                    const u64 r_hi = ((hh[q] << (64 - tb.g.rbits)) >> (64 - tb.g.rbits)) << CT_DISP_BITS;
+                    red_add_u64(tb.slots + (hh[q] >> tb.g.rbits), (r_hi | 1ull) << tb.g.cbits);
+                    if (own[q]) ++newk; else ++newr;
+                    done[q] = true;
+                }
+            }
+#ifndef PBK_CPU_EMUL
+            __syncwarp();
+#endif
+#pragma unroll
+            for (int q = 0; q < PASSB_KEYS_PER_THREAD; ++q) {
+                if (done[q]) continue;
+                const Table<W> &tb = own[q] ? table : remote;
+                const int r = ct_resolve(tb.slots, tb.g, hh[q], 0, tb.slots + (hh[q] >> tb.g.rbits), old[q]);
+                if (own[q]) newk += (r > 0); else newr += (r > 0);
+                if (r < 0) { u64 key = fmix64_inverse(hh[q]); spill_key<W>(&key, ctr, ovf, ovf_cap); }
+            }
+          }
+        } else {
+#pragma unroll 1
+            for (int q = 0; q < PASSB_KEYS_PER_THREAD; ++q) {
+                const u64 i = base_i + (u64)q * nthreads + threadIdx.x;
+                if (i >= n) continue;
+                u64 key[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) key[w] = keys[i * W + w];
+                const u64 h = hash_key<W>(key);
+                int r;
+                if (n_shards > 1 && shard_of_hash(h, n_shards) != rank) { r = remote.insert(key, h, 1u, true); newr += (r > 0); }
+                else { r = table.insert(key, h, 1u, true); newk += (r > 0); }
+                if (r < 0) spill_key<W>(key, ctr, ovf, ovf_cap);
+            }
+        }
     }
     newk = warp_sum_u32(newk);
     newr = warp_sum_u32(newr);
@@ -434,49 +549,48 @@ bucket_insert_kernel(const u64 *__restrict__ keys, u64 n, Slot<W> *table, u64 ca
 // table maintenance
 // =================================================================================================
 
-__global__ void __launch_bounds__(256) table_init1_kernel(uint4 *slots, u64 n)
-{
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    const uint4 empty = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) slots[i] = empty;
-}
-
 template <int W>
 __global__ void __launch_bounds__(256)
-rehash_kernel(const Slot<W> *__restrict__ from, u64 n_from, Slot<W> *to, u64 cap, Counters *ctr)
+rehash_kernel(Table<W> from, Table<W> to, Counters *ctr)
 {
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_from; i += stride) {
-        Slot<W> sl = from[i];
-        if (!slot_occupied<W>(sl)) continue;
-        const u64 h = hash_key<W>(sl.key);
-        if (table_insert<W>(to, cap, sl.key, h, sl.cs) < 0) atomicOr(&ctr->error_flags, ERR_OVERFLOW_LOST);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < from.cap; i += stride) {
+        u64 key[W];
+        u32 count;
+        if (!from.load(i, key, &count)) continue;
+        if (to.insert(key, hash_key<W>(key), count, false) < 0) atomicOr(&ctr->error_flags, ERR_OVERFLOW_LOST);
     }
 }
 
 template <int W>
-__global__ void __launch_bounds__(256) clamp_kernel(Slot<W> *t, u64 n)
+__global__ void __launch_bounds__(256) clamp_kernel(Table<W> t)
 {
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        if (t[i].cs > COUNT_SAT) t[i].cs = COUNT_SAT;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.cap; i += stride) t.clamp(i);
 }
 
 // clamp + ++occurrenceDistribution[count] (counter.h:496).  Low counts go through a shared-memory
 // histogram, the long tail straight to global atomics.
 constexpr int HIST_SMEM_BINS = 4096;
 template <int W>
-__global__ void __launch_bounds__(256) histogram_kernel(Slot<W> *t, u64 n, u64 *occ_hist)
+__global__ void __launch_bounds__(256) histogram_kernel(Table<W> t, u64 *occ_hist)
 {
     __shared__ u32 sh[HIST_SMEM_BINS];
     for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Slot<W> sl = t[i];
-        if (!slot_occupied<W>(sl)) continue;
-        u32 c = sl.cs;
-        if (c > COUNT_SAT) { c = COUNT_SAT; t[i].cs = c; }
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.cap; i += stride) {
+        u32 c;
+        if constexpr (W == 1) {                       // no need to rebuild the key here
+            const u64 v = t.slots[i];
+            if ((v >> t.g.cbits) == 0) continue;
+            const u64 cc = v & t.g.cmask;
+            c = cc > COUNT_SAT ? COUNT_SAT : (u32)cc;
+        } else {
+            c = t.slots[i].cs;
+            if (c == 0) continue;
+            if (c > COUNT_SAT) c = COUNT_SAT;
+        }
         if (c < HIST_SMEM_BINS) atomicAdd(&sh[c], 1u);
         else atomicAdd(&occ_hist[c], 1ull);
     }
@@ -487,19 +601,16 @@ __global__ void __launch_bounds__(256) histogram_kernel(Slot<W> *t, u64 n, u64 *
 
 template <int W>
 __global__ void __launch_bounds__(256)
-export_kernel(const Slot<W> *__restrict__ t, u64 n, u32 min_count, u64 *keys_out, uint16_t *counts_out,
-              u64 capacity, u64 *d_n_out)
+export_kernel(Table<W> t, u32 min_count, u64 *keys_out, uint16_t *counts_out, u64 capacity, u64 *d_n_out)
 {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    const u64 n_round = (n + 31) & ~31ull;
+    const u64 n_round = (t.cap + 31) & ~31ull;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        Slot<W> sl;
+        u64 key[W];
+        u32 count = 0;
         bool keep = false;
-        if (i < n) {
-            sl = t[i];
-            keep = slot_occupied<W>(sl) && sl.cs >= min_count;
-        }
+        if (i < t.cap) keep = t.load(i, key, &count) && count >= min_count;
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (m == 0) continue;
         const int leader = __ffs(m) - 1;
@@ -510,8 +621,8 @@ export_kernel(const Slot<W> *__restrict__ t, u64 n, u32 min_count, u64 *keys_out
             const u64 at = base + __popc(m & ((1u << lane) - 1u));
             if (at < capacity) {
 #pragma unroll
-                for (int j = 0; j < W; ++j) keys_out[at * W + j] = sl.key[j];
-                counts_out[at] = (uint16_t)(sl.cs > COUNT_SAT ? COUNT_SAT : sl.cs);
+                for (int j = 0; j < W; ++j) keys_out[at * W + j] = key[j];
+                counts_out[at] = (uint16_t)count;
             }
         }
     }
@@ -519,18 +630,19 @@ export_kernel(const Slot<W> *__restrict__ t, u64 n, u32 min_count, u64 *keys_out
 
 template <int W>
 __global__ void __launch_bounds__(256)
-shard_count_kernel(const Slot<W> *__restrict__ t, u64 n, u32 n_shards, u64 *d_counts)
+shard_count_kernel(Table<W> t, u32 n_shards, u64 *d_counts)
 {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    const u64 n_round = (n + 31) & ~31ull;
+    const u64 n_round = (t.cap + 31) & ~31ull;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         bool occ = false;
         u32 dest = 0;
-        if (i < n) {
-            Slot<W> sl = t[i];
-            occ = slot_occupied<W>(sl);
-            if (occ) dest = shard_of_hash(hash_key<W>(sl.key), n_shards);
+        if (i < t.cap) {
+            u64 key[W];
+            u32 count;
+            occ = t.load(i, key, &count);
+            if (occ) dest = shard_of_hash(hash_key<W>(key), n_shards);
         }
         const unsigned act = __ballot_sync(0xffffffffu, occ);
         if (occ) {
@@ -542,19 +654,18 @@ shard_count_kernel(const Slot<W> *__restrict__ t, u64 n, u32 n_shards, u64 *d_co
 
 template <int W>
 __global__ void __launch_bounds__(256)
-shard_pack_kernel(const Slot<W> *__restrict__ t, u64 n, u32 n_shards, u64 *d_cursors, u64 *rec_out)
+shard_pack_kernel(Table<W> t, u32 n_shards, u64 *d_cursors, u64 *rec_out)
 {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    const u64 n_round = (n + 31) & ~31ull;
+    const u64 n_round = (t.cap + 31) & ~31ull;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         bool occ = false;
-        u32 dest = 0;
-        Slot<W> sl;
-        if (i < n) {
-            sl = t[i];
-            occ = slot_occupied<W>(sl);
-            if (occ) dest = shard_of_hash(hash_key<W>(sl.key), n_shards);
+        u32 dest = 0, count = 0;
+        u64 key[W];
+        if (i < t.cap) {
+            occ = t.load(i, key, &count);
+            if (occ) dest = shard_of_hash(hash_key<W>(key), n_shards);
         }
         const unsigned act = __ballot_sync(0xffffffffu, occ);
         if (occ) {
@@ -565,8 +676,8 @@ shard_pack_kernel(const Slot<W> *__restrict__ t, u64 n, u32 n_shards, u64 *d_cur
             base = __shfl_sync(peers, base, leader);
             const u64 at = base + __popc(peers & ((1u << lane) - 1u));
 #pragma unroll
-            for (int j = 0; j < W; ++j) rec_out[at * (W + 1) + j] = sl.key[j];
-            rec_out[at * (W + 1) + W] = sl.cs > COUNT_SAT ? COUNT_SAT : sl.cs;
+            for (int j = 0; j < W; ++j) rec_out[at * (W + 1) + j] = key[j];
+            rec_out[at * (W + 1) + W] = count;
         }
     }
 }

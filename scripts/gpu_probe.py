@@ -9,17 +9,19 @@ from platanus_b_b200 import microbench_atomics  # noqa: E402
 
 out = []
 MB = 1 << 20
-for mb in (16, 32, 48 * 0 + 64, 128, 256, 1024, 4096, 16384):
-    for mode in (0, 1, 2):
+SIZES = [int(x) for x in os.environ.get("PROBE_MB", "16,32,64,128,256,1024,4096,16384").split(",")]
+MODES = [int(x) for x in os.environ.get("PROBE_MODES", "0,1,2").split(",")]
+for mb in SIZES:
+    for mode in MODES:
         slots = (mb * MB) // 16
-        n_ops = 1 << 28 if mode < 2 else slots // 2
+        n_ops = slots // 2 if mode == 2 else 1 << 28
         try:
             r = microbench_atomics(mb * MB, n_ops, mode)
         except Exception as e:  # noqa: BLE001
             r = None
             print("failed", mb, mode, e, flush=True)
-        rec = {"table_mb": mb, "mode": ["red", "ld+red", "cas-insert"][mode], "n_ops": n_ops, "gops": None if r is None else r / 1e9}
+        rec = {"table_mb": mb, "mode": ["red", "ld+red", "cas-insert", "atom64-ret(8B slot)", "ld64+red64(8B slot)"][mode], "n_ops": n_ops, "gops": None if r is None else r / 1e9}
         print(json.dumps(rec), flush=True)
         out.append(rec)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/atomics.json", "w"), indent=1)
+json.dump(out, open(os.environ.get("PROBE_OUT", "gpurun_out/atomics.json"), "w"), indent=1)

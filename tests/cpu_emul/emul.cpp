@@ -21,9 +21,17 @@ static int run(const uint8_t *bases, const u64 *off, u64 n_reads, int k, int enc
     std::vector<u64> stream(words + STREAM_PAD_WORDS + 1, 0);
     std::vector<u32> nflag(words + STREAM_PAD_WORDS + 1, 0), rflag(words + STREAM_PAD_WORDS + 1, 0);
     Counters ctr{};
-    std::vector<Slot<W>> table(table_slots), remote(n_shards > 1 ? table_slots : 1);
-    for (auto *t : {&table, &remote})
-        for (auto &s : *t) { for (int j = 0; j < W; ++j) s.key[j] = (W == 1) ? KEY_EMPTY : 0; s.cs = 0; s.pad = 0; }
+    typedef typename SlotType<W>::type slot_t;
+    if (W == 1) {                                  // compact slots: power-of-two capacity, >= 2^24 here (17-bit counts)
+        u64 p2 = 1ull << 24;
+        while (p2 < table_slots) p2 <<= 1;
+        if (table_slots < (1ull << 20)) p2 = 1ull << 24;
+        table_slots = p2;
+    }
+    std::vector<slot_t> table_v(table_slots), remote_v(n_shards > 1 ? table_slots : 1);
+    memset(table_v.data(), 0, table_v.size() * sizeof(slot_t));
+    memset(remote_v.data(), 0, remote_v.size() * sizeof(slot_t));
+    Table<W> table(table_v.data(), table_v.size()), remote(remote_v.data(), remote_v.size());
     const u64 OVF = 1 << 16;
     std::vector<u64> ovf((W + 1) * OVF);
 
@@ -37,10 +45,10 @@ static int run(const uint8_t *bases, const u64 *off, u64 n_reads, int k, int enc
     if (encoding == 1) npos_scatter_kernel(off, n_pos, n_pos_off, n_reads, nflag.data() + STREAM_PAD_WORDS);
     if (!g_partition) {
         count_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
-                        0, w_split, k, table.data(), table_slots, remote.data(), table_slots, n_shards, rank, &ctr,
+                        0, w_split, k, table, remote, n_shards, rank, &ctr,
                         ovf.data(), OVF);
         count_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
-                        w_split, words, k, table.data(), table_slots, remote.data(), table_slots, n_shards, rank, &ctr,
+                        w_split, words, k, table, remote, n_shards, rank, &ctr,
                         ovf.data(), OVF);
     } else {
         // Pass A into P buckets with deliberately tiny bins/segments so the direct-append and spill paths run too
@@ -51,35 +59,47 @@ static int run(const uint8_t *bases, const u64 *off, u64 n_reads, int k, int enc
                             0, w_split, k, P, bin_cap, bkt.data(), seg_cap, cursor.data(), &ctr, ovf.data(), OVF);
         partition_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
                             w_split, words, k, P, bin_cap, bkt.data(), seg_cap, cursor.data(), &ctr, ovf.data(), OVF);
-        for (u32 b = 0; b < P; ++b)
-            bucket_insert_kernel<W>(bkt.data() + (u64)b * seg_cap * W, std::min<u64>(cursor[b], seg_cap), table.data(), table_slots,
-                                    remote.data(), table_slots, n_shards, rank, nullptr, nullptr, nullptr, nullptr, &ctr,
-                                    ovf.data(), OVF);
+        // Pass B in two launches (pilot + rest), tiles of blockDim * 8 = 8 keys
+        std::vector<u64> count(P);
+        for (u32 b = 0; b < P; ++b) count[b] = std::min<u64>(cursor[b], seg_cap);
+        const u32 tk = PASSB_KEYS_PER_THREAD;
+        const u32 cuts[3] = {0, 2, P};
+        for (int part = 0; part < 2; ++part) {
+            const u32 b0 = cuts[part], b1 = cuts[part + 1];
+            std::vector<u64> tile_start(b1 - b0 + 1);
+            u64 tiles = 0;
+            for (u32 b = b0; b < b1; ++b) { tile_start[b - b0] = tiles; tiles += (count[b] + tk - 1) / tk; }
+            tile_start[b1 - b0] = tiles;
+            u64 ticket = 0;
+            bucket_insert_kernel<W>(bkt.data(), seg_cap, count.data(), tile_start.data(), b0, b1, P, &ticket, table, remote,
+                                    n_shards, rank, &ctr, ovf.data(), OVF, part);
+        }
     }
     if (ctr.overflow_n) {          // grow + rehash + re-insert, as pbk_api.cu does
-        std::vector<Slot<W>> bigger(table_slots * 4);
-        for (auto &s : bigger) { for (int j = 0; j < W; ++j) s.key[j] = (W == 1) ? KEY_EMPTY : 0; s.cs = 0; s.pad = 0; }
-        rehash_kernel<W>(table.data(), table_slots, bigger.data(), table_slots * 4, &ctr);
-        table.swap(bigger);
+        std::vector<slot_t> bigger(table_slots * 4);
+        memset(bigger.data(), 0, bigger.size() * sizeof(slot_t));
+        rehash_kernel<W>(table, Table<W>(bigger.data(), bigger.size()), &ctr);
+        table_v.swap(bigger);
         table_slots *= 4;
+        table = Table<W>(table_v.data(), table_v.size());
         std::vector<u64> copy(ovf.begin(), ovf.begin() + std::min<u64>(ctr.overflow_n, OVF) * (W + 1));
         const u64 n = std::min<u64>(ctr.overflow_n, OVF);
         ctr.overflow_n = 0;
-        insert_records_kernel<W>(copy.data(), n, 1, table.data(), table_slots, remote.data(), remote.size(), n_shards, rank, &ctr,
+        insert_records_kernel<W>(copy.data(), n, 1, table, remote, n_shards, rank, &ctr,
                                  ovf.data(), OVF);
     }
-    histogram_kernel<W>(table.data(), table_slots, occ_hist);
+    histogram_kernel<W>(table, occ_hist);
     *n_out = 0;
-    export_kernel<W>(table.data(), table_slots, min_count, keys_out, counts_out, cap_out, n_out);
+    export_kernel<W>(table, min_count, keys_out, counts_out, cap_out, n_out);
     *n_inst = ctr.instances;
     *err_flags = ctr.error_flags;
     *n_remote = 0;
     if (n_shards > 1 && remote_records) {
         std::vector<u64> cnt(n_shards, 0), cur(n_shards, 0);
-        shard_count_kernel<W>(remote.data(), remote.size(), n_shards, cnt.data());
+        shard_count_kernel<W>(remote, n_shards, cnt.data());
         u64 tot = 0;
         for (u32 i = 0; i < n_shards; ++i) { cur[i] = tot; tot += cnt[i]; }
-        shard_pack_kernel<W>(remote.data(), remote.size(), n_shards, cur.data(), remote_records);
+        shard_pack_kernel<W>(remote, n_shards, cur.data(), remote_records);
         *n_remote = tot;
     }
     return 0;
@@ -104,10 +124,12 @@ extern "C" int emul_insert_records(const u64 *records, u64 n, int k, u64 table_s
     const int Wd = (k + 31) / 32;
     Counters ctr{};
     std::vector<u64> ovf(16 * 9);
-#define INS(Wv) case Wv: { std::vector<Slot<Wv>> t(table_slots);                                                   \
-        for (auto &s : t) { for (int j = 0; j < Wv; ++j) s.key[j] = (Wv == 1) ? KEY_EMPTY : 0; s.cs = 0; s.pad = 0; } \
-        insert_records_kernel<Wv>(records, n, 1, t.data(), table_slots, t.data(), table_slots, 1, 0, &ctr, ovf.data(), 16); \
-        *n_out = 0; export_kernel<Wv>(t.data(), table_slots, 1, keys_out, counts_out, cap_out, n_out);               \
+#define INS(Wv) case Wv: { if (Wv == 1) table_slots = 1ull << 24;                                                  \
+        std::vector<SlotType<Wv>::type> tv(table_slots);                                                             \
+        memset(tv.data(), 0, tv.size() * sizeof(SlotType<Wv>::type));                                                \
+        Table<Wv> t(tv.data(), tv.size());                                                                           \
+        insert_records_kernel<Wv>(records, n, 1, t, t, 1, 0, &ctr, ovf.data(), 16);                                  \
+        *n_out = 0; export_kernel<Wv>(t, 1, keys_out, counts_out, cap_out, n_out);                                   \
         return ctr.overflow_n ? -2 : 0; }
     switch (Wd) { INS(1) INS(2) INS(3) INS(4) INS(5) INS(6) INS(7) INS(8) default: return -1; }
 }

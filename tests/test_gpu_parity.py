@@ -286,8 +286,9 @@ def test_table_growth_from_a_tiny_hint(oracle):
     O = oracle
     rs = synth.make_reads(synth.config("C3", scale=1 / 200))
     b, o = rs.flat()
-    want = O.count(_oracle_reads_from_set(O, rs), 32)
-    with KmerCounter(32, table_slots_hint=1024) as kc:
+    want = O.count(_oracle_reads_from_set(O, rs), 40)
+    # k = 40: wide slots, any capacity (k <= 32 tables start at 2^27 slots and would not need to grow here)
+    with KmerCounter(40, table_slots_hint=1024) as kc:
         kc.push_reads(b, o)
         kc.finalize()
         keys, counts = kc.export(1, sorted=True)
