@@ -56,7 +56,7 @@ struct pbk_ctx {
     PartitionPlan plan{};
     u64 *d_bkt_keys = nullptr; size_t bkt_bytes = 0;
     u64 *d_bkt_cursor = nullptr, *h_bkt_cursor = nullptr;
-    u64 *d_passb = nullptr, *h_passb = nullptr;     // [ticket][tile_start: P+1][count: P]
+    void *d_passb = nullptr, *h_passb = nullptr;    // Pass B bucket descriptors
     bool partition_enabled = true, partition_forced = false;
     u64 *d_len_hist = nullptr, *d_occ_hist = nullptr, *d_shard_counts = nullptr;
     std::vector<u64> h_occ_hist, h_shard_counts;
@@ -338,8 +338,8 @@ int prepare_partition(pbk_ctx *c, u64 windows_ub)
     if (!c->d_bkt_cursor) {
         TRY(dev_alloc(c, (void **)&c->d_bkt_cursor, PART_MAX_BUCKETS * 8));
         if (cudaMallocHost((void **)&c->h_bkt_cursor, PART_MAX_BUCKETS * 8) != cudaSuccess) return fail(c, PBK_E_NOMEM, "pinned host memory");
-        TRY(dev_alloc(c, (void **)&c->d_passb, (2 * PART_MAX_BUCKETS + 2) * 8));
-        if (cudaMallocHost((void **)&c->h_passb, (2 * PART_MAX_BUCKETS + 2) * 8) != cudaSuccess) return fail(c, PBK_E_NOMEM, "pinned host memory");
+        TRY(dev_alloc(c, (void **)&c->d_passb, passb_desc_bytes(PART_MAX_BUCKETS)));
+        if (cudaMallocHost((void **)&c->h_passb, passb_desc_bytes(PART_MAX_BUCKETS)) != cudaSuccess) return fail(c, PBK_E_NOMEM, "pinned host memory");
     }
     CK(cudaMemsetAsync(c->d_bkt_cursor, 0, PART_MAX_BUCKETS * 8, c->s_compute));
     // a spilled key (bucket segment or bin full) is rare; the list is also used by Pass B
@@ -347,22 +347,15 @@ int prepare_partition(pbk_ctx *c, u64 windows_ub)
     return PBK_OK;
 }
 
-// one persistent Pass B launch over buckets [b0, b1)
+// one Pass B launch over buckets [b0, b1)
 int passb_launch(pbk_ctx *c, u32 b0, u32 b1)
 {
-    const u32 P = c->plan.n_buckets, nb = b1 - b0, tk = passb_tile_keys();
-    u64 *h = c->h_passb;
-    h[0] = 0;                                        // ticket
-    u64 tiles = 0;
-    for (u32 i = 0; i < nb; ++i) { h[1 + i] = tiles; tiles += (c->h_bkt_cursor[b0 + i] + tk - 1) / tk; }
-    h[1 + nb] = tiles;
-    DBG("pass B buckets [%u,%u) of %u: %llu tiles, table %llu slots, occupied %llu", b0, b1, P, tiles, c->table.cap, c->occupied);
-    for (u32 i = 0; i < P; ++i) h[2 + nb + i] = c->h_bkt_cursor[i];
-    CK(cudaMemcpyAsync(c->d_passb, h, (2 + nb + P) * 8, cudaMemcpyHostToDevice, c->s_compute));
-    c->h2d_bytes += (2 + nb + P) * 8;
-    if (tiles) {
+    u64 total = 0;
+    for (u32 b = b0; b < b1; ++b) total += c->h_bkt_cursor[b];
+    DBG("pass B buckets [%u,%u) of %u: %llu keys, table %llu slots, occupied %llu", b0, b1, c->plan.n_buckets, total, c->table.cap, c->occupied);
+    {
         Span sp(c, LC_INSERT);
-        launch_bucket_insert(c->d_bkt_keys, c->plan.seg_cap, c->d_passb + 2 + nb, c->d_passb + 1, b0, b1, P, c->d_passb,
+        launch_bucket_insert(c->d_bkt_keys, c->plan.seg_cap, c->h_bkt_cursor, c->h_passb, c->d_passb, b0, b1, c->plan.n_buckets,
                              c->table, c->remote, c->shard, c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
     }
     CK(cudaGetLastError());
@@ -863,7 +856,7 @@ uint32_t pbk_shard_of_key(const uint64_t *key_words, uint32_t k, uint32_t n_shar
 
 int pbk_microbench_atomics(int device, uint64_t table_bytes, uint64_t n_ops, int mode, double *ops_per_s)
 {
-    if (!ops_per_s || table_bytes < 4096 || n_ops == 0 || mode < 0 || mode > 4) return PBK_E_ARG;
+    if (!ops_per_s || table_bytes < 4096 || n_ops == 0 || mode < 0 || mode > 11) return PBK_E_ARG;
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return PBK_E_NO_DEVICE; }
     if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return PBK_E_NO_DEVICE;
@@ -873,7 +866,9 @@ int pbk_microbench_atomics(int device, uint64_t table_bytes, uint64_t n_ops, int
     while ((32ull << log2slots) <= table_bytes) ++log2slots;     // 16-byte slots, largest power of two that fits
     TableView t{nullptr, 2ull << log2slots, 1};                 // bytes = 16 << log2slots
     if (getenv("PBK_L2_FETCH32")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
-    if (cudaMalloc(&t.slots, t.bytes()) != cudaSuccess) { cudaGetLastError(); return PBK_E_NOMEM; }
+    const size_t extra = mode >= 6 ? (size_t)1 << 30 : 0;       // modes 6-8 read keys from a 1 GiB stream behind the table
+    if (cudaMalloc(&t.slots, t.bytes() + extra) != cudaSuccess) { cudaGetLastError(); return PBK_E_NOMEM; }
+    if (extra) cudaMemset((char *)t.slots + t.bytes(), 0x5A, extra);
     cudaStream_t st; cudaStreamCreate(&st);
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     float best = 1e30f;

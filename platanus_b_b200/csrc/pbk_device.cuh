@@ -126,6 +126,32 @@ __device__ __forceinline__ void st_release_u32(u32 *p, u32 v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
+// Table traffic carries an L2 evict_last policy: the hash range being worked on must survive the key
+// stream flowing through the same L2 (a missed atomic waits for an HBM fill and holds an L1 request
+// slot several times longer than a hit).
+__device__ __forceinline__ u64 l2_keep_policy()
+{
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ u64 atom_add_keep_u64(u64 *p, u64 v, u64 policy)
+{
+    u64 old;
+    asm volatile("atom.global.add.L2::cache_hint.u64 %0, [%1], %2, %3;" : "=l"(old) : "l"(p), "l"(v), "l"(policy) : "memory");
+    return old;
+}
+__device__ __forceinline__ void red_add_keep_u64(u64 *p, u64 v, u64 policy)
+{
+    asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;" :: "l"(p), "l"(v), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void prefetch_keep(const void *p)
+{
+    asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(p));
+}
+// read-once / write-once data (the bucket store): evict-first, so it does not push table lines out of L2
+__device__ __forceinline__ u64 ld_stream_u64(const u64 *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream_u64(u64 *p, u64 v) { __stcs(p, v); }
 #else   // tests/cpu_emul: same source run sequentially on the host, see tests/cpu_emul/cuda_shim.h
 inline u64 ld_cg_u64(const u64 *p) { return *p; }
 inline u32 ld_cg_u32(const u32 *p) { return *p; }
@@ -133,6 +159,12 @@ inline void red_add_u32(u32 *p, u32 v) { *p += v; }
 inline void red_add_u64(u64 *p, u64 v) { *p += v; }
 inline void st_cg_u64(u64 *p, u64 v) { *p = v; }
 inline void st_release_u32(u32 *p, u32 v) { *p = v; }
+inline u64 l2_keep_policy() { return 0; }
+inline u64 atom_add_keep_u64(u64 *p, u64 v, u64) { u64 o = *p; *p += v; return o; }
+inline void red_add_keep_u64(u64 *p, u64 v, u64) { *p += v; }
+inline void prefetch_keep(const void *) {}
+inline u64 ld_stream_u64(const u64 *p) { return *p; }
+inline void st_stream_u64(u64 *p, u64 v) { *p = v; }
 #endif
 
 // reverse the order of the 32 2-bit groups of a word

@@ -94,7 +94,8 @@ PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words)
 {
     PartitionPlan p{};
     const u64 entries = PART_SMEM_BUDGET / (8 * (size_t)words);
-    u64 P = (est_table_bytes + PART_REGION_BYTES - 1) / PART_REGION_BYTES;
+    static const u64 region_bytes = getenv("PBK_REGION_MB") ? (u64)atoi(getenv("PBK_REGION_MB")) << 20 : PART_REGION_BYTES;
+    u64 P = (est_table_bytes + region_bytes - 1) / region_bytes;
     P = std::max<u64>(P, 8);
     P = std::min<u64>(P, std::min<u64>((u64)PART_MAX_BUCKETS, entries / 24));
     p.n_buckets = (u32)P;
@@ -130,18 +131,51 @@ void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64
                                overflow_keys, overflow_cap, grid, st)));
 }
 
-u32 passb_tile_keys() { return PASSB_TILE_KEYS; }
+size_t passb_desc_bytes(u32 n_buckets) { return 16 + (size_t)(n_buckets + 1) * sizeof(PassBBucket); }
 
-void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *d_count, const u64 *d_tile_start, u32 b_first,
-                          u32 b_end, u32 n_buckets, u64 *d_ticket, TableView table, TableView remote, ShardInfo shard,
+static void prefetch_region(const TableView &t, u32 pb, u32 n_buckets, const char **base, u32 *lines)
+{
+    *base = nullptr; *lines = 0;
+    if (!t.slots || pb >= n_buckets) return;
+    const unsigned __int128 cap = t.cap;
+    const u64 s0 = (u64)((cap * pb) / n_buckets);
+    u64 s1 = (u64)((cap * (pb + 1)) / n_buckets) + 128;
+    if (s1 > t.cap) s1 = t.cap;
+    *lines = (u32)(((s1 - s0) * t.slot_bytes() + 127) / 128);
+    *base = (const char *)t.slots + s0 * t.slot_bytes();
+}
+
+void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *counts, void *h_desc, void *d_desc,
+                          u32 b_first, u32 b_end, u32 n_buckets, TableView table, TableView remote, ShardInfo shard,
                           Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st)
 {
     if (b_end <= b_first) return;
-    const int grid = sm_count * 8;                      // persistent: 8 CTAs of 256 threads per SM
+    static const int pf_dist = getenv("PBK_PF_DIST") ? atoi(getenv("PBK_PF_DIST")) : 1;   // buckets of look-ahead
+    // layout of the descriptor buffer: [ticket (u64, padded to 16 bytes)][PassBBucket x (nb + 1)]
+    u64 *h_ticket = (u64 *)h_desc;
+    PassBBucket *h = (PassBBucket *)((char *)h_desc + 16);
+    h_ticket[0] = 0; h_ticket[1] = 0;
+    u64 tiles = 0;
+    for (u32 b = b_first; b < b_end; ++b) {
+        PassBBucket &d = h[b - b_first];
+        d.tile_start = tiles;
+        d.n_keys = counts[b];
+        tiles += (counts[b] + PASSB_TILE_KEYS - 1) / PASSB_TILE_KEYS;
+        d.pf_base = d.pf_base2 = nullptr; d.pf_lines = d.pf_lines2 = 0;
+        if (pf_dist > 0 && counts[b]) {
+            prefetch_region(table, b + pf_dist, n_buckets, &d.pf_base, &d.pf_lines);
+            if (shard.n_shards > 1) prefetch_region(remote, b + pf_dist, n_buckets, &d.pf_base2, &d.pf_lines2);
+        }
+    }
+    h[b_end - b_first] = PassBBucket{tiles, 0, nullptr, nullptr, 0, 0};
+    cudaMemcpyAsync(d_desc, h_desc, passb_desc_bytes(b_end - b_first), cudaMemcpyHostToDevice, st);
+    if (tiles == 0) return;
+    const int grid = sm_count * (table.words == 1 ? 3 : 2);      // persistent: every CTA resident
     PBK_DISPATCH_W(table.words,
-        (bucket_insert_kernel<W><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_count, d_tile_start, b_first, b_end,
-            n_buckets, d_ticket, Table<W>(table.slots, table.cap), Table<W>(remote.slots, remote.cap), shard.n_shards,
-            shard.rank, ctr, overflow_keys, overflow_cap, getenv("PBK_PASSB_SEQ") ? 1 : 0)));
+        (bucket_insert_kernel<W><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap,
+            (const PassBBucket *)((const char *)d_desc + 16), b_first, b_end, (u64 *)d_desc,
+            Table<W>(table.slots, table.cap), Table<W>(remote.slots, remote.cap), shard.n_shards, shard.rank, ctr,
+            overflow_keys, overflow_cap)));
 }
 
 void launch_table_init(TableView t, cudaStream_t st)
@@ -300,6 +334,73 @@ microbench_kernel(MbSlot *t, int log2slots, u64 n_ops, int mode, u64 seed)
         } else if (mode == 3) {                      // 8-byte slots: one atomic with return per op
             u64 *s8 = reinterpret_cast<u64 *>(t);
             const u64 old = atomicAdd(&s8[h >> (63 - log2slots)], 1ull);
+            sink += (u32)(old >> 40);
+        } else if (mode == 5) {                      // mode 3 with C1's skew: 7/8 of the ops on 1/28 of the slots
+            u64 *s8 = reinterpret_cast<u64 *>(t);
+            const u64 n8 = 2ull << log2slots;
+            u64 idx = h >> (63 - log2slots);
+            if ((h & 7) != 0) idx = (fmix64(h >> 3) % (n8 / 28)) * 28 + 5;
+            const u64 old = atomicAdd(&s8[idx], 1ull);
+            sink += (u32)(old >> 40);
+        } else if (mode >= 6 && mode <= 8) {
+            // Pass B skeleton on an L2-resident table: 6 = key from an HBM stream + atomic; 7 = + result-dependent
+            // follow-up (1 op in 8: take the +1 back, second atomic); 8 = 7 with eight keys per thread, atomics first
+            u64 *s8 = reinterpret_cast<u64 *>(t);
+            const u64 *stream = s8 + (2ull << log2slots);        // the key stream lives behind the table
+            const u64 smask = (1ull << 27) - 1;                  // 1 GiB of keys
+            if (mode < 8) {
+                const u64 k = __ldcs(stream + (i & smask));
+                const u64 hk = fmix64(k + i);
+                u64 *q = &s8[hk >> (63 - log2slots)];
+                const u64 old = atomicAdd(q, 1ull);
+                if (mode == 7 && ((old ^ hk) & 7) == 0) {
+                    red_add_u64(q, ~0ull);
+                    sink += (u32)atomicAdd(&s8[(hk >> (63 - log2slots)) ^ 1], 1ull);
+                }
+                sink += (u32)(old >> 40);
+            } else {
+                if ((i / stride) & 7) continue;                    // every 8th iteration does 8 ops
+                u64 hk[8], old[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hk[j] = fmix64(__ldcs(stream + ((i + j * stride) & smask)) + i + j * stride);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) old[j] = atomicAdd(&s8[hk[j] >> (63 - log2slots)], 1ull);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (((old[j] ^ hk[j]) & 7) == 0) {
+                        red_add_u64(&s8[hk[j] >> (63 - log2slots)], ~0ull);
+                        sink += (u32)atomicAdd(&s8[(hk[j] >> (63 - log2slots)) ^ 1], 1ull);
+                    }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sink += (u32)(old[j] >> 40);
+            }
+        } else if (mode >= 9 && mode <= 11) {
+            // mode 7 on a table that does NOT fit in L2: the ops sweep 128 consecutive regions, each op lands
+            // in the region its position i belongs to.  9 = no prefetch; 10 = prefetch.global.L2 of the
+            // region after the next, sector by sector; 11 = the same with plain loads (ld.cg) instead
+            u64 *s8 = reinterpret_cast<u64 *>(t);
+            const u64 n8 = 2ull << log2slots, rs = n8 >> 7;      // slots per region
+            const u64 *stream = s8 + n8;
+            const u64 smask = (1ull << 27) - 1;
+            const u64 per_region = (n_ops + 127) >> 7;
+            const u64 region = i / per_region, o = i - region * per_region;
+            if (mode >= 10 && region + 2 < 128) {
+                const u64 sectors = rs * 8 / 32;
+                const u64 a = (u64)((double)o * (double)sectors / (double)per_region), b = (u64)((double)(o + 1) * (double)sectors / (double)per_region);
+                if (b > a) {
+                    const char *pa = (const char *)(s8 + (region + 2) * rs) + a * 32;
+                    if (mode == 10) asm volatile("prefetch.global.L2 [%0];" :: "l"(pa));
+                    else sink += (u32)ld_cg_u32((const u32 *)pa);
+                }
+            }
+            const u64 k = __ldcs(stream + (i & smask));
+            const u64 hk = fmix64(k + i);
+            u64 *q = &s8[region * rs + (hk % rs)];
+            const u64 old = atomicAdd(q, 1ull);
+            if (((old ^ hk) & 7) == 0) {
+                red_add_u64(q, ~0ull);
+                sink += (u32)atomicAdd(&s8[region * rs + ((hk % rs) ^ 1)], 1ull);
+            }
             sink += (u32)(old >> 40);
         } else {                                     // 8-byte slots: load, then reduction
             u64 *s8 = reinterpret_cast<u64 *>(t);

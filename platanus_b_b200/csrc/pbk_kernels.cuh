@@ -55,11 +55,11 @@ PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words);
 void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
                       int words, const PartitionPlan &plan, u64 *bkt_keys, u64 *bkt_cursor, Counters *ctr,
                       u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st);
-// Pass B over buckets [b_first, b_end): one persistent launch.  d_count[b] = keys in bucket b,
-// d_tile_start[b - b_first] = first tile ticket of bucket b (b_end - b_first + 1 entries), *d_ticket = 0.
-u32 passb_tile_keys();
-void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *d_count, const u64 *d_tile_start, u32 b_first,
-                          u32 b_end, u32 n_buckets, u64 *d_ticket, TableView table, TableView remote, ShardInfo shard,
+// Pass B over buckets [b_first, b_end) in one launch.  `h_desc` is scratch for b_end - b_first + 1 bucket
+// descriptors (pinned host memory), `d_desc` the same on the device; `counts[b]` = keys in bucket b.
+size_t passb_desc_bytes(u32 n_buckets);
+void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *counts, void *h_desc, void *d_desc,
+                          u32 b_first, u32 b_end, u32 n_buckets, TableView table, TableView remote, ShardInfo shard,
                           Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st);
 
 // ---- table ------------------------------------------------------------------------------------

@@ -405,7 +405,7 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
                 const u32 b = b0 + t;
                 for (u32 i = lane; i < n * W; i += wsize) {
                     const u64 e = g + i / W;                 // entry index inside the bucket segment
-                    if (e < seg_cap) bkt_keys[((u64)b * seg_cap) * W + (g * W + i)] = bins[(u64)b * bin_cap * W + i];
+                    if (e < seg_cap) st_stream_u64(&bkt_keys[((u64)b * seg_cap) * W + (g * W + i)], bins[(u64)b * bin_cap * W + i]);
                     else if (i % W == 0) {
                         u64 key[W];
 #pragma unroll
@@ -421,125 +421,164 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
     if (lane == 0 && inst) atomicAdd(&ctr->instances, inst);
 }
 
-// Pass B, ONE persistent launch for all buckets.  Tiles of TILE_KEYS keys are handed out in bucket order
-// through an atomic ticket, so at any moment every CTA works inside the same one or two hash ranges and
-// the table region they touch stays in L2.  Tile j of bucket b also prefetches its share of the table
-// region of bucket b + 2, which turns the table's HBM traffic into one sequential pass.
+// Pass B, ONE persistent launch for buckets [b_first, b_end).
+//  * Order: tiles of PASSB_TILE_KEYS keys are handed out in bucket order through an atomic ticket, so
+//    at any moment every CTA works inside the same one or two hash ranges and the table region they
+//    touch stays in L2 (threads that are free to drift apart end up all over the table: 26 GB of HBM
+//    reads instead of 4).
+//  * Latency: the ticket and the keys of the NEXT tile are fetched while the current tile is inserted,
+//    and a thread issues the first-probe atomics of all its 8 keys before looking at any result; the
+//    few follow-up probes go in further rounds.  One atomic round trip is ~2.5 us under load, so
+//    throughput is set by how many independent atomics are in flight.
+//  * HBM: tile j of bucket b prefetches its share of the table region of a later bucket, which turns the
+//    table's HBM traffic into one sequential pass.
 constexpr int PASSB_THREADS = 256;
-constexpr int PASSB_KEYS_PER_THREAD = 8;
-constexpr int PASSB_TILE_KEYS = PASSB_THREADS * PASSB_KEYS_PER_THREAD;
+constexpr int PASSB_KPT = 8;
+constexpr int PASSB_TILE_KEYS = PASSB_THREADS * PASSB_KPT;
+
+struct PassBBucket {
+    u64 tile_start;         // first ticket of this bucket (tiles of the launch are numbered in bucket order)
+    u64 n_keys;             // keys in this bucket
+    const char *pf_base;    // region to prefetch while this bucket is processed (main table), nullptr = none
+    const char *pf_base2;   // same for the remote-staging table
+    u32 pf_lines, pf_lines2;   // 128-byte lines in those regions
+};
+
+__device__ __forceinline__ void passb_prefetch(const char *base, u64 lines, u64 j, u64 nt, u32 tid, u32 nthreads)
+{
+#ifndef PBK_CPU_EMUL
+    // this tile's slice of the region, one prefetch per 32-byte SECTOR: L2 fills sector by sector, a
+    // prefetch per 128-byte line left three quarters of the region to be fetched by missing atomics
+    const u64 s0 = 4 * lines * j / nt, s1 = 4 * lines * (j + 1) / nt;
+    for (u64 l = s0 + tid; l < s1; l += nthreads) prefetch_keep(base + l * 32);
+#endif
+}
 
 template <int W>
-__global__ void __launch_bounds__(PASSB_THREADS)
-bucket_insert_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const u64 *__restrict__ bkt_count,
-                     const u64 *__restrict__ tile_start, u32 b_first, u32 b_end, u32 n_buckets, u64 *ticket,
-                     Table<W> table, Table<W> remote, u32 n_shards, u32 rank, Counters *ctr, u64 *ovf, u64 ovf_cap,
-                     int mode)
+__global__ void __launch_bounds__(PASSB_THREADS, W == 1 ? 3 : 2)
+bucket_insert_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const PassBBucket *__restrict__ bk,
+                     u32 b_first, u32 b_end, u64 *ticket, Table<W> table, Table<W> remote, u32 n_shards, u32 rank,
+                     Counters *ctr, u64 *ovf, u64 ovf_cap)
 {
-    // buckets [b_first, b_end) of n_buckets; tile_start[b - b_first] = first ticket of bucket b
-    __shared__ u64 s_tile;
-    const u64 n_tiles = tile_start[b_end - b_first];
-    const u32 nthreads = blockDim.x, tile_keys = blockDim.x * PASSB_KEYS_PER_THREAD;
+    __shared__ PassBBucket s_bk[PART_MAX_BUCKETS + 1];
+    __shared__ u64 s_ticket[2];
+    const u32 nb = b_end - b_first, tid = threadIdx.x, nthreads = blockDim.x, tile_keys = blockDim.x * PASSB_KPT;
+    for (u32 i = tid; i <= nb; i += nthreads) s_bk[i] = bk[i];
+    if (tid == 0) { s_ticket[0] = atomicAdd(ticket, 1ull); s_ticket[1] = atomicAdd(ticket, 1ull); }
+    __syncthreads();
+    const u64 n_tiles = s_bk[nb].tile_start;
     u32 newk = 0, newr = 0;
-    u32 b = b_first;
-    for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1ull);
-        __syncthreads();
-        const u64 t = s_tile;
-        __syncthreads();
-        if (t >= n_tiles) break;
-        while (tile_start[b + 1 - b_first] <= t) ++b;            // tickets only grow: b only moves forward
-        const u64 j = t - tile_start[b - b_first], nt = tile_start[b + 1 - b_first] - tile_start[b - b_first];
-        const u64 n = bkt_count[b];
-        const u64 *keys = bkt_keys + (u64)b * seg_cap * W;
 
-#ifndef PBK_CPU_EMUL
-        if (b + 2 < n_buckets) {                                 // region of bucket b+2, slice j of nt
-            const u32 pb = b + 2;
-            const size_t sb = sizeof(typename SlotType<W>::type);
-            {
-                const u64 s0 = (u64)(((unsigned __int128)table.cap * pb) / n_buckets);
-                const u64 s1 = min((u64)(((unsigned __int128)table.cap * (pb + 1)) / n_buckets) + 128, table.cap);
-                const u64 bytes = (s1 - s0) * sb, lo = bytes * j / nt, hi = bytes * (j + 1) / nt;
-                const char *base = (const char *)(table.slots + s0);
-                for (u64 o = (lo & ~127ull) + (u64)threadIdx.x * 128; o < hi; o += (u64)nthreads * 128)
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(base + o));
-            }
-            if (n_shards > 1) {
-                const u64 s0 = (u64)(((unsigned __int128)remote.cap * pb) / n_buckets);
-                const u64 s1 = min((u64)(((unsigned __int128)remote.cap * (pb + 1)) / n_buckets) + 128, remote.cap);
-                const u64 bytes = (s1 - s0) * sb, lo = bytes * j / nt, hi = bytes * (j + 1) / nt;
-                const char *base = (const char *)(remote.slots + s0);
-                for (u64 o = (lo & ~127ull) + (u64)threadIdx.x * 128; o < hi; o += (u64)nthreads * 128)
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(base + o));
-            }
+    // software pipeline: `nxt` holds the keys of the tile this CTA processes next
+    u64 nxt[PASSB_KPT][W];
+    u32 lb = 0, lb_next = 0;                                     // bucket (relative to b_first) of the current / next tile
+    u64 t = s_ticket[0];
+    int par = 0;
+    auto load_tile = [&](u64 tt, u32 &bb) {
+        while (s_bk[bb + 1].tile_start <= tt) ++bb;
+        const u64 base_i = (tt - s_bk[bb].tile_start) * tile_keys, n = s_bk[bb].n_keys;
+        const u64 *src = bkt_keys + (u64)(b_first + bb) * seg_cap * W;
+#pragma unroll
+        for (int q = 0; q < PASSB_KPT; ++q) {
+            const u64 i = base_i + (u64)q * nthreads + tid;
+#pragma unroll
+            for (int w = 0; w < W; ++w) nxt[q][w] = i < n ? ld_stream_u64(src + i * W + w) : 0;
         }
-#endif
+    };
+    if (t < n_tiles) load_tile(t, lb_next);
+
+    while (t < n_tiles) {
+        lb = lb_next;
+        u64 key[PASSB_KPT][W];
+#pragma unroll
+        for (int q = 0; q < PASSB_KPT; ++q)
+#pragma unroll
+            for (int w = 0; w < W; ++w) key[q][w] = nxt[q][w];
+        const u64 j = t - s_bk[lb].tile_start, n = s_bk[lb].n_keys;
+        const u64 nt = s_bk[lb + 1].tile_start - s_bk[lb].tile_start;
         const u64 base_i = j * tile_keys;
-        if (W == 1 && mode == 0) {
-          if constexpr (W == 1) {
-            // all loads, then all first-probe atomics, then the (rare) follow-ups: 8 independent
-            // memory operations in flight per thread
-            u64 hh[PASSB_KEYS_PER_THREAD], old[PASSB_KEYS_PER_THREAD];
-            bool own[PASSB_KEYS_PER_THREAD];
+
+        const u64 t_next = s_ticket[par ^ 1];                    // fetched one iteration ago
+        if (t_next < n_tiles) load_tile(t_next, lb_next);
+        __syncthreads();                                         // everyone has read s_ticket[par]
+        if (tid == 0) s_ticket[par] = atomicAdd(ticket, 1ull);   // ticket for the tile after next
+        if (s_bk[lb].pf_base) passb_prefetch(s_bk[lb].pf_base, s_bk[lb].pf_lines, j, nt, tid, nthreads);
+        if (s_bk[lb].pf_base2) passb_prefetch(s_bk[lb].pf_base2, s_bk[lb].pf_lines2, j, nt, tid, nthreads);
+
+        if constexpr (W == 1) {
+            const u64 keep = l2_keep_policy();
+            u64 hh[PASSB_KPT], old[PASSB_KPT];
+            u32 pend = 0, remote_mask = 0;                       // bit q: key q still needs a probe / lives in the remote table
+            u64 dd = 0;                                          // 8 bits of displacement per key
 #pragma unroll
-            for (int q = 0; q < PASSB_KEYS_PER_THREAD; ++q) {
-                const u64 i = base_i + (u64)q * nthreads + threadIdx.x;
-                hh[q] = i < n ? fmix64(keys[i]) : 0;
-                own[q] = !(n_shards > 1 && shard_of_hash(hh[q], n_shards) != rank);
+            for (int q = 0; q < PASSB_KPT; ++q) {
+                hh[q] = fmix64(key[q][0]);
+                if (base_i + (u64)q * nthreads + tid < n) pend |= 1u << q;
+                if (n_shards > 1 && shard_of_hash(hh[q], n_shards) != rank) remote_mask |= 1u << q;
             }
+#pragma unroll 1
+            while (pend) {
+                // round: all probes out, then all claims published, only then look at (or wait for) results --
+                // a thread never waits for another thread's tag while it still owes one of its own
 #pragma unroll
-            for (int q = 0; q < PASSB_KEYS_PER_THREAD; ++q) {
-                const u64 i = base_i + (u64)q * nthreads + threadIdx.x;
-                const Table<W> &tb = own[q] ? table : remote;
-                if (i < n) old[q] = atomicAdd(tb.slots + (hh[q] >> tb.g.rbits), 1ull);
-            }
-            // A thread must never wait for another thread's tag while it still owes tags of its own
-            // (two threads could wait for each other): publish every claim first, then resolve the rest.
-            bool done[PASSB_KEYS_PER_THREAD];
+                for (int q = 0; q < PASSB_KPT; ++q)
+                    if (pend >> q & 1) {
+                        const Table<W> &tb = (remote_mask >> q & 1) ? remote : table;
+                        const u64 d = (dd >> (8 * q)) & 0xFF;
+                        old[q] = atom_add_keep_u64(tb.slots + (((hh[q] >> tb.g.rbits) + d) & tb.g.capmask), 1ull, keep);
+                    }
 #pragma unroll
-            for (int q = 0; q < PASSB_KEYS_PER_THREAD; ++q) {
-                const u64 i = base_i + (u64)q * nthreads + threadIdx.x;
-                done[q] = i >= n;
-                if (!done[q] && old[q] == 0) {
-                    const Table<W> &tb = own[q] ? table : remote;
-                    const u64 r_hi = ((hh[q] << (64 - tb.g.rbits)) >> (64 - tb.g.rbits)) << CT_DISP_BITS;
-                    red_add_u64(tb.slots + (hh[q] >> tb.g.rbits), (r_hi | 1ull) << tb.g.cbits);
-                    if (own[q]) ++newk; else ++newr;
-                    done[q] = true;
-                }
-            }
-#ifndef PBK_CPU_EMUL
-            __syncwarp();
-#endif
+                for (int q = 0; q < PASSB_KPT; ++q)
+                    if ((pend >> q & 1) && old[q] == 0) {
+                        const Table<W> &tb = (remote_mask >> q & 1) ? remote : table;
+                        const u64 d = (dd >> (8 * q)) & 0xFF;
+                        const u64 r_hi = ((hh[q] << (64 - tb.g.rbits)) >> (64 - tb.g.rbits)) << CT_DISP_BITS;
+                        red_add_keep_u64(tb.slots + (((hh[q] >> tb.g.rbits) + d) & tb.g.capmask), (r_hi | (d + 1)) << tb.g.cbits, keep);
+                        if (remote_mask >> q & 1) ++newr; else ++newk;
+                        pend &= ~(1u << q);
+                    }
 #pragma unroll
-            for (int q = 0; q < PASSB_KEYS_PER_THREAD; ++q) {
-                if (done[q]) continue;
-                const Table<W> &tb = own[q] ? table : remote;
-                const int r = ct_resolve(tb.slots, tb.g, hh[q], 0, tb.slots + (hh[q] >> tb.g.rbits), old[q]);
-                if (own[q]) newk += (r > 0); else newr += (r > 0);
-                if (r < 0) { u64 key = fmix64_inverse(hh[q]); spill_key<W>(&key, ctr, ovf, ovf_cap); }
+                for (int q = 0; q < PASSB_KPT; ++q)
+                    if (pend >> q & 1) {
+                        const Table<W> &tb = (remote_mask >> q & 1) ? remote : table;
+                        const u64 d = (dd >> (8 * q)) & 0xFF;
+                        u64 *sl = tb.slots + (((hh[q] >> tb.g.rbits) + d) & tb.g.capmask);
+                        const u64 r_hi = ((hh[q] << (64 - tb.g.rbits)) >> (64 - tb.g.rbits)) << CT_DISP_BITS;
+                        u64 o = old[q], hi = o >> tb.g.cbits;
+                        while (hi == 0) { o = *reinterpret_cast<volatile u64 *>(sl); hi = o >> tb.g.cbits; }
+                        if (hi == (r_hi | (d + 1))) {
+                            if ((o & tb.g.cmask) >= tb.g.dz) red_add_keep_u64(sl, ~0ull, keep);
+                            pend &= ~(1u << q);
+                        } else {
+                            red_add_keep_u64(sl, ~0ull, keep);   // not ours: take the +1 back, next slot next round
+                            if (d >= (u64)CT_MAX_DISP) {
+                                u64 k0 = key[q][0];
+                                spill_key<W>(&k0, ctr, ovf, ovf_cap);
+                                pend &= ~(1u << q);
+                            } else {
+                                dd += 1ull << (8 * q);
+                            }
+                        }
+                    }
             }
-          }
         } else {
 #pragma unroll 1
-            for (int q = 0; q < PASSB_KEYS_PER_THREAD; ++q) {
-                const u64 i = base_i + (u64)q * nthreads + threadIdx.x;
-                if (i >= n) continue;
-                u64 key[W];
-#pragma unroll
-                for (int w = 0; w < W; ++w) key[w] = keys[i * W + w];
-                const u64 h = hash_key<W>(key);
+            for (int q = 0; q < PASSB_KPT; ++q) {
+                if (base_i + (u64)q * nthreads + tid >= n) continue;
+                const u64 h = hash_key<W>(key[q]);
                 int r;
-                if (n_shards > 1 && shard_of_hash(h, n_shards) != rank) { r = remote.insert(key, h, 1u, true); newr += (r > 0); }
-                else { r = table.insert(key, h, 1u, true); newk += (r > 0); }
-                if (r < 0) spill_key<W>(key, ctr, ovf, ovf_cap);
+                if (n_shards > 1 && shard_of_hash(h, n_shards) != rank) { r = remote.insert(key[q], h, 1u, true); newr += (r > 0); }
+                else { r = table.insert(key[q], h, 1u, true); newk += (r > 0); }
+                if (r < 0) spill_key<W>(key[q], ctr, ovf, ovf_cap);
             }
         }
+        __syncthreads();                                         // s_ticket[par] written by thread 0
+        t = t_next;
+        par ^= 1;
     }
     newk = warp_sum_u32(newk);
     newr = warp_sum_u32(newr);
-    if ((threadIdx.x & 31) == 0) {
+    if ((tid & 31) == 0) {
         if (newk) atomicAdd(&ctr->new_keys, (u64)newk);
         if (newr) atomicAdd(&ctr->new_keys_remote, (u64)newr);
     }

@@ -59,20 +59,19 @@ static int run(const uint8_t *bases, const u64 *off, u64 n_reads, int k, int enc
                             0, w_split, k, P, bin_cap, bkt.data(), seg_cap, cursor.data(), &ctr, ovf.data(), OVF);
         partition_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
                             w_split, words, k, P, bin_cap, bkt.data(), seg_cap, cursor.data(), &ctr, ovf.data(), OVF);
-        // Pass B in two launches (pilot + rest), tiles of blockDim * 8 = 8 keys
+        // Pass B in two launches (pilot + rest)
         std::vector<u64> count(P);
         for (u32 b = 0; b < P; ++b) count[b] = std::min<u64>(cursor[b], seg_cap);
-        const u32 tk = PASSB_KEYS_PER_THREAD;
         const u32 cuts[3] = {0, 2, P};
         for (int part = 0; part < 2; ++part) {
             const u32 b0 = cuts[part], b1 = cuts[part + 1];
-            std::vector<u64> tile_start(b1 - b0 + 1);
-            u64 tiles = 0;
-            for (u32 b = b0; b < b1; ++b) { tile_start[b - b0] = tiles; tiles += (count[b] + tk - 1) / tk; }
-            tile_start[b1 - b0] = tiles;
-            u64 ticket = 0;
-            bucket_insert_kernel<W>(bkt.data(), seg_cap, count.data(), tile_start.data(), b0, b1, P, &ticket, table, remote,
-                                    n_shards, rank, &ctr, ovf.data(), OVF, part);
+            std::vector<PassBBucket> desc(b1 - b0 + 1);
+            const u64 tk = PASSB_KPT;                    // blockDim = 1 in the emulation
+            u64 tiles = 0, ticket = 0;
+            for (u32 b = b0; b < b1; ++b) { desc[b - b0] = PassBBucket{tiles, count[b], nullptr, nullptr, 0, 0}; tiles += (count[b] + tk - 1) / tk; }
+            desc[b1 - b0] = PassBBucket{tiles, 0, nullptr, nullptr, 0, 0};
+            bucket_insert_kernel<W>(bkt.data(), seg_cap, desc.data(), b0, b1, &ticket, table, remote, n_shards, rank, &ctr,
+                                    ovf.data(), OVF);
         }
     }
     if (ctr.overflow_n) {          // grow + rehash + re-insert, as pbk_api.cu does
