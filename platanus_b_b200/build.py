@@ -13,7 +13,7 @@ LIB = os.path.join(OUT_DIR, "libpbk.so")
 
 NVCC = os.environ.get("PBK_NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
+CFLAGS = (["-DPBK_EXPERIMENT"] if os.environ.get("PBK_EXPERIMENT") else []) + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
 UNITS = ["pbk_kernels.cu", "pbk_api.cu", "pbk_host.cpp"]
 HEADERS = ["pbk_device.cuh", "pbk_kernels.cuh", os.path.join("..", "..", "include", "pbk.h")]
 
@@ -51,5 +51,24 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+CLI = os.path.join(OUT_DIR, "pbk_assemble")
+HOST = os.path.join(HERE, "host")
+
+
+def build_cli(force: bool = False) -> str:
+    """The host C++ side of the drop-in (host/pbk_counter.hpp + host/pbk_assemble.cpp), linked against libpbk.so."""
+    lib = build_lib()
+    srcs = [os.path.join(HOST, "pbk_assemble.cpp"), os.path.join(HOST, "pbk_counter.hpp"),
+            os.path.join(HERE, "..", "include", "pbk.h")]
+    if force or _stale(CLI, srcs + [lib]):
+        env = dict(os.environ)
+        env.pop("CXX", None)
+        env.pop("CC", None)
+        subprocess.run(["g++", "-O2", "-std=c++11", "-Wall", "-Wextra", "-pthread", "-o", CLI, srcs[0],
+                        "-L" + OUT_DIR, "-lpbk", "-Wl,-rpath,$ORIGIN"], check=True, env=env)
+    return CLI
+
+
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_cli(force="--force" in sys.argv))

@@ -856,7 +856,7 @@ uint32_t pbk_shard_of_key(const uint64_t *key_words, uint32_t k, uint32_t n_shar
 
 int pbk_microbench_atomics(int device, uint64_t table_bytes, uint64_t n_ops, int mode, double *ops_per_s)
 {
-    if (!ops_per_s || table_bytes < 4096 || n_ops == 0 || mode < 0 || mode > 11) return PBK_E_ARG;
+    if (!ops_per_s || table_bytes < 4096 || n_ops == 0 || mode < 0 || (mode > 11 && mode < 100) || mode > 200) return PBK_E_ARG;
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return PBK_E_NO_DEVICE; }
     if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return PBK_E_NO_DEVICE;
@@ -866,7 +866,7 @@ int pbk_microbench_atomics(int device, uint64_t table_bytes, uint64_t n_ops, int
     while ((32ull << log2slots) <= table_bytes) ++log2slots;     // 16-byte slots, largest power of two that fits
     TableView t{nullptr, 2ull << log2slots, 1};                 // bytes = 16 << log2slots
     if (getenv("PBK_L2_FETCH32")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
-    const size_t extra = mode >= 6 ? (size_t)1 << 30 : 0;       // modes 6-8 read keys from a 1 GiB stream behind the table
+    const size_t extra = (mode >= 6 && (mode < 100 || (mode & 3) >= 2)) ? (size_t)1 << 30 : 0;       // modes 6-8 read keys from a 1 GiB stream behind the table
     if (cudaMalloc(&t.slots, t.bytes() + extra) != cudaSuccess) { cudaGetLastError(); return PBK_E_NOMEM; }
     if (extra) cudaMemset((char *)t.slots + t.bytes(), 0x5A, extra);
     cudaStream_t st; cudaStreamCreate(&st);

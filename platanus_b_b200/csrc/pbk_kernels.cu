@@ -88,13 +88,13 @@ void launch_insert_records(const u64 *records, u64 n, bool weighted, TableView t
 
 // ---- partitioned counting -------------------------------------------------------------------------
 constexpr size_t PART_SMEM_BUDGET = 100 * 1024;      // bins; two CTAs per SM (227 KB) so one computes while one flushes
-constexpr u64 PART_REGION_BYTES = 16ull << 20;       // table bytes per bucket: two regions + key stream << L2
+constexpr u64 PART_REGION_BYTES = 4ull << 20;        // table bytes per bucket (measured on C1: 4 MB beats 16 MB in both passes)
 
 PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words)
 {
     PartitionPlan p{};
     const u64 entries = PART_SMEM_BUDGET / (8 * (size_t)words);
-    static const u64 region_bytes = getenv("PBK_REGION_MB") ? (u64)atoi(getenv("PBK_REGION_MB")) << 20 : PART_REGION_BYTES;
+    const u64 region_bytes = getenv("PBK_REGION_MB") ? (u64)atoi(getenv("PBK_REGION_MB")) << 20 : PART_REGION_BYTES;
     u64 P = (est_table_bytes + region_bytes - 1) / region_bytes;
     P = std::max<u64>(P, 8);
     P = std::min<u64>(P, std::min<u64>((u64)PART_MAX_BUCKETS, entries / 24));
@@ -150,17 +150,18 @@ void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *counts, v
                           Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st)
 {
     if (b_end <= b_first) return;
-    static const int pf_dist = getenv("PBK_PF_DIST") ? atoi(getenv("PBK_PF_DIST")) : 1;   // buckets of look-ahead
+    const int pf_dist = getenv("PBK_PF_DIST") ? atoi(getenv("PBK_PF_DIST")) : 1;   // buckets of look-ahead
     // layout of the descriptor buffer: [ticket (u64, padded to 16 bytes)][PassBBucket x (nb + 1)]
     u64 *h_ticket = (u64 *)h_desc;
     PassBBucket *h = (PassBBucket *)((char *)h_desc + 16);
     h_ticket[0] = 0; h_ticket[1] = 0;
+    const u64 tile_keys = table.words == 1 ? PASSB1_TILE_KEYS : PASSB_TILE_KEYS;
     u64 tiles = 0;
     for (u32 b = b_first; b < b_end; ++b) {
         PassBBucket &d = h[b - b_first];
         d.tile_start = tiles;
         d.n_keys = counts[b];
-        tiles += (counts[b] + PASSB_TILE_KEYS - 1) / PASSB_TILE_KEYS;
+        tiles += (counts[b] + tile_keys - 1) / tile_keys;
         d.pf_base = d.pf_base2 = nullptr; d.pf_lines = d.pf_lines2 = 0;
         if (pf_dist > 0 && counts[b]) {
             prefetch_region(table, b + pf_dist, n_buckets, &d.pf_base, &d.pf_lines);
@@ -170,12 +171,31 @@ void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *counts, v
     h[b_end - b_first] = PassBBucket{tiles, 0, nullptr, nullptr, 0, 0};
     cudaMemcpyAsync(d_desc, h_desc, passb_desc_bytes(b_end - b_first), cudaMemcpyHostToDevice, st);
     if (tiles == 0) return;
-    const int grid = sm_count * (table.words == 1 ? 3 : 2);      // persistent: every CTA resident
-    PBK_DISPATCH_W(table.words,
-        (bucket_insert_kernel<W><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap,
-            (const PassBBucket *)((const char *)d_desc + 16), b_first, b_end, (u64 *)d_desc,
-            Table<W>(table.slots, table.cap), Table<W>(remote.slots, remote.cap), shard.n_shards, shard.rank, ctr,
-            overflow_keys, overflow_cap)));
+    const PassBBucket *d_bk = (const PassBBucket *)((const char *)d_desc + 16);
+    if (table.words == 1) {
+        // persistent: every CTA resident (3 per SM)
+        const int ctas = getenv("PBK_PASSB_CTAS") ? atoi(getenv("PBK_PASSB_CTAS")) : 3;
+        const u32 opts = getenv("PBK_PASSB_HINT") ? (u32)atoi(getenv("PBK_PASSB_HINT")) : 1u;
+        const int grid = (int)std::min<u64>(tiles, (u64)sm_count * ctas);
+        if (shard.n_shards > 1)
+            bucket_insert_compact_kernel<true><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, b_first, b_end,
+                (u64 *)d_desc, Table<1>(table.slots, table.cap), Table<1>(remote.slots, remote.cap), shard.n_shards,
+                shard.rank, ctr, overflow_keys, overflow_cap, opts);
+        else
+            bucket_insert_compact_kernel<false><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, b_first, b_end,
+                (u64 *)d_desc, Table<1>(table.slots, table.cap), Table<1>(remote.slots, remote.cap), 1, 0, ctr,
+                overflow_keys, overflow_cap, opts);
+        return;
+    }
+    const int grid = (int)std::min<u64>(tiles, (u64)sm_count * 2);
+    switch (table.words) {
+#define PBK_CASE_W(Wv) case Wv: bucket_insert_kernel<Wv><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, b_first,   \
+            b_end, (u64 *)d_desc, Table<Wv>(table.slots, table.cap), Table<Wv>(remote.slots, remote.cap), shard.n_shards,    \
+            shard.rank, ctr, overflow_keys, overflow_cap); break;
+    PBK_CASE_W(2) PBK_CASE_W(3) PBK_CASE_W(4) PBK_CASE_W(5) PBK_CASE_W(6) PBK_CASE_W(7) PBK_CASE_W(8)
+#undef PBK_CASE_W
+    default: break;
+    }
 }
 
 void launch_table_init(TableView t, cudaStream_t st)
@@ -401,6 +421,32 @@ microbench_kernel(MbSlot *t, int log2slots, u64 n_ops, int mode, u64 seed)
                 red_add_u64(q, ~0ull);
                 sink += (u32)atomicAdd(&s8[region * rs + ((hk % rs) ^ 1)], 1ull);
             }
+            sink += (u32)(old >> 40);
+        } else if (mode >= 100) {
+            // sweep with shift/mask index math only: mode = 100 + 4 * log2(regions) + variant.  The table is cut
+            // into 2^rl consecutive regions, op i lands in region i >> log2(n_ops / regions) (n_ops must be a
+            // power of two).  variant 0 = atomic with return; 1 = + prefetch.L2 of the next region, one per sector;
+            // 2 = atomic + streamed 8-byte key load; 3 = 2 + claim-style follow-up reduction on 1 op in 8
+            u64 *s8 = reinterpret_cast<u64 *>(t);
+            const int rl = (mode - 100) >> 2, variant = (mode - 100) & 3;
+            const u64 n8 = 2ull << log2slots;
+            const int rs_log = log2slots + 1 - rl;                 // slots per region
+            const int pr_log = 63 - __clzll((long long)n_ops) - rl;   // ops per region
+            const u64 region = i >> pr_log, o = i & ((1ull << pr_log) - 1);
+            if (variant == 1 && region + 1 < (1ull << rl)) {
+                const int sec_log = rs_log - 2;                    // sectors per region (4 slots per sector)
+                if (sec_log >= pr_log) {
+                    for (u64 q = o << (sec_log - pr_log); q < ((o + 1) << (sec_log - pr_log)); ++q)
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"((const char *)(s8 + ((region + 1) << rs_log)) + q * 32));
+                } else if ((o & ((1ull << (pr_log - sec_log)) - 1)) == 0) {
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"((const char *)(s8 + ((region + 1) << rs_log)) + (o >> (pr_log - sec_log)) * 32));
+                }
+            }
+            u64 hk = h;
+            if (variant >= 2) hk = fmix64(__ldcs(s8 + n8 + (i & ((1ull << 27) - 1))) + i);
+            u64 *q = &s8[(region << rs_log) + (hk >> (64 - rs_log))];
+            const u64 old = atomicAdd(q, 1ull);
+            if (variant == 3 && ((old ^ hk) & 7) == 0) red_add_u64(q, 1ull << 40);
             sink += (u32)(old >> 40);
         } else {                                     // 8-byte slots: load, then reduction
             u64 *s8 = reinterpret_cast<u64 *>(t);

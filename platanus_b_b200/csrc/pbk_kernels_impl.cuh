@@ -298,6 +298,17 @@ insert_records_kernel(const u64 *__restrict__ rec, u64 n, int weighted, Table<W>
 #endif
 
 
+// a bucket-store entry (W == 1: the hash of the key) back to a key, then spilled
+template <int W>
+__device__ __forceinline__ void spill_stored(const u64 *stored, Counters *ctr, u64 *ovf, u64 ovf_cap)
+{
+    u64 key[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) key[j] = stored[j];
+    if (W == 1) key[0] = fmix64_inverse(stored[0]);
+    spill_key<W>(key, ctr, ovf, ovf_cap);
+}
+
 template <int W>
 __device__ __forceinline__ void bucket_append_direct(const u64 *key, u32 b, u64 *bkt_keys, u64 seg_cap,
                                                      u64 *bkt_cursor, u64 *ovf, u64 ovf_cap, Counters *ctr)
@@ -307,7 +318,7 @@ __device__ __forceinline__ void bucket_append_direct(const u64 *key, u32 b, u64 
 #pragma unroll
         for (int j = 0; j < W; ++j) bkt_keys[((u64)b * seg_cap + at) * W + j] = key[j];
     } else {
-        spill_key<W>(key, ctr, ovf, ovf_cap);       // bucket segment full: goes through the overflow list
+        spill_stored<W>(key, ctr, ovf, ovf_cap);    // bucket segment full: goes through the overflow list
     }
 }
 
@@ -376,7 +387,9 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
                     u64 key[W];
 #pragma unroll
                     for (int j = 0; j < W; ++j) key[j] = use_rev ? rev[j] : fwd[j];
-                    const u32 bkt = (u32)__umul64hi(hash_key<W>(key), (u64)n_buckets);
+                    const u64 hh = hash_key<W>(key);
+                    const u32 bkt = (u32)__umul64hi(hh, (u64)n_buckets);
+                    if (W == 1) key[0] = hh;          // one-word keys travel as their (bijective) hash
                     ++inst;
                     const u32 pos = atomicAdd(&scount[bkt], 1u);
                     if (pos < bin_cap) {
@@ -410,7 +423,7 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
                         u64 key[W];
 #pragma unroll
                         for (int j = 0; j < W; ++j) key[j] = bins[(u64)b * bin_cap * W + i + j];
-                        spill_key<W>(key, ctr, ovf, ovf_cap);
+                        spill_stored<W>(key, ctr, ovf, ovf_cap);
                     }
                 }
             }
@@ -455,7 +468,7 @@ __device__ __forceinline__ void passb_prefetch(const char *base, u64 lines, u64 
 }
 
 template <int W>
-__global__ void __launch_bounds__(PASSB_THREADS, W == 1 ? 3 : 2)
+__global__ void __launch_bounds__(PASSB_THREADS, 2)
 bucket_insert_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const PassBBucket *__restrict__ bk,
                      u32 b_first, u32 b_end, u64 *ticket, Table<W> table, Table<W> remote, u32 n_shards, u32 rank,
                      Counters *ctr, u64 *ovf, u64 ovf_cap)
@@ -505,77 +518,218 @@ bucket_insert_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const PassBB
         if (s_bk[lb].pf_base) passb_prefetch(s_bk[lb].pf_base, s_bk[lb].pf_lines, j, nt, tid, nthreads);
         if (s_bk[lb].pf_base2) passb_prefetch(s_bk[lb].pf_base2, s_bk[lb].pf_lines2, j, nt, tid, nthreads);
 
-        if constexpr (W == 1) {
-            const u64 keep = l2_keep_policy();
-            u64 hh[PASSB_KPT], old[PASSB_KPT];
-            u32 pend = 0, remote_mask = 0;                       // bit q: key q still needs a probe / lives in the remote table
-            u64 dd = 0;                                          // 8 bits of displacement per key
-#pragma unroll
-            for (int q = 0; q < PASSB_KPT; ++q) {
-                hh[q] = fmix64(key[q][0]);
-                if (base_i + (u64)q * nthreads + tid < n) pend |= 1u << q;
-                if (n_shards > 1 && shard_of_hash(hh[q], n_shards) != rank) remote_mask |= 1u << q;
-            }
 #pragma unroll 1
-            while (pend) {
-                // round: all probes out, then all claims published, only then look at (or wait for) results --
-                // a thread never waits for another thread's tag while it still owes one of its own
+        for (int q = 0; q < PASSB_KPT; ++q) {
+            if (base_i + (u64)q * nthreads + tid >= n) continue;
+            const u64 h = hash_key<W>(key[q]);
+            int r;
+            if (n_shards > 1 && shard_of_hash(h, n_shards) != rank) { r = remote.insert(key[q], h, 1u, true); newr += (r > 0); }
+            else { r = table.insert(key[q], h, 1u, true); newk += (r > 0); }
+            if (r < 0) spill_key<W>(key[q], ctr, ovf, ovf_cap);
+        }
+        __syncthreads();                                         // s_ticket[par] written by thread 0
+        t = t_next;
+        par ^= 1;
+    }
+    newk = warp_sum_u32(newk);
+    newr = warp_sum_u32(newr);
+    if ((tid & 31) == 0) {
+        if (newk) atomicAdd(&ctr->new_keys, (u64)newk);
+        if (newr) atomicAdd(&ctr->new_keys_remote, (u64)newr);
+    }
+}
+
+// Pass B for one-word keys (k <= 32).  The bucket store holds h = fmix64(key), so a key costs one
+// streamed 8-byte load, one 64-bit atomic add on its home slot and a three-instruction test of the
+// returned word.  What does not finish there -- the home slot belongs to another key, or it is claimed
+// but its tag is not visible yet -- is NOT resolved on the spot: a dependent chain of L2 round trips
+// executed by one or two lanes stalls the whole warp (measured: the 1 % of such keys tripled the time
+// of the pass).  Instead the key goes on a small per-warp list in shared memory and rides along with
+// the next round's batch of atomics (as probe d+1, or as a plain re-read of the slot).  Every round
+// therefore is: loads out, all atomics out, one look at the results, no waiting on other threads.
+constexpr int PASSB1_KPT = 8;
+constexpr int PASSB1_ROUNDS = 4;
+constexpr int PASSB1_TILE_KEYS = PASSB_THREADS * PASSB1_KPT * PASSB1_ROUNDS;
+constexpr int PASSB1_DEF_CAP = 32 * (PASSB1_KPT + 2);   // deferred keys per warp: what one round can add, plus one batch
+constexpr u32 PASSB1_DONE = 0xFFFFu;
+constexpr u32 PASSB1_VERIFY = 1u << 8, PASSB1_REMOTE = 1u << 9;   // deferred-entry flags above the displacement
+
+#ifdef PBK_CPU_EMUL
+static inline void __syncwarp() {}
+#endif
+
+// Look at what probe `d` of key `h` returned.  `verify` = the +1 is already in the slot and `old` is a
+// fresh read of it.  Returns PASSB1_DONE or the list entry (displacement + flags) of the follow-up.
+__device__ __forceinline__ u32 passb1_classify(const Table<1> &tb, bool is_remote, u64 h, u32 d, bool verify, u64 old,
+                                               u64 keep, u32 &newk, u32 &newr, Counters *ctr, u64 *ovf, u64 ovf_cap)
+{
+    const u64 tag = (h << (64 - tb.g.rbits)) | ((u64)(d + 1) << tb.g.cbits);
+    const u64 x = old ^ tag;
+    if (x < tb.g.dz) return PASSB1_DONE;                          // our tag and room in the count field: the common case
+    u64 *s = tb.slots + (((h >> tb.g.rbits) + d) & tb.g.capmask);
+    if (old == 0) {                                               // we saw the slot empty: it is ours, publish the tag
+        if (keep) red_add_keep_u64(s, tag, keep); else red_add_u64(s, tag);
+        if (is_remote) ++newr; else ++newk;
+        return PASSB1_DONE;
+    }
+    if ((old >> tb.g.cbits) == 0)                                 // claimed, tag not visible yet: look again next round
+        return d | PASSB1_VERIFY | (is_remote ? PASSB1_REMOTE : 0u);
+    if (keep) red_add_keep_u64(s, ~0ull, keep); else red_add_u64(s, ~0ull);   // not ours, or ours but saturated for sure
+    if ((x >> tb.g.cbits) == 0) return PASSB1_DONE;
+    if (d >= (u32)CT_MAX_DISP) { u64 k0 = fmix64_inverse(h); spill_key<1>(&k0, ctr, ovf, ovf_cap); return PASSB1_DONE; }
+    return (d + 1) | (is_remote ? PASSB1_REMOTE : 0u);
+}
+
+template <bool SHARDED, bool FULL>
+__device__ __forceinline__ void passb1_round(const u64 *__restrict__ src, u32 n_valid, u32 tid, u32 nthreads, u32 lane,
+                                             const Table<1> &table, const Table<1> &remote, u32 n_shards, u32 rank,
+                                             u64 keep, u32 &newk, u32 &newr, Counters *ctr, u64 *ovf, u64 ovf_cap,
+                                             u64 *def_h, uint16_t *def_m, u32 &n_def, u32 opts)
+{
+    // deferred keys of earlier rounds: the top min(n_def, warp size) entries, one per lane
+    const u32 wsize = nthreads < 32u ? nthreads : 32u;
+    const u32 take = n_def < wsize ? n_def : wsize;
+    u64 xh = 0;
+    u32 xm = PASSB1_DONE;
+    __syncwarp();
+    if (lane < take) { xh = def_h[n_def - 1 - lane]; xm = def_m[n_def - 1 - lane]; }
+    __syncwarp();
+    n_def -= take;
+
+    u64 h[PASSB1_KPT], old[PASSB1_KPT];
+    u32 valid = 0, rem = 0;
 #pragma unroll
-                for (int q = 0; q < PASSB_KPT; ++q)
-                    if (pend >> q & 1) {
-                        const Table<W> &tb = (remote_mask >> q & 1) ? remote : table;
-                        const u64 d = (dd >> (8 * q)) & 0xFF;
-                        old[q] = atom_add_keep_u64(tb.slots + (((hh[q] >> tb.g.rbits) + d) & tb.g.capmask), 1ull, keep);
-                    }
+    for (int q = 0; q < PASSB1_KPT; ++q) {
+        const u32 i = (u32)q * nthreads + tid;
+        if (FULL || i < n_valid) { h[q] = ld_stream_u64(src + i); valid |= 1u << q; }
+        else h[q] = 0;
+    }
+#ifdef PBK_EXPERIMENT
+    if (opts & 2u) {                     // experiment: no table traffic at all
+        u64 acc = 0;
 #pragma unroll
-                for (int q = 0; q < PASSB_KPT; ++q)
-                    if ((pend >> q & 1) && old[q] == 0) {
-                        const Table<W> &tb = (remote_mask >> q & 1) ? remote : table;
-                        const u64 d = (dd >> (8 * q)) & 0xFF;
-                        const u64 r_hi = ((hh[q] << (64 - tb.g.rbits)) >> (64 - tb.g.rbits)) << CT_DISP_BITS;
-                        red_add_keep_u64(tb.slots + (((hh[q] >> tb.g.rbits) + d) & tb.g.capmask), (r_hi | (d + 1)) << tb.g.cbits, keep);
-                        if (remote_mask >> q & 1) ++newr; else ++newk;
-                        pend &= ~(1u << q);
-                    }
+        for (int q = 0; q < PASSB1_KPT; ++q) acc ^= h[q];
+        if (acc == 0x1234567ull) ++newk;
+        return;
+    }
+#endif
 #pragma unroll
-                for (int q = 0; q < PASSB_KPT; ++q)
-                    if (pend >> q & 1) {
-                        const Table<W> &tb = (remote_mask >> q & 1) ? remote : table;
-                        const u64 d = (dd >> (8 * q)) & 0xFF;
-                        u64 *sl = tb.slots + (((hh[q] >> tb.g.rbits) + d) & tb.g.capmask);
-                        const u64 r_hi = ((hh[q] << (64 - tb.g.rbits)) >> (64 - tb.g.rbits)) << CT_DISP_BITS;
-                        u64 o = old[q], hi = o >> tb.g.cbits;
-                        while (hi == 0) { o = *reinterpret_cast<volatile u64 *>(sl); hi = o >> tb.g.cbits; }
-                        if (hi == (r_hi | (d + 1))) {
-                            if ((o & tb.g.cmask) >= tb.g.dz) red_add_keep_u64(sl, ~0ull, keep);
-                            pend &= ~(1u << q);
-                        } else {
-                            red_add_keep_u64(sl, ~0ull, keep);   // not ours: take the +1 back, next slot next round
-                            if (d >= (u64)CT_MAX_DISP) {
-                                u64 k0 = key[q][0];
-                                spill_key<W>(&k0, ctr, ovf, ovf_cap);
-                                pend &= ~(1u << q);
-                            } else {
-                                dd += 1ull << (8 * q);
-                            }
-                        }
-                    }
+    for (int q = 0; q < PASSB1_KPT; ++q) {
+        if (SHARDED && shard_of_hash(h[q], n_shards) != rank) rem |= 1u << q;
+        const Table<1> &tb = (SHARDED && (rem >> q & 1)) ? remote : table;
+        if (FULL || (valid >> q & 1)) old[q] = keep ? atom_add_keep_u64(tb.slots + (h[q] >> tb.g.rbits), 1ull, keep)
+                                                    : atomicAdd(tb.slots + (h[q] >> tb.g.rbits), 1ull);
+        else old[q] = 0;
+    }
+    u64 xold = 0;
+    const bool x_remote = SHARDED && (xm & PASSB1_REMOTE), x_verify = (xm & PASSB1_VERIFY) != 0;
+    const u32 xd = xm & 0xFFu;
+    if (xm != PASSB1_DONE) {
+        const Table<1> &tb = x_remote ? remote : table;
+        u64 *s = tb.slots + (((xh >> tb.g.rbits) + xd) & tb.g.capmask);
+        xold = x_verify ? ld_cg_u64(s) : (keep ? atom_add_keep_u64(s, 1ull, keep) : atomicAdd(s, 1ull));
+    }
+#ifdef PBK_EXPERIMENT
+    if (opts & 8u) {                     // experiment: atomics only, results ignored
+        u64 acc = 0;
+#pragma unroll
+        for (int q = 0; q < PASSB1_KPT; ++q) acc ^= old[q];
+        if (acc == 0x1234567ull) ++newk;
+        return;
+    }
+#endif
+    // one look at every result; follow-ups go on the list
+#pragma unroll
+    for (int q = 0; q <= PASSB1_KPT; ++q) {
+        u32 m = PASSB1_DONE;
+        u64 hq;
+        if (q < PASSB1_KPT) {
+            hq = h[q < PASSB1_KPT ? q : 0];
+            if (FULL || (valid >> q & 1)) {
+                const bool r = SHARDED && (rem >> q & 1);
+                m = passb1_classify(r ? remote : table, r, hq, 0, false, old[q < PASSB1_KPT ? q : 0], keep, newk, newr, ctr, ovf, ovf_cap);
+            }
+        } else {
+            hq = xh;
+            if (xm != PASSB1_DONE) m = passb1_classify(x_remote ? remote : table, x_remote, hq, xd, x_verify, xold, keep, newk, newr, ctr, ovf, ovf_cap);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, m != PASSB1_DONE);
+        if (bal == 0) continue;
+        if (m != PASSB1_DONE) {
+            const u32 pos = n_def + (u32)__popc(bal & ((1u << lane) - 1u));
+            def_h[pos] = hq;                                     // pos < PASSB1_DEF_CAP: callers keep n_def <= one batch
+            def_m[pos] = (uint16_t)m;                            // before a round that brings new keys
+        }
+        n_def += (u32)__popc(bal);
+    }
+}
+
+template <bool SHARDED>
+__global__ void __launch_bounds__(PASSB_THREADS, 3)
+bucket_insert_compact_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, const PassBBucket *__restrict__ bk,
+                             u32 b_first, u32 b_end, u64 *ticket, Table<1> table, Table<1> remote, u32 n_shards,
+                             u32 rank, Counters *ctr, u64 *ovf, u64 ovf_cap, u32 opts)
+{
+    __shared__ PassBBucket s_bk[PART_MAX_BUCKETS + 1];
+    __shared__ u64 s_ticket[2];
+    __shared__ u64 s_def_h[PASSB_THREADS / 32][PASSB1_DEF_CAP];
+    __shared__ uint16_t s_def_m[PASSB_THREADS / 32][PASSB1_DEF_CAP];
+    const u32 nb = b_end - b_first, tid = threadIdx.x, nthreads = blockDim.x;
+    const u32 lane = nthreads < 32u ? 0u : (tid & 31u), warp = nthreads < 32u ? 0u : (tid >> 5);
+    u64 *def_h = s_def_h[warp];
+    uint16_t *def_m = s_def_m[warp];
+    u32 n_def = 0;
+    const u32 def_room = nthreads < 32u ? 1u : 32u;              // a round may only start with at most one batch listed
+    const u32 round_keys = nthreads * PASSB1_KPT, tile_keys = round_keys * PASSB1_ROUNDS;
+    for (u32 i = tid; i <= nb; i += nthreads) s_bk[i] = bk[i];
+    if (tid == 0) { s_ticket[0] = atomicAdd(ticket, 1ull); s_ticket[1] = atomicAdd(ticket, 1ull); }
+    __syncthreads();
+    const u64 n_tiles = s_bk[nb].tile_start;
+    const u64 keep = (opts & 1u) ? l2_keep_policy() : 0ull;      // 0 = plain atomics (a real policy word is never 0)
+    u32 newk = 0, newr = 0, lb = 0;
+    int par = 0;
+    u64 t = s_ticket[0];
+    while (t < n_tiles) {
+        while (s_bk[lb + 1].tile_start <= t) ++lb;
+        const u64 j = t - s_bk[lb].tile_start, n = s_bk[lb].n_keys;
+        const u64 nt = s_bk[lb + 1].tile_start - s_bk[lb].tile_start;
+        const u64 t_next = s_ticket[par ^ 1];                    // fetched one iteration ago
+        __syncthreads();                                         // everyone has read both tickets
+        if (tid == 0) s_ticket[par] = atomicAdd(ticket, 1ull);   // ticket for the tile after next
+        if (s_bk[lb].pf_base) passb_prefetch(s_bk[lb].pf_base, s_bk[lb].pf_lines, j, nt, tid, nthreads);
+        if (SHARDED && s_bk[lb].pf_base2) passb_prefetch(s_bk[lb].pf_base2, s_bk[lb].pf_lines2, j, nt, tid, nthreads);
+        const u64 *src = bkt_hash + (u64)(b_first + lb) * seg_cap + j * tile_keys;
+        const u64 left = n - j * tile_keys;                      // > 0 by construction of the tile numbering
+        if (left >= tile_keys) {
+#pragma unroll 1
+            for (int r = 0; r < PASSB1_ROUNDS; ++r) {
+#pragma unroll 1
+                while (n_def > def_room)
+                    passb1_round<SHARDED, false>(bkt_hash, 0u, tid, nthreads, lane, table, remote, n_shards, rank, keep, newk, newr,
+                                                 ctr, ovf, ovf_cap, def_h, def_m, n_def, opts);
+                passb1_round<SHARDED, true>(src + (u64)r * round_keys, round_keys, tid, nthreads, lane, table, remote, n_shards,
+                                            rank, keep, newk, newr, ctr, ovf, ovf_cap, def_h, def_m, n_def, opts);
             }
         } else {
 #pragma unroll 1
-            for (int q = 0; q < PASSB_KPT; ++q) {
-                if (base_i + (u64)q * nthreads + tid >= n) continue;
-                const u64 h = hash_key<W>(key[q]);
-                int r;
-                if (n_shards > 1 && shard_of_hash(h, n_shards) != rank) { r = remote.insert(key[q], h, 1u, true); newr += (r > 0); }
-                else { r = table.insert(key[q], h, 1u, true); newk += (r > 0); }
-                if (r < 0) spill_key<W>(key[q], ctr, ovf, ovf_cap);
+            for (u64 o = 0; o < left; o += round_keys) {
+#pragma unroll 1
+                while (n_def > def_room)
+                    passb1_round<SHARDED, false>(bkt_hash, 0u, tid, nthreads, lane, table, remote, n_shards, rank, keep, newk, newr,
+                                                 ctr, ovf, ovf_cap, def_h, def_m, n_def, opts);
+                passb1_round<SHARDED, false>(src + o, (u32)min((u64)round_keys, left - o), tid, nthreads, lane, table, remote,
+                                             n_shards, rank, keep, newk, newr, ctr, ovf, ovf_cap, def_h, def_m, n_def, opts);
             }
         }
         __syncthreads();                                         // s_ticket[par] written by thread 0
         t = t_next;
         par ^= 1;
     }
+    // drain the warp's list (n_def is warp-uniform); publishing never waits, so this terminates
+#pragma unroll 1
+    while (n_def)
+        passb1_round<SHARDED, false>(bkt_hash, 0u, tid, nthreads, lane, table, remote, n_shards, rank, keep, newk, newr, ctr, ovf,
+                                     ovf_cap, def_h, def_m, n_def, opts);
     newk = warp_sum_u32(newk);
     newr = warp_sum_u32(newr);
     if ((tid & 31) == 0) {

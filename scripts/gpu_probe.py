@@ -20,7 +20,12 @@ for mb in SIZES:
         except Exception as e:  # noqa: BLE001
             r = None
             print("failed", mb, mode, e, flush=True)
-        rec = {"table_mb": mb, "mode": ["red", "ld+red", "cas-insert", "atom64-ret(8B slot)", "ld64+red64(8B slot)", "atom64-ret skewed 7/8 on 1/28", "stream key + atom64", "stream key + atom64 + 1/8 follow-up", "same, 8 keys per thread batched", "sweep 128 regions, no prefetch", "sweep + prefetch.L2 2 regions ahead", "sweep + ld.cg 2 regions ahead"][mode], "n_ops": n_ops, "gops": None if r is None else r / 1e9}
+        labels = ["red", "ld+red", "cas-insert", "atom64-ret(8B slot)", "ld64+red64(8B slot)", "atom64-ret skewed 7/8 on 1/28", "stream key + atom64", "stream key + atom64 + 1/8 follow-up", "same, 8 keys per thread batched", "sweep 128 regions, no prefetch", "sweep + prefetch.L2 2 regions ahead", "sweep + ld.cg 2 regions ahead"]
+        if mode >= 100:
+            label = f"sweep {1 << ((mode - 100) >> 2)} regions (shift/mask), " + ["atom64-ret", "atom64-ret + prefetch.L2 next region", "stream key + atom64-ret", "stream key + atom64-ret + 1/8 red"][(mode - 100) & 3]
+        else:
+            label = labels[mode]
+        rec = {"table_mb": mb, "mode": label, "n_ops": n_ops, "gops": None if r is None else r / 1e9}
         print(json.dumps(rec), flush=True)
         out.append(rec)
 os.makedirs("gpurun_out", exist_ok=True)

@@ -66,12 +66,17 @@ static int run(const uint8_t *bases, const u64 *off, u64 n_reads, int k, int enc
         for (int part = 0; part < 2; ++part) {
             const u32 b0 = cuts[part], b1 = cuts[part + 1];
             std::vector<PassBBucket> desc(b1 - b0 + 1);
-            const u64 tk = PASSB_KPT;                    // blockDim = 1 in the emulation
+            const u64 tk = W == 1 ? PASSB1_KPT * PASSB1_ROUNDS : PASSB_KPT;     // blockDim = 1 in the emulation
             u64 tiles = 0, ticket = 0;
             for (u32 b = b0; b < b1; ++b) { desc[b - b0] = PassBBucket{tiles, count[b], nullptr, nullptr, 0, 0}; tiles += (count[b] + tk - 1) / tk; }
             desc[b1 - b0] = PassBBucket{tiles, 0, nullptr, nullptr, 0, 0};
-            bucket_insert_kernel<W>(bkt.data(), seg_cap, desc.data(), b0, b1, &ticket, table, remote, n_shards, rank, &ctr,
-                                    ovf.data(), OVF);
+            if constexpr (W == 1) {
+                if (n_shards > 1) bucket_insert_compact_kernel<true>(bkt.data(), seg_cap, desc.data(), b0, b1, &ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF, 1u);
+                else bucket_insert_compact_kernel<false>(bkt.data(), seg_cap, desc.data(), b0, b1, &ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF, 0u);
+            } else {
+                bucket_insert_kernel<W>(bkt.data(), seg_cap, desc.data(), b0, b1, &ticket, table, remote, n_shards, rank, &ctr,
+                                        ovf.data(), OVF);
+            }
         }
     }
     if (ctr.overflow_n) {          // grow + rehash + re-insert, as pbk_api.cu does
