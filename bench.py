@@ -47,6 +47,16 @@ def algorithmic_bytes_per_instance(read_len: int, k: int) -> float:
     return read_len / (read_len - k + 1.0) + 64.0
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one step's Pass A + Pass B launches, from the committed
+    `ncu --set full` capture of this workload (profiles/*_traffic.json); None when there is no capture."""
+    path = os.path.join(ROOT, "profiles", "r1b_traffic.json")
+    try:
+        return float(json.load(open(path))["dram_bytes_per_step"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -58,7 +68,10 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The timed region
+    of this bench is tens of milliseconds, so the sampler is started before the warm-up, polls every 20 ms, and
+    the summary only uses the samples whose arrival time falls inside [t0, t1] (widened to the nearest samples
+    under load if the window caught fewer than two)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -67,41 +80,50 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.idx, self.lines, self.proc = gpu_index, [], None
 
-    def start(self):
+    def start(self, wait_s: float = 3.0):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t_end = time.time() + wait_s
+            while not self.lines and time.time() < t_end:       # nvidia-smi takes a few hundred ms to come up
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0: float = 0.0, t1: float = float("inf")):
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        rows = []
+        for ts, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                rows.append((ts, float(f[1]), float(f[2]), [v.lower().startswith("active") for v in f[5:9]]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        if len(inside) < 2 and rows:                            # nearest samples around the window (still under load)
+            mid = 0.5 * (t0 + min(t1, time.time()))
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+        if not inside:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        reasons = set()
+        for r in inside:
+            for name, on in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                if on:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": float(max(r[2] for r in inside)),
+                "reasons": sorted(reasons), "samples": len(inside)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -182,7 +204,7 @@ def main_ours(args):
     import torch
     import torch.distributed as dist
 
-    from platanus_b_b200 import KmerCounter, synth
+    from platanus_b_b200 import KmerCounter, sharding, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -220,22 +242,19 @@ def main_ours(args):
     hist_dev = torch.zeros(65535, dtype=torch.int64, device="cuda")
 
     def exchange():
-        """hash-range all-to-all of pre-aggregated (k-mer, count) records + histogram all-reduce"""
+        """hash-range all-to-all of pre-aggregated (k-mer, count) records (platanus_b_b200/sharding.py over NCCL)"""
         nonlocal send_buf, recv_buf
         cnt = kc.shard_send_counts(world).astype(np.int64)
-        send_counts = torch.from_numpy(cnt).cuda()
-        recv_counts = torch.empty_like(send_counts)
-        dist.all_to_all_single(recv_counts, send_counts)
-        rc = recv_counts.cpu().numpy()
+        rc = sharding.exchange_counts(torch.from_numpy(cnt).cuda()).cpu().numpy()
         n_send, n_recv = int(cnt.sum()), int(rc.sum())
         if send_buf is None or send_buf.shape[0] < n_send + 1:
             send_buf = torch.empty((int(n_send * 1.2) + 1024, W + 1), dtype=torch.int64, device="cuda")
         if recv_buf is None or recv_buf.shape[0] < n_recv + 1:
             recv_buf = torch.empty((int(n_recv * 1.2) + 1024, W + 1), dtype=torch.int64, device="cuda")
         kc.shard_pack_device(send_buf.data_ptr(), send_buf.shape[0])
-        dist.all_to_all_single(recv_buf[:n_recv], send_buf[:n_send], rc.tolist(), cnt.tolist())
+        got = sharding.exchange_records(send_buf, cnt.tolist(), rc.tolist(), recv_buf)
         torch.cuda.current_stream().synchronize()
-        kc.shard_insert_device(recv_buf.data_ptr(), n_recv)
+        kc.shard_insert_device(got.data_ptr(), n_recv)
         return n_send * (W + 1) * 8
 
     def step(resident: bool):
@@ -248,22 +267,23 @@ def main_ours(args):
         kc.finalize_light()                     # D2H of the occurrence histogram: the step's result
         if world > 1:
             hist_dev.copy_(torch.from_numpy(kc.occ_hist.astype(np.int64)), non_blocking=False)
-            dist.all_reduce(hist_dev)
+            sharding.allreduce_histogram(hist_dev)
             torch.cuda.current_stream().synchronize()
         return sent
 
     def timed(resident: bool, steps: int, warmup: int):
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()                     # before the warm-up: it is already polling when the timed steps run
         for _ in range(warmup):
             step(resident)
         s0 = kc.stats()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         kc.timer_mark(0)
         t0 = time.perf_counter()
+        w0 = time.time()
         sent = 0
         for _ in range(steps):
             sent += step(resident)
@@ -271,7 +291,7 @@ def main_ours(args):
         ms_dev = kc.timer_elapsed_ms(0, 1)
         torch.cuda.synchronize()
         wall_ms = (time.perf_counter() - t0) * 1e3
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.stop(w0, time.time()) if rank == 0 else None
         ms = max(ms_dev, 0.0)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -297,18 +317,33 @@ def main_ours(args):
     value = total_inst * args.steps / (ms_res * 1e-3)
     e2e = total_inst * args.steps / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel (count_kernel: extraction + table insert) ----------------
+    # ---- roofline of the counting phase -----------------------------------------------------------
+    # Every k-mer instance is handled once by Pass A (partition_kernel: extraction + canonical key + hash ->
+    # hash-range bucket store) and once by Pass B (bucket_insert_compact_kernel: one 64-bit atomic on the
+    # L2-resident table region), so the "launch" the algorithmic bytes are divided by is the pair: all Pass A
+    # and Pass B launches of one step.  SURVEY.md 8d: L/(L-k+1) + 64 bytes per instance.
     peak, peak_src = measured_peaks()
     bpi = algorithmic_bytes_per_instance(L, K)
-    launches = max(1, int(d_res["launches_count"]))
-    inst_per_launch = n_inst_local * args.steps / launches
-    ms_per_launch = d_res["ms_count"] / launches
-    achieved = bpi * inst_per_launch / (ms_per_launch * 1e-3) / 1e9 if ms_per_launch > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "count_kernel<1> (rolling canonical k-mers + table insert)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_instance": bpi,
-                "instances_per_launch": inst_per_launch, "ms_per_launch": ms_per_launch,
-                "kernel_share_of_step": d_res["ms_count"] / max(ms_res, 1e-9)}
+    ms_pair = (d_res["ms_partition"] + d_res["ms_insert"]) / args.steps
+    direct = d_res["ms_count"] - d_res["ms_partition"] - d_res["ms_insert"]      # non-partitioned launches (small batches)
+    if ms_pair <= 0:
+        ms_pair = d_res["ms_count"] / args.steps
+    achieved = bpi * n_inst_local / (ms_pair * 1e-3) / 1e9 if ms_pair > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "partition_kernel<1> + bucket_insert_compact_kernel<false> (Pass A + Pass B: "
+                                          "each instance goes through both exactly once)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic_bytes(), "peak_source": peak_src, "algorithmic_bytes_per_instance": bpi,
+                "instances_per_launch": n_inst_local, "ms_per_launch": ms_pair,
+                "launches_per_step": {"partition_kernel": d_res["launches_partition"] / args.steps,
+                                      "bucket_insert_compact_kernel": d_res["launches_insert"] / args.steps},
+                "ms_per_step": {"partition_kernel": d_res["ms_partition"] / args.steps,
+                                "bucket_insert_compact_kernel": d_res["ms_insert"] / args.steps,
+                                "direct_count_kernel": direct / args.steps},
+                "kernel_share_of_step": ms_pair * args.steps / max(ms_res, 1e-9),
+                "frac_of_step": bpi * n_inst_local * args.steps / (ms_res * 1e-3) / 1e9 / peak,
+                "atomic_bound_note": "random 64-bit atomics with return: 125 G/s on an L2-resident table, 22 G/s on a table >> L2 "
+                                     "(profiles/r1a_atomics_microbench.json, profiles/r1b_atomics_sweep.json); Pass B alone "
+                                     "runs at instances / ms_per_step.bucket_insert_compact_kernel"}
 
     line = None
     if rank == 0:
@@ -326,7 +361,7 @@ def main_ours(args):
                     "d2h_bytes_per_step": int(d_e2e["d2h_bytes"] / args.steps), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(d_res["launches_pack"] + d_res["launches_count"] + d_res["launches_other"]),
             "roofline": roofline,
-            "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
+            "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")} if clocks else None,
             "kernel_ms_per_step": {"pack": d_res["ms_pack"] / args.steps, "count": d_res["ms_count"] / args.steps,
                                    "other": d_res["ms_other"] / args.steps,
                                    "count_partition_pass": d_res["ms_partition"] / args.steps,

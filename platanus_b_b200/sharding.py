@@ -1,0 +1,35 @@
+"""Host side of the hash-range exchange between GPUs: plumbing over
+torch.distributed -- NCCL over NVLink on the GPUs, gloo in the CPU tests.  The records themselves are
+produced and consumed by libpbk (pbk_shard_pack_device / pbk_shard_insert_device)."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def exchange_counts(send_counts: torch.Tensor, group=None) -> torch.Tensor:
+    """send_counts[d] = records this rank holds for owner d  ->  recv_counts[s] = records rank s holds for us."""
+    recv = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv, send_counts, group=group)
+    return recv
+
+
+def exchange_records(send_buf: torch.Tensor, send_counts, recv_counts, recv_buf: torch.Tensor | None = None,
+                     group=None) -> torch.Tensor:
+    """All-to-all of (key words..., count) records.  `send_buf` is [n_send, W + 1] int64 grouped by destination in
+    rank order (what pbk_shard_pack_device writes); returns the [n_recv, W + 1] records this rank owns."""
+    send_counts = [int(x) for x in send_counts]
+    recv_counts = [int(x) for x in recv_counts]
+    n_send, n_recv = sum(send_counts), sum(recv_counts)
+    width = send_buf.shape[1]
+    if recv_buf is None or recv_buf.shape[0] < n_recv:
+        recv_buf = torch.empty((n_recv, width), dtype=send_buf.dtype, device=send_buf.device)
+    out = recv_buf[:n_recv]
+    dist.all_to_all_single(out, send_buf[:n_send], recv_counts, send_counts, group=group)
+    return out
+
+
+def allreduce_histogram(hist: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum of the per-shard occurrence histograms: shards own disjoint key sets, so the sum is the global one."""
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    return hist

@@ -139,3 +139,33 @@ def test_reference_kmer_divide_accepts_our_bin(L, oracle, name, tmp_path):
         produced = sorted(x for x in os.listdir(tmp_path) if x.startswith(tag + "_") or x.startswith(tag + "."))
         outs.append({x[1:]: open(tmp_path / x, "rb").read() for x in produced if not x.endswith(".bin")})
     assert outs[0] and outs[0] == outs[1]
+
+
+def test_host_cpp_side_builds_and_fails_loudly_without_a_device(tmp_path):
+    """platanus_b_b200/host (pbk::Counter + pbk_assemble) compiles with plain g++ against include/pbk.h; without a
+    CUDA device the program must stop with pbk::GPUError (exit code 64) -- no CPU fallback, no output files."""
+    import subprocess
+
+    import torch
+
+    from platanus_b_b200 import build as pbuild
+    cli = pbuild.build_cli()
+    assert os.access(cli, os.X_OK)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    fa = os.path.join(ROOT, "tests", "golden", "inputs", "kat.fa")
+    p = subprocess.run([cli, "assemble", "-kmer_occ_only", "-k", "4", "-n", "1", "-o", str(tmp_path / "x"), "-f", fa],
+                       capture_output=True, text=True)
+    assert p.returncode == 64 and "GPU" in p.stderr
+    assert not os.path.exists(tmp_path / "x_4merFrq.tsv") and not os.path.exists(tmp_path / "x_kmer_occ.bin")
+    p = subprocess.run([cli, "assemble", "-k", "8"], capture_output=True, text=True)      # no -f: usage (baseCommand.cpp:56-136)
+    assert p.returncode == 1 and "Usage" in p.stderr
+
+
+def test_counter_shim_mirrors_the_reference_member_names():
+    """pbk::Counter must offer the members Assemble::initialKmerAssemble calls on Counter<KMER> (assemble.cpp:303-350)."""
+    hpp = open(os.path.join(ROOT, "platanus_b_b200", "host", "pbk_counter.hpp")).read()
+    for name in ("makeKmerReadDistributionMT", "getLeftLocalMinimalValue", "calcOccurrenceDistributionAverage",
+                 "calcLengthDistributionAverage", "getMaxOccurrence", "outputOccurrenceDistribution", "sortedKeyFromKmerFile",
+                 "loadKmer", "outputOccurrenceTableBinary", "setKmerLength", "getKmerLength", "getLengthDistributionI", "kmerFP"):
+        assert re.search(r"\b%s\b" % name, hpp), name

@@ -1,0 +1,81 @@
+"""The N > 1 path on CPU: two processes (gloo, world size 2) run the host side of the hash-range exchange
+(platanus_b_b200/sharding.py, the same functions bench.py uses over NCCL) around the product kernels compiled
+for the host (tests/cpu_emul: shard routing, remote staging, record packing, weighted inserts).  Every rank must
+end up with exactly the keys it owns, with the global counts; the all-reduced histogram must be the oracle's."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, k, fq, out_dir):
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import ctypes as C
+
+    from emul_helper import emul_count, emul_insert_records
+    from oracle import oracle as O
+    from platanus_b_b200 import capi, sharding
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = capi.load_library()
+        W = (k + 31) // 32
+        rd = O.Reads()
+        rd.add_file(fq)
+        bases, offs = rd.arrays()
+        n = len(offs) - 1
+        lo, hi = n * rank // world, n * (rank + 1) // world
+        got = emul_count(bases[int(offs[lo]):int(offs[hi])], offs[lo:hi + 1] - offs[lo], k, n_shards=world, rank=rank)
+        staged = got["remote"].astype(np.int64)              # grouped by destination, as pbk_shard_pack_device writes them
+        owner = np.array([L.pbk_shard_of_key(np.ascontiguousarray(r[:W]).astype(np.uint64).ctypes.data_as(C.c_void_p), k, world)
+                          for r in staged], dtype=np.int64) if len(staged) else np.zeros(0, np.int64)
+        assert np.all(np.diff(owner) >= 0) and not np.any(owner == rank)
+        send_counts = torch.from_numpy(np.bincount(owner, minlength=world).astype(np.int64))
+        recv_counts = sharding.exchange_counts(send_counts)
+        recv = sharding.exchange_records(torch.from_numpy(staged.reshape(-1, W + 1).copy()), send_counts.tolist(), recv_counts.tolist())
+        mine = np.concatenate([got["keys"], got["counts"].astype(np.uint64)[:, None]], axis=1)
+        keys, counts = emul_insert_records(np.concatenate([mine, recv.numpy().astype(np.uint64).reshape(-1, W + 1)]), k)
+        # expected: the oracle's table restricted to the keys this rank owns
+        want = O.count(rd, k)
+        sel = np.array([L.pbk_shard_of_key(np.ascontiguousarray(r).ctypes.data_as(C.c_void_p), k, world) == rank
+                        for r in want.keys], dtype=bool)
+        assert np.array_equal(keys, want.keys[sel]) and np.array_equal(counts, want.counts[sel])
+        hist = torch.from_numpy(np.bincount(counts.astype(np.int64), minlength=65535).astype(np.int64))
+        sharding.allreduce_histogram(hist)
+        assert np.array_equal(hist.numpy().astype(np.uint64), want.occ_hist)
+        inst = torch.tensor([got["n_instances"]], dtype=torch.int64)
+        dist.all_reduce(inst)
+        assert int(inst.item()) == want.n_instances
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("k", [32, 75])
+def test_two_rank_exchange_over_gloo(oracle, k, tmp_path):
+    import emul_helper
+    emul_helper.lib()                                        # build the emulation once, before the workers race for it
+    fq = os.path.join(HERE, "golden", "inputs", "small.fq")
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), k, fq, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
