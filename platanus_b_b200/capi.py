@@ -24,6 +24,7 @@ ENC_ASCII, ENC_PLATANUS = 0, 1
 F_TIMING = 1
 F_NO_PARTITION = 2
 F_FORCE_PARTITION = 4
+F_NO_PIPELINE = 8
 
 STATUS = {0: "PBK_OK", -1: "PBK_E_ARG", -2: "PBK_E_NO_DEVICE", -3: "PBK_E_CUDA", -4: "PBK_E_NOMEM",
           -5: "PBK_E_READ_TOO_LONG", -6: "PBK_E_BAD_BASE", -7: "PBK_E_KMER_DIST", -8: "PBK_E_STATE",
@@ -53,7 +54,8 @@ class PbkStats(C.Structure):
                 ("launches_other", C.c_uint64), ("ms_pack", C.c_double), ("ms_count", C.c_double),
                 ("ms_other", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("launches_partition", C.c_uint64), ("launches_insert", C.c_uint64),
-                ("ms_partition", C.c_double), ("ms_insert", C.c_double)]
+                ("ms_partition", C.c_double), ("ms_insert", C.c_double), ("ms_count_elapsed", C.c_double),
+                ("n_pipelined_batches", C.c_uint64)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -129,12 +131,13 @@ class KmerCounter:
     """One GPU's k-mer occurrence counter (a `pbk_ctx`)."""
 
     def __init__(self, k: int, device: int = -1, n_shards: int = 1, shard_rank: int = 0, timing: bool = False,
-                 table_slots_hint: int = 0, hbm_budget_bytes: int = 0, partition: bool | str = True):
+                 table_slots_hint: int = 0, hbm_budget_bytes: int = 0, partition: bool | str = True,
+                 pipeline: bool = True):
         self._L = load_library()
         self._ctx = C.c_void_p()
         self.k = int(k)
         self.words = (self.k + 31) // 32
-        cfg = PbkConfig(C.sizeof(PbkConfig), self.k, device, (F_TIMING if timing else 0) | (F_FORCE_PARTITION if partition == "force" else 0 if partition else F_NO_PARTITION),
+        cfg = PbkConfig(C.sizeof(PbkConfig), self.k, device, (F_TIMING if timing else 0) | (F_FORCE_PARTITION if partition == "force" else 0 if partition else F_NO_PARTITION) | (0 if pipeline else F_NO_PIPELINE),
                         n_shards, shard_rank,
                         table_slots_hint, hbm_budget_bytes)
         rc = self._L.pbk_create(C.byref(self._ctx), C.byref(cfg))

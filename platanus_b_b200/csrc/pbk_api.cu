@@ -33,6 +33,8 @@ struct TimedSpan { cudaEvent_t a, b; int cls; };
 
 }  // namespace
 
+constexpr int N_STAGE = 4;                       // H2D staging buffers: the copy stream may run this far ahead of the kernels
+
 struct pbk_ctx {
     int device = 0, sm_count = 148;
     u32 k = 0; int W = 0; u32 flags = 0;
@@ -43,8 +45,8 @@ struct pbk_ctx {
     // batch buffers (grow-only)
     u64 *d_stream_raw = nullptr; u32 *d_nflag_raw = nullptr, *d_rflag_raw = nullptr; u64 stream_cap_words = 0;
     u64 *d_offsets = nullptr; u64 offsets_cap = 0;
-    uint8_t *d_stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0;
-    cudaEvent_t ev_copy_done[2] = {nullptr, nullptr}, ev_stage_free[2] = {nullptr, nullptr};
+    uint8_t *d_stage[N_STAGE] = {}; size_t stage_bytes = 0;
+    cudaEvent_t ev_copy_done[N_STAGE] = {}, ev_stage_free[N_STAGE] = {};
 
     TableView table{nullptr, 0, 0}, remote{nullptr, 0, 0};
     u64 occupied = 0, occupied_remote = 0;
@@ -58,6 +60,10 @@ struct pbk_ctx {
     u64 *d_bkt_cursor = nullptr, *h_bkt_cursor = nullptr;
     void *d_passb = nullptr, *h_passb = nullptr;    // Pass B bucket descriptors
     bool partition_enabled = true, partition_forced = false;
+    // sub-batched counting of host input (k <= 32): Pass A + Pass B per group of chunks, chained on the GPU, so that
+    // only the last group's Pass B is left to do when the last H2D copy lands
+    bool pipeline_enabled = true, ratio_known = false;
+    u64 n_pipelined = 0;
     u64 *d_len_hist = nullptr, *d_occ_hist = nullptr, *d_shard_counts = nullptr;
     std::vector<u64> h_occ_hist, h_shard_counts;
 
@@ -321,10 +327,11 @@ int count_range(pbk_ctx *c, u64 w0, u64 w1)
 
 // ---- partitioned path ---------------------------------------------------------------------------
 
-int prepare_partition(pbk_ctx *c, u64 windows_ub)
+// bucket store for `windows_ub` windows (the whole batch, or one sub-batch); the table is sized for `windows_total`
+int prepare_partition(pbk_ctx *c, u64 windows_ub, u64 windows_total)
 {
     const u64 est_slots = round_slots(c, std::max<u64>(c->table.slots ? c->table.cap : 0,
-                                                       (u64)((c->occupied + windows_ub * c->new_ratio) / max_load(c))));
+                                                       (u64)((c->occupied + windows_total * c->new_ratio) / max_load(c))));
     TableView tv{nullptr, est_slots, c->W};
     c->plan = plan_partition(tv.bytes(), windows_ub, c->W);
     const size_t need = (size_t)c->plan.n_buckets * c->plan.seg_cap * c->W * 8;
@@ -344,6 +351,44 @@ int prepare_partition(pbk_ctx *c, u64 windows_ub)
     CK(cudaMemsetAsync(c->d_bkt_cursor, 0, PART_MAX_BUCKETS * 8, c->s_compute));
     // a spilled key (bucket segment or bin full) is rare; the list is also used by Pass B
     TRY(ensure_overflow(c, 1ull << 22));
+    return PBK_OK;
+}
+
+// ---- sub-batched path (k <= 32, host input): the chunks of a batch are counted in groups -- Pass A per chunk, then
+// a device-built tile map and Pass B for the group, all queued on the compute stream without a host round trip --
+// while the copy stream keeps feeding the staging buffers.  When the last copy lands only one group's Pass B is
+// left.  (Running Pass B on a second stream next to Pass A was measured and is slower: both passes are bound by
+// the SM's load/store path -- shared-memory atomics in A, 32-sector global atomics in B -- not by different units.)
+struct Pipe {
+    bool on = false;
+    u32 sb_chunks = 0, in_sb = 0;       // chunks per sub-batch, chunks already partitioned into the current one
+};
+
+int pipe_finish_subbatch(pbk_ctx *c, Pipe &p)
+{
+    if (p.in_sb == 0) return PBK_OK;
+    { Span sp(c, LC_OTHER); launch_passb_desc(c->d_bkt_cursor, c->plan.seg_cap, c->plan.n_buckets, c->table, c->remote, c->shard, c->d_passb, c->s_compute); }
+    CK(cudaGetLastError());
+    {
+        Span sp(c, LC_INSERT);
+        launch_bucket_insert_chained(c->d_bkt_keys, c->plan.seg_cap, c->d_passb, c->plan.n_buckets, c->table, c->remote, c->shard, c->d_ctr,
+                                     c->d_ovf, c->ovf_cap, c->sm_count, 3, c->s_compute);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(c->d_bkt_cursor, 0, PART_MAX_BUCKETS * 8, c->s_compute));
+    p.in_sb = 0;
+    return PBK_OK;
+}
+
+int pipe_end(pbk_ctx *c, Pipe &p)
+{
+    TRY(pipe_finish_subbatch(c, p));
+    const u64 occ_before = c->occupied + c->occupied_remote, inst_before = c->last.instances;
+    TRY(read_counters(c));
+    TRY(drain_overflow(c));
+    const u64 inst = c->last.instances - inst_before;
+    if (inst > 4096) c->new_ratio = std::max(0.01, std::min(1.0, (double)(c->occupied + c->occupied_remote - occ_before) / (double)inst));
+    c->n_pipelined += 1;
     return PBK_OK;
 }
 
@@ -391,7 +436,10 @@ int flush_buckets(pbk_ctx *c)
         TRY(ensure_room(c, (u64)((double)(total - pilot_keys) * std::min(1.0, per_key * 1.05)) + 4096));
         TRY(passb_launch(c, pilot, P));
     }
-    if (total > 4096) c->new_ratio = std::max(0.01, std::min(1.0, (double)(c->occupied + c->occupied_remote - occ_before) / (double)total));
+    if (total > 4096) {
+        c->new_ratio = std::max(0.01, std::min(1.0, (double)(c->occupied + c->occupied_remote - occ_before) / (double)total));
+        c->ratio_known = true;
+    }
     CK(cudaMemsetAsync(c->d_bkt_cursor, 0, PART_MAX_BUCKETS * 8, c->s_compute));
     return PBK_OK;
 }
@@ -424,13 +472,31 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
 
     const bool deferred_count = (encoding == PBK_ENC_PLATANUS);     // N flags arrive after all packs
     const bool partitioned = c->partition_enabled && (windows_ub >= PART_MIN_WINDOWS || (c->partition_forced && windows_ub > 0));
-    if (partitioned) TRY(prepare_partition(c, windows_ub));
+    // Sub-batched: host input only (it exists to hide the passes behind the H2D copies), the compact kernel (k <= 32), a
+    // measured new-key ratio to size the table up front (the first large batch of a context takes the other path,
+    // with its pilot launch) and at least four chunks.
+    const u64 n_chunks_total = (n_bases + CHUNK_BASES - 1) / CHUNK_BASES;
+    Pipe pipe;
+    pipe.on = partitioned && c->pipeline_enabled && h_bases != nullptr && !d_bases_in && c->W == 1 && c->ratio_known && n_chunks_total >= 4;
+    if (pipe.on) {
+        const u32 n_sb = (u32)std::min<u64>(4, n_chunks_total / 2);
+        pipe.sb_chunks = (u32)((n_chunks_total + n_sb - 1) / n_sb);
+        const u64 sb_windows = std::min<u64>(windows_ub, (u64)pipe.sb_chunks * CHUNK_BASES);
+        TRY(maybe_clamp(c, windows_ub));
+        TRY(ensure_room(c, (u64)(windows_ub * std::min(1.0, c->new_ratio * 1.15)) + 65536));
+        TRY(prepare_partition(c, sb_windows, windows_ub));
+    } else if (partitioned) {
+        TRY(prepare_partition(c, windows_ub, windows_ub));
+    }
     // large batches: Pass A per chunk (no host sync), Pass B once at the end.  Small ones: straight to the table.
     auto count_words = [&](u64 w0, u64 w1) -> int {
         if (!partitioned) return count_range(c, w0, w1);
-        Span sp(c, LC_PART);
-        launch_partition(stream, nflag, rflag, w0, w1, (int)c->k, c->W, c->plan, c->d_bkt_keys, c->d_bkt_cursor, c->d_ctr,
-                         c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+        {
+            Span sp(c, LC_PART);
+            launch_partition(stream, nflag, rflag, w0, w1, (int)c->k, c->W, c->plan, c->d_bkt_keys, c->d_bkt_cursor, c->d_ctr,
+                             c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+        }
+        if (pipe.on && ++pipe.in_sb == pipe.sb_chunks) TRY(pipe_finish_subbatch(c, pipe));
         return PBK_OK;
     };
     if (d_bases_in) {
@@ -443,7 +509,7 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
         }
     } else {
         if (!c->d_stage[0]) {
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < N_STAGE; ++i) {
                 TRY(dev_alloc(c, (void **)&c->d_stage[i], CHUNK_BASES));
                 CK(cudaEventCreateWithFlags(&c->ev_copy_done[i], cudaEventDisableTiming));
                 CK(cudaEventCreateWithFlags(&c->ev_stage_free[i], cudaEventDisableTiming));
@@ -452,7 +518,7 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
         }
         const u64 n_chunks = (n_bases + CHUNK_BASES - 1) / CHUNK_BASES;
         auto enqueue_copy = [&](u64 ci) -> int {
-            const int buf = (int)(ci & 1);
+            const int buf = (int)(ci % N_STAGE);
             const u64 b0 = ci * CHUNK_BASES, nb = std::min(CHUNK_BASES, n_bases - b0);
             CK(cudaStreamWaitEvent(c->s_copy, c->ev_stage_free[buf], 0));
             CK(cudaMemcpyAsync(c->d_stage[buf], h_bases + b0, nb, cudaMemcpyHostToDevice, c->s_copy));
@@ -460,11 +526,11 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
             c->h2d_bytes += nb;
             return PBK_OK;
         };
-        if (n_chunks) TRY(enqueue_copy(0));
+        for (u64 ci = 0; ci < std::min<u64>(n_chunks, N_STAGE - 1); ++ci) TRY(enqueue_copy(ci));
         for (u64 ci = 0; ci < n_chunks; ++ci) {
-            const int buf = (int)(ci & 1);
+            const int buf = (int)(ci % N_STAGE);
             const u64 b0 = ci * CHUNK_BASES, nb = std::min(CHUNK_BASES, n_bases - b0), w0 = b0 / 32, nw = (nb + 31) / 32;
-            if (ci + 1 < n_chunks) TRY(enqueue_copy(ci + 1));       // next copy overlaps this chunk's kernels
+            if (ci + N_STAGE - 1 < n_chunks) TRY(enqueue_copy(ci + N_STAGE - 1));   // copies run ahead of this chunk's kernels
             CK(cudaStreamWaitEvent(c->s_compute, c->ev_copy_done[buf], 0));
             { Span sp(c, LC_PACK); launch_pack(c->d_stage[buf], nb, nw, encoding, stream, nflag, w0, c->d_ctr, c->s_compute); }
             CK(cudaGetLastError());
@@ -490,7 +556,10 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
         dev_free(c, d_np, total_n * 4); dev_free(c, d_npo, (n_reads + 1) * 8);
         TRY(rc);
     }
-    if (partitioned) {
+    if (pipe.on) {
+        CK(cudaGetLastError());
+        TRY(pipe_end(c, pipe));
+    } else if (partitioned) {
         CK(cudaGetLastError());
         TRY(flush_buckets(c));
     }
@@ -506,7 +575,7 @@ void release_all(pbk_ctx *c)
     if (c->s_copy) cudaStreamSynchronize(c->s_copy);
     resolve_spans(c);
     cudaFree(c->d_stream_raw); cudaFree(c->d_nflag_raw); cudaFree(c->d_rflag_raw); cudaFree(c->d_offsets);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < N_STAGE; ++i) {
         cudaFree(c->d_stage[i]);
         if (c->ev_copy_done[i]) cudaEventDestroy(c->ev_copy_done[i]);
         if (c->ev_stage_free[i]) cudaEventDestroy(c->ev_stage_free[i]);
@@ -580,6 +649,7 @@ int pbk_create(pbk_ctx **out, const pbk_config *cfg)
     auto bail = [&](int code) { release_all(c); delete c; return code; };
     if (cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking) != cudaSuccess) return bail(PBK_E_CUDA);
     if (cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking) != cudaSuccess) return bail(PBK_E_CUDA);
+    c->pipeline_enabled = !(cfg->flags & PBK_F_NO_PIPELINE) && getenv("PBK_NO_PIPELINE") == nullptr;
     if (cudaMallocHost((void **)&c->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(PBK_E_NOMEM);
     memset(c->h_ctr, 0, sizeof(Counters));
     if (dev_alloc(c, (void **)&c->d_ctr, sizeof(Counters)) || dev_alloc(c, (void **)&c->d_len_hist, PBK_LEN_BINS * 8) ||
@@ -716,6 +786,8 @@ int pbk_get_stats(const pbk_ctx *cc, pbk_stats *out)
     out->ms_partition = c->ms[LC_PART]; out->ms_insert = c->ms[LC_INSERT];
     out->ms_count = c->ms[LC_COUNT] + c->ms[LC_PART] + c->ms[LC_INSERT];
     out->h2d_bytes = c->h2d_bytes; out->d2h_bytes = c->d2h_bytes;
+    out->ms_count_elapsed = out->ms_count;         // all counting launches are serial on one stream
+    out->n_pipelined_batches = c->n_pipelined;
     return PBK_OK;
 }
 

@@ -90,10 +90,11 @@ void launch_insert_records(const u64 *records, u64 n, bool weighted, TableView t
 constexpr size_t PART_SMEM_BUDGET = 100 * 1024;      // bins; two CTAs per SM (227 KB) so one computes while one flushes
 constexpr u64 PART_REGION_BYTES = 4ull << 20;        // table bytes per bucket (measured on C1: 4 MB beats 16 MB in both passes)
 
-PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words)
+PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words, size_t smem_budget)
 {
     PartitionPlan p{};
-    const u64 entries = PART_SMEM_BUDGET / (8 * (size_t)words);
+    if (smem_budget == 0) smem_budget = PART_SMEM_BUDGET;
+    const u64 entries = smem_budget / (8 * (size_t)words);
     const u64 region_bytes = getenv("PBK_REGION_MB") ? (u64)atoi(getenv("PBK_REGION_MB")) << 20 : PART_REGION_BYTES;
     u64 P = (est_table_bytes + region_bytes - 1) / region_bytes;
     P = std::max<u64>(P, 8);
@@ -196,6 +197,33 @@ void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *counts, v
 #undef PBK_CASE_W
     default: break;
     }
+}
+
+// device-chained variant for k <= 32: tile map built by a kernel from the cursors, Pass B launched on `st_insert`
+// right behind it (the caller orders the two streams with events)
+void launch_passb_desc(const u64 *d_cursor, u64 seg_cap, u32 n_buckets, TableView table, TableView remote, ShardInfo shard,
+                       void *d_desc, cudaStream_t st)
+{
+    const int pf_dist = getenv("PBK_PF_DIST") ? atoi(getenv("PBK_PF_DIST")) : 1;
+    passb_desc_kernel<<<1, PART_MAX_BUCKETS, 0, st>>>(d_cursor, seg_cap, n_buckets, (u32)PASSB1_TILE_KEYS, (const char *)table.slots,
+        table.cap, shard.n_shards > 1 ? (const char *)remote.slots : nullptr, remote.cap, (u32)table.slot_bytes(), pf_dist,
+        (u64 *)d_desc, (PassBBucket *)((char *)d_desc + 16));
+}
+
+void launch_bucket_insert_chained(const u64 *bkt_keys, u64 seg_cap, const void *d_desc, u32 n_buckets, TableView table,
+                                  TableView remote, ShardInfo shard, Counters *ctr, u64 *overflow_keys, u64 overflow_cap,
+                                  int sm_count, int ctas_per_sm, cudaStream_t st)
+{
+    const PassBBucket *d_bk = (const PassBBucket *)((const char *)d_desc + 16);
+    const u32 opts = getenv("PBK_PASSB_HINT") ? (u32)atoi(getenv("PBK_PASSB_HINT")) : 1u;
+    const int grid = sm_count * ctas_per_sm;                    // CTAs that find no tile left leave at once
+    if (shard.n_shards > 1)
+        bucket_insert_compact_kernel<true><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, 0, n_buckets, (u64 *)d_desc,
+            Table<1>(table.slots, table.cap), Table<1>(remote.slots, remote.cap), shard.n_shards, shard.rank, ctr,
+            overflow_keys, overflow_cap, opts);
+    else
+        bucket_insert_compact_kernel<false><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, 0, n_buckets, (u64 *)d_desc,
+            Table<1>(table.slots, table.cap), Table<1>(remote.slots, remote.cap), 1, 0, ctr, overflow_keys, overflow_cap, opts);
 }
 
 void launch_table_init(TableView t, cudaStream_t st)

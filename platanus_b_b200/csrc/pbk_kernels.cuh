@@ -50,7 +50,7 @@ struct PartitionPlan {
     u64    seg_cap;     // entries per bucket segment in the bucket store
 };
 // shared-memory budget -> bucket count / bin size / CTA size for keys of `words` words
-PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words);
+PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words, size_t smem_budget = 0);
 // Pass A over stream words [word_begin, word_end): keys go to bkt_keys (P segments of seg_cap entries)
 void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
                       int words, const PartitionPlan &plan, u64 *bkt_keys, u64 *bkt_cursor, Counters *ctr,
@@ -61,6 +61,13 @@ size_t passb_desc_bytes(u32 n_buckets);
 void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *counts, void *h_desc, void *d_desc,
                           u32 b_first, u32 b_end, u32 n_buckets, TableView table, TableView remote, ShardInfo shard,
                           Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st);
+
+// k <= 32, device-chained: build the tile map from the cursors on the GPU (stream `st`), then Pass B over all buckets
+void launch_passb_desc(const u64 *d_cursor, u64 seg_cap, u32 n_buckets, TableView table, TableView remote, ShardInfo shard,
+                       void *d_desc, cudaStream_t st);
+void launch_bucket_insert_chained(const u64 *bkt_keys, u64 seg_cap, const void *d_desc, u32 n_buckets, TableView table,
+                                  TableView remote, ShardInfo shard, Counters *ctr, u64 *overflow_keys, u64 overflow_cap,
+                                  int sm_count, int ctas_per_sm, cudaStream_t st);
 
 // ---- table ------------------------------------------------------------------------------------
 void launch_table_init(TableView t, cudaStream_t st);

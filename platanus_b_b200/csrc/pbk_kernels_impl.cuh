@@ -539,6 +539,54 @@ bucket_insert_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const PassBB
     }
 }
 
+// Tile map of a Pass B launch built on the device from the bucket cursors, so that Pass A and Pass B of a
+// sub-batch can be chained on the GPU without a host round trip (the host-built variant is
+// launch_bucket_insert in pbk_kernels.cu).  One CTA.
+__device__ __forceinline__ void passb_region(const char *slots, u64 cap, u32 slot_bytes, u32 pb, u32 n_buckets,
+                                             const char **base, u32 *lines)
+{
+    *base = nullptr; *lines = 0;
+    if (!slots || pb >= n_buckets) return;
+    const u64 s0 = cap * pb / n_buckets;                       // cap < 2^40, pb < 2^9: no overflow
+    u64 s1 = cap * (pb + 1) / n_buckets + 128;
+    if (s1 > cap) s1 = cap;
+    *lines = (u32)(((s1 - s0) * slot_bytes + 127) / 128);
+    *base = slots + s0 * slot_bytes;
+}
+
+__global__ void __launch_bounds__(PART_MAX_BUCKETS)
+passb_desc_kernel(const u64 *__restrict__ cursor, u64 seg_cap, u32 n_buckets, u32 tile_keys, const char *tab, u64 tab_cap,
+                  const char *rtab, u64 rtab_cap, u32 slot_bytes, int pf_dist, u64 *ticket, PassBBucket *out)
+{
+    __shared__ u64 s_tiles[PART_MAX_BUCKETS + 1];
+    for (u32 b = threadIdx.x; b < n_buckets; b += blockDim.x) {
+        const u64 n = min(cursor[b], seg_cap);
+        PassBBucket d;
+        d.tile_start = 0; d.n_keys = n;
+        d.pf_base = d.pf_base2 = nullptr; d.pf_lines = d.pf_lines2 = 0;
+        if (pf_dist > 0 && n) {
+            passb_region(tab, tab_cap, slot_bytes, b + pf_dist, n_buckets, &d.pf_base, &d.pf_lines);
+            passb_region(rtab, rtab_cap, slot_bytes, b + pf_dist, n_buckets, &d.pf_base2, &d.pf_lines2);
+        }
+        out[b] = d;
+        s_tiles[b] = (n + tile_keys - 1) / tile_keys;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 tiles = 0;
+        for (u32 b = 0; b < n_buckets; ++b) { const u64 t = s_tiles[b]; s_tiles[b] = tiles; tiles += t; }
+        s_tiles[n_buckets] = tiles;
+        ticket[0] = 0; ticket[1] = 0;
+    }
+    __syncthreads();
+    for (u32 b = threadIdx.x; b < n_buckets; b += blockDim.x) out[b].tile_start = s_tiles[b];
+    if (threadIdx.x == 0) {
+        PassBBucket e;
+        e.tile_start = s_tiles[n_buckets]; e.n_keys = 0; e.pf_base = e.pf_base2 = nullptr; e.pf_lines = e.pf_lines2 = 0;
+        out[n_buckets] = e;
+    }
+}
+
 // Pass B for one-word keys (k <= 32).  The bucket store holds h = fmix64(key), so a key costs one
 // streamed 8-byte load, one 64-bit atomic add on its home slot and a three-instruction test of the
 // returned word.  What does not finish there -- the home slot belongs to another key, or it is claimed
@@ -670,7 +718,8 @@ bucket_insert_compact_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, cons
                              u32 b_first, u32 b_end, u64 *ticket, Table<1> table, Table<1> remote, u32 n_shards,
                              u32 rank, Counters *ctr, u64 *ovf, u64 ovf_cap, u32 opts)
 {
-    __shared__ PassBBucket s_bk[PART_MAX_BUCKETS + 1];
+    // (the bucket descriptors are read straight from global memory: a few cached loads per 8192-key tile, and the
+    //  shared memory they would take is what lets two of these CTAs share an SM with two Pass A CTAs)
     __shared__ u64 s_ticket[2];
     __shared__ u64 s_def_h[PASSB_THREADS / 32][PASSB1_DEF_CAP];
     __shared__ uint16_t s_def_m[PASSB_THREADS / 32][PASSB1_DEF_CAP];
@@ -681,23 +730,22 @@ bucket_insert_compact_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, cons
     u32 n_def = 0;
     const u32 def_room = nthreads < 32u ? 1u : 32u;              // a round may only start with at most one batch listed
     const u32 round_keys = nthreads * PASSB1_KPT, tile_keys = round_keys * PASSB1_ROUNDS;
-    for (u32 i = tid; i <= nb; i += nthreads) s_bk[i] = bk[i];
     if (tid == 0) { s_ticket[0] = atomicAdd(ticket, 1ull); s_ticket[1] = atomicAdd(ticket, 1ull); }
     __syncthreads();
-    const u64 n_tiles = s_bk[nb].tile_start;
+    const u64 n_tiles = bk[nb].tile_start;
     const u64 keep = (opts & 1u) ? l2_keep_policy() : 0ull;      // 0 = plain atomics (a real policy word is never 0)
     u32 newk = 0, newr = 0, lb = 0;
     int par = 0;
     u64 t = s_ticket[0];
     while (t < n_tiles) {
-        while (s_bk[lb + 1].tile_start <= t) ++lb;
-        const u64 j = t - s_bk[lb].tile_start, n = s_bk[lb].n_keys;
-        const u64 nt = s_bk[lb + 1].tile_start - s_bk[lb].tile_start;
+        while (bk[lb + 1].tile_start <= t) ++lb;
+        const u64 j = t - bk[lb].tile_start, n = bk[lb].n_keys;
+        const u64 nt = bk[lb + 1].tile_start - bk[lb].tile_start;
         const u64 t_next = s_ticket[par ^ 1];                    // fetched one iteration ago
         __syncthreads();                                         // everyone has read both tickets
         if (tid == 0) s_ticket[par] = atomicAdd(ticket, 1ull);   // ticket for the tile after next
-        if (s_bk[lb].pf_base) passb_prefetch(s_bk[lb].pf_base, s_bk[lb].pf_lines, j, nt, tid, nthreads);
-        if (SHARDED && s_bk[lb].pf_base2) passb_prefetch(s_bk[lb].pf_base2, s_bk[lb].pf_lines2, j, nt, tid, nthreads);
+        if (bk[lb].pf_base) passb_prefetch(bk[lb].pf_base, bk[lb].pf_lines, j, nt, tid, nthreads);
+        if (SHARDED && bk[lb].pf_base2) passb_prefetch(bk[lb].pf_base2, bk[lb].pf_lines2, j, nt, tid, nthreads);
         const u64 *src = bkt_hash + (u64)(b_first + lb) * seg_cap + j * tile_keys;
         const u64 left = n - j * tile_keys;                      // > 0 by construction of the tile numbering
         if (left >= tile_keys) {

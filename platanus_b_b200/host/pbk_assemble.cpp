@@ -37,7 +37,7 @@ struct Options {
     Options()
     {
         single["-o"] = "out"; single["-k"] = "32"; single["-K"] = "0.5"; single["-s"] = "10"; single["-n"] = "0";
-        single["-c"] = "2"; single["-a"] = "10.0"; single["-u"] = "0"; single["-d"] = "0.5"; single["-e"] = "";
+        single["-c"] = "1"; single["-a"] = "10.0"; single["-u"] = "0"; single["-d"] = "0.5"; single["-e"] = "";
         single["-t"] = "1"; single["-m"] = "16"; single["-tmp"] = ".";
         multi["-f"] = std::vector<std::string>();
         flag["-kmer_occ_only"] = false; flag["-repeat"] = false;

@@ -318,3 +318,32 @@ def test_error_behaviour():
         assert len(counts) == 1 and int(counts[0]) == 65534 and int(keys[0, 0]) == 0   # saturated poly-A
         with pytest.raises(PbkError):
             kc.push_reads(ok, np.array([0, 10], np.uint64))            # push after finalize
+
+
+def test_pipelined_pass_overlap_gives_the_identical_table(oracle):
+    """k <= 32, >= 4 chunks, new-key ratio known from an earlier batch: Pass B of a sub-batch runs on a second stream
+    while Pass A of the next one runs (pbk_api.cu, `Pipe`).  Same reads through the serial and the pipelined path."""
+    rs = synth.make_reads(synth.config("C1", scale=0.3))
+    b, o = rs.flat()
+    with KmerCounter(32, timing=True) as kc:
+        kc.push_reads(b, o)                                   # first large batch of the context: serial, with pilot
+        kc.finalize()
+        assert kc.stats()["n_pipelined_batches"] == 0
+        first = kc.export(1, sorted=True) + (kc.occ_hist.copy(), kc.n_instances)
+        kc.reset()
+        kc.push_reads(b, o)                                   # now pipelined
+        kc.finalize()
+        st = kc.stats()
+        assert st["n_pipelined_batches"] == 1 and st["ms_count_elapsed"] > 0
+        second = kc.export(1, sorted=True) + (kc.occ_hist.copy(), kc.n_instances)
+    for x, y in zip(first[:3], second[:3]):
+        assert np.array_equal(x, y)
+    assert first[3] == second[3]
+    with KmerCounter(32, pipeline=False) as kc:
+        kc.push_reads(b, o)
+        kc.reset()
+        kc.push_reads(b, o)
+        kc.finalize()
+        assert kc.stats()["n_pipelined_batches"] == 0
+        k3, c3 = kc.export(1, sorted=True)
+    assert np.array_equal(k3, first[0]) and np.array_equal(c3, first[1])
