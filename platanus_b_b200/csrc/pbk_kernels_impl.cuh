@@ -322,6 +322,16 @@ __device__ __forceinline__ void bucket_append_direct(const u64 *key, u32 b, u64 
     }
 }
 
+// OR of x << j for j in [0, w), 0 <= w <= 32 (doubling: at most five shift/or steps)
+__device__ __forceinline__ u64 smear_up(u64 x, int w)
+{
+    if (w <= 0) return 0;
+    u64 r = x;
+    int s = 1;
+    while (2 * s <= w) { r |= r << s; s *= 2; }
+    return r | (r << (w - s));
+}
+
 // Pass A.  One thread owns one stream word (32 window ends), exactly like count_kernel, but instead of
 // touching the table it drops the canonical key into its bucket's shared-memory bin; full tiles are
 // then flushed warp-per-bucket with coalesced stores.
@@ -340,13 +350,44 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
     // (wsize is 32 on the GPU; tests/cpu_emul runs the kernel as a single one-lane "warp")
     const int wsize = blockDim.x < 32 ? (int)blockDim.x : 32;
     const int lane = threadIdx.x % wsize, warp = threadIdx.x / wsize, n_warps = blockDim.x / wsize;
+    // bucket = top log2(P) hash bits when P is a power of two (0 = use the generic mulhi form)
+    const int pshift = (n_buckets > 1 && (n_buckets & (n_buckets - 1)) == 0) ? 64 - (31 - __clz(n_buckets)) : 0;
     u64 inst = 0;
 
     for (u64 tile = word_begin + (u64)blockIdx.x * blockDim.x; tile < word_end; tile += (u64)gridDim.x * blockDim.x) {
         for (u32 b = threadIdx.x; b < n_buckets; b += blockDim.x) scount[b] = 0;
         __syncthreads();
         const u64 wi = tile + threadIdx.x;
-        if (wi < word_end) {
+        if (W == 1 && pshift && wi < word_end) {
+            // One-word keys and a power-of-two bucket count: the hot configuration (k <= 32).  Fully unrolled so that every shift is an immediate;
+            // which of the 32 windows are usable is worked out once per word with bit smears instead of a running
+            // counter: the window ending at position i is usable iff none of its k positions is an N and none of
+            // its last k-1 positions starts a read (flags of this and the previous word; bit j = position j).
+            const u64 cur = stream[wi];
+            const u64 nn = ((u64)nflag[wi] << 32) | nflag[wi - 1], rr = ((u64)rflag[wi] << 32) | rflag[wi - 1];
+            const u32 valid = ~(u32)((smear_up(nn, k) | smear_up(rr, k - 1)) >> 32);
+            if (valid) {
+                const u64 topmul = 1ull << top_shift;
+                u32 n_here = 0;
+                u64 f = stream[wi - 1], r = pair_reverse64(~f);
+                r = s ? (r >> s) : r;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const u32 b = (u32)(cur >> (62 - 2 * i)) & 3u;
+                    f = ((f << 2) | b) & top_mask;
+                    r = (r >> 2) | ((u64)(3u - b) * topmul);
+                    if ((valid >> i) & 1u) {
+                        const u64 hh = fmix64(r < f ? r : f);        // key = min(forward, reverse), counter.h:429
+                        const u32 bkt = (u32)(hh >> pshift);          // == mulhi(hh, n_buckets) for a power of two
+                        ++n_here;
+                        const u32 pos = atomicAdd(&scount[bkt], 1u);
+                        if (pos < bin_cap) bins[bkt * bin_cap + pos] = hh;
+                        else bucket_append_direct<W>(&hh, bkt, bkt_keys, seg_cap, bkt_cursor, ovf, ovf_cap, ctr);
+                    }
+                }
+                inst += n_here;
+            }
+        } else if (wi < word_end) {
             const u64 cur = stream[wi];
             const u32 nf = nflag[wi], rf = rflag[wi];
             int run = k;

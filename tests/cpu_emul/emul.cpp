@@ -52,7 +52,7 @@ static int run(const uint8_t *bases, const u64 *off, u64 n_reads, int k, int enc
                         ovf.data(), OVF);
     } else {
         // Pass A into P buckets with deliberately tiny bins/segments so the direct-append and spill paths run too
-        const u32 P = 7, bin_cap = 3;
+        const u32 P = (k & 1) ? 7 : 8, bin_cap = 3;     // odd k: generic bucket function, even k: the power-of-two shift
         const u64 seg_cap = std::max<u64>(4, n_bases / P * 3 / 4);
         std::vector<u64> bkt((u64)P * seg_cap * W, 0), cursor(P, 0);
         partition_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
