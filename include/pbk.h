@@ -59,7 +59,7 @@ enum {
     PBK_F_TIMING = 1u << 0,       /* bracket every kernel launch with CUDA events (see pbk_get_stats) */
     PBK_F_NO_PARTITION = 1u << 1, /* always insert straight into the table (no hash-range bucket pass)  */
     PBK_F_FORCE_PARTITION = 1u << 2, /* use the bucket pass even for tiny batches (tests)              */
-    PBK_F_NO_PIPELINE = 1u << 3   /* host input: one Pass B per batch instead of one per group of chunks */
+    PBK_F_NO_PIPELINE = 1u << 3   /* always size the table with a pilot launch and host round trips      */
 };
 
 typedef struct pbk_config {
@@ -95,7 +95,7 @@ typedef struct pbk_stats {
     double   ms_partition;       /* parts of ms_count                                                          */
     double   ms_insert;
     double   ms_count_elapsed;   /* counting phase, begin to end (= ms_count: the launches are serial)          */
-    uint64_t n_pipelined_batches;/* host-input pushes counted in sub-batches behind the H2D copies             */
+    uint64_t n_pipelined_batches;/* pushes whose Pass A / tile map / Pass B were chained on the GPU (no host sync) */
 } pbk_stats;
 
 const char *pbk_strerror(int status);

@@ -15,7 +15,7 @@ NVCC = os.environ.get("PBK_NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = (["-DPBK_EXPERIMENT"] if os.environ.get("PBK_EXPERIMENT") else []) + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
 UNITS = ["pbk_kernels.cu", "pbk_api.cu", "pbk_host.cpp"]
-HEADERS = ["pbk_device.cuh", "pbk_kernels.cuh", os.path.join("..", "..", "include", "pbk.h")]
+HEADERS = ["pbk_device.cuh", "pbk_kernels.cuh", "pbk_kernels_impl.cuh", os.path.join("..", "..", "include", "pbk.h")]
 
 
 def _stale(target: str, deps: list) -> bool:

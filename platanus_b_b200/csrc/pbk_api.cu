@@ -472,14 +472,15 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
 
     const bool deferred_count = (encoding == PBK_ENC_PLATANUS);     // N flags arrive after all packs
     const bool partitioned = c->partition_enabled && (windows_ub >= PART_MIN_WINDOWS || (c->partition_forced && windows_ub > 0));
-    // Sub-batched: host input only (it exists to hide the passes behind the H2D copies), the compact kernel (k <= 32), a
-    // measured new-key ratio to size the table up front (the first large batch of a context takes the other path,
-    // with its pilot launch) and at least four chunks.
+    // Chained (k <= 32, new-key ratio known from an earlier batch of this context, so the table can be sized up front;
+    // the first large batch takes the other path with its pilot launch): Pass A per chunk, then a device-built tile map
+    // and Pass B, all queued without a host round trip.  Host input is counted in up to four such groups of chunks so
+    // that only the last group's Pass B is left when the last H2D copy lands; device-resident input in one group.
     const u64 n_chunks_total = (n_bases + CHUNK_BASES - 1) / CHUNK_BASES;
     Pipe pipe;
-    pipe.on = partitioned && c->pipeline_enabled && h_bases != nullptr && !d_bases_in && c->W == 1 && c->ratio_known && n_chunks_total >= 4;
+    pipe.on = partitioned && c->pipeline_enabled && c->W == 1 && c->ratio_known;
     if (pipe.on) {
-        const u32 n_sb = (u32)std::min<u64>(4, n_chunks_total / 2);
+        const u32 n_sb = (h_bases != nullptr && n_chunks_total >= 4) ? (u32)std::min<u64>(4, n_chunks_total / 2) : 1u;
         pipe.sb_chunks = (u32)((n_chunks_total + n_sb - 1) / n_sb);
         const u64 sb_windows = std::min<u64>(windows_ub, (u64)pipe.sb_chunks * CHUNK_BASES);
         TRY(maybe_clamp(c, windows_ub));

@@ -88,12 +88,12 @@ void launch_insert_records(const u64 *records, u64 n, bool weighted, TableView t
 
 // ---- partitioned counting -------------------------------------------------------------------------
 constexpr size_t PART_SMEM_BUDGET = 100 * 1024;      // bins; two CTAs per SM (227 KB) so one computes while one flushes
-constexpr u64 PART_REGION_BYTES = 4ull << 20;        // table bytes per bucket (measured on C1: 4 MB beats 16 MB in both passes)
+constexpr u64 PART_REGION_BYTES = 16ull << 20;       // table bytes per bucket: Pass B is flat from 4 to 32 MB, Pass A prefers few, large bins
 
 PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words, size_t smem_budget)
 {
     PartitionPlan p{};
-    if (smem_budget == 0) smem_budget = PART_SMEM_BUDGET;
+    if (smem_budget == 0) smem_budget = getenv("PBK_PART_SMEM_KB") ? (size_t)atoi(getenv("PBK_PART_SMEM_KB")) * 1024 : PART_SMEM_BUDGET;
     const u64 entries = smem_budget / (8 * (size_t)words);
     const u64 region_bytes = getenv("PBK_REGION_MB") ? (u64)atoi(getenv("PBK_REGION_MB")) << 20 : PART_REGION_BYTES;
     u64 P = (est_table_bytes + region_bytes - 1) / region_bytes;
@@ -126,7 +126,8 @@ void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64
 {
     if (word_end <= word_begin) return;
     const u64 tiles = (word_end - word_begin + plan.threads - 1) / plan.threads;
-    const int grid = (int)std::min<u64>(tiles, (u64)sm_count * 2);
+    const int ctas = std::max(1, std::min(8, (int)((220 * 1024) / (plan.smem + 7 * 1024))));     // resident CTAs per SM
+    const int grid = (int)std::min<u64>(tiles, (u64)sm_count * ctas);
     PBK_DISPATCH_W(words,
         (partition_launch_w<W>(stream, nflag, rflag, word_begin, word_end, k, plan, bkt_keys, bkt_cursor, ctr,
                                overflow_keys, overflow_cap, grid, st)));

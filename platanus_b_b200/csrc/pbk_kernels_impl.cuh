@@ -343,13 +343,14 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
 {
     PBK_DYN_SMEM(u64, bins);                          // n_buckets * bin_cap * W words
     __shared__ u32 scount[PART_MAX_BUCKETS];
+    __shared__ u64 sbase[PART_MAX_BUCKETS];
     const int top_shift = 2 * ((k - 1) & 31);
     const u64 top_mask = (k & 31) ? ((1ull << (2 * (k & 31))) - 1ull) : ~0ull;
     const int s = 2 * (32 * W - k);
     const int nb = (k + 30) >> 5;
     // (wsize is 32 on the GPU; tests/cpu_emul runs the kernel as a single one-lane "warp")
     const int wsize = blockDim.x < 32 ? (int)blockDim.x : 32;
-    const int lane = threadIdx.x % wsize, warp = threadIdx.x / wsize, n_warps = blockDim.x / wsize;
+    const int lane = threadIdx.x % wsize;
     // bucket = top log2(P) hash bits when P is a power of two (0 = use the generic mulhi form)
     const int pshift = (n_buckets > 1 && (n_buckets & (n_buckets - 1)) == 0) ? 64 - (31 - __clz(n_buckets)) : 0;
     u64 inst = 0;
@@ -371,6 +372,7 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
                 u32 n_here = 0;
                 u64 f = stream[wi - 1], r = pair_reverse64(~f);
                 r = s ? (r >> s) : r;
+                // (interleaving four windows' hash chains by hand was measured: slower -- more registers, no gain)
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const u32 b = (u32)(cur >> (62 - 2 * i)) & 3u;
@@ -443,28 +445,30 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
             }
         }
         __syncthreads();
-        // flush: a warp takes wsize buckets at a time, reserves all their segments with one atomic per
-        // lane (all in flight together), then copies bin after bin with coalesced stores
-        for (u32 b0 = warp * wsize; b0 < n_buckets; b0 += n_warps * wsize) {
-            const u32 mine = b0 + lane;
-            u32 n_mine = 0;
-            u64 g_mine = 0;
-            if (mine < n_buckets) {
-                n_mine = min(scount[mine], bin_cap);
-                if (n_mine) g_mine = atomicAdd(&bkt_cursor[mine], (u64)n_mine);
-            }
-            for (int t = 0; t < wsize && b0 + t < n_buckets; ++t) {
-                const u32 n = __shfl_sync(0xffffffffu, n_mine, t);
-                const u64 g = __shfl_sync(0xffffffffu, g_mine, t);
-                const u32 b = b0 + t;
-                for (u32 i = lane; i < n * W; i += wsize) {
-                    const u64 e = g + i / W;                 // entry index inside the bucket segment
-                    if (e < seg_cap) st_stream_u64(&bkt_keys[((u64)b * seg_cap) * W + (g * W + i)], bins[(u64)b * bin_cap * W + i]);
-                    else if (i % W == 0) {
-                        u64 key[W];
-#pragma unroll
-                        for (int j = 0; j < W; ++j) key[j] = bins[(u64)b * bin_cap * W + i + j];
-                        spill_stored<W>(key, ctr, ovf, ovf_cap);
+        // flush, step 1: one thread per bucket reserves the bin's place in the bucket segment (all atomics of the
+        // tile in flight together); step 2: a group of 16 lanes per bucket copies the bin with coalesced stores
+        // (a bin holds ~27 keys: groups of 16 keep most lanes busy, a whole warp per bucket did not)
+        for (u32 b = threadIdx.x; b < n_buckets; b += blockDim.x) {
+            const u32 n = min(scount[b], bin_cap);
+            scount[b] = n;
+            sbase[b] = n ? atomicAdd(&bkt_cursor[b], (u64)n) : 0ull;
+        }
+        __syncthreads();
+        {
+            const u32 gs = blockDim.x < 16u ? blockDim.x : 16u;
+            const u32 gl = threadIdx.x % gs, n_groups = blockDim.x / gs;
+            for (u32 b = threadIdx.x / gs; b < n_buckets; b += n_groups) {
+                const u32 n = scount[b];
+                if (n == 0) continue;
+                const u64 g = sbase[b];
+                const u64 *src = bins + (u64)b * bin_cap * W;
+                u64 *dst = bkt_keys + ((u64)b * seg_cap + g) * W;
+                if (g + n <= seg_cap) {                              // the whole bin fits: plain coalesced copy
+                    for (u32 i = gl; i < n * W; i += gs) st_stream_u64(dst + i, src[i]);
+                } else {
+                    for (u32 i = gl; i < n * W; i += gs) {
+                        if (g + i / W < seg_cap) st_stream_u64(dst + i, src[i]);
+                        else if (i % W == 0) spill_stored<W>(src + i, ctr, ovf, ovf_cap);   // bucket segment full
                     }
                 }
             }

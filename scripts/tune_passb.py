@@ -20,7 +20,7 @@ db = torch.from_numpy(b.copy()).cuda()
 do = torch.from_numpy(o.astype(np.int64)).cuda()
 torch.cuda.synchronize()
 n_reads, n_bases = len(o) - 1, len(b)
-grid = json.loads(os.environ.get("TUNE_GRID", '{"PBK_REGION_MB": [4, 8, 16, 32, 64], "PBK_PF_DIST": [0, 1], "PBK_PASSB_HINT": [0, 1], "PBK_PASSB_CTAS": [3]}'))
+grid = json.loads(os.environ.get("TUNE_GRID", '{"PBK_REGION_MB": [4, 8, 16, 32, 64], "PBK_PF_DIST": [0, 1], "PBK_PASSB_HINT": [0, 1], "PBK_PASSB_CTAS": [3], "PBK_PART_SMEM_KB": [100]}'))
 names = sorted(grid)
 out = open("gpurun_out/tune_passb.jsonl", "a")
 kc = KmerCounter(32, timing=True)
