@@ -480,7 +480,8 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
     Pipe pipe;
     pipe.on = partitioned && c->pipeline_enabled && c->W == 1 && c->ratio_known;
     if (pipe.on) {
-        const u32 n_sb = (h_bases != nullptr && n_chunks_total >= 4) ? (u32)std::min<u64>(4, n_chunks_total / 2) : 1u;
+        const u32 max_sb = getenv("PBK_N_SB") ? (u32)atoi(getenv("PBK_N_SB")) : 4u;
+        const u32 n_sb = (h_bases != nullptr && n_chunks_total >= 4) ? (u32)std::max<u64>(1, std::min<u64>(max_sb, n_chunks_total / 2)) : 1u;
         pipe.sb_chunks = (u32)((n_chunks_total + n_sb - 1) / n_sb);
         const u64 sb_windows = std::min<u64>(windows_ub, (u64)pipe.sb_chunks * CHUNK_BASES);
         TRY(maybe_clamp(c, windows_ub));
@@ -831,7 +832,8 @@ int pbk_reset(pbk_ctx *c, uint32_t k)
     c->k = k; c->W = W;
     CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), c->s_compute));
     CK(cudaMemsetAsync(c->d_len_hist, 0, PBK_LEN_BINS * 8, c->s_compute));
-    CK(cudaStreamSynchronize(c->s_compute));
+    // (no synchronize here: everything that follows is ordered on s_compute, and the next push's H2D copies on the
+    //  copy stream only touch the staging buffers, so they may run while the table is still being cleared)
     c->last = Counters{}; c->occupied = c->occupied_remote = 0; c->inst_since_clamp = 0;
     c->n_reads = c->n_bases = 0; c->finalized = false; c->h_occ_hist.clear();
     return PBK_OK;

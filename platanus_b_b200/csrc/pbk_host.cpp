@@ -133,15 +133,31 @@ int pbk_write_kmer_occ_bin(const char *path, uint32_t k, const uint64_t *keys, c
     const u64 shifter = index_length >= 32 ? 0 : 2 * index_length;       // doubleHash.h:233-235
 
     std::vector<u64> bitmap((slots + 63) / 64, 0), slot(n), idx(n);
-    for (u64 i = 0; i < n; ++i) {
+    // the home slots are effectively random positions in a bitmap far larger than the caches: compute them a few
+    // keys ahead and prefetch, so the placement loop does not pay one DRAM miss per key
+    auto home_and_step = [&](u64 i, u64 *step) -> u64 {
         const uint64_t *key = keys + i * words;
         u64 h = 0, s = 0;                                                // makeHashKey / reHashKey
         for (unsigned j = 0; j < words; ++j) {
             h += key[j] + (key[j] >> index_length) + (key[j] >> shifter);
             s += ~key[j] ^ (key[j] >> index_length) ^ (key[j] >> shifter);
         }
-        u64 v = h & index_size;
-        const u64 step = s | 1;
+        *step = s | 1;
+        return h & index_size;
+    };
+    const u64 AHEAD = 32;
+    u64 ring_v[AHEAD], ring_s[AHEAD];
+    for (u64 i = 0; i < std::min<u64>(AHEAD, n); ++i) {
+        ring_v[i] = home_and_step(i, &ring_s[i]);
+        __builtin_prefetch(&bitmap[ring_v[i] >> 6], 1);
+    }
+    for (u64 i = 0; i < n; ++i) {
+        u64 v = ring_v[i % AHEAD];
+        const u64 step = ring_s[i % AHEAD];
+        if (i + AHEAD < n) {
+            ring_v[i % AHEAD] = home_and_step(i + AHEAD, &ring_s[i % AHEAD]);
+            __builtin_prefetch(&bitmap[ring_v[i % AHEAD] >> 6], 1);
+        }
         while (bitmap[v >> 6] >> (v & 63) & 1) v = (v + step) & index_size;   // find_any, keys are distinct
         bitmap[v >> 6] |= 1ull << (v & 63);
         slot[i] = v; idx[i] = i;

@@ -885,56 +885,78 @@ __global__ void __launch_bounds__(256) histogram_kernel(Table<W> t, u64 *occ_his
         if (sh[i]) atomicAdd(&occ_hist[i], (u64)sh[i]);
 }
 
+// Compaction of the entries with count >= min_count.  Output positions are reserved per CTA chunk (shared-memory
+// counter, one global atomic per chunk): a warp-level reservation on the single global counter serialises millions of
+// same-address atomics when the table is large.
 template <int W>
 __global__ void __launch_bounds__(256)
 export_kernel(Table<W> t, u32 min_count, u64 *keys_out, uint16_t *counts_out, u64 capacity, u64 *d_n_out)
 {
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31;
-    const u64 n_round = (t.cap + 31) & ~31ull;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        u64 key[W];
-        u32 count = 0;
-        bool keep = false;
-        if (i < t.cap) keep = t.load(i, key, &count) && count >= min_count;
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (m == 0) continue;
-        const int leader = __ffs(m) - 1;
-        u64 base = 0;
-        if (lane == leader) base = atomicAdd(d_n_out, (u64)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (keep) {
-            const u64 at = base + __popc(m & ((1u << lane) - 1u));
+    __shared__ u32 s_n;
+    __shared__ u64 s_base;
+    constexpr int PER_THREAD = 8;
+    const u64 chunk = (u64)blockDim.x * PER_THREAD;
+    for (u64 c0 = (u64)blockIdx.x * chunk; c0 < t.cap; c0 += (u64)gridDim.x * chunk) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        u64 key[PER_THREAD][W];
+        u32 count[PER_THREAD], rank[PER_THREAD];
+#pragma unroll
+        for (int q = 0; q < PER_THREAD; ++q) {
+            const u64 i = c0 + (u64)q * blockDim.x + threadIdx.x;
+            rank[q] = 0xFFFFFFFFu; count[q] = 0;
+            if (i < t.cap && t.load(i, key[q], &count[q]) && count[q] >= min_count) rank[q] = atomicAdd(&s_n, 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = s_n ? atomicAdd(d_n_out, (u64)s_n) : 0ull;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PER_THREAD; ++q) {
+            if (rank[q] == 0xFFFFFFFFu) continue;
+            const u64 at = s_base + rank[q];
             if (at < capacity) {
 #pragma unroll
-                for (int j = 0; j < W; ++j) keys_out[at * W + j] = key[j];
-                counts_out[at] = (uint16_t)count;
+                for (int j = 0; j < W; ++j) keys_out[at * W + j] = key[q][j];
+                counts_out[at] = (uint16_t)count[q];
             }
         }
+        __syncthreads();
     }
 }
+
+// Per-destination counts / record packing of the remote-staging table.  With few destinations nearly every warp
+// would hit the same one or two global counters (measured at N = 2: 10 ms of serialised same-address atomics per
+// step), so both kernels aggregate per CTA in shared memory first: cheap shared-memory atomics per entry, one global
+// atomic per destination per CTA (count) or per CTA chunk (pack).
+constexpr u32 SHARD_SMEM_MAX = 1024;                 // destinations handled through shared memory
 
 template <int W>
 __global__ void __launch_bounds__(256)
 shard_count_kernel(Table<W> t, u32 n_shards, u64 *d_counts)
 {
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31;
-    const u64 n_round = (t.cap + 31) & ~31ull;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        bool occ = false;
-        u32 dest = 0;
-        if (i < t.cap) {
+    __shared__ u32 s_cnt[SHARD_SMEM_MAX];
+    const bool use_smem = n_shards <= SHARD_SMEM_MAX;
+    if (use_smem) for (u32 i = threadIdx.x; i < n_shards; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    // contiguous range per CTA, so that a CTA's partial counts stay below 2^32
+    const u64 per_cta = (t.cap + gridDim.x - 1) / gridDim.x;
+    const u64 lo = (u64)blockIdx.x * per_cta, hi = min(t.cap, lo + per_cta);
+    for (u64 i0 = lo; i0 < hi; i0 += (u64)blockDim.x << 20) {          // flush before a counter could wrap
+        const u64 i1 = min(hi, i0 + ((u64)blockDim.x << 20));
+        for (u64 i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
             u64 key[W];
             u32 count;
-            occ = t.load(i, key, &count);
-            if (occ) dest = shard_of_hash(hash_key<W>(key), n_shards);
+            if (!t.load(i, key, &count)) continue;
+            const u32 dest = shard_of_hash(hash_key<W>(key), n_shards);
+            if (use_smem) atomicAdd(&s_cnt[dest], 1u); else atomicAdd(&d_counts[dest], 1ull);
         }
-        const unsigned act = __ballot_sync(0xffffffffu, occ);
-        if (occ) {
-            const unsigned peers = __match_any_sync(act, dest);
-            if (lane == __ffs(peers) - 1) atomicAdd(&d_counts[dest], (u64)__popc(peers));
-        }
+        __syncthreads();
+        if (use_smem)
+            for (u32 d = threadIdx.x; d < n_shards; d += blockDim.x) {
+                if (s_cnt[d]) atomicAdd(&d_counts[d], (u64)s_cnt[d]);
+                s_cnt[d] = 0;
+            }
+        __syncthreads();
     }
 }
 
@@ -942,29 +964,39 @@ template <int W>
 __global__ void __launch_bounds__(256)
 shard_pack_kernel(Table<W> t, u32 n_shards, u64 *d_cursors, u64 *rec_out)
 {
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31;
-    const u64 n_round = (t.cap + 31) & ~31ull;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        bool occ = false;
-        u32 dest = 0, count = 0;
-        u64 key[W];
-        if (i < t.cap) {
-            occ = t.load(i, key, &count);
-            if (occ) dest = shard_of_hash(hash_key<W>(key), n_shards);
-        }
-        const unsigned act = __ballot_sync(0xffffffffu, occ);
-        if (occ) {
-            const unsigned peers = __match_any_sync(act, dest);
-            const int leader = __ffs(peers) - 1;
-            u64 base = 0;
-            if (lane == leader) base = atomicAdd(&d_cursors[dest], (u64)__popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            const u64 at = base + __popc(peers & ((1u << lane) - 1u));
+    __shared__ u32 s_cnt[SHARD_SMEM_MAX];
+    __shared__ u64 s_base[SHARD_SMEM_MAX];
+    const bool use_smem = n_shards <= SHARD_SMEM_MAX;
+    constexpr int PER_THREAD = 8;                                       // slots per thread and chunk
+    const u64 chunk = (u64)blockDim.x * PER_THREAD;
+    for (u64 c0 = (u64)blockIdx.x * chunk; c0 < t.cap; c0 += (u64)gridDim.x * chunk) {
+        if (use_smem) for (u32 i = threadIdx.x; i < n_shards; i += blockDim.x) s_cnt[i] = 0;
+        __syncthreads();
+        u64 key[PER_THREAD][W];
+        u32 count[PER_THREAD], dest[PER_THREAD], rank[PER_THREAD];
 #pragma unroll
-            for (int j = 0; j < W; ++j) rec_out[at * (W + 1) + j] = key[j];
-            rec_out[at * (W + 1) + W] = count;
+        for (int q = 0; q < PER_THREAD; ++q) {
+            const u64 i = c0 + (u64)q * blockDim.x + threadIdx.x;
+            dest[q] = 0xFFFFFFFFu; rank[q] = 0; count[q] = 0;
+            if (i < t.cap && t.load(i, key[q], &count[q])) {
+                dest[q] = shard_of_hash(hash_key<W>(key[q]), n_shards);
+                if (use_smem) rank[q] = atomicAdd(&s_cnt[dest[q]], 1u);
+            }
         }
+        __syncthreads();
+        if (use_smem)
+            for (u32 d = threadIdx.x; d < n_shards; d += blockDim.x)
+                s_base[d] = s_cnt[d] ? atomicAdd(&d_cursors[d], (u64)s_cnt[d]) : 0ull;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PER_THREAD; ++q) {
+            if (dest[q] == 0xFFFFFFFFu) continue;
+            const u64 at = use_smem ? s_base[dest[q]] + rank[q] : atomicAdd(&d_cursors[dest[q]], 1ull);
+#pragma unroll
+            for (int j = 0; j < W; ++j) rec_out[at * (W + 1) + j] = key[q][j];
+            rec_out[at * (W + 1) + W] = count[q];
+        }
+        __syncthreads();
     }
 }
 

@@ -11,6 +11,7 @@
 // determines doubleHashSize (the kmer_occ.bin header), as in counter.h:300-309.
 #include "pbk_counter.hpp"
 
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <deque>
@@ -28,6 +29,20 @@
 namespace {
 
 typedef unsigned long long u64;
+
+// PBK_TIMING=1: phase times on stderr (the reference has no timers at all)
+struct PhaseTimer {
+    bool on; std::chrono::steady_clock::time_point t0, last;
+    PhaseTimer() : on(getenv("PBK_TIMING") != NULL), t0(std::chrono::steady_clock::now()), last(t0) {}
+    void mark(const char *what)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pbk_assemble] %-28s %8.3f s  (total %.3f s)\n", what, std::chrono::duration<double>(now - last).count(),
+                std::chrono::duration<double>(now - t0).count());
+        last = now;
+    }
+};
 
 // ---- options: the reference's three maps (assemble.cpp:52-71) -----------------------------------
 struct Options {
@@ -107,7 +122,8 @@ int check_file_format(const Mapped &f)
     return 0;
 }
 
-// one batch of reads in pinned host memory
+// one batch of reads in (pageable, page-aligned) host memory: the parsers must be able to run before the CUDA
+// context exists -- creating it takes seconds on a 180 GB GPU and is the largest fixed cost of the program
 struct Batch {
     uint8_t *bases; size_t cap, used;
     std::vector<uint64_t> offsets;
@@ -121,12 +137,12 @@ public:
         for (int i = 0; i < n_buffers; ++i) {
             Batch *b = new Batch();
             void *p = NULL;
-            if (pbk_host_alloc(&p, batch_bytes) != PBK_OK) throw pbk::GPUError("pinned host memory");
+            if (posix_memalign(&p, 4096, batch_bytes) != 0) throw pbk::ErrorBase(pbk::E_IO, "Error, out of host memory");
             b->bases = (uint8_t *)p; b->cap = batch_bytes;
             free_.push_back(b); all_.push_back(b);
         }
     }
-    ~BatchQueue() { for (size_t i = 0; i < all_.size(); ++i) { pbk_host_free(all_[i]->bases); delete all_[i]; } }
+    ~BatchQueue() { for (size_t i = 0; i < all_.size(); ++i) { free(all_[i]->bases); delete all_[i]; } }
     void add_producer() { std::lock_guard<std::mutex> g(m_); ++producers_; }
     void producer_done() { std::lock_guard<std::mutex> g(m_); --producers_; cv_.notify_all(); }
     Batch *get_free()
@@ -313,6 +329,7 @@ void exec(Options &opt)
     const std::string prefix = opt.single["-o"];
     const std::vector<std::string> &files = opt.multi["-f"];
 
+    PhaseTimer pt;
     pbk::Counter counter;
     std::vector<int> types;
     std::vector<Mapped *> maps;
@@ -336,12 +353,17 @@ void exec(Options &opt)
         double_hash_size = counter.makeKmerReadDistributionMT(k0, read_fp.data(), memory, num_thread);
         for (size_t i = 0; i < read_fp.size(); ++i) fclose(read_fp[i]);
     } else {
+    pt.mark("open + sniff inputs");
     std::cerr << "K = " << k0 << ", saving kmers from reads..." << std::endl;                   // assemble.cpp:306
-    counter.beginCounting(k0);
 
-    // ingest: one parser per file, at most -t at a time; the main thread feeds the GPU
+    // ingest: one parser per file, at most -t at a time, started BEFORE the CUDA context is created so that parsing
+    // runs behind that fixed cost; the main thread then feeds the GPU.  Enough batch buffers for ~2 GB of bases.
+    size_t total_bytes = 0;
+    for (size_t i = 0; i < maps.size(); ++i) total_bytes += maps[i]->n;
     const size_t n_par = (size_t)std::min<u64>(num_thread, files.size());
-    BatchQueue q((size_t)128 << 20, (int)n_par * 2 + 1);
+    const size_t batch_bytes = (size_t)128 << 20;
+    const int n_buf = (int)std::min<size_t>(16, std::max<size_t>(n_par * 2 + 1, total_bytes / 2 / batch_bytes + n_par + 1));
+    BatchQueue q(batch_bytes, n_buf);
     std::mutex err_m;
     std::vector<pbk::ErrorBase> errors;
     std::vector<std::thread> workers;
@@ -364,6 +386,8 @@ void exec(Options &opt)
         }));
     }
     pbk::ErrorBase *push_error = NULL;
+    try { counter.beginCounting(k0); } catch (pbk::ErrorBase &e) { push_error = new pbk::ErrorBase(e); }
+    pt.mark("pbk_create (CUDA context)");
     while (Batch *b = q.get_full()) {
         if (!push_error && b->offsets.size() > 1) {
             try { counter.pushReads(b->bases, b->offsets.data(), b->offsets.size() - 1); }
@@ -375,8 +399,10 @@ void exec(Options &opt)
     for (size_t i = 0; i < maps.size(); ++i) delete maps[i];
     if (!errors.empty()) throw errors[0];
     if (push_error) throw *push_error;
+    pt.mark("parse + push (overlapped)");
 
     double_hash_size = counter.endCounting(memory);
+    pt.mark("pbk_finalize");
     }
 
     // assemble.cpp:318-335
@@ -396,14 +422,19 @@ void exec(Options &opt)
     oss << prefix << '_' << k0 << "merFrq.tsv";
     counter.outputOccurrenceDistribution(oss.str());
 
+    pt.mark("cutoff + schedule + tsv");
     FILE *sorted_fp = counter.sortedKeyFromKmerFile(cutoff[0], opt.single["-tmp"]);
+    pt.mark("export sorted + sortedKeyFP");
     double_hash_size = counter.loadKmer(cutoff[0], double_hash_size);
     (void)double_hash_size;
     if (opt.flag["-kmer_occ_only"]) {
         counter.outputOccurrenceTableBinary(prefix + "_kmer_occ.bin");
+        pt.mark("kmer_occ.bin");
         fclose(sorted_fp);
         std::cerr << "assemble completed!" << std::endl;                                       // assemble.cpp:189
-        return;
+        // outputs are closed; skip the teardown of the CUDA context (the OS reclaims it faster than the driver frees it)
+        fflush(NULL);
+        _exit(0);
     }
     fclose(sorted_fp);
     throw pbk::ErrorBase(13, "pbk_assemble only implements the -kmer_occ_only path; run the reference for graph construction");

@@ -23,7 +23,8 @@ n_reads, n_bases = len(o) - 1, len(b)
 grid = json.loads(os.environ.get("TUNE_GRID", '{"PBK_REGION_MB": [4, 8, 16, 32, 64], "PBK_PF_DIST": [0, 1], "PBK_PASSB_HINT": [0, 1], "PBK_PASSB_CTAS": [3], "PBK_PART_SMEM_KB": [100]}'))
 names = sorted(grid)
 out = open("gpurun_out/tune_passb.jsonl", "a")
-kc = KmerCounter(32, timing=True)
+K = int(os.environ.get("TUNE_K", "32"))
+kc = KmerCounter(K, timing=True)
 for combo in itertools.product(*[grid[n] for n in names]):
     for n, v in zip(names, combo):
         os.environ[n] = str(v)
@@ -39,6 +40,7 @@ for combo in itertools.product(*[grid[n] for n in names]):
     ms = kc.timer_elapsed_ms(0, 1) / steps
     s1 = kc.stats()
     rec = dict(zip(names, combo))
+    rec["k"] = K
     rec.update(ms_step=ms, ms_partition=(s1["ms_partition"] - s0["ms_partition"]) / steps,
                ms_insert=(s1["ms_insert"] - s0["ms_insert"]) / steps, gkmers=kc.stats()["n_instances"] / ms / 1e6)
     print(json.dumps(rec), flush=True)
