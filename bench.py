@@ -41,7 +41,9 @@ K = 32
 METRIC = "canonical k-mers counted/sec at k=32"
 UNIT = "k-mers/s"
 BYTES_PER_INSTANCE = {150: 65.26, 250: 65.14}          # SURVEY.md section 8d (k=32)
-CPU_SAMPLE_DIV = 16                                     # reference arm: 1/16 of the N=1 workload
+CPU_FULL_RUN_S = 20.0                                   # one reference run over the whole C1 workload on a 16-core host
+REF_MEM_GB = 16                                         # the reference's default -m
+CPU_BUDGET_S = 180.0                                    # the reference arm must finish within a few minutes
 
 
 def algorithmic_bytes_per_instance(read_len: int, k: int) -> float:
@@ -51,7 +53,7 @@ def algorithmic_bytes_per_instance(read_len: int, k: int) -> float:
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of one step's Pass A + Pass B launches, from the committed
     `ncu --set full` capture of this workload (profiles/*_traffic.json); None when there is no capture."""
-    path = os.path.join(ROOT, "profiles", "r1b_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r1c_traffic.json")
     try:
         return float(json.load(open(path))["dram_bytes_per_step"])
     except Exception:
@@ -131,12 +133,18 @@ class ClockSampler:
 # the reference arm / cpu_baseline
 # ------------------------------------------------------------------------------------------------
 
-def reference_sample(workload: str, scale: float):
+def reference_sample(workload: str, scale: float, n_runs: int):
+    """The whole workload when `n_runs` reference runs of it fit the time budget (one run of C1 takes ~20 s on the
+    GPU box's 16 host cores), otherwise the first 1/2, 1/4, ... of the read pairs.  (A small sample flatters us: the
+    reference's fixed costs -- zero-filling and scanning its -m sized table -- do not shrink with the input.)"""
     from platanus_b_b200 import synth
     spec = synth.config(workload, scale=scale)
-    max_pairs = max(1, spec.n_pairs // CPU_SAMPLE_DIV)
-    rs = synth.make_reads(spec, max_pairs=max_pairs)
-    return spec, rs, f"first 1/{CPU_SAMPLE_DIV} of the {workload} read pairs ({rs.n_reads} reads x {rs.read_len} bp)"
+    div = 1
+    while div < 64 and n_runs * CPU_FULL_RUN_S * scale / div > CPU_BUDGET_S:
+        div *= 2
+    rs = synth.make_reads(spec, max_pairs=max(1, spec.n_pairs // div) if div > 1 else None)
+    what = f"the whole {workload} read set" if div == 1 else f"the first 1/{div} of the {workload} read pairs"
+    return spec, rs, f"{what} ({rs.n_reads} reads x {rs.read_len} bp)"
 
 
 def count_instances(rs, k: int) -> int:
@@ -160,20 +168,20 @@ def cpu_baseline(workload: str, scale: float, steps: int, warmup: int):
     from platanus_b_b200 import synth
     if not O.have_ref_binary():
         return None
-    spec, rs, sample = reference_sample(workload, scale)
+    spec, rs, sample = reference_sample(workload, scale, max(1, steps) + warmup)
     n_inst = count_instances(rs, K)
     cores = os.cpu_count() or 1
     tmp = tempfile.mkdtemp(prefix="pbk_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     try:
         files = synth.write_fastq(rs, os.path.join(tmp, "r_1.fq"), os.path.join(tmp, "r_2.fq"))
         for _ in range(warmup):
-            run_reference_once(files, tmp, cores, 2)
-        t = [run_reference_once(files, tmp, cores, 2) for _ in range(max(1, steps))]
+            run_reference_once(files, tmp, cores, REF_MEM_GB)
+        t = [run_reference_once(files, tmp, cores, REF_MEM_GB) for _ in range(max(1, steps))]
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     wall = float(np.mean(t))
     return {"value": n_inst / wall, "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": sample + f"; platanus_b assemble -kmer_occ_only -k {K} -t {cores} -m 2, whole-process wall clock "
+            "sample": sample + f"; platanus_b assemble -kmer_occ_only -k {K} -t {cores} -m {REF_MEM_GB}, whole-process wall clock "
                                f"{wall:.2f} s incl. FASTQ parse and kmer_occ.bin write",
             "n_instances": n_inst, "ms_per_step": wall * 1e3}
 
@@ -354,7 +362,7 @@ def main_ours(args):
                 "kernel_share_of_step": ms_pair * args.steps / max(ms_res, 1e-9),
                 "frac_of_step": bpi * n_inst_local * args.steps / (ms_res * 1e-3) / 1e9 / peak,
                 "atomic_bound_note": "random 64-bit atomics with return: 125 G/s on an L2-resident table, 22 G/s on a table >> L2 "
-                                     "(profiles/r1a_atomics_microbench.json, profiles/r1b_atomics_sweep.json); Pass B alone "
+                                     "(profiles/r1a_atomics_microbench.json, profiles/r1b_atomics_sweep.json, profiles/r1c_warp_ops_microbench.jsonl); Pass B alone "
                                      "runs at instances / ms_per_step.bucket_insert_compact_kernel"}
 
     line = None
