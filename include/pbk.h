@@ -150,6 +150,9 @@ int  pbk_export(pbk_ctx *ctx, uint32_t min_count, int sorted, uint64_t *keys, ui
                 uint64_t capacity, uint64_t *n_out);
 
 int  pbk_get_stats(const pbk_ctx *ctx, pbk_stats *out);
+/* switch the per-launch CUDA events of PBK_F_TIMING on or off (they cost 3-4 % of a step: measure throughput
+ * without them, the per-kernel breakdown with them) */
+int  pbk_set_timing(pbk_ctx *ctx, int on);
 
 /* Device-side stopwatch on the context's own compute stream (the stream every kernel of this context
  * is launched on, and that waits for every H2D copy): pbk_timer_mark records CUDA event `slot`

@@ -37,7 +37,7 @@ SYMBOLS = [
     "pbk_reset", "pbk_shard_record_bytes", "pbk_shard_send_counts", "pbk_shard_pack_device",
     "pbk_shard_insert_device", "pbk_shard_of_key", "pbk_left_local_min", "pbk_coverage_cutoff",
     "pbk_distribution_average", "pbk_double_hash_size", "pbk_write_frq_tsv", "pbk_write_kmer_occ_bin",
-    "pbk_microbench_atomics", "pbk_timer_mark", "pbk_timer_elapsed_ms",
+    "pbk_microbench_atomics", "pbk_timer_mark", "pbk_timer_elapsed_ms", "pbk_set_timing",
 ]
 
 
@@ -105,6 +105,7 @@ def load_library(build_if_missing: bool = True):
     L.pbk_export.argtypes = [vp, C.c_uint32, C.c_int, u64p, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.pbk_get_stats.argtypes = [vp, C.POINTER(PbkStats)]
     L.pbk_reset.argtypes = [vp, C.c_uint32]
+    L.pbk_set_timing.argtypes = [vp, C.c_int]
     L.pbk_timer_mark.argtypes = [vp, C.c_int]
     L.pbk_timer_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.pbk_shard_record_bytes.argtypes = [vp]; L.pbk_shard_record_bytes.restype = C.c_uint32
@@ -226,6 +227,9 @@ class KmerCounter:
         if k:
             self.k, self.words = int(k), (int(k) + 31) // 32
         self.occ_hist = self.len_hist = None
+
+    def set_timing(self, on: bool):
+        self._check(self._L.pbk_set_timing(self._ctx, int(on)), "pbk_set_timing")
 
     def timer_mark(self, slot: int):
         self._check(self._L.pbk_timer_mark(self._ctx, slot), "pbk_timer_mark")

@@ -793,6 +793,13 @@ int pbk_get_stats(const pbk_ctx *cc, pbk_stats *out)
     return PBK_OK;
 }
 
+int pbk_set_timing(pbk_ctx *c, int on)
+{
+    if (!c) return PBK_E_ARG;
+    if (on) c->flags |= PBK_F_TIMING; else c->flags &= ~(u32)PBK_F_TIMING;
+    return PBK_OK;
+}
+
 int pbk_timer_mark(pbk_ctx *c, int slot)
 {
     if (!c || slot < 0 || slot >= 8) return PBK_E_ARG;
