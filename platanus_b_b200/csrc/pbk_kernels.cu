@@ -189,7 +189,7 @@ void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *counts, v
                 overflow_keys, overflow_cap, opts);
         return;
     }
-    const int grid = (int)std::min<u64>(tiles, (u64)sm_count * 2);
+    const int grid = (int)std::min<u64>(tiles, (u64)sm_count * PASSB_WIDE_CTAS);
     switch (table.words) {
 #define PBK_CASE_W(Wv) case Wv: bucket_insert_kernel<Wv><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, b_first,   \
             b_end, (u64 *)d_desc, Table<Wv>(table.slots, table.cap), Table<Wv>(remote.slots, remote.cap), shard.n_shards,    \

@@ -493,6 +493,10 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
 constexpr int PASSB_THREADS = 256;
 constexpr int PASSB_KPT = 8;
 constexpr int PASSB_TILE_KEYS = PASSB_THREADS * PASSB_KPT;
+#ifndef PBK_PASSB_WIDE_CTAS
+#define PBK_PASSB_WIDE_CTAS 4
+#endif
+constexpr int PASSB_WIDE_CTAS = PBK_PASSB_WIDE_CTAS;   // resident CTAs per SM of the k > 32 kernel: it is latency bound, occupancy is what it needs
 
 struct PassBBucket {
     u64 tile_start;         // first ticket of this bucket (tiles of the launch are numbered in bucket order)
@@ -513,7 +517,7 @@ __device__ __forceinline__ void passb_prefetch(const char *base, u64 lines, u64 
 }
 
 template <int W>
-__global__ void __launch_bounds__(PASSB_THREADS, 2)
+__global__ void __launch_bounds__(PASSB_THREADS, PASSB_WIDE_CTAS)
 bucket_insert_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const PassBBucket *__restrict__ bk,
                      u32 b_first, u32 b_end, u64 *ticket, Table<W> table, Table<W> remote, u32 n_shards, u32 rank,
                      Counters *ctr, u64 *ovf, u64 ovf_cap)
