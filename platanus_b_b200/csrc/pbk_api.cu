@@ -26,6 +26,7 @@ constexpr double MAX_LOAD = 0.5;                  // k > 32 (16+ byte slots, any
 constexpr double MAX_LOAD_COMPACT = 0.6;          // k <= 32: capacity is a power of two, real load ends up 0.3-0.6
 constexpr u64 U32_HEADROOM = (1ull << 32) - 65536 - 2;
 constexpr u64 PART_MIN_WINDOWS = 1ull << 22;    // smaller batches go straight to the table
+constexpr u64 MAX_PUSH_BASES = 1ull << 31;       // larger pushes are cut into internal batches (2 Gi bases: 16 GiB of bucket store at k <= 32)
 
 enum LaunchClass { LC_PACK = 0, LC_COUNT = 1, LC_OTHER = 2, LC_PART = 3, LC_INSERT = 4, LC_N = 5 };
 
@@ -690,7 +691,28 @@ int pbk_push_reads(pbk_ctx *c, const uint8_t *bases, const uint64_t *read_offset
     if (read_offsets[0] != 0) return fail(c, PBK_E_ARG, "read_offsets[0] must be 0");
     const u64 n_bases = read_offsets[n_reads];
     if (n_bases && !bases) return fail(c, PBK_E_ARG, "bases is NULL");
-    return push_common(c, bases, nullptr, (const u64 *)read_offsets, nullptr, n_reads, n_bases, encoding, n_pos, (const u64 *)n_pos_offsets);
+    // A batch keeps its 2-bit stream and its bucket store (8W bytes per window) in HBM, so very large pushes are cut
+    // into internal batches of at most MAX_PUSH_BASES bases at read boundaries.
+    static const u64 max_push = getenv("PBK_MAX_PUSH_BASES") ? strtoull(getenv("PBK_MAX_PUSH_BASES"), nullptr, 10) : MAX_PUSH_BASES;
+    if (n_bases <= max_push)
+        return push_common(c, bases, nullptr, (const u64 *)read_offsets, nullptr, n_reads, n_bases, encoding, n_pos, (const u64 *)n_pos_offsets);
+    std::vector<u64> off, npo;
+    for (u64 r0 = 0; r0 < n_reads;) {
+        u64 r1 = r0 + 1;                                               // at least one read per batch
+        while (r1 < n_reads && read_offsets[r1 + 1] - read_offsets[r0] <= max_push) ++r1;
+        off.resize(r1 - r0 + 1);
+        for (u64 i = r0; i <= r1; ++i) off[i - r0] = read_offsets[i] - read_offsets[r0];
+        const int32_t *np = nullptr;
+        if (encoding == PBK_ENC_PLATANUS && n_pos && n_pos_offsets) {
+            npo.resize(r1 - r0 + 1);
+            for (u64 i = r0; i <= r1; ++i) npo[i - r0] = n_pos_offsets[i] - n_pos_offsets[r0];
+            np = n_pos + n_pos_offsets[r0];
+        }
+        TRY(push_common(c, bases + read_offsets[r0], nullptr, off.data(), nullptr, r1 - r0, off.back(), encoding, np,
+                        np ? npo.data() : nullptr));
+        r0 = r1;
+    }
+    return PBK_OK;
 }
 
 int pbk_push_reads_device(pbk_ctx *c, const void *d_bases, const void *d_read_offsets, uint64_t n_reads, uint64_t n_bases)

@@ -217,6 +217,7 @@ void launch_bucket_insert_chained(const u64 *bkt_keys, u64 seg_cap, const void *
 {
     const PassBBucket *d_bk = (const PassBBucket *)((const char *)d_desc + 16);
     const u32 opts = getenv("PBK_PASSB_HINT") ? (u32)atoi(getenv("PBK_PASSB_HINT")) : 1u;
+    if (getenv("PBK_PASSB_CTAS")) ctas_per_sm = atoi(getenv("PBK_PASSB_CTAS"));
     const int grid = sm_count * ctas_per_sm;                    // CTAs that find no tile left leave at once
     if (shard.n_shards > 1)
         bucket_insert_compact_kernel<true><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, 0, n_buckets, (u64 *)d_desc,

@@ -347,3 +347,42 @@ def test_pipelined_pass_overlap_gives_the_identical_table(oracle):
         assert kc.stats()["n_pipelined_batches"] == 0
         k3, c3 = kc.export(1, sorted=True)
     assert np.array_equal(k3, first[0]) and np.array_equal(c3, first[1])
+
+
+def test_large_pushes_are_cut_into_internal_batches(oracle):
+    """pbk_push_reads splits a push at read boundaries when it exceeds the internal batch limit (here forced down to
+    ~1/5 of the input through PBK_MAX_PUSH_BASES); ASCII and PLATANUS encodings."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+from oracle import oracle as O
+from platanus_b_b200 import KmerCounter, synth
+rs = synth.make_reads(synth.config("C1", scale=1 / 80))
+b, o = rs.flat()
+rd = O.Reads(); rd.add_array(b, o)
+want = O.count(rd, 32)
+with KmerCounter(32) as kc:
+    kc.push_reads(b, o); kc.finalize()
+    keys, counts = kc.export(1, sorted=True)
+    assert np.array_equal(keys, want.keys) and np.array_equal(counts, want.counts) and kc.n_instances == want.n_instances
+    assert np.array_equal(kc.len_hist, want.len_hist)
+codes = np.array([O.char2bin(int(x)) for x in range(256)], dtype=np.uint8)[b]
+isn = codes == 4
+npos, npo = [], [0]
+L = rs.read_len
+for r in range(len(o) - 1):
+    w = np.nonzero(isn[r * L:(r + 1) * L])[0]
+    npos.extend(w.tolist()); npo.append(len(npos))
+codes[isn] = 2
+with KmerCounter(32) as kc:
+    kc.push_reads(codes, o, encoding=1, n_pos=np.array(npos or [0], np.int32), n_pos_offsets=np.array(npo, np.uint64)); kc.finalize()
+    keys, counts = kc.export(1, sorted=True)
+    assert np.array_equal(keys, want.keys) and np.array_equal(counts, want.counts)
+print("ok")
+'''
+    env = dict(os.environ, PBK_MAX_PUSH_BASES=str(1_700_000))
+    p = subprocess.run([sys.executable, "-c", code, ROOT], capture_output=True, text=True, env=env)
+    assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
