@@ -418,7 +418,9 @@ def main():
     ap.add_argument("--workload", default="C1")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-mem-gb", type=int, default=REF_MEM_GB, help="-m of the reference arm (its default is 16)")
     args = ap.parse_args()
+    globals()["REF_MEM_GB"] = args.ref_mem_gb
     if args.impl == "reference":
         return main_reference(args)
     return main_ours(args)

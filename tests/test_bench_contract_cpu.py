@@ -1,0 +1,41 @@
+"""bench.py's reference arm (`--impl reference`: the unmodified reference program on the host cores) runs without a GPU,
+so its JSON-line contract can be checked here on a tiny workload.  Our own arm needs a B200 and must refuse to run
+without one (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "platanus_b")
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference binary not built")
+def test_reference_arm_prints_the_contract_line():
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--scale", "0.002", "--steps", "1",
+                        "--warmup", "0", "--ref-mem-gb", "1"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "canonical k-mers counted/sec at k=32" and line["unit"] == "k-mers/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["sample"]
+    assert line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
+                       text=True, env=env, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_our_arm_refuses_to_run_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                       timeout=300)
+    assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
