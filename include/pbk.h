@@ -200,7 +200,8 @@ int  pbk_write_kmer_occ_bin(const char *path, uint32_t k, const uint64_t *keys, 
 /* ---- measurement helper: random read-modify-write rate of this GPU's memory system -------------
  * Uniform-random 64-bit key probe + 32-bit atomic add on a table of `table_bytes` (SURVEY.md 8d:
  * R_atomic).  mode 0: red.add only; 1: ld key + red.add (steady-state hit path); 2: CAS-claim
- * inserts of distinct keys.  Returns operations per second in *ops_per_s. */
+ * inserts of distinct keys; 3-11 and >= 100: 64-bit atomics with return on 8-byte slots, skewed, streamed-key and
+ * region-sweep variants (pbk_kernels.cu, scripts/gpu_probe.py name them).  Returns operations per second. */
 int  pbk_microbench_atomics(int device, uint64_t table_bytes, uint64_t n_ops, int mode, double *ops_per_s);
 
 #ifdef __cplusplus

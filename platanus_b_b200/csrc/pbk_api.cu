@@ -1,9 +1,16 @@
 // pbk_api.cu -- the C ABI of libpbk.so (include/pbk.h): context, streams, batching, table growth.
 //
-// One context drives one GPU.  Reads arrive in batches (pbk_push_reads); each batch is cut into
-// chunks of CHUNK_BASES bases that flow  H2D copy (copy stream, double-buffered)  ->  pack kernel
-// ->  count kernel (compute stream).  After every chunk the host reads a 48-byte counter block to
-// decide whether the table has to grow; nothing else crosses PCIe until pbk_finalize/pbk_export.
+// One context drives one GPU.  Reads arrive in batches (pbk_push_reads); each batch is cut into chunks of
+// CHUNK_BASES bases that flow  H2D copy (copy stream, ring of N_STAGE staging buffers)  ->  pack kernel  ->
+// counting (compute stream).  Counting takes one of three routes:
+//   * small batches (< PART_MIN_WINDOWS windows): count_kernel inserts straight into the table, the host reads a
+//     48-byte counter block per chunk to decide whether the table has to grow;
+//   * the first large batch of a context: Pass A (partition_kernel) per chunk, then Pass B (bucket_insert_*) in a
+//     pilot launch over 1/16 of the buckets that measures the new-key ratio, then the rest (flush_buckets);
+//   * later large batches with k <= 32: the table is sized up front from that ratio and Pass A, the device-built
+//     tile map and Pass B are chained on the GPU without host round trips -- in up to four groups of chunks when
+//     the input comes from the host, so that the passes hide behind the H2D copies (`Pipe`).
+// Nothing but counters crosses PCIe back until pbk_finalize / pbk_export.
 #include "../../include/pbk.h"
 #include "pbk_kernels.cuh"
 
