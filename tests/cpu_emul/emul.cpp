@@ -59,23 +59,34 @@ static int run(const uint8_t *bases, const u64 *off, u64 n_reads, int k, int enc
                             0, w_split, k, P, bin_cap, bkt.data(), seg_cap, cursor.data(), &ctr, ovf.data(), OVF);
         partition_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
                             w_split, words, k, P, bin_cap, bkt.data(), seg_cap, cursor.data(), &ctr, ovf.data(), OVF);
-        // Pass B in two launches (pilot + rest)
         std::vector<u64> count(P);
         for (u32 b = 0; b < P; ++b) count[b] = std::min<u64>(cursor[b], seg_cap);
-        const u32 cuts[3] = {0, 2, P};
-        for (int part = 0; part < 2; ++part) {
-            const u32 b0 = cuts[part], b1 = cuts[part + 1];
-            std::vector<PassBBucket> desc(b1 - b0 + 1);
-            const u64 tk = W == 1 ? PASSB1_KPT * PASSB1_ROUNDS : PASSB_KPT;     // blockDim = 1 in the emulation
-            u64 tiles = 0, ticket = 0;
-            for (u32 b = b0; b < b1; ++b) { desc[b - b0] = PassBBucket{tiles, count[b], nullptr, nullptr, 0, 0}; tiles += (count[b] + tk - 1) / tk; }
-            desc[b1 - b0] = PassBBucket{tiles, 0, nullptr, nullptr, 0, 0};
+        const u64 tk = W == 1 ? PASSB1_KPT * PASSB1_ROUNDS : PASSB_KPT;     // blockDim = 1 in the emulation
+        auto pass_b = [&](const PassBBucket *desc, u32 b0, u32 b1, u64 *ticket) {
             if constexpr (W == 1) {
-                if (n_shards > 1) bucket_insert_compact_kernel<true>(bkt.data(), seg_cap, desc.data(), b0, b1, &ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF, 1u);
-                else bucket_insert_compact_kernel<false>(bkt.data(), seg_cap, desc.data(), b0, b1, &ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF, 0u);
+                if (n_shards > 1) bucket_insert_compact_kernel<true>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF, 1u);
+                else bucket_insert_compact_kernel<false>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF, 0u);
             } else {
-                bucket_insert_kernel<W>(bkt.data(), seg_cap, desc.data(), b0, b1, &ticket, table, remote, n_shards, rank, &ctr,
-                                        ovf.data(), OVF);
+                bucket_insert_kernel<W>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF);
+            }
+        };
+        if (W == 1 && (k % 3) == 0) {
+            // chained route of pbk_api.cu (`Pipe`): the tile map is built by passb_desc_kernel from the cursors
+            std::vector<PassBBucket> desc(P + 1);
+            u64 ticket[2] = {7, 7};
+            passb_desc_kernel(cursor.data(), seg_cap, P, (u32)tk, (const char *)table_v.data(), table_v.size(), nullptr, 0, 8u, 1,
+                              ticket, desc.data());
+            pass_b(desc.data(), 0, P, ticket);
+        } else {
+            // host-built tile map, Pass B in two launches (pilot + rest)
+            const u32 cuts[3] = {0, 2, P};
+            for (int part = 0; part < 2; ++part) {
+                const u32 b0 = cuts[part], b1 = cuts[part + 1];
+                std::vector<PassBBucket> desc(b1 - b0 + 1);
+                u64 tiles = 0, ticket = 0;
+                for (u32 b = b0; b < b1; ++b) { desc[b - b0] = PassBBucket{tiles, count[b], nullptr, nullptr, 0, 0}; tiles += (count[b] + tk - 1) / tk; }
+                desc[b1 - b0] = PassBBucket{tiles, 0, nullptr, nullptr, 0, 0};
+                pass_b(desc.data(), b0, b1, &ticket);
             }
         }
     }
