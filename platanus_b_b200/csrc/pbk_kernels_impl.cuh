@@ -322,6 +322,9 @@ __device__ __forceinline__ void bucket_append_direct(const u64 *key, u32 b, u64 
     }
 }
 
+// windows of one stream word a Pass A thread handles per tile
+template <int W> struct PART_WIN { static constexpr int value = W == 1 ? 32 : (W == 2 ? 16 : 8); };
+
 // OR of x << j for j in [0, w), 0 <= w <= 32 (doubling: at most five shift/or steps)
 __device__ __forceinline__ u64 smear_up(u64 x, int w)
 {
@@ -355,11 +358,19 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
     const int pshift = (n_buckets > 1 && (n_buckets & (n_buckets - 1)) == 0) ? 64 - (31 - __clz(n_buckets)) : 0;
     u64 inst = 0;
 
-    for (u64 tile = word_begin + (u64)blockIdx.x * blockDim.x; tile < word_end; tile += (u64)gridDim.x * blockDim.x) {
+    // A thread takes PART_WIN<W> consecutive windows of one stream word per tile: all 32 for one-word keys; 16 or 8 for
+    // multi-word keys, whose bin entries are W words each -- with a whole word per thread the shared-memory bins left
+    // room for only 2-4 warps per SM.
+    constexpr int WIN = PART_WIN<W>::value, SUBS = 32 / WIN;
+    const u64 n_items = (word_end - word_begin) * SUBS;
+    for (u64 tile = (u64)blockIdx.x * blockDim.x; tile < n_items; tile += (u64)gridDim.x * blockDim.x) {
         for (u32 b = threadIdx.x; b < n_buckets; b += blockDim.x) scount[b] = 0;
         __syncthreads();
-        const u64 wi = tile + threadIdx.x;
-        if (W == 1 && pshift && wi < word_end) {
+        const u64 item = tile + threadIdx.x;
+        const bool live = item < n_items;
+        const u64 wi = word_begin + item / SUBS;
+        const int i0 = (int)(item % SUBS) * WIN;
+        if (W == 1 && pshift && live) {
             // One-word keys and a power-of-two bucket count: the hot configuration (k <= 32).  Fully unrolled so that every shift is an immediate;
             // which of the 32 windows are usable is worked out once per word with bit smears instead of a running
             // counter: the window ending at position i is usable iff none of its k positions is an N and none of
@@ -389,9 +400,10 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
                 }
                 inst += n_here;
             }
-        } else if (wi < word_end) {
+        } else if (live) {
             const u64 cur = stream[wi];
             const u32 nf = nflag[wi], rf = rflag[wi];
+            // run = usable bases (same read, no N) ending just before window position i0 of this word
             int run = k;
             for (int j = 1; j <= nb; ++j) {
                 const u32 a = nflag[wi - j], b = rflag[wi - j];
@@ -402,9 +414,30 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
                     break;
                 }
             }
+            if (i0) {                                           // the positions of this word that other threads own
+                const u32 a = nf & ((1u << i0) - 1u), b = rf & ((1u << i0) - 1u);
+                if (a | b) {
+                    const int pn = a ? 32 - __clz(a) : 0;
+                    const int pr = b ? 31 - __clz(b) : 0;
+                    run = i0 - max(pn, pr);
+                } else {
+                    run += i0;
+                }
+            }
+            // rolling state = the 32 W bases that end just before position i0
             u64 fwd[W], rev[W];
+            if (i0 == 0) {
 #pragma unroll
-            for (int j = 0; j < W; ++j) fwd[j] = stream[wi - 1 - j];
+                for (int j = 0; j < W; ++j) fwd[j] = stream[wi - 1 - j];
+            } else {
+                u64 hi = cur;
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+                    const u64 lo = stream[wi - 1 - j];
+                    fwd[j] = (lo << (2 * i0)) | (hi >> (64 - 2 * i0));
+                    hi = lo;
+                }
+            }
             {
                 u64 y[W + 1];
 #pragma unroll
@@ -413,11 +446,14 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
 #pragma unroll
                 for (int j = 0; j < W; ++j) rev[j] = s ? ((y[j] >> s) | (y[j + 1] << (64 - s))) : y[j];
             }
+            u64 c = i0 ? cur << (2 * i0) : cur;
+            const u32 nfs = nf >> i0, rfs = rf >> i0;
 #pragma unroll 2
-            for (int i = 0; i < 32; ++i) {
-                const u32 b = (u32)(cur >> (62 - 2 * i)) & 3u;
-                if ((rf >> i) & 1u) run = 0;
-                run = ((nf >> i) & 1u) ? 0 : run + 1;
+            for (int i = 0; i < WIN; ++i) {
+                const u32 b = (u32)(c >> 62);
+                c <<= 2;
+                if ((rfs >> i) & 1u) run = 0;
+                run = ((nfs >> i) & 1u) ? 0 : run + 1;
 #pragma unroll
                 for (int j = W - 1; j > 0; --j) fwd[j] = (fwd[j] << 2) | (fwd[j - 1] >> 62);
                 fwd[0] = (fwd[0] << 2) | b;
