@@ -44,8 +44,10 @@ constexpr u64 CT_NOISE = 1ull << 19;      // > number of resident threads (148 S
 constexpr u64 CT_NOISE = 16;              // sequential emulation: nothing is ever in flight, small tables suffice
 #endif
 
+// Two- and three-word keys get 32-byte slots aligned to the 32-byte DRAM/L2 sector, so one 256-bit load
+// (LDG.256 on sm_100a) brings the key words and the state word in a single L2 request.
 template <int W>
-struct alignas(8) Slot {
+struct alignas(W <= 3 ? 32 : 8) Slot {
     u64 key[W];
     u32 cs;      // 0 = empty, CS_LOCKED = being written, else count
     u32 pad;
@@ -110,6 +112,17 @@ __device__ __forceinline__ u32 ld_cg_u32(const u32 *p)
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// whole 32-byte slot in one request; served by one L2 sector access, i.e. a snapshot of the slot
+__device__ __forceinline__ void ld_cg_256(const void *p, u64 &a, u64 &b, u64 &c, u64 &d)
+{
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+}
+// whole 32-byte slot in one store: one L2 sector write, so a reader's 256-bit load sees the old slot or the new
+// one, never a mix -- publishing a claimed slot this way needs no release fence
+__device__ __forceinline__ void st_cg_256(void *p, u64 a, u64 b, u64 c, u64 d)
+{
+    asm volatile("st.global.cg.v4.u64 [%0], {%1,%2,%3,%4};" :: "l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
 __device__ __forceinline__ void red_add_u32(u32 *p, u32 v)
 {
     asm volatile("red.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
@@ -151,10 +164,21 @@ __device__ __forceinline__ void prefetch_keep(const void *p)
 }
 // read-once / write-once data (the bucket store): evict-first, so it does not push table lines out of L2
 __device__ __forceinline__ u64 ld_stream_u64(const u64 *p) { return __ldcs(p); }
+__device__ __forceinline__ ulonglong2 ld_stream_u64x2(const u64 *p) { return __ldcs(reinterpret_cast<const ulonglong2 *>(p)); }
 __device__ __forceinline__ void st_stream_u64(u64 *p, u64 v) { __stcs(p, v); }
 #else   // tests/cpu_emul: same source run sequentially on the host, see tests/cpu_emul/cuda_shim.h
 inline u64 ld_cg_u64(const u64 *p) { return *p; }
 inline u32 ld_cg_u32(const u32 *p) { return *p; }
+inline void ld_cg_256(const void *p, u64 &a, u64 &b, u64 &c, u64 &d)
+{
+    const u64 *q = (const u64 *)p;
+    a = q[0]; b = q[1]; c = q[2]; d = q[3];
+}
+inline void st_cg_256(void *p, u64 a, u64 b, u64 c, u64 d)
+{
+    u64 *q = (u64 *)p;
+    q[0] = a; q[1] = b; q[2] = c; q[3] = d;
+}
 inline void red_add_u32(u32 *p, u32 v) { *p += v; }
 inline void red_add_u64(u64 *p, u64 v) { *p += v; }
 inline void st_cg_u64(u64 *p, u64 v) { *p = v; }
@@ -164,6 +188,9 @@ inline u64 atom_add_keep_u64(u64 *p, u64 v, u64) { u64 o = *p; *p += v; return o
 inline void red_add_keep_u64(u64 *p, u64 v, u64) { *p += v; }
 inline void prefetch_keep(const void *) {}
 inline u64 ld_stream_u64(const u64 *p) { return *p; }
+struct ulonglong2 { u64 x, y; };
+inline ulonglong2 make_ulonglong2(u64 x, u64 y) { return ulonglong2{x, y}; }
+inline ulonglong2 ld_stream_u64x2(const u64 *p) { return ulonglong2{p[0], p[1]}; }
 inline void st_stream_u64(u64 *p, u64 v) { *p = v; }
 #endif
 
@@ -311,9 +338,17 @@ __device__ __forceinline__ int wide_insert(Slot<W> *table, u64 cap, const u64 *k
         if (cs == 0) {
             const u32 old = atomicCAS(&s->cs, 0u, CS_LOCKED);
             if (old == 0) {
+                if constexpr (W <= 3) {                  // sector-sized slot: one 256-bit store publishes key and count
+                    u64 q[4] = {0, 0, 0, 0};
 #pragma unroll
-                for (int j = 0; j < W; ++j) st_cg_u64(&s->key[j], key[j]);
-                st_release_u32(&s->cs, add);          // key words become visible before the count
+                    for (int j = 0; j < W; ++j) q[j] = key[j];
+                    q[W] = add;
+                    st_cg_256(s, q[0], q[1], q[2], q[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < W; ++j) st_cg_u64(&s->key[j], key[j]);
+                    st_release_u32(&s->cs, add);          // key words become visible before the count
+                }
                 return 1;
             }
             cs = old;

@@ -192,9 +192,21 @@ void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *counts, v
                 overflow_keys, overflow_cap, opts);
         return;
     }
-    const int grid = (int)std::min<u64>(tiles, (u64)sm_count * PASSB_WIDE_CTAS);
-    switch (table.words) {
+    if (getenv("PBK_WIDE_SERIAL")) {                             // the one-key-at-a-time kernel
+        const int grid = (int)std::min<u64>(tiles, (u64)sm_count * PASSB_WIDE_CTAS);
+        switch (table.words) {
 #define PBK_CASE_W(Wv) case Wv: bucket_insert_kernel<Wv><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, b_first,   \
+                b_end, (u64 *)d_desc, Table<Wv>(table.slots, table.cap), Table<Wv>(remote.slots, remote.cap), shard.n_shards,    \
+                shard.rank, ctr, overflow_keys, overflow_cap); break;
+        PBK_CASE_W(2) PBK_CASE_W(3) PBK_CASE_W(4) PBK_CASE_W(5) PBK_CASE_W(6) PBK_CASE_W(7) PBK_CASE_W(8)
+#undef PBK_CASE_W
+        default: break;
+        }
+        return;
+    }
+    const int grid = (int)std::min<u64>(tiles, (u64)sm_count * 2);
+    switch (table.words) {
+#define PBK_CASE_W(Wv) case Wv: bucket_insert_wide_kernel<Wv><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, b_first,   \
             b_end, (u64 *)d_desc, Table<Wv>(table.slots, table.cap), Table<Wv>(remote.slots, remote.cap), shard.n_shards,    \
             shard.rank, ctr, overflow_keys, overflow_cap); break;
     PBK_CASE_W(2) PBK_CASE_W(3) PBK_CASE_W(4) PBK_CASE_W(5) PBK_CASE_W(6) PBK_CASE_W(7) PBK_CASE_W(8)

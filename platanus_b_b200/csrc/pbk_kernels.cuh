@@ -10,7 +10,7 @@ struct TableView {
     u64   cap;         // number of slots
     int   words;       // W
     u64   capacity() const { return cap; }
-    size_t slot_bytes() const { return words == 1 ? 8 : 8 * (size_t)words + 8; }   // compact vs wide slots
+    size_t slot_bytes() const { return words == 1 ? 8 : words <= 3 ? 32 : 8 * (size_t)words + 8; }   // compact / sector-sized / wide slots
     size_t bytes() const { return slot_bytes() * cap; }
 };
 

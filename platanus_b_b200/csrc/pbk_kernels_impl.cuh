@@ -871,6 +871,181 @@ bucket_insert_compact_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, cons
     }
 }
 
+// Pass B for multi-word keys (k > 32), batched like the one-word kernel: a thread works on PASSBW_KPT<W> new keys plus
+// one deferred key per round; the state words of all their slots are loaded together, then the claims (CAS) and the
+// key words of the occupied slots, then the matching keys get their reduction.  A slot that is locked by a claimer, a
+// lost claim or a slot held by another key is not waited for: the key goes on the per-warp list (as an index into the
+// bucket store, 10 bytes for any W) and retries with the next round.  bucket_insert_kernel<W> above is the one-key-
+// at-a-time form of the same protocol (kept selectable: PBK_WIDE_SERIAL=1).
+template <int W> struct PASSBW_KPT { static constexpr int value = W <= 3 ? 4 : 2; };
+constexpr u32 PASSBW_REMOTE = 1u << 9;               // deferred-entry flag above the probe count (MAX_PROBE < 256)
+
+template <int W>
+__global__ void __launch_bounds__(PASSB_THREADS, 2)
+bucket_insert_wide_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const PassBBucket *__restrict__ bk,
+                          u32 b_first, u32 b_end, u64 *ticket, Table<W> table, Table<W> remote, u32 n_shards, u32 rank,
+                          Counters *ctr, u64 *ovf, u64 ovf_cap)
+{
+    constexpr int KPT = PASSBW_KPT<W>::value, ROUNDS = PASSB_KPT / KPT, E = KPT + 1;
+    constexpr int DEF_CAP = 32 * (KPT + 2);
+    __shared__ u64 s_ticket[2];
+    __shared__ u64 s_def_i[PASSB_THREADS / 32][DEF_CAP];
+    __shared__ uint16_t s_def_m[PASSB_THREADS / 32][DEF_CAP];
+    const u32 nb = b_end - b_first, tid = threadIdx.x, nthreads = blockDim.x;
+    const u32 wsize = nthreads < 32u ? nthreads : 32u;
+    const u32 lane = tid % wsize, warp = tid / wsize;
+    u64 *def_i = s_def_i[warp];
+    uint16_t *def_m = s_def_m[warp];
+    u32 n_def = 0, newk = 0, newr = 0, lb = 0;
+    const u32 round_keys = nthreads * KPT, tile_keys = round_keys * ROUNDS;
+    if (tid == 0) { s_ticket[0] = atomicAdd(ticket, 1ull); s_ticket[1] = atomicAdd(ticket, 1ull); }
+    __syncthreads();
+    const u64 n_tiles = bk[nb].tile_start;
+
+    // one round: `n_new` keys starting at key index `first` (0 = only deferred keys)
+    auto round = [&](u64 first, u32 n_new) {
+        u64 key[E][W], kw[E][W], gi[E];
+        Slot<W> *sp[E];
+        u32 d[E], cs[E], act[E];                    // act: 0 none, 1 compare, 2 claim attempt, 3 locked (retry)
+        bool live[E], rem[E];
+        // deferred key of an earlier round (top of the warp's list)
+        const u32 take = n_def < wsize ? n_def : wsize;
+        __syncwarp();
+        live[KPT] = lane < take;
+        gi[KPT] = live[KPT] ? def_i[n_def - 1 - lane] : 0;
+        const u32 xm = live[KPT] ? def_m[n_def - 1 - lane] : 0u;
+        __syncwarp();
+        n_def -= take;
+        d[KPT] = xm & 0xFFu;
+#pragma unroll
+        for (int q = 0; q < KPT; ++q) {
+            const u32 i = (u32)q * nthreads + tid;
+            live[q] = i < n_new;
+            gi[q] = first + i;
+            d[q] = 0;
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            if constexpr (W == 2) {                   // 16-byte entries: one vector load
+                ulonglong2 v = make_ulonglong2(0, 0);
+                if (live[e]) v = ld_stream_u64x2(bkt_keys + gi[e] * 2);
+                key[e][0] = v.x; key[e][1] = v.y;
+            } else {
+#pragma unroll
+                for (int w = 0; w < W; ++w) key[e][w] = live[e] ? ld_stream_u64(bkt_keys + gi[e] * W + w) : 0;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const u64 h = hash_key<W>(key[e]);
+            rem[e] = n_shards > 1 && shard_of_hash(h, n_shards) != rank;
+            const Table<W> &tb = rem[e] ? remote : table;
+            u64 idx = __umul64hi(h, tb.cap) + d[e];
+            if (idx >= tb.cap) idx -= tb.cap;
+            sp[e] = tb.slots + idx;
+            cs[e] = 0;
+            if constexpr (W <= 3) {                   // sector-sized slot: key words and state word in ONE request
+                if (live[e]) {
+                    u64 q[4];
+                    ld_cg_256(sp[e], q[0], q[1], q[2], q[3]);
+#pragma unroll
+                    for (int w = 0; w < W; ++w) kw[e][w] = q[w];
+                    cs[e] = (u32)q[W];
+                }
+            } else {
+                if (live[e]) cs[e] = ld_cg_u32(&sp[e]->cs);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            act[e] = 0;
+            if (!live[e]) continue;
+            if (cs[e] == 0) { act[e] = 2; cs[e] = atomicCAS(&sp[e]->cs, 0u, CS_LOCKED); }
+            else if (cs[e] == CS_LOCKED) act[e] = 3;
+            else {
+                act[e] = 1;
+                if constexpr (W > 3) {
+#pragma unroll
+                    for (int w = 0; w < W; ++w) kw[e][w] = ld_cg_u64(&sp[e]->key[w]);
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            u32 m = 0xFFFFu;                         // 0xFFFF = finished, else the list entry of the retry
+            if (act[e] == 2) {
+                if (cs[e] == 0) {                    // the slot is ours
+                    if constexpr (W <= 3) {
+                        // sector-sized slot: key words and count 1 in ONE 256-bit store (the release fence of the
+                        // word-by-word form cost as many stall cycles as all the loads of the kernel together)
+                        u64 q[4] = {0, 0, 0, 0};
+#pragma unroll
+                        for (int w = 0; w < W; ++w) q[w] = key[e][w];
+                        q[W] = 1ull;
+                        st_cg_256(sp[e], q[0], q[1], q[2], q[3]);
+                    } else {                         // key words first, then the count publishes them
+#pragma unroll
+                        for (int w = 0; w < W; ++w) st_cg_u64(&sp[e]->key[w], key[e][w]);
+                        st_release_u32(&sp[e]->cs, 1u);
+                    }
+                    if (rem[e]) ++newr; else ++newk;
+                } else {
+                    m = d[e] | (rem[e] ? PASSBW_REMOTE : 0u);           // somebody else got it: look again next round
+                }
+            } else if (act[e] == 3) {
+                m = d[e] | (rem[e] ? PASSBW_REMOTE : 0u);
+            } else if (act[e] == 1) {
+                bool eq = true;
+#pragma unroll
+                for (int w = 0; w < W; ++w) eq &= (kw[e][w] == key[e][w]);
+                if (eq) red_add_u32(&sp[e]->cs, 1u);
+                else if (d[e] + 1 >= (u32)MAX_PROBE) spill_key<W>(key[e], ctr, ovf, ovf_cap);
+                else m = (d[e] + 1) | (rem[e] ? PASSBW_REMOTE : 0u);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, m != 0xFFFFu);
+            if (bal == 0) continue;
+            if (m != 0xFFFFu) {
+                const u32 pos = n_def + (u32)__popc(bal & ((1u << lane) - 1u));
+                def_i[pos] = gi[e];
+                def_m[pos] = (uint16_t)m;
+            }
+            n_def += (u32)__popc(bal);
+        }
+    };
+
+    int par = 0;
+    u64 t = s_ticket[0];
+    while (t < n_tiles) {
+        while (bk[lb + 1].tile_start <= t) ++lb;
+        const u64 j = t - bk[lb].tile_start, n = bk[lb].n_keys;
+        const u64 nt = bk[lb + 1].tile_start - bk[lb].tile_start;
+        const u64 t_next = s_ticket[par ^ 1];
+        __syncthreads();
+        if (tid == 0) s_ticket[par] = atomicAdd(ticket, 1ull);
+        if (bk[lb].pf_base) passb_prefetch(bk[lb].pf_base, bk[lb].pf_lines, j, nt, tid, nthreads);
+        if (bk[lb].pf_base2) passb_prefetch(bk[lb].pf_base2, bk[lb].pf_lines2, j, nt, tid, nthreads);
+        const u64 first = (u64)(b_first + lb) * seg_cap + j * tile_keys;
+        const u64 left = n - j * tile_keys;
+#pragma unroll 1
+        for (u64 o = 0; o < left && o < tile_keys; o += round_keys) {
+#pragma unroll 1
+            while (n_def > wsize) round(0, 0u);      // a round may only start with at most one batch listed
+            round(first + o, (u32)min((u64)round_keys, left - o));
+        }
+        __syncthreads();
+        t = t_next;
+        par ^= 1;
+    }
+#pragma unroll 1
+    while (n_def) round(0, 0u);                      // nobody ever waits, so the list drains
+    newk = warp_sum_u32(newk);
+    newr = warp_sum_u32(newr);
+    if ((tid & 31) == 0) {
+        if (newk) atomicAdd(&ctr->new_keys, (u64)newk);
+        if (newr) atomicAdd(&ctr->new_keys_remote, (u64)newr);
+    }
+}
+
 // =================================================================================================
 // table maintenance
 // =================================================================================================
