@@ -33,6 +33,10 @@ constexpr u32 COUNT_SAT = 65534u;         // counter.h:468
 constexpr int MAX_PROBE = 192;            // W >= 2: longer probe runs go to the overflow list
 constexpr int STREAM_PAD_WORDS = 16;      // zero words in front of stream / flag arrays
 constexpr int PART_MAX_BUCKETS = 512;     // hash-range buckets of the partitioned path
+#ifndef PBK_PART_WIN1
+#define PBK_PART_WIN1 16
+#endif
+constexpr int PART_WIN1 = PBK_PART_WIN1;  // windows of one stream word a Pass A thread handles per tile, one-word keys
 
 // compact (k <= 32) slot format
 constexpr int CT_DISP_BITS = 7;           // displacement + 1 in 1..127, 0 = slot not (yet) owned

@@ -101,9 +101,9 @@ PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words, siz
     P = std::min<u64>(P, std::min<u64>((u64)PART_MAX_BUCKETS, entries / 24));
     p.n_buckets = (u32)P;
     p.bin_cap = (u32)(entries / P);
-    // one tile = threads * win window ends (win = 32, 16, 8 for 1, 2, >= 3 key words), ~85 % of them valid; keep the
+    // one tile = threads * win window ends (win = PART_WIN1, 16, 8 for 1, 2, >= 3 key words), ~85 % of them valid; keep the
     // mean bin fill at 60 % of the bin
-    const double win = words == 1 ? 32.0 : words == 2 ? 16.0 : 8.0;
+    const double win = words == 1 ? (double)PART_WIN1 : words == 2 ? 16.0 : 8.0;
     u64 threads = (u64)(p.bin_cap * 0.6 * (double)P / (win * 0.85));
     threads = std::min<u64>(512, threads / 32 * 32);
     p.threads = (int)std::max<u64>(64, threads);
@@ -127,7 +127,7 @@ void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64
                       u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st)
 {
     if (word_end <= word_begin) return;
-    const u64 subs = words == 1 ? 1 : words == 2 ? 2 : 4;       // 32 / PART_WIN<W>: work items per stream word
+    const u64 subs = words == 1 ? 32 / PART_WIN1 : words == 2 ? 2 : 4;       // 32 / PART_WIN<W>: work items per stream word
     const u64 tiles = ((word_end - word_begin) * subs + plan.threads - 1) / plan.threads;
     const int ctas = std::max(1, std::min(8, (int)((220 * 1024) / (plan.smem + 7 * 1024))));     // resident CTAs per SM
     const int grid = (int)std::min<u64>(tiles, (u64)sm_count * ctas);

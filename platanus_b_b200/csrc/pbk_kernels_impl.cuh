@@ -323,7 +323,7 @@ __device__ __forceinline__ void bucket_append_direct(const u64 *key, u32 b, u64 
 }
 
 // windows of one stream word a Pass A thread handles per tile
-template <int W> struct PART_WIN { static constexpr int value = W == 1 ? 32 : (W == 2 ? 16 : 8); };
+template <int W> struct PART_WIN { static constexpr int value = W == 1 ? PART_WIN1 : (W == 2 ? 16 : 8); };
 
 // OR of x << j for j in [0, w), 0 <= w <= 32 (doubling: at most five shift/or steps)
 __device__ __forceinline__ u64 smear_up(u64 x, int w)
@@ -358,9 +358,9 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
     const int pshift = (n_buckets > 1 && (n_buckets & (n_buckets - 1)) == 0) ? 64 - (31 - __clz(n_buckets)) : 0;
     u64 inst = 0;
 
-    // A thread takes PART_WIN<W> consecutive windows of one stream word per tile: all 32 for one-word keys; 16 or 8 for
-    // multi-word keys, whose bin entries are W words each -- with a whole word per thread the shared-memory bins left
-    // room for only 2-4 warps per SM.
+    // A thread takes PART_WIN<W> consecutive windows of one stream word per tile (16, 16, 8 for 1, 2, >= 3 key words):
+    // the shared-memory bins take 8 W bytes per staged instance, so a whole word per thread leaves room for only 16
+    // (one-word keys) or 2-4 (multi-word keys) warps per SM.
     constexpr int WIN = PART_WIN<W>::value, SUBS = 32 / WIN;
     const u64 n_items = (word_end - word_begin) * SUBS;
     for (u64 tile = (u64)blockIdx.x * blockDim.x; tile < n_items; tile += (u64)gridDim.x * blockDim.x) {
@@ -377,16 +377,20 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
             // its last k-1 positions starts a read (flags of this and the previous word; bit j = position j).
             const u64 cur = stream[wi];
             const u64 nn = ((u64)nflag[wi] << 32) | nflag[wi - 1], rr = ((u64)rflag[wi] << 32) | rflag[wi - 1];
-            const u32 valid = ~(u32)((smear_up(nn, k) | smear_up(rr, k - 1)) >> 32);
+            const u32 valid = (~(u32)((smear_up(nn, k) | smear_up(rr, k - 1)) >> 32) >> i0) & (WIN < 32 ? (1u << (WIN & 31)) - 1u : ~0u);
             if (valid) {
                 const u64 topmul = 1ull << top_shift;
                 u32 n_here = 0;
-                u64 f = stream[wi - 1], r = pair_reverse64(~f);
+                // rolling state = the 32 bases that end just before position i0 of this word
+                u64 f = i0 ? ((stream[wi - 1] << (2 * i0)) | (cur >> (64 - 2 * i0))) : stream[wi - 1];
+                u64 r = pair_reverse64(~f);
                 r = s ? (r >> s) : r;
+                u64 c = i0 ? cur << (2 * i0) : cur;
                 // (interleaving four windows' hash chains by hand was measured: slower -- more registers, no gain)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const u32 b = (u32)(cur >> (62 - 2 * i)) & 3u;
+                for (int i = 0; i < WIN; ++i) {
+                    const u32 b = (u32)(c >> 62);
+                    c <<= 2;
                     f = ((f << 2) | b) & top_mask;
                     r = (r >> 2) | ((u64)(3u - b) * topmul);
                     if ((valid >> i) & 1u) {
