@@ -46,7 +46,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
         objs = list(ex.map(compile_one, UNITS))
     if force or _stale(LIB, objs):
-        subprocess.run([NVCC, *ARCH, "-ccbin", "g++", "-shared", "-o", LIB, *objs, "-cudart", "static"],
+        subprocess.run([NVCC, *ARCH, "-ccbin", "g++", "-shared", "-o", LIB, *objs, "-cudart", "static", "-lpthread"],
                        check=True, env=env)
     return LIB
 

@@ -8,7 +8,12 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <thread>
+#include <utility>
 #include <vector>
+
+#include <fcntl.h>
+#include <unistd.h>
 
 namespace {
 
@@ -32,25 +37,6 @@ u64 calc_length(u64 len)
     for (u64 i = 1; i < 64; ++i)
         if ((len >> i) == 0) return i;
     return 64;
-}
-
-// LSD radix sort of (slot, index) pairs by slot
-void sort_by_slot(std::vector<u64> &slot, std::vector<u64> &idx, u64 max_slot)
-{
-    const size_t n = slot.size();
-    std::vector<u64> s2(n), i2(n);
-    int bits = 1;
-    while (bits < 64 && (max_slot >> bits)) ++bits;
-    for (int shift = 0; shift < bits; shift += 11) {
-        size_t hist[2049] = {0};
-        for (size_t i = 0; i < n; ++i) ++hist[((slot[i] >> shift) & 2047) + 1];
-        for (int b = 0; b < 2048; ++b) hist[b + 1] += hist[b];
-        for (size_t i = 0; i < n; ++i) {
-            size_t at = hist[(slot[i] >> shift) & 2047]++;
-            s2[at] = slot[i]; i2[at] = idx[i];
-        }
-        slot.swap(s2); idx.swap(i2);
-    }
 }
 
 }  // namespace
@@ -132,7 +118,7 @@ int pbk_write_kmer_occ_bin(const char *path, uint32_t k, const uint64_t *keys, c
     const u64 index_size = slots - 1, index_length = calc_length(slots);
     const u64 shifter = index_length >= 32 ? 0 : 2 * index_length;       // doubleHash.h:233-235
 
-    std::vector<u64> bitmap((slots + 63) / 64, 0), slot(n), idx(n);
+    std::vector<u64> bitmap((slots + 63) / 64, 0), slot(n);
     // the home slots are effectively random positions in a bitmap far larger than the caches: compute them a few
     // keys ahead and prefetch, so the placement loop does not pay one DRAM miss per key
     auto home_and_step = [&](u64 i, u64 *step) -> u64 {
@@ -160,35 +146,59 @@ int pbk_write_kmer_occ_bin(const char *path, uint32_t k, const uint64_t *keys, c
         }
         while (bitmap[v >> 6] >> (v & 63) & 1) v = (v + step) & index_size;   // find_any, keys are distinct
         bitmap[v >> 6] |= 1ull << (v & 63);
-        slot[i] = v; idx[i] = i;
+        slot[i] = v;
     }
     std::vector<u64>().swap(bitmap);
-    sort_by_slot(slot, idx, index_size);
 
-    FILE *fp = fopen(path, "wb");
-    if (!fp) return PBK_E_IO;
+    // Records go out in ascending slot order (writeTable scans the table, doubleHash.h:270).  The slot space is cut
+    // into T ranges; every thread collects the entries of its range, sorts them, formats the records and writes
+    // them at its own file offset (the reference does all of this in one serial scan of up to 2^29+ slots).
     const u64 k64 = k, raw = key_raw_size(k);
     const size_t rec = 8 + raw + (k > 160 ? 8 * words : 0) + 2;
-    std::vector<unsigned char> buf;
-    buf.reserve(rec * 65536 + 16);
-    buf.resize(16);
-    memcpy(&buf[0], &k64, 8);                                            // counter.h:960
-    memcpy(&buf[8], &index_size, 8);                                     // doubleHash.h:268
-    bool ok = true;
-    for (u64 j = 0; j < n && ok; ++j) {
-        const size_t at = buf.size();
-        buf.resize(at + rec, 0);
-        unsigned char *p = &buf[at];
-        const uint64_t *key = keys + idx[j] * words;
-        memcpy(p, &slot[j], 8);                                          // doubleHash.h:272
-        if (k <= 32) memcpy(p + 8, key, 8);
-        else if (k <= 160) { memcpy(p + 8 + 16, &k64, 8); memcpy(p + 8 + 24, key, 8 * words); }   // {vptr, value*, len, entity}
-        else { memcpy(p + 8 + 16, &k64, 8); memcpy(p + 8 + 24, key, 8 * words); }                 // {vptr, value*, len} + words (doubleHash.h:77-80)
-        memcpy(p + rec - 2, &counts[idx[j]], 2);                         // doubleHash.h:275
-        if (buf.size() >= rec * 65536) { ok = fwrite(buf.data(), 1, buf.size(), fp) == buf.size(); buf.clear(); }
+    const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return PBK_E_IO;
+    unsigned char header[16];
+    memcpy(header, &k64, 8);                                             // counter.h:960
+    memcpy(header + 8, &index_size, 8);                                  // doubleHash.h:268
+    bool ok = pwrite(fd, header, 16, 0) == 16;
+    unsigned T = n < 200000 ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<u64> range_count(T, 0), range_first(T + 1, 0);
+    auto range_of = [&](u64 v) -> unsigned { return (unsigned)(((unsigned __int128)v * T) / slots); };
+    for (u64 i = 0; i < n; ++i) range_count[range_of(slot[i])] += 1;
+    for (unsigned t = 0; t < T; ++t) range_first[t + 1] = range_first[t] + range_count[t];
+    std::vector<int> thread_ok(T, 1);
+    auto work = [&](unsigned t) {
+        std::vector<std::pair<u64, u64> > mine;
+        mine.reserve(range_count[t]);
+        for (u64 i = 0; i < n; ++i)
+            if (range_of(slot[i]) == t) mine.push_back(std::make_pair(slot[i], i));
+        std::sort(mine.begin(), mine.end());
+        const size_t CH = 65536;
+        std::vector<unsigned char> buf(rec * CH);
+        for (size_t j0 = 0; j0 < mine.size(); j0 += CH) {
+            const size_t m = std::min(CH, mine.size() - j0);
+            memset(buf.data(), 0, rec * m);
+            for (size_t j = 0; j < m; ++j) {
+                unsigned char *p = &buf[rec * j];
+                const u64 i = mine[j0 + j].second;
+                const uint64_t *key = keys + i * words;
+                memcpy(p, &mine[j0 + j].first, 8);                       // doubleHash.h:272
+                if (k <= 32) memcpy(p + 8, key, 8);
+                else { memcpy(p + 8 + 16, &k64, 8); memcpy(p + 8 + 24, key, 8 * words); }   // {vptr, value*, len, entity | words} (doubleHash.h:73-80)
+                memcpy(p + rec - 2, &counts[i], 2);                      // doubleHash.h:275
+            }
+            const off_t at = (off_t)(16 + rec * (range_first[t] + j0));
+            if (pwrite(fd, buf.data(), rec * m, at) != (ssize_t)(rec * m)) { thread_ok[t] = 0; return; }
+        }
+    };
+    if (T == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; ++t) th.push_back(std::thread(work, t));
+        for (unsigned t = 0; t < T; ++t) th[t].join();
     }
-    if (ok && !buf.empty()) ok = fwrite(buf.data(), 1, buf.size(), fp) == buf.size();
-    ok = (fclose(fp) == 0) && ok;
+    for (unsigned t = 0; t < T; ++t) ok = ok && thread_ok[t];
+    ok = (close(fd) == 0) && ok;
     return ok ? PBK_OK : PBK_E_IO;
 }
 
