@@ -10,6 +10,7 @@
 // pbk_push_reads, and the GPU does the 2-bit packing.  `-t` bounds the parser threads; `-m` only
 // determines doubleHashSize (the kmer_occ.bin header), as in counter.h:300-309.
 #include "pbk_counter.hpp"
+#include "pbk_ingest.hpp"
 
 #include <chrono>
 #include <cmath>
@@ -94,19 +95,9 @@ struct Mapped {
     ~Mapped() { if (p) munmap((void *)p, n); if (fd >= 0) close(fd); }
 };
 
-struct Line { const char *s; size_t len; };
-struct LineReader {                      // std::getline semantics: '\n' stripped, last line may lack it
-    const char *cur, *end;
-    LineReader(const char *p, size_t n) : cur(p), end(p + n) {}
-    bool next(Line &l)
-    {
-        if (cur >= end) return false;
-        const char *nl = (const char *)memchr(cur, '\n', (size_t)(end - cur));
-        l.s = cur;
-        if (nl) { l.len = (size_t)(nl - cur); cur = nl + 1; } else { l.len = (size_t)(end - cur); cur = end; }
-        return true;
-    }
-};
+using pbk::ingest::Line;
+using pbk::ingest::LineReader;
+using pbk::ingest::ReadSink;
 
 // BaseCommand::checkFileFormat (baseCommand.cpp:29-50): 0 unknown, 1 FASTA, 2 FASTQ
 int check_file_format(const Mapped &f)
@@ -173,26 +164,13 @@ private:
     std::vector<Batch *> all_;
 };
 
-// where parsed reads go: SEQ::convertFromString + writeTemporaryFile in the reference (common.h:460, 426)
-struct ReadSink {
-    std::string read;                    // the read being assembled from lines
-    virtual ~ReadSink() {}
-    void append(const Line &l) { read.append(l.s, l.len); }
-    void flush()
-    {
-        if (read.size() >= 500000) throw pbk::ReadError();                  // common.h:465
-        emit();
-        read.clear();
-    }
-    virtual void emit() = 0;
-};
-
 // the fast path: ASCII batches in pinned memory; a read longer than a batch cannot exist (MAX_READ_LEN)
 struct BatchSink : ReadSink {
     BatchQueue &q; Batch *cur;
     explicit BatchSink(BatchQueue &q_) : q(q_), cur(q_.get_free()) {}
     void emit()
     {
+        if (read.size() >= 500000) throw pbk::ReadError();                  // common.h:465
         if (cur->used + read.size() > cur->cap) { q.put_full(cur); cur = q.get_free(); }
         memcpy(cur->bases + cur->used, read.data(), read.size());
         cur->used += read.size();
@@ -210,6 +188,7 @@ struct SeqTmpSink : ReadSink {
     explicit SeqTmpSink(std::vector<FILE *> &fp_) : fp(fp_), i(0) {}
     void emit()
     {
+        if (read.size() >= 500000) throw pbk::ReadError();                  // common.h:465
         static const char code[] = ".\x0.\x1\x3..\x2......\x4";               // platanus::Char2Bin (common.h:256)
         pos.clear();
         codes.resize(read.size());
@@ -226,37 +205,11 @@ struct SeqTmpSink : ReadSink {
     }
 };
 
-// Assemble::readFastaUncompressed (assemble.cpp:816-848)
-void parse_fasta(const Mapped &f, ReadSink &out)
+// one file, serially (the -seq_tmp route deals reads round-robin in file order like the reference)
+void parse_whole_file(const Mapped &f, bool fastq, ReadSink &out)
 {
-    LineReader r(f.p, f.n);
-    Line l;
-    while (r.next(l)) if (l.len && l.s[0] == '>') break;
-    while (r.next(l)) {
-        if (!(l.len && l.s[0] == '>')) out.append(l);
-        else if (!out.read.empty()) out.flush();
-    }
-    out.flush();                         // unconditional, also for an empty last read (assemble.cpp:844-845)
-}
-
-// Assemble::readFastqUncompressed (assemble.cpp:902-942): lines that do not start with '@' extend the
-// read until a line starting with '+'; the next line starting with '@' flushes it
-void parse_fastq(const Mapped &f, ReadSink &out)
-{
-    LineReader r(f.p, f.n);
-    Line l;
-    bool flag = true;
-    while (r.next(l)) if (l.len && l.s[0] == '@') break;
-    while (r.next(l)) {
-        if (l.len == 0) continue;
-        if (l.s[0] != '@') {
-            if (flag && l.s[0] != '+') out.append(l); else flag = false;
-        } else {
-            if (!out.read.empty()) out.flush();
-            flag = true;
-        }
-    }
-    out.flush();
+    const pbk::ingest::Plan pl = pbk::ingest::plan_ranges(f.p, f.n, fastq, 1);
+    pbk::ingest::parse_range(f.p, pl.s[0], pl.s[1], fastq, true, out);
 }
 
 // ---- Assemble::extendKmer and friends (assemble.cpp:657-736): the stderr schedule ------------------
@@ -346,7 +299,7 @@ void exec(Options &opt)
         for (u64 i = 0; i < num_thread; ++i) read_fp.push_back(pbk::Counter::makeTemporaryFile(opt.single["-tmp"]));
         SeqTmpSink sink(read_fp);
         for (size_t i = 0; i < files.size(); ++i) {
-            if (types[i] == 1) parse_fasta(*maps[i], sink); else parse_fastq(*maps[i], sink);
+            parse_whole_file(*maps[i], types[i] == 2, sink);
             delete maps[i];
         }
         std::cerr << "K = " << k0 << ", saving kmers from reads..." << std::endl;
@@ -356,32 +309,51 @@ void exec(Options &opt)
     pt.mark("open + sniff inputs");
     std::cerr << "K = " << k0 << ", saving kmers from reads..." << std::endl;                   // assemble.cpp:306
 
-    // ingest: one parser per file, at most -t at a time, started BEFORE the CUDA context is created so that parsing
-    // runs behind that fixed cost; the main thread then feeds the GPU.  Enough batch buffers for ~2 GB of bases.
+    // ingest: the files are cut into byte ranges that are parsed independently (pbk_ingest.hpp), -t workers at a
+    // time, started BEFORE the CUDA context is created so that parsing runs behind that fixed cost; the main thread
+    // then feeds the GPU.  Enough batch buffers for ~2 GB of bases.
     size_t total_bytes = 0;
     for (size_t i = 0; i < maps.size(); ++i) total_bytes += maps[i]->n;
-    const size_t n_par = (size_t)std::min<u64>(num_thread, files.size());
+    // PBK_INGEST_RANGE_BYTES: smallest byte range handed to one worker (default 32 MiB; tests set it low so that small
+    // files are cut into many ranges too)
+    size_t range_min = (size_t)32 << 20;
+    if (const char *e = getenv("PBK_INGEST_RANGE_BYTES")) { const long long v = atoll(e); if (v > 0) range_min = (size_t)v; }
+    const size_t range_target = std::max<size_t>(range_min, total_bytes / (size_t)(num_thread * 2) + 1);
+    struct Item { size_t file; unsigned t; };
+    std::vector<pbk::ingest::Plan> plans;
+    std::vector<Item> items;
+    for (size_t i = 0; i < maps.size(); ++i) {
+        const unsigned T = (unsigned)std::min<size_t>(64, std::max<size_t>(1, (maps[i]->n + range_target - 1) / range_target));
+        plans.push_back(pbk::ingest::plan_ranges(maps[i]->p, maps[i]->n, types[i] == 2, T));
+        for (unsigned t = 0; t < T; ++t)
+            if (plans[i].s[t] < plans[i].s[t + 1] || t == plans[i].final_owner) items.push_back(Item{i, t});
+    }
+    // every worker holds one batch buffer while it parses: at most 12 workers on 16 buffers, so that full batches can
+    // queue up behind the CUDA context creation without a worker waiting for a buffer to start with
+    const size_t n_par = std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)num_thread, 12), items.size()));
     const size_t batch_bytes = (size_t)128 << 20;
     const int n_buf = (int)std::min<size_t>(16, std::max<size_t>(n_par * 2 + 1, total_bytes / 2 / batch_bytes + n_par + 1));
     BatchQueue q(batch_bytes, n_buf);
     std::mutex err_m;
     std::vector<pbk::ErrorBase> errors;
     std::vector<std::thread> workers;
-    size_t next_file = 0;
+    size_t next_item = 0;
     std::mutex next_m;
     for (size_t w = 0; w < n_par; ++w) {
         q.add_producer();
         workers.push_back(std::thread([&]() {
+            BatchSink sink(q);
             for (;;) {
                 size_t i;
-                { std::lock_guard<std::mutex> g(next_m); i = next_file++; }
-                if (i >= files.size()) break;
-                BatchSink sink(q);
+                { std::lock_guard<std::mutex> g(next_m); i = next_item++; }
+                if (i >= items.size()) break;
+                const Item it = items[i];
+                const pbk::ingest::Plan &pl = plans[it.file];
                 try {
-                    if (types[i] == 1) parse_fasta(*maps[i], sink); else parse_fastq(*maps[i], sink);
-                } catch (pbk::ErrorBase &e) { std::lock_guard<std::mutex> g(err_m); errors.push_back(e); }
-                sink.finish();
+                    pbk::ingest::parse_range(maps[it.file]->p, pl.s[it.t], pl.s[it.t + 1], types[it.file] == 2, it.t == pl.final_owner, sink);
+                } catch (pbk::ErrorBase &e) { std::lock_guard<std::mutex> g(err_m); errors.push_back(e); sink.read.clear(); }
             }
+            sink.finish();
             q.producer_done();
         }));
     }

@@ -1,0 +1,33 @@
+// TEST ONLY: prints the reads pbk_ingest.hpp produces for a file cut into T ranges, one read per line (workers run one
+// after the other here, so the output is in file order), to be compared with the serial parse and with the oracle.
+#include "../../platanus_b_b200/host/pbk_ingest.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+struct PrintSink : pbk::ingest::ReadSink {
+    void emit() { fwrite(read.data(), 1, read.size(), stdout); fputc('\n', stdout); }
+};
+
+int main(int argc, char **argv)
+{
+    if (argc < 4) return 2;
+    FILE *fp = fopen(argv[1], "rb");
+    if (!fp) return 3;
+    std::vector<char> buf;
+    char tmp[65536];
+    size_t got;
+    while ((got = fread(tmp, 1, sizeof tmp, fp)) > 0) buf.insert(buf.end(), tmp, tmp + got);
+    fclose(fp);
+    const bool fastq = std::string(argv[2]) == "fq";
+    const unsigned T = (unsigned)atoi(argv[3]);
+    const pbk::ingest::Plan pl = pbk::ingest::plan_ranges(buf.data(), buf.size(), fastq, T);
+    for (unsigned t = 0; t < pl.n_workers; ++t) {
+        PrintSink sink;
+        if (pl.s[t] < pl.s[t + 1] || t == pl.final_owner)
+            pbk::ingest::parse_range(buf.data(), pl.s[t], pl.s[t + 1], fastq, t == pl.final_owner, sink);
+    }
+    return 0;
+}

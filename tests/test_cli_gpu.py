@@ -24,14 +24,14 @@ def cli():
     return pbuild.build_cli()
 
 
-def run_ours(cli, files, k, workdir, prefix="gpu", threads=2, mem_gb=1, n_opt=0, repeat=False, extra=()):
+def run_ours(cli, files, k, workdir, prefix="gpu", threads=2, mem_gb=1, n_opt=0, repeat=False, extra=(), env=None):
     cmd = [cli, "assemble", "-kmer_occ_only", "-k", str(k), "-t", str(threads), "-m", str(mem_gb), "-tmp", workdir,
            "-o", os.path.join(workdir, prefix), "-f", *files, *extra]
     if n_opt:
         cmd += ["-n", str(n_opt)]
     if repeat:
         cmd += ["-repeat"]
-    return subprocess.run(cmd, capture_output=True, text=True, cwd=workdir)
+    return subprocess.run(cmd, capture_output=True, text=True, cwd=workdir, env=dict(os.environ, **(env or {})))
 
 
 def markers(stderr, k):
@@ -94,6 +94,31 @@ def test_reference_kmer_divide_reads_our_bin(oracle, cli, k, tmp_path):
         assert produced, q.stderr
         outs[tag] = [open(tmp_path / f).read() for f in produced]
     assert outs["ref"] == outs["gpu"]
+
+
+@pytest.mark.parametrize("k", [32, 75])
+def test_range_parallel_ingest_gives_the_same_outputs(oracle, cli, k, tmp_path):
+    """The files cut into ~60 byte ranges parsed by 8 workers (pbk_ingest.hpp; PBK_INGEST_RANGE_BYTES forces small
+    ranges) against one range per file: same .tsv bytes, same stderr markers, same sorted dump.  FASTQ and FASTA."""
+    O = oracle
+    rs = synth.make_reads(synth.config("C1", scale=1 / 50))
+    files = list(synth.write_fastq(rs, str(tmp_path / "r_1.fq"), str(tmp_path / "r_2.fq")))
+    b, o = rs.flat()
+    fa = tmp_path / "r_3.fa"
+    with open(fa, "w") as fh:                                   # a FASTA file with multi-line records on top
+        for i in range(0, 20000):
+            s = bytes(b[int(o[i]):int(o[i + 1])]).decode()
+            fh.write(f">r{i}\n{s[:70]}\n{s[70:]}\n")
+    files.append(str(fa))
+    outs = []
+    for prefix, threads, env in (("one", 1, {"PBK_INGEST_RANGE_BYTES": str(1 << 40)}), ("many", 8, {"PBK_INGEST_RANGE_BYTES": str(1 << 20)})):
+        p = run_ours(cli, files, k, str(tmp_path), prefix=prefix, threads=threads, env=env)
+        assert p.returncode == 0, p.stderr
+        t = O.read_bin(str(tmp_path / f"{prefix}_kmer_occ.bin"))
+        assert t.reachable
+        outs.append((markers(p.stderr, k), open(tmp_path / f"{prefix}_{k}merFrq.tsv").read(), t.sorted_dump()))
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
+    assert np.array_equal(outs[0][2][0], outs[1][2][0]) and np.array_equal(outs[0][2][1], outs[1][2][1])
 
 
 def test_pbk_assemble_on_the_golden_inputs(oracle, cli, tmp_path):
