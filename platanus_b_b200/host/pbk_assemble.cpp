@@ -76,23 +76,13 @@ struct Options {
 };
 
 // ---- input files ---------------------------------------------------------------------------------
-struct Mapped {
-    const char *p; size_t n; int fd;
-    explicit Mapped(const std::string &name) : p(NULL), n(0), fd(-1)
+struct Mapped : pbk::ingest::MappedFile {                  // plain, gzip or bzip2 (pbk_ingest.hpp)
+    Mapped(const std::string &name, const std::string &tmp_dir)
     {
-        fd = open(name.c_str(), O_RDONLY);
-        if (fd < 0) throw pbk::FILEError(name);
-        struct stat st;
-        if (fstat(fd, &st) != 0) { close(fd); throw pbk::FILEError(name); }
-        n = (size_t)st.st_size;
-        if (n) {
-            void *m = mmap(NULL, n, PROT_READ, MAP_PRIVATE, fd, 0);
-            if (m == MAP_FAILED) { close(fd); throw pbk::FILEError(name); }
-            madvise(m, n, MADV_SEQUENTIAL);
-            p = (const char *)m;
-        }
+        const int rc = map(name, tmp_dir);
+        if (rc == -2) throw pbk::TMPError();
+        if (rc != 0) throw pbk::FILEError(name);
     }
-    ~Mapped() { if (p) munmap((void *)p, n); if (fd >= 0) close(fd); }
 };
 
 using pbk::ingest::Line;
@@ -259,7 +249,7 @@ void usage()
 {
     std::cerr << "\nUsage: pbk_assemble assemble -kmer_occ_only [Options]\nOptions:\n"
               << "    -o STR               : prefix of output files (default out)\n"
-              << "    -f FILE1 [FILE2 ...] : reads file (fasta or fastq, uncompressed)\n"
+              << "    -f FILE1 [FILE2 ...] : reads file (fasta or fastq; plain, gzip or bzip2)\n"
               << "    -k INT               : k-mer size (default 32)\n"
               << "    -n INT               : initial k-mer coverage cutoff (default 0, 0 means auto)\n"
               << "    -t INT               : number of threads (parsers; default 1)\n"
@@ -281,16 +271,34 @@ void exec(Options &opt)
     const unsigned k0 = (unsigned)atoi(opt.single["-k"].c_str());
     const std::string prefix = opt.single["-o"];
     const std::vector<std::string> &files = opt.multi["-f"];
+    const std::string tmp_dir = opt.single["-tmp"];
 
     PhaseTimer pt;
     pbk::Counter counter;
-    std::vector<int> types;
-    std::vector<Mapped *> maps;
-    for (size_t i = 0; i < files.size(); ++i) {
-        maps.push_back(new Mapped(files[i]));
-        const int t = check_file_format(*maps.back());
-        if (t == 0) throw pbk::ReadError("Read file is not FASTA/FASTQ format.");              // assemble.cpp:798
-        types.push_back(t);
+    // open (and, for gzip/bzip2 inputs, decompress: one `gzip -cd` per file, -t at a time) and sniff the inputs; the
+    // first failure in file order is the one reported, as in the reference's serial loop (assemble.cpp:162-163)
+    std::vector<int> types(files.size(), 0);
+    std::vector<Mapped *> maps(files.size(), (Mapped *)NULL);
+    {
+        std::vector<pbk::ErrorBase *> open_err(files.size(), (pbk::ErrorBase *)NULL);
+        std::vector<std::thread> openers;
+        std::mutex m;
+        size_t next = 0;
+        for (size_t w = 0; w < std::min<size_t>((size_t)num_thread, files.size()); ++w)
+            openers.push_back(std::thread([&]() {
+                for (;;) {
+                    size_t i;
+                    { std::lock_guard<std::mutex> g(m); i = next++; }
+                    if (i >= files.size()) return;
+                    try {
+                        maps[i] = new Mapped(files[i], tmp_dir);
+                        types[i] = check_file_format(*maps[i]);
+                        if (types[i] == 0) throw pbk::ReadError("Read file is not FASTA/FASTQ format.");   // assemble.cpp:798
+                    } catch (pbk::ErrorBase &e) { open_err[i] = new pbk::ErrorBase(e); }
+                }
+            }));
+        for (size_t w = 0; w < openers.size(); ++w) openers[w].join();
+        for (size_t i = 0; i < files.size(); ++i) if (open_err[i]) throw *open_err[i];
     }
     u64 double_hash_size = 0;
     if (opt.flag["-seq_tmp"]) {

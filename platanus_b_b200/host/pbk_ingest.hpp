@@ -14,11 +14,100 @@
 #define PBK_INGEST_HPP
 
 #include <cstddef>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 namespace pbk {
 namespace ingest {
+
+// ---- input files: plain, gzip or bzip2 (platanus::checkFileCompression / openFileAllowingCompression,
+//      common.cpp:88-143; readFastaCompressed / readFastqCompressed, assemble.cpp:851-885, 945-986) ----------------------
+// The reference asks `file -bL` whether a file is "gzip compressed" / "bzip2 compressed" and then reads the output of
+// `gzip -cd FILE` / `bzip2 -cd FILE` through a pipe with the same line loop as for plain files.  Here the type comes
+// from the magic numbers `file` itself goes by (1f 8b; "BZh"), and the same two programs write the plain text into
+// an unlinked temporary file in the -tmp directory, which is then mapped and parsed in ranges like any other input.
+// As in the reference, the decompressor's exit status is not looked at: a truncated archive yields the reads that
+// came out of it.
+enum Compression { UNCOMPRESSED = 0, GZIP = 1, BZIP2 = 2 };
+
+inline Compression sniff_compression(int fd)
+{
+    unsigned char m[3] = {0, 0, 0};
+    const ssize_t got = pread(fd, m, 3, 0);
+    if (got >= 2 && m[0] == 0x1f && m[1] == 0x8b) return GZIP;
+    if (got >= 3 && m[0] == 'B' && m[1] == 'Z' && m[2] == 'h') return BZIP2;
+    return UNCOMPRESSED;
+}
+
+// fd of an unlinked temp file holding the decompressed bytes of `name`; -1 if the temp file cannot be made
+inline int decompress_to_tmp(const std::string &name, Compression c, const std::string &tmp_dir)
+{
+    std::string templ = tmp_dir + "/XXXXXX";
+    std::vector<char> buf(templ.begin(), templ.end());
+    buf.push_back('\0');
+    const int out = mkstemp(buf.data());
+    if (out < 0) return -1;
+    unlink(buf.data());
+    const pid_t pid = fork();
+    if (pid < 0) { close(out); return -1; }
+    if (pid == 0) {                                          // child: PROGRAM -cd NAME > temp file (no shell in between)
+        dup2(out, 1);
+        close(out);
+        const char *prog = c == GZIP ? "gzip" : "bzip2";
+        execlp(prog, prog, "-cd", name.c_str(), (char *)NULL);
+        _exit(127);
+    }
+    int status = 0;
+    while (waitpid(pid, &status, 0) < 0) {}
+    return out;
+}
+
+struct MappedFile {
+    const char *p; size_t n; int fd; Compression compression;
+    MappedFile() : p(NULL), n(0), fd(-1), compression(UNCOMPRESSED) {}
+    ~MappedFile() { unmap(); }
+    // 0 = ok, -1 = cannot open / map the file (FILEError in the reference), -2 = no temp file (TMPError)
+    int map(const std::string &name, const std::string &tmp_dir)
+    {
+        unmap();
+        fd = open(name.c_str(), O_RDONLY);
+        if (fd < 0) return -1;
+        compression = sniff_compression(fd);
+        if (compression != UNCOMPRESSED) {
+            const int plain = decompress_to_tmp(name, compression, tmp_dir);
+            close(fd);
+            fd = plain;
+            if (fd < 0) return -2;
+        }
+        struct stat st;
+        if (fstat(fd, &st) != 0) { unmap(); return -1; }
+        n = (size_t)st.st_size;
+        if (n) {
+            void *m = mmap(NULL, n, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) { n = 0; unmap(); return -1; }
+            madvise(m, n, MADV_SEQUENTIAL);
+            p = (const char *)m;
+        }
+        return 0;
+    }
+    void unmap()
+    {
+        if (p) munmap((void *)p, n);
+        if (fd >= 0) close(fd);
+        p = NULL; n = 0; fd = -1;
+    }
+private:
+    MappedFile(const MappedFile &);
+    MappedFile &operator=(const MappedFile &);
+};
 
 struct Line { const char *s; size_t len; };
 

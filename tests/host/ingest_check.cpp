@@ -1,4 +1,4 @@
-// TEST ONLY: prints the reads pbk_ingest.hpp produces for a file cut into T ranges, one read per line (workers run one
+// TEST ONLY: prints the reads pbk_ingest.hpp produces for a (plain, gzip or bzip2) file cut into T ranges, one read per line (workers run one
 // after the other here, so the output is in file order), to be compared with the serial parse and with the oracle.
 #include "../../platanus_b_b200/host/pbk_ingest.hpp"
 
@@ -14,13 +14,9 @@ struct PrintSink : pbk::ingest::ReadSink {
 int main(int argc, char **argv)
 {
     if (argc < 4) return 2;
-    FILE *fp = fopen(argv[1], "rb");
-    if (!fp) return 3;
-    std::vector<char> buf;
-    char tmp[65536];
-    size_t got;
-    while ((got = fread(tmp, 1, sizeof tmp, fp)) > 0) buf.insert(buf.end(), tmp, tmp + got);
-    fclose(fp);
+    pbk::ingest::MappedFile f;                              // plain, gzip or bzip2
+    if (f.map(argv[1], argc > 4 ? argv[4] : "/tmp") != 0) return 3;
+    struct { const char *p; size_t n; const char *data() const { return p; } size_t size() const { return n; } } buf = {f.p, f.n};
     const bool fastq = std::string(argv[2]) == "fq";
     const unsigned T = (unsigned)atoi(argv[3]);
     const pbk::ingest::Plan pl = pbk::ingest::plan_ranges(buf.data(), buf.size(), fastq, T);

@@ -141,6 +141,27 @@ def test_pbk_assemble_on_the_golden_inputs(oracle, cli, tmp_path):
         assert np.array_equal(k2, g["keys"]) and np.array_equal(c2, g["counts"])
 
 
+def test_pbk_assemble_reads_gzip_and_bzip2_inputs(oracle, cli, tmp_path):
+    """readFast[aq]Compressed (assemble.cpp:851-885, 945-986): a gzip FASTQ + a bzip2 FASTA give the golden outputs of the
+    plain files (the reference itself cannot tell here: it asks the `file` utility, which this image lacks)."""
+    import shutil
+    if shutil.which("gzip") is None or shutil.which("bzip2") is None:
+        pytest.skip("gzip/bzip2 not installed")
+    O = oracle
+    case = G.CASE_BY_NAME["multi_k32_n2"]
+    g = np.load(G.golden_path(case), allow_pickle=False)
+    packed = []
+    for f, prog in zip(G.materialise(case, str(tmp_path)), ("gzip", "bzip2")):
+        packed.append(str(tmp_path / (os.path.basename(f) + ".z")))
+        with open(packed[-1], "wb") as out:
+            subprocess.run([prog, "-c", f], stdout=out, check=True)
+    p = run_ours(cli, packed, case.k, str(tmp_path), prefix="z", n_opt=case.n_opt)
+    assert p.returncode == 0, p.stderr
+    assert open(tmp_path / f"z_{case.k}merFrq.tsv").read() == str(g["tsv"])
+    k2, c2 = O.read_bin(str(tmp_path / "z_kmer_occ.bin")).sorted_dump()
+    assert np.array_equal(k2, g["keys"]) and np.array_equal(c2, g["counts"])
+
+
 def test_pbk_assemble_error_codes(cli, tmp_path):
     """empty distribution -> KmerDistError, exit code 6 (counter.h:225-237, main.cpp:121-124); not FASTA/FASTQ -> ReadError (4)"""
     case = G.CASE_BY_NAME["empty_k8"]

@@ -80,3 +80,23 @@ def test_random_files_with_quirks(oracle, exe, seed, tmp_path):
     want = oracle_reads(oracle, path)
     for T in (1, 2, 5, 13, 64):
         assert ours(exe, path, "fq" if fastq else "fa", T) == want, (seed, T)
+
+
+@pytest.mark.parametrize("prog", ["gzip", "bzip2"])
+@pytest.mark.parametrize("name", ["small.fq", "kat.fa", "tail_header.fa"])
+def test_compressed_inputs(oracle, exe, name, prog, tmp_path):
+    """readFastaCompressed / readFastqCompressed (assemble.cpp:851-885, 945-986): the same reads as from the plain file;
+    the type is recognised from the magic number, whatever the file is called."""
+    import shutil
+    if shutil.which(prog) is None:
+        pytest.skip(f"{prog} not installed")
+    plain = os.path.join(HERE, "golden", "inputs", name)
+    packed = str(tmp_path / ("reads_" + name))                          # no .gz/.bz2 suffix on purpose
+    with open(packed, "wb") as out:
+        subprocess.run([prog, "-c", plain], stdout=out, check=True)
+    want = oracle_reads(oracle, plain)
+    for T in (1, 3):
+        got = subprocess.run([exe, packed, "fq" if name.endswith("fq") else "fa", str(T), str(tmp_path)],
+                             capture_output=True, check=True).stdout.split(b"\n")[:-1]
+        assert got == want
+    assert not [f for f in os.listdir(tmp_path) if not f.startswith("reads_")]      # the temp file is unlinked
