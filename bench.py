@@ -259,6 +259,16 @@ def main_ours(args):
     W = kc.words
     send_buf = recv_buf = None
     hist_dev = torch.zeros(65535, dtype=torch.int64, device="cuda")
+    # --exchange keys (k <= 32): the k-mers travel BEFORE counting -- Pass A writes them straight into the all-to-all send
+    # buffer, every rank runs Pass B over what it received (include/pbk.h, pbk_keyx_*).  Default is the record exchange,
+    # the form measured in round 1.
+    keyx = world > 1 and args.exchange == "keys" and W == 1
+    if keyx:
+        max_w = sharding.max_windows_any_rank(n_bases - n_reads * (K - 1), device="cuda")
+        lay = kc.keyx_plan(max_w)
+        shape = (world, int(lay.n_regions), int(lay.seg_cap))
+        kx_send, kx_recv = (torch.empty(shape, dtype=torch.int64, device="cuda") for _ in range(2))
+        kx_cur, kx_rcur = (torch.zeros(shape[:2], dtype=torch.int64, device="cuda") for _ in range(2))
 
     def exchange():
         """hash-range all-to-all of pre-aggregated (k-mer, count) records (platanus_b_b200/sharding.py over NCCL)"""
@@ -276,13 +286,29 @@ def main_ours(args):
         kc.shard_insert_device(got.data_ptr(), n_recv)
         return n_send * (W + 1) * 8
 
+    def step_keyx(resident: bool):
+        if resident:
+            kc.keyx_partition_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, n_bases, kx_send.data_ptr(), kx_cur.data_ptr())
+        else:
+            kc.keyx_partition_ptr(h_bases.data_ptr(), h_offs.data_ptr(), n_reads, kx_send.data_ptr(), kx_cur.data_ptr())
+        sharding.exchange_keys(kx_send, kx_cur, kx_recv, kx_rcur)
+        torch.cuda.current_stream().synchronize()
+        kc.keyx_insert_device(kx_recv.data_ptr(), kx_rcur.data_ptr())
+        sent = (world - 1) * int(lay.bytes_per_dest)
+        if sharding.any_rank_staged(int(kc.shard_send_counts(world).sum()), device="cuda"):
+            sent += exchange()                  # keys whose segment was full (a k-mer repeated millions of times)
+        return sent
+
     def step(resident: bool):
         kc.reset()
-        if resident:
-            kc.push_reads_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, n_bases)
+        if keyx:
+            sent = step_keyx(resident)
         else:
-            kc.push_reads_ptr(h_bases.data_ptr(), h_offs.data_ptr(), n_reads)
-        sent = exchange() if world > 1 else 0
+            if resident:
+                kc.push_reads_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, n_bases)
+            else:
+                kc.push_reads_ptr(h_bases.data_ptr(), h_offs.data_ptr(), n_reads)
+            sent = exchange() if world > 1 else 0
         kc.finalize_light()                     # D2H of the occurrence histogram: the step's result
         if world > 1:
             hist_dev.copy_(torch.from_numpy(kc.occ_hist.astype(np.int64)), non_blocking=False)
@@ -399,6 +425,8 @@ def main_ours(args):
         }
         if world > 1:
             line["exchange_bytes_sent_per_gpu_per_step"] = int(sent_res / args.steps)
+            line["exchange"] = ("keys before counting (8-byte hashes, equal splits, pbk_keyx_*)" if keyx else
+                                "pre-aggregated (key, count) records after counting (pbk_shard_*)")
         if base is not None:
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
@@ -416,6 +444,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C1")
+    ap.add_argument("--exchange", default=os.environ.get("PBK_BENCH_EXCHANGE", "records"), choices=["records", "keys"],
+                    help="N > 1: what crosses NVLink -- (key, count) records after counting, or the keys before it")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-mem-gb", type=int, default=REF_MEM_GB, help="-m of the reference arm (its default is 16)")

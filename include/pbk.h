@@ -179,6 +179,42 @@ int  pbk_shard_insert_device(pbk_ctx *ctx, const void *d_records, uint64_t n_rec
 /* owner shard of a key (host helper, same function as on the device)                              */
 uint32_t pbk_shard_of_key(const uint64_t *key_words, uint32_t k, uint32_t n_shards);
 
+/* ---- hash-range sharding, second form (k <= 32): exchange the KEYS before counting --------------
+ * Pass A of the counter already sorts a batch's k-mers into hash-range buckets.  Here the buckets are
+ * ordered by owner shard first and table region second, in a buffer of the caller, so the bucket store
+ * IS the all-to-all send buffer (equal splits, no packing pass, no host round trip for counts); every
+ * shard then runs the ordinary Pass B over what it received.  Compared with the record exchange above
+ * there is no remote-staging table, no scan/pack of it and no weighted inserts; the wire carries 8 bytes
+ * per k-mer instance instead of 16 per pre-aggregated record (which form wins
+ * depends on coverage).  Ownership is the same function (pbk_shard_of_key), results are identical.
+ *   1. every rank: max over ranks of the batch's window count (n_bases - n_reads * (k - 1)) -> pbk_keyx_plan
+ *   2. pbk_keyx_partition[_device]  (pack + Pass A into d_send / d_cursors; returns when they are complete)
+ *   3. all-to-all of d_send (bytes_per_dest per rank) and d_cursors (cursors_per_dest u64 per rank)
+ *   4. pbk_keyx_insert_device(d_recv, d_recv_cursors)  (the caller has waited for its collective)
+ *   5. if pbk_shard_send_counts reports staged records on ANY rank (keys that found their segment full:
+ *      a k-mer repeated millions of times), run the record exchange above as well
+ *   6. pbk_finalize as usual.                                                                        */
+typedef struct pbk_keyx_layout {
+    uint32_t n_dest;            /* = n_shards                                                      */
+    uint32_t n_regions;         /* table regions (top hash bits) per destination                   */
+    uint64_t seg_cap;           /* entries per (destination, region) segment                       */
+    uint64_t entry_bytes;       /* 8: a k <= 32 key travels as its 64-bit hash (a bijection)       */
+    uint64_t bytes_per_dest;    /* n_regions * seg_cap * entry_bytes: the all-to-all split         */
+    uint64_t cursors_per_dest;  /* n_regions u64 fill counts per destination                       */
+} pbk_keyx_layout;
+/* same inputs -> same layout on every rank; PBK_E_UNSUPPORTED_K for k > 32 (use the record exchange) */
+int  pbk_keyx_plan(pbk_ctx *ctx, uint64_t max_windows_any_rank, pbk_keyx_layout *out);
+/* d_send: n_dest * bytes_per_dest bytes, d_cursors: n_dest * cursors_per_dest u64 (device pointers of
+ * the caller, both overwritten).  Other arguments as pbk_push_reads / pbk_push_reads_device.       */
+int  pbk_keyx_partition(pbk_ctx *ctx, const uint8_t *bases, const uint64_t *read_offsets, uint64_t n_reads,
+                        int encoding, const int32_t *n_pos, const uint64_t *n_pos_offsets,
+                        void *d_send, void *d_cursors);
+int  pbk_keyx_partition_device(pbk_ctx *ctx, const void *d_bases, const void *d_read_offsets,
+                               uint64_t n_reads, uint64_t n_bases, void *d_send, void *d_cursors);
+/* d_recv / d_recv_cursors: what the all-to-all delivered, [source rank][region][seg_cap] entries and
+ * [source rank][region] fill counts                                                               */
+int  pbk_keyx_insert_device(pbk_ctx *ctx, const void *d_recv, const void *d_recv_cursors);
+
 /* ---- host-side pieces of the path that stay on the CPU (negligible cost) --- */
 /* Counter::getLeftLocalMinimalValue (counter.h:245-267) */
 uint64_t pbk_left_local_min(const uint64_t *occ_hist, uint64_t max_occurrence, uint64_t window);

@@ -38,6 +38,7 @@ SYMBOLS = [
     "pbk_shard_insert_device", "pbk_shard_of_key", "pbk_left_local_min", "pbk_coverage_cutoff",
     "pbk_distribution_average", "pbk_double_hash_size", "pbk_write_frq_tsv", "pbk_write_kmer_occ_bin",
     "pbk_microbench_atomics", "pbk_timer_mark", "pbk_timer_elapsed_ms", "pbk_set_timing",
+    "pbk_keyx_plan", "pbk_keyx_partition", "pbk_keyx_partition_device", "pbk_keyx_insert_device",
 ]
 
 
@@ -59,6 +60,12 @@ class PbkStats(C.Structure):
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class PbkKeyxLayout(C.Structure):
+    """pbk_keyx_layout (include/pbk.h): the all-to-all layout of the key exchange"""
+    _fields_ = [("n_dest", C.c_uint32), ("n_regions", C.c_uint32), ("seg_cap", C.c_uint64), ("entry_bytes", C.c_uint64),
+                ("bytes_per_dest", C.c_uint64), ("cursors_per_dest", C.c_uint64)]
 
 
 class PbkError(RuntimeError):
@@ -113,6 +120,10 @@ def load_library(build_if_missing: bool = True):
     L.pbk_shard_pack_device.argtypes = [vp, vp, C.c_uint64]
     L.pbk_shard_insert_device.argtypes = [vp, vp, C.c_uint64]
     L.pbk_shard_of_key.argtypes = [u64p, C.c_uint32, C.c_uint32]; L.pbk_shard_of_key.restype = C.c_uint32
+    L.pbk_keyx_plan.argtypes = [vp, C.c_uint64, C.POINTER(PbkKeyxLayout)]
+    L.pbk_keyx_partition.argtypes = [vp, vp, u64p, C.c_uint64, C.c_int, vp, u64p, vp, vp]
+    L.pbk_keyx_partition_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, vp, vp]
+    L.pbk_keyx_insert_device.argtypes = [vp, vp, vp]
     L.pbk_left_local_min.argtypes = [u64p, C.c_uint64, C.c_uint64]; L.pbk_left_local_min.restype = C.c_uint64
     L.pbk_coverage_cutoff.argtypes = [u64p, C.c_uint64, C.c_int, C.c_int]; L.pbk_coverage_cutoff.restype = C.c_uint64
     L.pbk_distribution_average.argtypes = [u64p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]
@@ -260,6 +271,32 @@ class KmerCounter:
     def shard_insert_device(self, d_records_ptr: int, n_records: int):
         self._check(self._L.pbk_shard_insert_device(self._ctx, C.c_void_p(d_records_ptr), n_records),
                     "pbk_shard_insert_device")
+
+    # -- sharding, second form: keys exchanged before counting (k <= 32) ---------------------------
+    def keyx_plan(self, max_windows_any_rank: int) -> PbkKeyxLayout:
+        lay = PbkKeyxLayout()
+        self._check(self._L.pbk_keyx_plan(self._ctx, int(max_windows_any_rank), C.byref(lay)), "pbk_keyx_plan")
+        return lay
+
+    def keyx_partition(self, bases: np.ndarray, offsets: np.ndarray, d_send_ptr: int, d_cursors_ptr: int):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._check(self._L.pbk_keyx_partition(self._ctx, _ptr(bases), _ptr(offsets), len(offsets) - 1, ENC_ASCII, None, None,
+                                               C.c_void_p(d_send_ptr), C.c_void_p(d_cursors_ptr)), "pbk_keyx_partition")
+
+    def keyx_partition_ptr(self, bases_ptr: int, offsets_ptr: int, n_reads: int, d_send_ptr: int, d_cursors_ptr: int):
+        self._check(self._L.pbk_keyx_partition(self._ctx, C.c_void_p(bases_ptr), C.c_void_p(offsets_ptr), n_reads, ENC_ASCII,
+                                               None, None, C.c_void_p(d_send_ptr), C.c_void_p(d_cursors_ptr)), "pbk_keyx_partition")
+
+    def keyx_partition_device(self, d_bases_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int, d_send_ptr: int,
+                              d_cursors_ptr: int):
+        self._check(self._L.pbk_keyx_partition_device(self._ctx, C.c_void_p(d_bases_ptr), C.c_void_p(d_offsets_ptr), n_reads,
+                                                      n_bases, C.c_void_p(d_send_ptr), C.c_void_p(d_cursors_ptr)),
+                    "pbk_keyx_partition_device")
+
+    def keyx_insert_device(self, d_recv_ptr: int, d_recv_cursors_ptr: int):
+        self._check(self._L.pbk_keyx_insert_device(self._ctx, C.c_void_p(d_recv_ptr), C.c_void_p(d_recv_cursors_ptr)),
+                    "pbk_keyx_insert_device")
 
     # -- Counter<KMER> mirror (reference counter.h) ------------------------------------------------
     def make_kmer_read_distribution(self, bases, offsets, memory_bytes: int) -> int:

@@ -77,6 +77,11 @@ struct pbk_ctx {
     u64 stage_gen = 0, shard_counts_gen = ~0ull;   // remote-staging table changes / generation the cached counts belong to
     bool remote_dirty = false;                      // packed but not yet cleared (cleared lazily: a reset usually follows)
 
+    // key exchange (pbk_keyx_*): layout agreed between the ranks, and -- only during a pbk_keyx_partition* call -- the
+    // caller's send buffer and cursors that Pass A fills instead of the context's own bucket store
+    PartitionPlan keyx_plan{}; u64 keyx_max_windows = 0;
+    u64 *keyx_send = nullptr, *keyx_cursors = nullptr;
+
     bool finalized = false;
     u64 n_reads = 0, n_bases = 0, inst_since_clamp = 0, n_grow = 0;
     double new_ratio = 0.20;         // new keys per window, adapted from what the data shows
@@ -234,8 +239,11 @@ int ensure_overflow(pbk_ctx *c, u64 records)
 // Spilled keys (no slot within the probe limit, or a full bucket segment in Pass A): insert them from
 // a private copy of the list.  The table only grows if it is really loaded, or if a plain retry
 // spilled again.
+int ensure_tables(pbk_ctx *c, u64 first_batch_windows, bool need_remote);
+
 int drain_overflow(pbk_ctx *c)
 {
+    if (c->h_ctr->overflow_n > 0) TRY(ensure_tables(c, 1024, c->shard.n_shards > 1));   // (key-exchange pushes create no table)
     for (int attempt = 0; c->h_ctr->overflow_n > 0; ++attempt) {
         const u64 n = std::min<u64>(c->h_ctr->overflow_n, c->ovf_cap);
         DBG("drain overflow: %llu records (cap %llu), attempt %d", c->h_ctr->overflow_n, c->ovf_cap, attempt);
@@ -267,20 +275,19 @@ int maybe_clamp(pbk_ctx *c, u64 upcoming)
 {
     if (c->inst_since_clamp + upcoming < U32_HEADROOM) return PBK_OK;
     { Span sp(c, LC_OTHER); launch_table_clamp(c->table, c->s_compute); }
-    if (c->shard.n_shards > 1) { Span sp(c, LC_OTHER); launch_table_clamp(c->remote, c->s_compute); }
+    if (c->shard.n_shards > 1 && c->remote.slots) { Span sp(c, LC_OTHER); launch_table_clamp(c->remote, c->s_compute); }
     CK(cudaGetLastError());
     c->inst_since_clamp = 0;
     return PBK_OK;
 }
 
-int ensure_tables(pbk_ctx *c, u64 first_batch_windows)
+int ensure_tables(pbk_ctx *c, u64 first_batch_windows, bool need_remote)
 {
-    if (c->table.slots) return PBK_OK;
     u64 want = c->table_hint ? c->table_hint : (u64)(first_batch_windows * c->new_ratio / max_load(c)) + 1;
-    if (c->shard.n_shards > 1) {
+    if (need_remote && c->shard.n_shards > 1 && !c->remote.slots)
         TRY(table_alloc(c, &c->remote, round_slots(c, want)));     // remote-staging table holds (n-1)/n of the keys
-        want = want / c->shard.n_shards + 1;
-    }
+    if (c->table.slots) return PBK_OK;
+    if (c->shard.n_shards > 1) want = want / c->shard.n_shards + 1;
     TRY(table_alloc(c, &c->table, round_slots(c, want)));
     return PBK_OK;
 }
@@ -337,6 +344,17 @@ int count_range(pbk_ctx *c, u64 w0, u64 w1)
 
 // ---- partitioned path ---------------------------------------------------------------------------
 
+// cursors and Pass B descriptors, device + pinned host copies
+int ensure_passb_buffers(pbk_ctx *c)
+{
+    if (c->d_bkt_cursor) return PBK_OK;
+    TRY(dev_alloc(c, (void **)&c->d_bkt_cursor, PART_MAX_BUCKETS * 8));
+    if (cudaMallocHost((void **)&c->h_bkt_cursor, PART_MAX_BUCKETS * 8) != cudaSuccess) return fail(c, PBK_E_NOMEM, "pinned host memory");
+    TRY(dev_alloc(c, (void **)&c->d_passb, passb_desc_bytes(PART_MAX_BUCKETS)));
+    if (cudaMallocHost((void **)&c->h_passb, passb_desc_bytes(PART_MAX_BUCKETS)) != cudaSuccess) return fail(c, PBK_E_NOMEM, "pinned host memory");
+    return PBK_OK;
+}
+
 // bucket store for `windows_ub` windows (the whole batch, or one sub-batch); the table is sized for `windows_total`
 int prepare_partition(pbk_ctx *c, u64 windows_ub, u64 windows_total)
 {
@@ -352,12 +370,7 @@ int prepare_partition(pbk_ctx *c, u64 windows_ub, u64 windows_total)
         TRY(dev_alloc(c, (void **)&c->d_bkt_keys, need));
         c->bkt_bytes = need;
     }
-    if (!c->d_bkt_cursor) {
-        TRY(dev_alloc(c, (void **)&c->d_bkt_cursor, PART_MAX_BUCKETS * 8));
-        if (cudaMallocHost((void **)&c->h_bkt_cursor, PART_MAX_BUCKETS * 8) != cudaSuccess) return fail(c, PBK_E_NOMEM, "pinned host memory");
-        TRY(dev_alloc(c, (void **)&c->d_passb, passb_desc_bytes(PART_MAX_BUCKETS)));
-        if (cudaMallocHost((void **)&c->h_passb, passb_desc_bytes(PART_MAX_BUCKETS)) != cudaSuccess) return fail(c, PBK_E_NOMEM, "pinned host memory");
-    }
+    TRY(ensure_passb_buffers(c));
     CK(cudaMemsetAsync(c->d_bkt_cursor, 0, PART_MAX_BUCKETS * 8, c->s_compute));
     // a spilled key (bucket segment or bin full) is rare; the list is also used by Pass B
     TRY(ensure_overflow(c, 1ull << 22));
@@ -467,7 +480,11 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
     if (c->remote_dirty) { Span sp(c, LC_OTHER); launch_table_init(c->remote, c->s_compute); c->remote_dirty = false; }
     TRY(ensure_batch_buffers(c, n_bases, n_reads));
     const u64 windows_ub = n_bases > (u64)n_reads * (c->k - 1) ? n_bases - (u64)n_reads * (c->k - 1) : 0;
-    TRY(ensure_tables(c, std::max<u64>(windows_ub, 1024)));
+    const bool keyx = c->keyx_send != nullptr;       // Pass A only, into the caller's all-to-all send buffer
+    if (keyx && windows_ub > c->keyx_max_windows)
+        return fail(c, PBK_E_ARG, "batch has up to %llu windows, the key-exchange layout was planned for %llu",
+                    (unsigned long long)windows_ub, (unsigned long long)c->keyx_max_windows);
+    if (!keyx) TRY(ensure_tables(c, std::max<u64>(windows_ub, 1024), true));
 
     u64 *stream = c->d_stream_raw + STREAM_PAD_WORDS;
     u32 *nflag = c->d_nflag_raw + STREAM_PAD_WORDS, *rflag = c->d_rflag_raw + STREAM_PAD_WORDS;
@@ -485,14 +502,14 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
     CK(cudaGetLastError());
 
     const bool deferred_count = (encoding == PBK_ENC_PLATANUS);     // N flags arrive after all packs
-    const bool partitioned = c->partition_enabled && (windows_ub >= PART_MIN_WINDOWS || (c->partition_forced && windows_ub > 0));
+    const bool partitioned = keyx || (c->partition_enabled && (windows_ub >= PART_MIN_WINDOWS || (c->partition_forced && windows_ub > 0)));
     // Chained (k <= 32, new-key ratio known from an earlier batch of this context, so the table can be sized up front;
     // the first large batch takes the other path with its pilot launch): Pass A per chunk, then a device-built tile map
     // and Pass B, all queued without a host round trip.  Host input is counted in up to four such groups of chunks so
     // that only the last group's Pass B is left when the last H2D copy lands; device-resident input in one group.
     const u64 n_chunks_total = (n_bases + CHUNK_BASES - 1) / CHUNK_BASES;
     Pipe pipe;
-    pipe.on = partitioned && c->pipeline_enabled && c->W == 1 && c->ratio_known;
+    pipe.on = partitioned && !keyx && c->pipeline_enabled && c->W == 1 && c->ratio_known;
     if (pipe.on) {
         const u32 max_sb = getenv("PBK_N_SB") ? (u32)std::min(8, std::max(1, atoi(getenv("PBK_N_SB")))) : 4u;
         const u32 n_sb = (h_bases != nullptr && n_chunks_total >= 4) ? (u32)std::max<u64>(1, std::min<u64>(max_sb, n_chunks_total / 2)) : 1u;
@@ -505,16 +522,21 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
         TRY(maybe_clamp(c, windows_ub));
         TRY(ensure_room(c, (u64)(windows_ub * std::min(1.0, c->new_ratio * 1.15)) + 65536));
         TRY(prepare_partition(c, sb_windows, windows_ub));
+    } else if (keyx) {
+        c->plan = c->keyx_plan;
+        CK(cudaMemsetAsync(c->keyx_cursors, 0, (size_t)c->plan.n_buckets * 8, c->s_compute));
+        TRY(ensure_overflow(c, 1ull << 22));
     } else if (partitioned) {
         TRY(prepare_partition(c, windows_ub, windows_ub));
     }
+    u64 *const bkt_keys = keyx ? c->keyx_send : c->d_bkt_keys, *const bkt_cursor = keyx ? c->keyx_cursors : c->d_bkt_cursor;
     // large batches: Pass A per chunk (no host sync), Pass B once at the end.  Small ones: straight to the table.
     auto count_words = [&](u64 w0, u64 w1) -> int {
         if (!partitioned) return count_range(c, w0, w1);
         {
             Span sp(c, LC_PART);
-            launch_partition(stream, nflag, rflag, w0, w1, (int)c->k, c->W, c->plan, c->d_bkt_keys, c->d_bkt_cursor, c->d_ctr,
-                             c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+            launch_partition(stream, nflag, rflag, w0, w1, (int)c->k, c->W, c->plan, bkt_keys, bkt_cursor, c->d_ctr,
+                             c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute, keyx ? c->shard.n_shards : 1u);
         }
         if (pipe.on && ++pipe.in_sb >= pipe.sb_chunks()) TRY(pipe_finish_subbatch(c, pipe));
         return PBK_OK;
@@ -576,7 +598,14 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
         dev_free(c, d_np, total_n * 4); dev_free(c, d_npo, (n_reads + 1) * 8);
         TRY(rc);
     }
-    if (pipe.on) {
+    if (keyx) {
+        // the keys stay in the caller's buffer; what the host needs now: error flags, the instance count, and the few
+        // keys that found their segment full (a heavily repeated k-mer), which take the record route (remote-staging
+        // table -> pbk_shard_pack_device) to their owner
+        CK(cudaGetLastError());
+        TRY(read_counters(c));
+        TRY(drain_overflow(c));
+    } else if (pipe.on) {
         CK(cudaGetLastError());
         TRY(pipe_end(c, pipe));
     } else if (partitioned) {
@@ -942,7 +971,7 @@ int pbk_shard_insert_device(pbk_ctx *c, const void *d_records, uint64_t n_record
     if (!d_records) return PBK_E_ARG;
     if (c->finalized) return fail(c, PBK_E_STATE, "insert after finalize");
     CK(cudaSetDevice(c->device));
-    TRY(ensure_tables(c, n_records));
+    TRY(ensure_tables(c, n_records, false));
     const ShardInfo local{1, 0};                      // received records are owned by this shard
     for (u64 at = 0; at < n_records; at += CHUNK_BASES) {
         const u64 n = std::min<u64>(CHUNK_BASES, n_records - at);
@@ -958,6 +987,135 @@ int pbk_shard_insert_device(pbk_ctx *c, const void *d_records, uint64_t n_record
         CK(cudaGetLastError());
         TRY(read_counters(c));
         TRY(drain_overflow(c));
+    }
+    return PBK_OK;
+}
+
+// ---- key exchange (k <= 32) ----------------------------------------------------------------------
+
+int pbk_keyx_plan(pbk_ctx *c, uint64_t max_windows_any_rank, pbk_keyx_layout *out)
+{
+    if (!c || !out) return PBK_E_ARG;
+    if (c->W != 1) return fail(c, PBK_E_UNSUPPORTED_K, "the key exchange is implemented for k <= 32 (k = %u: use the record exchange)", c->k);
+    if (c->shard.n_shards < 2 || c->shard.n_shards > 64) return fail(c, PBK_E_ARG, "key exchange needs 2..64 shards");
+    c->keyx_plan = plan_partition_keyx(c->shard.n_shards, std::max<u64>(max_windows_any_rank, 1), c->W);
+    c->keyx_max_windows = max_windows_any_rank;
+    out->n_dest = c->shard.n_shards;
+    out->n_regions = c->keyx_plan.n_buckets / c->shard.n_shards;
+    out->seg_cap = c->keyx_plan.seg_cap;
+    out->entry_bytes = 8ull * c->W;
+    out->bytes_per_dest = (u64)out->n_regions * out->seg_cap * out->entry_bytes;
+    out->cursors_per_dest = out->n_regions;
+    return PBK_OK;
+}
+
+static int keyx_bind(pbk_ctx *c, void *d_send, void *d_cursors)
+{
+    if (!d_send || !d_cursors) return fail(c, PBK_E_ARG, "NULL key-exchange buffer");
+    if (c->keyx_plan.n_buckets == 0) return fail(c, PBK_E_STATE, "pbk_keyx_partition before pbk_keyx_plan");
+    if (c->W != 1) return fail(c, PBK_E_UNSUPPORTED_K, "the key exchange is implemented for k <= 32");
+    c->keyx_send = (u64 *)d_send; c->keyx_cursors = (u64 *)d_cursors;
+    return PBK_OK;
+}
+
+int pbk_keyx_partition(pbk_ctx *c, const uint8_t *bases, const uint64_t *read_offsets, uint64_t n_reads, int encoding,
+                       const int32_t *n_pos, const uint64_t *n_pos_offsets, void *d_send, void *d_cursors)
+{
+    if (!c) return PBK_E_ARG;
+    if (!read_offsets || (encoding != PBK_ENC_ASCII && encoding != PBK_ENC_PLATANUS)) return fail(c, PBK_E_ARG, "bad arguments");
+    if (n_reads && read_offsets[0] != 0) return fail(c, PBK_E_ARG, "read_offsets[0] must be 0");
+    const u64 n_bases = n_reads ? read_offsets[n_reads] : 0;
+    if (n_bases && !bases) return fail(c, PBK_E_ARG, "bases is NULL");
+    TRY(keyx_bind(c, d_send, d_cursors));
+    int rc;
+    if (n_reads == 0) {                                  // nothing to send, but the cursors must say so
+        rc = cudaMemsetAsync(d_cursors, 0, (size_t)c->keyx_plan.n_buckets * 8, c->s_compute) == cudaSuccess &&
+             cudaStreamSynchronize(c->s_compute) == cudaSuccess ? PBK_OK : fail(c, PBK_E_CUDA, "clearing the cursors failed");
+    } else {
+        rc = push_common(c, bases, nullptr, (const u64 *)read_offsets, nullptr, n_reads, n_bases, encoding, n_pos, (const u64 *)n_pos_offsets);
+    }
+    c->keyx_send = c->keyx_cursors = nullptr;
+    return rc;
+}
+
+int pbk_keyx_partition_device(pbk_ctx *c, const void *d_bases, const void *d_read_offsets, uint64_t n_reads,
+                              uint64_t n_bases, void *d_send, void *d_cursors)
+{
+    if (!c) return PBK_E_ARG;
+    if (n_reads && (!d_read_offsets || (n_bases && !d_bases))) return fail(c, PBK_E_ARG, "NULL device pointer");
+    TRY(keyx_bind(c, d_send, d_cursors));
+    int rc;
+    if (n_reads == 0) {
+        rc = cudaMemsetAsync(d_cursors, 0, (size_t)c->keyx_plan.n_buckets * 8, c->s_compute) == cudaSuccess &&
+             cudaStreamSynchronize(c->s_compute) == cudaSuccess ? PBK_OK : fail(c, PBK_E_CUDA, "clearing the cursors failed");
+    } else {
+        rc = push_common(c, nullptr, (const uint8_t *)d_bases, nullptr, (const u64 *)d_read_offsets, n_reads, n_bases, PBK_ENC_ASCII, nullptr, nullptr);
+    }
+    c->keyx_send = c->keyx_cursors = nullptr;
+    return rc;
+}
+
+int pbk_keyx_insert_device(pbk_ctx *c, const void *d_recv, const void *d_recv_cursors)
+{
+    if (!c || !d_recv || !d_recv_cursors) return PBK_E_ARG;
+    if (c->finalized) return fail(c, PBK_E_STATE, "insert after finalize");
+    if (c->keyx_plan.n_buckets == 0 || c->W != 1) return fail(c, PBK_E_STATE, "pbk_keyx_insert_device before pbk_keyx_plan");
+    CK(cudaSetDevice(c->device));
+    const u32 G = c->shard.n_shards, n_desc = c->keyx_plan.n_buckets, R = n_desc / G;
+    const u64 seg_cap = c->keyx_plan.seg_cap;
+    TRY(ensure_passb_buffers(c));
+    // fill counts, [source][region] -> descriptor order [region][source]
+    CK(cudaMemcpyAsync(c->h_bkt_cursor, d_recv_cursors, (size_t)n_desc * 8, cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));
+    c->d2h_bytes += (u64)n_desc * 8;
+    std::vector<u64> cnt(n_desc);
+    u64 total = 0;
+    for (u32 j = 0; j < R; ++j)
+        for (u32 s = 0; s < G; ++s) { cnt[j * G + s] = std::min<u64>(c->h_bkt_cursor[s * R + j], seg_cap); total += cnt[j * G + s]; }
+    DBG("keyx insert: %llu keys from %u sources in %u regions (seg_cap %llu)", (unsigned long long)total, G, R, (unsigned long long)seg_cap);
+    if (total == 0) return PBK_OK;
+    if (!c->table.slots) {
+        const u64 want = c->table_hint ? c->table_hint : (u64)(total * c->new_ratio / max_load(c)) + 1;
+        TRY(table_alloc(c, &c->table, round_slots(c, want)));
+    }
+    TRY(maybe_clamp(c, total));
+    TRY(ensure_overflow(c, 1ull << 22));
+    auto room_for = [&](u64 expect_new) -> int {
+        if ((double)(c->occupied + expect_new) > max_load(c) * (double)c->table.capacity())
+            return grow_table(c, &c->table, c->occupied, (u64)((c->occupied + expect_new) / max_load(c)) + 1);
+        return PBK_OK;
+    };
+    auto launch = [&](u32 d0, u32 d1) -> int {
+        {
+            Span sp(c, LC_INSERT);
+            launch_bucket_insert_gathered((const u64 *)d_recv, seg_cap, cnt.data(), c->h_passb, c->d_passb, d0, d1, G, R, c->table,
+                                          c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+        }
+        CK(cudaGetLastError());
+        TRY(read_counters(c));                          // also makes h_passb reusable
+        TRY(drain_overflow(c));
+        return PBK_OK;
+    };
+    const u64 occ_before = c->occupied;
+    TRY(room_for((u64)(total * std::min(1.0, c->new_ratio))));
+    if (!c->ratio_known) {
+        // first batch: the first 1/16 of the regions (statistically identical hash ranges) tell how many of the keys
+        // are new, then the table is sized once for the rest -- like flush_buckets
+        const u32 pilot = std::max<u32>(1, R / 16) * G;
+        u64 pilot_keys = 0;
+        for (u32 i = 0; i < pilot; ++i) pilot_keys += cnt[i];
+        TRY(launch(0, pilot));
+        const double per_key = pilot_keys ? (double)(c->occupied - occ_before) / (double)pilot_keys : c->new_ratio;
+        if (pilot < n_desc) {
+            TRY(room_for((u64)((double)(total - pilot_keys) * std::min(1.0, per_key * 1.05)) + 4096));
+            TRY(launch(pilot, n_desc));
+        }
+    } else {
+        TRY(launch(0, n_desc));
+    }
+    if (total > 4096) {
+        c->new_ratio = std::max(0.01, std::min(1.0, (double)(c->occupied - occ_before) / (double)total));
+        c->ratio_known = true;
     }
     return PBK_OK;
 }

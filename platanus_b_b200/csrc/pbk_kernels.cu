@@ -112,28 +112,57 @@ PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words, siz
     return p;
 }
 
-template <int W>
+// key-exchange layout (pbk_keyx_*): n_dest x n_regions buckets, destination-major.  n_regions is a function of the
+// number of shards alone and seg_cap of the largest batch of any rank, so every rank derives the same layout.
+PartitionPlan plan_partition_keyx(u32 n_dest, u64 max_windows_any_rank, int words, size_t smem_budget)
+{
+    u32 R = getenv("PBK_KEYX_REGIONS") ? (u32)atoi(getenv("PBK_KEYX_REGIONS")) : 64u;
+    while (R > 8 && (u64)R * n_dest > 256) R >>= 1;                 // 2, 4 shards: 64 regions; 8: 32; 16: 16
+    while (R & (R - 1)) R &= R - 1;                                 // power of two
+    R = std::max<u32>(R, 2);
+    PartitionPlan p{};
+    if (smem_budget == 0) smem_budget = getenv("PBK_PART_SMEM_KB") ? (size_t)atoi(getenv("PBK_PART_SMEM_KB")) * 1024 : PART_SMEM_BUDGET;
+    const u64 entries = smem_budget / (8 * (size_t)words);
+    const u64 P = std::min<u64>((u64)R * n_dest, (u64)PART_MAX_BUCKETS);
+    p.n_buckets = (u32)P;
+    p.bin_cap = (u32)std::max<u64>(1, entries / P);
+    const double win = words == 1 ? (double)PART_WIN1 : words == 2 ? 16.0 : 8.0;
+    u64 threads = (u64)(p.bin_cap * 0.6 * (double)P / (win * 0.85));
+    threads = std::min<u64>(512, threads / 32 * 32);
+    p.threads = (int)std::max<u64>(64, threads);
+    p.smem = (size_t)p.n_buckets * p.bin_cap * 8 * words;
+    p.seg_cap = max_windows_any_rank / P + max_windows_any_rank / (P * 16) + 8192;
+    return p;
+}
+
+template <int W, bool KEYX>
 static void partition_launch_w(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
                                const PartitionPlan &plan, u64 *bkt_keys, u64 *bkt_cursor, Counters *ctr,
-                               u64 *overflow_keys, u64 overflow_cap, int grid, cudaStream_t st)
+                               u64 *overflow_keys, u64 overflow_cap, int grid, u32 n_dest, cudaStream_t st)
 {
-    cudaFuncSetAttribute(partition_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
-    partition_kernel<W><<<grid, plan.threads, plan.smem, st>>>(stream, nflag, rflag, word_begin, word_end, k,
-        plan.n_buckets, plan.bin_cap, bkt_keys, plan.seg_cap, bkt_cursor, ctr, overflow_keys, overflow_cap);
+    cudaFuncSetAttribute(partition_kernel<W, KEYX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    partition_kernel<W, KEYX><<<grid, plan.threads, plan.smem, st>>>(stream, nflag, rflag, word_begin, word_end, k,
+        plan.n_buckets, plan.bin_cap, bkt_keys, plan.seg_cap, bkt_cursor, ctr, overflow_keys, overflow_cap, n_dest);
 }
 
 void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
                       int words, const PartitionPlan &plan, u64 *bkt_keys, u64 *bkt_cursor, Counters *ctr,
-                      u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st)
+                      u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st, u32 keyx_dest)
 {
     if (word_end <= word_begin) return;
     const u64 subs = words == 1 ? 32 / PART_WIN1 : words == 2 ? 2 : 4;       // 32 / PART_WIN<W>: work items per stream word
     const u64 tiles = ((word_end - word_begin) * subs + plan.threads - 1) / plan.threads;
     const int ctas = std::max(1, std::min(8, (int)((220 * 1024) / (plan.smem + 7 * 1024))));     // resident CTAs per SM
     const int grid = (int)std::min<u64>(tiles, (u64)sm_count * ctas);
+    if (keyx_dest > 1) {                                        // one-word keys only (pbk_keyx_plan refuses k > 32)
+        if (words == 1)
+            partition_launch_w<1, true>(stream, nflag, rflag, word_begin, word_end, k, plan, bkt_keys, bkt_cursor, ctr,
+                                        overflow_keys, overflow_cap, grid, keyx_dest, st);
+        return;
+    }
     PBK_DISPATCH_W(words,
-        (partition_launch_w<W>(stream, nflag, rflag, word_begin, word_end, k, plan, bkt_keys, bkt_cursor, ctr,
-                               overflow_keys, overflow_cap, grid, st)));
+        (partition_launch_w<W, false>(stream, nflag, rflag, word_begin, word_end, k, plan, bkt_keys, bkt_cursor, ctr,
+                                      overflow_keys, overflow_cap, grid, 1u, st)));
 }
 
 size_t passb_desc_bytes(u32 n_buckets) { return 16 + (size_t)(n_buckets + 1) * sizeof(PassBBucket); }
@@ -183,11 +212,11 @@ void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *counts, v
         const u32 opts = getenv("PBK_PASSB_HINT") ? (u32)atoi(getenv("PBK_PASSB_HINT")) : 1u;
         const int grid = (int)std::min<u64>(tiles, (u64)sm_count * ctas);
         if (shard.n_shards > 1)
-            bucket_insert_compact_kernel<true><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, b_first, b_end,
+            bucket_insert_compact_kernel<1><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, b_first, b_end,
                 (u64 *)d_desc, Table<1>(table.slots, table.cap), Table<1>(remote.slots, remote.cap), shard.n_shards,
                 shard.rank, ctr, overflow_keys, overflow_cap, opts);
         else
-            bucket_insert_compact_kernel<false><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, b_first, b_end,
+            bucket_insert_compact_kernel<0><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, b_first, b_end,
                 (u64 *)d_desc, Table<1>(table.slots, table.cap), Table<1>(remote.slots, remote.cap), 1, 0, ctr,
                 overflow_keys, overflow_cap, opts);
         return;
@@ -215,6 +244,41 @@ void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *counts, v
     }
 }
 
+// Key exchange (k <= 32): Pass B over the all-to-all receive buffer, [source][region][seg_cap] entries.  `counts`
+// are in descriptor order (descriptor i = region i / n_src, source i % n_src); descriptors [d_first, d_end) of
+// n_src x n_regions are inserted by this launch.  While (region j, source s) is worked on, slice s of region j + 1
+// is prefetched.
+void launch_bucket_insert_gathered(const u64 *recv_keys, u64 seg_cap, const u64 *counts, void *h_desc, void *d_desc,
+                                   u32 d_first, u32 d_end, u32 n_src, u32 n_regions, TableView table, Counters *ctr,
+                                   u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st)
+{
+    if (d_end <= d_first || table.words != 1) return;
+    const int pf_dist = getenv("PBK_PF_DIST") ? atoi(getenv("PBK_PF_DIST")) : 1;
+    const u32 n_desc = n_src * n_regions;
+    u64 *h_ticket = (u64 *)h_desc;
+    PassBBucket *h = (PassBBucket *)((char *)h_desc + 16);
+    h_ticket[0] = 0; h_ticket[1] = 0;
+    u64 tiles = 0;
+    for (u32 i = d_first; i < d_end; ++i) {
+        PassBBucket &d = h[i - d_first];
+        d.tile_start = tiles;
+        d.n_keys = counts[i];
+        tiles += (counts[i] + PASSB1_TILE_KEYS - 1) / PASSB1_TILE_KEYS;
+        d.pf_base = d.pf_base2 = nullptr; d.pf_lines = d.pf_lines2 = 0;
+        if (pf_dist > 0 && counts[i]) prefetch_region(table, i + (u32)pf_dist * n_src, n_desc, &d.pf_base, &d.pf_lines);
+    }
+    h[d_end - d_first] = PassBBucket{tiles, 0, nullptr, nullptr, 0, 0};
+    cudaMemcpyAsync(d_desc, h_desc, passb_desc_bytes(d_end - d_first), cudaMemcpyHostToDevice, st);
+    if (tiles == 0) return;
+    const PassBBucket *d_bk = (const PassBBucket *)((const char *)d_desc + 16);
+    const int ctas = getenv("PBK_PASSB_CTAS") ? atoi(getenv("PBK_PASSB_CTAS")) : 3;
+    const u32 opts = (getenv("PBK_PASSB_HINT") ? ((u32)atoi(getenv("PBK_PASSB_HINT")) & 0xFFu) : 1u) | (n_src << 8) | (n_regions << 16);
+    const int grid = (int)std::min<u64>(tiles, (u64)sm_count * ctas);
+    const Table<1> t(table.slots, table.cap);
+    bucket_insert_compact_kernel<2><<<grid, PASSB_THREADS, 0, st>>>(recv_keys, seg_cap, d_bk, d_first, d_end, (u64 *)d_desc,
+        t, t, 1, 0, ctr, overflow_keys, overflow_cap, opts);
+}
+
 // device-chained variant for k <= 32: tile map built by a kernel from the cursors, Pass B launched on `st_insert`
 // right behind it (the caller orders the two streams with events)
 void launch_passb_desc(const u64 *d_cursor, u64 seg_cap, u32 n_buckets, TableView table, TableView remote, ShardInfo shard,
@@ -235,11 +299,11 @@ void launch_bucket_insert_chained(const u64 *bkt_keys, u64 seg_cap, const void *
     if (getenv("PBK_PASSB_CTAS")) ctas_per_sm = atoi(getenv("PBK_PASSB_CTAS"));
     const int grid = sm_count * ctas_per_sm;                    // CTAs that find no tile left leave at once
     if (shard.n_shards > 1)
-        bucket_insert_compact_kernel<true><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, 0, n_buckets, (u64 *)d_desc,
+        bucket_insert_compact_kernel<1><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, 0, n_buckets, (u64 *)d_desc,
             Table<1>(table.slots, table.cap), Table<1>(remote.slots, remote.cap), shard.n_shards, shard.rank, ctr,
             overflow_keys, overflow_cap, opts);
     else
-        bucket_insert_compact_kernel<false><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, 0, n_buckets, (u64 *)d_desc,
+        bucket_insert_compact_kernel<0><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, 0, n_buckets, (u64 *)d_desc,
             Table<1>(table.slots, table.cap), Table<1>(remote.slots, remote.cap), 1, 0, ctr, overflow_keys, overflow_cap, opts);
 }
 

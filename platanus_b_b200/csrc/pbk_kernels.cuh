@@ -54,7 +54,13 @@ PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words, siz
 // Pass A over stream words [word_begin, word_end): keys go to bkt_keys (P segments of seg_cap entries)
 void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
                       int words, const PartitionPlan &plan, u64 *bkt_keys, u64 *bkt_cursor, Counters *ctr,
-                      u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st);
+                      u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st, u32 keyx_dest = 1);
+// Key exchange between GPUs (k <= 32, pbk_keyx_*): plan with n_dest x n_regions buckets in destination-major order
+// (launch_partition with keyx_dest = n_dest fills it), and Pass B over the all-to-all receive buffer.
+PartitionPlan plan_partition_keyx(u32 n_dest, u64 max_windows_any_rank, int words, size_t smem_budget = 0);
+void launch_bucket_insert_gathered(const u64 *recv_keys, u64 seg_cap, const u64 *counts, void *h_desc, void *d_desc,
+                                   u32 d_first, u32 d_end, u32 n_src, u32 n_regions, TableView table, Counters *ctr,
+                                   u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st);
 // Pass B over buckets [b_first, b_end) in one launch.  `h_desc` is scratch for b_end - b_first + 1 bucket
 // descriptors (pinned host memory), `d_desc` the same on the device; `counts[b]` = keys in bucket b.
 size_t passb_desc_bytes(u32 n_buckets);

@@ -338,11 +338,14 @@ __device__ __forceinline__ u64 smear_up(u64 x, int w)
 // Pass A.  One thread owns one stream word (32 window ends), exactly like count_kernel, but instead of
 // touching the table it drops the canonical key into its bucket's shared-memory bin; full tiles are
 // then flushed warp-per-bucket with coalesced stores.
-template <int W>
+// KEYX (key exchange between GPUs, pbk_keyx_*): the n_buckets = n_dest x R buckets are ordered by owner shard first
+// (shard_of_hash, the low hash bits) and by table region second (the top hash bits, R a power of two), so that the
+// segments of one destination are contiguous -- the bucket store is the all-to-all send buffer as it stands.
+template <int W, bool KEYX = false>
 __global__ void __launch_bounds__(512)
 partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, const u32 *__restrict__ rflag,
                  u64 word_begin, u64 word_end, int k, u32 n_buckets, u32 bin_cap, u64 *bkt_keys, u64 seg_cap,
-                 u64 *bkt_cursor, Counters *ctr, u64 *ovf, u64 ovf_cap)
+                 u64 *bkt_cursor, Counters *ctr, u64 *ovf, u64 ovf_cap, u32 n_dest)
 {
     PBK_DYN_SMEM(u64, bins);                          // n_buckets * bin_cap * W words
     __shared__ u32 scount[PART_MAX_BUCKETS];
@@ -355,7 +358,8 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
     const int wsize = blockDim.x < 32 ? (int)blockDim.x : 32;
     const int lane = threadIdx.x % wsize;
     // bucket = top log2(P) hash bits when P is a power of two (0 = use the generic mulhi form)
-    const int pshift = (n_buckets > 1 && (n_buckets & (n_buckets - 1)) == 0) ? 64 - (31 - __clz(n_buckets)) : 0;
+    const u32 n_part = KEYX ? n_buckets / n_dest : n_buckets;     // buckets that the top hash bits select among
+    const int pshift = (n_part > 1 && (n_part & (n_part - 1)) == 0) ? 64 - (31 - __clz(n_part)) : 0;
     u64 inst = 0;
 
     // A thread takes PART_WIN<W> consecutive windows of one stream word per tile (16, 16, 8 for 1, 2, >= 3 key words):
@@ -395,7 +399,8 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
                     r = (r >> 2) | ((u64)(3u - b) * topmul);
                     if ((valid >> i) & 1u) {
                         const u64 hh = fmix64(r < f ? r : f);        // key = min(forward, reverse), counter.h:429
-                        const u32 bkt = (u32)(hh >> pshift);          // == mulhi(hh, n_buckets) for a power of two
+                        u32 bkt = (u32)(hh >> pshift);                // == mulhi(hh, n_buckets) for a power of two
+                        if constexpr (KEYX) bkt += shard_of_hash(hh, n_dest) * n_part;
                         ++n_here;
                         const u32 pos = atomicAdd(&scount[bkt], 1u);
                         if (pos < bin_cap) bins[bkt * bin_cap + pos] = hh;
@@ -471,7 +476,8 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
 #pragma unroll
                     for (int j = 0; j < W; ++j) key[j] = use_rev ? rev[j] : fwd[j];
                     const u64 hh = hash_key<W>(key);
-                    const u32 bkt = (u32)__umul64hi(hh, (u64)n_buckets);
+                    u32 bkt = (u32)__umul64hi(hh, (u64)n_part);
+                    if constexpr (KEYX) bkt += shard_of_hash(hh, n_dest) * n_part;
                     if (W == 1) key[0] = hh;          // one-word keys travel as their (bijective) hash
                     ++inst;
                     const u32 pos = atomicAdd(&scount[bkt], 1u);
@@ -801,12 +807,18 @@ __device__ __forceinline__ void passb1_round(const u64 *__restrict__ src, u32 n_
     }
 }
 
-template <bool SHARDED>
+// MODE 0: every key is local.  MODE 1: keys of other shards go to the remote-staging table (record exchange after
+// counting).  MODE 2 (key exchange before counting, pbk_keyx_insert_device): every key is local and `bkt_hash` is the
+// all-to-all receive buffer, laid out [source rank][region][seg_cap]; the descriptors are in region-major order
+// (descriptor i = region i / G, source i % G, with G = opts bits 8-15 and the regions per source in bits 16-31), so
+// all sources' keys of one table region are inserted while that region is L2-resident.
+template <int MODE>
 __global__ void __launch_bounds__(PASSB_THREADS, 3)
 bucket_insert_compact_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, const PassBBucket *__restrict__ bk,
                              u32 b_first, u32 b_end, u64 *ticket, Table<1> table, Table<1> remote, u32 n_shards,
                              u32 rank, Counters *ctr, u64 *ovf, u64 ovf_cap, u32 opts)
 {
+    constexpr bool SHARDED = MODE == 1;
     // (the bucket descriptors are read straight from global memory: a few cached loads per 8192-key tile, and the
     //  shared memory they would take is what lets two of these CTAs share an SM with two Pass A CTAs)
     __shared__ u64 s_ticket[2];
@@ -835,7 +847,12 @@ bucket_insert_compact_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, cons
         if (tid == 0) s_ticket[par] = atomicAdd(ticket, 1ull);   // ticket for the tile after next
         if (bk[lb].pf_base) passb_prefetch(bk[lb].pf_base, bk[lb].pf_lines, j, nt, tid, nthreads);
         if (SHARDED && bk[lb].pf_base2) passb_prefetch(bk[lb].pf_base2, bk[lb].pf_lines2, j, nt, tid, nthreads);
-        const u64 *src = bkt_hash + (u64)(b_first + lb) * seg_cap + j * tile_keys;
+        u32 seg = b_first + lb;
+        if constexpr (MODE == 2) {
+            const u32 G = (opts >> 8) & 0xFFu, R = opts >> 16;
+            seg = (seg % G) * R + seg / G;
+        }
+        const u64 *src = bkt_hash + (u64)seg * seg_cap + j * tile_keys;
         const u64 left = n - j * tile_keys;                      // > 0 by construction of the tile numbering
         if (left >= tile_keys) {
 #pragma unroll 1

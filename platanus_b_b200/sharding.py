@@ -33,3 +33,29 @@ def allreduce_histogram(hist: torch.Tensor, group=None) -> torch.Tensor:
     """Sum of the per-shard occurrence histograms: shards own disjoint key sets, so the sum is the global one."""
     dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
     return hist
+
+
+# ---- second form: the keys themselves are exchanged before counting (k <= 32, pbk_keyx_* in include/pbk.h) ----------
+
+def max_windows_any_rank(n_windows: int, device=None, group=None) -> int:
+    """Every rank must derive the same all-to-all layout: the segment size follows from the largest batch."""
+    t = torch.tensor([int(n_windows)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item())
+
+
+def exchange_keys(send: torch.Tensor, cursors: torch.Tensor, recv: torch.Tensor, recv_cursors: torch.Tensor, group=None):
+    """Equal-split all-to-all of the bucket store Pass A filled: `send` is [n_dest, n_regions, seg_cap] int64 (the
+    hashes of this rank's k-mers, grouped by owner), `cursors` [n_dest, n_regions] the fill counts; afterwards
+    `recv` / `recv_cursors` hold the same by source rank -- the input of pbk_keyx_insert_device."""
+    dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
+    dist.all_to_all_single(recv_cursors.view(-1), cursors.view(-1), group=group)
+    return recv, recv_cursors
+
+
+def any_rank_staged(n_staged_here: int, device=None, group=None) -> bool:
+    """True if some rank holds staged (key, count) records -- keys whose segment was full -- so that every rank joins
+    the record exchange; False in the common case, and the record exchange is skipped by all."""
+    t = torch.tensor([int(n_staged_here)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item()) > 0

@@ -56,16 +56,16 @@ static int run(const uint8_t *bases, const u64 *off, u64 n_reads, int k, int enc
         const u64 seg_cap = std::max<u64>(4, n_bases / P * 3 / 4);
         std::vector<u64> bkt((u64)P * seg_cap * W, 0), cursor(P, 0);
         partition_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
-                            0, w_split, k, P, bin_cap, bkt.data(), seg_cap, cursor.data(), &ctr, ovf.data(), OVF);
+                            0, w_split, k, P, bin_cap, bkt.data(), seg_cap, cursor.data(), &ctr, ovf.data(), OVF, 1u);
         partition_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
-                            w_split, words, k, P, bin_cap, bkt.data(), seg_cap, cursor.data(), &ctr, ovf.data(), OVF);
+                            w_split, words, k, P, bin_cap, bkt.data(), seg_cap, cursor.data(), &ctr, ovf.data(), OVF, 1u);
         std::vector<u64> count(P);
         for (u32 b = 0; b < P; ++b) count[b] = std::min<u64>(cursor[b], seg_cap);
         const u64 tk = W == 1 ? PASSB1_KPT * PASSB1_ROUNDS : PASSB_KPT;     // blockDim = 1 in the emulation
         auto pass_b = [&](const PassBBucket *desc, u32 b0, u32 b1, u64 *ticket) {
             if constexpr (W == 1) {
-                if (n_shards > 1) bucket_insert_compact_kernel<true>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF, 1u);
-                else bucket_insert_compact_kernel<false>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF, 0u);
+                if (n_shards > 1) bucket_insert_compact_kernel<1>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF, 1u);
+                else bucket_insert_compact_kernel<0>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF, 0u);
             } else if (k % 2) {            // odd k: the batched kernel, even k: the one-key-at-a-time form of the protocol
                 bucket_insert_wide_kernel<W>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF);
             } else {
@@ -149,4 +149,67 @@ extern "C" int emul_insert_records(const u64 *records, u64 n, int k, u64 table_s
         *n_out = 0; export_kernel<Wv>(t, 1, keys_out, counts_out, cap_out, n_out);                                   \
         return ctr.overflow_n ? -2 : 0; }
     switch (Wd) { INS(1) INS(2) INS(3) INS(4) INS(5) INS(6) INS(7) INS(8) default: return -1; }
+}
+
+// ---- key exchange (pbk_keyx_*, k <= 32) -----------------------------------------------------------------------------
+// Pass A of one rank into the all-to-all send buffer: [dest][region][seg_cap] hashes + [dest][region] cursors.  Keys that
+// find their segment full come back as (key, weight) records -- pbk_api.cu routes those through the record exchange.
+extern "C" int emul_keyx_partition(const uint8_t *bases, const u64 *off, u64 n_reads, int k, u32 n_dest, u32 n_regions,
+                                   u64 seg_cap, u32 bin_cap, u64 *send, u64 *cursors, u64 *n_inst, u64 *spill_records,
+                                   u64 spill_cap, u64 *n_spill, u32 *err_flags)
+{
+    if (k > 32) return -1;
+    const u64 n_bases = off[n_reads], words = (n_bases + 31) / 32;
+    std::vector<u64> stream(words + STREAM_PAD_WORDS + 1, 0), len_hist(500001, 0);
+    std::vector<u32> nflag(words + STREAM_PAD_WORDS + 1, 0), rflag(words + STREAM_PAD_WORDS + 1, 0);
+    Counters ctr{};
+    read_marks_kernel(off, n_reads, len_hist.data(), rflag.data() + STREAM_PAD_WORDS, &ctr);
+    pack_kernel<false>(bases, n_bases, words, 0, stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, 0, &ctr);
+    const u32 P = n_dest * n_regions;
+    for (u32 b = 0; b < P; ++b) cursors[b] = 0;
+    const u64 w_split = words / 2;
+    for (int part = 0; part < 2; ++part)
+        partition_kernel<1, true>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS,
+                                  part ? w_split : 0, part ? words : w_split, k, P, bin_cap, send, seg_cap, cursors, &ctr,
+                                  spill_records, spill_cap, n_dest);
+    *n_inst = ctr.instances;
+    *n_spill = ctr.overflow_n;
+    *err_flags = ctr.error_flags;
+    return 0;
+}
+
+// Pass B of one rank over what the all-to-all delivered ([source][region][seg_cap], [source][region] cursors), descriptors
+// built as launch_bucket_insert_gathered builds them; `extra` = (key, weight) records that arrived by the record route
+extern "C" int emul_keyx_insert(const u64 *recv, const u64 *recv_cursors, u32 n_src, u32 n_regions, u64 seg_cap, int k,
+                                const u64 *extra, u64 n_extra, u64 *keys_out, uint16_t *counts_out, u64 cap_out, u64 *n_out)
+{
+    if (k > 32) return -1;
+    const u64 table_slots = 1ull << 24;
+    std::vector<u64> tv(table_slots, 0);
+    Table<1> t(tv.data(), tv.size());
+    Counters ctr{};
+    const u64 OVF = 1 << 12;
+    std::vector<u64> ovf(2 * OVF);
+    const u32 n_desc = n_src * n_regions;
+    const u64 tk = PASSB1_KPT * PASSB1_ROUNDS;                     // blockDim = 1 in the emulation
+    // two launches (pilot + rest), like pbk_keyx_insert_device on a first batch
+    const u32 cuts[3] = {0, n_src * (n_regions > 1 ? 1u : 0u), n_desc};
+    for (int part = 0; part < 2; ++part) {
+        const u32 d0 = cuts[part], d1 = cuts[part + 1];
+        if (d1 <= d0) continue;
+        std::vector<PassBBucket> desc(d1 - d0 + 1);
+        u64 tiles = 0, ticket[2] = {0, 0};
+        for (u32 i = d0; i < d1; ++i) {
+            const u64 n = std::min<u64>(recv_cursors[(i % n_src) * n_regions + i / n_src], seg_cap);
+            desc[i - d0] = PassBBucket{tiles, n, nullptr, nullptr, 0, 0};
+            tiles += (n + tk - 1) / tk;
+        }
+        desc[d1 - d0] = PassBBucket{tiles, 0, nullptr, nullptr, 0, 0};
+        if (tiles) bucket_insert_compact_kernel<2>(recv, seg_cap, desc.data(), d0, d1, ticket, t, t, 1, 0, &ctr, ovf.data(), OVF,
+                                                   (n_src << 8) | (n_regions << 16));
+    }
+    if (n_extra) insert_records_kernel<1>(extra, n_extra, 1, t, t, 1, 0, &ctr, ovf.data(), OVF);
+    *n_out = 0;
+    export_kernel<1>(t, 1, keys_out, counts_out, cap_out, n_out);
+    return ctr.overflow_n ? -2 : 0;
 }

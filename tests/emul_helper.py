@@ -81,3 +81,44 @@ def emul_insert_records(records: np.ndarray, k: int):
     keys, counts = keys[:m], counts[:m]
     order = np.lexsort(tuple(keys[:, w] for w in range(W)))
     return keys[order], counts[order]
+
+
+def emul_keyx_partition(bases: np.ndarray, offsets: np.ndarray, k: int, n_dest: int, n_regions: int, seg_cap: int,
+                        bin_cap: int = 3):
+    """Pass A of the key exchange: (send [n_dest, n_regions, seg_cap] u64, cursors [n_dest, n_regions] u64,
+    n_instances, spilled (key, weight) records)."""
+    bases = np.concatenate([np.ascontiguousarray(bases, dtype=np.uint8), np.zeros(64, np.uint8)])
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n_reads = len(offsets) - 1
+    send = np.zeros((n_dest, n_regions, seg_cap), np.uint64)
+    cursors = np.zeros((n_dest, n_regions), np.uint64)
+    spill_cap = max(1024, int(offsets[-1]))
+    spill = np.zeros((spill_cap, 2), np.uint64)
+    n_inst, n_spill, err = C.c_uint64(), C.c_uint64(), C.c_uint32()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().emul_keyx_partition(p(bases), p(offsets), C.c_uint64(n_reads), k, n_dest, n_regions, C.c_uint64(seg_cap), bin_cap,
+                                   p(send), p(cursors), C.byref(n_inst), p(spill), C.c_uint64(spill_cap), C.byref(n_spill),
+                                   C.byref(err))
+    assert rc == 0 and err.value == 0 and n_spill.value <= spill_cap
+    return send, cursors, n_inst.value, spill[:n_spill.value]
+
+
+def emul_keyx_insert(recv: np.ndarray, recv_cursors: np.ndarray, seg_cap: int, k: int, extra=None):
+    """Pass B of the key exchange over recv [n_src, n_regions, seg_cap] / recv_cursors [n_src, n_regions]; `extra` =
+    (key, weight) records received by the record route.  Returns the sorted (keys, counts) of this rank's table."""
+    recv = np.ascontiguousarray(recv, dtype=np.uint64)
+    recv_cursors = np.ascontiguousarray(recv_cursors, dtype=np.uint64)
+    n_src, n_regions = recv_cursors.shape
+    extra = np.zeros((0, 2), np.uint64) if extra is None else np.ascontiguousarray(extra, dtype=np.uint64).reshape(-1, 2)
+    cap = int(np.minimum(recv_cursors, seg_cap).sum()) + len(extra) + 1
+    keys = np.zeros((cap, 1), np.uint64)
+    counts = np.zeros(cap, np.uint16)
+    n_out = C.c_uint64()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().emul_keyx_insert(p(recv), p(recv_cursors), n_src, n_regions, C.c_uint64(seg_cap), k, p(extra),
+                                C.c_uint64(len(extra)), p(keys), p(counts), C.c_uint64(cap), C.byref(n_out))
+    assert rc == 0
+    m = n_out.value
+    keys, counts = keys[:m], counts[:m]
+    order = np.argsort(keys[:, 0], kind="stable")
+    return keys[order], counts[order]

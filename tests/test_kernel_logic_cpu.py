@@ -121,3 +121,46 @@ def test_hash_range_sharding_is_result_invariant(oracle, k, n_shards, tmp_path):
         sel = np.array([L.pbk_shard_of_key(np.ascontiguousarray(row).ctypes.data_as(C.c_void_p), k, n_shards) == dest
                         for row in want.keys], dtype=bool)
         assert np.array_equal(keys, want.keys[sel]) and np.array_equal(counts, want.counts[sel])
+
+
+@pytest.mark.parametrize("k,n_shards,n_regions,seg_cap", [(32, 2, 4, 4096), (21, 3, 2, 4096), (32, 4, 8, 40), (31, 8, 4, 4096)])
+def test_key_exchange_is_result_invariant(oracle, k, n_shards, n_regions, seg_cap, tmp_path):
+    """Second form of the sharding (pbk_keyx_*): Pass A writes [dest][region] segments of hashes, the all-to-all hands
+    every rank its [source][region] segments, Pass B (gather mode) inserts them region by region.  The merged tables must
+    be the unsharded one, every key on the rank pbk_shard_of_key names.  seg_cap = 40: most keys find their segment full
+    and take the record route instead."""
+    import ctypes as C
+    from emul_helper import emul_keyx_insert, emul_keyx_partition
+    from platanus_b_b200 import capi
+    L = capi.load_library()
+    O = oracle
+    rd = _reads(O, G.CASE_BY_NAME["smallfq_k32"], tmp_path)
+    want = O.count(rd, k)
+    bases, offs = rd.arrays()
+    n_reads = len(offs) - 1
+    cuts = [n_reads * r // n_shards for r in range(n_shards + 1)]
+    sends, cursors, spills, inst = [], [], [], 0
+    for r in range(n_shards):
+        lo, hi = cuts[r], cuts[r + 1]
+        s, c, n, sp = emul_keyx_partition(bases[int(offs[lo]):int(offs[hi])], offs[lo:hi + 1] - offs[lo], k, n_shards, n_regions, seg_cap)
+        sends.append(s); cursors.append(c); spills.append(sp); inst += n
+        for d in range(n_shards):                 # segment (d, j) holds hashes owned by shard d that live in table region j
+            for j in range(n_regions):
+                h = s[d, j, :min(int(c[d, j]), seg_cap)]
+                assert np.all(h >> np.uint64(64 - int(np.log2(n_regions))) == j)
+                assert np.all(((h & np.uint64(0xFFFFFFFF)) * np.uint64(n_shards)) >> np.uint64(32) == d)
+    assert inst == want.n_instances
+    assert (seg_cap == 40) == any(len(sp) for sp in spills)
+    owner_of = lambda key: L.pbk_shard_of_key(np.array([key], np.uint64).ctypes.data_as(C.c_void_p), k, n_shards)
+    spilled = np.concatenate(spills) if any(len(sp) for sp in spills) else np.zeros((0, 2), np.uint64)
+    spill_owner = np.array([owner_of(int(x)) for x in spilled[:, 0]], dtype=np.int64)
+    all_keys, all_counts = [], []
+    for dest in range(n_shards):
+        recv = np.stack([sends[src][dest] for src in range(n_shards)])              # what all_to_all_single delivers
+        rcur = np.stack([cursors[src][dest] for src in range(n_shards)])
+        keys, counts = emul_keyx_insert(recv, rcur, seg_cap, k, extra=spilled[spill_owner == dest])
+        assert all(owner_of(int(x)) == dest for x in keys[:, 0])
+        all_keys.append(keys); all_counts.append(counts)
+    keys = np.concatenate(all_keys); counts = np.concatenate(all_counts)
+    order = np.argsort(keys[:, 0], kind="stable")
+    assert np.array_equal(keys[order], want.keys) and np.array_equal(counts[order], want.counts)

@@ -79,3 +79,68 @@ def test_two_rank_exchange_over_gloo(oracle, k, tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), k, fq, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def _keyx_worker(rank, world, port, k, fq, seg_cap, out_dir):
+    """Second form of the exchange (pbk_keyx_*): the bucket store of Pass A is the all-to-all send buffer."""
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import ctypes as C
+
+    from emul_helper import emul_keyx_insert, emul_keyx_partition
+    from oracle import oracle as O
+    from platanus_b_b200 import capi, sharding
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = capi.load_library()
+        rd = O.Reads()
+        rd.add_file(fq)
+        bases, offs = rd.arrays()
+        n = len(offs) - 1
+        lo, hi = n * rank // world, n * (rank + 1) // world
+        b, o = bases[int(offs[lo]):int(offs[hi])], offs[lo:hi + 1] - offs[lo]
+        windows = int(o[-1]) - (len(o) - 1) * (k - 1)
+        assert sharding.max_windows_any_rank(windows) >= windows          # what pbk_keyx_plan is fed on every rank
+        n_regions = 4
+        send, cursors, n_inst, spilled = emul_keyx_partition(b, o, k, world, n_regions, seg_cap)
+        t_send, t_cur = torch.from_numpy(send.view(np.int64)), torch.from_numpy(cursors.view(np.int64))
+        recv, rcur = sharding.exchange_keys(t_send, t_cur, torch.empty_like(t_send), torch.empty_like(t_cur))
+        extra = None
+        if sharding.any_rank_staged(len(spilled)):                        # record route for keys whose segment was full
+            owner = np.array([L.pbk_shard_of_key(np.array([x], np.uint64).ctypes.data_as(C.c_void_p), k, world)
+                              for x in spilled[:, 0]], dtype=np.int64) if len(spilled) else np.zeros(0, np.int64)
+            order = np.argsort(owner, kind="stable")
+            staged = spilled[order].astype(np.int64)
+            cnt = torch.from_numpy(np.bincount(owner, minlength=world).astype(np.int64))
+            rc = sharding.exchange_counts(cnt)
+            extra = sharding.exchange_records(torch.from_numpy(staged.reshape(-1, 2).copy()), cnt.tolist(), rc.tolist()).numpy().astype(np.uint64)
+        else:
+            assert seg_cap >= 4096
+        keys, counts = emul_keyx_insert(recv.numpy().view(np.uint64), rcur.numpy().view(np.uint64), seg_cap, k, extra=extra)
+        want = O.count(rd, k)
+        sel = np.array([L.pbk_shard_of_key(np.ascontiguousarray(r).ctypes.data_as(C.c_void_p), k, world) == rank
+                        for r in want.keys], dtype=bool)
+        assert np.array_equal(keys, want.keys[sel]) and np.array_equal(counts, want.counts[sel])
+        hist = torch.from_numpy(np.bincount(counts.astype(np.int64), minlength=65535).astype(np.int64))
+        sharding.allreduce_histogram(hist)
+        assert np.array_equal(hist.numpy().astype(np.uint64), want.occ_hist)
+        inst = torch.tensor([n_inst], dtype=torch.int64)
+        dist.all_reduce(inst)
+        assert int(inst.item()) == want.n_instances
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("k,seg_cap", [(32, 8192), (21, 64)])
+def test_two_rank_key_exchange_over_gloo(oracle, k, seg_cap, tmp_path):
+    import emul_helper
+    emul_helper.lib()
+    fq = os.path.join(HERE, "golden", "inputs", "small.fq")
+    world = 2
+    mp.spawn(_keyx_worker, args=(world, _free_port(), k, fq, seg_cap, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
