@@ -282,95 +282,6 @@ def test_logical_shards_on_one_gpu_match_unsharded(oracle, k, n_shards):
             kc.close()
 
 
-def _keyx_logical_shards(O, b, o, k, n_shards):
-    """G logical shards on one GPU through pbk_keyx_*: partition per rank, the all-to-all replaced by device-to-device
-    copies of the equal splits, gathered Pass B per rank, then the record route for whatever was staged."""
-    from devbuf import DevBuf
-    n = len(o) - 1
-    ctxs = [KmerCounter(k, n_shards=n_shards, shard_rank=r) for r in range(n_shards)]
-    bufs = []
-    try:
-        parts = [(b[int(o[n * r // n_shards]):int(o[n * (r + 1) // n_shards])],
-                  o[n * r // n_shards:n * (r + 1) // n_shards + 1] - o[n * r // n_shards]) for r in range(n_shards)]
-        max_w = max(int(po[-1]) - (len(po) - 1) * (k - 1) for _, po in parts)
-        lays = [kc.keyx_plan(max_w) for kc in ctxs]
-        lay = lays[0]
-        assert all((l.n_regions, l.seg_cap, l.bytes_per_dest) == (lay.n_regions, lay.seg_cap, lay.bytes_per_dest) for l in lays)
-        assert lay.n_dest == n_shards and lay.bytes_per_dest == lay.n_regions * lay.seg_cap * 8
-        bpd, cpd = int(lay.bytes_per_dest), int(lay.cursors_per_dest) * 8
-        sends, curs = [], []
-        for kc, (pb, po) in zip(ctxs, parts):
-            sends.append(DevBuf(n_shards * bpd)); curs.append(DevBuf(n_shards * cpd))
-            bufs += [sends[-1], curs[-1]]
-            kc.keyx_partition(pb, po, sends[-1].ptr, curs[-1].ptr)
-        sent = sum(int(np.minimum(c.to_host(), lay.seg_cap).sum()) for c in curs)
-        for dest, kc in enumerate(ctxs):
-            recv, rcur = DevBuf(n_shards * bpd), DevBuf(n_shards * cpd)
-            bufs += [recv, rcur]
-            for src in range(n_shards):
-                recv.copy_from(sends[src], src * bpd, dest * bpd, bpd)
-                rcur.copy_from(curs[src], src * cpd, dest * cpd, cpd)
-            kc.keyx_insert_device(recv.ptr, rcur.ptr)
-        # record route: keys that found their segment full
-        W = 1
-        counts = [kc.shard_send_counts(n_shards) for kc in ctxs]
-        staged = int(sum(c.sum() for c in counts))
-        packs = []
-        for kc, cnt in zip(ctxs, counts):
-            packs.append(DevBuf((int(cnt.sum()) + 1) * (W + 1) * 8)); bufs.append(packs[-1])
-            kc.shard_pack_device(packs[-1].ptr, int(cnt.sum()) + 1)
-        for dest, kc in enumerate(ctxs):
-            for src in range(n_shards):
-                m = int(counts[src][dest])
-                if src == dest or m == 0:
-                    continue
-                part = DevBuf(m * (W + 1) * 8); bufs.append(part)
-                part.copy_from(packs[src], 0, int(counts[src][:dest].sum()) * (W + 1) * 8, m * (W + 1) * 8)
-                kc.shard_insert_device(part.ptr, m)
-        keys, cts, inst, hist = [], [], 0, np.zeros(65535, np.uint64)
-        for kc in ctxs:
-            kc.finalize()
-            kk, cc = kc.export(1, sorted=True)
-            keys.append(kk); cts.append(cc); inst += kc.n_instances; hist += kc.occ_hist
-        keys = np.concatenate(keys); cts = np.concatenate(cts)
-        order = np.argsort(keys[:, 0], kind="stable")
-        return keys[order], cts[order], inst, hist, sent, staged, [int(kc.n_distinct) for kc in ctxs]
-    finally:
-        for kc in ctxs:
-            kc.close()
-        for d in bufs:
-            d.free()
-
-
-@pytest.mark.parametrize("k,n_shards", [(32, 2), (21, 3), (32, 8)])
-def test_key_exchange_logical_shards_match_unsharded(oracle, k, n_shards):
-    """SURVEY.md section 8e, second form of the exchange (include/pbk.h, pbk_keyx_*): the keys travel before counting."""
-    O = oracle
-    rs = synth.make_reads(synth.config("C1", scale=1 / 60))
-    b, o = rs.flat()
-    want = O.count(_oracle_reads_from_set(O, rs), k)
-    keys, cts, inst, hist, sent, staged, sizes = _keyx_logical_shards(O, b, o, k, n_shards)
-    assert staged == 0 and sent == want.n_instances                  # uniform hashes: no segment overflows
-    assert np.array_equal(keys, want.keys) and np.array_equal(cts, want.counts)
-    assert inst == want.n_instances and np.array_equal(hist, want.occ_hist)
-    assert max(sizes) < 1.2 * (sum(sizes) / n_shards) + 64
-
-
-def test_key_exchange_full_segments_take_the_record_route(oracle, tmp_path):
-    """70 000 copies of one read: ten k-mers with 70 000 instances each overflow their (destination, region) segments;
-    the surplus is pre-aggregated in the remote-staging table and reaches its owner as (key, count) records.  Counts
-    saturate at 65 534 after summing."""
-    O = oracle
-    case = G.CASE_BY_NAME["sat_k32"]
-    rd = _reads(O, case, tmp_path)
-    want = O.count(rd, case.k)
-    b, o = rd.arrays()
-    keys, cts, inst, hist, sent, staged, _ = _keyx_logical_shards(O, b, o, case.k, 4)
-    assert staged > 0 and sent < want.n_instances
-    assert np.array_equal(keys, want.keys) and np.array_equal(cts, want.counts)
-    assert inst == want.n_instances and np.array_equal(hist, want.occ_hist)
-
-
 def test_table_growth_from_a_tiny_hint(oracle):
     O = oracle
     rs = synth.make_reads(synth.config("C3", scale=1 / 200))
