@@ -236,6 +236,22 @@ int ensure_overflow(pbk_ctx *c, u64 records)
     return PBK_OK;
 }
 
+// Overflow list for a partitioned batch of `windows` windows.  Pass A spills what does not fit its bucket segment, and
+// with heavily duplicated input (amplicons: millions of copies of a few k-mers) that can be most of the batch; every
+// window spills at most once, so a list as long as the batch cannot be exhausted.  It is only address space until
+// something is written to it.  If the HBM budget does not allow it, the old fixed size stays (and ERR_OVERFLOW_LOST
+// remains possible for such input).
+int ensure_overflow_for_batch(pbk_ctx *c, u64 windows)
+{
+    const u64 floor_records = 1ull << 22;
+    const u64 want = std::max<u64>(floor_records, windows);
+    if (want <= c->ovf_cap) return PBK_OK;
+    const int rc = ensure_overflow(c, want);
+    if (rc != PBK_E_NOMEM) return rc;
+    c->err.clear();
+    return ensure_overflow(c, floor_records);
+}
+
 // Spilled keys (no slot within the probe limit, or a full bucket segment in Pass A): insert them from
 // a private copy of the list.  The table only grows if it is really loaded, or if a plain retry
 // spilled again.
@@ -373,7 +389,7 @@ int prepare_partition(pbk_ctx *c, u64 windows_ub, u64 windows_total)
     TRY(ensure_passb_buffers(c));
     CK(cudaMemsetAsync(c->d_bkt_cursor, 0, PART_MAX_BUCKETS * 8, c->s_compute));
     // a spilled key (bucket segment or bin full) is rare; the list is also used by Pass B
-    TRY(ensure_overflow(c, 1ull << 22));
+    TRY(ensure_overflow_for_batch(c, windows_total));
     return PBK_OK;
 }
 
@@ -525,7 +541,7 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
     } else if (keyx) {
         c->plan = c->keyx_plan;
         CK(cudaMemsetAsync(c->keyx_cursors, 0, (size_t)c->plan.n_buckets * 8, c->s_compute));
-        TRY(ensure_overflow(c, 1ull << 22));
+        TRY(ensure_overflow_for_batch(c, windows_ub));
     } else if (partitioned) {
         TRY(prepare_partition(c, windows_ub, windows_ub));
     }

@@ -113,3 +113,27 @@ def test_key_exchange_full_segments_take_the_record_route(oracle, tmp_path):
     assert staged > 0 and sent < want.n_instances
     assert np.array_equal(keys, want.keys) and np.array_equal(cts, want.counts)
     assert inst == want.n_instances and np.array_equal(hist, want.occ_hist)
+
+
+def test_heavily_duplicated_input_cannot_exhaust_the_overflow_list(oracle):
+    """Amplicon-like input: 1.2 M copies of one 41 bp read = 12 M windows of ten k-mers.  Each k-mer has 1.2 M instances
+    but its bucket segment holds ~0.2 M, so ~10 M windows spill in Pass A -- more than the 4 M records the overflow list
+    used to hold (ERR_OVERFLOW_LOST).  The list is now as long as the batch; the counts saturate at 65 534 like the
+    reference's (counter.h:468)."""
+    O = oracle
+    copies = 1_200_000
+    read = np.frombuffer(G.SAT_READ, dtype=np.uint8)
+    b = np.tile(read, copies)
+    o = np.arange(copies + 1, dtype=np.uint64) * np.uint64(len(read))
+    rd = O.Reads()
+    rd.add_array(b, o)
+    want = O.count(rd, 32)
+    assert want.n_instances == copies * 10 and int(want.counts.max()) == 65534
+    with KmerCounter(32) as kc:
+        kc.push_reads(b, o)
+        kc.finalize()
+        keys, counts = kc.export(1, sorted=True)
+        assert kc.n_instances == want.n_instances
+        assert kc.stats()["launches_partition"] >= 1            # the bucket pass was taken
+    assert np.array_equal(keys, want.keys) and np.array_equal(counts, want.counts)
+    assert np.array_equal(kc.occ_hist, want.occ_hist)
