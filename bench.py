@@ -264,11 +264,21 @@ def main_ours(args):
     # the form measured in round 1.
     keyx = world > 1 and args.exchange == "keys" and W == 1
     if keyx:
-        max_w = sharding.max_windows_any_rank(n_bases - n_reads * (K - 1), device="cuda")
+        # the batch in --keyx-chunks chunks (cut at read boundaries): the all-to-all of one chunk is in flight while the
+        # next one is partitioned and the previous one inserted (sharding.pipelined_key_exchange)
+        ranges = sharding.chunk_read_ranges(offsets, max(1, args.keyx_chunks))
+        n_ch = sharding.max_windows_any_rank(len(ranges), device="cuda")          # same number of collectives on every rank
+        ranges += [(n_reads, n_reads)] * (n_ch - len(ranges))
+        ch = []
+        for r0, r1 in ranges:
+            o_c = (offsets[r0:r1 + 1] - offsets[r0]).astype(np.int64)
+            h_o = torch.from_numpy(o_c.copy()).pin_memory()
+            ch.append({"n_reads": r1 - r0, "b0": int(offsets[r0]), "n_bases": int(offsets[r1] - offsets[r0]), "h_offs": h_o, "d_offs": h_o.cuda()})
+        max_w = sharding.max_windows_any_rank(max(max(c["n_bases"] - c["n_reads"] * (K - 1), 0) for c in ch), device="cuda")
         lay = kc.keyx_plan(max_w)
         shape = (world, int(lay.n_regions), int(lay.seg_cap))
-        kx_send, kx_recv = (torch.empty(shape, dtype=torch.int64, device="cuda") for _ in range(2))
-        kx_cur, kx_rcur = (torch.zeros(shape[:2], dtype=torch.int64, device="cuda") for _ in range(2))
+        kx_send, kx_recv = ([torch.empty(shape, dtype=torch.int64, device="cuda") for _ in range(2)] for _ in range(2))
+        kx_cur, kx_rcur = ([torch.zeros(shape[:2], dtype=torch.int64, device="cuda") for _ in range(2)] for _ in range(2))
 
     def exchange():
         """hash-range all-to-all of pre-aggregated (k-mer, count) records (platanus_b_b200/sharding.py over NCCL)"""
@@ -287,14 +297,17 @@ def main_ours(args):
         return n_send * (W + 1) * 8
 
     def step_keyx(resident: bool):
-        if resident:
-            kc.keyx_partition_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, n_bases, kx_send.data_ptr(), kx_cur.data_ptr())
-        else:
-            kc.keyx_partition_ptr(h_bases.data_ptr(), h_offs.data_ptr(), n_reads, kx_send.data_ptr(), kx_cur.data_ptr())
-        sharding.exchange_keys(kx_send, kx_cur, kx_recv, kx_rcur)
-        torch.cuda.current_stream().synchronize()
-        kc.keyx_insert_device(kx_recv.data_ptr(), kx_rcur.data_ptr())
-        sent = (world - 1) * int(lay.bytes_per_dest)
+        def partition(i, send, cur):
+            c = ch[i]
+            if resident:
+                kc.keyx_partition_device(d_bases.data_ptr() + c["b0"], c["d_offs"].data_ptr(), c["n_reads"], c["n_bases"],
+                                         send.data_ptr(), cur.data_ptr())
+            else:
+                kc.keyx_partition_ptr(h_bases.data_ptr() + c["b0"], c["h_offs"].data_ptr(), c["n_reads"], send.data_ptr(), cur.data_ptr())
+
+        sharding.pipelined_key_exchange(len(ch), partition, lambda r, rc: kc.keyx_insert_device(r.data_ptr(), rc.data_ptr()),
+                                        kx_send, kx_cur, kx_recv, kx_rcur, torch.cuda.current_stream().synchronize)
+        sent = len(ch) * (world - 1) * int(lay.bytes_per_dest)
         if sharding.any_rank_staged(int(kc.shard_send_counts(world).sum()), device="cuda"):
             sent += exchange()                  # keys whose segment was full (a k-mer repeated millions of times)
         return sent
@@ -444,6 +457,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C1")
+    ap.add_argument("--keyx-chunks", type=int, default=int(os.environ.get("PBK_BENCH_KEYX_CHUNKS", "4")),
+                    help="--exchange keys: chunks per step (the all-to-all of one chunk overlaps the passes of its neighbours)")
     ap.add_argument("--exchange", default=os.environ.get("PBK_BENCH_EXCHANGE", "records"), choices=["records", "keys"],
                     help="N > 1: what crosses NVLink -- (key, count) records after counting, or the keys before it")
     ap.add_argument("--scale", type=float, default=1.0)

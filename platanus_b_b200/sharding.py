@@ -59,3 +59,51 @@ def any_rank_staged(n_staged_here: int, device=None, group=None) -> bool:
     t = torch.tensor([int(n_staged_here)], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return int(t.item()) > 0
+
+
+def pipelined_key_exchange(n_chunks: int, partition, insert, send, cursors, recv, recv_cursors, wait_collectives, group=None):
+    """The key exchange over a batch cut into chunks, so that the all-to-all of chunk i runs while Pass A of chunk i + 1
+    and Pass B of chunk i - 1 are computed.
+
+      partition(i, send_buf, cursor_buf)   Pass A of chunk i into the buffers (pbk_keyx_partition*; returns when they
+                                           are complete)
+      insert(recv_buf, recv_cursor_buf)    Pass B over a received chunk (pbk_keyx_insert_device)
+      send, cursors, recv, recv_cursors    two buffers each (double buffering), shaped as for exchange_keys
+      wait_collectives()                   blocks the host until the collectives issued so far have finished (NCCL:
+                                           synchronize the current stream after Work.wait(); gloo: nothing to do)
+
+    Buffer reuse: chunk i uses buffers i % 2.  Its send buffer is rewritten by partition(i + 2), which is called after
+    chunk i's all-to-all has been waited for; its receive buffer is rewritten by the all-to-all of chunk i + 2, which
+    is issued after insert() of chunk i has returned."""
+    def finish(p):
+        works, s = p
+        for w in works:
+            w.wait()
+        wait_collectives()
+        insert(recv[s], recv_cursors[s])
+
+    pending = None
+    for i in range(n_chunks):
+        s = i & 1
+        partition(i, send[s], cursors[s])
+        works = [dist.all_to_all_single(recv[s].view(-1), send[s].view(-1), group=group, async_op=True),
+                 dist.all_to_all_single(recv_cursors[s].view(-1), cursors[s].view(-1), group=group, async_op=True)]
+        if pending is not None:
+            finish(pending)
+        pending = (works, s)
+    if pending is not None:
+        finish(pending)
+
+
+def chunk_read_ranges(offsets, n_chunks: int):
+    """[lo, hi) read ranges of roughly equal base counts (chunks are cut at read boundaries)."""
+    import numpy as np
+    offsets = np.asarray(offsets)
+    n = len(offsets) - 1
+    total = int(offsets[-1])
+    cuts = [0]
+    for c in range(1, n_chunks):
+        cuts.append(int(np.searchsorted(offsets, total * c // n_chunks, side="left")))
+    cuts.append(n)
+    cuts = sorted(set(min(max(x, 0), n) for x in cuts))
+    return [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]]

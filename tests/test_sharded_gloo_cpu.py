@@ -136,6 +136,76 @@ def _keyx_worker(rank, world, port, k, fq, seg_cap, out_dir):
         dist.destroy_process_group()
 
 
+def _keyx_pipeline_worker(rank, world, port, k, fq, n_chunks, out_dir):
+    """sharding.pipelined_key_exchange: the batch in chunks, the all-to-all of one chunk in flight (async_op) while the
+    next chunk is partitioned and the previous one inserted; double-buffered send/receive buffers."""
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import ctypes as C
+
+    from emul_helper import emul_insert_records, emul_keyx_insert, emul_keyx_partition
+    from oracle import oracle as O
+    from platanus_b_b200 import capi, sharding
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = capi.load_library()
+        rd = O.Reads()
+        rd.add_file(fq)
+        bases, offs = rd.arrays()
+        n = len(offs) - 1
+        lo, hi = n * rank // world, n * (rank + 1) // world
+        b, o = bases[int(offs[lo]):int(offs[hi])], offs[lo:hi + 1] - offs[lo]
+        ranges = sharding.chunk_read_ranges(o, n_chunks)
+        assert ranges[0][0] == 0 and ranges[-1][1] == len(o) - 1 and all(a[1] == c[0] for a, c in zip(ranges, ranges[1:]))
+        n_ch = sharding.max_windows_any_rank(len(ranges))                 # every rank must issue the same collectives
+        ranges += [(len(o) - 1, len(o) - 1)] * (n_ch - len(ranges))       # empty chunks: zero cursors travel
+        n_regions, seg_cap = 4, 8192
+        send = [torch.zeros((world, n_regions, seg_cap), dtype=torch.int64) for _ in range(2)]
+        cur = [torch.zeros((world, n_regions), dtype=torch.int64) for _ in range(2)]
+        recv = [torch.zeros_like(send[0]) for _ in range(2)]
+        rcur = [torch.zeros_like(cur[0]) for _ in range(2)]
+        inst, tables = [0], []
+
+        def partition(i, send_buf, cur_buf):
+            r0, r1 = ranges[i]
+            s, c, n_inst, spilled = emul_keyx_partition(b[int(o[r0]):int(o[r1])], o[r0:r1 + 1] - o[r0], k, world, n_regions, seg_cap)
+            assert len(spilled) == 0
+            send_buf.copy_(torch.from_numpy(s.view(np.int64)))
+            cur_buf.copy_(torch.from_numpy(c.view(np.int64)))
+            inst[0] += n_inst
+
+        def insert(recv_buf, rcur_buf):                                    # (the emulation has no persistent table: one table
+            keys, counts = emul_keyx_insert(recv_buf.numpy().view(np.uint64).copy(), rcur_buf.numpy().view(np.uint64).copy(), seg_cap, k)
+            tables.append(np.concatenate([keys, counts.astype(np.uint64)[:, None]], axis=1))     # per chunk, merged below)
+
+        sharding.pipelined_key_exchange(len(ranges), partition, insert, send, cur, recv, rcur, lambda: None)
+        keys, counts = emul_insert_records(np.concatenate(tables), k)
+        want = O.count(rd, k)
+        sel = np.array([L.pbk_shard_of_key(np.ascontiguousarray(r).ctypes.data_as(C.c_void_p), k, world) == rank
+                        for r in want.keys], dtype=bool)
+        assert np.array_equal(keys, want.keys[sel]) and np.array_equal(counts, want.counts[sel])
+        t = torch.tensor([inst[0]], dtype=torch.int64)
+        dist.all_reduce(t)
+        assert int(t.item()) == want.n_instances
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_chunks", [1, 3, 4])
+def test_two_rank_pipelined_key_exchange_over_gloo(oracle, n_chunks, tmp_path):
+    import emul_helper
+    emul_helper.lib()
+    fq = os.path.join(HERE, "golden", "inputs", "small.fq")
+    world = 2
+    mp.spawn(_keyx_pipeline_worker, args=(world, _free_port(), 32, fq, n_chunks, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
 @pytest.mark.parametrize("k,seg_cap", [(32, 8192), (21, 64)])
 def test_two_rank_key_exchange_over_gloo(oracle, k, seg_cap, tmp_path):
     import emul_helper
