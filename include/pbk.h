@@ -215,6 +215,30 @@ int  pbk_keyx_partition_device(pbk_ctx *ctx, const void *d_bases, const void *d_
  * [source rank][region] fill counts                                                               */
 int  pbk_keyx_insert_device(pbk_ctx *ctx, const void *d_recv, const void *d_recv_cursors);
 
+/* ---- consumers of the table --------------------------------------
+ * Occurrence of every k-mer window of a batch of sequences: ContigDivider::getOccurrenceArray
+ * (kmer_divide.cpp:151-197, via Counter::findValue) and the table probe of
+ * divideKmerUsedMakingPreviousContig (counter.h:828-861).  The table is only read.
+ *   occ_out  u16 per BASE: occ_out[read_offsets[r] + i] = min(count, 65534) of the canonical k-mer of
+ *            the window starting at base i of read r; 0 if the k-mer is not in the table, if the
+ *            window contains an N, and for the last k - 1 bases of every read (no window starts there).
+ * With n_shards > 1 only keys this shard owns are found: summing occ_out over the shards gives the
+ * global answer.  Other arguments as pbk_push_reads; at most 2^31 bases per call.                  */
+int  pbk_lookup(pbk_ctx *ctx, const uint8_t *bases, const uint64_t *read_offsets, uint64_t n_reads,
+                int encoding, const int32_t *n_pos, const uint64_t *n_pos_offsets, uint16_t *occ_out);
+/* same with inputs and output in device memory (d_occ_out: n_bases u16, 8-byte aligned)              */
+int  pbk_lookup_device(pbk_ctx *ctx, const void *d_bases, const void *d_read_offsets, uint64_t n_reads,
+                       uint64_t n_bases, void *d_occ_out);
+/* Add n (key, count) entries to the table (host arrays; keys n x ceil(k/32) words, word 0 first):
+ * what Counter::readOccurrenceTableBinary leaves in memory, or a contig-seeded table
+ * (makeKmerReadDistributionFromContig, counter.h:511-593).  Counts of equal keys add up, saturating. */
+int  pbk_load_entries(pbk_ctx *ctx, const uint64_t *keys, const uint16_t *counts, uint64_t n);
+/* Counter::readOccurrenceTableBinary (counter.h:967-993) + DoubleHash::readTable (doubleHash.h:280-293):
+ * the entries of a PREFIX_kmer_occ.bin as malloc'ed arrays (release with pbk_free).                 */
+int  pbk_read_kmer_occ_bin(const char *path, uint32_t *k_out, uint64_t *index_size_out,
+                           uint64_t **keys_out, uint16_t **counts_out, uint64_t *n_out);
+void pbk_free(void *p);
+
 /* ---- host-side pieces of the path that stay on the CPU (negligible cost) --- */
 /* Counter::getLeftLocalMinimalValue (counter.h:245-267) */
 uint64_t pbk_left_local_min(const uint64_t *occ_hist, uint64_t max_occurrence, uint64_t window);

@@ -354,6 +354,73 @@ int pbo_count(const pbo_reads *r, unsigned k, pbo_result *res)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* occurrence lookup                                                                          */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Counter::findValue -> DoubleHash::findValue: the stored count, 0 when the key is absent.  The
+ * table here is the sorted (key, count) dump, searched by bisection. */
+static uint16_t table_find(const uint64_t *keys, const uint16_t *counts, uint64_t n, unsigned words, const uint64_t *key)
+{
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint64_t mid = lo + (hi - lo) / 2;
+        int c = pbo_key_cmp(keys + mid * words, key, words);
+        if (c == 0) return counts[mid];
+        if (c < 0) lo = mid + 1; else hi = mid;
+    }
+    return 0;
+}
+
+/* ContigDivider::getOccurrenceArray (kmer_divide.cpp:151-197) over sequences loaded the way
+ * Contig::setSeq does (common.h:528-537: base[i] = Char2Bin(c), an N stays 4).  out has one entry per
+ * BASE, out[offsets[r] + start] for the window starting at `start` of sequence r (the reference's
+ * OccurrenceArray has length - k + 1 entries per sequence, zero-initialised, kmer_divide.h:45-50);
+ * entries no window starts at stay 0.  Pinned by tests/golden/occ_*.npz (oracle/ref_occ_harness.cpp). */
+int pbo_occurrence_array(const pbo_reads *r, unsigned k, const uint64_t *keys, const uint16_t *counts,
+                         uint64_t n, uint16_t *out)
+{
+    if (k == 0) return PBO_E_ARG;
+    unsigned words = (k + 31) / 32;
+    if (words > MAXW) return PBO_E_ARG;
+    uint64_t *fwd = (uint64_t *)calloc(words, sizeof(uint64_t));
+    uint64_t *rev = (uint64_t *)calloc(words, sizeof(uint64_t));
+    if (!fwd || !rev) { free(fwd); free(rev); return PBO_E_NOMEM; }
+    memset(out, 0, r->offsets[r->n_reads] * sizeof(uint16_t));
+    for (uint64_t ri = 0; ri < r->n_reads; ++ri) {
+        const char *s = r->bases + r->offsets[ri];
+        uint64_t len = r->offsets[ri + 1] - r->offsets[ri];
+        if (len < k) continue;                                   /* numKmer == 0 (kmer_divide.cpp:160) */
+        uint64_t num_kmer = len - k + 1, start = 0;
+        uint16_t *o = out + r->offsets[ri];
+        int is_init = 1;
+        while (start < num_kmer) {
+            if (is_init) {
+                uint64_t j = 0;
+                for (; j < k - 1; ++j) {
+                    unsigned char b = pbo_char2bin(s[start + j]);
+                    if (b == 4) break;
+                    key_set(fwd, k - 2 - (unsigned)j, b);
+                    key_set(rev, (unsigned)j + 1, (unsigned char)(0x3 ^ b));
+                }
+                if (j == k - 1) is_init = 0;
+                else { start += j + 1; continue; }
+            }
+            unsigned char b = pbo_char2bin(s[start + k - 1]);
+            if (b == 4) { start += k; is_init = 1; continue; }
+            key_shl2(fwd, words, k);
+            key_shr2(rev, words);
+            key_set(fwd, 0, b);
+            key_set(rev, k - 1, (unsigned char)(0x3 ^ b));
+            const uint64_t *key = pbo_key_cmp(fwd, rev, words) <= 0 ? fwd : rev;
+            o[start] = table_find(keys, counts, n, words, key);
+            ++start;
+        }
+    }
+    free(fwd); free(rev);
+    return PBO_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* histogram statistics                                                                       */
 /* ------------------------------------------------------------------------------------------ */
 

@@ -67,6 +67,7 @@ def lib():
         L.pbo_char2bin.restype = C.c_ubyte
         L.pbo_count.argtypes = [C.POINTER(_Reads), C.c_uint, C.POINTER(_Result)]
         L.pbo_result_release.argtypes = [C.POINTER(_Result)]
+        L.pbo_occurrence_array.argtypes = [C.POINTER(_Reads), C.c_uint, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.pbo_left_local_min.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         L.pbo_left_local_min.restype = C.c_uint64
         L.pbo_dist_average.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]
@@ -176,6 +177,43 @@ def count(reads: Reads, k: int) -> CountResult:
         return CountResult(int(res.k), w, int(res.n_instances), keys, counts, occ, lh, int(res.max_occ))
     finally:
         lib().pbo_result_release(C.byref(res))
+
+
+def occurrence_array(seqs: Reads, k: int, keys: np.ndarray, counts: np.ndarray) -> np.ndarray:
+    """ContigDivider::getOccurrenceArray (kmer_divide.cpp:151-197): u16 per base of `seqs` (window start indexed), looked
+    up in the table given as its sorted dump (keys [n, words] ascending in reference order, counts [n])."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    counts = np.ascontiguousarray(counts, dtype=np.uint16)
+    _, offs = seqs.arrays()
+    out = np.zeros(int(offs[-1]), np.uint16)
+    rc = lib().pbo_occurrence_array(seqs._p, k, keys.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p),
+                                    len(counts), out.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise OracleError(rc, "pbo_occurrence_array")
+    return out
+
+
+REF_OCC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "ref_occ_harness")
+
+
+def run_ref_occurrence(bin_path: str, contigs_fa: str, workdir: str):
+    """oracle/ref_occ_harness.cpp: the UNMODIFIED reference's getOccurrenceArray + dumpKmerCoverage.  Returns
+    [(name, np.uint64 array)] per contig."""
+    import subprocess
+    out = os.path.join(workdir, "ref_occ.txt")
+    subprocess.run([REF_OCC, bin_path, contigs_fa, out], check=True, capture_output=True)
+    res, name, vals = [], None, []
+    for ln in open(out):
+        ln = ln.strip()
+        if ln.startswith(">"):
+            if name is not None:
+                res.append((name, np.array(vals, np.uint64)))
+            name, vals = ln[1:], []
+        elif ln:
+            vals.append(int(ln))
+    if name is not None:
+        res.append((name, np.array(vals, np.uint64)))
+    return res
 
 
 def _u64ptr(a: np.ndarray):

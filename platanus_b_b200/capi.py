@@ -39,6 +39,7 @@ SYMBOLS = [
     "pbk_distribution_average", "pbk_double_hash_size", "pbk_write_frq_tsv", "pbk_write_kmer_occ_bin",
     "pbk_microbench_atomics", "pbk_timer_mark", "pbk_timer_elapsed_ms", "pbk_set_timing",
     "pbk_keyx_plan", "pbk_keyx_partition", "pbk_keyx_partition_device", "pbk_keyx_insert_device",
+    "pbk_lookup", "pbk_lookup_device", "pbk_load_entries", "pbk_read_kmer_occ_bin", "pbk_free",
 ]
 
 
@@ -120,6 +121,12 @@ def load_library(build_if_missing: bool = True):
     L.pbk_shard_pack_device.argtypes = [vp, vp, C.c_uint64]
     L.pbk_shard_insert_device.argtypes = [vp, vp, C.c_uint64]
     L.pbk_shard_of_key.argtypes = [u64p, C.c_uint32, C.c_uint32]; L.pbk_shard_of_key.restype = C.c_uint32
+    L.pbk_lookup.argtypes = [vp, vp, u64p, C.c_uint64, C.c_int, vp, u64p, vp]
+    L.pbk_lookup_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, vp]
+    L.pbk_load_entries.argtypes = [vp, u64p, vp, C.c_uint64]
+    L.pbk_read_kmer_occ_bin.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp),
+                                        C.POINTER(C.c_uint64)]
+    L.pbk_free.argtypes = [vp]; L.pbk_free.restype = None
     L.pbk_keyx_plan.argtypes = [vp, C.c_uint64, C.POINTER(PbkKeyxLayout)]
     L.pbk_keyx_partition.argtypes = [vp, vp, u64p, C.c_uint64, C.c_int, vp, u64p, vp, vp]
     L.pbk_keyx_partition_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, vp, vp]
@@ -271,6 +278,41 @@ class KmerCounter:
     def shard_insert_device(self, d_records_ptr: int, n_records: int):
         self._check(self._L.pbk_shard_insert_device(self._ctx, C.c_void_p(d_records_ptr), n_records),
                     "pbk_shard_insert_device")
+
+    # -- consumers of the table (kmer_divide.cpp:151-197; counter.h:967-993) -------------------------
+    def lookup(self, bases: np.ndarray, offsets: np.ndarray, encoding: int = ENC_ASCII, n_pos=None, n_pos_offsets=None) -> np.ndarray:
+        """u16 per base: occurrence of the k-mer window starting there (ContigDivider::getOccurrenceArray), 0 if absent / N."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        out = np.zeros(int(offsets[-1]), np.uint16)
+        np_p = npo_p = None
+        if encoding == ENC_PLATANUS:
+            n_pos = np.ascontiguousarray(n_pos, dtype=np.int32)
+            n_pos_offsets = np.ascontiguousarray(n_pos_offsets, dtype=np.uint64)
+            np_p, npo_p = _ptr(n_pos), _ptr(n_pos_offsets)
+        self._check(self._L.pbk_lookup(self._ctx, _ptr(bases), _ptr(offsets), len(offsets) - 1, encoding, np_p, npo_p, _ptr(out)),
+                    "pbk_lookup")
+        return out
+
+    def load_entries(self, keys: np.ndarray, counts: np.ndarray):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        counts = np.ascontiguousarray(counts, dtype=np.uint16)
+        self._check(self._L.pbk_load_entries(self._ctx, _ptr(keys), _ptr(counts), len(counts)), "pbk_load_entries")
+
+    def read_occurrence_table_binary(self, path: str):
+        """Counter::readOccurrenceTableBinary (counter.h:967-993): load PREFIX_kmer_occ.bin into this counter's table."""
+        k, idx, n = C.c_uint32(), C.c_uint64(), C.c_uint64()
+        keys, counts = C.c_void_p(), C.c_void_p()
+        rc = self._L.pbk_read_kmer_occ_bin(path.encode(), C.byref(k), C.byref(idx), C.byref(keys), C.byref(counts), C.byref(n))
+        if rc:
+            raise PbkError(rc, "pbk_read_kmer_occ_bin", path)
+        try:
+            if k.value != self.k:
+                self.reset(k.value)
+            self._check(self._L.pbk_load_entries(self._ctx, keys, counts, n.value), "pbk_load_entries")
+        finally:
+            self._L.pbk_free(keys); self._L.pbk_free(counts)
+        return n.value
 
     # -- sharding, second form: keys exchanged before counting (k <= 32) ---------------------------
     def keyx_plan(self, max_windows_any_rank: int) -> PbkKeyxLayout:

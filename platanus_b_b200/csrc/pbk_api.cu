@@ -79,6 +79,7 @@ struct pbk_ctx {
 
     // key exchange (pbk_keyx_*): layout agreed between the ranks, and -- only during a pbk_keyx_partition* call -- the
     // caller's send buffer and cursors that Pass A fills instead of the context's own bucket store
+    u64 *d_len_scratch = nullptr; Counters *d_ctr_scratch = nullptr;     // pbk_lookup: its reads must not enter the histograms
     PartitionPlan keyx_plan{}; u64 keyx_max_windows = 0;
     u64 *keyx_send = nullptr, *keyx_cursors = nullptr;
 
@@ -649,6 +650,7 @@ void release_all(pbk_ctx *c)
     cudaFree(c->d_passb); if (c->h_passb) cudaFreeHost(c->h_passb);
     cudaFree(c->table.slots); cudaFree(c->remote.slots); cudaFree(c->d_ctr); cudaFree(c->d_ovf);
     cudaFree(c->d_len_hist); cudaFree(c->d_occ_hist); cudaFree(c->d_shard_counts);
+    cudaFree(c->d_len_scratch); cudaFree(c->d_ctr_scratch);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     for (auto &e : c->timer) if (e) cudaEventDestroy(e);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
@@ -980,12 +982,20 @@ int pbk_shard_pack_device(pbk_ctx *c, void *d_records, uint64_t capacity_records
     return PBK_OK;
 }
 
+static int insert_records_device(pbk_ctx *c, const void *d_records, uint64_t n_records);
+
 int pbk_shard_insert_device(pbk_ctx *c, const void *d_records, uint64_t n_records)
 {
     if (!c) return PBK_E_ARG;
     if (n_records == 0) return PBK_OK;
     if (!d_records) return PBK_E_ARG;
     if (c->finalized) return fail(c, PBK_E_STATE, "insert after finalize");
+    return insert_records_device(c, d_records, n_records);
+}
+
+// weighted inserts of (key words, count) records that this context owns
+static int insert_records_device(pbk_ctx *c, const void *d_records, uint64_t n_records)
+{
     CK(cudaSetDevice(c->device));
     TRY(ensure_tables(c, n_records, false));
     const ShardInfo local{1, 0};                      // received records are owned by this shard
@@ -1005,6 +1015,146 @@ int pbk_shard_insert_device(pbk_ctx *c, const void *d_records, uint64_t n_record
         TRY(drain_overflow(c));
     }
     return PBK_OK;
+}
+
+// ---- consumers of the table: bulk load and occurrence lookup ---------------------------------------
+
+int pbk_load_entries(pbk_ctx *c, const uint64_t *keys, const uint16_t *counts, uint64_t n)
+{
+    if (!c) return PBK_E_ARG;
+    if (n == 0) return PBK_OK;
+    if (!keys || !counts) return fail(c, PBK_E_ARG, "NULL entries");
+    if (c->finalized) return fail(c, PBK_E_STATE, "pbk_load_entries after pbk_finalize (call pbk_reset first)");
+    CK(cudaSetDevice(c->device));
+    const int W = c->W;
+    const u64 PIECE = 1ull << 22;                                    // records per upload
+    std::vector<u64> rec;
+    u64 *d_rec = nullptr;
+    const size_t bytes = (size_t)std::min<u64>(n, PIECE) * (W + 1) * 8;
+    TRY(dev_alloc(c, (void **)&d_rec, bytes));
+    int rc = PBK_OK;
+    for (u64 at = 0; at < n && rc == PBK_OK; at += PIECE) {
+        const u64 m = std::min<u64>(PIECE, n - at);
+        rec.clear();
+        rec.reserve((size_t)m * (W + 1));
+        for (u64 i = at; i < at + m; ++i) {
+            if (counts[i] == 0) continue;                            // an empty slot of the reference table
+            if (c->shard.n_shards > 1 && pbk_shard_of_key(keys + i * W, c->k, c->shard.n_shards) != c->shard.rank) continue;
+            for (int j = 0; j < W; ++j) rec.push_back(keys[i * W + j]);
+            rec.push_back(counts[i]);
+        }
+        const u64 kept = rec.size() / (W + 1);
+        if (kept == 0) continue;
+        if (cudaMemcpyAsync(d_rec, rec.data(), rec.size() * 8, cudaMemcpyHostToDevice, c->s_compute) != cudaSuccess ||
+            cudaStreamSynchronize(c->s_compute) != cudaSuccess) { rc = fail(c, PBK_E_CUDA, "upload of table entries failed"); break; }
+        c->h2d_bytes += rec.size() * 8;
+        rc = insert_records_device(c, d_rec, kept);
+    }
+    cudaStreamSynchronize(c->s_compute);
+    dev_free(c, d_rec, bytes);
+    return rc;
+}
+
+static int lookup_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, const u64 *h_offsets,
+                         const u64 *d_offsets_in, u64 n_reads, u64 n_bases, int encoding, const int32_t *n_pos,
+                         const u64 *n_pos_offsets, uint16_t *h_out, uint16_t *d_out)
+{
+    CK(cudaSetDevice(c->device));
+    if (n_bases > MAX_PUSH_BASES) return fail(c, PBK_E_ARG, "pbk_lookup takes at most %llu bases per call", (unsigned long long)MAX_PUSH_BASES);
+    if (h_out) memset(h_out, 0, n_bases * 2);
+    else CK(cudaMemsetAsync(d_out, 0, n_bases * 2, c->s_compute));
+    if (!c->table.slots || n_bases < c->k) { CK(cudaStreamSynchronize(c->s_compute)); return PBK_OK; }
+    TRY(ensure_batch_buffers(c, n_bases, n_reads));
+    if (!c->d_len_scratch) {
+        TRY(dev_alloc(c, (void **)&c->d_len_scratch, PBK_LEN_BINS * 8));
+        TRY(dev_alloc(c, (void **)&c->d_ctr_scratch, sizeof(Counters)));
+    }
+    CK(cudaMemsetAsync(c->d_ctr_scratch, 0, sizeof(Counters), c->s_compute));
+    u64 *stream = c->d_stream_raw + STREAM_PAD_WORDS;
+    u32 *nflag = c->d_nflag_raw + STREAM_PAD_WORDS, *rflag = c->d_rflag_raw + STREAM_PAD_WORDS;
+    const u64 words = (n_bases + 31) / 32;
+    const u64 *d_off = d_offsets_in;
+    if (!d_off) {
+        CK(cudaMemcpyAsync(c->d_offsets, h_offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->s_compute));
+        c->h2d_bytes += (n_reads + 1) * 8;
+        d_off = c->d_offsets;
+    }
+    CK(cudaMemsetAsync(rflag, 0, words * 4, c->s_compute));
+    { Span sp(c, LC_OTHER); launch_read_marks(d_off, n_reads, c->d_len_scratch, rflag, c->d_ctr_scratch, c->s_compute); }
+    CK(cudaGetLastError());
+    uint8_t *d_tmp_stage = nullptr;
+    if (!d_bases_in) TRY(dev_alloc(c, (void **)&d_tmp_stage, CHUNK_BASES));
+    uint16_t *d_occ = nullptr;
+    int32_t *d_np = nullptr; u64 *d_npo = nullptr;
+    const u64 total_n = (encoding == PBK_ENC_PLATANUS && n_pos_offsets) ? n_pos_offsets[n_reads] : 0;
+    int rc = dev_alloc(c, (void **)&d_occ, words * 64);
+    for (u64 b0 = 0; b0 < n_bases && rc == PBK_OK; b0 += CHUNK_BASES) {
+        const u64 nb = std::min(CHUNK_BASES, n_bases - b0), w0 = b0 / 32, nw = (nb + 31) / 32;
+        const uint8_t *src = d_bases_in ? d_bases_in + b0 : d_tmp_stage;
+        if (!d_bases_in) {
+            if (cudaMemcpyAsync(d_tmp_stage, h_bases + b0, nb, cudaMemcpyHostToDevice, c->s_compute) != cudaSuccess) rc = fail(c, PBK_E_CUDA, "H2D copy failed");
+            c->h2d_bytes += nb;
+        }
+        { Span sp(c, LC_PACK); launch_pack(src, nb, nw, encoding, stream, nflag, w0, c->d_ctr_scratch, c->s_compute); }
+    }
+    if (rc == PBK_OK && encoding == PBK_ENC_PLATANUS) {
+        if (!n_pos || !n_pos_offsets) rc = fail(c, PBK_E_ARG, "PBK_ENC_PLATANUS needs n_pos and n_pos_offsets");
+        if (rc == PBK_OK) rc = dev_alloc(c, (void **)&d_np, total_n * 4);
+        if (rc == PBK_OK) rc = dev_alloc(c, (void **)&d_npo, (n_reads + 1) * 8);
+        if (rc == PBK_OK) {
+            cudaMemcpyAsync(d_np, n_pos, total_n * 4, cudaMemcpyHostToDevice, c->s_compute);
+            cudaMemcpyAsync(d_npo, n_pos_offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->s_compute);
+            c->h2d_bytes += total_n * 4 + (n_reads + 1) * 8;
+            Span sp(c, LC_OTHER);
+            launch_npos_scatter(d_off, d_np, d_npo, n_reads, nflag, c->s_compute);
+        }
+    }
+    if (rc == PBK_OK) {
+        { Span sp(c, LC_OTHER); launch_lookup(stream, nflag, rflag, 0, words, (int)c->k, c->table, d_occ, c->sm_count, c->s_compute); }
+        // the kernel indexes by the window's END; the caller gets the window's START: shift by k - 1
+        const u64 n_starts = n_bases - (c->k - 1);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess)
+            e = h_out ? cudaMemcpyAsync(h_out, d_occ + (c->k - 1), n_starts * 2, cudaMemcpyDeviceToHost, c->s_compute)
+                      : cudaMemcpyAsync(d_out, d_occ + (c->k - 1), n_starts * 2, cudaMemcpyDeviceToDevice, c->s_compute);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_ctr, c->d_ctr_scratch, sizeof(Counters), cudaMemcpyDeviceToHost, c->s_compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_compute);
+        if (h_out) c->d2h_bytes += n_starts * 2;
+        if (e != cudaSuccess) rc = fail(c, PBK_E_CUDA, "lookup: %s", cudaGetErrorString(e));
+        else {
+            const u32 flags = c->h_ctr->error_flags;
+            *c->h_ctr = c->last;                                      // h_ctr mirrors the counting counters between calls
+            if (flags & ERR_READ_TOO_LONG) rc = fail(c, PBK_E_READ_TOO_LONG, "a read has >= 500000 bases");
+            else if (flags & ERR_BAD_BASE) rc = fail(c, PBK_E_BAD_BASE, "input contains a character with no Char2Bin code (only ACGTN, any case)");
+        }
+    }
+    cudaStreamSynchronize(c->s_compute);
+    dev_free(c, d_occ, words * 64); dev_free(c, d_tmp_stage, CHUNK_BASES);
+    dev_free(c, d_np, total_n * 4); dev_free(c, d_npo, (n_reads + 1) * 8);
+    return rc;
+}
+
+int pbk_lookup(pbk_ctx *c, const uint8_t *bases, const uint64_t *read_offsets, uint64_t n_reads, int encoding,
+               const int32_t *n_pos, const uint64_t *n_pos_offsets, uint16_t *occ_out)
+{
+    if (!c) return PBK_E_ARG;
+    if (n_reads == 0) return PBK_OK;
+    if (!read_offsets || !occ_out || (encoding != PBK_ENC_ASCII && encoding != PBK_ENC_PLATANUS)) return fail(c, PBK_E_ARG, "bad arguments");
+    if (read_offsets[0] != 0) return fail(c, PBK_E_ARG, "read_offsets[0] must be 0");
+    const u64 n_bases = read_offsets[n_reads];
+    if (n_bases && !bases) return fail(c, PBK_E_ARG, "bases is NULL");
+    if (n_bases == 0) return PBK_OK;
+    return lookup_common(c, bases, nullptr, (const u64 *)read_offsets, nullptr, n_reads, n_bases, encoding, n_pos,
+                         (const u64 *)n_pos_offsets, occ_out, nullptr);
+}
+
+int pbk_lookup_device(pbk_ctx *c, const void *d_bases, const void *d_read_offsets, uint64_t n_reads, uint64_t n_bases, void *d_occ_out)
+{
+    if (!c) return PBK_E_ARG;
+    if (n_reads == 0 || n_bases == 0) return PBK_OK;
+    if (!d_bases || !d_read_offsets || !d_occ_out) return fail(c, PBK_E_ARG, "NULL device pointer");
+    return lookup_common(c, nullptr, (const uint8_t *)d_bases, nullptr, (const u64 *)d_read_offsets, n_reads, n_bases,
+                         PBK_ENC_ASCII, nullptr, nullptr, nullptr, (uint16_t *)d_occ_out);
 }
 
 // ---- key exchange (k <= 32) ----------------------------------------------------------------------

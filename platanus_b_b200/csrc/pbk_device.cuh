@@ -327,6 +327,26 @@ __device__ __forceinline__ int ct_insert_weighted(u64 *tab, const CtGeom &g, u64
     return -1;
 }
 
+// Read-only lookup (no insert kernel running): clamped count of the key with hash h, 0 if it is not in the table.
+// A key sits in the first slot of its probe sequence that was free when it arrived and nothing is ever removed, so
+// the search ends at the first empty slot.
+__device__ __forceinline__ u32 ct_lookup(const u64 *tab, const CtGeom &g, u64 h)
+{
+    const u64 home = h >> g.rbits;
+    const u64 r_hi = ((h << (64 - g.rbits)) >> (64 - g.rbits)) << CT_DISP_BITS;
+#pragma unroll 1
+    for (u32 d = 0; d <= (u32)CT_MAX_DISP; ++d) {
+        const u64 v = ld_cg_u64(tab + ((home + d) & g.capmask));
+        const u64 hi = v >> g.cbits;
+        if (hi == 0) return 0;
+        if (hi == (r_hi | (u64)(d + 1))) {
+            const u64 c = v & g.cmask;
+            return c > COUNT_SAT ? COUNT_SAT : (u32)c;
+        }
+    }
+    return 0;
+}
+
 // -------------------------------------------------------------------------------------------------
 // generic table, k > 32
 // -------------------------------------------------------------------------------------------------
@@ -371,6 +391,24 @@ __device__ __forceinline__ int wide_insert(Slot<W> *table, u64 cap, const u64 *k
     return -1;
 }
 
+template <int W>
+__device__ __forceinline__ u32 wide_lookup(const Slot<W> *table, u64 cap, const u64 *key, u64 h)
+{
+    u64 idx = __umul64hi(h, cap);
+#pragma unroll 1
+    for (int probe = 0; probe < MAX_PROBE; ++probe) {
+        const Slot<W> *s = table + idx;
+        const u32 cs = ld_cg_u32(&s->cs);
+        if (cs == 0) return 0;
+        bool eq = true;
+#pragma unroll
+        for (int j = 0; j < W; ++j) eq &= (ld_cg_u64(&s->key[j]) == key[j]);
+        if (eq) return cs > COUNT_SAT ? COUNT_SAT : cs;
+        idx = (idx + 1 == cap) ? 0 : idx + 1;
+    }
+    return 0;
+}
+
 // -------------------------------------------------------------------------------------------------
 // uniform view used by every kernel: Table<W> wraps either format
 // -------------------------------------------------------------------------------------------------
@@ -394,6 +432,12 @@ struct Table {
         } else {
             return wide_insert<W>(slots, cap, key, h, w > COUNT_SAT ? COUNT_SAT : w);
         }
+    }
+    // clamped count of `key` (hash h), 0 if absent; only between insert kernels
+    __device__ __forceinline__ u32 find(const u64 *key, u64 h) const
+    {
+        if constexpr (W == 1) return ct_lookup(slots, g, h);
+        else return wide_lookup<W>(slots, cap, key, h);
     }
     // read slot i once all inserts have drained: false if empty
     __device__ __forceinline__ bool load(u64 i, u64 *key, u32 *count) const

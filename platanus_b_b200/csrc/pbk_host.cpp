@@ -7,12 +7,14 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <utility>
 #include <vector>
 
 #include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 namespace {
@@ -201,5 +203,59 @@ int pbk_write_kmer_occ_bin(const char *path, uint32_t k, const uint64_t *keys, c
     ok = (close(fd) == 0) && ok;
     return ok ? PBK_OK : PBK_E_IO;
 }
+
+// Counter::readOccurrenceTableBinary (counter.h:967-993) + DoubleHash::readTable / readKey (doubleHash.h:280-293,
+// 83-91): the (key, count) entries of a PREFIX_kmer_occ.bin.  The reference drops every record into the slot the file
+// names; here the entries are handed back as arrays (keys: n x ceil(k/32) words, word 0 first) and the caller's own
+// table decides where they live (pbk_load_entries).  The arrays are malloc'ed; release them with pbk_free.
+int pbk_read_kmer_occ_bin(const char *path, uint32_t *k_out, uint64_t *index_size_out, uint64_t **keys_out,
+                          uint16_t **counts_out, uint64_t *n_out)
+{
+    if (!path || !k_out || !keys_out || !counts_out || !n_out) return PBK_E_ARG;
+    *keys_out = NULL; *counts_out = NULL; *n_out = 0;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return PBK_E_IO;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 16) { close(fd); return PBK_E_IO; }
+    unsigned char header[16];
+    if (pread(fd, header, 16, 0) != 16) { close(fd); return PBK_E_IO; }
+    u64 k64, index_size;
+    memcpy(&k64, header, 8);                                             // counter.h:972
+    memcpy(&index_size, header + 8, 8);                                  // doubleHash.h:283
+    if (k64 == 0 || k64 > PBK_MAX_K) { close(fd); return PBK_E_UNSUPPORTED_K; }
+    const uint32_t k = (uint32_t)k64;
+    const unsigned words = (k + 31) / 32;
+    const u64 raw = key_raw_size(k);
+    const size_t rec = 8 + raw + (k > 160 ? 8 * words : 0) + 2, key_at = k <= 32 ? 8 : 8 + 24;
+    const u64 body = (u64)st.st_size - 16;
+    if (body % rec != 0) { close(fd); return PBK_E_IO; }                 // truncated file
+    const u64 n = body / rec;
+    uint64_t *keys = (uint64_t *)malloc(std::max<size_t>(8, (size_t)n * words * 8));
+    uint16_t *counts = (uint16_t *)malloc(std::max<size_t>(8, (size_t)n * 2));
+    if (!keys || !counts) { free(keys); free(counts); close(fd); return PBK_E_NOMEM; }
+    const size_t CH = 65536;
+    std::vector<unsigned char> buf(rec * CH);
+    bool ok = true;
+    for (u64 i0 = 0; i0 < n && ok; i0 += CH) {
+        const size_t m = (size_t)std::min<u64>(CH, n - i0);
+        ok = pread(fd, buf.data(), rec * m, (off_t)(16 + rec * i0)) == (ssize_t)(rec * m);
+        for (size_t j = 0; j < m && ok; ++j) {
+            const unsigned char *p = &buf[rec * j];
+            u64 slot;
+            memcpy(&slot, p, 8);
+            if (slot > index_size) ok = false;                           // not a slot of this table
+            memcpy(keys + (i0 + j) * words, p + key_at, 8 * words);
+            memcpy(counts + (i0 + j), p + rec - 2, 2);
+        }
+    }
+    close(fd);
+    if (!ok) { free(keys); free(counts); return PBK_E_IO; }
+    *k_out = k;
+    if (index_size_out) *index_size_out = index_size;
+    *keys_out = keys; *counts_out = counts; *n_out = n;
+    return PBK_OK;
+}
+
+void pbk_free(void *p) { free(p); }
 
 }  // extern "C"

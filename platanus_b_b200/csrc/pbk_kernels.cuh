@@ -35,6 +35,10 @@ void launch_npos_scatter(const u64 *offsets, const int32_t *n_pos, const u64 *n_
 void launch_count(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
                   TableView table, TableView remote, ShardInfo shard, Counters *ctr,
                   u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st);
+// occ[p] (u16, one per stream position of words [word_begin, word_end); 8-byte aligned) = clamped count of the window
+// that ENDS at p, 0 if unusable or absent.  Read-only on the table.
+void launch_lookup(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
+                   TableView table, uint16_t *occ, int sm_count, cudaStream_t st);
 // insert n (key words..., weight) records; a record has W + 1 words when weighted, W otherwise.
 // Overflow-list records always have W + 1 words.
 void launch_insert_records(const u64 *records, u64 n, bool weighted, TableView table, TableView remote,

@@ -240,6 +240,74 @@ count_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, cons
     }
 }
 
+// Occurrence lookup (ContigDivider::getOccurrenceArray, kmer_divide.cpp:151-197; the table probe of
+// divideKmerUsedMakingPreviousContig, counter.h:828-861): same window enumeration as count_kernel, but the canonical key
+// is only looked up.  occ[p] = clamped count of the window that ENDS at stream position p, 0 if the window is not usable
+// (contains an N, crosses a read start) or its k-mer is not in the table.  A thread writes its 32 results as eight
+// 8-byte words.
+template <int W>
+__global__ void __launch_bounds__(256)
+lookup_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, const u32 *__restrict__ rflag,
+              u64 word_begin, u64 word_end, int k, Table<W> table, u64 *__restrict__ occ4)
+{
+    const int top_shift = 2 * ((k - 1) & 31);
+    const u64 top_mask = (k & 31) ? ((1ull << (2 * (k & 31))) - 1ull) : ~0ull;
+    const int s = 2 * (32 * W - k);
+    const int nb = (k + 30) >> 5;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 wi = word_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; wi < word_end; wi += stride) {
+        const u64 cur = stream[wi];
+        const u32 nf = nflag[wi], rf = rflag[wi];
+        int run = k;
+        for (int j = 1; j <= nb; ++j) {
+            const u32 a = nflag[wi - j], b = rflag[wi - j];
+            if (a | b) {
+                const int pn = a ? 32 - __clz(a) : 0;
+                const int pr = b ? 31 - __clz(b) : 0;
+                run = 32 * j - max(pn, pr);
+                break;
+            }
+        }
+        u64 fwd[W], rev[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) fwd[j] = stream[wi - 1 - j];
+        {
+            u64 y[W + 1];
+#pragma unroll
+            for (int j = 0; j < W; ++j) y[j] = pair_reverse64(~fwd[W - 1 - j]);
+            y[W] = 0;
+#pragma unroll
+            for (int j = 0; j < W; ++j) rev[j] = s ? ((y[j] >> s) | (y[j + 1] << (64 - s))) : y[j];
+        }
+#pragma unroll 1
+        for (int g = 0; g < 8; ++g) {
+            u64 packed = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = 4 * g + q;
+                const u32 b = (u32)(cur >> (62 - 2 * i)) & 3u;
+                if ((rf >> i) & 1u) run = 0;
+                run = ((nf >> i) & 1u) ? 0 : run + 1;
+#pragma unroll
+                for (int j = W - 1; j > 0; --j) fwd[j] = (fwd[j] << 2) | (fwd[j - 1] >> 62);
+                fwd[0] = (fwd[0] << 2) | b;
+                fwd[W - 1] &= top_mask;
+#pragma unroll
+                for (int j = 0; j < W - 1; ++j) rev[j] = (rev[j] >> 2) | (rev[j + 1] << 62);
+                rev[W - 1] = (rev[W - 1] >> 2) | ((u64)(3u - b) << top_shift);
+                if (run >= k) {
+                    const bool use_rev = key_less<W>(rev, fwd);
+                    u64 key[W];
+#pragma unroll
+                    for (int j = 0; j < W; ++j) key[j] = use_rev ? rev[j] : fwd[j];
+                    packed |= (u64)table.find(key, hash_key<W>(key)) << (16 * q);
+                }
+            }
+            occ4[wi * 8 + g] = packed;
+        }
+    }
+}
+
 template <int W>
 __global__ void __launch_bounds__(256)
 insert_records_kernel(const u64 *__restrict__ rec, u64 n, int weighted, Table<W> table, Table<W> remote,

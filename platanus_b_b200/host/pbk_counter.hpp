@@ -143,6 +143,33 @@ public:
         return endCounting(memory);
     }
 
+    // ---- counter.h:967-993: PREFIX_kmer_occ.bin -> table (device resident), occurrenceDistribution, maxOccurrence ------
+    void readOccurrenceTableBinary(const std::string &filename)
+    {
+        uint32_t k = 0;
+        uint64_t indexSize = 0, n = 0, *keys = NULL;
+        uint16_t *counts = NULL;
+        const int rc = pbk_read_kmer_occ_bin(filename.c_str(), &k, &indexSize, &keys, &counts, &n);
+        if (rc != PBK_OK) throw FILEError(filename);
+        struct Release { uint64_t *k; uint16_t *c; ~Release() { pbk_free(k); pbk_free(c); } } release = {keys, counts};
+        beginCounting(k);                                            // counter.h:972: kmerLength comes from the file
+        check(pbk_load_entries(ctx_, keys, counts, n), "pbk_load_entries");
+        occurrenceDistribution_.assign(PBK_OCC_BINS, 0);
+        uint64_t nd = 0, ni = 0, mx = 0;
+        check(pbk_finalize(ctx_, (uint64_t *)occurrenceDistribution_.data(), NULL, &nd, &ni, &mx), "pbk_finalize");
+        nDistinct_ = nd; nInstances_ = ni;
+        if (nd) maxOccurrence_ = mx;
+        doubleHashSize_ = indexSize + 1;
+    }
+
+    // ---- ContigDivider::getOccurrenceArray (kmer_divide.cpp:151-197), which calls Counter::findValue once per window:
+    //      the whole array in one device pass.  ASCII sequences, concatenated; occ[offsets[r] + i] = occurrence of the
+    //      k-mer starting at base i of sequence r (0: absent, contains N, or no window starts there).
+    void occurrenceArray(const uint8_t *bases, const uint64_t *offsets, uint64_t n, uint16_t *occ)
+    {
+        check(pbk_lookup(ctx_, bases, offsets, n, PBK_ENC_ASCII, NULL, NULL, occ), "pbk_lookup");
+    }
+
     // ---- counter.h:1000-1007 ----------------------------------------------------------------------
     void outputOccurrenceDistribution(const std::string &filename)
     {

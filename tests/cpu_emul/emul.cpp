@@ -213,3 +213,44 @@ extern "C" int emul_keyx_insert(const u64 *recv, const u64 *recv_cursors, u32 n_
     export_kernel<1>(t, 1, keys_out, counts_out, cap_out, n_out);
     return ctr.overflow_n ? -2 : 0;
 }
+
+// ---- occurrence lookup (pbk_lookup) -----------------------------------------------------------------------------------
+template <int W>
+static int run_lookup(const uint8_t *bases, const u64 *off, u64 n_reads, int k, const u64 *keys, const uint16_t *counts,
+                      u64 n, uint16_t *out)
+{
+    const u64 n_bases = off[n_reads], words = (n_bases + 31) / 32;
+    std::vector<u64> stream(words + STREAM_PAD_WORDS + 1, 0), len_hist(500001, 0);
+    std::vector<u32> nflag(words + STREAM_PAD_WORDS + 1, 0), rflag(words + STREAM_PAD_WORDS + 1, 0);
+    Counters ctr{};
+    typedef typename SlotType<W>::type slot_t;
+    const u64 slots = W == 1 ? (1ull << 24) : 2 * n + 1024;
+    std::vector<slot_t> tv(slots);
+    memset(tv.data(), 0, tv.size() * sizeof(slot_t));
+    Table<W> table(tv.data(), tv.size());
+    std::vector<u64> rec(n * (W + 1) + 1), ovf(16 * (W + 1));
+    for (u64 i = 0; i < n; ++i) {
+        for (int j = 0; j < W; ++j) rec[i * (W + 1) + j] = keys[i * W + j];
+        rec[i * (W + 1) + W] = counts[i];
+    }
+    insert_records_kernel<W>(rec.data(), n, 1, table, table, 1, 0, &ctr, ovf.data(), 16);
+    if (ctr.overflow_n) return -2;
+    read_marks_kernel(off, n_reads, len_hist.data(), rflag.data() + STREAM_PAD_WORDS, &ctr);
+    pack_kernel<false>(bases, n_bases, words, 0, stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, 0, &ctr);
+    std::vector<u64> occ4(words * 8 + 1, 0);
+    const u64 w_split = words / 2;                     // two launches, like chunks of a larger batch
+    lookup_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS, 0, w_split, k, table, occ4.data());
+    lookup_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS, w_split, words, k, table, occ4.data());
+    const uint16_t *by_end = (const uint16_t *)occ4.data();
+    for (u64 i = 0; i < n_bases; ++i) out[i] = 0;
+    if (n_bases >= (u64)k)
+        for (u64 i = 0; i + k - 1 < n_bases; ++i) out[i] = by_end[i + k - 1];     // window END -> window START, as pbk_lookup does
+    return (ctr.error_flags & ERR_BAD_BASE) ? -3 : 0;
+}
+
+extern "C" int emul_lookup(const uint8_t *bases, const u64 *off, u64 n_reads, int k, const u64 *keys, const uint16_t *counts,
+                           u64 n, uint16_t *out)
+{
+#define LK(Wv) case Wv: return run_lookup<Wv>(bases, off, n_reads, k, keys, counts, n, out);
+    switch ((k + 31) / 32) { LK(1) LK(2) LK(3) LK(4) LK(5) LK(6) LK(7) LK(8) default: return -1; }
+}

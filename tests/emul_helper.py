@@ -122,3 +122,16 @@ def emul_keyx_insert(recv: np.ndarray, recv_cursors: np.ndarray, seg_cap: int, k
     keys, counts = keys[:m], counts[:m]
     order = np.argsort(keys[:, 0], kind="stable")
     return keys[order], counts[order]
+
+
+def emul_lookup(bases: np.ndarray, offsets: np.ndarray, k: int, keys: np.ndarray, counts: np.ndarray) -> np.ndarray:
+    """lookup_kernel over a table built from (keys, counts): u16 per base, indexed by window start (pbk_lookup's output)."""
+    bases = np.concatenate([np.ascontiguousarray(bases, dtype=np.uint8), np.zeros(64, np.uint8)])
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    counts = np.ascontiguousarray(counts, dtype=np.uint16)
+    out = np.zeros(int(offsets[-1]) + 1, np.uint16)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().emul_lookup(p(bases), p(offsets), C.c_uint64(len(offsets) - 1), k, p(keys), p(counts), C.c_uint64(len(counts)), p(out))
+    assert rc == 0, rc
+    return out[:int(offsets[-1])]

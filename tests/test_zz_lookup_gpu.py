@@ -1,0 +1,81 @@
+"""Occurrence lookup on the B200 through the C ABI (pbk_lookup, pbk_load_entries, pbk_read_kmer_occ_bin; SURVEY.md
+section 8f rows 1-2) against the reference's own getOccurrenceArray output (tests/golden/occ_k*.npz) and the oracle.
+Written after round 1's GPU budget was spent: NOT yet run on a B200 (the kernel's logic is covered on CPU by
+tests/test_lookup_cpu.py through the host emulation); the file sorts last so that it cannot mask other results."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import golden_cases as G
+from platanus_b_b200 import KmerCounter, synth
+from test_lookup_cpu import CASES, contig_reads, expected_per_base
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("path", CASES, ids=lambda p: os.path.basename(p)[:-4])
+def test_lookup_matches_the_reference_occurrence_arrays(oracle, path):
+    O = oracle
+    g = np.load(path, allow_pickle=False)
+    k = int(g["k"])
+    rd, seqs = contig_reads(O, g)
+    bases, offs = rd.arrays()
+    with KmerCounter(k) as kc:
+        kc.load_entries(g["keys"], g["counts"])
+        got = kc.lookup(bases, offs)
+        assert np.array_equal(got, expected_per_base(g, seqs, k))
+        kc.finalize()                                               # the loaded table is an ordinary table
+        keys, counts = kc.export(1, sorted=True)
+        assert np.array_equal(keys, g["keys"]) and np.array_equal(counts, g["counts"])
+        assert kc.stats()["n_instances"] == 0                       # lookups and loads are not counted reads
+
+
+@pytest.mark.parametrize("k", [32, 75])
+def test_lookup_of_the_counted_reads(oracle, k):
+    O = oracle
+    rs = synth.make_reads(synth.config("C1", scale=1 / 100))
+    b, o = rs.flat()
+    rd = O.Reads()
+    rd.add_array(b, o)
+    want = O.count(rd, k)
+    ref = O.occurrence_array(rd, k, want.keys, want.counts)
+    with KmerCounter(k) as kc:
+        kc.push_reads(b, o)
+        got = kc.lookup(b, o)                                        # no finalize needed: the table is quiescent between calls
+        assert np.array_equal(got, ref)
+        assert int((got > 0).sum()) == want.n_instances
+        kc.finalize()
+        assert kc.n_instances == want.n_instances
+        assert np.array_equal(kc.len_hist, want.len_hist)           # the lookup's reads did not enter the histograms
+        # foreign sequence: nothing found; bad character: flagged like pbk_push_reads
+        rng = np.random.default_rng(5)
+        junk = np.frombuffer(bytes(rng.choice(list(b"ACGT"), 4000).astype(np.uint8)), dtype=np.uint8)
+        assert int(kc.lookup(junk, np.array([0, len(junk)], np.uint64)).sum()) == 0
+        bad = junk.copy(); bad[100] = ord("R")
+        with pytest.raises(Exception):
+            kc.lookup(bad, np.array([0, len(bad)], np.uint64))
+
+
+def test_read_occurrence_table_binary_then_lookup(oracle, tmp_path):
+    """Counter::readOccurrenceTableBinary (counter.h:967-993): a kmer_occ.bin written by our writer (verified against the
+    reference's reader elsewhere) loaded into a fresh counter of another k."""
+    O = oracle
+    from platanus_b_b200 import capi
+    L = capi.load_library()
+    k = 75
+    rd = O.Reads()
+    rd.add_file(os.path.join(G.INPUTS, "cov.fq"))
+    want = O.count(rd, k)
+    keep = want.counts >= 2
+    path = str(tmp_path / "t_kmer_occ.bin")
+    assert L.pbk_write_kmer_occ_bin(path.encode(), k, np.ascontiguousarray(want.keys[keep]).ctypes.data_as(C.c_void_p),
+                                    np.ascontiguousarray(want.counts[keep]).ctypes.data_as(C.c_void_p), int(keep.sum()),
+                                    O.double_hash_size(10 ** 9, k), None) == 0
+    bases, offs = rd.arrays()
+    with KmerCounter(32) as kc:
+        assert kc.read_occurrence_table_binary(path) == int(keep.sum())
+        assert kc.k == k
+        got = kc.lookup(bases, offs)
+        assert np.array_equal(got, O.occurrence_array(rd, k, want.keys[keep], want.counts[keep]))
