@@ -229,6 +229,17 @@ int  pbk_lookup(pbk_ctx *ctx, const uint8_t *bases, const uint64_t *read_offsets
 /* same with inputs and output in device memory (d_occ_out: n_bases u16, 8-byte aligned)              */
 int  pbk_lookup_device(pbk_ctx *ctx, const void *d_bases, const void *d_read_offsets, uint64_t n_reads,
                        uint64_t n_bases, void *d_occ_out);
+/* Counter::pickupReadMatchedEdgeKmer (counter.h:870-910): matched_out[r] = 1 if a usable k-mer window
+ * of read r (no N) is in the table, else 0 -- the reads the next assembly round keeps.               */
+int  pbk_match_reads(pbk_ctx *ctx, const uint8_t *bases, const uint64_t *read_offsets, uint64_t n_reads,
+                     int encoding, const int32_t *n_pos, const uint64_t *n_pos_offsets, uint8_t *matched_out);
+/* Counter::makeKmerReadDistributionConsideringPreviousGraph (counter.h:663-750): the k-mers given here
+ * (the table Assemble::saveAndRedoAssemble seeds from the previous round's contigs, assemble.cpp:393-404)
+ * keep their value: read windows that hit them are not counted (divideKmerUsedMakingPreviousContig,
+ * counter.h:828-861) and every other k-mer of the reads is counted as usual.  Call before pbk_finalize,
+ * in any order with pbk_push_reads; entries with value 0 are ignored (counter.h:700); pbk_reset
+ * forgets them.                                                                                     */
+int  pbk_seed_entries(pbk_ctx *ctx, const uint64_t *keys, const uint16_t *counts, uint64_t n);
 /* Add n (key, count) entries to the table (host arrays; keys n x ceil(k/32) words, word 0 first):
  * what Counter::readOccurrenceTableBinary leaves in memory, or a contig-seeded table
  * (makeKmerReadDistributionFromContig, counter.h:511-593).  Counts of equal keys add up, saturating. */

@@ -258,7 +258,29 @@ void pbo_result_release(pbo_result *res)
     res->keys = NULL; res->counts = NULL; res->len_hist = NULL;
 }
 
+static uint16_t table_find(const uint64_t *keys, const uint16_t *counts, uint64_t n, unsigned words, const uint64_t *key);
+
+/* seeds == NULL: Counter::makeKmerReadDistributionMT.  With seeds (sorted (key, value) dump of the table the counter
+ * holds when it is called): Counter::makeKmerReadDistributionConsideringPreviousGraph (counter.h:663-750) -- a window
+ * whose k-mer has a non-zero value in the table is not counted (divideKmerUsedMakingPreviousContig, counter.h:828-861:
+ * `find_any(key)->second == 0` is the test for "not in the contigs"), the table's own entries are written with their
+ * values (counter.h:695-705), everything else is counted as in the first pass (countKmerPerThreadSecond). */
+static int count_impl(const pbo_reads *r, unsigned k, const uint64_t *seed_keys, const uint16_t *seed_counts,
+                      uint64_t n_seed, pbo_result *res);
+
 int pbo_count(const pbo_reads *r, unsigned k, pbo_result *res)
+{
+    return count_impl(r, k, NULL, NULL, 0, res);
+}
+
+int pbo_count_seeded(const pbo_reads *r, unsigned k, const uint64_t *seed_keys, const uint16_t *seed_counts,
+                     uint64_t n_seed, pbo_result *res)
+{
+    return count_impl(r, k, seed_keys, seed_counts, n_seed, res);
+}
+
+static int count_impl(const pbo_reads *r, unsigned k, const uint64_t *seed_keys, const uint16_t *seed_counts,
+                      uint64_t n_seed, pbo_result *res)
 {
     if (k == 0) return PBO_E_ARG;
     unsigned words = (k + 31) / 32;
@@ -321,6 +343,7 @@ int pbo_count(const pbo_reads *r, unsigned k, pbo_result *res)
                 continue;
             }
             const uint64_t *key = pbo_key_cmp(fwd, rev, words) <= 0 ? fwd : rev;   /* std::min */
+            if (seed_keys && table_find(seed_keys, seed_counts, n_seed, words, key) != 0) continue;   /* counter.h:853 */
             memcpy(inst + n_inst * words, key, words * sizeof(uint64_t));
             ++n_inst;
         }
@@ -344,6 +367,33 @@ int pbo_count(const pbo_reads *r, unsigned k, pbo_result *res)
         res->occ_hist[c] += 1;                                  /* counter.h:496 */
         ++nd;
         i = j;
+    }
+    /* the table's own entries, with their values (counter.h:695-705); none of them was counted above */
+    uint64_t n_add = 0;
+    for (uint64_t i = 0; i < n_seed; ++i) n_add += seed_counts[i] != 0;
+    if (n_add) {
+        uint64_t tot = nd + n_add;
+        uint64_t *mk = (uint64_t *)malloc(tot * (words + 1) * sizeof(uint64_t));      /* key words + count, sorted together */
+        if (!mk) { free(inst); free(counts); return PBO_E_NOMEM; }
+        uint64_t m = 0;
+        for (uint64_t i = 0; i < nd; ++i, ++m) { memcpy(mk + m * (words + 1), inst + i * words, words * 8); mk[m * (words + 1) + words] = counts[i]; }
+        for (uint64_t i = 0; i < n_seed; ++i) {
+            if (seed_counts[i] == 0) continue;
+            memcpy(mk + m * (words + 1), seed_keys + i * words, words * 8);
+            mk[m * (words + 1) + words] = seed_counts[i];
+            res->occ_hist[seed_counts[i] < PBO_OCC_BINS ? seed_counts[i] : PBO_OCC_BINS - 1] += 1;   /* counter.h:701 */
+            ++m;
+        }
+        /* sort records by key: pbo_key_cmp looks at the first `words` words only, the count rides along */
+        g_sort_words = words;
+        qsort(mk, tot, (words + 1) * sizeof(uint64_t), sort_cmp);
+        free(inst); free(counts);
+        inst = (uint64_t *)malloc(tot * words * sizeof(uint64_t));
+        counts = (uint16_t *)malloc(tot * sizeof(uint16_t));
+        if (!inst || !counts) { free(mk); free(inst); free(counts); return PBO_E_NOMEM; }
+        for (uint64_t i = 0; i < tot; ++i) { memcpy(inst + i * words, mk + i * (words + 1), words * 8); counts[i] = (uint16_t)mk[i * (words + 1) + words]; }
+        free(mk);
+        nd = tot;
     }
     res->keys = inst; res->counts = counts;
     res->n_distinct = nd; res->n_instances = n_inst;
@@ -369,6 +419,46 @@ static uint16_t table_find(const uint64_t *keys, const uint16_t *counts, uint64_
         if (c < 0) lo = mid + 1; else hi = mid;
     }
     return 0;
+}
+
+/* Counter::pickupReadMatchedEdgeKmer (counter.h:870-910): out[r] = 1 iff read r is kept -- it is at least k long and
+ * one of its windows without an N has a k-mer with a non-zero value in the table.  Reads go through
+ * SEQ::convertFromString like in pbo_count (N positions as a list, counter.h:882-884, 895-899). */
+int pbo_match_reads(const pbo_reads *r, unsigned k, const uint64_t *keys, const uint16_t *counts, uint64_t n, uint8_t *out)
+{
+    if (k == 0) return PBO_E_ARG;
+    unsigned words = (k + 31) / 32;
+    if (words > MAXW) return PBO_E_ARG;
+    uint64_t *fwd = (uint64_t *)calloc(words, sizeof(uint64_t));
+    uint64_t *rev = (uint64_t *)calloc(words, sizeof(uint64_t));
+    if (!fwd || !rev) { free(fwd); free(rev); return PBO_E_NOMEM; }
+    for (uint64_t ri = 0; ri < r->n_reads; ++ri) {
+        const char *s = r->bases + r->offsets[ri];
+        uint64_t len = r->offsets[ri + 1] - r->offsets[ri];
+        out[ri] = 0;
+        if (len < k) continue;                                        /* counter.h:880 */
+        for (unsigned i = 0; i + 1 < k; ++i) {
+            unsigned char b = pbo_char2bin(s[i]);
+            if (b == 4) b = 0;                                        /* the byte under an N is never part of a used window */
+            key_set(fwd, k - i - 2, b);
+            key_set(rev, i + 1, (unsigned char)(0x3 ^ b));
+        }
+        int64_t last_n = -1;
+        for (unsigned i = 0; i + 1 < k; ++i) if (pbo_char2bin(s[i]) == 4) last_n = (int64_t)i;
+        for (uint64_t i = 0; i < len - k + 1; ++i) {
+            unsigned char b = pbo_char2bin(s[i + k - 1]);
+            if (b == 4) { last_n = (int64_t)(i + k - 1); b = 0; }
+            key_shl2(fwd, words, k);
+            key_set(fwd, 0, b);
+            key_shr2(rev, words);
+            key_set(rev, k - 1, (unsigned char)(0x3 ^ b));
+            if (last_n >= (int64_t)i) continue;                       /* the window [i, i + k) holds an N (counter.h:895-899) */
+            const uint64_t *key = pbo_key_cmp(fwd, rev, words) <= 0 ? fwd : rev;
+            if (table_find(keys, counts, n, words, key) > 0) { out[ri] = 1; break; }   /* counter.h:900-903 */
+        }
+    }
+    free(fwd); free(rev);
+    return PBO_OK;
 }
 
 /* ContigDivider::getOccurrenceArray (kmer_divide.cpp:151-197) over sequences loaded the way

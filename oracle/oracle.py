@@ -67,6 +67,8 @@ def lib():
         L.pbo_char2bin.restype = C.c_ubyte
         L.pbo_count.argtypes = [C.POINTER(_Reads), C.c_uint, C.POINTER(_Result)]
         L.pbo_result_release.argtypes = [C.POINTER(_Result)]
+        L.pbo_count_seeded.argtypes = [C.POINTER(_Reads), C.c_uint, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(_Result)]
+        L.pbo_match_reads.argtypes = [C.POINTER(_Reads), C.c_uint, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.pbo_occurrence_array.argtypes = [C.POINTER(_Reads), C.c_uint, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.pbo_left_local_min.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         L.pbo_left_local_min.restype = C.c_uint64
@@ -162,9 +164,16 @@ def char2bin(c: int) -> int:
     return lib().pbo_char2bin(bytes([c & 0xFF]))
 
 
-def count(reads: Reads, k: int) -> CountResult:
+def count(reads: Reads, k: int, seed_keys=None, seed_counts=None) -> CountResult:
+    """makeKmerReadDistributionMT; with seeds (sorted (key, value) dump of the table the counter already holds):
+    makeKmerReadDistributionConsideringPreviousGraph (counter.h:663-750)."""
     res = _Result()
-    rc = lib().pbo_count(reads._p, k, C.byref(res))
+    if seed_keys is None:
+        rc = lib().pbo_count(reads._p, k, C.byref(res))
+    else:
+        sk = np.ascontiguousarray(seed_keys, dtype=np.uint64)
+        sc = np.ascontiguousarray(seed_counts, dtype=np.uint16)
+        rc = lib().pbo_count_seeded(reads._p, k, sk.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p), len(sc), C.byref(res))
     if rc:
         raise OracleError(rc, "pbo_count")
     try:
@@ -191,6 +200,40 @@ def occurrence_array(seqs: Reads, k: int, keys: np.ndarray, counts: np.ndarray) 
     if rc:
         raise OracleError(rc, "pbo_occurrence_array")
     return out
+
+
+def match_reads(reads: Reads, k: int, keys: np.ndarray, counts: np.ndarray) -> np.ndarray:
+    """Counter::pickupReadMatchedEdgeKmer (counter.h:870-910): bool per read."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    counts = np.ascontiguousarray(counts, dtype=np.uint16)
+    out = np.zeros(max(reads.n_reads, 1), np.uint8)
+    rc = lib().pbo_match_reads(reads._p, k, keys.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p), len(counts),
+                               out.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise OracleError(rc, "pbo_match_reads")
+    return out[:reads.n_reads].astype(bool)
+
+
+REF_ITER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "ref_iter_harness")
+
+
+def run_ref_iter(mode: str, bin_path: str, reads, n_threads: int, workdir: str, k: int):
+    """oracle/ref_iter_harness.cpp: the UNMODIFIED reference's pickupReadMatchedEdgeKmer ('pickup' -> list of kept reads)
+    or makeKmerReadDistributionConsideringPreviousGraph ('count' -> sorted keys, counts, maxOccurrence)."""
+    import subprocess
+    rp = os.path.join(workdir, "iter_reads.txt")
+    with open(rp, "w") as fh:
+        fh.write("".join(r + "\n" for r in reads))
+    out = os.path.join(workdir, "iter_out_" + mode)
+    p = subprocess.run([REF_ITER, mode, bin_path, rp, str(n_threads), out], check=True, capture_output=True, text=True, cwd=workdir)
+    if mode == "pickup":
+        return open(out).read().split("\n")[:-1]
+    w = (k + 31) // 32
+    raw = np.fromfile(out, dtype=np.uint8).reshape(-1, 8 * w + 2)
+    keys = np.ascontiguousarray(raw[:, :8 * w]).view(np.uint64).reshape(-1, w)
+    counts = np.ascontiguousarray(raw[:, 8 * w:]).view(np.uint16).reshape(-1)
+    order = np.lexsort(tuple(keys[:, j] for j in range(w)))
+    return keys[order], counts[order], int(p.stdout.split()[-1])
 
 
 REF_OCC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "ref_occ_harness")

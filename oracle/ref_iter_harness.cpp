@@ -1,0 +1,84 @@
+// TEST INFRASTRUCTURE ONLY -- drives the UNMODIFIED reference template Counter<KMER> (counter.h, compiled from the sources
+// where they lie under /root/reference; nothing is copied) through the two table-consuming steps of the iterative-k
+// assembly, which the reference only reaches from inside its graph stages:
+//   pickup : Counter::pickupReadMatchedEdgeKmer (counter.h:870-910)  -- keep the reads with a k-mer in the table
+//   count  : Counter::makeKmerReadDistributionConsideringPreviousGraph (counter.h:663-750) -- table entries keep their
+//            values, k-mers of the reads that are not in the table are counted
+// The table is loaded with the reference's own Counter::readOccurrenceTableBinary from a PREFIX_kmer_occ.bin.
+// Reads: one sequence per line (ACGTN), converted and dealt to NUM_THREAD SEQ temp files the way
+// Assemble::readFastaUncompressed does (assemble.cpp:836-845).
+//   usage: ref_iter_harness pickup|count TABLE.bin READS.txt NUM_THREAD OUT
+//   pickup -> OUT: the surviving reads, one per line, per temp file in order (file 0 first)
+//   count  -> OUT: the raw kmerFP records (key words + u16), then stdout: "maxOccurrence <n>"
+// Built with g++ -fno-access-control (kmerLength etc. are private).
+#include "counter.h"
+
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+template <typename KMER>
+static int run(const std::string &mode, const std::string &bin, const std::string &readsPath, unsigned long long numThread,
+               const std::string &out)
+{
+    Counter<KMER> counter;
+    counter.readOccurrenceTableBinary(bin);
+    const unsigned k = counter.getKmerLength();
+
+    std::vector<FILE *> readFP(numThread);
+    for (unsigned long long i = 0; i < numThread; ++i) readFP[i] = platanus::makeTemporaryFile();
+    {
+        std::ifstream ifs(readsPath.c_str());
+        std::string read;
+        platanus::SEQ seq;
+        unsigned long long i = 0;
+        while (std::getline(ifs, read)) {
+            seq.convertFromString(read);
+            seq.writeTemporaryFile(readFP[i]);
+            i = (i + 1) % numThread;
+        }
+    }
+
+    if (mode == "pickup") {
+        for (unsigned long long i = 0; i < numThread; ++i) counter.pickupReadMatchedEdgeKmer(&readFP[i]);
+        std::ofstream ofs(out.c_str());
+        platanus::SEQ seq;
+        for (unsigned long long i = 0; i < numThread; ++i) {
+            rewind(readFP[i]);
+            while (seq.readTemporaryFile(readFP[i])) {
+                std::string s(seq.length, 'A');
+                for (long j = 0; j < seq.length; ++j) s[j] = "ACGT"[seq.base[j] & 3];
+                for (int j = 0; j < seq.numUnknown; ++j) s[seq.positionUnknown[j]] = 'N';
+                ofs << s << '\n';
+            }
+        }
+        return 0;
+    }
+    counter.makeKmerReadDistributionConsideringPreviousGraph(k, readFP.data(), 1000000000ull, numThread);
+    FILE *fp = counter.kmerFP;
+    fflush(fp);
+    rewind(fp);
+    std::ofstream ofs(out.c_str(), std::ios::binary);
+    char buf[65536];
+    size_t got;
+    while ((got = fread(buf, 1, sizeof buf, fp)) > 0) ofs.write(buf, got);
+    std::cout << "maxOccurrence " << counter.getMaxOccurrence() << std::endl;
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc != 6) return 2;
+    const std::string mode = argv[1], bin = argv[2], reads = argv[3], out = argv[5];
+    const unsigned long long numThread = strtoull(argv[4], NULL, 10);
+    platanus::setGlobalTmpFileDir(".");
+    omp_set_num_threads(numThread);
+    const unsigned long long k = platanus::getKmerLengthFromBinary(bin);
+    if (k <= 32) return run<Kmer31>(mode, bin, reads, numThread, out);
+    if (k <= 64) return run<KmerN<Binstr63> >(mode, bin, reads, numThread, out);
+    if (k <= 96) return run<KmerN<Binstr95> >(mode, bin, reads, numThread, out);
+    if (k <= 128) return run<KmerN<Binstr127> >(mode, bin, reads, numThread, out);
+    if (k <= 160) return run<KmerN<Binstr159> >(mode, bin, reads, numThread, out);
+    return run<KmerN<binstr_t> >(mode, bin, reads, numThread, out);
+}

@@ -40,6 +40,7 @@ SYMBOLS = [
     "pbk_microbench_atomics", "pbk_timer_mark", "pbk_timer_elapsed_ms", "pbk_set_timing",
     "pbk_keyx_plan", "pbk_keyx_partition", "pbk_keyx_partition_device", "pbk_keyx_insert_device",
     "pbk_lookup", "pbk_lookup_device", "pbk_load_entries", "pbk_read_kmer_occ_bin", "pbk_free",
+    "pbk_match_reads", "pbk_seed_entries",
 ]
 
 
@@ -124,6 +125,8 @@ def load_library(build_if_missing: bool = True):
     L.pbk_lookup.argtypes = [vp, vp, u64p, C.c_uint64, C.c_int, vp, u64p, vp]
     L.pbk_lookup_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, vp]
     L.pbk_load_entries.argtypes = [vp, u64p, vp, C.c_uint64]
+    L.pbk_seed_entries.argtypes = [vp, u64p, vp, C.c_uint64]
+    L.pbk_match_reads.argtypes = [vp, vp, u64p, C.c_uint64, C.c_int, vp, u64p, vp]
     L.pbk_read_kmer_occ_bin.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp),
                                         C.POINTER(C.c_uint64)]
     L.pbk_free.argtypes = [vp]; L.pbk_free.restype = None
@@ -293,6 +296,21 @@ class KmerCounter:
         self._check(self._L.pbk_lookup(self._ctx, _ptr(bases), _ptr(offsets), len(offsets) - 1, encoding, np_p, npo_p, _ptr(out)),
                     "pbk_lookup")
         return out
+
+    def match_reads(self, bases: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+        """Counter::pickupReadMatchedEdgeKmer (counter.h:870-910): bool per read -- has a k-mer that is in the table."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        out = np.zeros(len(offsets) - 1, np.uint8)
+        self._check(self._L.pbk_match_reads(self._ctx, _ptr(bases), _ptr(offsets), len(offsets) - 1, ENC_ASCII, None, None, _ptr(out)),
+                    "pbk_match_reads")
+        return out.astype(bool)
+
+    def seed_entries(self, keys: np.ndarray, counts: np.ndarray):
+        """makeKmerReadDistributionConsideringPreviousGraph (counter.h:663-750): these k-mers keep their value."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        counts = np.ascontiguousarray(counts, dtype=np.uint16)
+        self._check(self._L.pbk_seed_entries(self._ctx, _ptr(keys), _ptr(counts), len(counts)), "pbk_seed_entries")
 
     def load_entries(self, keys: np.ndarray, counts: np.ndarray):
         keys = np.ascontiguousarray(keys, dtype=np.uint64)

@@ -80,6 +80,7 @@ struct pbk_ctx {
     // key exchange (pbk_keyx_*): layout agreed between the ranks, and -- only during a pbk_keyx_partition* call -- the
     // caller's send buffer and cursors that Pass A fills instead of the context's own bucket store
     u64 *d_len_scratch = nullptr; Counters *d_ctr_scratch = nullptr;     // pbk_lookup: its reads must not enter the histograms
+    std::vector<u64> seed_rec;                                           // pbk_seed_entries: (key words, value) records, applied by pbk_finalize
     PartitionPlan keyx_plan{}; u64 keyx_max_windows = 0;
     u64 *keyx_send = nullptr, *keyx_cursors = nullptr;
 
@@ -659,6 +660,37 @@ void release_all(pbk_ctx *c)
 
 }  // namespace
 
+// pbk_seed_entries: the seeded k-mers get their seeded value, whatever the reads added (see override_records_kernel)
+int apply_seeds(pbk_ctx *c)
+{
+    const u64 n = c->seed_rec.size() / (c->W + 1);
+    TRY(ensure_tables(c, std::max<u64>(n, 1024), false));
+    if ((double)(c->occupied + n) > max_load(c) * (double)c->table.capacity())
+        TRY(grow_table(c, &c->table, c->occupied, (u64)((c->occupied + n) / max_load(c)) + 1));
+    TRY(ensure_overflow(c, n));
+    u64 *d_rec = nullptr;
+    const size_t bytes = c->seed_rec.size() * 8;
+    TRY(dev_alloc(c, (void **)&d_rec, bytes));
+    int rc = PBK_OK;
+    if (cudaMemcpyAsync(d_rec, c->seed_rec.data(), bytes, cudaMemcpyHostToDevice, c->s_compute) != cudaSuccess) rc = fail(c, PBK_E_CUDA, "upload of seeded entries failed");
+    c->h2d_bytes += bytes;
+    if (rc == PBK_OK) {
+        { Span sp(c, LC_OTHER); launch_override_records(d_rec, n, c->table, c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute); }
+        if (cudaGetLastError() != cudaSuccess) rc = fail(c, PBK_E_CUDA, "override launch failed");
+    }
+    if (rc == PBK_OK) rc = read_counters(c);
+    else cudaStreamSynchronize(c->s_compute);
+    dev_free(c, d_rec, bytes);
+    TRY(rc);
+    // a seeded key that found no slot within the probe limit: absent from the table, so the weighted insert of the
+    // overflow route sets it as well
+    const ShardInfo keep = c->shard;
+    c->shard = ShardInfo{1, 0};
+    rc = drain_overflow(c);
+    c->shard = keep;
+    return rc;
+}
+
 // =================================================================================================
 // exported functions
 // =================================================================================================
@@ -795,6 +827,7 @@ int pbk_finalize(pbk_ctx *c, uint64_t *occ_hist, uint64_t *len_hist, uint64_t *n
     CK(cudaSetDevice(c->device));
     if (c->shard.n_shards > 1 && c->occupied_remote > 0)
         return fail(c, PBK_E_STATE, "%llu staged records have not been exchanged (pbk_shard_pack_device)", (unsigned long long)c->occupied_remote);
+    if (!c->seed_rec.empty()) TRY(apply_seeds(c));
     c->h_occ_hist.assign(PBK_OCC_BINS, 0);
     if (c->table.slots) {
         CK(cudaMemsetAsync(c->d_occ_hist, 0, PBK_OCC_BINS * 8, c->s_compute));
@@ -923,6 +956,7 @@ int pbk_reset(pbk_ctx *c, uint32_t k)
         if (c->remote.slots) { Span sp(c, LC_OTHER); launch_table_init(c->remote, c->s_compute); }
     }
     c->remote_dirty = false; c->stage_gen += 1;
+    c->seed_rec.clear();
     c->k = k; c->W = W;
     CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), c->s_compute));
     CK(cudaMemsetAsync(c->d_len_hist, 0, PBK_LEN_BINS * 8, c->s_compute));
@@ -1055,13 +1089,15 @@ int pbk_load_entries(pbk_ctx *c, const uint64_t *keys, const uint16_t *counts, u
     return rc;
 }
 
+// h_out / d_out: occurrence per base (pbk_lookup); h_match: one byte per read instead (pbk_match_reads)
 static int lookup_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, const u64 *h_offsets,
                          const u64 *d_offsets_in, u64 n_reads, u64 n_bases, int encoding, const int32_t *n_pos,
-                         const u64 *n_pos_offsets, uint16_t *h_out, uint16_t *d_out)
+                         const u64 *n_pos_offsets, uint16_t *h_out, uint16_t *d_out, uint8_t *h_match = nullptr)
 {
     CK(cudaSetDevice(c->device));
     if (n_bases > MAX_PUSH_BASES) return fail(c, PBK_E_ARG, "pbk_lookup takes at most %llu bases per call", (unsigned long long)MAX_PUSH_BASES);
-    if (h_out) memset(h_out, 0, n_bases * 2);
+    if (h_match) memset(h_match, 0, n_reads);
+    else if (h_out) memset(h_out, 0, n_bases * 2);
     else CK(cudaMemsetAsync(d_out, 0, n_bases * 2, c->s_compute));
     if (!c->table.slots || n_bases < c->k) { CK(cudaStreamSynchronize(c->s_compute)); return PBK_OK; }
     TRY(ensure_batch_buffers(c, n_bases, n_reads));
@@ -1085,6 +1121,7 @@ static int lookup_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_ba
     uint8_t *d_tmp_stage = nullptr;
     if (!d_bases_in) TRY(dev_alloc(c, (void **)&d_tmp_stage, CHUNK_BASES));
     uint16_t *d_occ = nullptr;
+    uint8_t *d_match = nullptr;
     int32_t *d_np = nullptr; u64 *d_npo = nullptr;
     const u64 total_n = (encoding == PBK_ENC_PLATANUS && n_pos_offsets) ? n_pos_offsets[n_reads] : 0;
     int rc = dev_alloc(c, (void **)&d_occ, words * 64);
@@ -1114,13 +1151,22 @@ static int lookup_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_ba
         // the kernel indexes by the window's END; the caller gets the window's START: shift by k - 1
         const u64 n_starts = n_bases - (c->k - 1);
         cudaError_t e = cudaGetLastError();
-        if (e == cudaSuccess)
+        if (e == cudaSuccess && h_match) {
+            rc = dev_alloc(c, (void **)&d_match, n_reads);
+            if (rc == PBK_OK) {
+                { Span sp(c, LC_OTHER); launch_read_match(d_off, n_reads, d_occ, (int)c->k, d_match, c->sm_count, c->s_compute); }
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaMemcpyAsync(h_match, d_match, n_reads, cudaMemcpyDeviceToHost, c->s_compute);
+                c->d2h_bytes += n_reads;
+            }
+        } else if (e == cudaSuccess)
             e = h_out ? cudaMemcpyAsync(h_out, d_occ + (c->k - 1), n_starts * 2, cudaMemcpyDeviceToHost, c->s_compute)
                       : cudaMemcpyAsync(d_out, d_occ + (c->k - 1), n_starts * 2, cudaMemcpyDeviceToDevice, c->s_compute);
         if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_ctr, c->d_ctr_scratch, sizeof(Counters), cudaMemcpyDeviceToHost, c->s_compute);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_compute);
-        if (h_out) c->d2h_bytes += n_starts * 2;
-        if (e != cudaSuccess) rc = fail(c, PBK_E_CUDA, "lookup: %s", cudaGetErrorString(e));
+        if (h_out && !h_match) c->d2h_bytes += n_starts * 2;
+        if (rc != PBK_OK) {}
+        else if (e != cudaSuccess) rc = fail(c, PBK_E_CUDA, "lookup: %s", cudaGetErrorString(e));
         else {
             const u32 flags = c->h_ctr->error_flags;
             *c->h_ctr = c->last;                                      // h_ctr mirrors the counting counters between calls
@@ -1129,7 +1175,7 @@ static int lookup_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_ba
         }
     }
     cudaStreamSynchronize(c->s_compute);
-    dev_free(c, d_occ, words * 64); dev_free(c, d_tmp_stage, CHUNK_BASES);
+    dev_free(c, d_occ, words * 64); dev_free(c, d_tmp_stage, CHUNK_BASES); dev_free(c, d_match, n_reads);
     dev_free(c, d_np, total_n * 4); dev_free(c, d_npo, (n_reads + 1) * 8);
     return rc;
 }
@@ -1146,6 +1192,36 @@ int pbk_lookup(pbk_ctx *c, const uint8_t *bases, const uint64_t *read_offsets, u
     if (n_bases == 0) return PBK_OK;
     return lookup_common(c, bases, nullptr, (const u64 *)read_offsets, nullptr, n_reads, n_bases, encoding, n_pos,
                          (const u64 *)n_pos_offsets, occ_out, nullptr);
+}
+
+int pbk_match_reads(pbk_ctx *c, const uint8_t *bases, const uint64_t *read_offsets, uint64_t n_reads, int encoding,
+                    const int32_t *n_pos, const uint64_t *n_pos_offsets, uint8_t *matched_out)
+{
+    if (!c) return PBK_E_ARG;
+    if (n_reads == 0) return PBK_OK;
+    if (!read_offsets || !matched_out || (encoding != PBK_ENC_ASCII && encoding != PBK_ENC_PLATANUS)) return fail(c, PBK_E_ARG, "bad arguments");
+    if (read_offsets[0] != 0) return fail(c, PBK_E_ARG, "read_offsets[0] must be 0");
+    const u64 n_bases = read_offsets[n_reads];
+    if (n_bases && !bases) return fail(c, PBK_E_ARG, "bases is NULL");
+    if (n_bases == 0) { memset(matched_out, 0, n_reads); return PBK_OK; }
+    return lookup_common(c, bases, nullptr, (const u64 *)read_offsets, nullptr, n_reads, n_bases, encoding, n_pos,
+                         (const u64 *)n_pos_offsets, nullptr, nullptr, matched_out);
+}
+
+int pbk_seed_entries(pbk_ctx *c, const uint64_t *keys, const uint16_t *counts, uint64_t n)
+{
+    if (!c) return PBK_E_ARG;
+    if (n == 0) return PBK_OK;
+    if (!keys || !counts) return fail(c, PBK_E_ARG, "NULL entries");
+    if (c->finalized) return fail(c, PBK_E_STATE, "pbk_seed_entries after pbk_finalize (call pbk_reset first)");
+    const int W = c->W;
+    for (u64 i = 0; i < n; ++i) {
+        if (counts[i] == 0) continue;                                // counter.h:700: only entries with a value are written
+        if (c->shard.n_shards > 1 && pbk_shard_of_key(keys + i * W, c->k, c->shard.n_shards) != c->shard.rank) continue;
+        for (int j = 0; j < W; ++j) c->seed_rec.push_back(keys[i * W + j]);
+        c->seed_rec.push_back(counts[i]);
+    }
+    return PBK_OK;
 }
 
 int pbk_lookup_device(pbk_ctx *c, const void *d_bases, const void *d_read_offsets, uint64_t n_reads, uint64_t n_bases, void *d_occ_out)

@@ -347,6 +347,23 @@ __device__ __forceinline__ u32 ct_lookup(const u64 *tab, const CtGeom &g, u64 h)
     return 0;
 }
 
+// Set the count of the key with hash h to `w` (no other kernel running; keys of one launch are distinct): true if the
+// key was there.  Used for seeded entries, whose value wins over whatever the reads added (counter.h:695-705).
+__device__ __forceinline__ bool ct_set_count(u64 *tab, const CtGeom &g, u64 h, u64 w)
+{
+    const u64 home = h >> g.rbits;
+    const u64 r_hi = ((h << (64 - g.rbits)) >> (64 - g.rbits)) << CT_DISP_BITS;
+#pragma unroll 1
+    for (u32 d = 0; d <= (u32)CT_MAX_DISP; ++d) {
+        u64 *s = tab + ((home + d) & g.capmask);
+        const u64 v = ld_cg_u64(s);
+        const u64 hi = v >> g.cbits;
+        if (hi == 0) return false;
+        if (hi == (r_hi | (u64)(d + 1))) { st_cg_u64(s, (v & ~g.cmask) | w); return true; }
+    }
+    return false;
+}
+
 // -------------------------------------------------------------------------------------------------
 // generic table, k > 32
 // -------------------------------------------------------------------------------------------------
@@ -409,6 +426,24 @@ __device__ __forceinline__ u32 wide_lookup(const Slot<W> *table, u64 cap, const 
     return 0;
 }
 
+template <int W>
+__device__ __forceinline__ bool wide_set_count(Slot<W> *table, u64 cap, const u64 *key, u64 h, u32 w)
+{
+    u64 idx = __umul64hi(h, cap);
+#pragma unroll 1
+    for (int probe = 0; probe < MAX_PROBE; ++probe) {
+        Slot<W> *s = table + idx;
+        const u32 cs = ld_cg_u32(&s->cs);
+        if (cs == 0) return false;
+        bool eq = true;
+#pragma unroll
+        for (int j = 0; j < W; ++j) eq &= (ld_cg_u64(&s->key[j]) == key[j]);
+        if (eq) { s->cs = w; return true; }
+        idx = (idx + 1 == cap) ? 0 : idx + 1;
+    }
+    return false;
+}
+
 // -------------------------------------------------------------------------------------------------
 // uniform view used by every kernel: Table<W> wraps either format
 // -------------------------------------------------------------------------------------------------
@@ -438,6 +473,12 @@ struct Table {
     {
         if constexpr (W == 1) return ct_lookup(slots, g, h);
         else return wide_lookup<W>(slots, cap, key, h);
+    }
+    // set the count of a key that is in the table; false if it is not
+    __device__ __forceinline__ bool set_count(const u64 *key, u64 h, u32 w) const
+    {
+        if constexpr (W == 1) return ct_set_count(slots, g, h, w);
+        else return wide_set_count<W>(slots, cap, key, h, w);
     }
     // read slot i once all inserts have drained: false if empty
     __device__ __forceinline__ bool load(u64 i, u64 *key, u32 *count) const

@@ -84,6 +84,21 @@ void launch_lookup(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 wo
             Table<W>(table.slots, table.cap), (u64 *)occ)));
 }
 
+void launch_override_records(const u64 *records, u64 n, TableView table, Counters *ctr, u64 *overflow_keys, u64 overflow_cap,
+                             int sm_count, cudaStream_t st)
+{
+    if (n == 0) return;
+    const int grid = grid_for(n, 256, sm_count, 8);
+    PBK_DISPATCH_W(table.words,
+        (override_records_kernel<W><<<grid, 256, 0, st>>>(records, n, Table<W>(table.slots, table.cap), ctr, overflow_keys, overflow_cap)));
+}
+
+void launch_read_match(const u64 *offsets, u64 n_reads, const uint16_t *occ, int k, uint8_t *matched, int sm_count, cudaStream_t st)
+{
+    if (n_reads == 0) return;
+    read_match_kernel<<<grid_for(n_reads, 256, sm_count, 8), 256, 0, st>>>(offsets, n_reads, occ, k, matched);
+}
+
 void launch_insert_records(const u64 *records, u64 n, bool weighted, TableView table, TableView remote,
                            ShardInfo shard, Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count,
                            cudaStream_t st)

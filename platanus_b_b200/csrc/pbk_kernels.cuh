@@ -39,6 +39,11 @@ void launch_count(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 wor
 // that ENDS at p, 0 if unusable or absent.  Read-only on the table.
 void launch_lookup(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
                    TableView table, uint16_t *occ, int sm_count, cudaStream_t st);
+// SET the count of n (key words..., value) records (insert those that are absent); value 0 = skip
+void launch_override_records(const u64 *records, u64 n, TableView table, Counters *ctr, u64 *overflow_keys, u64 overflow_cap,
+                             int sm_count, cudaStream_t st);
+// matched[r] = any window of read r found (occ: launch_lookup's output)
+void launch_read_match(const u64 *offsets, u64 n_reads, const uint16_t *occ, int k, uint8_t *matched, int sm_count, cudaStream_t st);
 // insert n (key words..., weight) records; a record has W + 1 words when weighted, W otherwise.
 // Overflow-list records always have W + 1 words.
 void launch_insert_records(const u64 *records, u64 n, bool weighted, TableView table, TableView remote,

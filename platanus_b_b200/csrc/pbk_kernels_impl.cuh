@@ -351,6 +351,57 @@ insert_records_kernel(const u64 *__restrict__ rec, u64 n, int weighted, Table<W>
     }
 }
 
+// Seeded entries (makeKmerReadDistributionConsideringPreviousGraph, counter.h:663-750): a k-mer that was in the table
+// before the reads were counted keeps its seeded value -- the reference never counts read windows that hit the table
+// (divideKmerUsedMakingPreviousContig, counter.h:828-861) and dumps the table as it was (counter.h:695-705).  Counting
+// everything and then SETTING the seeded keys gives the same table.  Records: W key words + value; value 0 = no entry.
+template <int W>
+__global__ void __launch_bounds__(256)
+override_records_kernel(const u64 *__restrict__ rec, u64 n, Table<W> table, Counters *ctr, u64 *ovf, u64 ovf_cap)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    u32 newk = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        u64 key[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) key[j] = rec[i * (W + 1) + j];
+        const u64 wgt = rec[i * (W + 1) + W];
+        if (wgt == 0) continue;
+        const u32 w = wgt > COUNT_SAT ? COUNT_SAT : (u32)wgt;
+        const u64 h = hash_key<W>(key);
+        if (table.set_count(key, h, w)) continue;
+        const int r = table.insert(key, h, w, false);              // no read contains it: a new entry
+        newk += (r > 0);
+        if (r < 0) {
+            const u64 at = atomicAdd(&ctr->overflow_n, 1ull);
+            if (at < ovf_cap) {
+#pragma unroll
+                for (int j = 0; j < W; ++j) ovf[at * (W + 1) + j] = key[j];
+                ovf[at * (W + 1) + W] = w;
+            } else {
+                atomicOr(&ctr->error_flags, ERR_OVERFLOW_LOST);
+            }
+        }
+    }
+    newk = warp_sum_u32(newk);
+    if ((threadIdx.x & 31) == 0 && newk) atomicAdd(&ctr->new_keys, (u64)newk);
+}
+
+// Counter::pickupReadMatchedEdgeKmer (counter.h:870-910): matched[r] = 1 iff some usable window of read r has its
+// k-mer in the table.  occ = lookup_kernel's output (u16 per stream position, indexed by window END).
+__global__ void __launch_bounds__(256)
+read_match_kernel(const u64 *__restrict__ off, u64 n_reads, const uint16_t *__restrict__ occ, int k, uint8_t *matched)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += stride) {
+        const u64 b = off[r], e = off[r + 1];
+        uint8_t m = 0;
+        for (u64 p = b + (u64)k - 1; p < e; ++p)
+            if (occ[p]) { m = 1; break; }
+        matched[r] = m;
+    }
+}
+
 // =================================================================================================
 // partitioned counting: Pass A scatters canonical k-mers into P hash-range buckets, Pass B inserts one
 // bucket at a time.  home slot = mulhi(hash, capacity) and bucket = mulhi(hash, P) are both monotone in

@@ -170,6 +170,19 @@ public:
         check(pbk_lookup(ctx_, bases, offsets, n, PBK_ENC_ASCII, NULL, NULL, occ), "pbk_lookup");
     }
 
+    // ---- Counter::pickupReadMatchedEdgeKmer (counter.h:870-910) on reads held in memory: matched[r] = the read stays
+    void matchReads(const uint8_t *bases, const uint64_t *offsets, uint64_t n, uint8_t *matched)
+    {
+        check(pbk_match_reads(ctx_, bases, offsets, n, PBK_ENC_ASCII, NULL, NULL, matched), "pbk_match_reads");
+    }
+
+    // ---- Counter::makeKmerReadDistributionConsideringPreviousGraph (counter.h:663-750), wide seam: beginCounting(k);
+    //      seedEntries(table of the previous round's contigs, assemble.cpp:400-403); pushReads(...); endCounting(memory)
+    void seedEntries(const uint64_t *keys, const uint16_t *values, uint64_t n)
+    {
+        check(pbk_seed_entries(ctx_, keys, values, n), "pbk_seed_entries");
+    }
+
     // ---- counter.h:1000-1007 ----------------------------------------------------------------------
     void outputOccurrenceDistribution(const std::string &filename)
     {

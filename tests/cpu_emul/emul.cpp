@@ -254,3 +254,52 @@ extern "C" int emul_lookup(const uint8_t *bases, const u64 *off, u64 n_reads, in
 #define LK(Wv) case Wv: return run_lookup<Wv>(bases, off, n_reads, k, keys, counts, n, out);
     switch ((k + 31) / 32) { LK(1) LK(2) LK(3) LK(4) LK(5) LK(6) LK(7) LK(8) default: return -1; }
 }
+
+// ---- iterative-k steps (pbk_seed_entries + pbk_finalize, pbk_match_reads) -----------------------------------------------
+template <int W>
+static int run_seeded(const uint8_t *bases, const u64 *off, u64 n_reads, int k, const u64 *seed_keys, const uint16_t *seed_counts,
+                      u64 n_seed, u64 *keys_out, uint16_t *counts_out, u64 cap_out, u64 *n_out, u64 *n_inst, uint8_t *matched)
+{
+    const u64 n_bases = off[n_reads], words = (n_bases + 31) / 32;
+    std::vector<u64> stream(words + STREAM_PAD_WORDS + 1, 0), len_hist(500001, 0);
+    std::vector<u32> nflag(words + STREAM_PAD_WORDS + 1, 0), rflag(words + STREAM_PAD_WORDS + 1, 0);
+    Counters ctr{};
+    typedef typename SlotType<W>::type slot_t;
+    const u64 slots = W == 1 ? (1ull << 24) : 2 * (n_bases + n_seed) + 1024;
+    std::vector<slot_t> tv(slots);
+    memset(tv.data(), 0, tv.size() * sizeof(slot_t));
+    Table<W> table(tv.data(), tv.size());
+    const u64 OVF = 1 << 12;
+    std::vector<u64> ovf((W + 1) * OVF), rec(n_seed * (W + 1) + 1);
+    for (u64 i = 0; i < n_seed; ++i) {
+        for (int j = 0; j < W; ++j) rec[i * (W + 1) + j] = seed_keys[i * W + j];
+        rec[i * (W + 1) + W] = seed_counts[i];
+    }
+    read_marks_kernel(off, n_reads, len_hist.data(), rflag.data() + STREAM_PAD_WORDS, &ctr);
+    pack_kernel<false>(bases, n_bases, words, 0, stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, 0, &ctr);
+    if (matched) {
+        // pbk_match_reads: the table holds the given entries, nothing is counted
+        insert_records_kernel<W>(rec.data(), n_seed, 1, table, table, 1, 0, &ctr, ovf.data(), OVF);
+        std::vector<u64> occ4(words * 8 + 1, 0);
+        lookup_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS, 0, words, k, table, occ4.data());
+        read_match_kernel(off, n_reads, (const uint16_t *)occ4.data(), k, matched);
+        return ctr.overflow_n ? -2 : 0;
+    }
+    // pbk_push_reads ... pbk_seed_entries ... pbk_finalize: count everything, then the seeded keys get their value
+    count_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS, 0, words, k,
+                    table, table, 1, 0, &ctr, ovf.data(), OVF);
+    if (ctr.overflow_n) return -2;
+    override_records_kernel<W>(rec.data(), n_seed, table, &ctr, ovf.data(), OVF);
+    if (ctr.overflow_n) return -2;
+    *n_out = 0;
+    export_kernel<W>(table, 1, keys_out, counts_out, cap_out, n_out);
+    *n_inst = ctr.instances;
+    return 0;
+}
+
+extern "C" int emul_seeded(const uint8_t *bases, const u64 *off, u64 n_reads, int k, const u64 *seed_keys, const uint16_t *seed_counts,
+                           u64 n_seed, u64 *keys_out, uint16_t *counts_out, u64 cap_out, u64 *n_out, u64 *n_inst, uint8_t *matched)
+{
+#define SD(Wv) case Wv: return run_seeded<Wv>(bases, off, n_reads, k, seed_keys, seed_counts, n_seed, keys_out, counts_out, cap_out, n_out, n_inst, matched);
+    switch ((k + 31) / 32) { SD(1) SD(2) SD(3) SD(4) SD(5) SD(6) SD(7) SD(8) default: return -1; }
+}

@@ -135,3 +135,39 @@ def emul_lookup(bases: np.ndarray, offsets: np.ndarray, k: int, keys: np.ndarray
     rc = lib().emul_lookup(p(bases), p(offsets), C.c_uint64(len(offsets) - 1), k, p(keys), p(counts), C.c_uint64(len(counts)), p(out))
     assert rc == 0, rc
     return out[:int(offsets[-1])]
+
+
+def emul_seeded_count(bases, offsets, k: int, seed_keys, seed_counts):
+    """pbk_push_reads + pbk_seed_entries + pbk_finalize: sorted (keys, counts) of the table, n_instances counted."""
+    W = (k + 31) // 32
+    bases = np.concatenate([np.ascontiguousarray(bases, dtype=np.uint8), np.zeros(64, np.uint8)])
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    sk = np.ascontiguousarray(seed_keys, dtype=np.uint64).reshape(-1, W)
+    sc = np.ascontiguousarray(seed_counts, dtype=np.uint16)
+    cap = int(offsets[-1]) + len(sc) + 1
+    keys = np.zeros((cap, W), np.uint64)
+    counts = np.zeros(cap, np.uint16)
+    n_out, n_inst = C.c_uint64(), C.c_uint64()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().emul_seeded(p(bases), p(offsets), C.c_uint64(len(offsets) - 1), k, p(sk), p(sc), C.c_uint64(len(sc)), p(keys), p(counts),
+                           C.c_uint64(cap), C.byref(n_out), C.byref(n_inst), None)
+    assert rc == 0, rc
+    keys, counts = keys[:n_out.value], counts[:n_out.value]
+    order = np.lexsort(tuple(keys[:, w] for w in range(W)))
+    return keys[order], counts[order], n_inst.value
+
+
+def emul_match_reads(bases, offsets, k: int, keys, counts) -> np.ndarray:
+    """pbk_match_reads over a table holding (keys, counts): bool per read."""
+    W = (k + 31) // 32
+    bases = np.concatenate([np.ascontiguousarray(bases, dtype=np.uint8), np.zeros(64, np.uint8)])
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    sk = np.ascontiguousarray(keys, dtype=np.uint64).reshape(-1, W)
+    sc = np.ascontiguousarray(counts, dtype=np.uint16)
+    out = np.zeros(len(offsets), np.uint8)
+    n_out, n_inst = C.c_uint64(), C.c_uint64()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().emul_seeded(p(bases), p(offsets), C.c_uint64(len(offsets) - 1), k, p(sk), p(sc), C.c_uint64(len(sc)), None, None,
+                           C.c_uint64(0), C.byref(n_out), C.byref(n_inst), p(out))
+    assert rc == 0, rc
+    return out[:len(offsets) - 1].astype(bool)

@@ -145,3 +145,48 @@ def test_bin_reader_on_a_file_written_by_the_reference_program(oracle, k, tmp_pa
     order = np.lexsort(tuple(keys[:, w] for w in range(W)))
     assert kk == k and idx == ref.table.index_size
     assert np.array_equal(keys[order], rk) and np.array_equal(counts[order], rc_)
+
+
+# ---- the two table-consuming steps of the iterative-k assembly ---------------------------
+ITER_CASES = sorted(glob.glob(os.path.join(G.GOLDEN, "iter_k*.npz")), key=lambda p: int(os.path.basename(p)[6:-4]))
+
+
+def iter_reads(O, g):
+    rd = O.Reads()
+    for r in str(g["reads"]).split("\n"):
+        rd.add(r.encode())
+    return rd
+
+
+def test_there_are_iterative_k_golden_vectors():
+    assert len(ITER_CASES) >= 5
+
+
+@pytest.mark.parametrize("path", ITER_CASES, ids=lambda p: os.path.basename(p)[:-4])
+def test_oracle_iterative_k_steps_match_the_reference(oracle, path):
+    """tests/golden/iter_k*.npz: what the UNMODIFIED reference's pickupReadMatchedEdgeKmer and
+    makeKmerReadDistributionConsideringPreviousGraph produce (oracle/ref_iter_harness.cpp, oracle/make_golden_iter.py)."""
+    O = oracle
+    g = np.load(path, allow_pickle=False)
+    k = int(g["k"])
+    rd = iter_reads(O, g)
+    assert np.array_equal(O.match_reads(rd, k, g["table_keys"], g["table_counts"]), g["kept"])
+    res = O.count(rd, k, g["table_keys"], g["table_counts"])
+    assert np.array_equal(res.keys, g["keys"]) and np.array_equal(res.counts, g["counts"])
+    assert res.max_occ == int(g["max_occ"])
+    # the seeded values differ from the plain counts somewhere, or the case would prove nothing
+    plain = O.count(rd, k)
+    assert not (len(plain.counts) == len(res.counts) and np.array_equal(plain.counts, res.counts))
+
+
+@pytest.mark.parametrize("path", ITER_CASES, ids=lambda p: os.path.basename(p)[:-4])
+def test_kernels_iterative_k_steps_match_the_reference(oracle, path):
+    from emul_helper import emul_match_reads, emul_seeded_count
+    O = oracle
+    g = np.load(path, allow_pickle=False)
+    k = int(g["k"])
+    rd = iter_reads(O, g)
+    bases, offs = rd.arrays()
+    assert np.array_equal(emul_match_reads(bases, offs, k, g["table_keys"], g["table_counts"]), g["kept"])
+    keys, counts, n_inst = emul_seeded_count(bases, offs, k, g["table_keys"], g["table_counts"])
+    assert np.array_equal(keys, g["keys"]) and np.array_equal(counts, g["counts"])

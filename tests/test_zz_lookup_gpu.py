@@ -79,3 +79,41 @@ def test_read_occurrence_table_binary_then_lookup(oracle, tmp_path):
         assert kc.k == k
         got = kc.lookup(bases, offs)
         assert np.array_equal(got, O.occurrence_array(rd, k, want.keys[keep], want.counts[keep]))
+
+
+# ---- iterative-k steps (pbk_match_reads, pbk_seed_entries) against the reference's own outputs ---------------------------
+from test_lookup_cpu import ITER_CASES, iter_reads          # noqa: E402
+
+
+@pytest.mark.parametrize("path", ITER_CASES, ids=lambda p: os.path.basename(p)[:-4])
+def test_iterative_k_steps_match_the_reference(oracle, path):
+    """tests/golden/iter_k*.npz = outputs of the unmodified Counter<KMER>::pickupReadMatchedEdgeKmer and
+    makeKmerReadDistributionConsideringPreviousGraph (oracle/ref_iter_harness.cpp)."""
+    O = oracle
+    g = np.load(path, allow_pickle=False)
+    k = int(g["k"])
+    rd = iter_reads(O, g)
+    bases, offs = rd.arrays()
+    with KmerCounter(k) as kc:                                   # the table the previous round left
+        kc.load_entries(g["table_keys"], g["table_counts"])
+        assert np.array_equal(kc.match_reads(bases, offs), g["kept"])
+    for order, partition in (("seed first", True), ("reads first", "force")):
+        with KmerCounter(k, partition=partition) as kc:
+            if order == "seed first":
+                kc.seed_entries(g["table_keys"], g["table_counts"])
+                kc.push_reads(bases, offs)
+            else:
+                kc.push_reads(bases, offs)
+                kc.seed_entries(g["table_keys"], g["table_counts"])
+            kc.finalize()
+            keys, counts = kc.export(1, sorted=True)
+            assert np.array_equal(keys, g["keys"]) and np.array_equal(counts, g["counts"])
+            assert kc.max_occurrence == int(g["max_occ"])
+            want = O.count(rd, k, g["table_keys"], g["table_counts"])
+            assert np.array_equal(kc.occ_hist, want.occ_hist)
+            kc.reset()                                               # the seeds are forgotten with the counts
+            kc.push_reads(bases, offs)
+            kc.finalize()
+            plain = O.count(rd, k)
+            keys, counts = kc.export(1, sorted=True)
+            assert np.array_equal(keys, plain.keys) and np.array_equal(counts, plain.counts)
