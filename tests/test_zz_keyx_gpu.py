@@ -9,7 +9,7 @@ import pytest
 import golden_cases as G
 from platanus_b_b200 import KmerCounter, synth
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]      # a hung kernel must not hang the box
 
 
 def _reads(O, case, tmp_path):
