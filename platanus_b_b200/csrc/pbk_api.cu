@@ -1385,6 +1385,9 @@ uint32_t pbk_shard_of_key(const uint64_t *key_words, uint32_t k, uint32_t n_shar
 int pbk_microbench_atomics(int device, uint64_t table_bytes, uint64_t n_ops, int mode, double *ops_per_s)
 {
     if (!ops_per_s || table_bytes < 4096 || n_ops == 0 || mode < 0 || (mode > 11 && mode < 100) || mode > 200) return PBK_E_ARG;
+#ifdef PBK_CPU_EMUL
+    return PBK_E_NO_DEVICE;                          // (host emulation of the ABI for the CPU tests: nothing to measure)
+#endif
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return PBK_E_NO_DEVICE; }
     if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return PBK_E_NO_DEVICE;

@@ -657,7 +657,14 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
 //    table's HBM traffic into one sequential pass.
 constexpr int PASSB_THREADS = 256;
 constexpr int PASSB_KPT = 8;
-constexpr int PASSB_TILE_KEYS = PASSB_THREADS * PASSB_KPT;
+// threads per CTA as the HOST counts tiles (the kernels derive theirs from blockDim): tests/cpu_emul runs every kernel as
+// a single thread
+#ifndef PBK_CPU_EMUL
+constexpr int PASSB_LAUNCH_THREADS = PASSB_THREADS;
+#else
+constexpr int PASSB_LAUNCH_THREADS = 1;
+#endif
+constexpr int PASSB_TILE_KEYS = PASSB_LAUNCH_THREADS * PASSB_KPT;
 #ifndef PBK_PASSB_WIDE_CTAS
 #define PBK_PASSB_WIDE_CTAS 4
 #endif
@@ -811,7 +818,7 @@ passb_desc_kernel(const u64 *__restrict__ cursor, u64 seg_cap, u32 n_buckets, u3
 // therefore is: loads out, all atomics out, one look at the results, no waiting on other threads.
 constexpr int PASSB1_KPT = 8;
 constexpr int PASSB1_ROUNDS = 4;
-constexpr int PASSB1_TILE_KEYS = PASSB_THREADS * PASSB1_KPT * PASSB1_ROUNDS;
+constexpr int PASSB1_TILE_KEYS = PASSB_LAUNCH_THREADS * PASSB1_KPT * PASSB1_ROUNDS;
 constexpr int PASSB1_DEF_CAP = 32 * (PASSB1_KPT + 2);   // deferred keys per warp: what one round can add, plus one batch
 constexpr u32 PASSB1_DONE = 0xFFFFu;
 constexpr u32 PASSB1_VERIFY = 1u << 8, PASSB1_REMOTE = 1u << 9;   // deferred-entry flags above the displacement

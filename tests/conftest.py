@@ -9,7 +9,18 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
+def _use_emulated_abi():
+    """PBK_TEST_EMULATED_ABI=1 (set by tests/test_abi_emulated_cpu.py for a child pytest only): the `-m gpu` tests are pointed
+    at the C ABI compiled for the host (tests/cpu_emul/cuda_rt_shim.h) -- a check of pbk_api.cu's host logic in the GPU-less
+    container.  TEST ONLY: the product never looks at this variable."""
+    import emul_helper
+    from platanus_b_b200 import build
+    build.LIB = emul_helper.abi_lib_path()
+
+
 def pytest_configure(config):
+    if os.environ.get("PBK_TEST_EMULATED_ABI"):
+        _use_emulated_abi()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "slow: larger CPU cases")
 

@@ -2,14 +2,42 @@
 without importing torch.  libpbk links its own static cudart; both runtimes share the device's primary context, so
 pointers are interchangeable."""
 import ctypes as C
+import os
 
 import numpy as np
 
 _rt = None
 
 
+class _HostRuntime:
+    """PBK_TEST_EMULATED_ABI (tests/conftest.py): "device" memory of the emulated ABI is host memory"""
+    def __init__(self):
+        self.libc = C.CDLL(None)
+        self.libc.malloc.restype = C.c_void_p
+        self.libc.malloc.argtypes = [C.c_size_t]
+        self.libc.free.argtypes = [C.c_void_p]
+
+    def cudaMalloc(self, pp, n):
+        pp._obj.value = self.libc.malloc(n)
+        return 0 if pp._obj.value else 2
+
+    def cudaFree(self, p):
+        self.libc.free(p)
+        return 0
+
+    def cudaMemcpy(self, d, s, n, kind):
+        C.memmove(d, s, n)
+        return 0
+
+    def cudaMemset(self, d, v, n):
+        C.memset(d, v, n)
+        return 0
+
+
 def _cudart():
     global _rt
+    if _rt is None and os.environ.get("PBK_TEST_EMULATED_ABI"):
+        _rt = _HostRuntime()
     if _rt is None:
         last = None
         for name in ("libcudart.so.12", "libcudart.so", "/usr/local/cuda/lib64/libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so"):

@@ -171,3 +171,38 @@ def emul_match_reads(bases, offsets, k: int, keys, counts) -> np.ndarray:
                            C.c_uint64(0), C.byref(n_out), C.byref(n_inst), p(out))
     assert rc == 0, rc
     return out[:len(offsets) - 1].astype(bool)
+
+
+# ---- the WHOLE C ABI compiled for the host (cuda_rt_shim.h): pbk_api.cu + the launch wrappers of pbk_kernels.cu ------------
+ABI_OUT = os.path.join(HERE, "cpu_emul", "_build", "libpbk_emul_abi.so")
+
+
+def abi_lib_path() -> str:
+    """Build (if stale) and return the emulated libpbk: same sources as the product, kernels run as one host thread.
+    pbk_kernels.cu is compiled from a copy whose `<<<grid, block, smem, stream>>>` launch configurations are removed."""
+    import re
+    emul_dir = os.path.join(HERE, "cpu_emul")
+    srcs = [os.path.join(CSRC, f) for f in ("pbk_kernels.cu", "pbk_api.cu", "pbk_host.cpp", "pbk_device.cuh", "pbk_kernels.cuh",
+                                            "pbk_kernels_impl.cuh")]
+    deps = srcs + [os.path.join(emul_dir, f) for f in ("cuda_shim.h", "cuda_rt_shim.h", "abi_extra.cpp")] + [
+        os.path.join(os.path.dirname(HERE), "include", "pbk.h")]
+    if os.path.exists(ABI_OUT) and os.path.getmtime(ABI_OUT) >= max(os.path.getmtime(d) for d in deps):
+        return ABI_OUT
+    build = os.path.dirname(ABI_OUT)
+    os.makedirs(build, exist_ok=True)
+    text = open(srcs[0]).read()
+    text, n = re.subn(r"<<<[^;]*?>>>", "", text)
+    assert n >= 25, n
+    text = text.replace('#include "pbk_kernels.cuh"', f'#include "{CSRC}/pbk_kernels.cuh"').replace(
+        '#include "pbk_kernels_impl.cuh"', f'#include "{CSRC}/pbk_kernels_impl.cuh"')
+    gen = os.path.join(build, "pbk_kernels_emul.cpp")
+    open(gen, "w").write("// GENERATED from platanus_b_b200/csrc/pbk_kernels.cu (launch configurations removed)\n" + text)
+    flags = ["-O1", "-std=c++17", "-fPIC", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable", "-DPBK_CPU_EMUL=1",
+             "-include", os.path.join(emul_dir, "cuda_shim.h"), "-include", os.path.join(emul_dir, "cuda_rt_shim.h")]
+    objs = []
+    for src in (gen, srcs[1], os.path.join(emul_dir, "abi_extra.cpp"), srcs[2]):
+        obj = os.path.join(build, os.path.basename(src).split(".")[0] + "_abi.o")
+        subprocess.run(["g++", *flags, "-x", "c++", "-c", src, "-o", obj], check=True)
+        objs.append(obj)
+    subprocess.run(["g++", "-shared", "-o", ABI_OUT, *objs, "-lpthread"], check=True)
+    return ABI_OUT

@@ -1,0 +1,44 @@
+"""The host logic of the C ABI (platanus_b_b200/csrc/pbk_api.cu: batching, table sizing and growth, overflow handling,
+sharding, key exchange, lookup, seeded counting) checked in the GPU-less build container: the product sources are
+compiled for the host against a synchronous stand-in for the CUDA runtime (tests/cpu_emul/cuda_rt_shim.h, kernels run as
+one sequential thread), and the `-m gpu` tests of the listed files run against that library in a child pytest.
+
+This is a logic check only -- never shipped, never timed, and no fallback: the product library has no path to it.  The real
+parity tests are the same test functions run on a B200."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def run_child(args, timeout):
+    env = dict(os.environ, PBK_TEST_EMULATED_ABI="1")
+    return subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "--runxfail", "-p", "no:cacheprovider", "-x", *args],
+                          cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+
+
+def test_emulated_abi_builds_and_exports_the_abi():
+    import ctypes as C
+
+    import emul_helper
+    from platanus_b_b200 import capi
+    L = C.CDLL(emul_helper.abi_lib_path())
+    for name in capi.SYMBOLS:
+        assert hasattr(L, name), name
+
+
+@pytest.mark.parametrize("selection", [
+    ["tests/test_zz_keyx_gpu.py"],
+    ["tests/test_zz_lookup_gpu.py"],
+    ["tests/test_gpu_parity.py", "-k", "golden_cases and (kat_k4 or smallfq_k32 or smallfq_k75 or smallfa_k200 or cov_k21_auto or multi_k32_n2 or sat_k32)"],
+    ["tests/test_gpu_parity.py", "-k", "table_growth or error_behaviour or pipelined_pass_overlap"],
+], ids=["key_exchange", "lookup_and_iterative_k", "golden_cases", "sharding_growth_errors"])
+def test_gpu_tests_pass_against_the_emulated_abi(selection):
+    p = run_child(selection, timeout=1500)
+    tail = "\n".join(p.stdout.splitlines()[-25:])
+    assert p.returncode == 0, tail + "\n" + p.stderr[-2000:]
+    assert " passed" in tail and "failed" not in tail, tail

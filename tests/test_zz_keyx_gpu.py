@@ -86,7 +86,7 @@ def _keyx_logical_shards(O, b, o, k, n_shards):
             d.free()
 
 
-UNRUN = pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: never run on a B200 yet "
+UNRUN = pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: passes against the host-emulated ABI (tests/test_abi_emulated_cpu.py), never run on a B200 yet "
                                                "(XPASS = passes; the mark goes away once seen to pass)")
 
 
