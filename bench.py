@@ -257,7 +257,6 @@ def main_ours(args):
 
     kc = KmerCounter(K, device=local_rank, n_shards=world, shard_rank=rank, timing=True)
     W = kc.words
-    send_buf = recv_buf = None
     hist_dev = torch.zeros(65535, dtype=torch.int64, device="cuda")
     # --exchange keys (k <= 32): the k-mers travel BEFORE counting -- Pass A writes them straight into the all-to-all send
     # buffer, every rank runs Pass B over what it received (include/pbk.h, pbk_keyx_*).  Default is the record exchange,
@@ -274,43 +273,23 @@ def main_ours(args):
             o_c = (offsets[r0:r1 + 1] - offsets[r0]).astype(np.int64)
             h_o = torch.from_numpy(o_c.copy()).pin_memory()
             ch.append({"n_reads": r1 - r0, "b0": int(offsets[r0]), "n_bases": int(offsets[r1] - offsets[r0]), "h_offs": h_o, "d_offs": h_o.cuda()})
-        max_w = sharding.max_windows_any_rank(max(max(c["n_bases"] - c["n_reads"] * (K - 1), 0) for c in ch), device="cuda")
-        lay = kc.keyx_plan(max_w)
-        shape = (world, int(lay.n_regions), int(lay.seg_cap))
-        kx_send, kx_recv = ([torch.empty(shape, dtype=torch.int64, device="cuda") for _ in range(2)] for _ in range(2))
-        kx_cur, kx_rcur = ([torch.zeros(shape[:2], dtype=torch.int64, device="cuda") for _ in range(2)] for _ in range(2))
+        kx = sharding.KeyExchange(kc, world, max(max(c["n_bases"] - c["n_reads"] * (K - 1), 0) for c in ch), device="cuda")
+
+    record_bufs = {}
 
     def exchange():
         """hash-range all-to-all of pre-aggregated (k-mer, count) records (platanus_b_b200/sharding.py over NCCL)"""
-        nonlocal send_buf, recv_buf
-        cnt = kc.shard_send_counts(world).astype(np.int64)
-        rc = sharding.exchange_counts(torch.from_numpy(cnt).cuda()).cpu().numpy()
-        n_send, n_recv = int(cnt.sum()), int(rc.sum())
-        if send_buf is None or send_buf.shape[0] < n_send + 1:
-            send_buf = torch.empty((int(n_send * 1.2) + 1024, W + 1), dtype=torch.int64, device="cuda")
-        if recv_buf is None or recv_buf.shape[0] < n_recv + 1:
-            recv_buf = torch.empty((int(n_recv * 1.2) + 1024, W + 1), dtype=torch.int64, device="cuda")
-        kc.shard_pack_device(send_buf.data_ptr(), send_buf.shape[0])
-        got = sharding.exchange_records(send_buf, cnt.tolist(), rc.tolist(), recv_buf)
-        torch.cuda.current_stream().synchronize()
-        kc.shard_insert_device(got.data_ptr(), n_recv)
-        return n_send * (W + 1) * 8
+        return sharding.exchange_staged_records(kc, world, "cuda", record_bufs, torch.cuda.current_stream().synchronize)
 
     def step_keyx(resident: bool):
-        def partition(i, send, cur):
+        def partition(i, send_ptr, cur_ptr):
             c = ch[i]
             if resident:
-                kc.keyx_partition_device(d_bases.data_ptr() + c["b0"], c["d_offs"].data_ptr(), c["n_reads"], c["n_bases"],
-                                         send.data_ptr(), cur.data_ptr())
+                kc.keyx_partition_device(d_bases.data_ptr() + c["b0"], c["d_offs"].data_ptr(), c["n_reads"], c["n_bases"], send_ptr, cur_ptr)
             else:
-                kc.keyx_partition_ptr(h_bases.data_ptr() + c["b0"], c["h_offs"].data_ptr(), c["n_reads"], send.data_ptr(), cur.data_ptr())
+                kc.keyx_partition_ptr(h_bases.data_ptr() + c["b0"], c["h_offs"].data_ptr(), c["n_reads"], send_ptr, cur_ptr)
 
-        sharding.pipelined_key_exchange(len(ch), partition, lambda r, rc: kc.keyx_insert_device(r.data_ptr(), rc.data_ptr()),
-                                        kx_send, kx_cur, kx_recv, kx_rcur, torch.cuda.current_stream().synchronize)
-        sent = len(ch) * (world - 1) * int(lay.bytes_per_dest)
-        if sharding.any_rank_staged(int(kc.shard_send_counts(world).sum()), device="cuda"):
-            sent += exchange()                  # keys whose segment was full (a k-mer repeated millions of times)
-        return sent
+        return kx.step(len(ch), partition, torch.cuda.current_stream().synchronize)
 
     def step(resident: bool):
         kc.reset()

@@ -107,3 +107,49 @@ def chunk_read_ranges(offsets, n_chunks: int):
     cuts.append(n)
     cuts = sorted(set(min(max(x, 0), n) for x in cuts))
     return [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]]
+
+
+# ---- the two exchanges as whole steps around a KmerCounter (what bench.py runs per step; tests drive the same code) ----------
+
+def exchange_staged_records(kc, world: int, device=None, bufs: dict | None = None, sync=None, group=None) -> int:
+    """Record exchange after counting: all-to-all of the pre-aggregated (key, count) records a sharded KmerCounter staged
+    (pbk_shard_send_counts / pack_device / insert_device).  Returns the bytes this rank sent."""
+    import numpy as np
+    bufs = bufs if bufs is not None else {}
+    W = kc.words
+    cnt = kc.shard_send_counts(world).astype(np.int64)
+    rc = exchange_counts(torch.from_numpy(cnt).to(device) if device is not None else torch.from_numpy(cnt), group=group).cpu().numpy()
+    n_send, n_recv = int(cnt.sum()), int(rc.sum())
+    for name, need in (("send", n_send), ("recv", n_recv)):
+        if bufs.get(name) is None or bufs[name].shape[0] < need + 1:
+            bufs[name] = torch.empty((int(need * 1.2) + 1024, W + 1), dtype=torch.int64, device=device)
+    kc.shard_pack_device(bufs["send"].data_ptr(), bufs["send"].shape[0])
+    got = exchange_records(bufs["send"], cnt.tolist(), rc.tolist(), bufs["recv"], group=group)
+    if sync is not None:
+        sync()
+    kc.shard_insert_device(got.data_ptr(), n_recv)
+    return n_send * (W + 1) * 8
+
+
+class KeyExchange:
+    """Key exchange before counting (pbk_keyx_*) for one sharded KmerCounter: layout agreed between the ranks, double-buffered
+    send / receive tensors, and the chunked, overlapped step."""
+
+    def __init__(self, kc, world: int, max_windows_per_chunk: int, device=None, group=None):
+        self.kc, self.world, self.device, self.group = kc, world, device, group
+        self.lay = kc.keyx_plan(max_windows_any_rank(max_windows_per_chunk, device=device, group=group))
+        shape = (world, int(self.lay.n_regions), int(self.lay.seg_cap))
+        mk = lambda shp, zero: [(torch.zeros if zero else torch.empty)(shp, dtype=torch.int64, device=device) for _ in range(2)]
+        self.send, self.recv = mk(shape, False), mk(shape, False)
+        self.cur, self.rcur = mk(shape[:2], True), mk(shape[:2], True)
+        self.record_bufs: dict = {}
+
+    def step(self, n_chunks: int, partition_chunk, sync) -> int:
+        """partition_chunk(i, d_send_ptr, d_cursors_ptr) runs pbk_keyx_partition* for chunk i.  Returns the bytes sent."""
+        pipelined_key_exchange(n_chunks, lambda i, s, c: partition_chunk(i, s.data_ptr(), c.data_ptr()),
+                               lambda r, rc: self.kc.keyx_insert_device(r.data_ptr(), rc.data_ptr()),
+                               self.send, self.cur, self.recv, self.rcur, sync, group=self.group)
+        sent = n_chunks * (self.world - 1) * int(self.lay.bytes_per_dest)
+        if any_rank_staged(int(self.kc.shard_send_counts(self.world).sum()), device=self.device, group=self.group):
+            sent += exchange_staged_records(self.kc, self.world, self.device, self.record_bufs, sync, self.group)
+        return sent

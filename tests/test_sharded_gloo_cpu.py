@@ -214,3 +214,71 @@ def test_two_rank_key_exchange_over_gloo(oracle, k, seg_cap, tmp_path):
     world = 2
     mp.spawn(_keyx_worker, args=(world, _free_port(), k, fq, seg_cap, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def _abi_worker(rank, world, port, k, mode, n_chunks, out_dir):
+    """Both exchanges as bench.py runs them (sharding.KeyExchange.step / sharding.exchange_staged_records) around a real
+    sharded KmerCounter -- the C ABI compiled for the host (tests/cpu_emul/cuda_rt_shim.h), so a torch CPU tensor's
+    data_ptr() is a valid "device" pointer -- over gloo."""
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import emul_helper
+    from platanus_b_b200 import build
+    build.LIB = emul_helper.abi_lib_path()
+    import ctypes as C
+
+    from oracle import oracle as O
+    from platanus_b_b200 import KmerCounter, capi, sharding, synth
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = capi.load_library()
+        rs = synth.make_reads(synth.config("C1", scale=1 / 400))
+        bases, offs = rs.flat()
+        rd = O.Reads()
+        rd.add_array(bases, offs)
+        want = O.count(rd, k)
+        n = len(offs) - 1
+        lo, hi = n * rank // world, n * (rank + 1) // world
+        b = np.ascontiguousarray(bases[int(offs[lo]):int(offs[hi])])
+        o = (offs[lo:hi + 1] - offs[lo]).astype(np.uint64)
+        with KmerCounter(k, n_shards=world, shard_rank=rank) as kc:
+            for rep in range(2):                                    # second pass: reset, tables and layout reused
+                kc.reset()
+                if mode == "keys":
+                    ranges = sharding.chunk_read_ranges(o, n_chunks)
+                    n_ch = sharding.max_windows_any_rank(len(ranges))
+                    ranges += [(len(o) - 1, len(o) - 1)] * (n_ch - len(ranges))
+                    chunks = [(np.ascontiguousarray(b[int(o[r0]):int(o[r1])]), (o[r0:r1 + 1] - o[r0]).astype(np.uint64)) for r0, r1 in ranges]
+                    kx = sharding.KeyExchange(kc, world, max(max(int(co[-1]) - (len(co) - 1) * (k - 1), 0) for _, co in chunks))
+                    sent = kx.step(len(chunks), lambda i, sp, cp: kc.keyx_partition(chunks[i][0], chunks[i][1], sp, cp), lambda: None)
+                else:
+                    kc.push_reads(b, o)
+                    sent = sharding.exchange_staged_records(kc, world)
+                assert sent > 0
+                kc.finalize()
+                hist = torch.from_numpy(kc.occ_hist.astype(np.int64))
+                sharding.allreduce_histogram(hist)
+                assert np.array_equal(hist.numpy().astype(np.uint64), want.occ_hist)
+                keys, counts = kc.export(1, sorted=True)
+                sel = np.array([L.pbk_shard_of_key(np.ascontiguousarray(r).ctypes.data_as(C.c_void_p), k, world) == rank
+                                for r in want.keys], dtype=bool)
+                assert np.array_equal(keys, want.keys[sel]) and np.array_equal(counts, want.counts[sel])
+                inst = torch.tensor([kc.n_instances], dtype=torch.int64)
+                dist.all_reduce(inst)
+                assert int(inst.item()) == want.n_instances
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("k,mode,n_chunks", [(32, "keys", 3), (32, "records", 1), (75, "records", 1)])
+def test_two_rank_exchanges_through_the_c_abi(oracle, k, mode, n_chunks, tmp_path):
+    import emul_helper
+    emul_helper.abi_lib_path()                               # build once, before the workers race for it
+    world = 2
+    mp.spawn(_abi_worker, args=(world, _free_port(), k, mode, n_chunks, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
