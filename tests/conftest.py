@@ -16,6 +16,7 @@ def _use_emulated_abi():
     import emul_helper
     from platanus_b_b200 import build
     build.LIB = emul_helper.abi_lib_path()
+    build.build_cli = lambda force=False: emul_helper.abi_cli_path()      # pbk_assemble linked against the same library
 
 
 def pytest_configure(config):

@@ -206,3 +206,22 @@ def abi_lib_path() -> str:
         objs.append(obj)
     subprocess.run(["g++", "-shared", "-o", ABI_OUT, *objs, "-lpthread"], check=True)
     return ABI_OUT
+
+
+def abi_cli_path() -> str:
+    """pbk_assemble (platanus_b_b200/host) linked against the emulated libpbk: the C++ host side end to end on CPU."""
+    lib = abi_lib_path()
+    build = os.path.join(os.path.dirname(lib), "cli")
+    os.makedirs(build, exist_ok=True)
+    link = os.path.join(build, "libpbk.so")
+    if not os.path.exists(link) or os.path.getmtime(link) < os.path.getmtime(lib):
+        import shutil
+        shutil.copyfile(lib, link)
+    host = os.path.join(os.path.dirname(HERE), "platanus_b_b200", "host")
+    srcs = [os.path.join(host, f) for f in ("pbk_assemble.cpp", "pbk_counter.hpp", "pbk_ingest.hpp")]
+    exe = os.path.join(build, "pbk_assemble")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(x) for x in srcs + [link]):
+        env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+        subprocess.run(["g++", "-O2", "-std=c++11", "-Wall", "-Wextra", "-pthread", "-o", exe, srcs[0], "-L" + build, "-lpbk",
+                        "-Wl,-rpath,$ORIGIN"], check=True, env=env)
+    return exe

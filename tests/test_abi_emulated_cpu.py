@@ -1,7 +1,8 @@
 """The host logic of the C ABI (platanus_b_b200/csrc/pbk_api.cu: batching, table sizing and growth, overflow handling,
 sharding, key exchange, lookup, seeded counting) checked in the GPU-less build container: the product sources are
 compiled for the host against a synchronous stand-in for the CUDA runtime (tests/cpu_emul/cuda_rt_shim.h, kernels run as
-one sequential thread), and the `-m gpu` tests of the listed files run against that library in a child pytest.
+one sequential thread), and the `-m gpu` tests of the listed files run against that library in a child pytest -- including the
+C++ program pbk_assemble (linked against the same library) against the unmodified reference program.
 
 This is a logic check only -- never shipped, never timed, and no fallback: the product library has no path to it.  The real
 parity tests are the same test functions run on a B200."""
@@ -36,7 +37,8 @@ def test_emulated_abi_builds_and_exports_the_abi():
     ["tests/test_zz_lookup_gpu.py"],
     ["tests/test_gpu_parity.py", "-k", "golden_cases and (kat_k4 or smallfq_k32 or smallfq_k75 or smallfa_k200 or cov_k21_auto or multi_k32_n2 or sat_k32)"],
     ["tests/test_gpu_parity.py", "-k", "table_growth or error_behaviour or pipelined_pass_overlap"],
-], ids=["key_exchange", "lookup_and_iterative_k", "golden_cases", "sharding_growth_errors"])
+    ["tests/test_cli_gpu.py"],
+], ids=["key_exchange", "lookup_and_iterative_k", "golden_cases", "sharding_growth_errors", "pbk_assemble_vs_reference_program"])
 def test_gpu_tests_pass_against_the_emulated_abi(selection):
     p = run_child(selection, timeout=1500)
     tail = "\n".join(p.stdout.splitlines()[-25:])
