@@ -119,3 +119,31 @@ def test_iterative_k_steps_match_the_reference(oracle, path):
             plain = O.count(rd, k)
             keys, counts = kc.export(1, sorted=True)
             assert np.array_equal(keys, plain.keys) and np.array_equal(counts, plain.counts)
+
+
+@pytest.mark.parametrize("k,n_shards", [(32, 2), (75, 3)])
+def test_lookup_and_seeds_with_hash_range_shards(oracle, k, n_shards):
+    """Sharded contexts keep only the entries they own (pbk_load_entries / pbk_seed_entries filter by pbk_shard_of_key), so
+    the per-shard lookups of one sequence set add up to the unsharded answer, and the seeded tables partition the seeded count."""
+    O = oracle
+    g = np.load(ITER_CASES[1] if k == 32 else ITER_CASES[3], allow_pickle=False)
+    assert int(g["k"]) == k
+    rd = iter_reads(O, g)
+    bases, offs = rd.arrays()
+    want_occ = O.occurrence_array(rd, k, g["table_keys"], g["table_counts"])
+    total = np.zeros(len(bases), np.uint32)
+    keys_all, counts_all = [], []
+    for r in range(n_shards):
+        with KmerCounter(k, n_shards=n_shards, shard_rank=r) as kc:
+            kc.load_entries(g["table_keys"], g["table_counts"])
+            total += kc.lookup(bases, offs)
+        with KmerCounter(k, n_shards=n_shards, shard_rank=r) as kc:
+            kc.seed_entries(g["table_keys"], g["table_counts"])
+            kc.finalize()                                            # seeds alone: a contig-seeded table without reads
+            kk, cc = kc.export(1, sorted=True)
+            keys_all.append(kk); counts_all.append(cc)
+    assert np.array_equal(total.astype(np.uint16), want_occ)
+    keys = np.concatenate(keys_all); counts = np.concatenate(counts_all)
+    W = (k + 31) // 32
+    order = np.lexsort(tuple(keys[:, w] for w in range(W)))
+    assert np.array_equal(keys[order], g["table_keys"]) and np.array_equal(counts[order], g["table_counts"])
