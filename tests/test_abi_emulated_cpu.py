@@ -17,8 +17,12 @@ ROOT = os.path.dirname(HERE)
 
 
 def run_child(args, timeout):
+    import emul_helper
+    emul_helper.abi_lib_path()                       # built here, once: the child's workers only find them up to date
+    emul_helper.abi_cli_path()
     env = dict(os.environ, PBK_TEST_EMULATED_ABI="1")
-    return subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "--runxfail", "-p", "no:cacheprovider", "-x", *args],
+    workers = ["-n", str(min(4, os.cpu_count() or 1))] if (os.cpu_count() or 1) >= 4 else []      # pytest-xdist: the cases are independent
+    return subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "--runxfail", "-p", "no:cacheprovider", "-x", *workers, *args],
                           cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
 
 
