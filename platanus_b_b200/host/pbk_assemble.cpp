@@ -158,12 +158,12 @@ private:
 struct BatchSink : ReadSink {
     BatchQueue &q; Batch *cur;
     explicit BatchSink(BatchQueue &q_) : q(q_), cur(q_.get_free()) {}
-    void emit()
+    void emit_span(const char *s, size_t len)
     {
-        if (read.size() >= 500000) throw pbk::ReadError();                  // common.h:465
-        if (cur->used + read.size() > cur->cap) { q.put_full(cur); cur = q.get_free(); }
-        memcpy(cur->bases + cur->used, read.data(), read.size());
-        cur->used += read.size();
+        if (len >= 500000) throw pbk::ReadError();                          // common.h:465
+        if (cur->used + len > cur->cap) { q.put_full(cur); cur = q.get_free(); }
+        memcpy(cur->bases + cur->used, s, len);
+        cur->used += len;
         cur->offsets.push_back(cur->used);
     }
     void finish() { q.put_full(cur); cur = NULL; }
@@ -176,17 +176,17 @@ struct SeqTmpSink : ReadSink {
     std::vector<int32_t> pos;
     std::string codes;
     explicit SeqTmpSink(std::vector<FILE *> &fp_) : fp(fp_), i(0) {}
-    void emit()
+    void emit_span(const char *rd, size_t rd_len)
     {
-        if (read.size() >= 500000) throw pbk::ReadError();                  // common.h:465
+        if (rd_len >= 500000) throw pbk::ReadError();                  // common.h:465
         static const char code[] = ".\x0.\x1\x3..\x2......\x4";               // platanus::Char2Bin (common.h:256)
         pos.clear();
-        codes.resize(read.size());
-        for (size_t j = 0; j < read.size(); ++j) {
-            const char c = code[read[j] & 0xF];
+        codes.resize(rd_len);
+        for (size_t j = 0; j < rd_len; ++j) {
+            const char c = code[rd[j] & 0xF];
             if (c == 4) { pos.push_back((int32_t)j); codes[j] = 0; } else codes[j] = c;
         }
-        const int32_t nn = (int32_t)pos.size(), len = (int32_t)read.size();
+        const int32_t nn = (int32_t)pos.size(), len = (int32_t)rd_len;
         fwrite(&nn, 4, 1, fp[i]);
         if (nn) fwrite(pos.data(), 4, (size_t)nn, fp[i]);
         fwrite(&len, 4, 1, fp[i]);

@@ -129,8 +129,10 @@ struct ReadSink {
     std::string read;                    // the read being assembled from lines
     virtual ~ReadSink() {}
     void append(const Line &l) { read.append(l.s, l.len); }
-    void flush() { emit(); read.clear(); }
-    virtual void emit() = 0;             // consume `read` (implementations throw on length >= MAX_READ_LEN, common.h:465)
+    void flush() { emit_span(read.data(), read.size()); read.clear(); }
+    // consume one read (implementations throw on length >= MAX_READ_LEN, common.h:465).  Single-line records -- the usual
+    // FASTQ -- are handed over straight from the mapped file, without a detour through `read`.
+    virtual void emit_span(const char *s, size_t len) = 0;
 };
 
 // offset of the first line that starts at or after `from` and begins with `mark`; n if there is none
@@ -159,21 +161,34 @@ inline void parse_range(const char *p, size_t s_begin, size_t s_end, bool fastq,
     LineReader r(p + s_begin, s_end - s_begin);
     Line l;
     bool flag = true;
+    // `early`: the record in progress was a single line whose end was in sight (the next line closes it: '+' in FASTQ,
+    // a header in FASTA), so it has been emitted already and `read` stays empty until the next header.  The reference
+    // would emit it at that header, or at the end of the file: same reads, same order.
+    bool early = false;
     while (r.next(l)) {
         if (fastq) {
             if (l.len == 0) continue;                                   // assemble.cpp:922
             if (l.s[0] != mark) {
-                if (flag && l.s[0] != '+') out.append(l); else flag = false;
+                if (flag && l.s[0] != '+') {
+                    // (after an early emit the next line starts with '+' and clears `flag`: no line is appended while `early`)
+                    if (out.read.empty() && r.cur < r.end && *r.cur == '+') { out.emit_span(l.s, l.len); early = true; }
+                    else out.append(l);
+                } else flag = false;
             } else {
                 if (!out.read.empty()) out.flush();
-                flag = true;
+                flag = true; early = false;
             }
         } else {
-            if (!(l.len && l.s[0] == mark)) out.append(l);
-            else if (!out.read.empty()) out.flush();
+            if (!(l.len && l.s[0] == mark)) {
+                if (out.read.empty() && l.len && r.cur < r.end && *r.cur == mark) { out.emit_span(l.s, l.len); early = true; }
+                else out.append(l);
+            } else {
+                if (!out.read.empty()) out.flush();
+                early = false;
+            }
         }
     }
-    if (final_flush) out.flush();                                       // also when the read is empty
+    if (final_flush) { if (!early) out.flush(); }                       // also when the read is empty (assemble.cpp:844-845, 938-939)
     else if (!out.read.empty()) out.flush();                            // what the next worker's header line would do
 }
 

@@ -8,7 +8,7 @@
 #include <vector>
 
 struct PrintSink : pbk::ingest::ReadSink {
-    void emit() { fwrite(read.data(), 1, read.size(), stdout); fputc('\n', stdout); }
+    void emit_span(const char *s, size_t len) { fwrite(s, 1, len, stdout); fputc('\n', stdout); }
 };
 
 int main(int argc, char **argv)
