@@ -11,7 +11,7 @@
  *
  * The reference has no FFI layer: the seam is the header-only template
  * Counter<KMER>.  The host C++ shim that re-implements those member functions on top of this ABI
- * is platanus_b_b200/host/pbk_counter_shim.h; INTEGRATION.md shows how a maintainer wires it in.
+ * is platanus_b_b200/host/pbk_counter.hpp; INTEGRATION.md shows how a maintainer wires it in.
  *
  * Conventions: plain C types only; every function returns 0 (PBK_OK) or a negative pbk_status;
  * no exceptions cross the boundary; the caller owns every host buffer it passes in; the context

@@ -48,3 +48,12 @@ def test_gpu_tests_pass_against_the_emulated_abi(selection):
     tail = "\n".join(p.stdout.splitlines()[-25:])
     assert p.returncode == 0, tail + "\n" + p.stderr[-2000:]
     assert " passed" in tail and "failed" not in tail, tail
+
+
+def test_short_differential_fuzz_of_the_emulated_abi():
+    """scripts/fuzz_emulated_abi.py for 20 s: random read sets and k, every counting route, seeded counting, lookup, both
+    sharded exchanges -- the C ABI compiled for the host against the oracle."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fuzz_emulated_abi.py"), "--seconds", "20", "--seed", "3"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-1500:]
+    assert "cases ok" in p.stdout
