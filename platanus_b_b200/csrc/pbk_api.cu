@@ -82,6 +82,8 @@ struct pbk_ctx {
     u64 *d_len_scratch = nullptr; Counters *d_ctr_scratch = nullptr;     // pbk_lookup: its reads must not enter the histograms
     std::vector<u64> seed_rec;                                           // pbk_seed_entries: (key words, value) records, applied by pbk_finalize
     PartitionPlan keyx_plan{}; u64 keyx_max_windows = 0;
+    u64 keyx_last_total = 0;            // keys received by the last host-sized insert: sizes the table for the queued ones
+    bool counters_pending = false;      // a queued key-exchange insert has not had its counters read back yet (settle())
     u64 *keyx_send = nullptr, *keyx_cursors = nullptr;
 
     bool finalized = false;
@@ -289,6 +291,16 @@ int drain_overflow(pbk_ctx *c)
     return PBK_OK;
 }
 
+// pbk_keyx_insert_device may queue its launches and return (no host round trip per received chunk); whoever needs the
+// host's view of the table (occupancy, staged records, the overflow list) calls this first
+int settle(pbk_ctx *c)
+{
+    if (!c->counters_pending) return PBK_OK;
+    c->counters_pending = false;
+    TRY(read_counters(c));
+    return drain_overflow(c);
+}
+
 int maybe_clamp(pbk_ctx *c, u64 upcoming)
 {
     if (c->inst_since_clamp + upcoming < U32_HEADROOM) return PBK_OK;
@@ -494,6 +506,7 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
     if (c->finalized) return fail(c, PBK_E_STATE, "pbk_push_reads after pbk_finalize (call pbk_reset first)");
     if (n_reads == 0) return PBK_OK;
     CK(cudaSetDevice(c->device));
+    if (!c->keyx_send) TRY(settle(c));              // (a key-exchange partition only runs Pass A; its own read-back at the end settles)
     c->stage_gen += 1;
     if (c->remote_dirty) { Span sp(c, LC_OTHER); launch_table_init(c->remote, c->s_compute); c->remote_dirty = false; }
     TRY(ensure_batch_buffers(c, n_bases, n_reads));
@@ -621,6 +634,7 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
         // keys that found their segment full (a heavily repeated k-mer), which take the record route (remote-staging
         // table -> pbk_shard_pack_device) to their owner
         CK(cudaGetLastError());
+        c->counters_pending = false;                    // the read-back below also covers a queued pbk_keyx_insert_device
         TRY(read_counters(c));
         TRY(drain_overflow(c));
     } else if (pipe.on) {
@@ -825,6 +839,7 @@ int pbk_finalize(pbk_ctx *c, uint64_t *occ_hist, uint64_t *len_hist, uint64_t *n
 {
     if (!c) return PBK_E_ARG;
     CK(cudaSetDevice(c->device));
+    TRY(settle(c));
     if (c->shard.n_shards > 1 && c->occupied_remote > 0)
         return fail(c, PBK_E_STATE, "%llu staged records have not been exchanged (pbk_shard_pack_device)", (unsigned long long)c->occupied_remote);
     if (!c->seed_rec.empty()) TRY(apply_seeds(c));
@@ -895,6 +910,7 @@ int pbk_get_stats(const pbk_ctx *cc, pbk_stats *out)
     pbk_ctx *c = const_cast<pbk_ctx *>(cc);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->s_compute);
+    if (settle(c) != PBK_OK) return PBK_E_CUDA;
     resolve_spans(c);
     memset(out, 0, sizeof(*out));
     out->n_reads = c->n_reads; out->n_bases = c->n_bases; out->n_instances = c->last.instances;
@@ -945,6 +961,7 @@ int pbk_reset(pbk_ctx *c, uint32_t k)
     if (k > PBK_MAX_K) return PBK_E_UNSUPPORTED_K;
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->s_compute));
+    c->counters_pending = false;                       // whatever was queued is about to be forgotten
     const int W = (int)((k + 31) / 32);
     if (W != c->W) {                                   // slot size changes: tables are re-created lazily
         if (c->table.slots) dev_free(c, c->table.slots, c->table.bytes());
@@ -974,6 +991,7 @@ uint32_t pbk_shard_record_bytes(const pbk_ctx *c) { return c ? (uint32_t)((c->W 
 int pbk_shard_send_counts(pbk_ctx *c, uint64_t *counts)
 {
     if (!c || !counts) return PBK_E_ARG;
+    TRY(settle(c));
     const u32 n = c->shard.n_shards;
     if (c->shard_counts_gen == c->stage_gen && c->h_shard_counts.size() == n) {    // nothing staged since the last scan
         memcpy(counts, c->h_shard_counts.data(), n * 8);
@@ -1031,6 +1049,7 @@ int pbk_shard_insert_device(pbk_ctx *c, const void *d_records, uint64_t n_record
 static int insert_records_device(pbk_ctx *c, const void *d_records, uint64_t n_records)
 {
     CK(cudaSetDevice(c->device));
+    TRY(settle(c));
     TRY(ensure_tables(c, n_records, false));
     const ShardInfo local{1, 0};                      // received records are owned by this shard
     for (u64 at = 0; at < n_records; at += CHUNK_BASES) {
@@ -1095,6 +1114,7 @@ static int lookup_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_ba
                          const u64 *n_pos_offsets, uint16_t *h_out, uint16_t *d_out, uint8_t *h_match = nullptr)
 {
     CK(cudaSetDevice(c->device));
+    TRY(settle(c));
     if (n_bases > MAX_PUSH_BASES) return fail(c, PBK_E_ARG, "pbk_lookup takes at most %llu bases per call", (unsigned long long)MAX_PUSH_BASES);
     if (h_match) memset(h_match, 0, n_reads);
     else if (h_out) memset(h_out, 0, n_bases * 2);
@@ -1306,6 +1326,28 @@ int pbk_keyx_insert_device(pbk_ctx *c, const void *d_recv, const void *d_recv_cu
     const u32 G = c->shard.n_shards, n_desc = c->keyx_plan.n_buckets, R = n_desc / G;
     const u64 seg_cap = c->keyx_plan.seg_cap;
     TRY(ensure_passb_buffers(c));
+    // Steady state (an earlier insert of this context measured how many of the received keys are new and how many arrive):
+    // size the table from that, build the tile map on the device, queue Pass B and return -- no host round trip per
+    // received chunk.  A table that turns out too small only costs the overflow route (settle()).  PBK_KEYX_SYNC=1 keeps
+    // the host-sized path below.
+    static const bool always_sync = getenv("PBK_KEYX_SYNC") != nullptr;
+    if (c->ratio_known && c->keyx_last_total && c->table.slots && c->pipeline_enabled && !always_sync) {
+        const u64 expect = (u64)(c->keyx_last_total * std::min(1.0, c->new_ratio * 1.15)) + 65536;
+        TRY(settle(c));                                 // c->occupied up to date before the growth decision
+        TRY(maybe_clamp(c, c->keyx_last_total + c->keyx_last_total / 8));
+        if ((double)(c->occupied + expect) > max_load(c) * (double)c->table.capacity())
+            TRY(grow_table(c, &c->table, c->occupied, (u64)((c->occupied + expect) / max_load(c)) + 1));
+        TRY(ensure_overflow(c, 1ull << 22));
+        {
+            Span sp(c, LC_INSERT);
+            launch_bucket_insert_gathered_chained((const u64 *)d_recv, (const u64 *)d_recv_cursors, seg_cap, c->d_passb, G, R, c->table,
+                                                  c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+        }
+        CK(cudaGetLastError());
+        c->counters_pending = true;
+        c->n_pipelined += 1;
+        return PBK_OK;
+    }
     // fill counts, [source][region] -> descriptor order [region][source]
     CK(cudaMemcpyAsync(c->h_bkt_cursor, d_recv_cursors, (size_t)n_desc * 8, cudaMemcpyDeviceToHost, c->s_compute));
     CK(cudaStreamSynchronize(c->s_compute));
@@ -1358,6 +1400,7 @@ int pbk_keyx_insert_device(pbk_ctx *c, const void *d_recv, const void *d_recv_cu
     if (total > 4096) {
         c->new_ratio = std::max(0.01, std::min(1.0, (double)(c->occupied - occ_before) / (double)total));
         c->ratio_known = true;
+        c->keyx_last_total = total;
     }
     return PBK_OK;
 }

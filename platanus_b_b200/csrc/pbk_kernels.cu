@@ -306,6 +306,24 @@ void launch_bucket_insert_gathered(const u64 *recv_keys, u64 seg_cap, const u64 
         t, t, 1, 0, ctr, overflow_keys, overflow_cap, opts);
 }
 
+// the same without a host round trip: tile map built on the device from the received cursors, Pass B right behind it
+void launch_bucket_insert_gathered_chained(const u64 *recv_keys, const u64 *d_recv_cursors, u64 seg_cap, void *d_desc, u32 n_src,
+                                           u32 n_regions, TableView table, Counters *ctr, u64 *overflow_keys, u64 overflow_cap,
+                                           int sm_count, cudaStream_t st)
+{
+    if (table.words != 1) return;
+    const int pf_dist = getenv("PBK_PF_DIST") ? atoi(getenv("PBK_PF_DIST")) : 1;
+    const u32 n_desc = n_src * n_regions;
+    passb_desc_gather_kernel<<<1, PART_MAX_BUCKETS, 0, st>>>(d_recv_cursors, seg_cap, n_src, n_regions, (u32)PASSB1_TILE_KEYS,
+        (const char *)table.slots, table.cap, (u32)table.slot_bytes(), pf_dist, (u64 *)d_desc, (PassBBucket *)((char *)d_desc + 16));
+    const PassBBucket *d_bk = (const PassBBucket *)((const char *)d_desc + 16);
+    const int ctas = getenv("PBK_PASSB_CTAS") ? atoi(getenv("PBK_PASSB_CTAS")) : 3;
+    const u32 opts = (getenv("PBK_PASSB_HINT") ? ((u32)atoi(getenv("PBK_PASSB_HINT")) & 0xFFu) : 1u) | (n_src << 8) | (n_regions << 16);
+    const Table<1> t(table.slots, table.cap);
+    bucket_insert_compact_kernel<2><<<sm_count * ctas, PASSB_THREADS, 0, st>>>(recv_keys, seg_cap, d_bk, 0, n_desc, (u64 *)d_desc,
+        t, t, 1, 0, ctr, overflow_keys, overflow_cap, opts);                  // CTAs that find no tile left leave at once
+}
+
 // device-chained variant for k <= 32: tile map built by a kernel from the cursors, Pass B launched on `st_insert`
 // right behind it (the caller orders the two streams with events)
 void launch_passb_desc(const u64 *d_cursor, u64 seg_cap, u32 n_buckets, TableView table, TableView remote, ShardInfo shard,

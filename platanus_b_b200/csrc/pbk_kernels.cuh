@@ -70,6 +70,9 @@ PartitionPlan plan_partition_keyx(u32 n_dest, u64 max_windows_any_rank, int word
 void launch_bucket_insert_gathered(const u64 *recv_keys, u64 seg_cap, const u64 *counts, void *h_desc, void *d_desc,
                                    u32 d_first, u32 d_end, u32 n_src, u32 n_regions, TableView table, Counters *ctr,
                                    u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st);
+void launch_bucket_insert_gathered_chained(const u64 *recv_keys, const u64 *d_recv_cursors, u64 seg_cap, void *d_desc, u32 n_src,
+                                           u32 n_regions, TableView table, Counters *ctr, u64 *overflow_keys, u64 overflow_cap,
+                                           int sm_count, cudaStream_t st);
 // Pass B over buckets [b_first, b_end) in one launch.  `h_desc` is scratch for b_end - b_first + 1 bucket
 // descriptors (pinned host memory), `d_desc` the same on the device; `counts[b]` = keys in bucket b.
 size_t passb_desc_bytes(u32 n_buckets);

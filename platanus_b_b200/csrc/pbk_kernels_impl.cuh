@@ -808,6 +808,40 @@ passb_desc_kernel(const u64 *__restrict__ cursor, u64 seg_cap, u32 n_buckets, u3
     }
 }
 
+// Tile map for Pass B in gather mode (key exchange): descriptor i = (table region i / n_src, source i % n_src), its fill
+// count is cursor[source][region] of the all-to-all receive buffer.  Built on the device so that a received chunk can be
+// inserted without a host round trip.
+__global__ void __launch_bounds__(PART_MAX_BUCKETS)
+passb_desc_gather_kernel(const u64 *__restrict__ recv_cursor, u64 seg_cap, u32 n_src, u32 n_regions, u32 tile_keys, const char *tab,
+                         u64 tab_cap, u32 slot_bytes, int pf_dist, u64 *ticket, PassBBucket *out)
+{
+    __shared__ u64 s_tiles[PART_MAX_BUCKETS + 1];
+    const u32 n_desc = n_src * n_regions;
+    for (u32 i = threadIdx.x; i < n_desc; i += blockDim.x) {
+        const u64 n = min(recv_cursor[(i % n_src) * n_regions + i / n_src], seg_cap);
+        PassBBucket d;
+        d.tile_start = 0; d.n_keys = n;
+        d.pf_base = d.pf_base2 = nullptr; d.pf_lines = d.pf_lines2 = 0;
+        if (pf_dist > 0 && n) passb_region(tab, tab_cap, slot_bytes, i + (u32)pf_dist * n_src, n_desc, &d.pf_base, &d.pf_lines);
+        out[i] = d;
+        s_tiles[i] = (n + tile_keys - 1) / tile_keys;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 tiles = 0;
+        for (u32 i = 0; i < n_desc; ++i) { const u64 t = s_tiles[i]; s_tiles[i] = tiles; tiles += t; }
+        s_tiles[n_desc] = tiles;
+        ticket[0] = 0; ticket[1] = 0;
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < n_desc; i += blockDim.x) out[i].tile_start = s_tiles[i];
+    if (threadIdx.x == 0) {
+        PassBBucket e;
+        e.tile_start = s_tiles[n_desc]; e.n_keys = 0; e.pf_base = e.pf_base2 = nullptr; e.pf_lines = e.pf_lines2 = 0;
+        out[n_desc] = e;
+    }
+}
+
 // Pass B for one-word keys (k <= 32).  The bucket store holds h = fmix64(key), so a key costs one
 // streamed 8-byte load, one 64-bit atomic add on its home slot and a three-instruction test of the
 // returned word.  What does not finish there -- the home slot belongs to another key, or it is claimed

@@ -259,6 +259,8 @@ def _abi_worker(rank, world, port, k, mode, n_chunks, out_dir):
                     kc.push_reads(b, o)
                     sent = sharding.exchange_staged_records(kc, world)
                 assert sent > 0
+                if mode == "keys" and rep == 1:                     # steady state: received chunks are inserted without a host round trip
+                    assert kc.stats()["n_pipelined_batches"] >= 1
                 kc.finalize()
                 hist = torch.from_numpy(kc.occ_hist.astype(np.int64))
                 sharding.allreduce_histogram(hist)
