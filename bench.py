@@ -422,6 +422,14 @@ def main_ours(args):
         if base is not None:
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
+    if args.write_outputs:                      # the sharded count's files, as the single-GPU program writes them (untimed)
+        step(True)
+        if world > 1:
+            sharding.write_outputs(kc, args.write_outputs, K, world, rank, 16 * 10 ** 9, device="cuda")
+        else:
+            kc.output_occurrence_distribution(f"{args.write_outputs}_{K}merFrq.tsv")
+            kc.output_occurrence_table_binary(f"{args.write_outputs}_kmer_occ.bin", kc.coverage_cutoff(),
+                                              int(kc._L.pbk_double_hash_size(16 * 10 ** 9, K)))
     kc.close()
     if world > 1:
         dist.barrier()
@@ -436,6 +444,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C1")
+    ap.add_argument("--write-outputs", default="", metavar="PREFIX",
+                    help="after the timed steps: write PREFIX_<k>merFrq.tsv and PREFIX_kmer_occ.bin of the (sharded) count, rank 0 (untimed)")
     ap.add_argument("--keyx-chunks", type=int, default=int(os.environ.get("PBK_BENCH_KEYX_CHUNKS", "4")),
                     help="--exchange keys: chunks per step (the all-to-all of one chunk overlaps the passes of its neighbours)")
     ap.add_argument("--exchange", default=os.environ.get("PBK_BENCH_EXCHANGE", "records"), choices=["records", "keys"],

@@ -153,3 +153,63 @@ class KeyExchange:
         if any_rank_staged(int(self.kc.shard_send_counts(self.world).sum()), device=self.device, group=self.group):
             sent += exchange_staged_records(self.kc, self.world, self.device, self.record_bufs, sync, self.group)
         return sent
+
+
+# ---- the outputs of a sharded count (collective 3) --------------------------------------------------
+
+def gather_sorted_entries(kc, min_count: int, world: int, rank: int, dst: int = 0, group=None, device=None):
+    """Every rank exports the entries it owns with count >= min_count (sorted by key on its GPU); rank `dst` receives them
+    all and merges them into ONE ascending list -- what sortedKeyFromKmerFile / loadKmer see in the single-process program
+    (counter.h:917-951, 600-640).  Shards are hash ranges, not key ranges, so a global merge is needed.
+    Returns (keys [n, W] uint64, counts [n] uint16) on `dst`, (None, None) elsewhere."""
+    import numpy as np
+    keys, counts = kc.export(min_count, sorted=True)
+    W = keys.shape[1] if keys.ndim == 2 else kc.words
+    # `device`: where the collective's tensors live ("cuda" under NCCL, None = host under gloo)
+    n_here = torch.tensor([len(counts)], dtype=torch.int64, device=device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, n_here, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    # (entries >= cutoff are on their way to a file; the table itself never leaves the GPUs)
+    payload = torch.from_numpy(np.concatenate([keys.reshape(-1).view(np.int64), counts.astype(np.int64)]) if len(counts) else np.zeros(0, np.int64)).to(device)
+    if rank == dst:
+        parts = [torch.zeros(s * (W + 1), dtype=torch.int64, device=device) for s in sizes]
+        reqs = [dist.irecv(parts[src], src=src, group=group) for src in range(world) if src != dst and sizes[src]]
+        parts[dst] = payload
+        for r in reqs:
+            r.wait()
+        parts = [p.cpu() for p in parts]
+        ks = [p.numpy()[:s * W].view(np.uint64).reshape(s, W) for p, s in zip(parts, sizes)]
+        cs = [p.numpy()[s * W:].astype(np.uint16) for p, s in zip(parts, sizes)]
+        allk, allc = np.concatenate(ks), np.concatenate(cs)
+        order = np.lexsort(tuple(allk[:, w] for w in range(W)))       # reference order: top word first (binstr.h:460-466)
+        return np.ascontiguousarray(allk[order]), np.ascontiguousarray(allc[order])
+    if len(counts):
+        dist.send(payload, dst=dst, group=group)
+    return None, None
+
+
+def write_outputs(kc, prefix: str, k: int, world: int, rank: int, memory_bytes: int, n_opt: int = 0, repeat: bool = False, group=None,
+                  device=None):
+    """PREFIX_<k>merFrq.tsv and PREFIX_kmer_occ.bin of a sharded count, written by rank 0 exactly as the single-GPU path
+    writes them (pbk_write_frq_tsv, pbk_write_kmer_occ_bin): all-reduced occurrence histogram -> cutoff (assemble.cpp:318-321)
+    -> merged entries >= cutoff.  Call after finalize() on every rank.  Returns the coverage cutoff."""
+    import ctypes as C
+
+    import numpy as np
+    L = kc._L
+    hist = torch.from_numpy(kc.occ_hist.astype(np.int64)).to(device)
+    allreduce_histogram(hist, group=group)
+    occ = np.ascontiguousarray(hist.cpu().numpy().astype(np.uint64))
+    nz = np.nonzero(occ[1:])[0]
+    max_occ = int(nz[-1]) + 1 if len(nz) else 0
+    cutoff = int(L.pbk_coverage_cutoff(occ.ctypes.data_as(C.c_void_p), max_occ, int(n_opt), int(repeat)))
+    keys, counts = gather_sorted_entries(kc, cutoff, world, rank, 0, group, device)
+    if rank == 0:
+        if L.pbk_write_frq_tsv(f"{prefix}_{k}merFrq.tsv".encode(), occ.ctypes.data_as(C.c_void_p), max_occ) != 0:
+            raise OSError(f"cannot write {prefix}_{k}merFrq.tsv")
+        dh = int(L.pbk_double_hash_size(int(memory_bytes), int(k)))
+        if L.pbk_write_kmer_occ_bin(f"{prefix}_kmer_occ.bin".encode(), int(k), keys.ctypes.data_as(C.c_void_p),
+                                    counts.ctypes.data_as(C.c_void_p), len(counts), dh, None) != 0:
+            raise OSError(f"cannot write {prefix}_kmer_occ.bin")
+    return cutoff

@@ -272,6 +272,16 @@ def _abi_worker(rank, world, port, k, mode, n_chunks, out_dir):
                 inst = torch.tensor([kc.n_instances], dtype=torch.int64)
                 dist.all_reduce(inst)
                 assert int(inst.item()) == want.n_instances
+            # the output files of the sharded count (rank 0): identical to what the unsharded oracle table gives
+            cutoff = sharding.write_outputs(kc, os.path.join(out_dir, "sh"), k, world, rank, 10 ** 9)
+            assert cutoff == O.coverage_cutoff(want.occ_hist, want.max_occ)
+            if rank == 0:
+                assert open(os.path.join(out_dir, f"sh_{k}merFrq.tsv")).read() == O.tsv_text(want.occ_hist, want.max_occ)
+                t = O.read_bin(os.path.join(out_dir, "sh_kmer_occ.bin"))
+                keep = want.counts >= cutoff
+                bk, bc = t.sorted_dump()
+                assert t.reachable and t.k == k and t.index_size == max(O.load_size(int(keep.sum())), O.double_hash_size(10 ** 9, k)) - 1
+                assert np.array_equal(bk, want.keys[keep]) and np.array_equal(bc, want.counts[keep])
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
