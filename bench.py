@@ -285,11 +285,14 @@ def main_ours(args):
         def partition(i, send_ptr, cur_ptr):
             c = ch[i]
             if resident:
-                kc.keyx_partition_device(d_bases.data_ptr() + c["b0"], c["d_offs"].data_ptr(), c["n_reads"], c["n_bases"], send_ptr, cur_ptr)
+                (kc.keyx_partition_device_async if args.keyx_async else kc.keyx_partition_device)(
+                    d_bases.data_ptr() + c["b0"], c["d_offs"].data_ptr(), c["n_reads"], c["n_bases"], send_ptr, cur_ptr)
             else:
                 kc.keyx_partition_ptr(h_bases.data_ptr() + c["b0"], c["h_offs"].data_ptr(), c["n_reads"], send_ptr, cur_ptr)
 
-        return kx.step(len(ch), partition, torch.cuda.current_stream().synchronize)
+        ordered = args.keyx_async and resident         # chunks chained on the device: no host synchronisation inside the step
+        return kx.step(len(ch), partition, torch.cuda.current_stream().synchronize,
+                       caller_stream=(lambda: torch.cuda.current_stream().cuda_stream) if ordered else None)
 
     def step(resident: bool):
         kc.reset()
@@ -446,6 +449,8 @@ def main():
     ap.add_argument("--workload", default="C1")
     ap.add_argument("--write-outputs", default="", metavar="PREFIX",
                     help="after the timed steps: write PREFIX_<k>merFrq.tsv and PREFIX_kmer_occ.bin of the (sharded) count, rank 0 (untimed)")
+    ap.add_argument("--keyx-async", action="store_true", default=bool(os.environ.get("PBK_BENCH_KEYX_ASYNC")),
+                    help="--exchange keys: order Pass A -> all-to-all -> Pass B by CUDA events (pbk_stream_signal/wait) instead of host syncs")
     ap.add_argument("--keyx-chunks", type=int, default=int(os.environ.get("PBK_BENCH_KEYX_CHUNKS", "4")),
                     help="--exchange keys: chunks per step (the all-to-all of one chunk overlaps the passes of its neighbours)")
     ap.add_argument("--exchange", default=os.environ.get("PBK_BENCH_EXCHANGE", "records"), choices=["records", "keys"],

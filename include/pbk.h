@@ -211,6 +211,18 @@ int  pbk_keyx_partition(pbk_ctx *ctx, const uint8_t *bases, const uint64_t *read
                         void *d_send, void *d_cursors);
 int  pbk_keyx_partition_device(pbk_ctx *ctx, const void *d_bases, const void *d_read_offsets,
                                uint64_t n_reads, uint64_t n_bases, void *d_send, void *d_cursors);
+/* Device-side ordering between the context's compute stream and a stream of the caller (e.g. the one its
+ * collective library enqueues on), so that the steps above can be chained without host synchronisation:
+ *   pbk_stream_signal  the caller's stream waits for everything queued on the context so far
+ *   pbk_stream_wait    the context waits for everything queued on the caller's stream so far
+ * `stream` is a cudaStream_t passed as void* (torch: torch.cuda.current_stream().cuda_stream).
+ * pbk_keyx_partition_device_async is pbk_keyx_partition_device without the read-back at its end: it returns
+ * when its kernels are queued; error flags, the instance count and keys that found their segment full are
+ * picked up by the next call that needs the host's view (pbk_finalize, pbk_shard_send_counts, ...).   */
+int  pbk_stream_signal(pbk_ctx *ctx, void *stream);
+int  pbk_stream_wait(pbk_ctx *ctx, void *stream);
+int  pbk_keyx_partition_device_async(pbk_ctx *ctx, const void *d_bases, const void *d_read_offsets,
+                                     uint64_t n_reads, uint64_t n_bases, void *d_send, void *d_cursors);
 /* d_recv / d_recv_cursors: what the all-to-all delivered, [source rank][region][seg_cap] entries and
  * [source rank][region] fill counts                                                               */
 int  pbk_keyx_insert_device(pbk_ctx *ctx, const void *d_recv, const void *d_recv_cursors);

@@ -40,7 +40,7 @@ SYMBOLS = [
     "pbk_microbench_atomics", "pbk_timer_mark", "pbk_timer_elapsed_ms", "pbk_set_timing",
     "pbk_keyx_plan", "pbk_keyx_partition", "pbk_keyx_partition_device", "pbk_keyx_insert_device",
     "pbk_lookup", "pbk_lookup_device", "pbk_load_entries", "pbk_read_kmer_occ_bin", "pbk_free",
-    "pbk_match_reads", "pbk_seed_entries",
+    "pbk_match_reads", "pbk_seed_entries", "pbk_stream_signal", "pbk_stream_wait", "pbk_keyx_partition_device_async",
 ]
 
 
@@ -134,6 +134,9 @@ def load_library(build_if_missing: bool = True):
     L.pbk_keyx_partition.argtypes = [vp, vp, u64p, C.c_uint64, C.c_int, vp, u64p, vp, vp]
     L.pbk_keyx_partition_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, vp, vp]
     L.pbk_keyx_insert_device.argtypes = [vp, vp, vp]
+    L.pbk_keyx_partition_device_async.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, vp, vp]
+    L.pbk_stream_signal.argtypes = [vp, vp]
+    L.pbk_stream_wait.argtypes = [vp, vp]
     L.pbk_left_local_min.argtypes = [u64p, C.c_uint64, C.c_uint64]; L.pbk_left_local_min.restype = C.c_uint64
     L.pbk_coverage_cutoff.argtypes = [u64p, C.c_uint64, C.c_int, C.c_int]; L.pbk_coverage_cutoff.restype = C.c_uint64
     L.pbk_distribution_average.argtypes = [u64p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]
@@ -353,6 +356,20 @@ class KmerCounter:
         self._check(self._L.pbk_keyx_partition_device(self._ctx, C.c_void_p(d_bases_ptr), C.c_void_p(d_offsets_ptr), n_reads,
                                                       n_bases, C.c_void_p(d_send_ptr), C.c_void_p(d_cursors_ptr)),
                     "pbk_keyx_partition_device")
+
+    def keyx_partition_device_async(self, d_bases_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int, d_send_ptr: int,
+                                    d_cursors_ptr: int):
+        self._check(self._L.pbk_keyx_partition_device_async(self._ctx, C.c_void_p(d_bases_ptr), C.c_void_p(d_offsets_ptr), n_reads,
+                                                            n_bases, C.c_void_p(d_send_ptr), C.c_void_p(d_cursors_ptr)),
+                    "pbk_keyx_partition_device_async")
+
+    def stream_signal(self, cuda_stream: int):
+        """the caller's stream (a raw cudaStream_t) waits for what this context has queued"""
+        self._check(self._L.pbk_stream_signal(self._ctx, C.c_void_p(cuda_stream)), "pbk_stream_signal")
+
+    def stream_wait(self, cuda_stream: int):
+        """this context waits for what has been queued on the caller's stream"""
+        self._check(self._L.pbk_stream_wait(self._ctx, C.c_void_p(cuda_stream)), "pbk_stream_wait")
 
     def keyx_insert_device(self, d_recv_ptr: int, d_recv_cursors_ptr: int):
         self._check(self._L.pbk_keyx_insert_device(self._ctx, C.c_void_p(d_recv_ptr), C.c_void_p(d_recv_cursors_ptr)),

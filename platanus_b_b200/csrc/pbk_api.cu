@@ -85,6 +85,8 @@ struct pbk_ctx {
     u64 keyx_last_total = 0;            // keys received by the last host-sized insert: sizes the table for the queued ones
     bool counters_pending = false;      // a queued key-exchange insert has not had its counters read back yet (settle())
     u64 *keyx_send = nullptr, *keyx_cursors = nullptr;
+    bool keyx_async = false;            // this partition call returns without reading the counters back
+    cudaEvent_t ev_signal = nullptr, ev_wait = nullptr;     // pbk_stream_signal / pbk_stream_wait
 
     bool finalized = false;
     u64 n_reads = 0, n_bases = 0, inst_since_clamp = 0, n_grow = 0;
@@ -231,9 +233,12 @@ int ensure_room(pbk_ctx *c, u64 expect_new)
     return PBK_OK;
 }
 
+int settle(pbk_ctx *c);
+
 int ensure_overflow(pbk_ctx *c, u64 records)
 {
     if (records <= c->ovf_cap) return PBK_OK;
+    TRY(settle(c));                                  // queued launches may still append to the list that is about to be replaced
     if (c->d_ovf) { CK(cudaStreamSynchronize(c->s_compute)); dev_free(c, c->d_ovf, c->ovf_cap * (c->W + 1) * 8); c->d_ovf = nullptr; c->ovf_cap = 0; }
     TRY(dev_alloc(c, (void **)&c->d_ovf, records * (c->W + 1) * 8));
     c->ovf_cap = records;
@@ -634,9 +639,13 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
         // keys that found their segment full (a heavily repeated k-mer), which take the record route (remote-staging
         // table -> pbk_shard_pack_device) to their owner
         CK(cudaGetLastError());
-        c->counters_pending = false;                    // the read-back below also covers a queued pbk_keyx_insert_device
-        TRY(read_counters(c));
-        TRY(drain_overflow(c));
+        if (c->keyx_async) {
+            c->counters_pending = true;                 // settle() reads them (and drains spills) when the host next needs them
+        } else {
+            c->counters_pending = false;                // the read-back below also covers a queued pbk_keyx_insert_device
+            TRY(read_counters(c));
+            TRY(drain_overflow(c));
+        }
     } else if (pipe.on) {
         CK(cudaGetLastError());
         TRY(pipe_end(c, pipe));
@@ -668,6 +677,8 @@ void release_all(pbk_ctx *c)
     cudaFree(c->d_len_scratch); cudaFree(c->d_ctr_scratch);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     for (auto &e : c->timer) if (e) cudaEventDestroy(e);
+    if (c->ev_signal) cudaEventDestroy(c->ev_signal);
+    if (c->ev_wait) cudaEventDestroy(c->ev_wait);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
 }
@@ -1315,6 +1326,37 @@ int pbk_keyx_partition_device(pbk_ctx *c, const void *d_bases, const void *d_rea
     }
     c->keyx_send = c->keyx_cursors = nullptr;
     return rc;
+}
+
+int pbk_keyx_partition_device_async(pbk_ctx *c, const void *d_bases, const void *d_read_offsets, uint64_t n_reads,
+                                    uint64_t n_bases, void *d_send, void *d_cursors)
+{
+    if (!c) return PBK_E_ARG;
+    // buffers that must grow are reallocated behind a stream synchronisation: fine, just not asynchronous that time
+    c->keyx_async = n_reads != 0;
+    const int rc = pbk_keyx_partition_device(c, d_bases, d_read_offsets, n_reads, n_bases, d_send, d_cursors);
+    c->keyx_async = false;
+    return rc;
+}
+
+int pbk_stream_signal(pbk_ctx *c, void *stream)
+{
+    if (!c) return PBK_E_ARG;
+    CK(cudaSetDevice(c->device));
+    if (!c->ev_signal) CK(cudaEventCreateWithFlags(&c->ev_signal, cudaEventDisableTiming));
+    CK(cudaEventRecord(c->ev_signal, c->s_compute));
+    CK(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_signal, 0));
+    return PBK_OK;
+}
+
+int pbk_stream_wait(pbk_ctx *c, void *stream)
+{
+    if (!c) return PBK_E_ARG;
+    CK(cudaSetDevice(c->device));
+    if (!c->ev_wait) CK(cudaEventCreateWithFlags(&c->ev_wait, cudaEventDisableTiming));
+    CK(cudaEventRecord(c->ev_wait, (cudaStream_t)stream));
+    CK(cudaStreamWaitEvent(c->s_compute, c->ev_wait, 0));
+    return PBK_OK;
 }
 
 int pbk_keyx_insert_device(pbk_ctx *c, const void *d_recv, const void *d_recv_cursors)

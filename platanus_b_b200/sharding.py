@@ -61,7 +61,8 @@ def any_rank_staged(n_staged_here: int, device=None, group=None) -> bool:
     return int(t.item()) > 0
 
 
-def pipelined_key_exchange(n_chunks: int, partition, insert, send, cursors, recv, recv_cursors, wait_collectives, group=None):
+def pipelined_key_exchange(n_chunks: int, partition, insert, send, cursors, recv, recv_cursors, wait_collectives, group=None,
+                           after_partition=None, before_insert=None):
     """The key exchange over a batch cut into chunks, so that the all-to-all of chunk i runs while Pass A of chunk i + 1
     and Pass B of chunk i - 1 are computed.
 
@@ -72,6 +73,12 @@ def pipelined_key_exchange(n_chunks: int, partition, insert, send, cursors, recv
       wait_collectives()                   blocks the host until the collectives issued so far have finished (NCCL:
                                            synchronize the current stream after Work.wait(); gloo: nothing to do)
 
+      after_partition(), before_insert()   optional, device-side ordering instead of host synchronisation: after_partition
+                                           makes the collective's stream wait for Pass A (pbk_stream_signal, with a partition
+                                           call that does not block: pbk_keyx_partition_device_async), before_insert makes the
+                                           counter's stream wait for the collective (pbk_stream_wait) and replaces
+                                           wait_collectives().  Everything is then ordered by the two streams alone.
+
     Buffer reuse: chunk i uses buffers i % 2.  Its send buffer is rewritten by partition(i + 2), which is called after
     chunk i's all-to-all has been waited for; its receive buffer is rewritten by the all-to-all of chunk i + 2, which
     is issued after insert() of chunk i has returned."""
@@ -79,13 +86,18 @@ def pipelined_key_exchange(n_chunks: int, partition, insert, send, cursors, recv
         works, s = p
         for w in works:
             w.wait()
-        wait_collectives()
+        if before_insert is not None:
+            before_insert()
+        else:
+            wait_collectives()
         insert(recv[s], recv_cursors[s])
 
     pending = None
     for i in range(n_chunks):
         s = i & 1
         partition(i, send[s], cursors[s])
+        if after_partition is not None:
+            after_partition()
         works = [dist.all_to_all_single(recv[s].view(-1), send[s].view(-1), group=group, async_op=True),
                  dist.all_to_all_single(recv_cursors[s].view(-1), cursors[s].view(-1), group=group, async_op=True)]
         if pending is not None:
@@ -144,11 +156,17 @@ class KeyExchange:
         self.cur, self.rcur = mk(shape[:2], True), mk(shape[:2], True)
         self.record_bufs: dict = {}
 
-    def step(self, n_chunks: int, partition_chunk, sync) -> int:
-        """partition_chunk(i, d_send_ptr, d_cursors_ptr) runs pbk_keyx_partition* for chunk i.  Returns the bytes sent."""
+    def step(self, n_chunks: int, partition_chunk, sync, caller_stream=None) -> int:
+        """partition_chunk(i, d_send_ptr, d_cursors_ptr) runs pbk_keyx_partition* for chunk i.  Returns the bytes sent.
+        caller_stream: a callable returning the raw cudaStream_t the collectives are issued from; when given, the step is
+        ordered on the device (pbk_stream_signal / pbk_stream_wait) and partition_chunk should be the _async form."""
+        hooks = {}
+        if caller_stream is not None:
+            hooks = {"after_partition": lambda: self.kc.stream_signal(caller_stream()),
+                     "before_insert": lambda: self.kc.stream_wait(caller_stream())}
         pipelined_key_exchange(n_chunks, lambda i, s, c: partition_chunk(i, s.data_ptr(), c.data_ptr()),
                                lambda r, rc: self.kc.keyx_insert_device(r.data_ptr(), rc.data_ptr()),
-                               self.send, self.cur, self.recv, self.rcur, sync, group=self.group)
+                               self.send, self.cur, self.recv, self.rcur, sync, group=self.group, **hooks)
         sent = n_chunks * (self.world - 1) * int(self.lay.bytes_per_dest)
         if any_rank_staged(int(self.kc.shard_send_counts(self.world).sum()), device=self.device, group=self.group):
             sent += exchange_staged_records(self.kc, self.world, self.device, self.record_bufs, sync, self.group)

@@ -254,7 +254,14 @@ def _abi_worker(rank, world, port, k, mode, n_chunks, out_dir):
                     ranges += [(len(o) - 1, len(o) - 1)] * (n_ch - len(ranges))
                     chunks = [(np.ascontiguousarray(b[int(o[r0]):int(o[r1])]), (o[r0:r1 + 1] - o[r0]).astype(np.uint64)) for r0, r1 in ranges]
                     kx = sharding.KeyExchange(kc, world, max(max(int(co[-1]) - (len(co) - 1) * (k - 1), 0) for _, co in chunks))
-                    sent = kx.step(len(chunks), lambda i, sp, cp: kc.keyx_partition(chunks[i][0], chunks[i][1], sp, cp), lambda: None)
+                    if rep == 0:
+                        sent = kx.step(len(chunks), lambda i, sp, cp: kc.keyx_partition(chunks[i][0], chunks[i][1], sp, cp), lambda: None)
+                    else:                                           # device-ordered form (stream hooks are no-ops in the emulation)
+                        t_b = [torch.from_numpy(cb) for cb, _ in chunks]
+                        t_o = [torch.from_numpy(co.view(np.int64)) for _, co in chunks]
+                        sent = kx.step(len(chunks), lambda i, sp, cp: kc.keyx_partition_device_async(
+                            t_b[i].data_ptr(), t_o[i].data_ptr(), len(chunks[i][1]) - 1, int(chunks[i][1][-1]), sp, cp), lambda: None,
+                            caller_stream=lambda: 0)
                 else:
                     kc.push_reads(b, o)
                     sent = sharding.exchange_staged_records(kc, world)
