@@ -1,7 +1,9 @@
 #!/bin/bash
 # Round-2 opener: everything that was built after round 1's GPU budget ran out, on ONE B200, in one gpurun call (~6 min):
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash scripts/r2_first_call.sh'
-# Then (separate calls): torchrun --nproc-per-node 2/8 bench.py --gpus N --exchange keys  vs  --exchange records.
+# Then, on 2 GPUs (gpurun --gpus 2), the correctness gate of every exchange form over NCCL and the first timings:
+#   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/sharded_check.py
+#   ... bench.py --gpus 2 --exchange records | --exchange keys | --exchange keys --keyx-async   (then the same at --gpus 8)
 set -u
 mkdir -p gpurun_out
 # 1. the GPU cases that have only been seen to pass against the host-emulated ABI (xfail marks ignored: failures are real here)

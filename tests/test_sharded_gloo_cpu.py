@@ -217,84 +217,29 @@ def test_two_rank_key_exchange_over_gloo(oracle, k, seg_cap, tmp_path):
 
 
 def _abi_worker(rank, world, port, k, mode, n_chunks, out_dir):
-    """Both exchanges as bench.py runs them (sharding.KeyExchange.step / sharding.exchange_staged_records) around a real
+    """Every exchange form as bench.py runs it (sharding.KeyExchange.step / sharding.exchange_staged_records) around a real
     sharded KmerCounter -- the C ABI compiled for the host (tests/cpu_emul/cuda_rt_shim.h), so a torch CPU tensor's
-    data_ptr() is a valid "device" pointer -- over gloo."""
+    data_ptr() is a valid "device" pointer -- over gloo.  The body is tests/sharded_check.py, which also runs under torchrun
+    on real GPUs."""
     for p in (ROOT, HERE):
         if p not in sys.path:
             sys.path.insert(0, p)
     import emul_helper
     from platanus_b_b200 import build
     build.LIB = emul_helper.abi_lib_path()
-    import ctypes as C
-
-    from oracle import oracle as O
-    from platanus_b_b200 import KmerCounter, capi, sharding, synth
+    import sharded_check
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        L = capi.load_library()
-        rs = synth.make_reads(synth.config("C1", scale=1 / 400))
-        bases, offs = rs.flat()
-        rd = O.Reads()
-        rd.add_array(bases, offs)
-        want = O.count(rd, k)
-        n = len(offs) - 1
-        lo, hi = n * rank // world, n * (rank + 1) // world
-        b = np.ascontiguousarray(bases[int(offs[lo]):int(offs[hi])])
-        o = (offs[lo:hi + 1] - offs[lo]).astype(np.uint64)
-        with KmerCounter(k, n_shards=world, shard_rank=rank) as kc:
-            for rep in range(2):                                    # second pass: reset, tables and layout reused
-                kc.reset()
-                if mode == "keys":
-                    ranges = sharding.chunk_read_ranges(o, n_chunks)
-                    n_ch = sharding.max_windows_any_rank(len(ranges))
-                    ranges += [(len(o) - 1, len(o) - 1)] * (n_ch - len(ranges))
-                    chunks = [(np.ascontiguousarray(b[int(o[r0]):int(o[r1])]), (o[r0:r1 + 1] - o[r0]).astype(np.uint64)) for r0, r1 in ranges]
-                    kx = sharding.KeyExchange(kc, world, max(max(int(co[-1]) - (len(co) - 1) * (k - 1), 0) for _, co in chunks))
-                    if rep == 0:
-                        sent = kx.step(len(chunks), lambda i, sp, cp: kc.keyx_partition(chunks[i][0], chunks[i][1], sp, cp), lambda: None)
-                    else:                                           # device-ordered form (stream hooks are no-ops in the emulation)
-                        t_b = [torch.from_numpy(cb) for cb, _ in chunks]
-                        t_o = [torch.from_numpy(co.view(np.int64)) for _, co in chunks]
-                        sent = kx.step(len(chunks), lambda i, sp, cp: kc.keyx_partition_device_async(
-                            t_b[i].data_ptr(), t_o[i].data_ptr(), len(chunks[i][1]) - 1, int(chunks[i][1][-1]), sp, cp), lambda: None,
-                            caller_stream=lambda: 0)
-                else:
-                    kc.push_reads(b, o)
-                    sent = sharding.exchange_staged_records(kc, world)
-                assert sent > 0
-                if mode == "keys" and rep == 1:                     # steady state: received chunks are inserted without a host round trip
-                    assert kc.stats()["n_pipelined_batches"] >= 1
-                kc.finalize()
-                hist = torch.from_numpy(kc.occ_hist.astype(np.int64))
-                sharding.allreduce_histogram(hist)
-                assert np.array_equal(hist.numpy().astype(np.uint64), want.occ_hist)
-                keys, counts = kc.export(1, sorted=True)
-                sel = np.array([L.pbk_shard_of_key(np.ascontiguousarray(r).ctypes.data_as(C.c_void_p), k, world) == rank
-                                for r in want.keys], dtype=bool)
-                assert np.array_equal(keys, want.keys[sel]) and np.array_equal(counts, want.counts[sel])
-                inst = torch.tensor([kc.n_instances], dtype=torch.int64)
-                dist.all_reduce(inst)
-                assert int(inst.item()) == want.n_instances
-            # the output files of the sharded count (rank 0): identical to what the unsharded oracle table gives
-            cutoff = sharding.write_outputs(kc, os.path.join(out_dir, "sh"), k, world, rank, 10 ** 9)
-            assert cutoff == O.coverage_cutoff(want.occ_hist, want.max_occ)
-            if rank == 0:
-                assert open(os.path.join(out_dir, f"sh_{k}merFrq.tsv")).read() == O.tsv_text(want.occ_hist, want.max_occ)
-                t = O.read_bin(os.path.join(out_dir, "sh_kmer_occ.bin"))
-                keep = want.counts >= cutoff
-                bk, bc = t.sorted_dump()
-                assert t.reachable and t.k == k and t.index_size == max(O.load_size(int(keep.sum())), O.double_hash_size(10 ** 9, k)) - 1
-                assert np.array_equal(bk, want.keys[keep]) and np.array_equal(bc, want.counts[keep])
+        sharded_check.run_checks(rank, world, k, mode, n_chunks, out_dir, device=None)
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("k,mode,n_chunks", [(32, "keys", 3), (32, "records", 1), (75, "records", 1)])
+@pytest.mark.parametrize("k,mode,n_chunks", [(32, "keys", 3), (32, "keys_async", 4), (32, "records", 1), (75, "records", 1)])
 def test_two_rank_exchanges_through_the_c_abi(oracle, k, mode, n_chunks, tmp_path):
     import emul_helper
     emul_helper.abi_lib_path()                               # build once, before the workers race for it
