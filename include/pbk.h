@@ -252,6 +252,13 @@ int  pbk_match_reads(pbk_ctx *ctx, const uint8_t *bases, const uint64_t *read_of
  * in any order with pbk_push_reads; entries with value 0 are ignored (counter.h:700); pbk_reset
  * forgets them.                                                                                     */
 int  pbk_seed_entries(pbk_ctx *ctx, const uint64_t *keys, const uint16_t *counts, uint64_t n);
+/* Counter::makeKmerReadDistributionFromContig (counter.h:511-593): every k-mer of the given sequences gets
+ * max(its value so far, max(coverage of its sequence, min_occurrence)) -- a k-mer of several contigs keeps the
+ * largest.  pbk_finalize then yields the distribution writeKmerDistribution would (counter.h:582-590).
+ * ASCII sequences; windows containing N are skipped (the reference feeds them in as garbage; its contigs
+ * carry no N here); sequences may be as long as the whole call (no 500000 limit: read_offsets semantics only). */
+int  pbk_push_contigs(pbk_ctx *ctx, const uint8_t *bases, const uint64_t *seq_offsets, uint64_t n_seqs,
+                      const uint16_t *coverage, uint64_t min_occurrence);
 /* Add n (key, count) entries to the table (host arrays; keys n x ceil(k/32) words, word 0 first):
  * what Counter::readOccurrenceTableBinary leaves in memory, or a contig-seeded table
  * (makeKmerReadDistributionFromContig, counter.h:511-593).  Counts of equal keys add up, saturating. */

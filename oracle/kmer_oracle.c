@@ -421,6 +421,79 @@ static uint16_t table_find(const uint64_t *keys, const uint16_t *counts, uint64_
     return 0;
 }
 
+/* Counter::makeKmerReadDistributionFromContig (counter.h:511-593): occurrenceTable[key] = max(itself,
+ * max(coverage[contig], minOccurrence)) over every window of every contig of length >= k, then
+ * writeKmerDistribution (entries with a non-zero value, counter.h:483-507).  Sequences are loaded as Contig::setSeq does
+ * (common.h:528-537: base = Char2Bin(c)); like the reference, windows with an N are NOT skipped (the skip is commented
+ * out, counter.h:559-566) -- the code 4 goes into the 2-bit fields as it is. */
+int pbo_count_contigs(const pbo_reads *r, unsigned k, const uint16_t *coverage, uint64_t min_occ, pbo_result *res)
+{
+    if (k == 0) return PBO_E_ARG;
+    unsigned words = (k + 31) / 32;
+    if (words > MAXW) return PBO_E_ARG;
+    memset(res, 0, sizeof(*res));
+    res->k = k; res->words = words;
+    res->len_hist = (uint64_t *)calloc(PBO_MAX_READ_LEN + 1, sizeof(uint64_t));
+    if (!res->len_hist) return PBO_E_NOMEM;
+    uint64_t max_inst = 0;
+    for (uint64_t i = 0; i < r->n_reads; ++i) {
+        uint64_t len = r->offsets[i + 1] - r->offsets[i];
+        if (len >= k) max_inst += len - k + 1;
+    }
+    const unsigned rw = words + 1;                                    /* key words + value, sorted together */
+    uint64_t *rec = (uint64_t *)malloc((max_inst ? max_inst : 1) * rw * sizeof(uint64_t));
+    uint64_t *fwd = (uint64_t *)calloc(words, sizeof(uint64_t)), *rev = (uint64_t *)calloc(words, sizeof(uint64_t));
+    if (!rec || !fwd || !rev) { free(rec); free(fwd); free(rev); return PBO_E_NOMEM; }
+    uint64_t n = 0;
+    for (uint64_t ri = 0; ri < r->n_reads; ++ri) {
+        const char *s = r->bases + r->offsets[ri];
+        uint64_t len = r->offsets[ri + 1] - r->offsets[ri];
+        if (len < k) continue;                                        /* counter.h:543-544 */
+        uint64_t v = coverage[ri] > min_occ ? coverage[ri] : min_occ;  /* counter.h:573 */
+        v &= 0xFFFF;                                                  /* stored in an unsigned short */
+        for (unsigned i = 0; i + 1 < k; ++i) {
+            unsigned char b = pbo_char2bin(s[i]);
+            key_set(fwd, k - i - 2, b);
+            key_set(rev, i + 1, (unsigned char)(0x3 ^ b));
+        }
+        for (uint64_t i = 0; i < len - k + 1; ++i) {
+            unsigned char b = pbo_char2bin(s[i + k - 1]);
+            key_shl2(fwd, words, k);
+            key_set(fwd, 0, b);
+            key_shr2(rev, words);
+            key_set(rev, k - 1, (unsigned char)(0x3 ^ b));
+            const uint64_t *key = pbo_key_cmp(fwd, rev, words) <= 0 ? fwd : rev;
+            memcpy(rec + n * rw, key, words * 8);
+            rec[n * rw + words] = v;
+            ++n;
+        }
+    }
+    free(fwd); free(rev);
+    g_sort_words = words;
+    qsort(rec, n, rw * sizeof(uint64_t), sort_cmp);
+    uint64_t *keys = (uint64_t *)malloc((n ? n : 1) * words * sizeof(uint64_t));
+    uint16_t *counts = (uint16_t *)malloc((n ? n : 1) * sizeof(uint16_t));
+    if (!keys || !counts) { free(rec); free(keys); free(counts); return PBO_E_NOMEM; }
+    uint64_t nd = 0;
+    for (uint64_t i = 0; i < n;) {
+        uint64_t j = i, best = 0;
+        while (j < n && pbo_key_cmp(rec + i * rw, rec + j * rw, words) == 0) { if (rec[j * rw + words] > best) best = rec[j * rw + words]; ++j; }
+        if (best != 0) {                                              /* counter.h:490 */
+            memcpy(keys + nd * words, rec + i * rw, words * 8);
+            counts[nd] = (uint16_t)best;
+            res->occ_hist[best < PBO_OCC_BINS ? best : PBO_OCC_BINS - 1] += 1;
+            ++nd;
+        }
+        i = j;
+    }
+    free(rec);
+    res->keys = keys; res->counts = counts; res->n_distinct = nd; res->n_instances = 0;
+    res->max_occ = 0;
+    for (unsigned i = PBO_OCC_BINS - 1; i > 0; --i)
+        if (res->occ_hist[i] > 0) { res->max_occ = i; break; }
+    return PBO_OK;
+}
+
 /* Counter::pickupReadMatchedEdgeKmer (counter.h:870-910): out[r] = 1 iff read r is kept -- it is at least k long and
  * one of its windows without an N has a k-mer with a non-zero value in the table.  Reads go through
  * SEQ::convertFromString like in pbo_count (N positions as a list, counter.h:882-884, 895-899). */

@@ -68,6 +68,7 @@ def lib():
         L.pbo_count.argtypes = [C.POINTER(_Reads), C.c_uint, C.POINTER(_Result)]
         L.pbo_result_release.argtypes = [C.POINTER(_Result)]
         L.pbo_count_seeded.argtypes = [C.POINTER(_Reads), C.c_uint, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(_Result)]
+        L.pbo_count_contigs.argtypes = [C.POINTER(_Reads), C.c_uint, C.c_void_p, C.c_uint64, C.POINTER(_Result)]
         L.pbo_match_reads.argtypes = [C.POINTER(_Reads), C.c_uint, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.pbo_occurrence_array.argtypes = [C.POINTER(_Reads), C.c_uint, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.pbo_left_local_min.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
@@ -200,6 +201,37 @@ def occurrence_array(seqs: Reads, k: int, keys: np.ndarray, counts: np.ndarray) 
     if rc:
         raise OracleError(rc, "pbo_occurrence_array")
     return out
+
+
+def count_contigs(seqs: Reads, k: int, coverage: np.ndarray, min_occurrence: int = 1) -> CountResult:
+    """Counter::makeKmerReadDistributionFromContig (counter.h:511-593)."""
+    cov = np.ascontiguousarray(coverage, dtype=np.uint16)
+    res = _Result()
+    rc = lib().pbo_count_contigs(seqs._p, k, cov.ctypes.data_as(C.c_void_p), int(min_occurrence), C.byref(res))
+    if rc:
+        raise OracleError(rc, "pbo_count_contigs")
+    try:
+        nd, w = int(res.n_distinct), int(res.words)
+        keys = (np.ctypeslib.as_array(res.keys, shape=(nd * w,)).copy().reshape(nd, w) if nd else np.zeros((0, w), np.uint64))
+        counts = np.ctypeslib.as_array(res.counts, shape=(nd,)).copy() if nd else np.zeros(0, np.uint16)
+        occ = np.frombuffer(bytes(res.occ_hist), dtype=np.uint64).copy()
+        lh = np.ctypeslib.as_array(res.len_hist, shape=(MAX_READ_LEN + 1,)).copy()
+        return CountResult(int(res.k), w, 0, keys, counts, occ, lh, int(res.max_occ))
+    finally:
+        lib().pbo_result_release(C.byref(res))
+
+
+def run_ref_contig(k: int, contigs_fa: str, min_occurrence: int, workdir: str):
+    """oracle/ref_iter_harness.cpp, mode contig: sorted keys, counts, maxOccurrence of makeKmerReadDistributionFromContig."""
+    import subprocess
+    out = os.path.join(workdir, "contig_out")
+    p = subprocess.run([REF_ITER, "contig", str(k), contigs_fa, str(min_occurrence), out], check=True, capture_output=True, text=True, cwd=workdir)
+    w = (k + 31) // 32
+    raw = np.fromfile(out, dtype=np.uint8).reshape(-1, 8 * w + 2)
+    keys = np.ascontiguousarray(raw[:, :8 * w]).view(np.uint64).reshape(-1, w)
+    counts = np.ascontiguousarray(raw[:, 8 * w:]).view(np.uint16).reshape(-1)
+    order = np.lexsort(tuple(keys[:, j] for j in range(w)))
+    return keys[order], counts[order], int(p.stdout.split()[-1])
 
 
 def match_reads(reads: Reads, k: int, keys: np.ndarray, counts: np.ndarray) -> np.ndarray:

@@ -7,6 +7,8 @@
 // The table is loaded with the reference's own Counter::readOccurrenceTableBinary from a PREFIX_kmer_occ.bin.
 // Reads: one sequence per line (ACGTN), converted and dealt to NUM_THREAD SEQ temp files the way
 // Assemble::readFastaUncompressed does (assemble.cpp:836-845).
+//   contig : Counter::makeKmerReadDistributionFromContig (counter.h:511-593) -- table built from contigs and their coverages
+//            usage: ref_iter_harness contig K CONTIGS.fa MIN_OCCURRENCE OUT   (raw kmerFP records, stdout: maxOccurrence)
 //   usage: ref_iter_harness pickup|count TABLE.bin READS.txt NUM_THREAD OUT
 //   pickup -> OUT: the surviving reads, one per line, per temp file in order (file 0 first)
 //   count  -> OUT: the raw kmerFP records (key words + u16), then stdout: "maxOccurrence <n>"
@@ -67,9 +69,38 @@ static int run(const std::string &mode, const std::string &bin, const std::strin
     return 0;
 }
 
+template <typename KMER>
+static int run_contig(unsigned long long k, const std::string &fa, unsigned long long minOccurrence, const std::string &out)
+{
+    platanus::Contig contig;
+    contig.readFastaCoverage(fa);
+    Counter<KMER> counter(k);
+    counter.makeKmerReadDistributionFromContig(contig, k, minOccurrence, 100000000ull);
+    FILE *fp = counter.kmerFP;
+    fflush(fp);
+    rewind(fp);
+    std::ofstream ofs(out.c_str(), std::ios::binary);
+    char buf[65536];
+    size_t got;
+    while ((got = fread(buf, 1, sizeof buf, fp)) > 0) ofs.write(buf, got);
+    std::cout << "maxOccurrence " << counter.getMaxOccurrence() << std::endl;
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     if (argc != 6) return 2;
+    if (std::string(argv[1]) == "contig") {
+        platanus::setGlobalTmpFileDir(".");
+        const unsigned long long k = strtoull(argv[2], NULL, 10), minOcc = strtoull(argv[4], NULL, 10);
+        const std::string fa = argv[3], out = argv[5];
+        if (k <= 32) return run_contig<Kmer31>(k, fa, minOcc, out);
+        if (k <= 64) return run_contig<KmerN<Binstr63> >(k, fa, minOcc, out);
+        if (k <= 96) return run_contig<KmerN<Binstr95> >(k, fa, minOcc, out);
+        if (k <= 128) return run_contig<KmerN<Binstr127> >(k, fa, minOcc, out);
+        if (k <= 160) return run_contig<KmerN<Binstr159> >(k, fa, minOcc, out);
+        return run_contig<KmerN<binstr_t> >(k, fa, minOcc, out);
+    }
     const std::string mode = argv[1], bin = argv[2], reads = argv[3], out = argv[5];
     const unsigned long long numThread = strtoull(argv[4], NULL, 10);
     platanus::setGlobalTmpFileDir(".");

@@ -41,6 +41,7 @@ SYMBOLS = [
     "pbk_keyx_plan", "pbk_keyx_partition", "pbk_keyx_partition_device", "pbk_keyx_insert_device",
     "pbk_lookup", "pbk_lookup_device", "pbk_load_entries", "pbk_read_kmer_occ_bin", "pbk_free",
     "pbk_match_reads", "pbk_seed_entries", "pbk_stream_signal", "pbk_stream_wait", "pbk_keyx_partition_device_async",
+    "pbk_push_contigs",
 ]
 
 
@@ -126,6 +127,7 @@ def load_library(build_if_missing: bool = True):
     L.pbk_lookup_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, vp]
     L.pbk_load_entries.argtypes = [vp, u64p, vp, C.c_uint64]
     L.pbk_seed_entries.argtypes = [vp, u64p, vp, C.c_uint64]
+    L.pbk_push_contigs.argtypes = [vp, vp, u64p, C.c_uint64, vp, C.c_uint64]
     L.pbk_match_reads.argtypes = [vp, vp, u64p, C.c_uint64, C.c_int, vp, u64p, vp]
     L.pbk_read_kmer_occ_bin.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp),
                                         C.POINTER(C.c_uint64)]
@@ -314,6 +316,14 @@ class KmerCounter:
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
         counts = np.ascontiguousarray(counts, dtype=np.uint16)
         self._check(self._L.pbk_seed_entries(self._ctx, _ptr(keys), _ptr(counts), len(counts)), "pbk_seed_entries")
+
+    def push_contigs(self, bases: np.ndarray, offsets: np.ndarray, coverage: np.ndarray, min_occurrence: int = 1):
+        """makeKmerReadDistributionFromContig (counter.h:511-593): table[k-mer] = max over its contigs of max(coverage, min_occurrence)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        coverage = np.ascontiguousarray(coverage, dtype=np.uint16)
+        self._check(self._L.pbk_push_contigs(self._ctx, _ptr(bases), _ptr(offsets), len(offsets) - 1, _ptr(coverage), int(min_occurrence)),
+                    "pbk_push_contigs")
 
     def load_entries(self, keys: np.ndarray, counts: np.ndarray):
         keys = np.ascontiguousarray(keys, dtype=np.uint64)

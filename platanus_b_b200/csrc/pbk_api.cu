@@ -1239,6 +1239,75 @@ int pbk_match_reads(pbk_ctx *c, const uint8_t *bases, const uint64_t *read_offse
                          (const u64 *)n_pos_offsets, nullptr, nullptr, matched_out);
 }
 
+int pbk_push_contigs(pbk_ctx *c, const uint8_t *bases, const uint64_t *seq_offsets, uint64_t n_seqs, const uint16_t *coverage,
+                     uint64_t min_occurrence)
+{
+    if (!c) return PBK_E_ARG;
+    if (n_seqs == 0) return PBK_OK;
+    if (!seq_offsets || !coverage || seq_offsets[0] != 0) return fail(c, PBK_E_ARG, "bad arguments");
+    if (c->finalized) return fail(c, PBK_E_STATE, "pbk_push_contigs after pbk_finalize (call pbk_reset first)");
+    const u64 n_bases = seq_offsets[n_seqs];
+    if (n_bases == 0) return PBK_OK;
+    if (!bases) return fail(c, PBK_E_ARG, "bases is NULL");
+    if (n_bases > MAX_PUSH_BASES) return fail(c, PBK_E_ARG, "pbk_push_contigs takes at most %llu bases per call", (unsigned long long)MAX_PUSH_BASES);
+    CK(cudaSetDevice(c->device));
+    TRY(settle(c));
+    // every window may be a new key: make room for all of them, so that no probe sequence can run out (see contig_max_kernel)
+    const u64 windows = n_bases;
+    TRY(ensure_tables(c, (u64)(windows / std::max(0.05, c->new_ratio)) + 1024, false));
+    TRY(maybe_clamp(c, 0));
+    if ((double)(c->occupied + windows) > max_load(c) * (double)c->table.capacity())
+        TRY(grow_table(c, &c->table, c->occupied, (u64)((c->occupied + windows) / max_load(c)) + 1));
+    TRY(ensure_batch_buffers(c, n_bases, n_seqs));
+    if (!c->d_len_scratch) {
+        TRY(dev_alloc(c, (void **)&c->d_len_scratch, PBK_LEN_BINS * 8));
+        TRY(dev_alloc(c, (void **)&c->d_ctr_scratch, sizeof(Counters)));
+    }
+    CK(cudaMemsetAsync(c->d_ctr_scratch, 0, sizeof(Counters), c->s_compute));
+    u64 *stream = c->d_stream_raw + STREAM_PAD_WORDS;
+    u32 *nflag = c->d_nflag_raw + STREAM_PAD_WORDS, *rflag = c->d_rflag_raw + STREAM_PAD_WORDS;
+    const u64 words = (n_bases + 31) / 32;
+    // value of every stream position: max(coverage of its contig, minOccurrence) (counter.h:573-574)
+    std::vector<uint16_t> val(words * 32, 0);
+    for (u64 r = 0; r < n_seqs; ++r) {
+        const u64 v = std::min<u64>(std::max<u64>(coverage[r], min_occurrence), COUNT_SAT);
+        std::fill(val.begin() + seq_offsets[r], val.begin() + seq_offsets[r + 1], (uint16_t)v);
+    }
+    CK(cudaMemcpyAsync(c->d_offsets, seq_offsets, (n_seqs + 1) * 8, cudaMemcpyHostToDevice, c->s_compute));
+    CK(cudaMemsetAsync(rflag, 0, words * 4, c->s_compute));
+    { Span sp(c, LC_OTHER); launch_read_marks(c->d_offsets, n_seqs, c->d_len_scratch, rflag, c->d_ctr_scratch, c->s_compute); }
+    uint8_t *d_stage = nullptr; uint16_t *d_val = nullptr;
+    TRY(dev_alloc(c, (void **)&d_stage, CHUNK_BASES));
+    int rc = dev_alloc(c, (void **)&d_val, words * 64);
+    if (rc == PBK_OK && cudaMemcpyAsync(d_val, val.data(), words * 64, cudaMemcpyHostToDevice, c->s_compute) != cudaSuccess) rc = fail(c, PBK_E_CUDA, "H2D copy failed");
+    c->h2d_bytes += words * 64 + n_bases + (n_seqs + 1) * 8;
+    for (u64 b0 = 0; b0 < n_bases && rc == PBK_OK; b0 += CHUNK_BASES) {
+        const u64 nb = std::min(CHUNK_BASES, n_bases - b0), w0 = b0 / 32, nw = (nb + 31) / 32;
+        if (cudaMemcpyAsync(d_stage, bases + b0, nb, cudaMemcpyHostToDevice, c->s_compute) != cudaSuccess) rc = fail(c, PBK_E_CUDA, "H2D copy failed");
+        { Span sp(c, LC_PACK); launch_pack(d_stage, nb, nw, PBK_ENC_ASCII, stream, nflag, w0, c->d_ctr_scratch, c->s_compute); }
+    }
+    if (rc == PBK_OK) {
+        { Span sp(c, LC_OTHER); launch_contig_max(stream, nflag, rflag, 0, words, (int)c->k, c->table, d_val, c->d_ctr, c->sm_count, c->s_compute); }
+        if (cudaGetLastError() != cudaSuccess) rc = fail(c, PBK_E_CUDA, "contig_max launch failed");
+    }
+    if (rc == PBK_OK) rc = read_counters(c);
+    else cudaStreamSynchronize(c->s_compute);
+    if (rc == PBK_OK && c->h_ctr->overflow_n > 0) {
+        cudaMemsetAsync(&c->d_ctr->overflow_n, 0, sizeof(u64), c->s_compute);
+        c->last.overflow_n = 0; c->h_ctr->overflow_n = 0;
+        rc = fail(c, PBK_E_CUDA, "internal: a contig k-mer found no slot in a table sized for every window");
+    }
+    if (rc == PBK_OK) {                                   // characters without a Char2Bin code, over-long sequences
+        Counters sc;
+        if (cudaMemcpyAsync(&sc, c->d_ctr_scratch, sizeof sc, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess ||
+            cudaStreamSynchronize(c->s_compute) != cudaSuccess) rc = fail(c, PBK_E_CUDA, "read-back failed");
+        else if (sc.error_flags & ERR_BAD_BASE) rc = fail(c, PBK_E_BAD_BASE, "input contains a character with no Char2Bin code (only ACGTN, any case)");
+    }
+    cudaStreamSynchronize(c->s_compute);
+    dev_free(c, d_stage, CHUNK_BASES); dev_free(c, d_val, words * 64);
+    return rc;
+}
+
 int pbk_seed_entries(pbk_ctx *c, const uint64_t *keys, const uint16_t *counts, uint64_t n)
 {
     if (!c) return PBK_E_ARG;

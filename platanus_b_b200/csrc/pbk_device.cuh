@@ -327,6 +327,35 @@ __device__ __forceinline__ int ct_insert_weighted(u64 *tab, const CtGeom &g, u64
     return -1;
 }
 
+// value = max(value, w), inserting the key if absent (makeKmerReadDistributionFromContig, counter.h:572-575: a k-mer of
+// several contigs keeps the largest coverage).  Same compare-and-swap protocol as ct_insert_weighted.
+__device__ __forceinline__ int ct_insert_max(u64 *tab, const CtGeom &g, u64 h, u64 w)
+{
+    const u64 home = h >> g.rbits;
+    const u64 r_hi = ((h << (64 - g.rbits)) >> (64 - g.rbits)) << CT_DISP_BITS;
+    if (w > COUNT_SAT) w = COUNT_SAT;
+#pragma unroll 1
+    for (u32 d = 0; d <= (u32)CT_MAX_DISP; ++d) {
+        u64 *s = tab + ((home + d) & g.capmask);
+        const u64 tag = (r_hi | (u64)(d + 1)) << g.cbits;
+        u64 cur = ld_cg_u64(s);
+        if (cur == 0) {
+            const u64 prev = atomicCAS(s, 0ull, tag | w);
+            if (prev == 0) return 1;
+            cur = prev;
+        }
+        if ((cur >> g.cbits) == (tag >> g.cbits)) {
+            for (;;) {
+                if ((cur & g.cmask) >= w) return 0;
+                const u64 prev = atomicCAS(s, cur, tag | w);
+                if (prev == cur) return 0;
+                cur = prev;
+            }
+        }
+    }
+    return -1;
+}
+
 // Read-only lookup (no insert kernel running): clamped count of the key with hash h, 0 if it is not in the table.
 // A key sits in the first slot of its probe sequence that was free when it arrived and nothing is ever removed, so
 // the search ends at the first empty slot.
@@ -408,6 +437,37 @@ __device__ __forceinline__ int wide_insert(Slot<W> *table, u64 cap, const u64 *k
     return -1;
 }
 
+// wide_insert with "largest value wins" instead of "values add up"
+template <int W>
+__device__ __forceinline__ int wide_insert_max(Slot<W> *table, u64 cap, const u64 *key, u64 h, u32 w)
+{
+    u64 idx = __umul64hi(h, cap);
+    int probe = 0;
+#pragma unroll 1
+    while (probe < MAX_PROBE) {
+        Slot<W> *s = table + idx;
+        u32 cs = ld_cg_u32(&s->cs);
+        if (cs == 0) {
+            const u32 old = atomicCAS(&s->cs, 0u, CS_LOCKED);
+            if (old == 0) {
+#pragma unroll
+                for (int j = 0; j < W; ++j) st_cg_u64(&s->key[j], key[j]);
+                st_release_u32(&s->cs, w);
+                return 1;
+            }
+            cs = old;
+        }
+        if (cs == CS_LOCKED) continue;                 // claimed, not yet published: look at the same slot again
+        bool eq = true;
+#pragma unroll
+        for (int j = 0; j < W; ++j) eq &= (ld_cg_u64(&s->key[j]) == key[j]);
+        if (eq) { atomicMax(&s->cs, w); return 0; }
+        ++probe;
+        idx = (idx + 1 == cap) ? 0 : idx + 1;
+    }
+    return -1;
+}
+
 template <int W>
 __device__ __forceinline__ u32 wide_lookup(const Slot<W> *table, u64 cap, const u64 *key, u64 h)
 {
@@ -467,6 +527,12 @@ struct Table {
         } else {
             return wide_insert<W>(slots, cap, key, h, w > COUNT_SAT ? COUNT_SAT : w);
         }
+    }
+    // value = max(value, w); 1 = new key, 0 = existing, -1 = no slot
+    __device__ __forceinline__ int insert_max(const u64 *key, u64 h, u32 w) const
+    {
+        if constexpr (W == 1) return ct_insert_max(slots, g, h, w);
+        else return wide_insert_max<W>(slots, cap, key, h, w > COUNT_SAT ? COUNT_SAT : w);
     }
     // clamped count of `key` (hash h), 0 if absent; only between insert kernels
     __device__ __forceinline__ u32 find(const u64 *key, u64 h) const

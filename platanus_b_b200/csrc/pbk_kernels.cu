@@ -86,6 +86,16 @@ void launch_lookup(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 wo
             Table<W>(table.slots, table.cap), (u64 *)occ)));
 }
 
+void launch_contig_max(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
+                       TableView table, const uint16_t *val, Counters *ctr, int sm_count, cudaStream_t st)
+{
+    if (word_end <= word_begin) return;
+    const int grid = grid_for(word_end - word_begin, 256, sm_count, 8);
+    PBK_DISPATCH_W(table.words,
+        (contig_max_kernel<W><<<grid, 256, 0, st>>>(stream, nflag, rflag, word_begin, word_end, k,
+            Table<W>(table.slots, table.cap), val, ctr)));
+}
+
 void launch_override_records(const u64 *records, u64 n, TableView table, Counters *ctr, u64 *overflow_keys, u64 overflow_cap,
                              int sm_count, cudaStream_t st)
 {

@@ -39,6 +39,9 @@ void launch_count(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 wor
 // that ENDS at p, 0 if unusable or absent.  Read-only on the table.
 void launch_lookup(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
                    TableView table, uint16_t *occ, int sm_count, cudaStream_t st);
+// table[k-mer of the window ending at p] = max(itself, val[p]) over stream words [word_begin, word_end)
+void launch_contig_max(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
+                       TableView table, const uint16_t *val, Counters *ctr, int sm_count, cudaStream_t st);
 // SET the count of n (key words..., value) records (insert those that are absent); value 0 = skip
 void launch_override_records(const u64 *records, u64 n, TableView table, Counters *ctr, u64 *overflow_keys, u64 overflow_cap,
                              int sm_count, cudaStream_t st);

@@ -351,6 +351,74 @@ insert_records_kernel(const u64 *__restrict__ rec, u64 n, int weighted, Table<W>
     }
 }
 
+// Table from contigs (makeKmerReadDistributionFromContig, counter.h:511-593): every k-mer window of a contig gets
+// max(its value so far, value of the contig), the contig's value = max(coverage, minOccurrence) supplied per stream position
+// (val[p] for the window ENDING at p).  Same window enumeration as count_kernel.  Windows with an N are skipped (the
+// reference does not skip them and feeds code 4 into the 2-bit fields; its contigs never contain N at this point).
+template <int W>
+__global__ void __launch_bounds__(256)
+contig_max_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, const u32 *__restrict__ rflag,
+                  u64 word_begin, u64 word_end, int k, Table<W> table, const uint16_t *__restrict__ val, Counters *ctr)
+{
+    const int top_shift = 2 * ((k - 1) & 31);
+    const u64 top_mask = (k & 31) ? ((1ull << (2 * (k & 31))) - 1ull) : ~0ull;
+    const int s = 2 * (32 * W - k);
+    const int nb = (k + 30) >> 5;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    u32 newk = 0;
+    for (u64 wi = word_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; wi < word_end; wi += stride) {
+        const u64 cur = stream[wi];
+        const u32 nf = nflag[wi], rf = rflag[wi];
+        int run = k;
+        for (int j = 1; j <= nb; ++j) {
+            const u32 a = nflag[wi - j], b = rflag[wi - j];
+            if (a | b) {
+                const int pn = a ? 32 - __clz(a) : 0;
+                const int pr = b ? 31 - __clz(b) : 0;
+                run = 32 * j - max(pn, pr);
+                break;
+            }
+        }
+        u64 fwd[W], rev[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) fwd[j] = stream[wi - 1 - j];
+        {
+            u64 y[W + 1];
+#pragma unroll
+            for (int j = 0; j < W; ++j) y[j] = pair_reverse64(~fwd[W - 1 - j]);
+            y[W] = 0;
+#pragma unroll
+            for (int j = 0; j < W; ++j) rev[j] = s ? ((y[j] >> s) | (y[j + 1] << (64 - s))) : y[j];
+        }
+#pragma unroll 2
+        for (int i = 0; i < 32; ++i) {
+            const u32 b = (u32)(cur >> (62 - 2 * i)) & 3u;
+            if ((rf >> i) & 1u) run = 0;
+            run = ((nf >> i) & 1u) ? 0 : run + 1;
+#pragma unroll
+            for (int j = W - 1; j > 0; --j) fwd[j] = (fwd[j] << 2) | (fwd[j - 1] >> 62);
+            fwd[0] = (fwd[0] << 2) | b;
+            fwd[W - 1] &= top_mask;
+#pragma unroll
+            for (int j = 0; j < W - 1; ++j) rev[j] = (rev[j] >> 2) | (rev[j + 1] << 62);
+            rev[W - 1] = (rev[W - 1] >> 2) | ((u64)(3u - b) << top_shift);
+            if (run >= k) {
+                const u32 v = val[wi * 32 + i];
+                if (v == 0) continue;                               // a value of 0 is "no entry" (counter.h:490)
+                const bool use_rev = key_less<W>(rev, fwd);
+                u64 key[W];
+#pragma unroll
+                for (int j = 0; j < W; ++j) key[j] = use_rev ? rev[j] : fwd[j];
+                const int r = table.insert_max(key, hash_key<W>(key), v);
+                newk += (r > 0);
+                if (r < 0) atomicAdd(&ctr->overflow_n, 1ull);       // the caller sized the table for every window: treated as an error
+            }
+        }
+    }
+    newk = warp_sum_u32(newk);
+    if ((threadIdx.x & 31) == 0 && newk) atomicAdd(&ctr->new_keys, (u64)newk);
+}
+
 // Seeded entries (makeKmerReadDistributionConsideringPreviousGraph, counter.h:663-750): a k-mer that was in the table
 // before the reads were counted keeps its seeded value -- the reference never counts read windows that hit the table
 // (divideKmerUsedMakingPreviousContig, counter.h:828-861) and dumps the table as it was (counter.h:695-705).  Counting

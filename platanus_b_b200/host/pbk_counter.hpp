@@ -183,6 +183,13 @@ public:
         check(pbk_seed_entries(ctx_, keys, values, n), "pbk_seed_entries");
     }
 
+    // ---- Counter::makeKmerReadDistributionFromContig (counter.h:511-593) on contigs held in memory (ASCII, concatenated):
+    //      beginCounting(k); pushContigs(...); endCounting(memory) leaves the distribution writeKmerDistribution would
+    void pushContigs(const uint8_t *bases, const uint64_t *offsets, uint64_t n, const uint16_t *coverage, u64_t minOccurrence)
+    {
+        check(pbk_push_contigs(ctx_, bases, offsets, n, coverage, minOccurrence), "pbk_push_contigs");
+    }
+
     // ---- counter.h:1000-1007 ----------------------------------------------------------------------
     void outputOccurrenceDistribution(const std::string &filename)
     {

@@ -44,6 +44,7 @@ template <typename T, typename U, typename V> static inline T atomicCAS(T *p, U 
     if (o == (T)cmp) *p = (T)val;
     return o;
 }
+template <typename T, typename U> static inline T atomicMax(T *p, U v) { T o = *p; if ((T)v > o) *p = (T)v; return o; }
 template <typename T, typename U> static inline T atomicExch(T *p, U v) { T o = *p; *p = (T)v; return o; }
 static inline void __threadfence() {}
 static inline void __syncthreads() {}

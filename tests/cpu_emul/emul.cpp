@@ -303,3 +303,39 @@ extern "C" int emul_seeded(const uint8_t *bases, const u64 *off, u64 n_reads, in
 #define SD(Wv) case Wv: return run_seeded<Wv>(bases, off, n_reads, k, seed_keys, seed_counts, n_seed, keys_out, counts_out, cap_out, n_out, n_inst, matched);
     switch ((k + 31) / 32) { SD(1) SD(2) SD(3) SD(4) SD(5) SD(6) SD(7) SD(8) default: return -1; }
 }
+
+// ---- table from contigs (pbk_push_contigs) -------------------------------------------------------------------------------
+template <int W>
+static int run_contigs(const uint8_t *bases, const u64 *off, u64 n_seqs, int k, const uint16_t *coverage, u64 min_occ,
+                       u64 *keys_out, uint16_t *counts_out, u64 cap_out, u64 *n_out)
+{
+    const u64 n_bases = off[n_seqs], words = (n_bases + 31) / 32;
+    std::vector<u64> stream(words + STREAM_PAD_WORDS + 1, 0), len_hist(500001, 0);
+    std::vector<u32> nflag(words + STREAM_PAD_WORDS + 1, 0), rflag(words + STREAM_PAD_WORDS + 1, 0);
+    std::vector<uint16_t> val(words * 32, 0);
+    for (u64 r = 0; r < n_seqs; ++r) {
+        const u64 v = std::min<u64>(std::max<u64>(coverage[r], min_occ), COUNT_SAT);
+        for (u64 p = off[r]; p < off[r + 1]; ++p) val[p] = (uint16_t)v;
+    }
+    Counters ctr{};
+    typedef typename SlotType<W>::type slot_t;
+    const u64 slots = W == 1 ? (1ull << 24) : 2 * n_bases + 1024;
+    std::vector<slot_t> tv(slots);
+    memset(tv.data(), 0, tv.size() * sizeof(slot_t));
+    Table<W> table(tv.data(), tv.size());
+    read_marks_kernel(off, n_seqs, len_hist.data(), rflag.data() + STREAM_PAD_WORDS, &ctr);
+    pack_kernel<false>(bases, n_bases, words, 0, stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, 0, &ctr);
+    contig_max_kernel<W>(stream.data() + STREAM_PAD_WORDS, nflag.data() + STREAM_PAD_WORDS, rflag.data() + STREAM_PAD_WORDS, 0, words, k,
+                         table, val.data(), &ctr);
+    if (ctr.overflow_n) return -2;
+    *n_out = 0;
+    export_kernel<W>(table, 1, keys_out, counts_out, cap_out, n_out);
+    return 0;
+}
+
+extern "C" int emul_contigs(const uint8_t *bases, const u64 *off, u64 n_seqs, int k, const uint16_t *coverage, u64 min_occ,
+                            u64 *keys_out, uint16_t *counts_out, u64 cap_out, u64 *n_out)
+{
+#define CT(Wv) case Wv: return run_contigs<Wv>(bases, off, n_seqs, k, coverage, min_occ, keys_out, counts_out, cap_out, n_out);
+    switch ((k + 31) / 32) { CT(1) CT(2) CT(3) CT(4) CT(5) CT(6) CT(7) CT(8) default: return -1; }
+}

@@ -225,3 +225,22 @@ def abi_cli_path() -> str:
         subprocess.run(["g++", "-O2", "-std=c++11", "-Wall", "-Wextra", "-pthread", "-o", exe, srcs[0], "-L" + build, "-lpbk",
                         "-Wl,-rpath,$ORIGIN"], check=True, env=env)
     return exe
+
+
+def emul_contigs(bases, offsets, k: int, coverage, min_occurrence: int = 1):
+    """contig_max_kernel (pbk_push_contigs): sorted (keys, values) of the table built from contigs and their coverages."""
+    W = (k + 31) // 32
+    bases = np.concatenate([np.ascontiguousarray(bases, dtype=np.uint8), np.zeros(64, np.uint8)])
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    cov = np.ascontiguousarray(coverage, dtype=np.uint16)
+    cap = int(offsets[-1]) + 1
+    keys = np.zeros((cap, W), np.uint64)
+    counts = np.zeros(cap, np.uint16)
+    n_out = C.c_uint64()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().emul_contigs(p(bases), p(offsets), C.c_uint64(len(offsets) - 1), k, p(cov), C.c_uint64(min_occurrence), p(keys), p(counts),
+                            C.c_uint64(cap), C.byref(n_out))
+    assert rc == 0, rc
+    keys, counts = keys[:n_out.value], counts[:n_out.value]
+    order = np.lexsort(tuple(keys[:, w] for w in range(W)))
+    return keys[order], counts[order]

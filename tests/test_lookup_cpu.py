@@ -190,3 +190,31 @@ def test_kernels_iterative_k_steps_match_the_reference(oracle, path):
     assert np.array_equal(emul_match_reads(bases, offs, k, g["table_keys"], g["table_counts"]), g["kept"])
     keys, counts, n_inst = emul_seeded_count(bases, offs, k, g["table_keys"], g["table_counts"])
     assert np.array_equal(keys, g["keys"]) and np.array_equal(counts, g["counts"])
+
+
+# ---- table from contigs (makeKmerReadDistributionFromContig, counter.h:511-593) ---------------------------------------------
+CONTIG_CASES = sorted(glob.glob(os.path.join(G.GOLDEN, "contig_k*.npz")), key=lambda p: int(os.path.basename(p)[8:-4]))
+
+
+def contig_seqs(O, g):
+    rd = O.Reads()
+    for s in parse_fasta(str(g["contigs_fa"])):
+        rd.add(s.encode())
+    return rd
+
+
+@pytest.mark.parametrize("path", CONTIG_CASES, ids=lambda p: os.path.basename(p)[:-4])
+def test_contig_table_matches_the_reference(oracle, path):
+    """tests/golden/contig_k*.npz: the kmerFP records the UNMODIFIED reference's makeKmerReadDistributionFromContig writes
+    (oracle/ref_iter_harness.cpp mode contig, oracle/make_golden_contig.py) -- oracle restatement and the product kernel."""
+    from emul_helper import emul_contigs
+    O = oracle
+    g = np.load(path, allow_pickle=False)
+    k, min_occ = int(g["k"]), int(g["min_occ"])
+    rd = contig_seqs(O, g)
+    res = O.count_contigs(rd, k, g["coverage"], min_occ)
+    assert np.array_equal(res.keys, g["keys"]) and np.array_equal(res.counts, g["counts"]) and res.max_occ == int(g["max_occ"])
+    assert len(set(g["counts"].tolist())) >= 4                    # overlapping contigs: the larger coverage must have won somewhere
+    bases, offs = rd.arrays()
+    keys, counts = emul_contigs(bases, offs, k, g["coverage"], min_occ)
+    assert np.array_equal(keys, g["keys"]) and np.array_equal(counts, g["counts"])

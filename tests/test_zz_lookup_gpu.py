@@ -147,3 +147,33 @@ def test_lookup_and_seeds_with_hash_range_shards(oracle, k, n_shards):
     W = (k + 31) // 32
     order = np.lexsort(tuple(keys[:, w] for w in range(W)))
     assert np.array_equal(keys[order], g["table_keys"]) and np.array_equal(counts[order], g["table_counts"])
+
+
+from test_lookup_cpu import CONTIG_CASES, contig_seqs          # noqa: E402
+
+
+@pytest.mark.parametrize("path", CONTIG_CASES, ids=lambda p: os.path.basename(p)[:-4])
+def test_contig_table_matches_the_reference(oracle, path):
+    """pbk_push_contigs = Counter::makeKmerReadDistributionFromContig (counter.h:511-593) against the reference's own output;
+    pushed in two calls and in the other order as well: the maximum does not care."""
+    O = oracle
+    g = np.load(path, allow_pickle=False)
+    k, min_occ = int(g["k"]), int(g["min_occ"])
+    rd = contig_seqs(O, g)
+    bases, offs = rd.arrays()
+    cov = g["coverage"].astype(np.uint16)
+    want = O.count_contigs(rd, k, cov, min_occ)
+    n = len(offs) - 1
+    for order in ("one call", "two calls, reversed"):
+        with KmerCounter(k) as kc:
+            if order == "one call":
+                kc.push_contigs(bases, offs, cov, min_occ)
+            else:
+                h = n // 2
+                kc.push_contigs(bases[int(offs[h]):], offs[h:] - offs[h], cov[h:], min_occ)
+                kc.push_contigs(bases[:int(offs[h])], offs[:h + 1], cov[:h], min_occ)
+            kc.finalize()
+            keys, counts = kc.export(1, sorted=True)
+            assert np.array_equal(keys, g["keys"]) and np.array_equal(counts, g["counts"])
+            assert kc.max_occurrence == int(g["max_occ"]) and np.array_equal(kc.occ_hist, want.occ_hist)
+            assert kc.n_instances == 0
