@@ -73,7 +73,7 @@ def one_case(rng, case_no):
     rd = oracle_reads(reads)
     want = O.count(rd, k)
     b, o = as_arrays(reads)
-    mode = rng.choice(["plain", "multi_push", "seeded", "lookup", "records", "keys"])
+    mode = rng.choice(["plain", "multi_push", "seeded", "lookup", "records", "keys", "contigs"])
     if mode == "keys" and W > 1:
         mode = "records"
     partition = rng.choice([True, "force", False])
@@ -108,6 +108,19 @@ def one_case(rng, case_no):
                 kc.seed_entries(sk, sc); kc.push_reads(b, o)
             else:
                 kc.push_reads(b, o); kc.seed_entries(sk, sc)
+            kc.finalize()
+            check_table(kc, ref, desc)
+    elif mode == "contigs":
+        seqs = [r.replace("N", "A").replace("n", "a") for r in reads]           # (the reference does not skip N windows of contigs)
+        crd = oracle_reads(seqs)
+        cb, co = as_arrays(seqs)
+        cov = np.array([rng.choice([0, 1, 5, 40, 300, 65534]) for _ in seqs], np.uint16)
+        min_occ = rng.choice([0, 1, 3])
+        ref = O.count_contigs(crd, k, cov, min_occ)
+        with KmerCounter(k) as kc:
+            h = rng.randint(0, len(seqs))
+            kc.push_contigs(cb[:int(co[h])], co[:h + 1], cov[:h], min_occ)
+            kc.push_contigs(cb[int(co[h]):], co[h:] - co[h], cov[h:], min_occ)
             kc.finalize()
             check_table(kc, ref, desc)
     elif mode == "lookup":
