@@ -374,8 +374,10 @@ def main_ours(args):
     ms_pair = d_res["ms_count_elapsed"] / args.steps
     direct = d_res["ms_count"] - d_res["ms_partition"] - d_res["ms_insert"]      # non-partitioned launches (small batches)
     achieved = bpi * n_inst_local / (ms_pair * 1e-3) / 1e9 if ms_pair > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "partition_kernel<1> + bucket_insert_compact_kernel<false> (Pass A + Pass B: "
-                                          "each instance goes through both exactly once)",
+    roofline = {"bound": "hbm", "kernel": ("partition_kernel<1, KEYX> + bucket_insert_compact_kernel<2> (Pass A into the all-to-all send "
+                                          "buffer + Pass B over the received keys: each instance goes through both exactly once)" if keyx else
+                                          "partition_kernel<1> + bucket_insert_compact_kernel<0> (Pass A + Pass B: "
+                                          "each instance goes through both exactly once)"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic_bytes(), "peak_source": peak_src, "algorithmic_bytes_per_instance": bpi,
                 "instances_per_launch": n_inst_local, "ms_per_launch": ms_pair,
