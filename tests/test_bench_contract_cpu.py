@@ -60,3 +60,18 @@ def test_committed_bench_line_has_every_contract_key():
     assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(line["clocks"]) and line["clocks"]["sm_mhz"] is not None
     assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert line["gpu_launches"] > 0 and line["warmup"] >= 3
+
+
+def test_bench_flows_run_end_to_end_on_the_emulated_abi(tmp_path):
+    """scripts/bench_dry_run.py: bench.py's own control flow -- N = 1, and N = 2 over gloo with the record exchange, the key
+    exchange and the device-ordered key exchange + --write-outputs -- against the C ABI compiled for the host, torch.cuda
+    stubbed out.  A check of the script (every flow reaches its JSON line with the contract keys), not a measurement."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "scripts", "bench_dry_run.py"), "--tmp", str(tmp_path)], cwd=root,
+                       capture_output=True, text=True, timeout=1500)
+    assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-3000:]
+    for flow in ("n1", "records", "keys", "keys_async"):
+        assert f"flow {flow}: ok" in p.stdout
+    assert os.path.exists(tmp_path / "bench_dry_out_32merFrq.tsv") and os.path.exists(tmp_path / "bench_dry_out_kmer_occ.bin")
