@@ -1448,7 +1448,7 @@ int pbk_keyx_insert_device(pbk_ctx *c, const void *d_recv, const void *d_recv_cu
         TRY(maybe_clamp(c, c->keyx_last_total + c->keyx_last_total / 8));
         if ((double)(c->occupied + expect) > max_load(c) * (double)c->table.capacity())
             TRY(grow_table(c, &c->table, c->occupied, (u64)((c->occupied + expect) / max_load(c)) + 1));
-        TRY(ensure_overflow(c, 1ull << 22));
+        TRY(ensure_overflow_for_batch(c, c->keyx_last_total + c->keyx_last_total / 8));
         {
             Span sp(c, LC_INSERT);
             launch_bucket_insert_gathered_chained((const u64 *)d_recv, (const u64 *)d_recv_cursors, seg_cap, c->d_passb, G, R, c->table,
@@ -1474,7 +1474,7 @@ int pbk_keyx_insert_device(pbk_ctx *c, const void *d_recv, const void *d_recv_cu
         TRY(table_alloc(c, &c->table, round_slots(c, want)));
     }
     TRY(maybe_clamp(c, total));
-    TRY(ensure_overflow(c, 1ull << 22));
+    TRY(ensure_overflow_for_batch(c, total));          // a first batch of mostly new keys can overrun the pilot's table regions
     auto room_for = [&](u64 expect_new) -> int {
         if ((double)(c->occupied + expect_new) > max_load(c) * (double)c->table.capacity())
             return grow_table(c, &c->table, c->occupied, (u64)((c->occupied + expect_new) / max_load(c)) + 1);
