@@ -21,7 +21,7 @@ def run_child(args, timeout):
     emul_helper.abi_lib_path()                       # built here, once: the child's workers only find them up to date
     emul_helper.abi_cli_path()
     env = dict(os.environ, PBK_TEST_EMULATED_ABI="1")
-    workers = ["-n", str(min(4, os.cpu_count() or 1))] if (os.cpu_count() or 1) >= 4 else []      # pytest-xdist: the cases are independent
+    workers = ["-n", str(min(6, os.cpu_count() or 1))] if (os.cpu_count() or 1) >= 4 else []      # pytest-xdist: the cases are independent
     return subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "--runxfail", "-p", "no:cacheprovider", "-x", *workers, *args],
                           cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
 
@@ -36,15 +36,19 @@ def test_emulated_abi_builds_and_exports_the_abi():
         assert hasattr(L, name), name
 
 
-@pytest.mark.parametrize("selection", [
-    ["tests/test_zz_keyx_gpu.py"],
-    ["tests/test_zz_lookup_gpu.py"],
-    ["tests/test_gpu_parity.py", "-k", "golden_cases and (kat_k4 or smallfq_k32 or smallfq_k75 or smallfa_k200 or cov_k21_auto or multi_k32_n2 or sat_k32)"],
-    ["tests/test_gpu_parity.py", "-k", "table_growth or error_behaviour or pipelined_pass_overlap"],
-    ["tests/test_cli_gpu.py"],
-], ids=["key_exchange", "lookup_and_iterative_k", "golden_cases", "sharding_growth_errors", "pbk_assemble_vs_reference_program"])
-def test_gpu_tests_pass_against_the_emulated_abi(selection):
-    p = run_child(selection, timeout=1500)
+SELECTION = (
+    ["tests/test_zz_keyx_gpu.py", "tests/test_zz_lookup_gpu.py", "tests/test_cli_gpu.py"]
+    + [f"tests/test_gpu_parity.py::test_golden_cases_bit_exact[{c}]"
+       for c in ("kat_k4", "smallfq_k32", "smallfq_k75", "smallfa_k200", "cov_k21_auto", "multi_k32_n2", "sat_k32")]
+    + ["tests/test_gpu_parity.py::test_table_growth_from_a_tiny_hint", "tests/test_gpu_parity.py::test_error_behaviour"])
+# (tests/test_gpu_parity.py::test_pipelined_pass_overlap_gives_the_identical_table also passes this way, but its batch of > 4 M
+#  windows takes 80 s in the emulation: run by hand when the chained Pass A -> Pass B route of pbk_api.cu changes)
+
+
+def test_gpu_tests_pass_against_the_emulated_abi():
+    """key exchange, lookup / read filter / seeded counting / contig tables, pbk_assemble against the reference program, a
+    subset of the golden cases, table growth, error behaviour -- one child pytest, xdist workers"""
+    p = run_child(SELECTION, timeout=2000)
     tail = "\n".join(p.stdout.splitlines()[-25:])
     assert p.returncode == 0, tail + "\n" + p.stderr[-2000:]
     assert " passed" in tail and "failed" not in tail, tail
