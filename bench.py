@@ -43,7 +43,8 @@ UNIT = "k-mers/s"
 BYTES_PER_INSTANCE = {150: 65.26, 250: 65.14}          # SURVEY.md section 8d (k=32)
 CPU_FULL_RUN_S = 20.0                                   # one reference run over the whole C1 workload on a 16-core host
 REF_MEM_GB = 16                                         # the reference's default -m
-CPU_BUDGET_S = 180.0                                    # the reference arm must finish within a few minutes
+CPU_BUDGET_S = 620.0                                    # the reference arm counts the WHOLE C1 read set for the driver's --steps 20 --warmup 5
+                                                        # (25 runs x ~20 s on 16 cores): same config as our arm, not a flattering fraction
 
 
 def algorithmic_bytes_per_instance(read_len: int, k: int) -> float:
@@ -209,6 +210,57 @@ def main_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------------
 
+def verify_result(kc, step, world, rank, n_inst_local, total_inst, hist_dev, d_bases, d_offs, n_reads, n_bases, recount=True):
+    """After the timed steps: one more step whose result is CHECKED (a lost or duplicated exchange chunk must not print a
+    throughput).  (1) every rank's own window count, all-reduced, equals the expected total; (2) sum of i * hist[i] over the
+    all-reduced occurrence histogram equals it too (when nothing saturated); (3) N > 1: rank 0 gathers every rank's reads over
+    NCCL and recounts them on ONE unsharded context -- the all-reduced histogram and the number of distinct k-mers must be identical."""
+    import torch
+    import torch.distributed as dist
+
+    from platanus_b_b200 import KmerCounter
+    step(True)
+    hist = kc.occ_hist.astype(np.int64)
+    inst, distinct = int(kc.n_instances), int(kc.n_distinct)
+    if world > 1:
+        hist = hist_dev.cpu().numpy()                               # step() left the all-reduced histogram there
+        t = torch.tensor([inst, distinct], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        inst, distinct = int(t[0].item()), int(t[1].item())
+    else:
+        assert inst == n_inst_local, (inst, n_inst_local)
+    assert inst == total_inst, ("instances counted over all ranks", inst, total_inst)
+    weighted = int((hist * np.arange(hist.shape[0], dtype=np.int64)).sum())
+    assert int(hist.sum()) == distinct, ("distinct k-mers vs histogram", int(hist.sum()), distinct)
+    assert weighted == total_inst if hist[65534] == 0 else weighted <= total_inst, ("sum i*hist[i]", weighted, total_inst)
+    out = {"instances": inst, "sum_i_hist_i": weighted, "distinct": distinct, "single_gpu_recount": None}
+    if world > 1 and recount:
+        sizes = torch.tensor([n_reads, n_bases], dtype=torch.int64, device="cuda")
+        all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+        dist.all_gather(all_sizes, sizes)
+        if rank == 0:
+            with KmerCounter(K, device=int(os.environ.get("LOCAL_RANK", "0"))) as one:
+                one.push_reads_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, n_bases)
+                for src in range(1, world):
+                    nr, nb = (int(x) for x in all_sizes[src].tolist())
+                    rb = torch.empty(nb, dtype=torch.uint8, device="cuda")
+                    ro = torch.empty(nr + 1, dtype=torch.int64, device="cuda")
+                    dist.recv(rb, src=src)
+                    dist.recv(ro, src=src)
+                    torch.cuda.synchronize()
+                    one.push_reads_device(rb.data_ptr(), ro.data_ptr(), nr, nb)
+                one.finalize()
+                assert int(one.n_instances) == total_inst, (int(one.n_instances), total_inst)
+                assert int(one.n_distinct) == distinct, ("distinct: sharded vs one GPU", distinct, int(one.n_distinct))
+                assert np.array_equal(one.occ_hist.astype(np.int64), hist), "all-reduced histogram differs from the single-GPU recount"
+            out["single_gpu_recount"] = "identical histogram and distinct count (all ranks' reads recounted unsharded on rank 0)"
+        else:
+            dist.send(d_bases, dst=0)
+            dist.send(d_offs, dst=0)
+        dist.barrier()
+    return out
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -356,8 +408,9 @@ def main_ours(args):
     kc.set_timing(True)
     ms_inst, _, d_res, _, _ = timed(True, args.steps, 1)
 
-    # sanity: the counter saw exactly the windows we expect
-    assert kc.n_instances == n_inst_local or world > 1, (kc.n_instances, n_inst_local)
+    # sanity: the counter saw exactly the windows we expect -- on every rank, and the exchanged result is the right one
+    verified = verify_result(kc, step, world, rank, n_inst_local, total_inst, hist_dev, d_bases, d_offs, n_reads, n_bases,
+                             recount=not args.no_verify_recount)
 
     value = total_inst * args.steps / (ms_res * 1e-3)
     e2e = total_inst * args.steps / (ms_e2e * 1e-3)
@@ -417,6 +470,7 @@ def main_ours(args):
                                    "count_partition_pass": d_res["ms_partition"] / args.steps,
                                    "count_insert_pass": d_res["ms_insert"] / args.steps},
             "wall_ms_per_step": wall_res / args.steps,
+            "verified": verified,
             "table": {"slots": int(kc.stats()["table_slots"]), "bytes": int(kc.stats()["table_bytes"]),
                       "distinct_local": int(kc.n_distinct), "grows_in_timed_region": int(d_res["n_grow"])},
         }
@@ -459,6 +513,7 @@ def main():
                     help="N > 1: what crosses NVLink -- (key, count) records after counting, or the keys before it")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify-recount", action="store_true", help="N > 1: skip the single-GPU recount of all ranks' reads on rank 0 (the sum checks stay)")
     ap.add_argument("--ref-mem-gb", type=int, default=REF_MEM_GB, help="-m of the reference arm (its default is 16)")
     args = ap.parse_args()
     globals()["REF_MEM_GB"] = args.ref_mem_gb

@@ -86,11 +86,7 @@ def _keyx_logical_shards(O, b, o, k, n_shards):
             d.free()
 
 
-UNRUN = pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: passes against the host-emulated ABI (tests/test_abi_emulated_cpu.py), never run on a B200 yet "
-                                               "(XPASS = passes; the mark goes away once seen to pass)")
-
-
-@pytest.mark.parametrize("k,n_shards", [(32, 2), pytest.param(21, 3, marks=UNRUN), pytest.param(32, 8, marks=UNRUN)])
+@pytest.mark.parametrize("k,n_shards", [(32, 2), (21, 3), (32, 8)])
 def test_key_exchange_logical_shards_match_unsharded(oracle, k, n_shards):
     """SURVEY.md section 8e, second form of the exchange (include/pbk.h, pbk_keyx_*): the keys travel before counting."""
     O = oracle
@@ -104,7 +100,6 @@ def test_key_exchange_logical_shards_match_unsharded(oracle, k, n_shards):
     assert max(sizes) < 1.2 * (sum(sizes) / n_shards) + 64
 
 
-@UNRUN
 def test_key_exchange_full_segments_take_the_record_route(oracle, tmp_path):
     """70 000 copies of one read: ten k-mers with 70 000 instances each overflow their (destination, region) segments;
     the surplus is pre-aggregated in the remote-staging table and reaches its owner as (key, count) records.  Counts
@@ -120,7 +115,6 @@ def test_key_exchange_full_segments_take_the_record_route(oracle, tmp_path):
     assert inst == want.n_instances and np.array_equal(hist, want.occ_hist)
 
 
-@UNRUN
 def test_heavily_duplicated_input_cannot_exhaust_the_overflow_list(oracle):
     """Amplicon-like input: 1.2 M copies of one 41 bp read = 12 M windows of ten k-mers.  Each k-mer has 1.2 M instances
     but its bucket segment holds ~0.2 M, so ~10 M windows spill in Pass A -- more than the 4 M records the overflow list

@@ -1,7 +1,7 @@
 """Occurrence lookup on the B200 through the C ABI (pbk_lookup, pbk_load_entries, pbk_read_kmer_occ_bin; SURVEY.md
 section 8f rows 1-2) against the reference's own getOccurrenceArray output (tests/golden/occ_k*.npz) and the oracle.
-Written after round 1's GPU budget was spent: NOT yet run on a B200 (the kernel's logic is covered on CPU by
-tests/test_lookup_cpu.py through the host emulation); the file sorts last so that it cannot mask other results."""
+First seen to pass on a B200 at the end of round 1 (GPUTEST_r01); the kernel's logic is also covered on CPU by
+tests/test_lookup_cpu.py through the host emulation."""
 import ctypes as C
 import os
 
@@ -12,9 +12,7 @@ import golden_cases as G
 from platanus_b_b200 import KmerCounter, synth
 from test_lookup_cpu import CASES, contig_reads, expected_per_base
 
-# xfail(strict=False): these run and report at round end (XPASS = they pass on the B200) without turning the suite red if the
-# first run on hardware finds something; the mark goes away as soon as they have been seen to pass.
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread"), pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: passes against the host-emulated ABI (tests/test_abi_emulated_cpu.py), never run on a B200 yet")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
 
 
 @pytest.mark.parametrize("path", CASES, ids=lambda p: os.path.basename(p)[:-4])
