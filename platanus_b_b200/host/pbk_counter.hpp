@@ -118,6 +118,12 @@ public:
     u64_t makeKmerReadDistributionMT(u64_t kLength, FILE **readFP, u64_t memory, u64_t numThread)
     {
         beginCounting(kLength);
+        pushSeqTempFiles(readFP, numThread);
+        return endCounting(memory);
+    }
+    // the reads of numThread SEQ temp files (common.h:426-448), in batches of 256 MB, through PBK_ENC_PLATANUS
+    void pushSeqTempFiles(FILE **readFP, u64_t numThread)
+    {
         std::vector<uint8_t> bases;
         std::vector<uint64_t> offsets(1, 0), nposOff(1, 0);
         std::vector<int32_t> npos;
@@ -140,7 +146,6 @@ public:
             }
         }
         flushPlatanus(bases, offsets, npos, nposOff);
-        return endCounting(memory);
     }
 
     // ---- counter.h:967-993: PREFIX_kmer_occ.bin -> table (device resident), occurrenceDistribution, maxOccurrence ------
@@ -174,6 +179,19 @@ public:
     void matchReads(const uint8_t *bases, const uint64_t *offsets, uint64_t n, uint8_t *matched)
     {
         check(pbk_match_reads(ctx_, bases, offsets, n, PBK_ENC_ASCII, NULL, NULL, matched), "pbk_match_reads");
+    }
+
+    // the same on reads in the SEQ temp-file form (bytes 0..3 + N position list), as the patched reference holds them
+    void matchReadsPlatanus(const uint8_t *bases, const uint64_t *offsets, uint64_t n, const int32_t *npos, const uint64_t *nposOffsets,
+                            uint8_t *matched)
+    {
+        static const int32_t none = 0;
+        check(pbk_match_reads(ctx_, bases, offsets, n, PBK_ENC_PLATANUS, npos ? npos : &none, nposOffsets, matched), "pbk_match_reads");
+    }
+    // (key, value) entries into the table: what setOccurrenceValue (counter.h:92) does on the host DoubleHash
+    void loadEntries(const uint64_t *keys, const uint16_t *values, uint64_t n)
+    {
+        check(pbk_load_entries(ctx_, keys, values, n), "pbk_load_entries");
     }
 
     // ---- Counter::makeKmerReadDistributionConsideringPreviousGraph (counter.h:663-750), wide seam: beginCounting(k);
