@@ -9,7 +9,10 @@ histogram (+ hash-range exchange and histogram all-reduce when N > 1).
 
   value  whole-job k-mer instances/s with the reads already resident in HBM (pbk_push_reads_device)
   e2e    the same through the reference-facing C ABI with HOST buffers: H2D of the reads from pinned
-         memory and D2H of the histogram inside the timed region (pbk_push_reads + pbk_finalize)
+         memory, D2H of the occurrence histogram, the coverage cutoff, and the sorted (key, count)
+         entries >= cutoff back in host memory (pbk_push_reads + pbk_finalize + pbk_export) -- everything
+         the reference's makeKmerReadDistributionMT .. sortedKeyFromKmerFile leave behind -- inside the
+         timed region
 
 N = 1 runs BASELINE config C1 (4.6 Mb genome, 2x150 bp, 100x, k=32).  N > 1 is weak scaling of the same
 configuration: every rank counts its own C1-sized sample of the same genome, keys are owned by hash range
@@ -23,6 +26,7 @@ OpenMP, all host cores) on a bounded sample of the same workload; the same run i
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import shutil
@@ -346,6 +350,24 @@ def main_ours(args):
         return kx.step(len(ch), partition, torch.cuda.current_stream().synchronize,
                        caller_stream=(lambda: torch.cuda.current_stream().cuda_stream) if ordered else None)
 
+    export_bufs = {}
+
+    def export_kept(global_hist=None):
+        """e2e only: the path's result as the reference's caller gets it -- coverage cutoff (assemble.cpp:318-321) from the
+        (all-reduced) histogram, then this rank's entries >= cutoff, sorted on the GPU, copied into pinned host memory."""
+        if global_hist is not None:
+            occ = np.ascontiguousarray(global_hist.astype(np.uint64))
+            nz = np.nonzero(occ[1:])[0]
+            cutoff = int(kc._L.pbk_coverage_cutoff(occ.ctypes.data_as(C.c_void_p), int(nz[-1]) + 1 if len(nz) else 0, 0, 0))
+        else:
+            cutoff = kc.coverage_cutoff()
+        n = kc.export_count(cutoff)
+        if export_bufs.get("cap", 0) < n:
+            cap = int(n * 1.25) + 1024
+            export_bufs.update(cap=cap, keys=torch.empty((cap, W), dtype=torch.int64).pin_memory(), counts=torch.empty(cap, dtype=torch.int16).pin_memory())
+        got = kc.export_into(cutoff, True, export_bufs["keys"].data_ptr(), export_bufs["counts"].data_ptr(), export_bufs["cap"])
+        export_bufs.update(n=got, cutoff=cutoff)
+
     def step(resident: bool):
         kc.reset()
         if keyx:
@@ -361,6 +383,8 @@ def main_ours(args):
             hist_dev.copy_(torch.from_numpy(kc.occ_hist.astype(np.int64)), non_blocking=False)
             sharding.allreduce_histogram(hist_dev)
             torch.cuda.current_stream().synchronize()
+        if not resident:
+            export_kept(hist_dev.cpu().numpy() if world > 1 else None)
         return sent
 
     def timed(resident: bool, steps: int, warmup: int):
@@ -429,10 +453,13 @@ def main_ours(args):
     achieved = bpi * n_inst_local / (ms_pair * 1e-3) / 1e9 if ms_pair > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": ("partition_kernel<1, KEYX> + bucket_insert_compact_kernel<2> (Pass A into the all-to-all send "
                                           "buffer + Pass B over the received keys: each instance goes through both exactly once)" if keyx else
+                                          f"partition_kernel<{W}> + bucket_insert_wide_kernel<{W}> (Pass A + Pass B, multi-word keys: "
+                                          "each instance goes through both exactly once)" if W > 1 else
                                           "partition_kernel<1> + bucket_insert_compact_kernel<0> (Pass A + Pass B: "
                                           "each instance goes through both exactly once)"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic_bytes(), "peak_source": peak_src, "algorithmic_bytes_per_instance": bpi,
+                "traffic": ncu_traffic_bytes() if (W == 1 and world == 1 and args.workload == "C1" and args.scale == 1.0) else None,
+                "traffic_source": "committed ncu --set full capture of this workload (profiles/), not measured in this run", "peak_source": peak_src, "algorithmic_bytes_per_instance": bpi,
                 "instances_per_launch": n_inst_local, "ms_per_launch": ms_pair,
                 "launches_per_step": {"partition_kernel": d_res["launches_partition"] / args.steps,
                                       "bucket_insert_compact_kernel": d_res["launches_insert"] / args.steps},
@@ -461,7 +488,9 @@ def main_ours(args):
                                        "on the library's compute stream, max over ranks; value and e2e are timed without "
                                        "per-launch events, kernel durations come from a third pass of the same K steps with them"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(d_e2e["h2d_bytes"] / args.steps),
-                    "d2h_bytes_per_step": int(d_e2e["d2h_bytes"] / args.steps), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": int(d_e2e["d2h_bytes"] / args.steps), "ms_per_step": ms_e2e / args.steps,
+                    "result": "occurrence histogram + coverage cutoff + the sorted (key, count) entries >= cutoff in pinned host memory",
+                    "coverage_cutoff": export_bufs.get("cutoff"), "entries_exported_per_gpu": export_bufs.get("n")},
             "gpu_launches": int(d_plain["launches_pack"] + d_plain["launches_count"] + d_plain["launches_other"]),
             "roofline": roofline,
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")} if clocks else None,
@@ -512,11 +541,14 @@ def main():
     ap.add_argument("--exchange", default=os.environ.get("PBK_BENCH_EXCHANGE", "records"), choices=["records", "keys"],
                     help="N > 1: what crosses NVLink -- (key, count) records after counting, or the keys before it")
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--k", type=int, default=32, help="k-mer length (BASELINE metric: 32; 75 = the multi-word target of north_star)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify-recount", action="store_true", help="N > 1: skip the single-GPU recount of all ranks' reads on rank 0 (the sum checks stay)")
     ap.add_argument("--ref-mem-gb", type=int, default=REF_MEM_GB, help="-m of the reference arm (its default is 16)")
     args = ap.parse_args()
     globals()["REF_MEM_GB"] = args.ref_mem_gb
+    globals()["K"] = args.k
+    globals()["METRIC"] = f"canonical k-mers counted/sec at k={args.k}"
     if args.impl == "reference":
         return main_reference(args)
     return main_ours(args)

@@ -248,6 +248,18 @@ class KmerCounter:
                                            C.byref(n)), "pbk_export")
         return keys, counts
 
+    def export_count(self, min_count: int = 1) -> int:
+        n = C.c_uint64()
+        self._check(self._L.pbk_export(self._ctx, min_count, 0, None, None, 0, C.byref(n)), "pbk_export")
+        return n.value
+
+    def export_into(self, min_count: int, sorted: bool, keys_ptr: int, counts_ptr: int, capacity: int) -> int:
+        """pbk_export into host buffers of the caller (e.g. pinned torch tensors): returns the number of entries."""
+        n = C.c_uint64()
+        self._check(self._L.pbk_export(self._ctx, min_count, int(sorted), C.c_void_p(keys_ptr), C.c_void_p(counts_ptr), capacity,
+                                       C.byref(n)), "pbk_export")
+        return n.value
+
     def reset(self, k: int = 0):
         self._check(self._L.pbk_reset(self._ctx, k), "pbk_reset")
         if k:

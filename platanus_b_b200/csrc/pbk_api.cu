@@ -88,6 +88,8 @@ struct pbk_ctx {
     bool keyx_async = false;            // this partition call returns without reading the counters back
     cudaEvent_t ev_signal = nullptr, ev_wait = nullptr;     // pbk_stream_signal / pbk_stream_wait
 
+    void *d_scratch = nullptr; size_t scratch_bytes = 0;   // grow-only arena of pbk_export (entries, sort temporaries)
+
     bool finalized = false;
     u64 n_reads = 0, n_bases = 0, inst_since_clamp = 0, n_grow = 0;
     double new_ratio = 0.20;         // new keys per window, adapted from what the data shows
@@ -674,7 +676,7 @@ void release_all(pbk_ctx *c)
     cudaFree(c->d_passb); if (c->h_passb) cudaFreeHost(c->h_passb);
     cudaFree(c->table.slots); cudaFree(c->remote.slots); cudaFree(c->d_ctr); cudaFree(c->d_ovf);
     cudaFree(c->d_len_hist); cudaFree(c->d_occ_hist); cudaFree(c->d_shard_counts);
-    cudaFree(c->d_len_scratch); cudaFree(c->d_ctr_scratch);
+    cudaFree(c->d_len_scratch); cudaFree(c->d_ctr_scratch); cudaFree(c->d_scratch);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     for (auto &e : c->timer) if (e) cudaEventDestroy(e);
     if (c->ev_signal) cudaEventDestroy(c->ev_signal);
@@ -891,27 +893,35 @@ int pbk_export(pbk_ctx *c, uint32_t min_count, int sorted, uint64_t *keys, uint1
     if (capacity == 0) return PBK_OK;
     if (capacity < n || !keys || !counts) return fail(c, PBK_E_ARG, "export needs room for %llu entries", (unsigned long long)n);
     if (n == 0) return PBK_OK;
-    u64 *d_keys = nullptr, *d_n = nullptr; uint16_t *d_counts = nullptr;
+    // entries, their counter and the sort's temporaries live in one grow-only block of the context (no cudaMalloc /
+    // cudaFree -- both synchronise the device -- on the repeated-export path)
     const size_t kb = n * 8 * c->W, cb = n * 2;
-    TRY(dev_alloc(c, (void **)&d_keys, kb));
-    int rc = dev_alloc(c, (void **)&d_counts, cb);
-    if (rc == PBK_OK) rc = dev_alloc(c, (void **)&d_n, 8);
-    if (rc == PBK_OK) {
-        cudaMemsetAsync(d_n, 0, 8, c->s_compute);
-        { Span sp(c, LC_OTHER); launch_table_export(c->table, std::max<u32>(min_count, 1), d_keys, d_counts, n, d_n, c->s_compute); }
-        cudaError_t e = cudaGetLastError();
-        if (e == cudaSuccess && sorted) { c->launches[LC_OTHER] += 1; e = sort_export(d_keys, d_counts, n, c->W, (int)c->k, c->s_compute); }
-        u64 got = 0;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&got, d_n, 8, cudaMemcpyDeviceToHost, c->s_compute);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(keys, d_keys, kb, cudaMemcpyDeviceToHost, c->s_compute);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(counts, d_counts, cb, cudaMemcpyDeviceToHost, c->s_compute);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_compute);
-        c->d2h_bytes += kb + cb + 8;
-        if (e != cudaSuccess) rc = fail(c, PBK_E_CUDA, "export: %s", cudaGetErrorString(e));
-        else if (got != n) rc = fail(c, PBK_E_CUDA, "internal: export found %llu entries, histogram says %llu", (unsigned long long)got, (unsigned long long)n);
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t sort_bytes = sorted ? sort_export_scratch_bytes(n, c->W) : 0;
+    const size_t need = al(kb) + al(cb) + 256 + sort_bytes;
+    if (need > c->scratch_bytes) {
+        CK(cudaStreamSynchronize(c->s_compute));
+        dev_free(c, c->d_scratch, c->scratch_bytes);
+        c->d_scratch = nullptr; c->scratch_bytes = 0;
+        TRY(dev_alloc(c, &c->d_scratch, need + need / 8));
+        c->scratch_bytes = need + need / 8;
     }
-    cudaStreamSynchronize(c->s_compute);
-    dev_free(c, d_keys, kb); dev_free(c, d_counts, cb); dev_free(c, d_n, 8);
+    char *base = (char *)c->d_scratch;
+    u64 *d_keys = (u64 *)base; uint16_t *d_counts = (uint16_t *)(base + al(kb)); u64 *d_n = (u64 *)(base + al(kb) + al(cb));
+    void *d_sort = base + al(kb) + al(cb) + 256;
+    int rc = PBK_OK;
+    cudaMemsetAsync(d_n, 0, 8, c->s_compute);
+    { Span sp(c, LC_OTHER); launch_table_export(c->table, std::max<u32>(min_count, 1), d_keys, d_counts, n, d_n, c->s_compute); }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && sorted) { c->launches[LC_OTHER] += 1; e = sort_export(d_keys, d_counts, n, c->W, (int)c->k, d_sort, sort_bytes, c->s_compute); }
+    u64 got = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&got, d_n, 8, cudaMemcpyDeviceToHost, c->s_compute);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(keys, d_keys, kb, cudaMemcpyDeviceToHost, c->s_compute);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts, d_counts, cb, cudaMemcpyDeviceToHost, c->s_compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_compute);
+    c->d2h_bytes += kb + cb + 8;
+    if (e != cudaSuccess) { cudaStreamSynchronize(c->s_compute); rc = fail(c, PBK_E_CUDA, "export: %s", cudaGetErrorString(e)); }
+    else if (got != n) rc = fail(c, PBK_E_CUDA, "internal: export found %llu entries, histogram says %llu", (unsigned long long)got, (unsigned long long)n);
     return rc;
 }
 

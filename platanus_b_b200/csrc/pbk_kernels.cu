@@ -436,61 +436,78 @@ __global__ void gather_rows_kernel(const u64 *keys, const uint16_t *counts, cons
     }
 }
 
-cudaError_t sort_export(u64 *keys, uint16_t *counts, u64 n, int words, int k, cudaStream_t st)
+namespace {
+inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+struct SortCarve {                                  // where each temporary lives inside the caller's scratch block
+    size_t k2, c2, perm, perm2, kw, kw2, keys_tmp, counts_tmp, cub, cub_bytes, total;
+};
+SortCarve sort_carve(u64 n, int words)
+{
+    SortCarve c{};
+    size_t at = 0;
+    auto take = [&](size_t bytes) { const size_t o = at; at += al256(bytes); return o; };
+    if (words == 1) {
+        c.k2 = take(n * 8); c.c2 = take(n * 2);
+        cub::DoubleBuffer<u64> dk(nullptr, nullptr);
+        cub::DoubleBuffer<uint16_t> dc(nullptr, nullptr);
+        cub::DeviceRadixSort::SortPairs(nullptr, c.cub_bytes, dk, dc, (long long)n, 0, 64, (cudaStream_t)0);
+    } else {
+        c.perm = take(n * 4); c.perm2 = take(n * 4); c.kw = take(n * 8); c.kw2 = take(n * 8);
+        c.keys_tmp = take(n * 8 * words); c.counts_tmp = take(n * 2);
+        cub::DoubleBuffer<u64> dk(nullptr, nullptr);
+        cub::DoubleBuffer<u32> dp(nullptr, nullptr);
+        cub::DeviceRadixSort::SortPairs(nullptr, c.cub_bytes, dk, dp, (long long)n, 0, 64, (cudaStream_t)0);
+    }
+    c.cub = take(c.cub_bytes ? c.cub_bytes : 1);
+    c.total = at;
+    return c;
+}
+}  // namespace
+
+size_t sort_export_scratch_bytes(u64 n, int words) { return n < 2 ? 0 : sort_carve(n, words).total; }
+
+// Everything is queued on `st`; no allocation, no synchronisation (the scratch block belongs to the context's HBM budget).
+cudaError_t sort_export(u64 *keys, uint16_t *counts, u64 n, int words, int k, void *scratch, size_t scratch_bytes, cudaStream_t st)
 {
     if (n < 2) return cudaSuccess;
-    if (n >= (1ull << 32)) return cudaErrorInvalidValue;
+    if (n >= (1ull << 32)) return cudaErrorInvalidValue;        // the permutation of the multi-word path is 32-bit
+    const SortCarve c = sort_carve(n, words);
+    if (!scratch || scratch_bytes < c.total) return cudaErrorInvalidValue;
+    char *base = (char *)scratch;
+    size_t tmp_bytes = c.cub_bytes;
     cudaError_t e;
     const int grid = grid_for(n, 256, 148, 8);
+    const long long items = (long long)n;                        // 64-bit item count: n may exceed INT_MAX
     if (words == 1) {
-        u64 *k2 = nullptr; uint16_t *c2 = nullptr; void *tmp = nullptr; size_t tmp_bytes = 0;
-        if ((e = cudaMalloc(&k2, n * 8))) return e;
-        if ((e = cudaMalloc(&c2, n * 2))) { cudaFree(k2); return e; }
-        cub::DoubleBuffer<u64> dk(keys, k2);
-        cub::DoubleBuffer<uint16_t> dc(counts, c2);
+        cub::DoubleBuffer<u64> dk(keys, (u64 *)(base + c.k2));
+        cub::DoubleBuffer<uint16_t> dc(counts, (uint16_t *)(base + c.c2));
         const int end_bit = 2 * k > 64 ? 64 : 2 * k;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dc, (int)n, 0, end_bit, st);
-        if ((e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1))) { cudaFree(k2); cudaFree(c2); return e; }
-        e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dc, (int)n, 0, end_bit, st);
+        e = cub::DeviceRadixSort::SortPairs(base + c.cub, tmp_bytes, dk, dc, items, 0, end_bit, st);
         if (!e && dk.Current() != keys) {
             cudaMemcpyAsync(keys, dk.Current(), n * 8, cudaMemcpyDeviceToDevice, st);
             cudaMemcpyAsync(counts, dc.Current(), n * 2, cudaMemcpyDeviceToDevice, st);
         }
-        cudaError_t e2 = cudaStreamSynchronize(st);
-        cudaFree(k2); cudaFree(c2); cudaFree(tmp);
-        return e ? e : e2;
+        return e;
     }
-    u32 *perm = nullptr, *perm2 = nullptr; u64 *kw = nullptr, *kw2 = nullptr, *keys_tmp = nullptr; uint16_t *counts_tmp = nullptr;
-    void *tmp = nullptr; size_t tmp_bytes = 0;
-    e = cudaMalloc(&perm, n * 4);
-    if (!e) e = cudaMalloc(&perm2, n * 4);
-    if (!e) e = cudaMalloc(&kw, n * 8);
-    if (!e) e = cudaMalloc(&kw2, n * 8);
-    if (!e) e = cudaMalloc(&keys_tmp, n * 8 * words);
-    if (!e) e = cudaMalloc(&counts_tmp, n * 2);
+    u32 *perm = (u32 *)(base + c.perm);
+    u64 *keys_tmp = (u64 *)(base + c.keys_tmp);
+    uint16_t *counts_tmp = (uint16_t *)(base + c.counts_tmp);
+    cub::DoubleBuffer<u64> dk((u64 *)(base + c.kw), (u64 *)(base + c.kw2));
+    cub::DoubleBuffer<u32> dp(perm, (u32 *)(base + c.perm2));
+    iota_kernel<<<grid, 256, 0, st>>>(perm, n);
+    e = cudaGetLastError();
+    for (int w = 0; w < words && !e; ++w) {
+        gather_word_kernel<<<grid, 256, 0, st>>>(keys, dp.Current(), n, words, w, dk.Current());
+        int end_bit = 64;
+        if (w == words - 1 && (k & 31)) end_bit = 2 * (k & 31);
+        e = cub::DeviceRadixSort::SortPairs(base + c.cub, tmp_bytes, dk, dp, items, 0, end_bit, st);
+    }
     if (!e) {
-        cub::DoubleBuffer<u64> dk(kw, kw2);
-        cub::DoubleBuffer<u32> dp(perm, perm2);
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dp, (int)n, 0, 64, st);
-        e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
-        if (!e) {
-            iota_kernel<<<grid, 256, 0, st>>>(perm, n);
-            for (int w = 0; w < words && !e; ++w) {
-                gather_word_kernel<<<grid, 256, 0, st>>>(keys, dp.Current(), n, words, w, dk.Current());
-                int end_bit = 64;
-                if (w == words - 1 && (k & 31)) end_bit = 2 * (k & 31);
-                e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dp, (int)n, 0, end_bit, st);
-            }
-            if (!e) {
-                gather_rows_kernel<<<grid, 256, 0, st>>>(keys, counts, dp.Current(), n, words, keys_tmp, counts_tmp);
-                cudaMemcpyAsync(keys, keys_tmp, n * 8 * words, cudaMemcpyDeviceToDevice, st);
-                cudaMemcpyAsync(counts, counts_tmp, n * 2, cudaMemcpyDeviceToDevice, st);
-            }
-        }
+        gather_rows_kernel<<<grid, 256, 0, st>>>(keys, counts, dp.Current(), n, words, keys_tmp, counts_tmp);
+        cudaMemcpyAsync(keys, keys_tmp, n * 8 * words, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(counts, counts_tmp, n * 2, cudaMemcpyDeviceToDevice, st);
     }
-    cudaError_t e2 = cudaStreamSynchronize(st);
-    cudaFree(perm); cudaFree(perm2); cudaFree(kw); cudaFree(kw2); cudaFree(keys_tmp); cudaFree(counts_tmp); cudaFree(tmp);
-    return e ? e : e2;
+    return e;
 }
 
 // =================================================================================================

@@ -101,8 +101,10 @@ void launch_table_histogram(TableView t, u64 *occ_hist, cudaStream_t st);
 // compact entries with count >= min_count: keys (n x W, word 0 first), counts u16; *d_n_out += n
 void launch_table_export(TableView t, u32 min_count, u64 *keys_out, uint16_t *counts_out, u64 capacity,
                          u64 *d_n_out, cudaStream_t st);
-// sort exported entries ascending in reference order (top word first); temp storage managed inside
-cudaError_t sort_export(u64 *keys, uint16_t *counts, u64 n, int words, int k, cudaStream_t st);
+// sort exported entries ascending in reference order (top word first); queued on `st`, temporaries carved from `scratch`
+// (sort_export_scratch_bytes(n, words) bytes, provided by the caller from the context's HBM budget)
+size_t sort_export_scratch_bytes(u64 n, int words);
+cudaError_t sort_export(u64 *keys, uint16_t *counts, u64 n, int words, int k, void *scratch, size_t scratch_bytes, cudaStream_t st);
 
 // ---- sharding ---------------------------------------------------------------------------------
 // per-destination number of entries in the remote-staging table

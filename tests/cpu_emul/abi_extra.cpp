@@ -8,7 +8,9 @@
 
 namespace pbk {
 
-cudaError_t sort_export(u64 *keys, uint16_t *counts, u64 n, int words, int, cudaStream_t)
+size_t sort_export_scratch_bytes(u64, int) { return 0; }
+
+cudaError_t sort_export(u64 *keys, uint16_t *counts, u64 n, int words, int, void *, size_t, cudaStream_t)
 {
     std::vector<u64> perm(n);
     std::iota(perm.begin(), perm.end(), 0ull);
