@@ -318,6 +318,11 @@ def main_ours(args):
     # buffer, every rank runs Pass B over what it received (include/pbk.h, pbk_keyx_*).  Default is the record exchange,
     # the form measured in round 1.
     keyx = world > 1 and args.exchange == "keys" and W == 1
+    # --exchange pull (k <= 32): nobody sends keys.  Pass A fills the rank's own owner-major store, a barrier, and every rank's
+    # Pass B reads the segments addressed to it out of its peers' HBM over NVLink while it inserts (pbk_keyx_pull_*).
+    pull = world > 1 and args.exchange == "pull" and W == 1
+    if pull:
+        puller = sharding.KeyPull(kc, world, rank, max(n_bases - n_reads * (K - 1), 0), device="cuda")
     if keyx:
         # the batch in --keyx-chunks chunks (cut at read boundaries): the all-to-all of one chunk is in flight while the
         # next one is partitioned and the previous one inserted (sharding.pipelined_key_exchange)
@@ -368,9 +373,17 @@ def main_ours(args):
         got = kc.export_into(cutoff, True, export_bufs["keys"].data_ptr(), export_bufs["counts"].data_ptr(), export_bufs["cap"])
         export_bufs.update(n=got, cutoff=cutoff)
 
+    def step_pull(resident: bool):
+        if resident:
+            part = lambda: kc.keyx_pull_partition_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, n_bases, True)
+            return puller.step(part, torch.cuda.current_stream().synchronize, caller_stream=lambda: torch.cuda.current_stream().cuda_stream)
+        return puller.step(lambda: kc.keyx_pull_partition_ptr(h_bases.data_ptr(), h_offs.data_ptr(), n_reads), torch.cuda.current_stream().synchronize)
+
     def step(resident: bool):
         kc.reset()
-        if keyx:
+        if pull:
+            sent = step_pull(resident)
+        elif keyx:
             sent = step_keyx(resident)
         else:
             if resident:
@@ -451,7 +464,9 @@ def main_ours(args):
     ms_pair = d_res["ms_count_elapsed"] / args.steps
     direct = d_res["ms_count"] - d_res["ms_partition"] - d_res["ms_insert"]      # non-partitioned launches (small batches)
     achieved = bpi * n_inst_local / (ms_pair * 1e-3) / 1e9 if ms_pair > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": ("partition_kernel<1, KEYX> + bucket_insert_compact_kernel<2> (Pass A into the all-to-all send "
+    roofline = {"bound": "hbm", "kernel": ("partition_kernel<1, KEYX> + bucket_insert_gather_kernel (Pass A into the rank's own owner-major store + Pass B "
+                                          "reading every peer's store over NVLink: each instance goes through both exactly once)" if pull else
+                                          "partition_kernel<1, KEYX> + bucket_insert_gather_kernel (Pass A into the all-to-all send "
                                           "buffer + Pass B over the received keys: each instance goes through both exactly once)" if keyx else
                                           f"partition_kernel<{W}> + bucket_insert_wide_kernel<{W}> (Pass A + Pass B, multi-word keys: "
                                           "each instance goes through both exactly once)" if W > 1 else
@@ -505,7 +520,9 @@ def main_ours(args):
         }
         if world > 1:
             line["exchange_bytes_sent_per_gpu_per_step"] = int(sent_res / args.steps)
-            line["exchange"] = ("keys before counting (8-byte hashes, equal splits, pbk_keyx_*)" if keyx else
+            line["exchange"] = ("pull: Pass B reads the peers' bucket stores in place over NVLink (P2P loads, no collective moves the keys; "
+                                "bytes = what this rank's peers read from it, pbk_keyx_pull_*)" if pull else
+                                "keys before counting (8-byte hashes, equal splits, pbk_keyx_*)" if keyx else
                                 "pre-aggregated (key, count) records after counting (pbk_shard_*)")
         if base is not None:
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -538,7 +555,7 @@ def main():
                     help="--exchange keys: order Pass A -> all-to-all -> Pass B by CUDA events (pbk_stream_signal/wait) instead of host syncs")
     ap.add_argument("--keyx-chunks", type=int, default=int(os.environ.get("PBK_BENCH_KEYX_CHUNKS", "4")),
                     help="--exchange keys: chunks per step (the all-to-all of one chunk overlaps the passes of its neighbours)")
-    ap.add_argument("--exchange", default=os.environ.get("PBK_BENCH_EXCHANGE", "records"), choices=["records", "keys"],
+    ap.add_argument("--exchange", default=os.environ.get("PBK_BENCH_EXCHANGE", "records"), choices=["records", "keys", "pull"],
                     help="N > 1: what crosses NVLink -- (key, count) records after counting, or the keys before it")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--k", type=int, default=32, help="k-mer length (BASELINE metric: 32; 75 = the multi-word target of north_star)")

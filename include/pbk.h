@@ -227,6 +227,31 @@ int  pbk_keyx_partition_device_async(pbk_ctx *ctx, const void *d_bases, const vo
  * [source rank][region] fill counts                                                               */
 int  pbk_keyx_insert_device(pbk_ctx *ctx, const void *d_recv, const void *d_recv_cursors);
 
+/* ---- hash-range sharding, third form (k <= 32): the pull exchange -- no collective moves the keys ----------------------
+ * Pass A fills the context's OWN owner-major bucket store (same layout as above); every shard's Pass B then reads the
+ * segments addressed to it in place, out of its peers' HBM over NVLink / NVSwitch (P2P loads through peer-mapped
+ * pointers).  The transfer is Pass B's own streamed key loads and overlaps its table atomics tile by tile; between the
+ * two passes there is only a barrier.  Results are identical to the other two forms (same ownership function).
+ *   1. every rank: pbk_keyx_pull_setup(max over ranks of the batch's window count)  -- plans the layout and allocates the
+ *      store (two parities: a store is rewritten two partition calls later, when every peer has finished reading it)
+ *   2. connect every peer once: same process -> pbk_keyx_pull_connect_local(ctx, r, ctx_of_rank_r);
+ *      other processes -> exchange pbk_keyx_pull_handle() blobs by any means, pbk_keyx_pull_connect_ipc(ctx, r, blob_of_r)
+ *   3. per batch: pbk_keyx_pull_partition[_device]  ->  BARRIER over all ranks that is ordered after every rank's
+ *      partition on its GPU and before this rank's insert (any collective on a stream bracketed by pbk_stream_signal /
+ *      pbk_stream_wait; CUDA events between the contexts of one process; or host synchronisation)  ->  pbk_keyx_pull_insert
+ *   4. staged records (keys that found their segment full) as in the second form; pbk_finalize as usual.            */
+#define PBK_KEYX_HANDLE_BYTES 64
+int  pbk_keyx_pull_setup(pbk_ctx *ctx, uint64_t max_windows_any_rank, pbk_keyx_layout *out);
+int  pbk_keyx_pull_handle(pbk_ctx *ctx, void *handle_out /* PBK_KEYX_HANDLE_BYTES */);
+int  pbk_keyx_pull_connect_ipc(pbk_ctx *ctx, uint32_t src_rank, const void *handle);
+int  pbk_keyx_pull_connect_local(pbk_ctx *ctx, uint32_t src_rank, pbk_ctx *peer);
+int  pbk_keyx_pull_partition(pbk_ctx *ctx, const uint8_t *bases, const uint64_t *read_offsets, uint64_t n_reads,
+                             int encoding, const int32_t *n_pos, const uint64_t *n_pos_offsets);
+/* async != 0: returns when the kernels are queued (see pbk_keyx_partition_device_async) */
+int  pbk_keyx_pull_partition_device(pbk_ctx *ctx, const void *d_bases, const void *d_read_offsets, uint64_t n_reads,
+                                    uint64_t n_bases, int async);
+int  pbk_keyx_pull_insert(pbk_ctx *ctx);
+
 /* ---- consumers of the table --------------------------------------
  * Occurrence of every k-mer window of a batch of sequences: ContigDivider::getOccurrenceArray
  * (kmer_divide.cpp:151-197, via Counter::findValue) and the table probe of

@@ -41,7 +41,8 @@ SYMBOLS = [
     "pbk_keyx_plan", "pbk_keyx_partition", "pbk_keyx_partition_device", "pbk_keyx_insert_device",
     "pbk_lookup", "pbk_lookup_device", "pbk_load_entries", "pbk_read_kmer_occ_bin", "pbk_free",
     "pbk_match_reads", "pbk_seed_entries", "pbk_stream_signal", "pbk_stream_wait", "pbk_keyx_partition_device_async",
-    "pbk_push_contigs",
+    "pbk_push_contigs", "pbk_keyx_pull_setup", "pbk_keyx_pull_handle", "pbk_keyx_pull_connect_ipc", "pbk_keyx_pull_connect_local",
+    "pbk_keyx_pull_partition", "pbk_keyx_pull_partition_device", "pbk_keyx_pull_insert",
 ]
 
 
@@ -137,6 +138,13 @@ def load_library(build_if_missing: bool = True):
     L.pbk_keyx_partition_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, vp, vp]
     L.pbk_keyx_insert_device.argtypes = [vp, vp, vp]
     L.pbk_keyx_partition_device_async.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, vp, vp]
+    L.pbk_keyx_pull_setup.argtypes = [vp, C.c_uint64, C.POINTER(PbkKeyxLayout)]
+    L.pbk_keyx_pull_handle.argtypes = [vp, vp]
+    L.pbk_keyx_pull_connect_ipc.argtypes = [vp, C.c_uint32, vp]
+    L.pbk_keyx_pull_connect_local.argtypes = [vp, C.c_uint32, vp]
+    L.pbk_keyx_pull_partition.argtypes = [vp, vp, u64p, C.c_uint64, C.c_int, vp, u64p]
+    L.pbk_keyx_pull_partition_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int]
+    L.pbk_keyx_pull_insert.argtypes = [vp]
     L.pbk_stream_signal.argtypes = [vp, vp]
     L.pbk_stream_wait.argtypes = [vp, vp]
     L.pbk_left_local_min.argtypes = [u64p, C.c_uint64, C.c_uint64]; L.pbk_left_local_min.restype = C.c_uint64
@@ -396,6 +404,43 @@ class KmerCounter:
     def keyx_insert_device(self, d_recv_ptr: int, d_recv_cursors_ptr: int):
         self._check(self._L.pbk_keyx_insert_device(self._ctx, C.c_void_p(d_recv_ptr), C.c_void_p(d_recv_cursors_ptr)),
                     "pbk_keyx_insert_device")
+
+    # -- pull form of the key exchange: Pass B reads the peers' bucket stores in place over NVLink (pbk_keyx_pull_*) -------
+    KEYX_HANDLE_BYTES = 64
+
+    def keyx_pull_setup(self, max_windows_any_rank: int) -> PbkKeyxLayout:
+        lay = PbkKeyxLayout()
+        self._check(self._L.pbk_keyx_pull_setup(self._ctx, int(max_windows_any_rank), C.byref(lay)), "pbk_keyx_pull_setup")
+        return lay
+
+    def keyx_pull_handle(self) -> bytes:
+        buf = C.create_string_buffer(self.KEYX_HANDLE_BYTES)
+        self._check(self._L.pbk_keyx_pull_handle(self._ctx, buf), "pbk_keyx_pull_handle")
+        return buf.raw
+
+    def keyx_pull_connect_ipc(self, src_rank: int, handle: bytes):
+        buf = C.create_string_buffer(bytes(handle), self.KEYX_HANDLE_BYTES)
+        self._check(self._L.pbk_keyx_pull_connect_ipc(self._ctx, int(src_rank), buf), "pbk_keyx_pull_connect_ipc")
+
+    def keyx_pull_connect_local(self, src_rank: int, peer: "KmerCounter"):
+        self._check(self._L.pbk_keyx_pull_connect_local(self._ctx, int(src_rank), peer._ctx), "pbk_keyx_pull_connect_local")
+
+    def keyx_pull_partition(self, bases: np.ndarray, offsets: np.ndarray):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._check(self._L.pbk_keyx_pull_partition(self._ctx, _ptr(bases), _ptr(offsets), len(offsets) - 1, ENC_ASCII, None, None),
+                    "pbk_keyx_pull_partition")
+
+    def keyx_pull_partition_ptr(self, bases_ptr: int, offsets_ptr: int, n_reads: int):
+        self._check(self._L.pbk_keyx_pull_partition(self._ctx, C.c_void_p(bases_ptr), C.c_void_p(offsets_ptr), n_reads, ENC_ASCII, None, None),
+                    "pbk_keyx_pull_partition")
+
+    def keyx_pull_partition_device(self, d_bases_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int, asynchronous: bool = False):
+        self._check(self._L.pbk_keyx_pull_partition_device(self._ctx, C.c_void_p(d_bases_ptr), C.c_void_p(d_offsets_ptr), n_reads, n_bases,
+                                                           int(asynchronous)), "pbk_keyx_pull_partition_device")
+
+    def keyx_pull_insert(self):
+        self._check(self._L.pbk_keyx_pull_insert(self._ctx), "pbk_keyx_pull_insert")
 
     # -- Counter<KMER> mirror (reference counter.h) ------------------------------------------------
     def make_kmer_read_distribution(self, bases, offsets, memory_bytes: int) -> int:

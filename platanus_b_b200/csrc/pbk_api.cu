@@ -86,6 +86,13 @@ struct pbk_ctx {
     bool counters_pending = false;      // a queued key-exchange insert has not had its counters read back yet (settle())
     u64 *keyx_send = nullptr, *keyx_cursors = nullptr;
     bool keyx_async = false;            // this partition call returns without reading the counters back
+    // pull form of the key exchange (pbk_keyx_pull_*): this context's own owner-major bucket store, double-buffered, in ONE
+    // allocation [keys parity 0][keys parity 1][cursors parity 0][cursors parity 1] that the peers map (same process: peer
+    // access; other processes: CUDA IPC) and read in place during their Pass B
+    char *pull_base = nullptr; size_t pull_bytes = 0, pull_keys_bytes = 0, pull_cur_bytes = 0;
+    char *pull_peer[KEYX_MAX_SRC] = {};      // base of every rank's allocation as seen from this GPU ([rank] = own)
+    bool pull_peer_ipc[KEYX_MAX_SRC] = {};
+    int pull_parity = 1;                     // parity of the store the last partition call filled (first call: 0)
     cudaEvent_t ev_signal = nullptr, ev_wait = nullptr;     // pbk_stream_signal / pbk_stream_wait
 
     void *d_scratch = nullptr; size_t scratch_bytes = 0;   // grow-only arena of pbk_export (entries, sort temporaries)
@@ -677,6 +684,8 @@ void release_all(pbk_ctx *c)
     cudaFree(c->table.slots); cudaFree(c->remote.slots); cudaFree(c->d_ctr); cudaFree(c->d_ovf);
     cudaFree(c->d_len_hist); cudaFree(c->d_occ_hist); cudaFree(c->d_shard_counts);
     cudaFree(c->d_len_scratch); cudaFree(c->d_ctr_scratch); cudaFree(c->d_scratch);
+    for (int i = 0; i < KEYX_MAX_SRC; ++i) if (c->pull_peer_ipc[i] && c->pull_peer[i]) cudaIpcCloseMemHandle(c->pull_peer[i]);
+    cudaFree(c->pull_base);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     for (auto &e : c->timer) if (e) cudaEventDestroy(e);
     if (c->ev_signal) cudaEventDestroy(c->ev_signal);
@@ -1438,11 +1447,10 @@ int pbk_stream_wait(pbk_ctx *c, void *stream)
     return PBK_OK;
 }
 
-int pbk_keyx_insert_device(pbk_ctx *c, const void *d_recv, const void *d_recv_cursors)
+// Pass B of the key exchange over `srcs` (per source rank: its keys and fill counts for this shard)
+static int keyx_insert_common(pbk_ctx *c, const KeyxSources &srcs)
 {
-    if (!c || !d_recv || !d_recv_cursors) return PBK_E_ARG;
     if (c->finalized) return fail(c, PBK_E_STATE, "insert after finalize");
-    if (c->keyx_plan.n_buckets == 0 || c->W != 1) return fail(c, PBK_E_STATE, "pbk_keyx_insert_device before pbk_keyx_plan");
     CK(cudaSetDevice(c->device));
     const u32 G = c->shard.n_shards, n_desc = c->keyx_plan.n_buckets, R = n_desc / G;
     const u64 seg_cap = c->keyx_plan.seg_cap;
@@ -1461,8 +1469,8 @@ int pbk_keyx_insert_device(pbk_ctx *c, const void *d_recv, const void *d_recv_cu
         TRY(ensure_overflow_for_batch(c, c->keyx_last_total + c->keyx_last_total / 8));
         {
             Span sp(c, LC_INSERT);
-            launch_bucket_insert_gathered_chained((const u64 *)d_recv, (const u64 *)d_recv_cursors, seg_cap, c->d_passb, G, R, c->table,
-                                                  c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+            launch_bucket_insert_gathered_chained(srcs, seg_cap, c->d_passb, G, R, c->table, c->d_ctr, c->d_ovf, c->ovf_cap,
+                                                  c->sm_count, c->s_compute);
         }
         CK(cudaGetLastError());
         c->counters_pending = true;
@@ -1470,13 +1478,14 @@ int pbk_keyx_insert_device(pbk_ctx *c, const void *d_recv, const void *d_recv_cu
         return PBK_OK;
     }
     // fill counts, [source][region] -> descriptor order [region][source]
-    CK(cudaMemcpyAsync(c->h_bkt_cursor, d_recv_cursors, (size_t)n_desc * 8, cudaMemcpyDeviceToHost, c->s_compute));
+    for (u32 sr = 0; sr < G; ++sr)
+        CK(cudaMemcpyAsync(c->h_bkt_cursor + (size_t)sr * R, srcs.cursors[sr], (size_t)R * 8, cudaMemcpyDefault, c->s_compute));
     CK(cudaStreamSynchronize(c->s_compute));
     c->d2h_bytes += (u64)n_desc * 8;
     std::vector<u64> cnt(n_desc);
     u64 total = 0;
     for (u32 j = 0; j < R; ++j)
-        for (u32 s = 0; s < G; ++s) { cnt[j * G + s] = std::min<u64>(c->h_bkt_cursor[s * R + j], seg_cap); total += cnt[j * G + s]; }
+        for (u32 sr = 0; sr < G; ++sr) { cnt[j * G + sr] = std::min<u64>(c->h_bkt_cursor[sr * R + j], seg_cap); total += cnt[j * G + sr]; }
     DBG("keyx insert: %llu keys from %u sources in %u regions (seg_cap %llu)", (unsigned long long)total, G, R, (unsigned long long)seg_cap);
     if (total == 0) return PBK_OK;
     if (!c->table.slots) {
@@ -1493,7 +1502,7 @@ int pbk_keyx_insert_device(pbk_ctx *c, const void *d_recv, const void *d_recv_cu
     auto launch = [&](u32 d0, u32 d1) -> int {
         {
             Span sp(c, LC_INSERT);
-            launch_bucket_insert_gathered((const u64 *)d_recv, seg_cap, cnt.data(), c->h_passb, c->d_passb, d0, d1, G, R, c->table,
+            launch_bucket_insert_gathered(srcs, seg_cap, cnt.data(), c->h_passb, c->d_passb, d0, d1, G, R, c->table,
                                           c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
         }
         CK(cudaGetLastError());
@@ -1524,6 +1533,137 @@ int pbk_keyx_insert_device(pbk_ctx *c, const void *d_recv, const void *d_recv_cu
         c->keyx_last_total = total;
     }
     return PBK_OK;
+}
+
+int pbk_keyx_insert_device(pbk_ctx *c, const void *d_recv, const void *d_recv_cursors)
+{
+    if (!c || !d_recv || !d_recv_cursors) return PBK_E_ARG;
+    if (c->keyx_plan.n_buckets == 0 || c->W != 1) return fail(c, PBK_E_STATE, "pbk_keyx_insert_device before pbk_keyx_plan");
+    const u32 G = c->shard.n_shards, R = c->keyx_plan.n_buckets / G;
+    if (G > (u32)KEYX_MAX_SRC) return fail(c, PBK_E_ARG, "key exchange supports up to %d shards", KEYX_MAX_SRC);
+    KeyxSources srcs{};
+    for (u32 sr = 0; sr < G; ++sr) {
+        srcs.keys[sr] = (const u64 *)d_recv + (u64)sr * R * c->keyx_plan.seg_cap;
+        srcs.cursors[sr] = (const u64 *)d_recv_cursors + (u64)sr * R;
+    }
+    return keyx_insert_common(c, srcs);
+}
+
+// ---- key exchange, pull form: nobody sends anything ---------------------------------------------------------------------
+// Pass A fills this context's own owner-major bucket store; every shard's Pass B then reads the segments addressed to it in
+// place, out of its peers' HBM over NVLink (P2P loads through peer-mapped pointers), so the transfer is Pass B's own streamed
+// loads and overlaps its atomics tile by tile.  What remains between the two passes is a barrier, not a data movement.
+
+int pbk_keyx_pull_setup(pbk_ctx *c, uint64_t max_windows_any_rank, pbk_keyx_layout *out)
+{
+    if (!c || !out) return PBK_E_ARG;
+    TRY(pbk_keyx_plan(c, max_windows_any_rank, out));
+    if (c->shard.n_shards > (u32)KEYX_MAX_SRC) return fail(c, PBK_E_ARG, "the pull exchange supports up to %d shards", KEYX_MAX_SRC);
+    CK(cudaSetDevice(c->device));
+    const size_t keys_bytes = (size_t)c->keyx_plan.n_buckets * c->keyx_plan.seg_cap * 8;
+    const size_t cur_bytes = ((size_t)c->keyx_plan.n_buckets * 8 + 255) & ~(size_t)255;
+    const size_t need = 2 * keys_bytes + 2 * cur_bytes;
+    if (c->pull_base && (keys_bytes != c->pull_keys_bytes || cur_bytes != c->pull_cur_bytes))
+        return fail(c, PBK_E_STATE, "the pull store is already shared with another layout (destroy the context to change it)");
+    if (!c->pull_base) {
+        void *p = nullptr;
+        TRY(dev_alloc(c, &p, need));                    // plain cudaMalloc: exportable with cudaIpcGetMemHandle
+        c->pull_base = (char *)p; c->pull_bytes = need; c->pull_keys_bytes = keys_bytes; c->pull_cur_bytes = cur_bytes;
+        CK(cudaMemsetAsync(c->pull_base + 2 * keys_bytes, 0, 2 * cur_bytes, c->s_compute));
+        CK(cudaStreamSynchronize(c->s_compute));
+        c->pull_peer[c->shard.rank] = c->pull_base;
+        c->pull_parity = 1;
+    }
+    return PBK_OK;
+}
+
+int pbk_keyx_pull_handle(pbk_ctx *c, void *handle_out)
+{
+    if (!c || !handle_out) return PBK_E_ARG;
+    if (!c->pull_base) return fail(c, PBK_E_STATE, "pbk_keyx_pull_handle before pbk_keyx_pull_setup");
+    CK(cudaSetDevice(c->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) <= PBK_KEYX_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->pull_base));
+    memset(handle_out, 0, PBK_KEYX_HANDLE_BYTES);
+    memcpy(handle_out, &h, sizeof h);
+    return PBK_OK;
+}
+
+int pbk_keyx_pull_connect_ipc(pbk_ctx *c, uint32_t src_rank, const void *handle)
+{
+    if (!c || !handle) return PBK_E_ARG;
+    if (!c->pull_base) return fail(c, PBK_E_STATE, "pbk_keyx_pull_connect_ipc before pbk_keyx_pull_setup");
+    if (src_rank >= c->shard.n_shards || src_rank == c->shard.rank) return fail(c, PBK_E_ARG, "bad source rank %u", src_rank);
+    CK(cudaSetDevice(c->device));
+    if (c->pull_peer[src_rank] && c->pull_peer_ipc[src_rank]) { cudaIpcCloseMemHandle(c->pull_peer[src_rank]); c->pull_peer[src_rank] = nullptr; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->pull_peer[src_rank] = (char *)p; c->pull_peer_ipc[src_rank] = true;
+    return PBK_OK;
+}
+
+int pbk_keyx_pull_connect_local(pbk_ctx *c, uint32_t src_rank, pbk_ctx *peer)
+{
+    if (!c || !peer) return PBK_E_ARG;
+    if (!c->pull_base || !peer->pull_base) return fail(c, PBK_E_STATE, "pbk_keyx_pull_connect_local before pbk_keyx_pull_setup on both contexts");
+    if (src_rank >= c->shard.n_shards || src_rank == c->shard.rank || peer->shard.rank != src_rank || peer->shard.n_shards != c->shard.n_shards)
+        return fail(c, PBK_E_ARG, "bad source rank %u", src_rank);
+    if (peer->pull_keys_bytes != c->pull_keys_bytes) return fail(c, PBK_E_ARG, "the two contexts planned different layouts");
+    CK(cudaSetDevice(c->device));
+    if (peer->device != c->device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, c->device, peer->device));
+        if (!can) return fail(c, PBK_E_CUDA, "GPU %d cannot map the memory of GPU %d (no peer access)", c->device, peer->device);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+        cudaGetLastError();
+    }
+    c->pull_peer[src_rank] = peer->pull_base; c->pull_peer_ipc[src_rank] = false;
+    return PBK_OK;
+}
+
+static int pull_bind(pbk_ctx *c)
+{
+    if (!c->pull_base) return fail(c, PBK_E_STATE, "pbk_keyx_pull_partition before pbk_keyx_pull_setup");
+    c->pull_parity ^= 1;
+    return PBK_OK;
+}
+static void *pull_keys(pbk_ctx *c) { return c->pull_base + (size_t)c->pull_parity * c->pull_keys_bytes; }
+static void *pull_cursors(pbk_ctx *c) { return c->pull_base + 2 * c->pull_keys_bytes + (size_t)c->pull_parity * c->pull_cur_bytes; }
+
+int pbk_keyx_pull_partition(pbk_ctx *c, const uint8_t *bases, const uint64_t *read_offsets, uint64_t n_reads, int encoding,
+                            const int32_t *n_pos, const uint64_t *n_pos_offsets)
+{
+    if (!c) return PBK_E_ARG;
+    TRY(pull_bind(c));
+    return pbk_keyx_partition(c, bases, read_offsets, n_reads, encoding, n_pos, n_pos_offsets, pull_keys(c), pull_cursors(c));
+}
+
+int pbk_keyx_pull_partition_device(pbk_ctx *c, const void *d_bases, const void *d_read_offsets, uint64_t n_reads, uint64_t n_bases,
+                                   int async)
+{
+    if (!c) return PBK_E_ARG;
+    TRY(pull_bind(c));
+    return (async ? pbk_keyx_partition_device_async : pbk_keyx_partition_device)(c, d_bases, d_read_offsets, n_reads, n_bases,
+                                                                                 pull_keys(c), pull_cursors(c));
+}
+
+int pbk_keyx_pull_insert(pbk_ctx *c)
+{
+    if (!c) return PBK_E_ARG;
+    if (!c->pull_base || c->W != 1) return fail(c, PBK_E_STATE, "pbk_keyx_pull_insert before pbk_keyx_pull_setup");
+    const u32 G = c->shard.n_shards, R = c->keyx_plan.n_buckets / G, me = c->shard.rank;
+    KeyxSources srcs{};
+    for (u32 sr = 0; sr < G; ++sr) {
+        const char *base = c->pull_peer[sr];
+        if (!base) return fail(c, PBK_E_STATE, "source rank %u is not connected (pbk_keyx_pull_connect_*)", sr);
+        srcs.keys[sr] = (const u64 *)(base + (size_t)c->pull_parity * c->pull_keys_bytes) + (u64)me * R * c->keyx_plan.seg_cap;
+        srcs.cursors[sr] = (const u64 *)(base + 2 * c->pull_keys_bytes + (size_t)c->pull_parity * c->pull_cur_bytes) + (u64)me * R;
+    }
+    return keyx_insert_common(c, srcs);
 }
 
 uint32_t pbk_shard_of_key(const uint64_t *key_words, uint32_t k, uint32_t n_shards)

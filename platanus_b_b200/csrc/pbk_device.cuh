@@ -69,6 +69,17 @@ struct Counters {
     u32 pad;
 };
 
+// Where Pass B of the key exchange finds the keys addressed to this shard: per source rank s, keys[s] = that source's
+// segments for this destination, [region][seg_cap] entries, and cursors[s] = their fill counts, [region].  Two ways to get
+// there: the all-to-all receive buffer of this GPU (pbk_keyx_insert_device: keys[s] = recv + s * R * seg_cap), or -- the
+// pull form, pbk_keyx_pull_* -- the bucket store Pass A filled on GPU s, read in place over NVLink (peer pointers): the
+// transfer then IS Pass B's own streaming loads, tile by tile, and no collective moves the keys.
+constexpr int KEYX_MAX_SRC = 16;
+struct KeyxSources {
+    const u64 *keys[KEYX_MAX_SRC];
+    const u64 *cursors[KEYX_MAX_SRC];
+};
+
 enum : u32 { ERR_BAD_BASE = 1u, ERR_READ_TOO_LONG = 2u, ERR_OVERFLOW_LOST = 4u };
 
 __host__ __device__ __forceinline__ u64 fmix64(u64 x)

@@ -281,11 +281,11 @@ void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *counts, v
     }
 }
 
-// Key exchange (k <= 32): Pass B over the all-to-all receive buffer, [source][region][seg_cap] entries.  `counts`
-// are in descriptor order (descriptor i = region i / n_src, source i % n_src); descriptors [d_first, d_end) of
-// n_src x n_regions are inserted by this launch.  While (region j, source s) is worked on, slice s of region j + 1
-// is prefetched.
-void launch_bucket_insert_gathered(const u64 *recv_keys, u64 seg_cap, const u64 *counts, void *h_desc, void *d_desc,
+// Key exchange (k <= 32): Pass B over the keys every source holds for this shard (KeyxSources: slices of the all-to-all
+// receive buffer, or the peers' bucket stores read in place over NVLink).  `counts` are in descriptor order (descriptor
+// i = region i / n_src, source i % n_src); descriptors [d_first, d_end) of n_src x n_regions are inserted by this launch.
+// While (region j, source s) is worked on, slice s of region j + 1 is prefetched.
+void launch_bucket_insert_gathered(const KeyxSources &srcs, u64 seg_cap, const u64 *counts, void *h_desc, void *d_desc,
                                    u32 d_first, u32 d_end, u32 n_src, u32 n_regions, TableView table, Counters *ctr,
                                    u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st)
 {
@@ -311,27 +311,25 @@ void launch_bucket_insert_gathered(const u64 *recv_keys, u64 seg_cap, const u64 
     const int ctas = getenv("PBK_PASSB_CTAS") ? atoi(getenv("PBK_PASSB_CTAS")) : 3;
     const u32 opts = (getenv("PBK_PASSB_HINT") ? ((u32)atoi(getenv("PBK_PASSB_HINT")) & 0xFFu) : 1u) | (n_src << 8) | (n_regions << 16);
     const int grid = (int)std::min<u64>(tiles, (u64)sm_count * ctas);
-    const Table<1> t(table.slots, table.cap);
-    bucket_insert_compact_kernel<2><<<grid, PASSB_THREADS, 0, st>>>(recv_keys, seg_cap, d_bk, d_first, d_end, (u64 *)d_desc,
-        t, t, 1, 0, ctr, overflow_keys, overflow_cap, opts);
+    bucket_insert_gather_kernel<<<grid, PASSB_THREADS, 0, st>>>(srcs, seg_cap, d_bk, d_first, d_end, (u64 *)d_desc,
+        Table<1>(table.slots, table.cap), ctr, overflow_keys, overflow_cap, opts);
 }
 
-// the same without a host round trip: tile map built on the device from the received cursors, Pass B right behind it
-void launch_bucket_insert_gathered_chained(const u64 *recv_keys, const u64 *d_recv_cursors, u64 seg_cap, void *d_desc, u32 n_src,
+// the same without a host round trip: tile map built on the device from the sources' cursors, Pass B right behind it
+void launch_bucket_insert_gathered_chained(const KeyxSources &srcs, u64 seg_cap, void *d_desc, u32 n_src,
                                            u32 n_regions, TableView table, Counters *ctr, u64 *overflow_keys, u64 overflow_cap,
                                            int sm_count, cudaStream_t st)
 {
     if (table.words != 1) return;
     const int pf_dist = getenv("PBK_PF_DIST") ? atoi(getenv("PBK_PF_DIST")) : 1;
     const u32 n_desc = n_src * n_regions;
-    passb_desc_gather_kernel<<<1, PART_MAX_BUCKETS, 0, st>>>(d_recv_cursors, seg_cap, n_src, n_regions, (u32)PASSB1_TILE_KEYS,
+    passb_desc_gather_kernel<<<1, PART_MAX_BUCKETS, 0, st>>>(srcs, seg_cap, n_src, n_regions, (u32)PASSB1_TILE_KEYS,
         (const char *)table.slots, table.cap, (u32)table.slot_bytes(), pf_dist, (u64 *)d_desc, (PassBBucket *)((char *)d_desc + 16));
     const PassBBucket *d_bk = (const PassBBucket *)((const char *)d_desc + 16);
     const int ctas = getenv("PBK_PASSB_CTAS") ? atoi(getenv("PBK_PASSB_CTAS")) : 3;
     const u32 opts = (getenv("PBK_PASSB_HINT") ? ((u32)atoi(getenv("PBK_PASSB_HINT")) & 0xFFu) : 1u) | (n_src << 8) | (n_regions << 16);
-    const Table<1> t(table.slots, table.cap);
-    bucket_insert_compact_kernel<2><<<sm_count * ctas, PASSB_THREADS, 0, st>>>(recv_keys, seg_cap, d_bk, 0, n_desc, (u64 *)d_desc,
-        t, t, 1, 0, ctr, overflow_keys, overflow_cap, opts);                  // CTAs that find no tile left leave at once
+    bucket_insert_gather_kernel<<<sm_count * ctas, PASSB_THREADS, 0, st>>>(srcs, seg_cap, d_bk, 0, n_desc, (u64 *)d_desc,
+        Table<1>(table.slots, table.cap), ctr, overflow_keys, overflow_cap, opts);    // CTAs that find no tile left leave at once
 }
 
 // device-chained variant for k <= 32: tile map built by a kernel from the cursors, Pass B launched on `st_insert`
@@ -382,7 +380,7 @@ void launch_table_clamp(TableView t, cudaStream_t st)
 
 void launch_table_histogram(TableView t, u64 *occ_hist, cudaStream_t st)
 {
-    const int grid = grid_for(t.capacity(), 256, 148, 4);
+    const int grid = grid_for(t.capacity() / 8 + 1, 256, 148, 8);      // 8 slots per thread and iteration, 8 resident CTAs per SM
     PBK_DISPATCH_W(t.words, (histogram_kernel<W><<<grid, 256, 0, st>>>(Table<W>(t.slots, t.cap), occ_hist)));
 }
 

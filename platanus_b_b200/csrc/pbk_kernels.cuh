@@ -70,10 +70,10 @@ void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64
 // Key exchange between GPUs (k <= 32, pbk_keyx_*): plan with n_dest x n_regions buckets in destination-major order
 // (launch_partition with keyx_dest = n_dest fills it), and Pass B over the all-to-all receive buffer.
 PartitionPlan plan_partition_keyx(u32 n_dest, u64 max_windows_any_rank, int words, size_t smem_budget = 0);
-void launch_bucket_insert_gathered(const u64 *recv_keys, u64 seg_cap, const u64 *counts, void *h_desc, void *d_desc,
+void launch_bucket_insert_gathered(const KeyxSources &srcs, u64 seg_cap, const u64 *counts, void *h_desc, void *d_desc,
                                    u32 d_first, u32 d_end, u32 n_src, u32 n_regions, TableView table, Counters *ctr,
                                    u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st);
-void launch_bucket_insert_gathered_chained(const u64 *recv_keys, const u64 *d_recv_cursors, u64 seg_cap, void *d_desc, u32 n_src,
+void launch_bucket_insert_gathered_chained(const KeyxSources &srcs, u64 seg_cap, void *d_desc, u32 n_src,
                                            u32 n_regions, TableView table, Counters *ctr, u64 *overflow_keys, u64 overflow_cap,
                                            int sm_count, cudaStream_t st);
 // Pass B over buckets [b_first, b_end) in one launch.  `h_desc` is scratch for b_end - b_first + 1 bucket

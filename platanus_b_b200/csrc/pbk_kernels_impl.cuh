@@ -877,16 +877,16 @@ passb_desc_kernel(const u64 *__restrict__ cursor, u64 seg_cap, u32 n_buckets, u3
 }
 
 // Tile map for Pass B in gather mode (key exchange): descriptor i = (table region i / n_src, source i % n_src), its fill
-// count is cursor[source][region] of the all-to-all receive buffer.  Built on the device so that a received chunk can be
+// count is the cursor of that source for (this destination, region).  Built on the device so that a chunk can be
 // inserted without a host round trip.
 __global__ void __launch_bounds__(PART_MAX_BUCKETS)
-passb_desc_gather_kernel(const u64 *__restrict__ recv_cursor, u64 seg_cap, u32 n_src, u32 n_regions, u32 tile_keys, const char *tab,
+passb_desc_gather_kernel(const __grid_constant__ KeyxSources srcs, u64 seg_cap, u32 n_src, u32 n_regions, u32 tile_keys, const char *tab,
                          u64 tab_cap, u32 slot_bytes, int pf_dist, u64 *ticket, PassBBucket *out)
 {
     __shared__ u64 s_tiles[PART_MAX_BUCKETS + 1];
     const u32 n_desc = n_src * n_regions;
     for (u32 i = threadIdx.x; i < n_desc; i += blockDim.x) {
-        const u64 n = min(recv_cursor[(i % n_src) * n_regions + i / n_src], seg_cap);
+        const u64 n = min(ld_cg_u64(srcs.cursors[i % n_src] + i / n_src), seg_cap);
         PassBBucket d;
         d.tile_start = 0; d.n_keys = n;
         d.pf_base = d.pf_base2 = nullptr; d.pf_lines = d.pf_lines2 = 0;
@@ -1041,10 +1041,10 @@ __device__ __forceinline__ void passb1_round(const u64 *__restrict__ src, u32 n_
 // (descriptor i = region i / G, source i % G, with G = opts bits 8-15 and the regions per source in bits 16-31), so
 // all sources' keys of one table region are inserted while that region is L2-resident.
 template <int MODE>
-__global__ void __launch_bounds__(PASSB_THREADS, 3)
-bucket_insert_compact_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, const PassBBucket *__restrict__ bk,
-                             u32 b_first, u32 b_end, u64 *ticket, Table<1> table, Table<1> remote, u32 n_shards,
-                             u32 rank, Counters *ctr, u64 *ovf, u64 ovf_cap, u32 opts)
+__device__ __forceinline__ void
+bucket_insert_compact_body(const u64 *__restrict__ bkt_hash, u64 seg_cap, const PassBBucket *__restrict__ bk,
+                           u32 b_first, u32 b_end, u64 *ticket, const Table<1> &table, const Table<1> &remote, u32 n_shards,
+                           u32 rank, Counters *ctr, u64 *ovf, u64 ovf_cap, u32 opts, const KeyxSources *srcs)
 {
     constexpr bool SHARDED = MODE == 1;
     // (the bucket descriptors are read straight from global memory: a few cached loads per 8192-key tile, and the
@@ -1075,12 +1075,14 @@ bucket_insert_compact_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, cons
         if (tid == 0) s_ticket[par] = atomicAdd(ticket, 1ull);   // ticket for the tile after next
         if (bk[lb].pf_base) passb_prefetch(bk[lb].pf_base, bk[lb].pf_lines, j, nt, tid, nthreads);
         if (SHARDED && bk[lb].pf_base2) passb_prefetch(bk[lb].pf_base2, bk[lb].pf_lines2, j, nt, tid, nthreads);
-        u32 seg = b_first + lb;
-        if constexpr (MODE == 2) {
-            const u32 G = (opts >> 8) & 0xFFu, R = opts >> 16;
-            seg = (seg % G) * R + seg / G;
+        const u32 seg = b_first + lb;
+        const u64 *src;
+        if constexpr (MODE == 2) {                               // descriptor = (region seg / G, source seg % G)
+            const u32 G = (opts >> 8) & 0xFFu;
+            src = srcs->keys[seg % G] + (u64)(seg / G) * seg_cap + j * tile_keys;
+        } else {
+            src = bkt_hash + (u64)seg * seg_cap + j * tile_keys;
         }
-        const u64 *src = bkt_hash + (u64)seg * seg_cap + j * tile_keys;
         const u64 left = n - j * tile_keys;                      // > 0 by construction of the tile numbering
         if (left >= tile_keys) {
 #pragma unroll 1
@@ -1118,6 +1120,25 @@ bucket_insert_compact_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, cons
         if (newk) atomicAdd(&ctr->new_keys, (u64)newk);
         if (newr) atomicAdd(&ctr->new_keys_remote, (u64)newr);
     }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(PASSB_THREADS, 3)
+bucket_insert_compact_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, const PassBBucket *__restrict__ bk,
+                             u32 b_first, u32 b_end, u64 *ticket, Table<1> table, Table<1> remote, u32 n_shards,
+                             u32 rank, Counters *ctr, u64 *ovf, u64 ovf_cap, u32 opts)
+{
+    static_assert(MODE == 0 || MODE == 1, "MODE 2 (key exchange) is bucket_insert_gather_kernel");
+    bucket_insert_compact_body<MODE>(bkt_hash, seg_cap, bk, b_first, b_end, ticket, table, remote, n_shards, rank, ctr, ovf, ovf_cap,
+                                     opts, nullptr);
+}
+
+// MODE 2 as a kernel: Pass B over the keys every source rank holds for this shard (KeyxSources: receive buffer or peer HBM)
+__global__ void __launch_bounds__(PASSB_THREADS, 3)
+bucket_insert_gather_kernel(const __grid_constant__ KeyxSources srcs, u64 seg_cap, const PassBBucket *__restrict__ bk,
+                            u32 b_first, u32 b_end, u64 *ticket, Table<1> table, Counters *ctr, u64 *ovf, u64 ovf_cap, u32 opts)
+{
+    bucket_insert_compact_body<2>(nullptr, seg_cap, bk, b_first, b_end, ticket, table, table, 1u, 0u, ctr, ovf, ovf_cap, opts, &srcs);
 }
 
 // Pass B for multi-word keys (k > 32), batched like the one-word kernel: a thread works on PASSBW_KPT<W> new keys plus
@@ -1319,31 +1340,60 @@ __global__ void __launch_bounds__(256) clamp_kernel(Table<W> t)
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.cap; i += stride) t.clamp(i);
 }
 
-// clamp + ++occurrenceDistribution[count] (counter.h:496).  Low counts go through a shared-memory
-// histogram, the long tail straight to global atomics.
+// clamp + ++occurrenceDistribution[count] (counter.h:496): one streaming pass over the table.  Low counts go through a
+// shared-memory histogram, the long tail straight to global atomics; count 1 -- most of a read set's distinct k-mers are
+// sequencing-error singletons, which would put nearly every shared-memory atomic of a warp on ONE address -- is tallied in a
+// register.  A thread keeps HIST_ILP independent 16-byte loads in flight (the first version had one 8-byte load per thread
+// outstanding and ran at a third of the HBM rate).
 constexpr int HIST_SMEM_BINS = 4096;
+constexpr int HIST_ILP = 4;
 template <int W>
 __global__ void __launch_bounds__(256) histogram_kernel(Table<W> t, u64 *occ_hist)
 {
     __shared__ u32 sh[HIST_SMEM_BINS];
     for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.cap; i += stride) {
-        u32 c;
-        if constexpr (W == 1) {                       // no need to rebuild the key here
-            const u64 v = t.slots[i];
-            if ((v >> t.g.cbits) == 0) continue;
-            const u64 cc = v & t.g.cmask;
-            c = cc > COUNT_SAT ? COUNT_SAT : (u32)cc;
-        } else {
-            c = t.slots[i].cs;
-            if (c == 0) continue;
-            if (c > COUNT_SAT) c = COUNT_SAT;
-        }
+    const u64 stride = (u64)gridDim.x * blockDim.x, gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 ones = 0;
+    auto tally = [&](u32 c) {
+        if (c == 0) return;
+        if (c == 1) { ++ones; return; }
+        if (c > COUNT_SAT) c = COUNT_SAT;
         if (c < HIST_SMEM_BINS) atomicAdd(&sh[c], 1u);
         else atomicAdd(&occ_hist[c], 1ull);
+    };
+    if constexpr (W == 1) {                           // two 8-byte slots per load; the key is not needed here
+        const u64 n2 = t.cap / 2;                     // capacity is a power of two >= 2^27 (tests/cpu_emul: any even number)
+        const int cbits = t.g.cbits;
+        const u64 cmask = t.g.cmask;
+        for (u64 i0 = gtid; i0 < n2; i0 += stride * HIST_ILP) {
+            ulonglong2 v[HIST_ILP];
+#pragma unroll
+            for (int j = 0; j < HIST_ILP; ++j) {
+                const u64 i = i0 + (u64)j * stride;
+                v[j] = i < n2 ? ld_stream_u64x2(t.slots + 2 * i) : make_ulonglong2(0, 0);
+            }
+#pragma unroll
+            for (int j = 0; j < HIST_ILP; ++j) {
+                if (v[j].x >> cbits) { const u64 c = v[j].x & cmask; tally(c > COUNT_SAT ? COUNT_SAT : (u32)c); }
+                if (v[j].y >> cbits) { const u64 c = v[j].y & cmask; tally(c > COUNT_SAT ? COUNT_SAT : (u32)c); }
+            }
+        }
+        if (t.cap & 1) { if (gtid == 0) { u64 key, c; if (ct_decode(t.slots[t.cap - 1], t.cap - 1, t.g, &key, &c)) tally(c > COUNT_SAT ? COUNT_SAT : (u32)c); } }
+    } else {
+        for (u64 i0 = gtid; i0 < t.cap; i0 += stride * HIST_ILP) {
+            u32 c[HIST_ILP];
+#pragma unroll
+            for (int j = 0; j < HIST_ILP; ++j) {
+                const u64 i = i0 + (u64)j * stride;
+                c[j] = i < t.cap ? ld_cg_u32(&t.slots[i].cs) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < HIST_ILP; ++j) tally(c[j]);
+        }
     }
+    ones = warp_sum_u32(ones);
+    if ((threadIdx.x & 31) == 0 && ones) atomicAdd(&sh[1], ones);
     __syncthreads();
     for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x)
         if (sh[i]) atomicAdd(&occ_hist[i], (u64)sh[i]);

@@ -173,6 +173,43 @@ class KeyExchange:
         return sent
 
 
+class KeyPull:
+    """Pull form of the key exchange (pbk_keyx_pull_*): no collective moves the keys.  Every rank's Pass A fills its own owner-major
+    bucket store; after a barrier every rank's Pass B reads the segments addressed to it straight out of its peers' HBM over
+    NVLink (the stores are mapped into each other's address space once, at set-up: CUDA IPC handles travel through one
+    all_gather).  Per step the host side is: partition -> barrier (a one-element all_reduce on the caller's stream, ordered
+    against the library's stream on the device) -> insert."""
+
+    def __init__(self, kc, world: int, rank: int, max_windows: int, device=None, group=None):
+        self.kc, self.world, self.rank, self.device, self.group = kc, world, rank, device, group
+        self.lay = kc.keyx_pull_setup(max_windows_any_rank(max_windows, device=device, group=group))
+        mine = torch.frombuffer(bytearray(kc.keyx_pull_handle()), dtype=torch.uint8).to(device)
+        handles = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(handles, mine, group=group)
+        for r in range(world):
+            if r != rank:
+                kc.keyx_pull_connect_ipc(r, bytes(handles[r].cpu().numpy().tobytes()))
+        self._token = torch.zeros(1, dtype=torch.int32, device=device)
+        self.record_bufs: dict = {}
+        dist.barrier(group=group)                    # every rank has mapped every store before anybody starts reading
+
+    def step(self, partition, sync, caller_stream=None) -> int:
+        """partition() runs pbk_keyx_pull_partition* for this rank's batch.  Returns the bytes this rank's peers read from it."""
+        partition()
+        if caller_stream is not None:                # device-ordered: no host synchronisation inside the step
+            self.kc.stream_signal(caller_stream())
+            dist.all_reduce(self._token, group=self.group)
+            self.kc.stream_wait(caller_stream())
+        else:
+            dist.all_reduce(self._token, group=self.group)
+            sync()
+        self.kc.keyx_pull_insert()
+        pulled = (self.world - 1) * int(self.lay.bytes_per_dest)
+        if any_rank_staged(int(self.kc.shard_send_counts(self.world).sum()), device=self.device, group=self.group):
+            pulled += exchange_staged_records(self.kc, self.world, self.device, self.record_bufs, sync, self.group)
+        return pulled
+
+
 # ---- the outputs of a sharded count (SURVEY.md section 8e, collective 3) --------------------------------------------------
 
 def gather_sorted_entries(kc, min_count: int, world: int, rank: int, dst: int = 0, group=None, device=None):

@@ -14,6 +14,7 @@
 #define __forceinline__ inline
 #define __noinline__
 #define __restrict__
+#define __grid_constant__
 #define __launch_bounds__(...)
 #define __shared__ static
 

@@ -205,8 +205,10 @@ extern "C" int emul_keyx_insert(const u64 *recv, const u64 *recv_cursors, u32 n_
             tiles += (n + tk - 1) / tk;
         }
         desc[d1 - d0] = PassBBucket{tiles, 0, nullptr, nullptr, 0, 0};
-        if (tiles) bucket_insert_compact_kernel<2>(recv, seg_cap, desc.data(), d0, d1, ticket, t, t, 1, 0, &ctr, ovf.data(), OVF,
-                                                   (n_src << 8) | (n_regions << 16));
+        KeyxSources srcs{};
+        for (u32 sr = 0; sr < n_src; ++sr) { srcs.keys[sr] = recv + (u64)sr * n_regions * seg_cap; srcs.cursors[sr] = recv_cursors + (u64)sr * n_regions; }
+        if (tiles) bucket_insert_gather_kernel(srcs, seg_cap, desc.data(), d0, d1, ticket, t, &ctr, ovf.data(), OVF,
+                                               (n_src << 8) | (n_regions << 16));
     }
     if (n_extra) insert_records_kernel<1>(extra, n_extra, 1, t, t, 1, 0, &ctr, ovf.data(), OVF);
     *n_out = 0;

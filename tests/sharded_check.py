@@ -20,7 +20,8 @@ for p in (ROOT, HERE):
 
 
 def run_checks(rank: int, world: int, k: int, mode: str, n_chunks: int, out_dir: str, device=None, scale: float = 1 / 400, reps: int = 2):
-    """mode: 'records' | 'keys' | 'keys_async'.  device None = host tensors (emulated ABI), 'cuda' = the real thing."""
+    """mode: 'records' | 'keys' | 'keys_async' | 'pull' | 'pull_async'.  device None = host tensors (emulated ABI), 'cuda' = the real
+    thing ('pull*' maps the peers' HBM through CUDA IPC and therefore only exists there)."""
     from oracle import oracle as O
     from platanus_b_b200 import KmerCounter, capi, sharding, synth
     L = capi.load_library()
@@ -36,9 +37,23 @@ def run_checks(rank: int, world: int, k: int, mode: str, n_chunks: int, out_dir:
     b = np.ascontiguousarray(bases[int(offs[lo]):int(offs[hi])])
     o = (offs[lo:hi + 1] - offs[lo]).astype(np.uint64)
     with KmerCounter(k, device=(torch.cuda.current_device() if cuda else -1), n_shards=world, shard_rank=rank) as kc:
+        puller = None
         for rep in range(reps):                                     # later passes: reset, tables and layout reused, queued inserts
             kc.reset()
-            if mode.startswith("keys"):
+            if mode.startswith("pull"):
+                if puller is None:
+                    puller = sharding.KeyPull(kc, world, rank, max(int(o[-1]) - (len(o) - 1) * (k - 1), 0), device=device)
+                if mode == "pull" or rep == 0:
+                    sent = puller.step(lambda: kc.keyx_pull_partition(b, o), sync)
+                else:                                               # device-ordered: inputs resident, no host sync inside the step
+                    t_b = torch.from_numpy(b).to(device)
+                    t_o = torch.from_numpy(o.view(np.int64)).to(device)
+                    sync()
+                    sent = puller.step(lambda: kc.keyx_pull_partition_device(t_b.data_ptr(), t_o.data_ptr(), len(o) - 1, int(o[-1]), True), sync,
+                                       caller_stream=lambda: torch.cuda.current_stream().cuda_stream)
+                if rep >= 1:
+                    assert kc.stats()["n_pipelined_batches"] >= 1
+            elif mode.startswith("keys"):
                 ranges = sharding.chunk_read_ranges(o, n_chunks)
                 n_ch = sharding.max_windows_any_rank(len(ranges), device=device)
                 ranges += [(len(o) - 1, len(o) - 1)] * (n_ch - len(ranges))
@@ -92,7 +107,8 @@ def main():
     scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1 / 20
     out = tempfile.mkdtemp()
     try:
-        for k, mode, n_chunks in ((32, "records", 1), (75, "records", 1), (32, "keys", 3), (32, "keys_async", 4), (21, "keys_async", 2)):
+        for k, mode, n_chunks in ((32, "records", 1), (75, "records", 1), (32, "keys", 3), (32, "keys_async", 4), (21, "keys_async", 2),
+                                  (32, "pull", 1), (32, "pull_async", 1), (21, "pull_async", 1)):
             run_checks(rank, world, k, mode, n_chunks, out, device="cuda", scale=scale, reps=3)
             dist.barrier()
             if rank == 0:

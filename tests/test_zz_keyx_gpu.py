@@ -137,3 +137,84 @@ def test_heavily_duplicated_input_cannot_exhaust_the_overflow_list(oracle):
         assert kc.stats()["launches_partition"] >= 1            # the bucket pass was taken
     assert np.array_equal(keys, want.keys) and np.array_equal(counts, want.counts)
     assert np.array_equal(kc.occ_hist, want.occ_hist)
+
+
+# ---- third form: the pull exchange (pbk_keyx_pull_*) -- Pass B reads the peers' bucket stores in place ---------------------------
+
+def _pull_logical_shards(O, b, o, k, n_shards, n_batches=1):
+    """G logical shards on one GPU (contexts of one process, pbk_keyx_pull_connect_local): per batch every shard partitions into
+    its own store, then -- all partitions done: the host is the barrier here -- every shard inserts what its peers hold for it."""
+    n = len(o) - 1
+    ctxs = [KmerCounter(k, n_shards=n_shards, shard_rank=r) for r in range(n_shards)]
+    try:
+        cuts = [n * i // (n_shards * n_batches) for i in range(n_shards * n_batches + 1)]
+        parts = [(b[int(o[cuts[i]]):int(o[cuts[i + 1]])], o[cuts[i]:cuts[i + 1] + 1] - o[cuts[i]]) for i in range(n_shards * n_batches)]
+        max_w = max(max(int(po[-1]) - (len(po) - 1) * (k - 1), 0) for _, po in parts)
+        lays = [kc.keyx_pull_setup(max_w) for kc in ctxs]
+        assert all((l.n_regions, l.seg_cap) == (lays[0].n_regions, lays[0].seg_cap) for l in lays)
+        for r, kc in enumerate(ctxs):
+            for s, peer in enumerate(ctxs):
+                if s != r:
+                    kc.keyx_pull_connect_local(s, peer)
+        staged = 0
+        for bi in range(n_batches):                               # successive batches alternate between the two store parities
+            for r, kc in enumerate(ctxs):
+                pb, po = parts[bi * n_shards + r]
+                kc.keyx_pull_partition(pb, po)
+            for kc in ctxs:
+                kc.keyx_pull_insert()
+            counts = [kc.shard_send_counts(n_shards) for kc in ctxs]      # record route: keys that found their segment full
+            staged += int(sum(c.sum() for c in counts))
+            from devbuf import DevBuf
+            packs, tmp = [], []
+            for kc, cnt in zip(ctxs, counts):
+                packs.append(DevBuf((int(cnt.sum()) + 1) * 16)); tmp.append(packs[-1])
+                kc.shard_pack_device(packs[-1].ptr, int(cnt.sum()) + 1)
+            for dest, kc in enumerate(ctxs):
+                for src in range(n_shards):
+                    m = int(counts[src][dest])
+                    if src == dest or m == 0:
+                        continue
+                    part = DevBuf(m * 16); tmp.append(part)
+                    part.copy_from(packs[src], 0, int(counts[src][:dest].sum()) * 16, m * 16)
+                    kc.shard_insert_device(part.ptr, m)
+            for d in tmp:
+                d.free()
+        keys, cts, inst, hist = [], [], 0, np.zeros(65535, np.uint64)
+        for kc in ctxs:
+            kc.finalize()
+            kk, cc = kc.export(1, sorted=True)
+            keys.append(kk); cts.append(cc); inst += kc.n_instances; hist += kc.occ_hist
+        keys = np.concatenate(keys); cts = np.concatenate(cts)
+        order = np.argsort(keys[:, 0], kind="stable")
+        return keys[order], cts[order], inst, hist, staged, [int(kc.n_distinct) for kc in ctxs]
+    finally:
+        for kc in ctxs:
+            kc.close()
+
+
+@pytest.mark.parametrize("k,n_shards,n_batches", [(32, 2, 1), (21, 3, 3), (32, 8, 2)])
+def test_pull_exchange_logical_shards_match_unsharded(oracle, k, n_shards, n_batches):
+    """SURVEY.md section 8e, third form (include/pbk.h, pbk_keyx_pull_*): nobody sends keys, every shard's Pass B reads its peers'
+    stores through mapped pointers.  Several batches: the two store parities alternate and the table is kept between them."""
+    O = oracle
+    rs = synth.make_reads(synth.config("C1", scale=1 / 60))
+    b, o = rs.flat()
+    want = O.count(_oracle_reads_from_set(O, rs), k)
+    keys, cts, inst, hist, staged, sizes = _pull_logical_shards(O, b, o, k, n_shards, n_batches)
+    assert staged == 0
+    assert np.array_equal(keys, want.keys) and np.array_equal(cts, want.counts)
+    assert inst == want.n_instances and np.array_equal(hist, want.occ_hist)
+    assert max(sizes) < 1.2 * (sum(sizes) / n_shards) + 64
+
+
+def test_pull_exchange_full_segments_take_the_record_route(oracle, tmp_path):
+    O = oracle
+    case = G.CASE_BY_NAME["sat_k32"]
+    rd = _reads(O, case, tmp_path)
+    want = O.count(rd, case.k)
+    b, o = rd.arrays()
+    keys, cts, inst, hist, staged, _ = _pull_logical_shards(O, b, o, case.k, 4)
+    assert staged > 0
+    assert np.array_equal(keys, want.keys) and np.array_equal(cts, want.counts)
+    assert inst == want.n_instances and np.array_equal(hist, want.occ_hist)
