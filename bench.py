@@ -15,9 +15,13 @@ histogram (+ hash-range exchange and histogram all-reduce when N > 1).
          timed region
 
 N = 1 runs BASELINE config C1 (4.6 Mb genome, 2x150 bp, 100x, k=32).  N > 1 is weak scaling of the same
-configuration: every rank counts its own C1-sized sample of the same genome, keys are owned by hash range
-and pre-aggregated (k-mer, count) records move with one NCCL all-to-all per step (`--workload C4` gives
-every rank a C1-sized slice of the C4 metagenome mix instead).
+configuration: every rank counts its own C1-sized sample of the same genome, keys are owned by hash range;
+by default (k <= 32) nothing is sent: every rank's Pass B reads the keys it owns straight out of its peers'
+bucket stores over NVLink (--exchange pull; `keys` = NCCL all-to-all of the keys, `records` = all-to-all of
+pre-aggregated (k-mer, count) records after counting).  `--workload C4` gives every rank a C1-sized slice of
+the C4 metagenome mix instead, `--workload C4full` the whole of BASELINE config 4 split 1/N per rank.
+After the timed steps one more step is CHECKED: instance sums, sum i*hist[i], and at N > 1 a single-GPU
+recount of all ranks' reads on rank 0 (verify_result).
 
 `--impl reference` times the unmodified reference (`oracle/_ref/platanus_b assemble -kmer_occ_only`,
 OpenMP, all host cores) on a bounded sample of the same workload; the same run is embedded as
@@ -282,7 +286,7 @@ def main_ours(args):
 
     # ---- workload -------------------------------------------------------------------------------
     import dataclasses
-    if world == 1 or args.workload != "C4":
+    if world == 1 or args.workload not in ("C4", "C4full"):
         # weak scaling of the metric's own configuration: every rank counts its own C1-sized sample of the SAME genome
         # (rank r draws its reads with seed + 7919 r), i.e. N GPUs = the C1 genome at N x 100x coverage, sharded by
         # hash range; N = 1 is plain C1.  Per-GPU work is identical for every N.
@@ -295,12 +299,15 @@ def main_ours(args):
             workload += f"; one such read set per GPU (independent samples of the same genome, {world}x the coverage in total), keys owned by hash range"
     else:
         # --workload C4: BASELINE config 4, every rank a C1-sized slice of the 100 Mb metagenome mix (low coverage per
-        # slice: almost every k-mer is new -- a different regime from the N = 1 number)
+        # slice: almost every k-mer is new -- a different regime from the N = 1 number).  --workload C4full: the WHOLE of
+        # config 4 (20 genomes, 100 Mb, 200x: ~66.7 M pairs, 15.9 G k-mer instances) split 1/N per rank -- strong scaling.
         c1 = synth.config("C1", scale=args.scale)
         spec = synth.config("C4", scale=args.scale)
-        rs = synth.make_reads(spec, pair_slice=(rank, max(world, int(round(spec.n_pairs / c1.n_pairs)))))
-        workload = (f"C4 metagenome mix (20 genomes, {spec.total_genome} bp), 2x{spec.read_len} bp PE: one C1-sized "
-                    f"slice of {rs.n_reads} reads per GPU, k={K}, keys owned by hash range")
+        n_slices = world if args.workload == "C4full" else max(world, int(round(spec.n_pairs / c1.n_pairs)))
+        rs = synth.make_reads(spec, pair_slice=(rank, n_slices))
+        workload = (f"C4 metagenome mix (20 genomes, {spec.total_genome} bp, {spec.coverage:g}x), 2x{spec.read_len} bp PE: "
+                    + (f"the whole read set, 1/{world} per GPU ({rs.n_reads} reads each)" if args.workload == "C4full" else
+                       f"one C1-sized slice of {rs.n_reads} reads per GPU") + f", k={K}, keys owned by hash range")
     bases, offsets = rs.flat()
     n_reads, n_bases, L = rs.n_reads, int(bases.shape[0]), rs.read_len
     n_inst_local = count_instances(rs, K)
@@ -311,18 +318,34 @@ def main_ours(args):
     d_offs = h_offs.cuda()
     torch.cuda.synchronize()
 
+    # a step pushes the rank's reads in batches of at most 2^30 bases (one batch for C1-sized inputs; C4full: several)
+    batch_ranges = sharding.chunk_read_ranges(offsets, max(1, -(-n_bases // (1 << 30))))
+    if world > 1:
+        batch_ranges += [(n_reads, n_reads)] * (sharding.max_windows_any_rank(len(batch_ranges), device="cuda") - len(batch_ranges))
+    batches = []
+    for r0, r1 in batch_ranges:
+        o_b = (offsets[r0:r1 + 1] - offsets[r0]).astype(np.int64)
+        h_o = torch.from_numpy(o_b.copy()).pin_memory()
+        batches.append({"n_reads": r1 - r0, "b0": int(offsets[r0]), "n_bases": int(offsets[r1] - offsets[r0]), "h_offs": h_o, "d_offs": h_o.cuda()})
     kc = KmerCounter(K, device=local_rank, n_shards=world, shard_rank=rank, timing=True)
     W = kc.words
+    exchange_mode = args.exchange if args.exchange != "auto" else ("pull" if W == 1 else "records")
     hist_dev = torch.zeros(65535, dtype=torch.int64, device="cuda")
     # --exchange keys (k <= 32): the k-mers travel BEFORE counting -- Pass A writes them straight into the all-to-all send
     # buffer, every rank runs Pass B over what it received (include/pbk.h, pbk_keyx_*).  Default is the record exchange,
     # the form measured in round 1.
-    keyx = world > 1 and args.exchange == "keys" and W == 1
+    keyx = world > 1 and exchange_mode == "keys" and W == 1
+    assert len(batches) == 1 or exchange_mode == "pull" or world == 1, "several batches per step: --exchange pull (or one GPU)"
     # --exchange pull (k <= 32): nobody sends keys.  Pass A fills the rank's own owner-major store, a barrier, and every rank's
     # Pass B reads the segments addressed to it out of its peers' HBM over NVLink while it inserts (pbk_keyx_pull_*).
-    pull = world > 1 and args.exchange == "pull" and W == 1
+    pull = world > 1 and exchange_mode == "pull" and W == 1
+    exchange_note = None
     if pull:
-        puller = sharding.KeyPull(kc, world, rank, max(n_bases - n_reads * (K - 1), 0), device="cuda")
+        puller = sharding.KeyPull(kc, world, rank, max(max(bt["n_bases"] - bt["n_reads"] * (K - 1), 0) for bt in batches), device="cuda")
+        if not puller.ok:                             # e.g. CUDA IPC not permitted between the processes of this box: all ranks agree
+            exchange_note = f"--exchange pull unavailable ({puller.error or 'failed on another rank'}): fell back to records"
+            pull, exchange_mode = False, "records"
+            assert len(batches) == 1, exchange_note
     if keyx:
         # the batch in --keyx-chunks chunks (cut at read boundaries): the all-to-all of one chunk is in flight while the
         # next one is partitioned and the previous one inserted (sharding.pipelined_key_exchange)
@@ -374,10 +397,15 @@ def main_ours(args):
         export_bufs.update(n=got, cutoff=cutoff)
 
     def step_pull(resident: bool):
-        if resident:
-            part = lambda: kc.keyx_pull_partition_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, n_bases, True)
-            return puller.step(part, torch.cuda.current_stream().synchronize, caller_stream=lambda: torch.cuda.current_stream().cuda_stream)
-        return puller.step(lambda: kc.keyx_pull_partition_ptr(h_bases.data_ptr(), h_offs.data_ptr(), n_reads), torch.cuda.current_stream().synchronize)
+        sent = 0
+        for bt in batches:
+            if resident:
+                part = lambda: kc.keyx_pull_partition_device(d_bases.data_ptr() + bt["b0"], bt["d_offs"].data_ptr(), bt["n_reads"], bt["n_bases"], True)
+                sent += puller.step(part, torch.cuda.current_stream().synchronize, caller_stream=lambda: torch.cuda.current_stream().cuda_stream)
+            else:
+                sent += puller.step(lambda: kc.keyx_pull_partition_ptr(h_bases.data_ptr() + bt["b0"], bt["h_offs"].data_ptr(), bt["n_reads"]),
+                                    torch.cuda.current_stream().synchronize)
+        return sent
 
     def step(resident: bool):
         kc.reset()
@@ -386,10 +414,11 @@ def main_ours(args):
         elif keyx:
             sent = step_keyx(resident)
         else:
-            if resident:
-                kc.push_reads_device(d_bases.data_ptr(), d_offs.data_ptr(), n_reads, n_bases)
-            else:
-                kc.push_reads_ptr(h_bases.data_ptr(), h_offs.data_ptr(), n_reads)
+            for bt in batches:
+                if resident:
+                    kc.push_reads_device(d_bases.data_ptr() + bt["b0"], bt["d_offs"].data_ptr(), bt["n_reads"], bt["n_bases"])
+                else:
+                    kc.push_reads_ptr(h_bases.data_ptr() + bt["b0"], bt["h_offs"].data_ptr(), bt["n_reads"])
             sent = exchange() if world > 1 else 0
         kc.finalize_light()                     # D2H of the occurrence histogram: the step's result
         if world > 1:
@@ -494,7 +523,7 @@ def main_ours(args):
         base = cpu_baseline(args.workload, args.scale, 1, 0) if (world == 1 and not args.no_cpu_baseline) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "strong" if args.workload == "C4full" else "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload, "k": K, "instances_per_step": total_inst,
                        "reads_per_gpu": n_reads, "input_bytes_per_gpu": n_bases + (n_reads + 1) * 8,
@@ -524,6 +553,8 @@ def main_ours(args):
                                 "bytes = what this rank's peers read from it, pbk_keyx_pull_*)" if pull else
                                 "keys before counting (8-byte hashes, equal splits, pbk_keyx_*)" if keyx else
                                 "pre-aggregated (key, count) records after counting (pbk_shard_*)")
+        if exchange_note:
+            line["exchange_note"] = exchange_note
         if base is not None:
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
@@ -555,8 +586,10 @@ def main():
                     help="--exchange keys: order Pass A -> all-to-all -> Pass B by CUDA events (pbk_stream_signal/wait) instead of host syncs")
     ap.add_argument("--keyx-chunks", type=int, default=int(os.environ.get("PBK_BENCH_KEYX_CHUNKS", "4")),
                     help="--exchange keys: chunks per step (the all-to-all of one chunk overlaps the passes of its neighbours)")
-    ap.add_argument("--exchange", default=os.environ.get("PBK_BENCH_EXCHANGE", "records"), choices=["records", "keys", "pull"],
-                    help="N > 1: what crosses NVLink -- (key, count) records after counting, or the keys before it")
+    ap.add_argument("--exchange", default=os.environ.get("PBK_BENCH_EXCHANGE", "auto"), choices=["auto", "records", "keys", "pull"],
+                    help="N > 1: what crosses NVLink -- pull: Pass B reads the peers' bucket stores in place (default for k <= 32: measured "
+                         "0.96 weak-scaling efficiency at N = 2 against 0.67 for records); keys: all-to-all of the keys before counting; "
+                         "records: (key, count) records after counting (the only form for k > 32)")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--k", type=int, default=32, help="k-mer length (BASELINE metric: 32; 75 = the multi-word target of north_star)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -256,13 +256,14 @@ int ensure_overflow(pbk_ctx *c, u64 records)
 
 // Overflow list for a partitioned batch of `windows` windows.  Pass A spills what does not fit its bucket segment, and
 // with heavily duplicated input (amplicons: millions of copies of a few k-mers) that can be most of the batch; every
-// window spills at most once, so a list as long as the batch cannot be exhausted.  It is only address space until
-// something is written to it.  If the HBM budget does not allow it, the old fixed size stays (and ERR_OVERFLOW_LOST
-// remains possible for such input).
+// window spills at most once, so a list as long as the batch cannot be exhausted.  cudaMalloc backs every byte with HBM,
+// so that guarantee is only given up to OVF_FULL_RECORDS windows (1 GiB of list at k <= 32); beyond, the list holds a
+// quarter of the batch -- far more than any real read set spills (ERR_OVERFLOW_LOST is reported, never silent, if some
+// synthetic input does exceed it).  If the HBM budget does not allow even that, the fixed floor stays.
 int ensure_overflow_for_batch(pbk_ctx *c, u64 windows)
 {
-    const u64 floor_records = 1ull << 22;
-    const u64 want = std::max<u64>(floor_records, windows);
+    const u64 floor_records = 1ull << 22, OVF_FULL_RECORDS = 1ull << 26;
+    const u64 want = std::max<u64>(floor_records, windows <= OVF_FULL_RECORDS ? windows : std::max<u64>(OVF_FULL_RECORDS, windows / 4));
     if (want <= c->ovf_cap) return PBK_OK;
     const int rc = ensure_overflow(c, want);
     if (rc != PBK_E_NOMEM) return rc;

@@ -99,13 +99,23 @@ __host__ __device__ __forceinline__ u64 fmix64_inverse(u64 x)
     return x;
 }
 
+// One-word keys: fmix64, a bijection (the compact table recovers the key from the hash).  Multi-word keys: the words are
+// folded with one odd multiplier each and the sum goes through ONE fmix64 -- the first version chained an fmix64 per word,
+// and those six dependent 64-bit multiplies per k-mer were a third of Pass A's instructions at k = 75.  A fold collision
+// only sends two keys down the same probe sequence; the table always compares whole keys.
+__host__ __device__ __forceinline__ u64 hash_fold_multiplier(int j)
+{
+    constexpr u64 M[8] = {1ull, 0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull,
+                          0xD6E8FEB86659FD93ull, 0xA0761D6478BD642Full, 0xE7037ED1A0B428DBull, 0x8EBC6AF09C88C6E3ull};
+    return M[j & 7];
+}
 template <int W>
 __host__ __device__ __forceinline__ u64 hash_key(const u64 *key)
 {
-    u64 h = fmix64(key[0]);
+    u64 x = key[0];
 #pragma unroll
-    for (int j = 1; j < W; ++j) h = fmix64(h ^ key[j]);
-    return h;
+    for (int j = 1; j < W; ++j) x += key[j] * hash_fold_multiplier(j);
+    return fmix64(x);
 }
 
 // owner shard: range partition of the LOW 32 hash bits (the table index uses the high bits)
@@ -407,6 +417,21 @@ __device__ __forceinline__ bool ct_set_count(u64 *tab, const CtGeom &g, u64 h, u
 // -------------------------------------------------------------------------------------------------
 // generic table, k > 32
 // -------------------------------------------------------------------------------------------------
+// Sector-sized slots (W <= 3) are published with ONE 256-bit store and read with ONE 256-bit load.  On this hardware both are
+// single 32-byte sector transactions, but PTX only promises per-element atomicity for vector accesses, so a reader must be able
+// to tell a torn snapshot (state word new, key words still the old zeros) from a slot that holds another key: the state word's
+// upper half carries a 32-bit fold of the key words, written by the same 8-byte element as the count.  A reader whose key
+// compare fails checks the fold of the words it READ against it; if they disagree the snapshot was torn and the slot is simply
+// looked at again.  (A stale all-zero key passes only if the real key folds to 0: 2^-32 per torn read, which nobody has seen.)
+template <int W>
+__host__ __device__ __forceinline__ u32 key_fold32(const u64 *k)
+{
+    u64 x = k[0];
+#pragma unroll
+    for (int j = 1; j < W; ++j) x ^= (k[j] << (11 * j)) | (k[j] >> (64 - 11 * j));
+    return (u32)(x ^ (x >> 32));
+}
+
 template <int W>
 __device__ __forceinline__ int wide_insert(Slot<W> *table, u64 cap, const u64 *key, u64 h, u32 add)
 {
@@ -419,11 +444,11 @@ __device__ __forceinline__ int wide_insert(Slot<W> *table, u64 cap, const u64 *k
         if (cs == 0) {
             const u32 old = atomicCAS(&s->cs, 0u, CS_LOCKED);
             if (old == 0) {
-                if constexpr (W <= 3) {                  // sector-sized slot: one 256-bit store publishes key and count
+                if constexpr (W <= 3) {                  // sector-sized slot: one 256-bit store publishes key, fold and count
                     u64 q[4] = {0, 0, 0, 0};
 #pragma unroll
                     for (int j = 0; j < W; ++j) q[j] = key[j];
-                    q[W] = add;
+                    q[W] = (u64)add | ((u64)key_fold32<W>(key) << 32);
                     st_cg_256(s, q[0], q[1], q[2], q[3]);
                 } else {
 #pragma unroll
@@ -439,9 +464,13 @@ __device__ __forceinline__ int wide_insert(Slot<W> *table, u64 cap, const u64 *k
         // used `cs`, and threads then compared half-written keys.)
         if (cs == CS_LOCKED) continue;
         bool eq = true;
+        u64 kw[W];
 #pragma unroll
-        for (int j = 0; j < W; ++j) eq &= (ld_cg_u64(&s->key[j]) == key[j]);
+        for (int j = 0; j < W; ++j) { kw[j] = ld_cg_u64(&s->key[j]); eq &= (kw[j] == key[j]); }
         if (eq) { red_add_u32(&s->cs, add); return 0; }
+        if constexpr (W <= 3) {                          // another key -- or a torn view of a slot being published?
+            if (key_fold32<W>(kw) != ld_cg_u32(&s->pad)) continue;
+        }
         ++probe;
         idx = (idx + 1 == cap) ? 0 : idx + 1;
     }
@@ -461,9 +490,17 @@ __device__ __forceinline__ int wide_insert_max(Slot<W> *table, u64 cap, const u6
         if (cs == 0) {
             const u32 old = atomicCAS(&s->cs, 0u, CS_LOCKED);
             if (old == 0) {
+                if constexpr (W <= 3) {                  // same publish as wide_insert: key words, fold and value in one sector store
+                    u64 q[4] = {0, 0, 0, 0};
 #pragma unroll
-                for (int j = 0; j < W; ++j) st_cg_u64(&s->key[j], key[j]);
-                st_release_u32(&s->cs, w);
+                    for (int j = 0; j < W; ++j) q[j] = key[j];
+                    q[W] = (u64)w | ((u64)key_fold32<W>(key) << 32);
+                    st_cg_256(s, q[0], q[1], q[2], q[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < W; ++j) st_cg_u64(&s->key[j], key[j]);
+                    st_release_u32(&s->cs, w);
+                }
                 return 1;
             }
             cs = old;

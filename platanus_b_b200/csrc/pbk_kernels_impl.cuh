@@ -1176,7 +1176,7 @@ bucket_insert_wide_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const P
     auto round = [&](u64 first, u32 n_new) {
         u64 key[E][W], kw[E][W], gi[E];
         Slot<W> *sp[E];
-        u32 d[E], cs[E], act[E];                    // act: 0 none, 1 compare, 2 claim attempt, 3 locked (retry)
+        u32 d[E], cs[E], act[E], fold[E];           // act: 0 none, 1 compare, 2 claim attempt, 3 locked (retry); fold: see key_fold32
         bool live[E], rem[E];
         // deferred key of an earlier round (top of the warp's list)
         const u32 take = n_def < wsize ? n_def : wsize;
@@ -1213,7 +1213,7 @@ bucket_insert_wide_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const P
             u64 idx = __umul64hi(h, tb.cap) + d[e];
             if (idx >= tb.cap) idx -= tb.cap;
             sp[e] = tb.slots + idx;
-            cs[e] = 0;
+            cs[e] = 0; fold[e] = 0;
             if constexpr (W <= 3) {                   // sector-sized slot: key words and state word in ONE request
                 if (live[e]) {
                     u64 q[4];
@@ -1221,6 +1221,7 @@ bucket_insert_wide_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const P
 #pragma unroll
                     for (int w = 0; w < W; ++w) kw[e][w] = q[w];
                     cs[e] = (u32)q[W];
+                    fold[e] = (u32)(q[W] >> 32);
                 }
             } else {
                 if (live[e]) cs[e] = ld_cg_u32(&sp[e]->cs);
@@ -1251,7 +1252,7 @@ bucket_insert_wide_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const P
                         u64 q[4] = {0, 0, 0, 0};
 #pragma unroll
                         for (int w = 0; w < W; ++w) q[w] = key[e][w];
-                        q[W] = 1ull;
+                        q[W] = 1ull | ((u64)key_fold32<W>(key[e]) << 32);
                         st_cg_256(sp[e], q[0], q[1], q[2], q[3]);
                     } else {                         // key words first, then the count publishes them
 #pragma unroll
@@ -1268,7 +1269,10 @@ bucket_insert_wide_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const P
                 bool eq = true;
 #pragma unroll
                 for (int w = 0; w < W; ++w) eq &= (kw[e][w] == key[e][w]);
+                bool torn = false;                   // W <= 3: the words read do not fold to what the state word says -> look again
+                if constexpr (W <= 3) torn = !eq && key_fold32<W>(kw[e]) != fold[e];
                 if (eq) red_add_u32(&sp[e]->cs, 1u);
+                else if (torn) m = d[e] | (rem[e] ? PASSBW_REMOTE : 0u);
                 else if (d[e] + 1 >= (u32)MAX_PROBE) spill_key<W>(key[e], ctr, ovf, ovf_cap);
                 else m = (d[e] + 1) | (rem[e] ? PASSBW_REMOTE : 0u);
             }

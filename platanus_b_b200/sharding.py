@@ -181,17 +181,33 @@ class KeyPull:
     against the library's stream on the device) -> insert."""
 
     def __init__(self, kc, world: int, rank: int, max_windows: int, device=None, group=None):
+        """Collective: every rank calls it.  The collectives inside are issued in the same order whether or not a local step
+        fails, and `self.ok` is the AND over all ranks -- so a box that does not allow CUDA IPC between its processes makes
+        every rank see ok == False (and fall back to another exchange form) instead of hanging some of them."""
         self.kc, self.world, self.rank, self.device, self.group = kc, world, rank, device, group
-        self.lay = kc.keyx_pull_setup(max_windows_any_rank(max_windows, device=device, group=group))
-        mine = torch.frombuffer(bytearray(kc.keyx_pull_handle()), dtype=torch.uint8).to(device)
+        self.error = ""
+        max_w = max_windows_any_rank(max_windows, device=device, group=group)
+        handle = bytes(kc.KEYX_HANDLE_BYTES)
+        try:
+            self.lay = kc.keyx_pull_setup(max_w)
+            handle = kc.keyx_pull_handle()
+        except Exception as e:                       # noqa: BLE001 -- reported through self.error, agreed on below
+            self.error = str(e)
+        mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(device)
         handles = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(handles, mine, group=group)
-        for r in range(world):
-            if r != rank:
-                kc.keyx_pull_connect_ipc(r, bytes(handles[r].cpu().numpy().tobytes()))
+        if not self.error:
+            try:
+                for r in range(world):
+                    if r != rank:
+                        kc.keyx_pull_connect_ipc(r, bytes(handles[r].cpu().numpy().tobytes()))
+            except Exception as e:                   # noqa: BLE001
+                self.error = str(e)
+        flag = torch.tensor([0 if self.error else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)     # also the barrier: every store is mapped before anybody reads
+        self.ok = bool(int(flag.item()))
         self._token = torch.zeros(1, dtype=torch.int32, device=device)
         self.record_bufs: dict = {}
-        dist.barrier(group=group)                    # every rank has mapped every store before anybody starts reading
 
     def step(self, partition, sync, caller_stream=None) -> int:
         """partition() runs pbk_keyx_pull_partition* for this rank's batch.  Returns the bytes this rank's peers read from it."""

@@ -2,7 +2,9 @@
 """Dry run of bench.py's control flow in the GPU-less container -- a check of the SCRIPT, not a measurement: the C ABI
 compiled for the host (tests/cpu_emul), gloo instead of NCCL, torch.cuda stubbed out, the clock sampler replaced.  Every
 number it prints is meaningless; what matters is that each flow (N = 1; N = 2 with the record exchange, the key exchange,
-the device-ordered key exchange + --write-outputs) runs to its JSON line with every contract key.
+the device-ordered key exchange + --write-outputs) runs to its JSON line with every contract key.  (The default exchange at N > 1,
+--exchange pull, maps the peers' device memory through CUDA IPC and cannot be dry-run between host processes: its logic is covered
+in-process by tests/test_zz_keyx_gpu.py against the emulated ABI, and on real GPUs by tests/sharded_check.py.)
 
     python scripts/bench_dry_run.py [--scale 0.004] [--flows n1,records,keys,keys_async]"""
 import argparse
@@ -15,7 +17,7 @@ import torch
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-FLOWS = {"n1": (1, []), "records": (2, []), "keys": (2, ["--exchange", "keys", "--keyx-chunks", "3"]),
+FLOWS = {"n1": (1, []), "records": (2, ["--exchange", "records"]), "keys": (2, ["--exchange", "keys", "--keyx-chunks", "3"]),
          "keys_async": (2, ["--exchange", "keys", "--keyx-async"])}
 
 

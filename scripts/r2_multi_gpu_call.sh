@@ -19,6 +19,7 @@ for form in $FORMS; do
     keys_async) extra="--exchange keys --keyx-async --keyx-chunks 4" ;;
     keys_async2) extra="--exchange keys --keyx-async --keyx-chunks 2" ;;
     keys_async8) extra="--exchange keys --keyx-async --keyx-chunks 8" ;;
+    pull)       extra="--exchange pull" ;;
   esac
   port=$((port+1))
   timeout 600 $TR --master-port $port bench.py --gpus $N --steps 5 --warmup 3 --workload $wl --no-cpu-baseline $extra \

@@ -169,6 +169,53 @@ def test_against_the_reference_binary_on_the_box(oracle, k, repeat, tmp_path):
         assert t.reachable and t.index_size == ref.table.index_size
 
 
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "platanus_b")
+
+
+def _compare_with_reference_run(O, rs, k, repeat, tmp_path, mem_gb, counter_kwargs=None):
+    """the unmodified reference program and the GPU path on the same FASTQ files: .tsv bytes, auto cutoff, averages as printed,
+    .bin header and the sorted (key, count) dump of everything >= cutoff"""
+    files = synth.write_fastq(rs, str(tmp_path / "r_1.fq"), str(tmp_path / "r_2.fq"))
+    ref = O.run_reference(files, k, str(tmp_path), threads=os.cpu_count() or 1, mem_gb=mem_gb, repeat=repeat)
+    assert ref.returncode == 0, ref.stderr[-2000:]
+    b, o = rs.flat()
+    with KmerCounter(k, **(counter_kwargs or {})) as kc:
+        dh = kc.make_kmer_read_distribution(b, o, mem_gb * 10 ** 9)
+        cutoff = kc.coverage_cutoff(0, repeat)
+        assert cutoff == ref.cutoff
+        tsv = str(tmp_path / "g.tsv")
+        kc.output_occurrence_distribution(tsv)
+        assert open(tsv).read() == ref.tsv
+        assert "%g" % kc.calc_length_distribution_average() == ref.ave_read_len
+        keys, counts = kc.sorted_key_from_kmer_file(cutoff)
+        rk, rc = ref.table.sorted_dump()
+        assert len(rc) > 0 and np.array_equal(keys, rk) and np.array_equal(counts, rc)
+        if keys.shape[1] > 1:                                         # no key twice (a torn slot read would split a key's count)
+            assert not np.any(np.all(keys[1:] == keys[:-1], axis=1))
+        assert dh == ref.table.index_size + 1 or O.load_size(len(rc)) > dh
+        return kc.n_instances, len(rc)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="reference binary not built")
+@pytest.mark.parametrize("k", [32, 75])
+def test_full_size_c1_against_the_reference_binary(oracle, k, tmp_path):
+    """BASELINE config 1 at FULL size (4.6 Mb, 2x150 bp, 100x: 364 M / 233 M k-mer instances) against the unmodified reference
+    on the box's host cores with its default -m 16 -- the two k of the target (one-word and three-word keys)."""
+    rs = synth.make_reads(synth.config("C1"))
+    inst, kept = _compare_with_reference_run(oracle, rs, k, False, tmp_path, 16)
+    assert inst > 200_000_000 and 0.9 * 4_600_000 < kept < 1.1 * 4_600_000
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="reference binary not built")
+@pytest.mark.parametrize("name,scale", [("C3", 0.1), ("C5", 0.1)])
+def test_tenth_scale_c3_c5_against_the_reference_binary(oracle, name, scale, tmp_path):
+    """BASELINE configs 3 (high GC, 2x250 bp, 300x, 1 % errors: mostly singletons) and 5 (-repeat, 7 operon copies at 1000x: a few
+    thousand k-mers with ~5 000 occurrences each -- same-address traffic in Pass B) at a tenth of their genome sizes."""
+    spec = synth.config(name, scale=scale)
+    rs = synth.make_reads(spec)
+    _compare_with_reference_run(oracle, rs, spec.k, spec.repeat_mode, tmp_path, 4)
+
+
 def test_c1_full_size_properties():
     """BASELINE config 1 at full size (4.6 Mb, 2x150 bp, 100x): too big for the oracle in a test, so
     check what must hold at any size."""
