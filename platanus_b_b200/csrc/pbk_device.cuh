@@ -19,6 +19,7 @@
 #pragma once
 
 #include <cstdint>
+#include <cstring>
 #ifndef PBK_CPU_EMUL
 #include <cuda_runtime.h>
 #endif
@@ -187,6 +188,33 @@ __device__ __forceinline__ void prefetch_keep(const void *p)
 {
     asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(p));
 }
+// ---- TMA 1-D bulk copy global -> shared memory, completion on an mbarrier (cp.async.bulk, SASS UBLKCP): one elected thread
+// moves a whole tile of the bucket store; the consuming threads never hold the keys' global loads in flight themselves.
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+// src and dst 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
 // read-once / write-once data (the bucket store): evict-first, so it does not push table lines out of L2
 __device__ __forceinline__ u64 ld_stream_u64(const u64 *p) { return __ldcs(p); }
 __device__ __forceinline__ ulonglong2 ld_stream_u64x2(const u64 *p) { return __ldcs(reinterpret_cast<const ulonglong2 *>(p)); }
@@ -212,6 +240,11 @@ inline u64 l2_keep_policy() { return 0; }
 inline u64 atom_add_keep_u64(u64 *p, u64 v, u64) { u64 o = *p; *p += v; return o; }
 inline void red_add_keep_u64(u64 *p, u64 v, u64) { *p += v; }
 inline void prefetch_keep(const void *) {}
+inline void mbar_init(u64 *, u32) {}
+inline void mbar_fence_init() {}
+inline void mbar_expect_tx(u64 *, u32) {}
+inline void bulk_copy_g2s(void *dst, const void *src, u32 bytes, u64 *) { memcpy(dst, src, bytes); }   // completes at once
+inline void mbar_wait(u64 *, u32) {}
 inline u64 ld_stream_u64(const u64 *p) { return *p; }
 struct ulonglong2 { u64 x, y; };
 inline ulonglong2 make_ulonglong2(u64 x, u64 y) { return ulonglong2{x, y}; }

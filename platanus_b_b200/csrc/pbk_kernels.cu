@@ -145,7 +145,7 @@ PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words, siz
     threads = std::min<u64>(512, threads / 32 * 32);
     p.threads = (int)std::max<u64>(64, threads);
     p.smem = (size_t)p.n_buckets * p.bin_cap * 8 * words;
-    p.seg_cap = windows_ub / P + windows_ub / (P * 16) + 8192;
+    p.seg_cap = (windows_ub / P + windows_ub / (P * 16) + 8192 + 1) & ~1ull;    // even: segment byte offsets stay 16-byte aligned for any W
     return p;
 }
 
@@ -271,10 +271,22 @@ void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *counts, v
         return;
     }
     const int grid = (int)std::min<u64>(tiles, (u64)sm_count * 2);
+    // keys staged through TMA bulk copies (two tiles in shared memory) unless PBK_WIDE_STAGED=0; needs even seg_cap for odd W
+    static const bool staged_on = !(getenv("PBK_WIDE_STAGED") && atoi(getenv("PBK_WIDE_STAGED")) == 0);
+    const size_t stage_bytes = 2 * (size_t)PASSB_TILE_KEYS * table.words * 8;
+    const bool staged = staged_on && stage_bytes <= 110 * 1024 && ((seg_cap * table.words) % 2 == 0);
     switch (table.words) {
-#define PBK_CASE_W(Wv) case Wv: bucket_insert_wide_kernel<Wv><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, b_first,   \
-            b_end, (u64 *)d_desc, Table<Wv>(table.slots, table.cap), Table<Wv>(remote.slots, remote.cap), shard.n_shards,    \
-            shard.rank, ctr, overflow_keys, overflow_cap); break;
+#define PBK_CASE_W(Wv) case Wv:                                                                                                   \
+        if (staged) {                                                                                                          \
+            cudaFuncSetAttribute(bucket_insert_wide_kernel<Wv, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);   \
+            bucket_insert_wide_kernel<Wv, true><<<grid, PASSB_THREADS, stage_bytes, st>>>(bkt_keys, seg_cap, d_bk, b_first,       \
+                b_end, (u64 *)d_desc, Table<Wv>(table.slots, table.cap), Table<Wv>(remote.slots, remote.cap), shard.n_shards,  \
+                shard.rank, ctr, overflow_keys, overflow_cap);                                                                 \
+        } else {                                                                                                               \
+            bucket_insert_wide_kernel<Wv, false><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, b_first,               \
+                b_end, (u64 *)d_desc, Table<Wv>(table.slots, table.cap), Table<Wv>(remote.slots, remote.cap), shard.n_shards,  \
+                shard.rank, ctr, overflow_keys, overflow_cap);                                                                 \
+        } break;
     PBK_CASE_W(2) PBK_CASE_W(3) PBK_CASE_W(4) PBK_CASE_W(5) PBK_CASE_W(6) PBK_CASE_W(7) PBK_CASE_W(8)
 #undef PBK_CASE_W
     default: break;

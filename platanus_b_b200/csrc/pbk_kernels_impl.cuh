@@ -1150,7 +1150,13 @@ bucket_insert_gather_kernel(const __grid_constant__ KeyxSources srcs, u64 seg_ca
 template <int W> struct PASSBW_KPT { static constexpr int value = W <= 3 ? 4 : 2; };
 constexpr u32 PASSBW_REMOTE = 1u << 9;               // deferred-entry flag above the probe count (MAX_PROBE < 256)
 
-template <int W>
+// STAGED: the keys of a tile do not come through the threads' own global loads but through TMA bulk copies (cp.async.bulk ->
+// shared memory, completion on an mbarrier): one thread issues the copy of the NEXT tile (one contiguous piece of the bucket
+// store: tile_keys x 8 W bytes) while the CTA inserts the current one, so the only global-memory latency left on a round's
+// critical path is the table slot itself, and the bucket store is read in whole 128-byte lines instead of 8-byte loads with a
+// stride of 8 W bytes.  Needs 2 x tile_keys x 8 W bytes of dynamic shared memory (96 KB at W = 3) and segments whose byte
+// offsets are 16-byte aligned (plan_partition keeps seg_cap even).
+template <int W, bool STAGED>
 __global__ void __launch_bounds__(PASSB_THREADS, 2)
 bucket_insert_wide_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const PassBBucket *__restrict__ bk,
                           u32 b_first, u32 b_end, u64 *ticket, Table<W> table, Table<W> remote, u32 n_shards, u32 rank,
@@ -1158,6 +1164,8 @@ bucket_insert_wide_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const P
 {
     constexpr int KPT = PASSBW_KPT<W>::value, ROUNDS = PASSB_KPT / KPT, E = KPT + 1;
     constexpr int DEF_CAP = 32 * (KPT + 2);
+    PBK_DYN_SMEM(u64, s_stage);                      // STAGED: two tiles of keys
+    __shared__ u64 s_mbar[2];
     __shared__ u64 s_ticket[2];
     __shared__ u64 s_def_i[PASSB_THREADS / 32][DEF_CAP];
     __shared__ uint16_t s_def_m[PASSB_THREADS / 32][DEF_CAP];
@@ -1172,8 +1180,9 @@ bucket_insert_wide_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const P
     __syncthreads();
     const u64 n_tiles = bk[nb].tile_start;
 
-    // one round: `n_new` keys starting at key index `first` (0 = only deferred keys)
-    auto round = [&](u64 first, u32 n_new) {
+    // one round: `n_new` keys starting at key index `first` (0 = only deferred keys); STAGED: the same keys sit in shared
+    // memory at `staged`
+    auto round = [&](u64 first, u32 n_new, const u64 *staged) {
         u64 key[E][W], kw[E][W], gi[E];
         Slot<W> *sp[E];
         u32 d[E], cs[E], act[E], fold[E];           // act: 0 none, 1 compare, 2 claim attempt, 3 locked (retry); fold: see key_fold32
@@ -1196,7 +1205,11 @@ bucket_insert_wide_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const P
         }
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            if constexpr (W == 2) {                   // 16-byte entries: one vector load
+            if (STAGED && e < KPT && staged != nullptr) {          // this round's new keys: already in shared memory
+                const u32 i = (u32)e * nthreads + tid;
+#pragma unroll
+                for (int w = 0; w < W; ++w) key[e][w] = live[e] ? staged[(u64)i * W + w] : 0;
+            } else if constexpr (W == 2) {            // 16-byte entries: one vector load
                 ulonglong2 v = make_ulonglong2(0, 0);
                 if (live[e]) v = ld_stream_u64x2(bkt_keys + gi[e] * 2);
                 key[e][0] = v.x; key[e][1] = v.y;
@@ -1287,31 +1300,57 @@ bucket_insert_wide_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const P
         }
     };
 
+    // STAGED: thread 0 starts the bulk copy of tile `tt` into stage buffer `buf`
+    u32 lb_issue = 0;
+    auto issue_tile = [&](u64 tt, int buf) {
+        while (bk[lb_issue + 1].tile_start <= tt) ++lb_issue;
+        const u64 jj = tt - bk[lb_issue].tile_start;
+        const u64 first_i = (u64)(b_first + lb_issue) * seg_cap + jj * tile_keys;
+        const u64 n_i = min((u64)tile_keys, bk[lb_issue].n_keys - jj * tile_keys);
+        const u32 bytes = (u32)((n_i * W * 8 + 15) & ~15ull);
+        mbar_expect_tx(&s_mbar[buf], bytes);
+        bulk_copy_g2s(s_stage + (size_t)buf * tile_keys * W, bkt_keys + first_i * W, bytes, &s_mbar[buf]);
+    };
     int par = 0;
+    u32 phase[2] = {0, 0};
     u64 t = s_ticket[0];
+    if constexpr (STAGED) {
+        if (tid == 0) { mbar_init(&s_mbar[0], 1); mbar_init(&s_mbar[1], 1); mbar_fence_init(); }
+        __syncthreads();
+        if (tid == 0 && t < n_tiles) issue_tile(t, 0);
+    }
     while (t < n_tiles) {
         while (bk[lb + 1].tile_start <= t) ++lb;
         const u64 j = t - bk[lb].tile_start, n = bk[lb].n_keys;
         const u64 nt = bk[lb + 1].tile_start - bk[lb].tile_start;
         const u64 t_next = s_ticket[par ^ 1];
-        __syncthreads();
-        if (tid == 0) s_ticket[par] = atomicAdd(ticket, 1ull);
+        __syncthreads();                              // (also: everybody is done with stage buffer par ^ 1)
+        if (tid == 0) {
+            s_ticket[par] = atomicAdd(ticket, 1ull);
+            if (STAGED && t_next < n_tiles) issue_tile(t_next, par ^ 1);
+        }
         if (bk[lb].pf_base) passb_prefetch(bk[lb].pf_base, bk[lb].pf_lines, j, nt, tid, nthreads);
         if (bk[lb].pf_base2) passb_prefetch(bk[lb].pf_base2, bk[lb].pf_lines2, j, nt, tid, nthreads);
         const u64 first = (u64)(b_first + lb) * seg_cap + j * tile_keys;
         const u64 left = n - j * tile_keys;
+        const u64 *stage = nullptr;
+        if constexpr (STAGED) {
+            mbar_wait(&s_mbar[par], phase[par]);      // this tile's keys have landed
+            phase[par] ^= 1u;
+            stage = s_stage + (size_t)par * tile_keys * W;
+        }
 #pragma unroll 1
         for (u64 o = 0; o < left && o < tile_keys; o += round_keys) {
 #pragma unroll 1
-            while (n_def > wsize) round(0, 0u);      // a round may only start with at most one batch listed
-            round(first + o, (u32)min((u64)round_keys, left - o));
+            while (n_def > wsize) round(0, 0u, nullptr);      // a round may only start with at most one batch listed
+            round(first + o, (u32)min((u64)round_keys, left - o), STAGED ? stage + o * W : nullptr);
         }
         __syncthreads();
         t = t_next;
         par ^= 1;
     }
 #pragma unroll 1
-    while (n_def) round(0, 0u);                      // nobody ever waits, so the list drains
+    while (n_def) round(0, 0u, nullptr);             // nobody ever waits, so the list drains
     newk = warp_sum_u32(newk);
     newr = warp_sum_u32(newr);
     if ((tid & 31) == 0) {

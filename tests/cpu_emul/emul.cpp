@@ -67,7 +67,7 @@ static int run(const uint8_t *bases, const u64 *off, u64 n_reads, int k, int enc
                 if (n_shards > 1) bucket_insert_compact_kernel<1>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF, 1u);
                 else bucket_insert_compact_kernel<0>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF, 0u);
             } else if (k % 2) {            // odd k: the batched kernel, even k: the one-key-at-a-time form of the protocol
-                bucket_insert_wide_kernel<W>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF);
+                bucket_insert_wide_kernel<W, true>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF);
             } else {
                 bucket_insert_kernel<W>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF);
             }
