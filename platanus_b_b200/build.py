@@ -8,12 +8,14 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT_DIR = os.path.join(HERE, "_lib")
+# PBK_LIB_TAG / PBK_EXTRA_CFLAGS: tuning builds only (scripts/tune_variants.sh) -- a second library next to the product one
+_TAG = os.environ.get("PBK_LIB_TAG", "")
+OUT_DIR = os.path.join(HERE, "_lib" + ("_" + _TAG if _TAG else ""))
 LIB = os.path.join(OUT_DIR, "libpbk.so")
 
 NVCC = os.environ.get("PBK_NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CFLAGS = (["-DPBK_EXPERIMENT"] if os.environ.get("PBK_EXPERIMENT") else []) + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
+CFLAGS = (["-DPBK_EXPERIMENT"] if os.environ.get("PBK_EXPERIMENT") else []) + os.environ.get("PBK_EXTRA_CFLAGS", "").split() + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
 UNITS = ["pbk_kernels.cu", "pbk_api.cu", "pbk_host.cpp"]
 HEADERS = ["pbk_device.cuh", "pbk_kernels.cuh", "pbk_kernels_impl.cuh", os.path.join("..", "..", "include", "pbk.h")]
 

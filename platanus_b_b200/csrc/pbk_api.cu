@@ -113,7 +113,11 @@ namespace {
 const bool g_debug = getenv("PBK_DEBUG") != nullptr;
 #define DBG(...) do { if (g_debug) { fprintf(stderr, "[pbk] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
 
-double max_load(const pbk_ctx *c) { return c->W == 1 ? MAX_LOAD_COMPACT : MAX_LOAD; }
+double max_load(const pbk_ctx *c)
+{
+    static const double wide = getenv("PBK_MAX_LOAD_WIDE") ? std::min(0.9, std::max(0.2, atof(getenv("PBK_MAX_LOAD_WIDE")))) : MAX_LOAD;
+    return c->W == 1 ? MAX_LOAD_COMPACT : wide;
+}
 
 int fail(pbk_ctx *c, int code, const char *fmt, ...)
 {

@@ -140,7 +140,7 @@ PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words, siz
     p.bin_cap = (u32)(entries / P);
     // one tile = threads * win window ends (win = PART_WIN1, 16, 8 for 1, 2, >= 3 key words), ~85 % of them valid; keep the
     // mean bin fill at 60 % of the bin
-    const double win = words == 1 ? (double)PART_WIN1 : words == 2 ? 16.0 : 8.0;
+    const double win = words == 1 ? (double)PART_WIN1 : words == 2 ? 16.0 : (double)PBK_PART_WIN3;
     u64 threads = (u64)(p.bin_cap * 0.6 * (double)P / (win * 0.85));
     threads = std::min<u64>(512, threads / 32 * 32);
     p.threads = (int)std::max<u64>(64, threads);
@@ -168,7 +168,7 @@ PartitionPlan plan_partition_keyx(u32 n_dest, u64 max_windows_any_rank, int word
     threads = std::min<u64>(512, threads / 32 * 32);
     p.threads = (int)std::max<u64>(64, threads);
     p.smem = (size_t)p.n_buckets * p.bin_cap * 8 * words;
-    p.seg_cap = max_windows_any_rank / P + max_windows_any_rank / (P * 16) + 8192;
+    p.seg_cap = (max_windows_any_rank / P + max_windows_any_rank / (P * 16) + 8192 + 1) & ~1ull;   // even: 16-byte aligned segments
     return p;
 }
 
@@ -187,7 +187,7 @@ void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64
                       u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st, u32 keyx_dest)
 {
     if (word_end <= word_begin) return;
-    const u64 subs = words == 1 ? 32 / PART_WIN1 : words == 2 ? 2 : 4;       // 32 / PART_WIN<W>: work items per stream word
+    const u64 subs = words == 1 ? 32 / PART_WIN1 : words == 2 ? 2 : 32 / PBK_PART_WIN3;       // 32 / PART_WIN<W>: work items per stream word
     const u64 tiles = ((word_end - word_begin) * subs + plan.threads - 1) / plan.threads;
     const int ctas = std::max(1, std::min(8, (int)((220 * 1024) / (plan.smem + 7 * 1024))));     // resident CTAs per SM
     const int grid = (int)std::min<u64>(tiles, (u64)sm_count * ctas);
@@ -200,6 +200,17 @@ void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64
     PBK_DISPATCH_W(words,
         (partition_launch_w<W, false>(stream, nflag, rflag, word_begin, word_end, k, plan, bkt_keys, bkt_cursor, ctr,
                                       overflow_keys, overflow_cap, grid, 1u, st)));
+}
+
+// one-word Pass B: keys staged through per-warp TMA bulk copies unless PBK_PASSB_STAGED=0 (needs even seg_cap: 16-byte aligned copies)
+static bool passb1_staged(u64 seg_cap)
+{
+    static const bool on = !(getenv("PBK_PASSB_STAGED") && atoi(getenv("PBK_PASSB_STAGED")) == 0);
+    return on && (seg_cap % 2 == 0);
+}
+template <typename K> static void passb1_staged_attr(K kernel)
+{
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PASSB1_RING_BYTES);
 }
 
 size_t passb_desc_bytes(u32 n_buckets) { return 16 + (size_t)(n_buckets + 1) * sizeof(PassBBucket); }
@@ -248,6 +259,20 @@ void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *counts, v
         const int ctas = getenv("PBK_PASSB_CTAS") ? atoi(getenv("PBK_PASSB_CTAS")) : 3;
         const u32 opts = getenv("PBK_PASSB_HINT") ? (u32)atoi(getenv("PBK_PASSB_HINT")) : 1u;
         const int grid = (int)std::min<u64>(tiles, (u64)sm_count * ctas);
+        if (passb1_staged(seg_cap)) {
+            if (shard.n_shards > 1) {
+                passb1_staged_attr(bucket_insert_compact_staged_kernel<1>);
+                bucket_insert_compact_staged_kernel<1><<<grid, PASSB_THREADS, PASSB1_RING_BYTES, st>>>(bkt_keys, seg_cap, d_bk, b_first, b_end,
+                    (u64 *)d_desc, Table<1>(table.slots, table.cap), Table<1>(remote.slots, remote.cap), shard.n_shards,
+                    shard.rank, ctr, overflow_keys, overflow_cap, opts);
+            } else {
+                passb1_staged_attr(bucket_insert_compact_staged_kernel<0>);
+                bucket_insert_compact_staged_kernel<0><<<grid, PASSB_THREADS, PASSB1_RING_BYTES, st>>>(bkt_keys, seg_cap, d_bk, b_first, b_end,
+                    (u64 *)d_desc, Table<1>(table.slots, table.cap), Table<1>(remote.slots, remote.cap), 1, 0, ctr,
+                    overflow_keys, overflow_cap, opts);
+            }
+            return;
+        }
         if (shard.n_shards > 1)
             bucket_insert_compact_kernel<1><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, b_first, b_end,
                 (u64 *)d_desc, Table<1>(table.slots, table.cap), Table<1>(remote.slots, remote.cap), shard.n_shards,
@@ -270,11 +295,11 @@ void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *counts, v
         }
         return;
     }
-    const int grid = (int)std::min<u64>(tiles, (u64)sm_count * 2);
+    const int grid = (int)std::min<u64>(tiles, (u64)sm_count * PBK_PASSBW_MINCTAS);
     // keys staged through TMA bulk copies (two tiles in shared memory) unless PBK_WIDE_STAGED=0; needs even seg_cap for odd W
     static const bool staged_on = !(getenv("PBK_WIDE_STAGED") && atoi(getenv("PBK_WIDE_STAGED")) == 0);
     const size_t stage_bytes = 2 * (size_t)PASSB_TILE_KEYS * table.words * 8;
-    const bool staged = staged_on && stage_bytes <= 110 * 1024 && ((seg_cap * table.words) % 2 == 0);
+    const bool staged = staged_on && stage_bytes * PBK_PASSBW_MINCTAS <= 200 * 1024 && ((seg_cap * table.words) % 2 == 0);
     switch (table.words) {
 #define PBK_CASE_W(Wv) case Wv:                                                                                                   \
         if (staged) {                                                                                                          \
@@ -323,6 +348,12 @@ void launch_bucket_insert_gathered(const KeyxSources &srcs, u64 seg_cap, const u
     const int ctas = getenv("PBK_PASSB_CTAS") ? atoi(getenv("PBK_PASSB_CTAS")) : 3;
     const u32 opts = (getenv("PBK_PASSB_HINT") ? ((u32)atoi(getenv("PBK_PASSB_HINT")) & 0xFFu) : 1u) | (n_src << 8) | (n_regions << 16);
     const int grid = (int)std::min<u64>(tiles, (u64)sm_count * ctas);
+    if (passb1_staged(seg_cap)) {
+        passb1_staged_attr(bucket_insert_gather_staged_kernel);
+        bucket_insert_gather_staged_kernel<<<grid, PASSB_THREADS, PASSB1_RING_BYTES, st>>>(srcs, seg_cap, d_bk, d_first, d_end, (u64 *)d_desc,
+            Table<1>(table.slots, table.cap), ctr, overflow_keys, overflow_cap, opts);
+        return;
+    }
     bucket_insert_gather_kernel<<<grid, PASSB_THREADS, 0, st>>>(srcs, seg_cap, d_bk, d_first, d_end, (u64 *)d_desc,
         Table<1>(table.slots, table.cap), ctr, overflow_keys, overflow_cap, opts);
 }
@@ -340,6 +371,12 @@ void launch_bucket_insert_gathered_chained(const KeyxSources &srcs, u64 seg_cap,
     const PassBBucket *d_bk = (const PassBBucket *)((const char *)d_desc + 16);
     const int ctas = getenv("PBK_PASSB_CTAS") ? atoi(getenv("PBK_PASSB_CTAS")) : 3;
     const u32 opts = (getenv("PBK_PASSB_HINT") ? ((u32)atoi(getenv("PBK_PASSB_HINT")) & 0xFFu) : 1u) | (n_src << 8) | (n_regions << 16);
+    if (passb1_staged(seg_cap)) {
+        passb1_staged_attr(bucket_insert_gather_staged_kernel);
+        bucket_insert_gather_staged_kernel<<<sm_count * ctas, PASSB_THREADS, PASSB1_RING_BYTES, st>>>(srcs, seg_cap, d_bk, 0, n_desc, (u64 *)d_desc,
+            Table<1>(table.slots, table.cap), ctr, overflow_keys, overflow_cap, opts);
+        return;
+    }
     bucket_insert_gather_kernel<<<sm_count * ctas, PASSB_THREADS, 0, st>>>(srcs, seg_cap, d_bk, 0, n_desc, (u64 *)d_desc,
         Table<1>(table.slots, table.cap), ctr, overflow_keys, overflow_cap, opts);    // CTAs that find no tile left leave at once
 }
@@ -363,6 +400,19 @@ void launch_bucket_insert_chained(const u64 *bkt_keys, u64 seg_cap, const void *
     const u32 opts = getenv("PBK_PASSB_HINT") ? (u32)atoi(getenv("PBK_PASSB_HINT")) : 1u;
     if (getenv("PBK_PASSB_CTAS")) ctas_per_sm = atoi(getenv("PBK_PASSB_CTAS"));
     const int grid = sm_count * ctas_per_sm;                    // CTAs that find no tile left leave at once
+    if (passb1_staged(seg_cap)) {
+        if (shard.n_shards > 1) {
+            passb1_staged_attr(bucket_insert_compact_staged_kernel<1>);
+            bucket_insert_compact_staged_kernel<1><<<grid, PASSB_THREADS, PASSB1_RING_BYTES, st>>>(bkt_keys, seg_cap, d_bk, 0, n_buckets, (u64 *)d_desc,
+                Table<1>(table.slots, table.cap), Table<1>(remote.slots, remote.cap), shard.n_shards, shard.rank, ctr,
+                overflow_keys, overflow_cap, opts);
+        } else {
+            passb1_staged_attr(bucket_insert_compact_staged_kernel<0>);
+            bucket_insert_compact_staged_kernel<0><<<grid, PASSB_THREADS, PASSB1_RING_BYTES, st>>>(bkt_keys, seg_cap, d_bk, 0, n_buckets, (u64 *)d_desc,
+                Table<1>(table.slots, table.cap), Table<1>(remote.slots, remote.cap), 1, 0, ctr, overflow_keys, overflow_cap, opts);
+        }
+        return;
+    }
     if (shard.n_shards > 1)
         bucket_insert_compact_kernel<1><<<grid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, 0, n_buckets, (u64 *)d_desc,
             Table<1>(table.slots, table.cap), Table<1>(remote.slots, remote.cap), shard.n_shards, shard.rank, ctr,

@@ -510,7 +510,10 @@ __device__ __forceinline__ void bucket_append_direct(const u64 *key, u32 b, u64 
 }
 
 // windows of one stream word a Pass A thread handles per tile
-template <int W> struct PART_WIN { static constexpr int value = W == 1 ? PART_WIN1 : (W == 2 ? 16 : 8); };
+#ifndef PBK_PART_WIN3
+#define PBK_PART_WIN3 8
+#endif
+template <int W> struct PART_WIN { static constexpr int value = W == 1 ? PART_WIN1 : (W == 2 ? 16 : PBK_PART_WIN3); };
 
 // OR of x << j for j in [0, w), 0 <= w <= 32 (doubling: at most five shift/or steps)
 __device__ __forceinline__ u64 smear_up(u64 x, int w)
@@ -951,7 +954,9 @@ __device__ __forceinline__ u32 passb1_classify(const Table<1> &tb, bool is_remot
     return (d + 1) | (is_remote ? PASSB1_REMOTE : 0u);
 }
 
-template <bool SHARDED, bool FULL>
+// `src` / `n_valid`: this WARP's keys of the round (KPT x warp-size consecutive entries of the bucket store, lane-strided);
+// STAGED: they were brought into shared memory by a TMA bulk copy and `src` points there.
+template <bool SHARDED, bool FULL, bool STAGED = false>
 __device__ __forceinline__ void passb1_round(const u64 *__restrict__ src, u32 n_valid, u32 tid, u32 nthreads, u32 lane,
                                              const Table<1> &table, const Table<1> &remote, u32 n_shards, u32 rank,
                                              u64 keep, u32 &newk, u32 &newr, Counters *ctr, u64 *ovf, u64 ovf_cap,
@@ -971,8 +976,8 @@ __device__ __forceinline__ void passb1_round(const u64 *__restrict__ src, u32 n_
     u32 valid = 0, rem = 0;
 #pragma unroll
     for (int q = 0; q < PASSB1_KPT; ++q) {
-        const u32 i = (u32)q * nthreads + tid;
-        if (FULL || i < n_valid) { h[q] = ld_stream_u64(src + i); valid |= 1u << q; }
+        const u32 i = (u32)q * wsize + lane;
+        if (FULL || i < n_valid) { h[q] = STAGED ? src[i] : ld_stream_u64(src + i); valid |= 1u << q; }
         else h[q] = 0;
     }
 #ifdef PBK_EXPERIMENT
@@ -1040,7 +1045,14 @@ __device__ __forceinline__ void passb1_round(const u64 *__restrict__ src, u32 n_
 // all-to-all receive buffer, laid out [source rank][region][seg_cap]; the descriptors are in region-major order
 // (descriptor i = region i / G, source i % G, with G = opts bits 8-15 and the regions per source in bits 16-31), so
 // all sources' keys of one table region are inserted while that region is L2-resident.
-template <int MODE>
+// STAGED: a warp's keys of a round (KPT x 32 entries = 2 KB, contiguous in the bucket store -- local HBM, or a peer's over
+// NVLink in the key exchange) arrive through a TMA bulk copy (cp.async.bulk -> shared memory, completion on the warp's own
+// mbarrier) that lane 0 issues ONE ROUND AHEAD, into the other half of the warp's two-stage ring: the threads never have the
+// key loads in flight themselves, and a remote store is read in 2 KB bursts instead of 256-byte warp requests.  Warps stay
+// independent (no CTA barrier per round).
+constexpr int PASSB1_WARP_KEYS = 32 * PASSB1_KPT;
+constexpr size_t PASSB1_RING_BYTES = (size_t)(PASSB_THREADS / 32) * 2 * PASSB1_WARP_KEYS * 8;     // 32 KB per CTA
+template <int MODE, bool STAGED>
 __device__ __forceinline__ void
 bucket_insert_compact_body(const u64 *__restrict__ bkt_hash, u64 seg_cap, const PassBBucket *__restrict__ bk,
                            u32 b_first, u32 b_end, u64 *ticket, const Table<1> &table, const Table<1> &remote, u32 n_shards,
@@ -1052,8 +1064,11 @@ bucket_insert_compact_body(const u64 *__restrict__ bkt_hash, u64 seg_cap, const 
     __shared__ u64 s_ticket[2];
     __shared__ u64 s_def_h[PASSB_THREADS / 32][PASSB1_DEF_CAP];
     __shared__ uint16_t s_def_m[PASSB_THREADS / 32][PASSB1_DEF_CAP];
+    PBK_DYN_SMEM(u64, s_ring);                       // STAGED: [warp][half][PASSB1_WARP_KEYS], PASSB1_RING_BYTES of dynamic shared memory
+    __shared__ u64 s_wbar[PASSB_THREADS / 32][2];
     const u32 nb = b_end - b_first, tid = threadIdx.x, nthreads = blockDim.x;
     const u32 lane = nthreads < 32u ? 0u : (tid & 31u), warp = nthreads < 32u ? 0u : (tid >> 5);
+    const u32 wsize = nthreads < 32u ? nthreads : 32u, warp_keys = wsize * PASSB1_KPT;
     u64 *def_h = s_def_h[warp];
     uint16_t *def_m = s_def_m[warp];
     u32 n_def = 0;
@@ -1066,44 +1081,76 @@ bucket_insert_compact_body(const u64 *__restrict__ bkt_hash, u64 seg_cap, const 
     u32 newk = 0, newr = 0, lb = 0;
     int par = 0;
     u64 t = s_ticket[0];
+    // where tile `tt` starts in the (local or peer) bucket store, and how many keys it has; `bb` = monotone bucket cursor
+    auto tile_src = [&](u64 tt, u32 &bb, u64 &n_in_tile) -> const u64 * {
+        while (bk[bb + 1].tile_start <= tt) ++bb;
+        const u64 jj = tt - bk[bb].tile_start;
+        n_in_tile = min((u64)tile_keys, bk[bb].n_keys - jj * tile_keys);
+        const u32 seg = b_first + bb;
+        if constexpr (MODE == 2) {                               // descriptor = (region seg / G, source seg % G)
+            const u32 G = (opts >> 8) & 0xFFu;
+            return srcs->keys[seg % G] + (u64)(seg / G) * seg_cap + jj * tile_keys;
+        } else {
+            return bkt_hash + (u64)seg * seg_cap + jj * tile_keys;
+        }
+    };
+    // STAGED: lane 0 starts the bulk copy of this warp's keys of round r of the tile at `base` into ring half `half`
+    int ring = 0;
+    u32 ring_phase = 0;                                       // bit h = parity the next wait on ring half h expects
+    auto issue = [&](const u64 *base, u64 n_in_tile, u32 r, int half) {
+        const u64 off = (u64)r * round_keys + (u64)warp * warp_keys;
+        if (off >= n_in_tile) return;                            // nothing for this warp in that round: no copy, no wait
+        const u32 cnt = (u32)min((u64)warp_keys, n_in_tile - off);
+        const u32 bytes = (cnt * 8u + 15u) & ~15u;
+        if (lane == 0) {
+            mbar_expect_tx(&s_wbar[warp][half], bytes);
+            bulk_copy_g2s(s_ring + (size_t)(warp * 2 + half) * PASSB1_WARP_KEYS, base + off, bytes, &s_wbar[warp][half]);
+        }
+    };
+    u32 lb_next = 0;
+    if constexpr (STAGED) {
+        if (lane == 0) { mbar_init(&s_wbar[warp][0], 1); mbar_init(&s_wbar[warp][1], 1); mbar_fence_init(); }
+        __syncwarp();
+        if (t < n_tiles) { u64 n0; const u64 *b0 = tile_src(t, lb_next, n0); issue(b0, n0, 0, 0); }
+    }
     while (t < n_tiles) {
-        while (bk[lb + 1].tile_start <= t) ++lb;
-        const u64 j = t - bk[lb].tile_start, n = bk[lb].n_keys;
+        u64 n_tile;
+        const u64 *src = tile_src(t, lb, n_tile);
+        const u64 j = t - bk[lb].tile_start;
         const u64 nt = bk[lb + 1].tile_start - bk[lb].tile_start;
         const u64 t_next = s_ticket[par ^ 1];                    // fetched one iteration ago
         __syncthreads();                                         // everyone has read both tickets
         if (tid == 0) s_ticket[par] = atomicAdd(ticket, 1ull);   // ticket for the tile after next
         if (bk[lb].pf_base) passb_prefetch(bk[lb].pf_base, bk[lb].pf_lines, j, nt, tid, nthreads);
         if (SHARDED && bk[lb].pf_base2) passb_prefetch(bk[lb].pf_base2, bk[lb].pf_lines2, j, nt, tid, nthreads);
-        const u32 seg = b_first + lb;
-        const u64 *src;
-        if constexpr (MODE == 2) {                               // descriptor = (region seg / G, source seg % G)
-            const u32 G = (opts >> 8) & 0xFFu;
-            src = srcs->keys[seg % G] + (u64)(seg / G) * seg_cap + j * tile_keys;
-        } else {
-            src = bkt_hash + (u64)seg * seg_cap + j * tile_keys;
-        }
-        const u64 left = n - j * tile_keys;                      // > 0 by construction of the tile numbering
-        if (left >= tile_keys) {
+        const u64 *src_next = nullptr;
+        u64 n_next = 0;
+        if (STAGED && t_next < n_tiles) src_next = tile_src(t_next, lb_next, n_next);
+        const u32 n_rounds = (u32)((n_tile + round_keys - 1) / round_keys);
 #pragma unroll 1
-            for (int r = 0; r < PASSB1_ROUNDS; ++r) {
-#pragma unroll 1
-                while (n_def > def_room)
-                    passb1_round<SHARDED, false>(bkt_hash, 0u, tid, nthreads, lane, table, remote, n_shards, rank, keep, newk, newr,
-                                                 ctr, ovf, ovf_cap, def_h, def_m, n_def, opts);
-                passb1_round<SHARDED, true>(src + (u64)r * round_keys, round_keys, tid, nthreads, lane, table, remote, n_shards,
-                                            rank, keep, newk, newr, ctr, ovf, ovf_cap, def_h, def_m, n_def, opts);
+        for (u32 r = 0; r < n_rounds; ++r) {
+            if constexpr (STAGED) {                              // the warp's next round -- of this tile or of the next -- goes out first
+                if (r + 1 < n_rounds) issue(src, n_tile, r + 1, ring ^ 1);
+                else if (src_next) issue(src_next, n_next, 0, ring ^ 1);
             }
-        } else {
 #pragma unroll 1
-            for (u64 o = 0; o < left; o += round_keys) {
-#pragma unroll 1
-                while (n_def > def_room)
-                    passb1_round<SHARDED, false>(bkt_hash, 0u, tid, nthreads, lane, table, remote, n_shards, rank, keep, newk, newr,
-                                                 ctr, ovf, ovf_cap, def_h, def_m, n_def, opts);
-                passb1_round<SHARDED, false>(src + o, (u32)min((u64)round_keys, left - o), tid, nthreads, lane, table, remote,
-                                             n_shards, rank, keep, newk, newr, ctr, ovf, ovf_cap, def_h, def_m, n_def, opts);
+            while (n_def > def_room)
+                passb1_round<SHARDED, false>(bkt_hash, 0u, tid, nthreads, lane, table, remote, n_shards, rank, keep, newk, newr,
+                                             ctr, ovf, ovf_cap, def_h, def_m, n_def, opts);
+            const u64 off = (u64)r * round_keys + (u64)warp * warp_keys;
+            const u32 cnt = off < n_tile ? (u32)min((u64)warp_keys, n_tile - off) : 0u;
+            const u64 *wsrc = src + off;
+            if constexpr (STAGED) {
+                if (cnt) { mbar_wait(&s_wbar[warp][ring], (ring_phase >> ring) & 1u); ring_phase ^= 1u << ring; }
+                wsrc = s_ring + (size_t)(warp * 2 + ring) * PASSB1_WARP_KEYS;
             }
+            if (cnt == warp_keys)
+                passb1_round<SHARDED, true, STAGED>(wsrc, cnt, tid, nthreads, lane, table, remote, n_shards, rank, keep, newk, newr,
+                                                    ctr, ovf, ovf_cap, def_h, def_m, n_def, opts);
+            else if (cnt)
+                passb1_round<SHARDED, false, STAGED>(wsrc, cnt, tid, nthreads, lane, table, remote, n_shards, rank, keep, newk, newr,
+                                                     ctr, ovf, ovf_cap, def_h, def_m, n_def, opts);
+            if constexpr (STAGED) { __syncwarp(); ring ^= 1; }   // every lane has its keys in registers before the half is refilled
         }
         __syncthreads();                                         // s_ticket[par] written by thread 0
         t = t_next;
@@ -1129,8 +1176,18 @@ bucket_insert_compact_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, cons
                              u32 rank, Counters *ctr, u64 *ovf, u64 ovf_cap, u32 opts)
 {
     static_assert(MODE == 0 || MODE == 1, "MODE 2 (key exchange) is bucket_insert_gather_kernel");
-    bucket_insert_compact_body<MODE>(bkt_hash, seg_cap, bk, b_first, b_end, ticket, table, remote, n_shards, rank, ctr, ovf, ovf_cap,
-                                     opts, nullptr);
+    bucket_insert_compact_body<MODE, false>(bkt_hash, seg_cap, bk, b_first, b_end, ticket, table, remote, n_shards, rank, ctr, ovf, ovf_cap,
+                                            opts, nullptr);
+}
+// the same with the keys staged through per-warp TMA bulk copies (see bucket_insert_compact_body)
+template <int MODE>
+__global__ void __launch_bounds__(PASSB_THREADS, 3)
+bucket_insert_compact_staged_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, const PassBBucket *__restrict__ bk,
+                                    u32 b_first, u32 b_end, u64 *ticket, Table<1> table, Table<1> remote, u32 n_shards,
+                                    u32 rank, Counters *ctr, u64 *ovf, u64 ovf_cap, u32 opts)
+{
+    bucket_insert_compact_body<MODE, true>(bkt_hash, seg_cap, bk, b_first, b_end, ticket, table, remote, n_shards, rank, ctr, ovf, ovf_cap,
+                                           opts, nullptr);
 }
 
 // MODE 2 as a kernel: Pass B over the keys every source rank holds for this shard (KeyxSources: receive buffer or peer HBM)
@@ -1138,7 +1195,13 @@ __global__ void __launch_bounds__(PASSB_THREADS, 3)
 bucket_insert_gather_kernel(const __grid_constant__ KeyxSources srcs, u64 seg_cap, const PassBBucket *__restrict__ bk,
                             u32 b_first, u32 b_end, u64 *ticket, Table<1> table, Counters *ctr, u64 *ovf, u64 ovf_cap, u32 opts)
 {
-    bucket_insert_compact_body<2>(nullptr, seg_cap, bk, b_first, b_end, ticket, table, table, 1u, 0u, ctr, ovf, ovf_cap, opts, &srcs);
+    bucket_insert_compact_body<2, false>(nullptr, seg_cap, bk, b_first, b_end, ticket, table, table, 1u, 0u, ctr, ovf, ovf_cap, opts, &srcs);
+}
+__global__ void __launch_bounds__(PASSB_THREADS, 3)
+bucket_insert_gather_staged_kernel(const __grid_constant__ KeyxSources srcs, u64 seg_cap, const PassBBucket *__restrict__ bk,
+                                   u32 b_first, u32 b_end, u64 *ticket, Table<1> table, Counters *ctr, u64 *ovf, u64 ovf_cap, u32 opts)
+{
+    bucket_insert_compact_body<2, true>(nullptr, seg_cap, bk, b_first, b_end, ticket, table, table, 1u, 0u, ctr, ovf, ovf_cap, opts, &srcs);
 }
 
 // Pass B for multi-word keys (k > 32), batched like the one-word kernel: a thread works on PASSBW_KPT<W> new keys plus
@@ -1147,7 +1210,13 @@ bucket_insert_gather_kernel(const __grid_constant__ KeyxSources srcs, u64 seg_ca
 // lost claim or a slot held by another key is not waited for: the key goes on the per-warp list (as an index into the
 // bucket store, 10 bytes for any W) and retries with the next round.  bucket_insert_kernel<W> above is the one-key-
 // at-a-time form of the same protocol (kept selectable: PBK_WIDE_SERIAL=1).
-template <int W> struct PASSBW_KPT { static constexpr int value = W <= 3 ? 4 : 2; };
+#ifndef PBK_PASSBW_KPT
+#define PBK_PASSBW_KPT 4
+#endif
+#ifndef PBK_PASSBW_MINCTAS
+#define PBK_PASSBW_MINCTAS 2
+#endif
+template <int W> struct PASSBW_KPT { static constexpr int value = W <= 3 ? PBK_PASSBW_KPT : 2; };
 constexpr u32 PASSBW_REMOTE = 1u << 9;               // deferred-entry flag above the probe count (MAX_PROBE < 256)
 
 // STAGED: the keys of a tile do not come through the threads' own global loads but through TMA bulk copies (cp.async.bulk ->
@@ -1157,7 +1226,7 @@ constexpr u32 PASSBW_REMOTE = 1u << 9;               // deferred-entry flag abov
 // stride of 8 W bytes.  Needs 2 x tile_keys x 8 W bytes of dynamic shared memory (96 KB at W = 3) and segments whose byte
 // offsets are 16-byte aligned (plan_partition keeps seg_cap even).
 template <int W, bool STAGED>
-__global__ void __launch_bounds__(PASSB_THREADS, 2)
+__global__ void __launch_bounds__(PASSB_THREADS, PBK_PASSBW_MINCTAS)
 bucket_insert_wide_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const PassBBucket *__restrict__ bk,
                           u32 b_first, u32 b_end, u64 *ticket, Table<W> table, Table<W> remote, u32 n_shards, u32 rank,
                           Counters *ctr, u64 *ovf, u64 ovf_cap)
@@ -1312,7 +1381,7 @@ bucket_insert_wide_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const P
         bulk_copy_g2s(s_stage + (size_t)buf * tile_keys * W, bkt_keys + first_i * W, bytes, &s_mbar[buf]);
     };
     int par = 0;
-    u32 phase[2] = {0, 0};
+    u32 phase = 0;                                            // bit b = parity the next wait on stage buffer b expects
     u64 t = s_ticket[0];
     if constexpr (STAGED) {
         if (tid == 0) { mbar_init(&s_mbar[0], 1); mbar_init(&s_mbar[1], 1); mbar_fence_init(); }
@@ -1335,8 +1404,8 @@ bucket_insert_wide_kernel(const u64 *__restrict__ bkt_keys, u64 seg_cap, const P
         const u64 left = n - j * tile_keys;
         const u64 *stage = nullptr;
         if constexpr (STAGED) {
-            mbar_wait(&s_mbar[par], phase[par]);      // this tile's keys have landed
-            phase[par] ^= 1u;
+            mbar_wait(&s_mbar[par], (phase >> par) & 1u);      // this tile's keys have landed
+            phase ^= 1u << par;
             stage = s_stage + (size_t)par * tile_keys * W;
         }
 #pragma unroll 1

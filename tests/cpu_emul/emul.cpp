@@ -64,8 +64,8 @@ static int run(const uint8_t *bases, const u64 *off, u64 n_reads, int k, int enc
         const u64 tk = W == 1 ? PASSB1_KPT * PASSB1_ROUNDS : PASSB_KPT;     // blockDim = 1 in the emulation
         auto pass_b = [&](const PassBBucket *desc, u32 b0, u32 b1, u64 *ticket) {
             if constexpr (W == 1) {
-                if (n_shards > 1) bucket_insert_compact_kernel<1>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF, 1u);
-                else bucket_insert_compact_kernel<0>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF, 0u);
+                if (n_shards > 1) bucket_insert_compact_staged_kernel<1>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF, 1u);
+                else bucket_insert_compact_staged_kernel<0>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF, 0u);
             } else if (k % 2) {            // odd k: the batched kernel, even k: the one-key-at-a-time form of the protocol
                 bucket_insert_wide_kernel<W, true>(bkt.data(), seg_cap, desc, b0, b1, ticket, table, remote, n_shards, rank, &ctr, ovf.data(), OVF);
             } else {
@@ -207,7 +207,7 @@ extern "C" int emul_keyx_insert(const u64 *recv, const u64 *recv_cursors, u32 n_
         desc[d1 - d0] = PassBBucket{tiles, 0, nullptr, nullptr, 0, 0};
         KeyxSources srcs{};
         for (u32 sr = 0; sr < n_src; ++sr) { srcs.keys[sr] = recv + (u64)sr * n_regions * seg_cap; srcs.cursors[sr] = recv_cursors + (u64)sr * n_regions; }
-        if (tiles) bucket_insert_gather_kernel(srcs, seg_cap, desc.data(), d0, d1, ticket, t, &ctr, ovf.data(), OVF,
+        if (tiles) bucket_insert_gather_staged_kernel(srcs, seg_cap, desc.data(), d0, d1, ticket, t, &ctr, ovf.data(), OVF,
                                                (n_src << 8) | (n_regions << 16));
     }
     if (n_extra) insert_records_kernel<1>(extra, n_extra, 1, t, t, 1, 0, &ctr, ovf.data(), OVF);
