@@ -251,6 +251,33 @@ int  pbk_keyx_pull_partition(pbk_ctx *ctx, const uint8_t *bases, const uint64_t 
 int  pbk_keyx_pull_partition_device(pbk_ctx *ctx, const void *d_bases, const void *d_read_offsets, uint64_t n_reads,
                                     uint64_t n_bases, int async);
 int  pbk_keyx_pull_insert(pbk_ctx *ctx);
+/* frees the store and drops every mapping (to plan a larger layout; every peer must release before anybody partitions again) */
+int  pbk_keyx_pull_release(pbk_ctx *ctx);
+
+/* ---- several GPUs of one box behind one handle (SURVEY.md section 8b "Ownership": the library owns the devices' contexts
+ * and the exchange between them) ------------------------------------------------------------------------------------------
+ * For a host program that is ONE process, like the reference's `assemble` (iterate.cpp:244-264 spawns it): the group owns
+ * one pbk_ctx per device, cuts every batch into one slice per device, drives the devices from one host thread each, and
+ * exchanges keys inside the library -- k <= 32: the pull exchange above over peer-mapped HBM (NVLink), k > 32: (key, count)
+ * records with cudaMemcpyPeer.  No collective library, no second process.  Results are identical to a one-GPU count.
+ * cfg->device / n_shards / shard_rank are ignored; devices == NULL means ordinals 0..n_devices-1.                        */
+typedef struct pbk_group pbk_group;
+int  pbk_device_count(void);
+int  pbk_group_create(pbk_group **out, const pbk_config *cfg, const int32_t *devices, uint32_t n_devices);
+void pbk_group_destroy(pbk_group *g);
+uint32_t pbk_group_size(const pbk_group *g);
+pbk_ctx *pbk_group_member(pbk_group *g, uint32_t i);            /* e.g. for pbk_get_stats of one device */
+const char *pbk_group_last_error(const pbk_group *g);
+int  pbk_group_reset(pbk_group *g, uint32_t k);
+/* as pbk_push_reads: returns when the batch has been counted into the devices' tables */
+int  pbk_group_push_reads(pbk_group *g, const uint8_t *bases, const uint64_t *read_offsets, uint64_t n_reads,
+                          int encoding, const int32_t *n_pos, const uint64_t *n_pos_offsets);
+/* as pbk_finalize, over all devices: the shards' histograms add up (disjoint key sets) */
+int  pbk_group_finalize(pbk_group *g, uint64_t *occ_hist, uint64_t *len_hist, uint64_t *n_distinct,
+                        uint64_t *n_instances, uint64_t *max_occurrence);
+/* as pbk_export, over all devices: sorted != 0 merges the shards' sorted pieces into one ascending list */
+int  pbk_group_export(pbk_group *g, uint32_t min_count, int sorted, uint64_t *keys, uint16_t *counts,
+                      uint64_t capacity, uint64_t *n_out);
 
 /* ---- consumers of the table --------------------------------------
  * Occurrence of every k-mer window of a batch of sequences: ContigDivider::getOccurrenceArray

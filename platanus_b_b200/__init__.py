@@ -4,6 +4,6 @@ The product is libpbk.so (platanus_b_b200/csrc, C ABI in include/pbk.h) plus the
 platanus_b_b200/host/.  This Python package is plumbing: it builds and loads the library (ctypes),
 mirrors the reference's Counter interface for tests/benchmarks, and generates synthetic reads.
 """
-from .capi import KmerCounter, PbkError, load_library, library_path, microbench_atomics  # noqa: F401
+from .capi import KmerCounter, KmerGroup, PbkError, load_library, library_path, microbench_atomics  # noqa: F401
 
-__all__ = ["KmerCounter", "PbkError", "load_library", "library_path", "microbench_atomics"]
+__all__ = ["KmerCounter", "KmerGroup", "PbkError", "load_library", "library_path", "microbench_atomics"]

@@ -16,7 +16,7 @@ LIB = os.path.join(OUT_DIR, "libpbk.so")
 NVCC = os.environ.get("PBK_NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = (["-DPBK_EXPERIMENT"] if os.environ.get("PBK_EXPERIMENT") else []) + os.environ.get("PBK_EXTRA_CFLAGS", "").split() + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
-UNITS = ["pbk_kernels.cu", "pbk_api.cu", "pbk_host.cpp"]
+UNITS = ["pbk_kernels.cu", "pbk_api.cu", "pbk_group.cu", "pbk_host.cpp"]
 HEADERS = ["pbk_device.cuh", "pbk_kernels.cuh", "pbk_kernels_impl.cuh", os.path.join("..", "..", "include", "pbk.h")]
 
 

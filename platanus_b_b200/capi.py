@@ -42,7 +42,9 @@ SYMBOLS = [
     "pbk_lookup", "pbk_lookup_device", "pbk_load_entries", "pbk_read_kmer_occ_bin", "pbk_free",
     "pbk_match_reads", "pbk_seed_entries", "pbk_stream_signal", "pbk_stream_wait", "pbk_keyx_partition_device_async",
     "pbk_push_contigs", "pbk_keyx_pull_setup", "pbk_keyx_pull_handle", "pbk_keyx_pull_connect_ipc", "pbk_keyx_pull_connect_local",
-    "pbk_keyx_pull_partition", "pbk_keyx_pull_partition_device", "pbk_keyx_pull_insert",
+    "pbk_keyx_pull_partition", "pbk_keyx_pull_partition_device", "pbk_keyx_pull_insert", "pbk_keyx_pull_release",
+    "pbk_device_count", "pbk_group_create", "pbk_group_destroy", "pbk_group_size", "pbk_group_member", "pbk_group_last_error",
+    "pbk_group_reset", "pbk_group_push_reads", "pbk_group_finalize", "pbk_group_export",
 ]
 
 
@@ -145,6 +147,17 @@ def load_library(build_if_missing: bool = True):
     L.pbk_keyx_pull_partition.argtypes = [vp, vp, u64p, C.c_uint64, C.c_int, vp, u64p]
     L.pbk_keyx_pull_partition_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int]
     L.pbk_keyx_pull_insert.argtypes = [vp]
+    L.pbk_keyx_pull_release.argtypes = [vp]
+    L.pbk_device_count.restype = C.c_int
+    L.pbk_group_create.argtypes = [C.POINTER(vp), C.POINTER(PbkConfig), vp, C.c_uint32]
+    L.pbk_group_destroy.argtypes = [vp]; L.pbk_group_destroy.restype = None
+    L.pbk_group_size.argtypes = [vp]; L.pbk_group_size.restype = C.c_uint32
+    L.pbk_group_member.argtypes = [vp, C.c_uint32]; L.pbk_group_member.restype = vp
+    L.pbk_group_last_error.argtypes = [vp]; L.pbk_group_last_error.restype = C.c_char_p
+    L.pbk_group_reset.argtypes = [vp, C.c_uint32]
+    L.pbk_group_push_reads.argtypes = [vp, vp, u64p, C.c_uint64, C.c_int, vp, u64p]
+    L.pbk_group_finalize.argtypes = [vp, u64p, u64p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.pbk_group_export.argtypes = [vp, C.c_uint32, C.c_int, u64p, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.pbk_stream_signal.argtypes = [vp, vp]
     L.pbk_stream_wait.argtypes = [vp, vp]
     L.pbk_left_local_min.argtypes = [u64p, C.c_uint64, C.c_uint64]; L.pbk_left_local_min.restype = C.c_uint64
@@ -160,6 +173,76 @@ def load_library(build_if_missing: bool = True):
 
 def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class KmerGroup:
+    """Several GPUs of one box behind one handle (a `pbk_group`): the library cuts every batch into one slice per device and
+    exchanges keys between the devices itself (pull exchange over peer-mapped HBM for k <= 32, records for k > 32)."""
+
+    def __init__(self, k: int, devices, partition: bool | str = True):
+        self._L = load_library()
+        self._g = C.c_void_p()
+        self.k, self.words = int(k), (int(k) + 31) // 32
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        cfg = PbkConfig(C.sizeof(PbkConfig), self.k, -1, F_FORCE_PARTITION if partition == "force" else 0 if partition else F_NO_PARTITION, 0, 0, 0, 0)
+        rc = self._L.pbk_group_create(C.byref(self._g), C.byref(cfg), _ptr(devs), len(devs))
+        if rc:
+            self._g = C.c_void_p()
+            raise PbkError(rc, "pbk_group_create", self._L.pbk_strerror(rc).decode())
+        self.occ_hist = self.len_hist = None
+        self.n_distinct = self.n_instances = self.max_occurrence = 0
+
+    def close(self):
+        if getattr(self, "_g", None) and self._g.value:
+            self._L.pbk_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int, what: str):
+        if rc:
+            raise PbkError(rc, what, self._L.pbk_group_last_error(self._g).decode())
+
+    def push_reads(self, bases: np.ndarray, offsets: np.ndarray):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._check(self._L.pbk_group_push_reads(self._g, _ptr(bases), _ptr(offsets), len(offsets) - 1, ENC_ASCII, None, None), "pbk_group_push_reads")
+
+    def finalize(self):
+        occ = np.zeros(OCC_BINS, np.uint64)
+        lh = np.zeros(LEN_BINS, np.uint64)
+        nd, ni, mx = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._L.pbk_group_finalize(self._g, _ptr(occ), _ptr(lh), C.byref(nd), C.byref(ni), C.byref(mx)), "pbk_group_finalize")
+        self.occ_hist, self.len_hist = occ, lh
+        self.n_distinct, self.n_instances, self.max_occurrence = nd.value, ni.value, mx.value
+        return self
+
+    def export(self, min_count: int = 1, sorted: bool = True):
+        n = C.c_uint64()
+        self._check(self._L.pbk_group_export(self._g, min_count, int(sorted), None, None, 0, C.byref(n)), "pbk_group_export")
+        keys = np.zeros((n.value, self.words), np.uint64)
+        counts = np.zeros(n.value, np.uint16)
+        if n.value:
+            self._check(self._L.pbk_group_export(self._g, min_count, int(sorted), _ptr(keys), _ptr(counts), n.value, C.byref(n)), "pbk_group_export")
+        return keys, counts
+
+    def reset(self, k: int = 0):
+        self._check(self._L.pbk_group_reset(self._g, k), "pbk_group_reset")
+        if k:
+            self.k, self.words = int(k), (int(k) + 31) // 32
+
+    def member_stats(self, i: int) -> dict:
+        st = PbkStats()
+        rc = self._L.pbk_get_stats(self._L.pbk_group_member(self._g, i), C.byref(st))
+        if rc:
+            raise PbkError(rc, "pbk_get_stats")
+        return st.asdict()
 
 
 class KmerCounter:

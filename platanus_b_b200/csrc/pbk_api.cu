@@ -1630,6 +1630,24 @@ int pbk_keyx_pull_connect_local(pbk_ctx *c, uint32_t src_rank, pbk_ctx *peer)
     return PBK_OK;
 }
 
+// forget the store and every mapping (a larger layout is wanted: pbk_group_push_reads; the peers must release theirs too
+// before anybody partitions again)
+int pbk_keyx_pull_release(pbk_ctx *c)
+{
+    if (!c) return PBK_E_ARG;
+    if (!c->pull_base) return PBK_OK;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->s_compute));
+    for (int i = 0; i < KEYX_MAX_SRC; ++i) {
+        if (c->pull_peer_ipc[i] && c->pull_peer[i]) cudaIpcCloseMemHandle(c->pull_peer[i]);
+        c->pull_peer[i] = nullptr; c->pull_peer_ipc[i] = false;
+    }
+    dev_free(c, c->pull_base, c->pull_bytes);
+    c->pull_base = nullptr; c->pull_bytes = c->pull_keys_bytes = c->pull_cur_bytes = 0;
+    c->pull_parity = 1;
+    return PBK_OK;
+}
+
 static int pull_bind(pbk_ctx *c)
 {
     if (!c->pull_base) return fail(c, PBK_E_STATE, "pbk_keyx_pull_partition before pbk_keyx_pull_setup");

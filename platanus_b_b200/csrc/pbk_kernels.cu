@@ -202,10 +202,13 @@ void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64
                                       overflow_keys, overflow_cap, grid, 1u, st)));
 }
 
-// one-word Pass B: keys staged through per-warp TMA bulk copies unless PBK_PASSB_STAGED=0 (needs even seg_cap: 16-byte aligned copies)
+// one-word Pass B with the keys staged through per-warp TMA bulk copies: opt-in (PBK_PASSB_STAGED=1).  Measured on one B200
+// (profiles/r2b_tune_variants.jsonl) it is SLOWER than the threads' own streaming loads when the bucket store is local
+// (Pass B 4.47 vs 3.71 ms on C1: the pass is bound by its atomics, and the per-round mbarrier waits only add latency).
+// Needs even seg_cap (16-byte aligned copies).
 static bool passb1_staged(u64 seg_cap)
 {
-    static const bool on = !(getenv("PBK_PASSB_STAGED") && atoi(getenv("PBK_PASSB_STAGED")) == 0);
+    static const bool on = getenv("PBK_PASSB_STAGED") && atoi(getenv("PBK_PASSB_STAGED")) != 0;
     return on && (seg_cap % 2 == 0);
 }
 template <typename K> static void passb1_staged_attr(K kernel)
@@ -296,8 +299,9 @@ void launch_bucket_insert(const u64 *bkt_keys, u64 seg_cap, const u64 *counts, v
         return;
     }
     const int grid = (int)std::min<u64>(tiles, (u64)sm_count * PBK_PASSBW_MINCTAS);
-    // keys staged through TMA bulk copies (two tiles in shared memory) unless PBK_WIDE_STAGED=0; needs even seg_cap for odd W
-    static const bool staged_on = !(getenv("PBK_WIDE_STAGED") && atoi(getenv("PBK_WIDE_STAGED")) == 0);
+    // keys staged through TMA bulk copies (two tiles in shared memory): opt-in, PBK_WIDE_STAGED=1 (measured 6 % slower than the
+    // threads' own loads at k = 75, profiles/r2b_tune_variants.jsonl); needs even seg_cap for odd W
+    static const bool staged_on = getenv("PBK_WIDE_STAGED") && atoi(getenv("PBK_WIDE_STAGED")) != 0;
     const size_t stage_bytes = 2 * (size_t)PASSB_TILE_KEYS * table.words * 8;
     const bool staged = staged_on && stage_bytes * PBK_PASSBW_MINCTAS <= 200 * 1024 && ((seg_cap * table.words) % 2 == 0);
     switch (table.words) {

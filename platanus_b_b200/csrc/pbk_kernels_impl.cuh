@@ -623,6 +623,10 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
                     run += i0;
                 }
             }
+            // Nothing to do if no window ending in [i0, i0 + WIN) can be usable: flags inside the range only shorten the run, so
+            // run + WIN < k settles it.  With k = 75 on 150-base reads the first 74 positions of every read -- half of all
+            // work items -- end here, before any key word is built.
+            if (run + WIN >= k) {
             // rolling state = the 32 W bases that end just before position i0
             u64 fwd[W], rev[W];
             if (i0 == 0) {
@@ -672,13 +676,15 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
                     ++inst;
                     const u32 pos = atomicAdd(&scount[bkt], 1u);
                     if (pos < bin_cap) {
+                        u64 *dst = bins + (bkt * bin_cap + pos) * (u32)W;      // (bins hold < 2^15 words: 32-bit index arithmetic)
 #pragma unroll
-                        for (int j = 0; j < W; ++j) bins[((u64)bkt * bin_cap + pos) * W + j] = key[j];
+                        for (int j = 0; j < W; ++j) dst[j] = key[j];
                     } else {
                         bucket_append_direct<W>(key, bkt, bkt_keys, seg_cap, bkt_cursor, ovf, ovf_cap, ctr);
                     }
                 }
             }
+            }   // run + WIN >= k
         }
         __syncthreads();
         // flush, step 1: one thread per bucket reserves the bin's place in the bucket segment (all atomics of the
@@ -1210,11 +1216,13 @@ bucket_insert_gather_staged_kernel(const __grid_constant__ KeyxSources srcs, u64
 // lost claim or a slot held by another key is not waited for: the key goes on the per-warp list (as an index into the
 // bucket store, 10 bytes for any W) and retries with the next round.  bucket_insert_kernel<W> above is the one-key-
 // at-a-time form of the same protocol (kept selectable: PBK_WIDE_SERIAL=1).
+// measured on C1 (scripts/tune_variants.sh, profiles/r2b_tune_variants.jsonl): 2 new keys + 1 deferred per thread and round at 3
+// CTAs per SM (76 registers) beats 4 + 1 at 2 CTAs (126 registers): k = 75 Pass B 6.6 -> 5.8 ms, k = 42 7.7 -> 6.8 ms
 #ifndef PBK_PASSBW_KPT
-#define PBK_PASSBW_KPT 4
+#define PBK_PASSBW_KPT 2
 #endif
 #ifndef PBK_PASSBW_MINCTAS
-#define PBK_PASSBW_MINCTAS 2
+#define PBK_PASSBW_MINCTAS 3
 #endif
 template <int W> struct PASSBW_KPT { static constexpr int value = W <= 3 ? PBK_PASSBW_KPT : 2; };
 constexpr u32 PASSBW_REMOTE = 1u << 9;               // deferred-entry flag above the probe count (MAX_PROBE < 256)

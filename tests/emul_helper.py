@@ -183,7 +183,7 @@ def abi_lib_path() -> str:
     import re
     emul_dir = os.path.join(HERE, "cpu_emul")
     srcs = [os.path.join(CSRC, f) for f in ("pbk_kernels.cu", "pbk_api.cu", "pbk_host.cpp", "pbk_device.cuh", "pbk_kernels.cuh",
-                                            "pbk_kernels_impl.cuh")]
+                                            "pbk_kernels_impl.cuh", "pbk_group.cu")]
     deps = srcs + [os.path.join(emul_dir, f) for f in ("cuda_shim.h", "cuda_rt_shim.h", "abi_extra.cpp")] + [
         os.path.join(os.path.dirname(HERE), "include", "pbk.h")]
     if os.path.exists(ABI_OUT) and os.path.getmtime(ABI_OUT) >= max(os.path.getmtime(d) for d in deps):
@@ -200,7 +200,7 @@ def abi_lib_path() -> str:
     flags = ["-O1", "-std=c++17", "-fPIC", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable", "-DPBK_CPU_EMUL=1",
              "-include", os.path.join(emul_dir, "cuda_shim.h"), "-include", os.path.join(emul_dir, "cuda_rt_shim.h")]
     objs = []
-    for src in (gen, srcs[1], os.path.join(emul_dir, "abi_extra.cpp"), srcs[2]):
+    for src in (gen, srcs[1], os.path.join(CSRC, "pbk_group.cu"), os.path.join(emul_dir, "abi_extra.cpp"), srcs[2]):
         obj = os.path.join(build, os.path.basename(src).split(".")[0] + "_abi.o")
         subprocess.run(["g++", *flags, "-x", "c++", "-c", src, "-o", obj], check=True)
         objs.append(obj)
