@@ -365,6 +365,21 @@ void exec(Options &opt)
             q.producer_done();
         }));
     }
+    // How many GPUs: PBK_NUM_GPUS (a number, or "all"), else one per 2 GiB of input text, never more than are visible
+    // (CUDA_VISIBLE_DEVICES chooses which; there is no new command-line flag, iterate.cpp:244-251 spawns a fixed command line).
+    {
+        const int visible = std::max(1, pbk_device_count());
+        unsigned want = (unsigned)std::max<size_t>(1, total_bytes >> 31);
+        if (const char *e = getenv("PBK_NUM_GPUS")) want = strcmp(e, "all") == 0 ? (unsigned)visible : (unsigned)std::max(1, atoi(e));
+        if (getenv("PBK_GROUP_LOGICAL") && want > (unsigned)visible) {      // tests: more shards than GPUs, several members per device
+            std::vector<int32_t> devs;
+            for (unsigned i = 0; i < std::min(want, 16u); ++i) devs.push_back((int32_t)(i % (unsigned)visible));
+            counter.setDevices(devs);
+        } else {
+            counter.setNumDevices(std::min<unsigned>(want, (unsigned)visible));
+        }
+        if (counter.getNumDevices() > 1 && getenv("PBK_TIMING")) std::cerr << "[pbk] counting on " << counter.getNumDevices() << " GPUs" << std::endl;
+    }
     pbk::ErrorBase *push_error = NULL;
     try { counter.beginCounting(k0); } catch (pbk::ErrorBase &e) { push_error = new pbk::ErrorBase(e); }
     pt.mark("pbk_create (CUDA context)");

@@ -50,15 +50,23 @@ public:
 
     FILE *kmerFP;      // kept for source compatibility (counter.h:77); the (key, count) stream stays in HBM
 
-    Counter() : kmerFP(NULL), ctx_(NULL), kmerLength_(0), maxOccurrence_(0), doubleHashSize_(0), nInstances_(0), nDistinct_(0),
-                device_(-1), flags_(0) {}
-    explicit Counter(u64_t k) : kmerFP(NULL), ctx_(NULL), kmerLength_(k), maxOccurrence_(0), doubleHashSize_(0), nInstances_(0),
-                                nDistinct_(0), device_(-1), flags_(0) {}
-    ~Counter() { if (ctx_) pbk_destroy(ctx_); }
+    Counter() : kmerFP(NULL), ctx_(NULL), group_(NULL), kmerLength_(0), maxOccurrence_(0), doubleHashSize_(0), nInstances_(0), nDistinct_(0),
+                device_(-1), flags_(0), numDevices_(1) {}
+    explicit Counter(u64_t k) : kmerFP(NULL), ctx_(NULL), group_(NULL), kmerLength_(k), maxOccurrence_(0), doubleHashSize_(0), nInstances_(0),
+                                nDistinct_(0), device_(-1), flags_(0), numDevices_(1) {}
+    ~Counter() { if (ctx_) pbk_destroy(ctx_); if (group_) pbk_group_destroy(group_); }
     Counter(const Counter &) = delete;
     Counter &operator=(const Counter &) = delete;
 
     void setDevice(int device) { device_ = device; }
+    // count on the first n visible GPUs (CUDA_VISIBLE_DEVICES selects which): the library shards the keys by hash range and
+    // exchanges them between the devices itself (pbk_group_*).  Must be called before the first beginCounting.  The counting
+    // members (beginCounting .. exportKmers and what builds on them) work on the group; the table consumers (occurrenceArray,
+    // matchReads, seedEntries, pushContigs, readOccurrenceTableBinary) need a single device.
+    void setNumDevices(unsigned n) { numDevices_ = n < 1 ? 1 : n; deviceList_.clear(); }
+    // the same with explicit device ordinals (an ordinal may repeat: logical shards on one GPU, used by the tests)
+    void setDevices(const std::vector<int32_t> &devices) { deviceList_ = devices; numDevices_ = devices.empty() ? 1u : (unsigned)devices.size(); }
+    unsigned getNumDevices() const { return numDevices_; }
     void setFlags(unsigned flags) { flags_ = flags; }
     pbk_ctx *context() { return ctx_; }
 
@@ -86,17 +94,25 @@ public:
     void beginCounting(u64_t kLength)
     {
         kmerLength_ = kLength;
+        keptValid_ = false;
+        if (group_) { check(pbk_group_reset(group_, (uint32_t)kLength), "pbk_group_reset"); return; }
         if (ctx_) { check(pbk_reset(ctx_, (uint32_t)kLength), "pbk_reset"); return; }
         pbk_config cfg;
         memset(&cfg, 0, sizeof cfg);
         cfg.struct_size = sizeof cfg; cfg.k = (uint32_t)kLength; cfg.device = device_; cfg.flags = flags_;
+        if (numDevices_ > 1) {
+            const int rc = pbk_group_create(&group_, &cfg, deviceList_.empty() ? NULL : deviceList_.data(), numDevices_);
+            if (rc != PBK_OK) { group_ = NULL; throw GPUError(pbk_strerror(rc)); }
+            return;
+        }
         const int rc = pbk_create(&ctx_, &cfg);
         if (rc != PBK_OK) { ctx_ = NULL; throw GPUError(pbk_strerror(rc)); }
     }
     // ASCII bases of n reads, concatenated; offsets[n + 1]
     void pushReads(const uint8_t *bases, const uint64_t *offsets, uint64_t n)
     {
-        check(pbk_push_reads(ctx_, bases, offsets, n, PBK_ENC_ASCII, NULL, NULL), "pbk_push_reads");
+        if (group_) check(pbk_group_push_reads(group_, bases, offsets, n, PBK_ENC_ASCII, NULL, NULL), "pbk_group_push_reads");
+        else check(pbk_push_reads(ctx_, bases, offsets, n, PBK_ENC_ASCII, NULL, NULL), "pbk_push_reads");
     }
     // finish: fills lengthDistribution, occurrenceDistribution, maxOccurrence; returns doubleHashSize
     u64_t endCounting(u64_t memory)
@@ -104,8 +120,12 @@ public:
         occurrenceDistribution_.assign(PBK_OCC_BINS, 0);
         lengthDistribution_.assign(PBK_LEN_BINS, 0);
         uint64_t nd = 0, ni = 0, mx = 0;
-        check(pbk_finalize(ctx_, (uint64_t *)occurrenceDistribution_.data(), (uint64_t *)lengthDistribution_.data(), &nd, &ni, &mx),
-              "pbk_finalize");
+        if (group_)
+            check(pbk_group_finalize(group_, (uint64_t *)occurrenceDistribution_.data(), (uint64_t *)lengthDistribution_.data(), &nd, &ni, &mx),
+                  "pbk_group_finalize");
+        else
+            check(pbk_finalize(ctx_, (uint64_t *)occurrenceDistribution_.data(), (uint64_t *)lengthDistribution_.data(), &nd, &ni, &mx),
+                  "pbk_finalize");
         nDistinct_ = nd; nInstances_ = ni;
         if (nd) maxOccurrence_ = mx;                       // counter.h:371-376 leaves it unchanged when nothing was counted
         doubleHashSize_ = pbk_double_hash_size(memory, (uint32_t)kmerLength_);
@@ -255,8 +275,16 @@ public:
     void exportKmers(u64_t minOccurrence, bool sorted)
     {
         uint64_t n = 0;
-        check(pbk_export(ctx_, (uint32_t)minOccurrence, sorted ? 1 : 0, NULL, NULL, 0, &n), "pbk_export");
         const size_t W = (size_t)((kmerLength_ + 31) / 32);
+        if (group_) {
+            check(pbk_group_export(group_, (uint32_t)minOccurrence, sorted ? 1 : 0, NULL, NULL, 0, &n), "pbk_group_export");
+            keptKeys_.assign(n * W, 0);
+            keptCounts_.assign(n, 0);
+            if (n) check(pbk_group_export(group_, (uint32_t)minOccurrence, sorted ? 1 : 0, keptKeys_.data(), keptCounts_.data(), n, &n), "pbk_group_export");
+            keptMin_ = minOccurrence; keptValid_ = true;
+            return;
+        }
+        check(pbk_export(ctx_, (uint32_t)minOccurrence, sorted ? 1 : 0, NULL, NULL, 0, &n), "pbk_export");
         keptKeys_.assign(n * W, 0);
         keptCounts_.assign(n, 0);
         if (n) check(pbk_export(ctx_, (uint32_t)minOccurrence, sorted ? 1 : 0, keptKeys_.data(), keptCounts_.data(), n, &n), "pbk_export");
@@ -283,10 +311,12 @@ private:
     void check(int rc, const char *what)
     {
         if (rc == PBK_OK) return;
+        if (!ctx_ && !group_) throw GPUError(std::string(what) + ": no device context (several GPUs: only the counting members are available)");
         if (rc == PBK_E_READ_TOO_LONG) throw ReadError();                      // common.h:465
         if (rc == PBK_E_KMER_DIST) throw KmerDistError();
         std::string m = std::string(what) + ": " + pbk_strerror(rc);
         if (ctx_ && pbk_last_error(ctx_)[0]) m += std::string(" (") + pbk_last_error(ctx_) + ")";
+        if (group_ && pbk_group_last_error(group_)[0]) m += std::string(" (") + pbk_group_last_error(group_) + ")";
         if (rc == PBK_E_BAD_BASE) throw ReadError(m);
         throw GPUError(m);
     }
@@ -310,9 +340,11 @@ private:
     }
 
     pbk_ctx *ctx_;
+    pbk_group *group_;
     u64_t kmerLength_, maxOccurrence_, doubleHashSize_, nInstances_, nDistinct_;
     int device_;
-    unsigned flags_;
+    unsigned flags_, numDevices_;
+    std::vector<int32_t> deviceList_;
     std::vector<u64_t> lengthDistribution_, occurrenceDistribution_;
     std::vector<uint64_t> keptKeys_;
     std::vector<uint16_t> keptCounts_;

@@ -174,3 +174,26 @@ def test_pbk_assemble_error_codes(cli, tmp_path):
     assert p.returncode == 4
     p = subprocess.run([cli, "assemble", "-k", "8"], capture_output=True, text=True)          # no -f: usage, exit 1
     assert p.returncode == 1 and "Usage" in p.stderr
+
+
+@needs_ref
+@pytest.mark.parametrize("k,n_gpus", [(32, 2), (75, 3)])
+def test_pbk_assemble_on_several_gpus_gives_identical_files(oracle, cli, k, n_gpus, tmp_path):
+    """The C++ host program on a pbk_group (include/pbk.h): PBK_NUM_GPUS devices -- logical shards when the box has fewer
+    (PBK_GROUP_LOGICAL, a test switch; `gpurun --gpus 2` runs the k = 32 case on two real B200s) -- must write the same .tsv,
+    print the same marker lines and dump the same sorted table as the unmodified reference program."""
+    O = oracle
+    rs = synth.make_reads(synth.config("C1", scale=1 / 25))
+    files = synth.write_fastq(rs, str(tmp_path / "r_1.fq"), str(tmp_path / "r_2.fq"))
+    ref = O.run_reference(files, k, str(tmp_path), threads=min(8, os.cpu_count() or 1), mem_gb=1)
+    assert ref.returncode == 0, ref.stderr
+    p = run_ours(cli, files, k, str(tmp_path), env={"PBK_NUM_GPUS": str(n_gpus), "PBK_GROUP_LOGICAL": "1", "PBK_TIMING": "1"})
+    assert p.returncode == 0, p.stderr
+    assert f"counting on {n_gpus} GPUs" in p.stderr
+    assert markers(p.stderr, k) == markers(ref.stderr, k)
+    assert open(tmp_path / f"gpu_{k}merFrq.tsv").read() == ref.tsv
+    t = O.read_bin(str(tmp_path / "gpu_kmer_occ.bin"))
+    assert t.reachable and t.k == k and t.index_size == ref.table.index_size
+    gk, gc = t.sorted_dump()
+    rk, rc = ref.table.sorted_dump()
+    assert np.array_equal(gk, rk) and np.array_equal(gc, rc)
