@@ -52,7 +52,8 @@ typedef struct pbk_ctx pbk_ctx;
 
 enum {
     PBK_ENC_ASCII    = 0,  /* raw characters as the parser hands them to SEQ::convertFromString     */
-    PBK_ENC_PLATANUS = 1   /* SEQ temp-file form (common.h:426-448): bytes 0..3, N positions listed */
+    PBK_ENC_PLATANUS = 1,  /* SEQ temp-file form (common.h:426-448): bytes 0..3, N positions listed */
+    PBK_ENC_PACKED2  = 2   /* 2-bit words + absolute N positions: pbk_push_reads_packed only          */
 };
 
 enum {
@@ -123,6 +124,23 @@ void pbk_host_free(void *p);
  */
 int  pbk_push_reads(pbk_ctx *ctx, const uint8_t *bases, const uint64_t *read_offsets, uint64_t n_reads,
                     int encoding, const int32_t *n_pos, const uint64_t *n_pos_offsets);
+
+/*
+ * Opt-in third input form: the bases already packed to 2 bits by the host parser as it copies each record -- exactly the
+ * library's device layout (32 bases per u64, first base in the two most significant bits; reads concatenated without
+ * separators; the last word zero-padded), so the H2D copy goes straight into the stream buffer, there is no pack kernel,
+ * and PCIe carries 0.25 byte per base instead of 1 (host buffers through pbk_push_reads(PBK_ENC_ASCII) cap at
+ * ~44 G k-mers/s on a 55 GB/s link whatever the kernels do).
+ *   words         ceil(read_offsets[n_reads] / 32) u64
+ *   n_positions   stream positions (0-based, over the whole batch) of every N, ascending or not; the two bits under an N
+ *                 are ignored
+ * pbk_pack_reads produces this form from ASCII with Char2Bin semantics (common.h:256): returns PBK_E_BAD_BASE for a
+ * character without a code; *n_n_out = number of N found (n_positions_out filled up to n_cap; PBK_E_ARG if more).
+ * Reads of this form may be mixed with the other pushes; ASCII stays the default form the reference's parser hands over.   */
+int  pbk_pack_reads(const uint8_t *bases, uint64_t n_bases, uint64_t *words_out, uint64_t *n_positions_out,
+                    uint64_t n_cap, uint64_t *n_n_out);
+int  pbk_push_reads_packed(pbk_ctx *ctx, const uint64_t *words, const uint64_t *read_offsets, uint64_t n_reads,
+                           const uint64_t *n_positions, uint64_t n_n);
 
 /* Same with `bases` and `read_offsets` already resident in device memory (PBK_ENC_ASCII only). */
 int  pbk_push_reads_device(pbk_ctx *ctx, const void *d_bases, const void *d_read_offsets,

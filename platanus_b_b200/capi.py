@@ -45,6 +45,7 @@ SYMBOLS = [
     "pbk_keyx_pull_partition", "pbk_keyx_pull_partition_device", "pbk_keyx_pull_insert", "pbk_keyx_pull_release",
     "pbk_device_count", "pbk_group_create", "pbk_group_destroy", "pbk_group_size", "pbk_group_member", "pbk_group_last_error",
     "pbk_group_reset", "pbk_group_push_reads", "pbk_group_finalize", "pbk_group_export",
+    "pbk_pack_reads", "pbk_push_reads_packed",
 ]
 
 
@@ -114,6 +115,8 @@ def load_library(build_if_missing: bool = True):
     L.pbk_host_free.argtypes = [vp]; L.pbk_host_free.restype = None
     L.pbk_push_reads.argtypes = [vp, vp, u64p, C.c_uint64, C.c_int, vp, u64p]
     L.pbk_push_reads_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64]
+    L.pbk_pack_reads.argtypes = [vp, C.c_uint64, u64p, u64p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.pbk_push_reads_packed.argtypes = [vp, u64p, u64p, C.c_uint64, u64p, C.c_uint64]
     L.pbk_finalize.argtypes = [vp, u64p, u64p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.pbk_export.argtypes = [vp, C.c_uint32, C.c_int, u64p, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.pbk_get_stats.argtypes = [vp, C.POINTER(PbkStats)]
@@ -173,6 +176,25 @@ def load_library(build_if_missing: bool = True):
 
 def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def pack_reads(bases: np.ndarray):
+    """pbk_pack_reads: ASCII bases (all reads concatenated) -> (2-bit stream words uint64, absolute N positions uint64) --
+    what a host parser that packs as it copies hands to push_reads_packed."""
+    L = load_library()
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    n = len(bases)
+    words = np.zeros((n + 31) // 32, np.uint64)
+    n_n = C.c_uint64()
+    rc = L.pbk_pack_reads(_ptr(bases), n, _ptr(words), None, 0, C.byref(n_n))
+    if rc:
+        raise PbkError(rc, "pbk_pack_reads")
+    npos = np.zeros(n_n.value, np.uint64)
+    if n_n.value:
+        rc = L.pbk_pack_reads(_ptr(bases), n, _ptr(words), _ptr(npos), n_n.value, C.byref(n_n))
+        if rc:
+            raise PbkError(rc, "pbk_pack_reads")
+    return words, npos
 
 
 class KmerGroup:
@@ -303,6 +325,18 @@ class KmerCounter:
         """Host pointers (e.g. torch pinned tensors' data_ptr())."""
         self._check(self._L.pbk_push_reads(self._ctx, C.c_void_p(bases_ptr), C.c_void_p(offsets_ptr), n_reads,
                                            ENC_ASCII, None, None), "pbk_push_reads")
+
+    def push_reads_packed(self, words: np.ndarray, offsets: np.ndarray, n_positions: np.ndarray):
+        """Opt-in host form: 2-bit words (pack_reads) + absolute N positions: 0.25 byte per base over PCIe, no pack kernel."""
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n_positions = np.ascontiguousarray(n_positions, dtype=np.uint64)
+        self._check(self._L.pbk_push_reads_packed(self._ctx, _ptr(words), _ptr(offsets), len(offsets) - 1,
+                                                  _ptr(n_positions) if len(n_positions) else None, len(n_positions)), "pbk_push_reads_packed")
+
+    def push_reads_packed_ptr(self, words_ptr: int, offsets_ptr: int, n_reads: int, npos_ptr: int, n_n: int):
+        self._check(self._L.pbk_push_reads_packed(self._ctx, C.c_void_p(words_ptr), C.c_void_p(offsets_ptr), n_reads,
+                                                  C.c_void_p(npos_ptr) if n_n else None, n_n), "pbk_push_reads_packed")
 
     def push_reads_device(self, d_bases_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int):
         """Device pointers (inputs already resident in HBM)."""

@@ -95,6 +95,8 @@ struct pbk_ctx {
     int pull_parity = 1;                     // parity of the store the last partition call filled (first call: 0)
     cudaEvent_t ev_signal = nullptr, ev_wait = nullptr;     // pbk_stream_signal / pbk_stream_wait
 
+    u64 *d_npos_abs = nullptr; u64 npos_abs_cap = 0;      // PBK_ENC_PACKED2: N positions of the current batch (grow-only)
+    cudaEvent_t ev_stream_free = nullptr;                 // PBK_ENC_PACKED2: H2D copies go straight into the stream buffer
     void *d_scratch = nullptr; size_t scratch_bytes = 0;   // grow-only arena of pbk_export (entries, sort temporaries)
 
     bool finalized = false;
@@ -599,11 +601,48 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
             CK(cudaGetLastError());
             TRY(count_words(w0, w0 + nw));
         }
+    } else if (encoding == PBK_ENC_PACKED2) {
+        // the host hands over 2-bit words in the stream's own layout: chunks are copied straight into the stream buffer on the
+        // copy stream (no staging ring, no pack kernel); n_pos carries the batch's absolute N positions, n_pos_offsets[0] their number
+        const u64 *h_words = reinterpret_cast<const u64 *>(h_bases);
+        const u64 *h_npos = reinterpret_cast<const u64 *>(n_pos);
+        const u64 n_n = n_pos_offsets ? n_pos_offsets[0] : 0;
+        for (int i = 0; i < N_STAGE; ++i)
+            if (!c->ev_copy_done[i]) CK(cudaEventCreateWithFlags(&c->ev_copy_done[i], cudaEventDisableTiming));
+        if (!c->ev_stream_free) CK(cudaEventCreateWithFlags(&c->ev_stream_free, cudaEventDisableTiming));
+        if (n_n > c->npos_abs_cap) {
+            CK(cudaStreamSynchronize(c->s_compute));
+            dev_free(c, c->d_npos_abs, c->npos_abs_cap * 8);
+            c->d_npos_abs = nullptr; c->npos_abs_cap = 0;
+            TRY(dev_alloc(c, (void **)&c->d_npos_abs, (n_n + n_n / 4 + 1024) * 8));
+            c->npos_abs_cap = n_n + n_n / 4 + 1024;
+        }
+        CK(cudaMemsetAsync(nflag, 0, words * 4, c->s_compute));
+        if (n_n) { CK(cudaMemcpyAsync(c->d_npos_abs, h_npos, n_n * 8, cudaMemcpyHostToDevice, c->s_compute)); c->h2d_bytes += n_n * 8; }
+        { Span sp(c, LC_OTHER); launch_npos_abs_scatter(c->d_npos_abs, n_n, n_bases, nflag, c->s_compute); }
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c->ev_stream_free, c->s_compute));          // whatever still read the previous batch's stream is queued before this
+        CK(cudaStreamWaitEvent(c->s_copy, c->ev_stream_free, 0));
+        const u64 n_chunks = (n_bases + CHUNK_BASES - 1) / CHUNK_BASES;
+        auto enqueue_copy = [&](u64 ci) -> int {
+            const u64 w0 = ci * (CHUNK_BASES / 32), nw = std::min<u64>(CHUNK_BASES / 32, words - w0);
+            CK(cudaMemcpyAsync(stream + w0, h_words + w0, nw * 8, cudaMemcpyHostToDevice, c->s_copy));
+            CK(cudaEventRecord(c->ev_copy_done[ci % N_STAGE], c->s_copy));
+            c->h2d_bytes += nw * 8;
+            return PBK_OK;
+        };
+        for (u64 ci = 0; ci < std::min<u64>(n_chunks, N_STAGE - 1); ++ci) TRY(enqueue_copy(ci));
+        for (u64 ci = 0; ci < n_chunks; ++ci) {
+            const u64 w0 = ci * (CHUNK_BASES / 32), nw = std::min<u64>(CHUNK_BASES / 32, words - w0);
+            if (ci + N_STAGE - 1 < n_chunks) TRY(enqueue_copy(ci + N_STAGE - 1));
+            CK(cudaStreamWaitEvent(c->s_compute, c->ev_copy_done[ci % N_STAGE], 0));
+            TRY(count_words(w0, w0 + nw));
+        }
     } else {
         if (!c->d_stage[0]) {
             for (int i = 0; i < N_STAGE; ++i) {
                 TRY(dev_alloc(c, (void **)&c->d_stage[i], CHUNK_BASES));
-                CK(cudaEventCreateWithFlags(&c->ev_copy_done[i], cudaEventDisableTiming));
+                if (!c->ev_copy_done[i]) CK(cudaEventCreateWithFlags(&c->ev_copy_done[i], cudaEventDisableTiming));
                 CK(cudaEventCreateWithFlags(&c->ev_stage_free[i], cudaEventDisableTiming));
             }
             c->stage_bytes = CHUNK_BASES;
@@ -688,7 +727,8 @@ void release_all(pbk_ctx *c)
     cudaFree(c->d_passb); if (c->h_passb) cudaFreeHost(c->h_passb);
     cudaFree(c->table.slots); cudaFree(c->remote.slots); cudaFree(c->d_ctr); cudaFree(c->d_ovf);
     cudaFree(c->d_len_hist); cudaFree(c->d_occ_hist); cudaFree(c->d_shard_counts);
-    cudaFree(c->d_len_scratch); cudaFree(c->d_ctr_scratch); cudaFree(c->d_scratch);
+    cudaFree(c->d_len_scratch); cudaFree(c->d_ctr_scratch); cudaFree(c->d_scratch); cudaFree(c->d_npos_abs);
+    if (c->ev_stream_free) cudaEventDestroy(c->ev_stream_free);
     for (int i = 0; i < KEYX_MAX_SRC; ++i) if (c->pull_peer_ipc[i] && c->pull_peer[i]) cudaIpcCloseMemHandle(c->pull_peer[i]);
     cudaFree(c->pull_base);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
@@ -850,6 +890,22 @@ int pbk_push_reads(pbk_ctx *c, const uint8_t *bases, const uint64_t *read_offset
         r0 = r1;
     }
     return PBK_OK;
+}
+
+int pbk_push_reads_packed(pbk_ctx *c, const uint64_t *words, const uint64_t *read_offsets, uint64_t n_reads,
+                          const uint64_t *n_positions, uint64_t n_n)
+{
+    if (!c) return PBK_E_ARG;
+    if (n_reads == 0) return PBK_OK;
+    if (!read_offsets || read_offsets[0] != 0) return fail(c, PBK_E_ARG, "bad read_offsets");
+    const u64 n_bases = read_offsets[n_reads];
+    if (n_bases && !words) return fail(c, PBK_E_ARG, "words is NULL");
+    if (n_n && !n_positions) return fail(c, PBK_E_ARG, "n_positions is NULL");
+    if (n_bases > MAX_PUSH_BASES) return fail(c, PBK_E_ARG, "pbk_push_reads_packed takes at most %llu bases per call", (unsigned long long)MAX_PUSH_BASES);
+    // (push_common's n_pos / n_pos_offsets slots carry the absolute N positions and their number for this encoding)
+    const u64 count = n_n;
+    return push_common(c, reinterpret_cast<const uint8_t *>(words), nullptr, (const u64 *)read_offsets, nullptr, n_reads, n_bases,
+                       PBK_ENC_PACKED2, reinterpret_cast<const int32_t *>(n_positions), &count);
 }
 
 int pbk_push_reads_device(pbk_ctx *c, const void *d_bases, const void *d_read_offsets, uint64_t n_reads, uint64_t n_bases)

@@ -92,6 +92,38 @@ uint64_t pbk_double_hash_size(uint64_t memory_bytes, uint32_t k)
     return tmp;
 }
 
+// ASCII -> the library's 2-bit stream words + N position list (pbk_push_reads_packed).  Same character rules as the device
+// pack_kernel (Char2Bin, common.h:256, looks at the low nibble only): 1/A 3/C 7/G 4/T, 14/N, 15 -> A; anything else has no code.
+int pbk_pack_reads(const uint8_t *bases, uint64_t n_bases, uint64_t *words_out, uint64_t *n_positions_out, uint64_t n_cap,
+                   uint64_t *n_n_out)
+{
+    if ((n_bases && (!bases || !words_out)) || !n_n_out) return PBK_E_ARG;
+    static const struct Lut { uint8_t code[256]; Lut() {
+        for (int c = 0; c < 256; ++c) {
+            const int nib = c & 15;
+            code[c] = nib == 1 ? 0 : nib == 3 ? 1 : nib == 7 ? 2 : nib == 4 ? 3 : nib == 15 ? 0 : nib == 14 ? 4 : 255;
+        }
+    } } lut;
+    u64 n_n = 0;
+    bool bad = false, full = false;
+    const u64 n_words = (n_bases + 31) / 32;
+    for (u64 w = 0; w < n_words; ++w) {
+        const u64 b0 = w * 32, m = std::min<u64>(32, n_bases - b0);
+        u64 word = 0;
+        for (u64 i = 0; i < m; ++i) {
+            const uint8_t c = lut.code[bases[b0 + i]];
+            if (c <= 3) { word |= (u64)c << (62 - 2 * i); continue; }
+            if (c == 255) { bad = true; continue; }
+            if (n_positions_out && n_n < n_cap) n_positions_out[n_n] = b0 + i; else full = true;
+            ++n_n;
+        }
+        words_out[w] = word;
+    }
+    *n_n_out = n_n;
+    if (bad) return PBK_E_BAD_BASE;
+    return (full && n_positions_out) ? PBK_E_ARG : PBK_OK;
+}
+
 // Counter::outputOccurrenceDistribution (counter.h:1000-1007)
 int pbk_write_frq_tsv(const char *path, const uint64_t *occ, uint64_t max_occ)
 {

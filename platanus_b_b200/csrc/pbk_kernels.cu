@@ -52,6 +52,11 @@ void launch_read_marks(const u64 *offsets, u64 n_reads, u64 *len_hist, u32 *rfla
     read_marks_kernel<<<grid_for(n_reads, 256, 148, 8), 256, 0, st>>>(offsets, n_reads, len_hist, rflag, ctr);
 }
 
+void launch_npos_abs_scatter(const u64 *n_positions, u64 n_n, u64 n_bases, u32 *nflag, cudaStream_t st)
+{
+    npos_abs_scatter_kernel<<<grid_for(n_n + 1, 256, 148, 4), 256, 0, st>>>(n_positions, n_n, n_bases, nflag);
+}
+
 void launch_npos_scatter(const u64 *offsets, const int32_t *n_pos, const u64 *n_pos_offsets, u64 n_reads,
                          u32 *nflag, cudaStream_t st)
 {

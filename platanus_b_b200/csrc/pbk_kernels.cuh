@@ -30,6 +30,9 @@ void launch_read_marks(const u64 *offsets, u64 n_reads, u64 *len_hist, u32 *rfla
 void launch_npos_scatter(const u64 *offsets, const int32_t *n_pos, const u64 *n_pos_offsets, u64 n_reads,
                          u32 *nflag, cudaStream_t st);
 
+// PBK_ENC_PACKED2: absolute N positions + the padding behind the last base into nflag
+void launch_npos_abs_scatter(const u64 *n_positions, u64 n_n, u64 n_bases, u32 *nflag, cudaStream_t st);
+
 // ---- counting ---------------------------------------------------------------------------------
 // windows that END in stream words [word_begin, word_end) are canonicalised and inserted
 void launch_count(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,

@@ -136,6 +136,19 @@ npos_scatter_kernel(const u64 *__restrict__ off, const int32_t *__restrict__ n_p
 }
 
 
+// PBK_ENC_PACKED2: N positions given as stream positions of the batch; positions past the last base (the zero padding of the
+// last word) are flagged too, so that no window can end there (pack_kernel does the same for its tail)
+__global__ void __launch_bounds__(256)
+npos_abs_scatter_kernel(const u64 *__restrict__ n_positions, u64 n_n, u64 n_bases, u32 *nflag)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x, gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    for (u64 i = gtid; i < n_n; i += stride) {
+        const u64 p = n_positions[i];
+        if (p < n_bases) atomicOr(&nflag[p >> 5], 1u << (p & 31));
+    }
+    if (gtid == 0 && (n_bases & 31)) atomicOr(&nflag[n_bases >> 5], ~0u << (n_bases & 31));
+}
+
 // =================================================================================================
 // counting: rolling canonical k-mers (counter.h:413-429) + table insert (counter.h:459-476)
 // =================================================================================================

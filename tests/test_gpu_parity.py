@@ -1,6 +1,7 @@
 """Parity tests proper: the CUDA path through the C ABI (libpbk.so) against the oracle, the committed
 reference-binary golden vectors and -- at full BASELINE sizes -- size-independent properties.
 Run on a B200 with `pytest -m gpu`.  Bar: bit-exact (integer work)."""
+import dataclasses
 import os
 
 import numpy as np
@@ -17,6 +18,12 @@ def _reads(O, case, tmp_path):
     rd = O.Reads()
     for f in G.materialise(case, str(tmp_path)):
         rd.add_file(f)
+    return rd
+
+
+def _reads_from_arrays(O, b, o):
+    rd = O.Reads()
+    rd.add_array(b, o)
     return rd
 
 
@@ -433,3 +440,39 @@ print("ok")
     env = dict(os.environ, PBK_MAX_PUSH_BASES=str(1_700_000))
     p = subprocess.run([sys.executable, "-c", code, ROOT], capture_output=True, text=True, env=env)
     assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
+
+
+@pytest.mark.parametrize("k,partition", [(32, True), (32, "force"), (75, "force"), (21, True)])
+def test_packed_two_bit_host_input_equals_ascii_input(oracle, k, partition):
+    """Opt-in host form PBK_ENC_PACKED2 (pbk_pack_reads + pbk_push_reads_packed): the host packs 2 bits per base as it copies,
+    the H2D copy lands in the stream buffer itself.  Lower case, N (also in the last, partial word) and several pushes; the
+    result must be the oracle's, like the ASCII form's."""
+    from platanus_b_b200 import capi
+    O = oracle
+    rs = synth.make_reads(dataclasses.replace(synth.config("C1", scale=1 / 100), n_rate=0.002))
+    b, o = rs.flat()
+    b = b.copy()
+    b[::7] |= 0x20                                                     # lower case is the same base (Char2Bin looks at the low nibble)
+    b[-5:] = ord("N")
+    want = O.count(_oracle_reads_from_set(O, rs), k)
+    n = len(o) - 1
+    cut = n // 3
+    with KmerCounter(k, partition=partition) as kc:
+        for lo, hi in ((0, cut), (cut, n)):
+            bb = b[int(o[lo]):int(o[hi])]
+            words, npos = capi.pack_reads(bb)
+            assert len(words) == (len(bb) + 31) // 32
+            kc.push_reads_packed(words, o[lo:hi + 1] - o[lo], npos)
+        kc.finalize()
+        keys, counts = kc.export(1, sorted=True)
+        assert kc.stats()["launches_pack"] == 0                        # no pack kernel ran
+    want2 = O.count(_reads_from_arrays(O, b, o), k)
+    assert np.array_equal(keys, want2.keys) and np.array_equal(counts, want2.counts) and np.array_equal(kc.occ_hist, want2.occ_hist)
+    assert kc.n_instances == want2.n_instances and want2.n_instances < want.n_instances      # the extra N removed windows
+
+
+def test_pack_reads_rejects_characters_without_a_code():
+    from platanus_b_b200 import capi
+    with pytest.raises(capi.PbkError) as e:
+        capi.pack_reads(np.frombuffer(b"ACGTRACGT", dtype=np.uint8))
+    assert e.value.status == -6
