@@ -296,6 +296,8 @@ int  pbk_group_finalize(pbk_group *g, uint64_t *occ_hist, uint64_t *len_hist, ui
 /* as pbk_export, over all devices: sorted != 0 merges the shards' sorted pieces into one ascending list */
 int  pbk_group_export(pbk_group *g, uint32_t min_count, int sorted, uint64_t *keys, uint16_t *counts,
                       uint64_t capacity, uint64_t *n_out);
+/* as pbk_neighbor_flags, over all devices (OR of the shards' answers) */
+int  pbk_group_neighbor_flags(pbk_group *g, uint32_t min_count, const uint64_t *keys, uint64_t n, uint8_t *flags_out);
 
 /* ---- consumers of the table --------------------------------------
  * Occurrence of every k-mer window of a batch of sequences: ContigDivider::getOccurrenceArray
@@ -311,6 +313,15 @@ int  pbk_lookup(pbk_ctx *ctx, const uint8_t *bases, const uint64_t *read_offsets
 /* same with inputs and output in device memory (d_occ_out: n_bases u16, 8-byte aligned)              */
 int  pbk_lookup_device(pbk_ctx *ctx, const void *d_bases, const void *d_read_offsets, uint64_t n_reads,
                        uint64_t n_bases, void *d_occ_out);
+/* The eight neighbour probes BruijnGraph::makeInitialBruijnGraph makes for every k-mer of sortedKeyFP before it can tell a
+ * junction from a straight node (graph.h:337-375: 4 x findValue on the left, 4 on the right, each a random access into the
+ * host DoubleHash) -- SURVEY.md section 8f row 4 -- answered for all kept k-mers in one device pass over the resident table:
+ *   keys       n x ceil(k/32) words, e.g. what pbk_export(min_count, sorted = 1) returned (stored orientation = canonical)
+ *   flags_out  n bytes: (leftFlags << 4) | rightFlags, bit b of leftFlags = "base b + first k-1 bases" is a k-mer with count
+ *              >= min_count, bit b of rightFlags = "last k-1 bases + base b" is -- the value Junction::out gets (graph.h:398).
+ * For the other orientation of a k-mer (graph.h walks both) mirror it: left'[b] = right[3 - b], right'[b] = left[3 - b].
+ * With n_shards > 1 only neighbours this shard owns are found: OR the shards' outputs (pbk_group_neighbor_flags does).       */
+int  pbk_neighbor_flags(pbk_ctx *ctx, uint32_t min_count, const uint64_t *keys, uint64_t n, uint8_t *flags_out);
 /* Counter::pickupReadMatchedEdgeKmer (counter.h:870-910): matched_out[r] = 1 if a usable k-mer window
  * of read r (no N) is in the table, else 0 -- the reads the next assembly round keeps.               */
 int  pbk_match_reads(pbk_ctx *ctx, const uint8_t *bases, const uint64_t *read_offsets, uint64_t n_reads,

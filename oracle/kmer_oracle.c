@@ -583,6 +583,49 @@ int pbo_occurrence_array(const pbo_reads *r, unsigned k, const uint64_t *keys, c
     return PBO_OK;
 }
 
+/* The eight neighbour probes BruijnGraph::makeInitialBruijnGraph makes per k-mer (graph.h:337-375): for the k-mer as it
+ * stands in sortedKeyFP (its forward orientation = the canonical key), bit b of leftFlags says that the k-mer
+ * "b + first k-1 bases" is in the table, bit b of rightFlags that "last k-1 bases + b" is (canonical form looked up,
+ * findValue != 0); out[i] = (leftFlags << 4) | rightFlags, the layout of Junction::out (graph.h:398).  The table is the one
+ * loadKmer builds: only keys with count >= min_count count as present.  Pinned by tests/golden/flags_k*.npz
+ * (oracle/ref_iter_harness.cpp, mode flags: the reference's own KMER primitives and Counter::findValue). */
+int pbo_neighbor_flags(unsigned k, const uint64_t *keys, const uint16_t *counts, uint64_t n, uint32_t min_count, uint8_t *out)
+{
+    if (k == 0) return PBO_E_ARG;
+    unsigned words = (k + 31) / 32;
+    if (words > MAXW) return PBO_E_ARG;
+    uint64_t *buf = (uint64_t *)calloc(4 * (size_t)words, sizeof(uint64_t));
+    if (!buf) return PBO_E_NOMEM;
+    uint64_t *fwd = buf, *rev = buf + words, *nf = buf + 2 * words, *nr = buf + 3 * words;
+    for (uint64_t i = 0; i < n; ++i) {
+        out[i] = 0;
+        if (counts[i] < min_count) continue;
+        const uint64_t *key = keys + i * words;
+        memcpy(fwd, key, words * sizeof(uint64_t));
+        memset(rev, 0, words * sizeof(uint64_t));                    /* KmerBase::reverseComplement */
+        for (unsigned j = 0; j < k; ++j)
+            key_set(rev, k - 1 - j, (unsigned char)(0x3 ^ ((fwd[j / 32] >> (2 * (j % 32))) & 3)));
+        unsigned left = 0, right = 0;
+        for (unsigned char b = 0; b < 4; ++b) {
+            /* leftKmer: forward >>= 2, reverse <<= 2 (masked), base b at the top of forward / its complement at the bottom of reverse */
+            memcpy(nf, fwd, words * sizeof(uint64_t)); memcpy(nr, rev, words * sizeof(uint64_t));
+            key_shr2(nf, words); key_shl2(nr, words, k);
+            key_set(nf, k - 1, b); key_set(nr, 0, (unsigned char)(0x3 ^ b));
+            const uint64_t *c = pbo_key_cmp(nf, nr, words) <= 0 ? nf : nr;
+            if (table_find(keys, counts, n, words, c) >= (min_count ? min_count : 1)) left |= 1u << b;
+            /* rightKmer: forward <<= 2 (masked), reverse >>= 2, base b at the bottom of forward / its complement at the top of reverse */
+            memcpy(nf, fwd, words * sizeof(uint64_t)); memcpy(nr, rev, words * sizeof(uint64_t));
+            key_shl2(nf, words, k); key_shr2(nr, words);
+            key_set(nf, 0, b); key_set(nr, k - 1, (unsigned char)(0x3 ^ b));
+            c = pbo_key_cmp(nf, nr, words) <= 0 ? nf : nr;
+            if (table_find(keys, counts, n, words, c) >= (min_count ? min_count : 1)) right |= 1u << b;
+        }
+        out[i] = (uint8_t)((left << 4) | right);
+    }
+    free(buf);
+    return PBO_OK;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* histogram statistics                                                                       */
 /* ------------------------------------------------------------------------------------------ */

@@ -71,6 +71,7 @@ def lib():
         L.pbo_count_contigs.argtypes = [C.POINTER(_Reads), C.c_uint, C.c_void_p, C.c_uint64, C.POINTER(_Result)]
         L.pbo_match_reads.argtypes = [C.POINTER(_Reads), C.c_uint, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.pbo_occurrence_array.argtypes = [C.POINTER(_Reads), C.c_uint, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.pbo_neighbor_flags.argtypes = [C.c_uint, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
         L.pbo_left_local_min.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         L.pbo_left_local_min.restype = C.c_uint64
         L.pbo_dist_average.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]
@@ -200,6 +201,19 @@ def occurrence_array(seqs: Reads, k: int, keys: np.ndarray, counts: np.ndarray) 
                                     len(counts), out.ctypes.data_as(C.c_void_p))
     if rc:
         raise OracleError(rc, "pbo_occurrence_array")
+    return out
+
+
+def neighbor_flags(k: int, keys: np.ndarray, counts: np.ndarray, min_count: int = 1) -> np.ndarray:
+    """The eight findValue probes of makeInitialBruijnGraph (graph.h:337-375) per key of a sorted table: u8 per key,
+    (leftFlags << 4) | rightFlags; keys below min_count are not in the table."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    counts = np.ascontiguousarray(counts, dtype=np.uint16)
+    out = np.zeros(len(counts), np.uint8)
+    rc = lib().pbo_neighbor_flags(k, keys.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p), len(counts), int(min_count),
+                                  out.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise OracleError(rc, "pbo_neighbor_flags")
     return out
 
 

@@ -12,6 +12,10 @@
 //   usage: ref_iter_harness pickup|count TABLE.bin READS.txt NUM_THREAD OUT
 //   pickup -> OUT: the surviving reads, one per line, per temp file in order (file 0 first)
 //   count  -> OUT: the raw kmerFP records (key words + u16), then stdout: "maxOccurrence <n>"
+//   flags  : the eight neighbour probes BruijnGraph::makeInitialBruijnGraph makes per k-mer of sortedKeyFP (graph.h:337-375), with
+//            the reference's own KMER primitives and Counter::findValue on a table loaded by readOccurrenceTableBinary
+//            usage: ref_iter_harness flags TABLE.bin - 1 OUT   (OUT: per key in ascending order, key words + one byte
+//            (leftFlags << 4) | rightFlags -- the value Junction::out gets, graph.h:398)
 // Built with g++ -fno-access-control (kmerLength etc. are private).
 #include "counter.h"
 
@@ -70,6 +74,51 @@ static int run(const std::string &mode, const std::string &bin, const std::strin
 }
 
 template <typename KMER>
+static int run_flags(const std::string &bin, const std::string &out)
+{
+    Counter<KMER> counter;
+    counter.readOccurrenceTableBinary(bin);
+    const unsigned k = counter.getKmerLength();
+    const unsigned long long mask = k >= 32 ? ~static_cast<unsigned long long>(0) : ~(~static_cast<unsigned long long>(0) << (2 * k));
+    std::vector<typename KMER::keyType> keys;
+    for (auto it = counter.occurrenceTable.begin(), end = counter.occurrenceTable.end(); it != end; ++it)
+        if (it->second != 0) keys.push_back(it->first);
+    std::sort(keys.begin(), keys.end());                                  // what sortedKeyFromKmerFile hands to the graph builder
+    FILE *fp = fopen(out.c_str(), "wb");
+    KMER startKmer(k), leftKmer(k), rightKmer(k);
+    for (size_t i = 0; i < keys.size(); ++i) {
+        startKmer.forward = keys[i];
+        startKmer.reverseComplement();
+        // graph.h:340-357
+        leftKmer = startKmer;
+        leftKmer.forward >>= 2;
+        leftKmer.reverse <<= 2;
+        leftKmer.maskReverse(mask);
+        unsigned char leftFlags = 0, rightFlags = 0;
+        for (unsigned char base = 0; base < 4; ++base) {
+            leftKmer.setForward(leftKmer.kmerLength - 1, base);
+            leftKmer.setReverse(0, 0x3 ^ base);
+            if (counter.findValue(std::min(leftKmer.forward, leftKmer.reverse)) != 0) leftFlags |= 1 << base;
+        }
+        // graph.h:360-375
+        rightKmer = startKmer;
+        rightKmer.forward <<= 2;
+        rightKmer.maskForward(mask);
+        rightKmer.reverse >>= 2;
+        for (unsigned char base = 0; base < 4; ++base) {
+            rightKmer.setForward(0, base);
+            rightKmer.setReverse(rightKmer.kmerLength - 1, 0x3 ^ base);
+            if (counter.findValue(std::min(rightKmer.forward, rightKmer.reverse)) != 0) rightFlags |= 1 << base;
+        }
+        startKmer.writeKey(fp, keys[i]);
+        const unsigned char o = (leftFlags << 4) | rightFlags;
+        fwrite(&o, 1, 1, fp);
+    }
+    fclose(fp);
+    return 0;
+}
+
+template <typename KMER>
 static int run_contig(unsigned long long k, const std::string &fa, unsigned long long minOccurrence, const std::string &out)
 {
     platanus::Contig contig;
@@ -106,6 +155,14 @@ int main(int argc, char **argv)
     platanus::setGlobalTmpFileDir(".");
     omp_set_num_threads(numThread);
     const unsigned long long k = platanus::getKmerLengthFromBinary(bin);
+    if (mode == "flags") {
+        if (k <= 32) return run_flags<Kmer31>(bin, out);
+        if (k <= 64) return run_flags<KmerN<Binstr63> >(bin, out);
+        if (k <= 96) return run_flags<KmerN<Binstr95> >(bin, out);
+        if (k <= 128) return run_flags<KmerN<Binstr127> >(bin, out);
+        if (k <= 160) return run_flags<KmerN<Binstr159> >(bin, out);
+        return run_flags<KmerN<binstr_t> >(bin, out);
+    }
     if (k <= 32) return run<Kmer31>(mode, bin, reads, numThread, out);
     if (k <= 64) return run<KmerN<Binstr63> >(mode, bin, reads, numThread, out);
     if (k <= 96) return run<KmerN<Binstr95> >(mode, bin, reads, numThread, out);

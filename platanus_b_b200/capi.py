@@ -45,7 +45,7 @@ SYMBOLS = [
     "pbk_keyx_pull_partition", "pbk_keyx_pull_partition_device", "pbk_keyx_pull_insert", "pbk_keyx_pull_release",
     "pbk_device_count", "pbk_group_create", "pbk_group_destroy", "pbk_group_size", "pbk_group_member", "pbk_group_last_error",
     "pbk_group_reset", "pbk_group_push_reads", "pbk_group_finalize", "pbk_group_export",
-    "pbk_pack_reads", "pbk_push_reads_packed",
+    "pbk_pack_reads", "pbk_push_reads_packed", "pbk_neighbor_flags", "pbk_group_neighbor_flags",
 ]
 
 
@@ -117,6 +117,8 @@ def load_library(build_if_missing: bool = True):
     L.pbk_push_reads_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64]
     L.pbk_pack_reads.argtypes = [vp, C.c_uint64, u64p, u64p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.pbk_push_reads_packed.argtypes = [vp, u64p, u64p, C.c_uint64, u64p, C.c_uint64]
+    L.pbk_neighbor_flags.argtypes = [vp, C.c_uint32, u64p, C.c_uint64, vp]
+    L.pbk_group_neighbor_flags.argtypes = [vp, C.c_uint32, u64p, C.c_uint64, vp]
     L.pbk_finalize.argtypes = [vp, u64p, u64p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.pbk_export.argtypes = [vp, C.c_uint32, C.c_int, u64p, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.pbk_get_stats.argtypes = [vp, C.POINTER(PbkStats)]
@@ -253,6 +255,13 @@ class KmerGroup:
         if n.value:
             self._check(self._L.pbk_group_export(self._g, min_count, int(sorted), _ptr(keys), _ptr(counts), n.value, C.byref(n)), "pbk_group_export")
         return keys, counts
+
+    def neighbor_flags(self, keys: np.ndarray, min_count: int = 1) -> np.ndarray:
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        n = keys.shape[0] if keys.ndim == 2 else len(keys) // self.words
+        out = np.zeros(n, np.uint8)
+        self._check(self._L.pbk_group_neighbor_flags(self._g, int(min_count), _ptr(keys), n, _ptr(out)), "pbk_group_neighbor_flags")
+        return out
 
     def reset(self, k: int = 0):
         self._check(self._L.pbk_group_reset(self._g, k), "pbk_group_reset")
@@ -437,6 +446,14 @@ class KmerCounter:
             np_p, npo_p = _ptr(n_pos), _ptr(n_pos_offsets)
         self._check(self._L.pbk_lookup(self._ctx, _ptr(bases), _ptr(offsets), len(offsets) - 1, encoding, np_p, npo_p, _ptr(out)),
                     "pbk_lookup")
+        return out
+
+    def neighbor_flags(self, keys: np.ndarray, min_count: int = 1) -> np.ndarray:
+        """makeInitialBruijnGraph's eight findValue probes per k-mer (graph.h:337-375): u8 per key, (leftFlags << 4) | rightFlags."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        n = keys.shape[0] if keys.ndim == 2 else len(keys) // self.words
+        out = np.zeros(n, np.uint8)
+        self._check(self._L.pbk_neighbor_flags(self._ctx, int(min_count), _ptr(keys), n, _ptr(out)), "pbk_neighbor_flags")
         return out
 
     def match_reads(self, bases: np.ndarray, offsets: np.ndarray) -> np.ndarray:

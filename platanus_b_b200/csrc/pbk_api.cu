@@ -1413,6 +1413,37 @@ int pbk_lookup_device(pbk_ctx *c, const void *d_bases, const void *d_read_offset
                          PBK_ENC_ASCII, nullptr, nullptr, nullptr, (uint16_t *)d_occ_out);
 }
 
+// the graph builder's eight findValue probes per kept k-mer, for all of them at once
+int pbk_neighbor_flags(pbk_ctx *c, uint32_t min_count, const uint64_t *keys, uint64_t n, uint8_t *flags_out)
+{
+    if (!c) return PBK_E_ARG;
+    if (n == 0) return PBK_OK;
+    if (!keys || !flags_out) return fail(c, PBK_E_ARG, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    TRY(settle(c));
+    memset(flags_out, 0, n);
+    if (!c->table.slots) return PBK_OK;
+    const size_t kb = (size_t)n * c->W * 8;
+    u64 *d_keys = nullptr; uint8_t *d_out = nullptr;
+    TRY(dev_alloc(c, (void **)&d_keys, kb));
+    int rc = dev_alloc(c, (void **)&d_out, n);
+    if (rc == PBK_OK) {
+        cudaError_t e = cudaMemcpyAsync(d_keys, keys, kb, cudaMemcpyHostToDevice, c->s_compute);
+        c->h2d_bytes += kb;
+        if (e == cudaSuccess) {
+            { Span sp(c, LC_OTHER); launch_neighbor_flags(d_keys, n, (int)c->k, c->table, min_count, d_out, c->sm_count, c->s_compute); }
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(flags_out, d_out, n, cudaMemcpyDeviceToHost, c->s_compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_compute);
+        c->d2h_bytes += n;
+        if (e != cudaSuccess) rc = fail(c, PBK_E_CUDA, "neighbor flags: %s", cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(c->s_compute);
+    dev_free(c, d_keys, kb); dev_free(c, d_out, n);
+    return rc;
+}
+
 // ---- key exchange (k <= 32) ----------------------------------------------------------------------
 
 int pbk_keyx_plan(pbk_ctx *c, uint64_t max_windows_any_rank, pbk_keyx_layout *out)

@@ -88,7 +88,13 @@ int exchange_records(pbk_group *g)
             for (uint32_t d = 0; d < dst; ++d) before += cnt[src][d];
             void *tmp = nullptr;
             if (cudaMalloc(&tmp, m * rec_bytes) != cudaSuccess) { cudaGetLastError(); return PBK_E_NOMEM; }
-            cudaError_t e = cudaMemcpyPeer(tmp, g->device[dst], (const char *)g->d_rec[src] + before * rec_bytes, g->device[src], m * rec_bytes);
+            // (cudaMemcpyPeer itself runs on the legacy default stream, which the contexts' non-blocking streams do not wait
+            //  for: the copy gets its own stream and the host waits for it before the insert is queued)
+            cudaStream_t cs = nullptr;
+            cudaError_t e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaMemcpyPeerAsync(tmp, g->device[dst], (const char *)g->d_rec[src] + before * rec_bytes, g->device[src], m * rec_bytes, cs);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+            if (cs) cudaStreamDestroy(cs);
             int r = e == cudaSuccess ? pbk_shard_insert_device(g->ctx[dst], tmp, m) : PBK_E_CUDA;
             cudaFree(tmp);
             if (r != PBK_OK) return r;
@@ -307,6 +313,21 @@ int pbk_group_export(pbk_group *g, uint32_t min_count, int sorted, uint64_t *key
         counts[o] = cbuf[at[best]];
         ++at[best];
     }
+    return PBK_OK;
+}
+
+// the shards answer for the neighbours they own: the flags of a key are the OR over the devices
+int pbk_group_neighbor_flags(pbk_group *g, uint32_t min_count, const uint64_t *keys, uint64_t n, uint8_t *flags_out)
+{
+    if (!g) return PBK_E_ARG;
+    if (n == 0) return PBK_OK;
+    if (!keys || !flags_out) return gfail(g, PBK_E_ARG, "NULL argument");
+    const size_t m = g->ctx.size();
+    std::vector<std::vector<uint8_t>> part(m, std::vector<uint8_t>(n, 0));
+    const int rc = for_all(g, [&](size_t i) { return pbk_neighbor_flags(g->ctx[i], min_count, keys, n, part[i].data()); });
+    if (rc != PBK_OK) return rc;
+    memset(flags_out, 0, n);
+    for (size_t i = 0; i < m; ++i) for (uint64_t j = 0; j < n; ++j) flags_out[j] |= part[i][j];
     return PBK_OK;
 }
 

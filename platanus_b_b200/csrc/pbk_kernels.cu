@@ -110,6 +110,13 @@ void launch_override_records(const u64 *records, u64 n, TableView table, Counter
         (override_records_kernel<W><<<grid, 256, 0, st>>>(records, n, Table<W>(table.slots, table.cap), ctr, overflow_keys, overflow_cap)));
 }
 
+void launch_neighbor_flags(const u64 *keys, u64 n, int k, TableView table, u32 min_count, uint8_t *out, int sm_count, cudaStream_t st)
+{
+    if (n == 0) return;
+    const int grid = grid_for(n, 256, sm_count, 8);
+    PBK_DISPATCH_W(table.words, (neighbor_flags_kernel<W><<<grid, 256, 0, st>>>(keys, n, k, Table<W>(table.slots, table.cap), min_count, out)));
+}
+
 void launch_read_match(const u64 *offsets, u64 n_reads, const uint16_t *occ, int k, uint8_t *matched, int sm_count, cudaStream_t st)
 {
     if (n_reads == 0) return;

@@ -48,6 +48,8 @@ void launch_contig_max(const u64 *stream, const u32 *nflag, const u32 *rflag, u6
 // SET the count of n (key words..., value) records (insert those that are absent); value 0 = skip
 void launch_override_records(const u64 *records, u64 n, TableView table, Counters *ctr, u64 *overflow_keys, u64 overflow_cap,
                              int sm_count, cudaStream_t st);
+// out[i] = (leftFlags << 4) | rightFlags of key i: which of its eight neighbours are in the table with count >= min_count
+void launch_neighbor_flags(const u64 *keys, u64 n, int k, TableView table, u32 min_count, uint8_t *out, int sm_count, cudaStream_t st);
 // matched[r] = any window of read r found (occ: launch_lookup's output)
 void launch_read_match(const u64 *offsets, u64 n_reads, const uint16_t *occ, int k, uint8_t *matched, int sm_count, cudaStream_t st);
 // insert n (key words..., weight) records; a record has W + 1 words when weighted, W otherwise.

@@ -432,6 +432,66 @@ contig_max_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag,
     if ((threadIdx.x & 31) == 0 && newk) atomicAdd(&ctr->new_keys, (u64)newk);
 }
 
+// The eight neighbour probes BruijnGraph::makeInitialBruijnGraph makes per k-mer of sortedKeyFP (graph.h:337-375; SURVEY.md
+// section 8f row 4): for key i in its stored (canonical = forward) orientation, bit b of the high nibble says that the k-mer
+// "b + first k-1 bases" is in the table, bit b of the low nibble that "last k-1 bases + b" is -- each looked up in canonical
+// form with a count >= min_count (the table loadKmer would build holds only those).  out[i] = (leftFlags << 4) | rightFlags,
+// the layout of Junction::out (graph.h:398).  One thread per key, eight independent read-only probes.
+template <int W>
+__global__ void __launch_bounds__(256)
+neighbor_flags_kernel(const u64 *__restrict__ keys, u64 n, int k, Table<W> table, u32 min_count, uint8_t *__restrict__ out)
+{
+    const int top_w = (k - 1) >> 5, top_sh = 2 * ((k - 1) & 31);       // word and shift of key position k-1 (the leftmost base)
+    const u64 top_mask = (k & 31) ? ((1ull << (2 * (k & 31))) - 1ull) : ~0ull;
+    const int s = 2 * (32 * W - k);
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    if (min_count == 0) min_count = 1;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        u64 fwd[W], rev[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) fwd[j] = keys[i * W + j];
+        {
+            u64 y[W + 1];
+#pragma unroll
+            for (int j = 0; j < W; ++j) y[j] = pair_reverse64(~fwd[W - 1 - j]);
+            y[W] = 0;
+#pragma unroll
+            for (int j = 0; j < W; ++j) rev[j] = s ? ((y[j] >> s) | (y[j + 1] << (64 - s))) : y[j];
+        }
+        // the k-1 shared bases, shifted into place once per side
+        u64 lf[W], lr[W], rf[W], rr[W];
+#pragma unroll
+        for (int j = 0; j < W - 1; ++j) { lf[j] = (fwd[j] >> 2) | (fwd[j + 1] << 62); rr[j] = (rev[j] >> 2) | (rev[j + 1] << 62); }
+        lf[W - 1] = fwd[W - 1] >> 2; rr[W - 1] = rev[W - 1] >> 2;
+#pragma unroll
+        for (int j = W - 1; j > 0; --j) { lr[j] = (rev[j] << 2) | (rev[j - 1] >> 62); rf[j] = (fwd[j] << 2) | (fwd[j - 1] >> 62); }
+        lr[0] = rev[0] << 2; rf[0] = fwd[0] << 2;
+        lr[W - 1] &= top_mask; rf[W - 1] &= top_mask;
+        u32 left = 0, right = 0;
+#pragma unroll
+        for (u32 b = 0; b < 4; ++b) {
+            u64 a[W], c[W];
+            // left neighbour: b becomes the leftmost base of forward, its complement the rightmost of reverse
+#pragma unroll
+            for (int j = 0; j < W; ++j) { a[j] = lf[j]; c[j] = lr[j]; }
+            a[top_w] |= (u64)b << top_sh; c[0] |= (u64)(3u - b);
+            {
+                const u64 *key = key_less<W>(c, a) ? c : a;
+                if (table.find(key, hash_key<W>(key)) >= min_count) left |= 1u << b;
+            }
+            // right neighbour: b becomes the rightmost base of forward, its complement the leftmost of reverse
+#pragma unroll
+            for (int j = 0; j < W; ++j) { a[j] = rf[j]; c[j] = rr[j]; }
+            a[0] |= (u64)b; c[top_w] |= (u64)(3u - b) << top_sh;
+            {
+                const u64 *key = key_less<W>(c, a) ? c : a;
+                if (table.find(key, hash_key<W>(key)) >= min_count) right |= 1u << b;
+            }
+        }
+        out[i] = (uint8_t)((left << 4) | right);
+    }
+}
+
 // Seeded entries (makeKmerReadDistributionConsideringPreviousGraph, counter.h:663-750): a k-mer that was in the table
 // before the reads were counted keeps its seeded value -- the reference never counts read windows that hit the table
 // (divideKmerUsedMakingPreviousContig, counter.h:828-861) and dumps the table as it was (counter.h:695-705).  Counting

@@ -290,6 +290,17 @@ public:
         if (n) check(pbk_export(ctx_, (uint32_t)minOccurrence, sorted ? 1 : 0, keptKeys_.data(), keptCounts_.data(), n, &n), "pbk_export");
         keptMin_ = minOccurrence; keptValid_ = true;
     }
+    // ---- graph.h:337-375: the eight findValue probes makeInitialBruijnGraph makes per k-mer of sortedKeyFP, for all kept k-mers
+    //      (the list of the last exportKmers / sortedKeyFromKmerFile) in one device pass: flags[i] = (leftFlags << 4) | rightFlags
+    std::vector<uint8_t> neighborFlags()
+    {
+        if (!keptValid_) throw GPUError("neighborFlags before sortedKeyFromKmerFile / exportKmers");
+        std::vector<uint8_t> flags(keptCounts_.size(), 0);
+        if (flags.empty()) return flags;
+        if (group_) check(pbk_group_neighbor_flags(group_, (uint32_t)keptMin_, keptKeys_.data(), flags.size(), flags.data()), "pbk_group_neighbor_flags");
+        else check(pbk_neighbor_flags(ctx_, (uint32_t)keptMin_, keptKeys_.data(), flags.size(), flags.data()), "pbk_neighbor_flags");
+        return flags;
+    }
     const std::vector<uint64_t> &keptKeys() const { return keptKeys_; }
     const std::vector<uint16_t> &keptCounts() const { return keptCounts_; }
 

@@ -56,4 +56,4 @@ static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, u
 static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 1; return cudaSuccess; }
 static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
-static inline cudaError_t cudaMemcpyPeer(void *d, int, const void *s, int, size_t n) { if (n) memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyPeerAsync(void *d, int, const void *s, int, size_t n, cudaStream_t) { if (n) memmove(d, s, n); return cudaSuccess; }

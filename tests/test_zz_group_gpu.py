@@ -46,6 +46,11 @@ def test_group_matches_the_unsharded_oracle(oracle, k, n_members, n_pushes):
             sel = want.counts >= 3
             order = np.lexsort(tuple(ku[:, w] for w in range(ku.shape[1])))
             assert np.array_equal(ku[order], want.keys[sel]) and np.array_equal(cu[order], want.counts[sel])
+        # graph hand-off (pbk_group_neighbor_flags): every shard answers for the neighbours it owns, the group ORs them
+        cutoff = O.coverage_cutoff(want.occ_hist, want.max_occ)
+        kk, _ = g.export(cutoff, sorted=True)
+        sel = want.counts >= cutoff
+        assert np.array_equal(g.neighbor_flags(kk, cutoff), O.neighbor_flags(k, want.keys, want.counts, cutoff)[sel])
         sizes = [g.member_stats(i)["n_distinct"] for i in range(n_members)]
         assert sum(sizes) == want.n_distinct and max(sizes) < 1.25 * (sum(sizes) / n_members) + 64
 

@@ -175,3 +175,44 @@ def test_contig_table_matches_the_reference(oracle, path):
             assert np.array_equal(keys, g["keys"]) and np.array_equal(counts, g["counts"])
             assert kc.max_occurrence == int(g["max_occ"]) and np.array_equal(kc.occ_hist, want.occ_hist)
             assert kc.n_instances == 0
+
+
+# ---- neighbour-presence flags for the graph builder (pbk_neighbor_flags) -------------------------------
+import glob as _glob
+
+FLAG_CASES = sorted(_glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "flags_k*.npz")))
+
+
+@pytest.mark.parametrize("path", FLAG_CASES, ids=lambda p: os.path.basename(p)[:-4])
+def test_neighbor_flags_match_the_reference_probes(path):
+    """table loaded from the golden (key, count) list; the device answers makeInitialBruijnGraph's eight findValue probes per key
+    (graph.h:337-375) exactly like the reference's own primitives did"""
+    g = np.load(path, allow_pickle=False)
+    k = int(g["k"])
+    with KmerCounter(k) as kc:
+        kc.load_entries(g["keys"], g["counts"])
+        kc.finalize()
+        assert np.array_equal(kc.neighbor_flags(g["keys"], 1), g["flags"])
+
+
+@pytest.mark.parametrize("k", [32, 75])
+def test_neighbor_flags_after_counting_match_the_oracle(oracle, k):
+    """the real hand-off: count reads, cutoff, sorted export, flags of the kept k-mers against the resident table (which also
+    holds the k-mers below the cutoff: they must not count as neighbours)"""
+    O = oracle
+    rs = synth.make_reads(synth.config("C1", scale=1 / 100))
+    b, o = rs.flat()
+    rd = O.Reads()
+    rd.add_array(b, o)
+    want = O.count(rd, k)
+    with KmerCounter(k) as kc:
+        kc.push_reads(b, o)
+        kc.finalize()
+        cutoff = kc.coverage_cutoff()
+        keys, counts = kc.export(cutoff, sorted=True)
+        flags = kc.neighbor_flags(keys, cutoff)
+    sel = want.counts >= cutoff
+    assert np.array_equal(keys, want.keys[sel])
+    assert np.array_equal(flags, O.neighbor_flags(k, want.keys, want.counts, cutoff)[sel])
+    # a 100x genome: nearly all kept k-mers are interior nodes of a path (exactly one neighbour on each side)
+    assert (flags != 0).mean() > 0.99
