@@ -1053,11 +1053,24 @@ __device__ __forceinline__ void passb1_round(const u64 *__restrict__ src, u32 n_
 
     u64 h[PASSB1_KPT], old[PASSB1_KPT];
     u32 valid = 0, rem = 0;
+    if constexpr (FULL && !STAGED) {
+        // a full warp slice: four 16-byte loads per lane (512 contiguous bytes per warp request) instead of eight 8-byte ones --
+        // half as many requests for the same keys, which is what counts when the bucket store is a peer's, behind NVLink
+        // (the key exchange's pull form); which lane inserts which key is irrelevant.  Slices start 16-byte aligned (even seg_cap).
+        static_assert(PASSB1_KPT % 2 == 0, "pairs of keys");
 #pragma unroll
-    for (int q = 0; q < PASSB1_KPT; ++q) {
-        const u32 i = (u32)q * wsize + lane;
-        if (FULL || i < n_valid) { h[q] = STAGED ? src[i] : ld_stream_u64(src + i); valid |= 1u << q; }
-        else h[q] = 0;
+        for (int p = 0; p < PASSB1_KPT / 2; ++p) {
+            const ulonglong2 v = ld_stream_u64x2(src + 2 * ((u32)p * wsize + lane));
+            h[2 * p] = v.x; h[2 * p + 1] = v.y;
+        }
+        valid = (1u << PASSB1_KPT) - 1u;
+    } else {
+#pragma unroll
+        for (int q = 0; q < PASSB1_KPT; ++q) {
+            const u32 i = (u32)q * wsize + lane;
+            if (FULL || i < n_valid) { h[q] = STAGED ? src[i] : ld_stream_u64(src + i); valid |= 1u << q; }
+            else h[q] = 0;
+        }
     }
 #ifdef PBK_EXPERIMENT
     if (opts & 2u) {                     // experiment: no table traffic at all
