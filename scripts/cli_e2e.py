@@ -28,13 +28,20 @@ out = {"workload": f"C1 x {scale:g}: {rs.n_reads} reads x {rs.read_len} bp, k={k
 try:
     files = synth.write_fastq(rs, os.path.join(tmp, "r_1.fq"), os.path.join(tmp, "r_2.fq"))
     out["fastq_bytes"] = sum(os.path.getsize(f) for f in files)
+    # --gpus 1,2: the same program on one GPU and on a pbk_group of two (PBK_NUM_GPUS; the library exchanges the keys itself)
+    gpu_counts = [int(x) for x in sys.argv[sys.argv.index("--gpus") + 1].split(",")] if "--gpus" in sys.argv else [1]
     walls = []
-    for rep in range(3):
-        t0 = time.time()
-        p = subprocess.run([cli, "assemble", "-kmer_occ_only", "-k", str(k), "-t", "2", "-m", "16", "-tmp", tmp, "-o",
-                            os.path.join(tmp, "gpu"), "-f", *files], capture_output=True, text=True)
-        walls.append(time.time() - t0)
-        assert p.returncode == 0, p.stderr
+    for n_gpus in gpu_counts:
+        w = []
+        for rep in range(3):
+            t0 = time.time()
+            p = subprocess.run([cli, "assemble", "-kmer_occ_only", "-k", str(k), "-t", str(min(16, os.cpu_count() or 2)), "-m", "16", "-tmp", tmp, "-o",
+                                os.path.join(tmp, "gpu"), "-f", *files], capture_output=True, text=True,
+                               env=dict(os.environ, PBK_NUM_GPUS=str(n_gpus), PBK_TIMING="1"))
+            w.append(time.time() - t0)
+            assert p.returncode == 0, p.stderr
+        out[f"pbk_assemble_wall_s_{n_gpus}gpu"] = w
+        walls = w if n_gpus == gpu_counts[0] else walls
     out["pbk_assemble_wall_s"] = walls
     out["pbk_assemble_stderr_tail"] = p.stderr.strip().splitlines()[-6:]
     ours = O.read_bin(os.path.join(tmp, "gpu_kmer_occ.bin"))
