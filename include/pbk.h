@@ -269,6 +269,10 @@ int  pbk_keyx_pull_partition(pbk_ctx *ctx, const uint8_t *bases, const uint64_t 
 int  pbk_keyx_pull_partition_device(pbk_ctx *ctx, const void *d_bases, const void *d_read_offsets, uint64_t n_reads,
                                     uint64_t n_bases, int async);
 int  pbk_keyx_pull_insert(pbk_ctx *ctx);
+/* queues a copy of two u64 counters -- records staged since pbk_reset, keys waiting on the overflow list (a full segment puts
+ * them there) -- into 16 bytes of device memory of the caller: summed over the ranks by the barrier's own collective, a
+ * non-zero sum tells every rank that the record route has to run, without a collective and a host round trip of its own */
+int  pbk_keyx_staged_count_device(pbk_ctx *ctx, void *d_two_u64);
 /* frees the store and drops every mapping (to plan a larger layout; every peer must release before anybody partitions again) */
 int  pbk_keyx_pull_release(pbk_ctx *ctx);
 

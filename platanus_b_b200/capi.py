@@ -42,7 +42,7 @@ SYMBOLS = [
     "pbk_lookup", "pbk_lookup_device", "pbk_load_entries", "pbk_read_kmer_occ_bin", "pbk_free",
     "pbk_match_reads", "pbk_seed_entries", "pbk_stream_signal", "pbk_stream_wait", "pbk_keyx_partition_device_async",
     "pbk_push_contigs", "pbk_keyx_pull_setup", "pbk_keyx_pull_handle", "pbk_keyx_pull_connect_ipc", "pbk_keyx_pull_connect_local",
-    "pbk_keyx_pull_partition", "pbk_keyx_pull_partition_device", "pbk_keyx_pull_insert", "pbk_keyx_pull_release",
+    "pbk_keyx_pull_partition", "pbk_keyx_pull_partition_device", "pbk_keyx_pull_insert", "pbk_keyx_pull_release", "pbk_keyx_staged_count_device",
     "pbk_device_count", "pbk_group_create", "pbk_group_destroy", "pbk_group_size", "pbk_group_member", "pbk_group_last_error",
     "pbk_group_reset", "pbk_group_push_reads", "pbk_group_finalize", "pbk_group_export",
     "pbk_pack_reads", "pbk_push_reads_packed", "pbk_neighbor_flags", "pbk_group_neighbor_flags",
@@ -153,6 +153,7 @@ def load_library(build_if_missing: bool = True):
     L.pbk_keyx_pull_partition_device.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int]
     L.pbk_keyx_pull_insert.argtypes = [vp]
     L.pbk_keyx_pull_release.argtypes = [vp]
+    L.pbk_keyx_staged_count_device.argtypes = [vp, vp]
     L.pbk_device_count.restype = C.c_int
     L.pbk_group_create.argtypes = [C.POINTER(vp), C.POINTER(PbkConfig), vp, C.c_uint32]
     L.pbk_group_destroy.argtypes = [vp]; L.pbk_group_destroy.restype = None
@@ -572,6 +573,9 @@ class KmerCounter:
     def keyx_pull_partition_device(self, d_bases_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int, asynchronous: bool = False):
         self._check(self._L.pbk_keyx_pull_partition_device(self._ctx, C.c_void_p(d_bases_ptr), C.c_void_p(d_offsets_ptr), n_reads, n_bases,
                                                            int(asynchronous)), "pbk_keyx_pull_partition_device")
+
+    def keyx_staged_count_device(self, d_count_ptr: int):
+        self._check(self._L.pbk_keyx_staged_count_device(self._ctx, C.c_void_p(d_count_ptr)), "pbk_keyx_staged_count_device")
 
     def keyx_pull_insert(self):
         self._check(self._L.pbk_keyx_pull_insert(self._ctx), "pbk_keyx_pull_insert")

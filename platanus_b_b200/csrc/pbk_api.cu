@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -84,6 +85,7 @@ struct pbk_ctx {
     PartitionPlan keyx_plan{}; u64 keyx_max_windows = 0;
     u64 keyx_last_total = 0;            // keys received by the last host-sized insert: sizes the table for the queued ones
     bool counters_pending = false;      // a queued key-exchange insert has not had its counters read back yet (settle())
+    u64 pending_new = 0;                // upper bound on the new keys of the inserts queued since the last read-back
     u64 *keyx_send = nullptr, *keyx_cursors = nullptr;
     bool keyx_async = false;            // this partition call returns without reading the counters back
     // pull form of the key exchange (pbk_keyx_pull_*): this context's own owner-major bucket store, double-buffered, in ONE
@@ -318,6 +320,7 @@ int settle(pbk_ctx *c)
 {
     if (!c->counters_pending) return PBK_OK;
     c->counters_pending = false;
+    c->pending_new = 0;
     TRY(read_counters(c));
     return drain_overflow(c);
 }
@@ -1053,6 +1056,7 @@ int pbk_reset(pbk_ctx *c, uint32_t k)
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->s_compute));
     c->counters_pending = false;                       // whatever was queued is about to be forgotten
+    c->pending_new = 0;
     const int W = (int)((k + 31) / 32);
     if (W != c->W) {                                   // slot size changes: tables are re-created lazily
         if (c->table.slots) dev_free(c, c->table.slots, c->table.bytes());
@@ -1554,10 +1558,16 @@ static int keyx_insert_common(pbk_ctx *c, const KeyxSources &srcs)
     static const bool always_sync = getenv("PBK_KEYX_SYNC") != nullptr;
     if (c->ratio_known && c->keyx_last_total && c->table.slots && c->pipeline_enabled && !always_sync) {
         const u64 expect = (u64)(c->keyx_last_total * std::min(1.0, c->new_ratio * 1.15)) + 65536;
-        TRY(settle(c));                                 // c->occupied up to date before the growth decision
+        // The host's view of the table (c->occupied) is stale while launches are queued (a Pass A that returned without its
+        // read-back, earlier inserts of this step).  Reading the counters back costs a stream synchronisation in the middle
+        // of the step, so it only happens if the table might NOT have room even for everything queued so far.
+        if (c->counters_pending && (double)(c->occupied + c->pending_new + expect) > max_load(c) * (double)c->table.capacity())
+            TRY(settle(c));
+        if (!c->counters_pending) c->pending_new = 0;
         TRY(maybe_clamp(c, c->keyx_last_total + c->keyx_last_total / 8));
-        if ((double)(c->occupied + expect) > max_load(c) * (double)c->table.capacity())
+        if ((double)(c->occupied + c->pending_new + expect) > max_load(c) * (double)c->table.capacity())
             TRY(grow_table(c, &c->table, c->occupied, (u64)((c->occupied + expect) / max_load(c)) + 1));
+        c->pending_new += expect;
         TRY(ensure_overflow_for_batch(c, c->keyx_last_total + c->keyx_last_total / 8));
         {
             Span sp(c, LC_INSERT);
@@ -1759,6 +1769,21 @@ int pbk_keyx_pull_partition_device(pbk_ctx *c, const void *d_bases, const void *
     TRY(pull_bind(c));
     return (async ? pbk_keyx_partition_device_async : pbk_keyx_partition_device)(c, d_bases, d_read_offsets, n_reads, n_bases,
                                                                                  pull_keys(c), pull_cursors(c));
+}
+
+// Queue (on the context's stream) a copy of the number of records this context has staged since pbk_reset -- keys that found
+// their segment full in Pass A -- into an 8-byte device word of the caller.  Summed over the ranks by the collective that also
+// serves as the barrier between Pass A and Pass B, it tells every rank whether the record route has to run at all, without a
+// collective and a host round trip of its own.
+int pbk_keyx_staged_count_device(pbk_ctx *c, void *d_count_u64)
+{
+    if (!c || !d_count_u64) return PBK_E_ARG;
+    CK(cudaSetDevice(c->device));
+    // two consecutive counters: records already in the staging table, and keys still on the overflow list (a full segment in
+    // Pass A puts them there; the host moves them to the staging table when it next reads the counters back)
+    static_assert(offsetof(Counters, overflow_n) == offsetof(Counters, new_keys_remote) + 8, "counter layout");
+    CK(cudaMemcpyAsync(d_count_u64, &c->d_ctr->new_keys_remote, 16, cudaMemcpyDeviceToDevice, c->s_compute));
+    return PBK_OK;
 }
 
 int pbk_keyx_pull_insert(pbk_ctx *c)

@@ -206,22 +206,29 @@ class KeyPull:
         flag = torch.tensor([0 if self.error else 1], dtype=torch.int32, device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)     # also the barrier: every store is mapped before anybody reads
         self.ok = bool(int(flag.item()))
-        self._token = torch.zeros(1, dtype=torch.int32, device=device)
+        self._token = torch.zeros(2, dtype=torch.int64, device=device)
         self.record_bufs: dict = {}
 
     def step(self, partition, sync, caller_stream=None) -> int:
-        """partition() runs pbk_keyx_pull_partition* for this rank's batch.  Returns the bytes this rank's peers read from it."""
+        """partition() runs pbk_keyx_pull_partition* for this rank's batch.  Returns the bytes this rank's peers read from it.
+        The barrier between Pass A and Pass B is ONE all-reduce of two 8-byte words that every rank first sets to the number of
+        records it has staged and of keys on its overflow list (keys that found their segment full): the sum also tells whether the record route has to run."""
         partition()
-        if caller_stream is not None:                # device-ordered: no host synchronisation inside the step
+        if caller_stream is not None:                # device-ordered: the host does not wait inside the step
+            self.kc.keyx_staged_count_device(self._token.data_ptr())
             self.kc.stream_signal(caller_stream())
             dist.all_reduce(self._token, group=self.group)
             self.kc.stream_wait(caller_stream())
+            self.kc.keyx_pull_insert()               # queued behind the barrier; the host runs ahead
+            staged_anywhere = int(self._token.sum().item()) > 0
         else:
+            self._token.zero_()
             dist.all_reduce(self._token, group=self.group)
             sync()
-        self.kc.keyx_pull_insert()
+            self.kc.keyx_pull_insert()
+            staged_anywhere = any_rank_staged(int(self.kc.shard_send_counts(self.world).sum()), device=self.device, group=self.group)
         pulled = (self.world - 1) * int(self.lay.bytes_per_dest)
-        if any_rank_staged(int(self.kc.shard_send_counts(self.world).sum()), device=self.device, group=self.group):
+        if staged_anywhere:
             pulled += exchange_staged_records(self.kc, self.world, self.device, self.record_bufs, sync, self.group)
         return pulled
 
