@@ -60,7 +60,9 @@ enum {
     PBK_F_TIMING = 1u << 0,       /* bracket every kernel launch with CUDA events (see pbk_get_stats) */
     PBK_F_NO_PARTITION = 1u << 1, /* always insert straight into the table (no hash-range bucket pass)  */
     PBK_F_FORCE_PARTITION = 1u << 2, /* use the bucket pass even for tiny batches (tests)              */
-    PBK_F_NO_PIPELINE = 1u << 3   /* always size the table with a pilot launch and host round trips      */
+    PBK_F_NO_PIPELINE = 1u << 3,  /* always size the table with a pilot launch and host round trips      */
+    PBK_F_UNKNOWN_AS_N = 1u << 4  /* a character without a Char2Bin code (IUPAC ambiguity codes ...) counts as N instead of failing
+                                     with PBK_E_BAD_BASE (the reference silently miscodes it, common.h:256); also: PBK_UNKNOWN_AS_N=1 */
 };
 
 typedef struct pbk_config {

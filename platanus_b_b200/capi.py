@@ -25,6 +25,7 @@ F_TIMING = 1
 F_NO_PARTITION = 2
 F_FORCE_PARTITION = 4
 F_NO_PIPELINE = 8
+F_UNKNOWN_AS_N = 16
 
 STATUS = {0: "PBK_OK", -1: "PBK_E_ARG", -2: "PBK_E_NO_DEVICE", -3: "PBK_E_CUDA", -4: "PBK_E_NOMEM",
           -5: "PBK_E_READ_TOO_LONG", -6: "PBK_E_BAD_BASE", -7: "PBK_E_KMER_DIST", -8: "PBK_E_STATE",
@@ -282,12 +283,12 @@ class KmerCounter:
 
     def __init__(self, k: int, device: int = -1, n_shards: int = 1, shard_rank: int = 0, timing: bool = False,
                  table_slots_hint: int = 0, hbm_budget_bytes: int = 0, partition: bool | str = True,
-                 pipeline: bool = True):
+                 pipeline: bool = True, unknown_as_n: bool = False):
         self._L = load_library()
         self._ctx = C.c_void_p()
         self.k = int(k)
         self.words = (self.k + 31) // 32
-        cfg = PbkConfig(C.sizeof(PbkConfig), self.k, device, (F_TIMING if timing else 0) | (F_FORCE_PARTITION if partition == "force" else 0 if partition else F_NO_PARTITION) | (0 if pipeline else F_NO_PIPELINE),
+        cfg = PbkConfig(C.sizeof(PbkConfig), self.k, device, (F_TIMING if timing else 0) | (F_FORCE_PARTITION if partition == "force" else 0 if partition else F_NO_PARTITION) | (0 if pipeline else F_NO_PIPELINE) | (F_UNKNOWN_AS_N if unknown_as_n else 0),
                         n_shards, shard_rank,
                         table_slots_hint, hbm_budget_bytes)
         rc = self._L.pbk_create(C.byref(self._ctx), C.byref(cfg))

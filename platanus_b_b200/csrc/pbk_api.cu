@@ -600,7 +600,7 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
         // inputs already in HBM: pack chunk by chunk so the chunk's stream words are still in L2 when counted
         for (u64 b0 = 0; b0 < n_bases; b0 += CHUNK_BASES) {
             const u64 nb = std::min(CHUNK_BASES, n_bases - b0), w0 = b0 / 32, nw = (nb + 31) / 32;
-            { Span sp(c, LC_PACK); launch_pack(d_bases_in + b0, nb, nw, encoding, stream, nflag, w0, c->d_ctr, c->s_compute); }
+            { Span sp(c, LC_PACK); launch_pack(d_bases_in + b0, nb, nw, encoding | ((c->flags & PBK_F_UNKNOWN_AS_N) ? 0x100 : 0), stream, nflag, w0, c->d_ctr, c->s_compute); }
             CK(cudaGetLastError());
             TRY(count_words(w0, w0 + nw));
         }
@@ -666,7 +666,7 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
             const u64 b0 = ci * CHUNK_BASES, nb = std::min(CHUNK_BASES, n_bases - b0), w0 = b0 / 32, nw = (nb + 31) / 32;
             if (ci + N_STAGE - 1 < n_chunks) TRY(enqueue_copy(ci + N_STAGE - 1));   // copies run ahead of this chunk's kernels
             CK(cudaStreamWaitEvent(c->s_compute, c->ev_copy_done[buf], 0));
-            { Span sp(c, LC_PACK); launch_pack(c->d_stage[buf], nb, nw, encoding, stream, nflag, w0, c->d_ctr, c->s_compute); }
+            { Span sp(c, LC_PACK); launch_pack(c->d_stage[buf], nb, nw, encoding | ((c->flags & PBK_F_UNKNOWN_AS_N) ? 0x100 : 0), stream, nflag, w0, c->d_ctr, c->s_compute); }
             CK(cudaGetLastError());
             CK(cudaEventRecord(c->ev_stage_free[buf], c->s_compute));
             if (!deferred_count) TRY(count_words(w0, w0 + nw));
@@ -833,6 +833,7 @@ int pbk_create(pbk_ctx **out, const pbk_config *cfg)
     if (cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking) != cudaSuccess) return bail(PBK_E_CUDA);
     if (cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking) != cudaSuccess) return bail(PBK_E_CUDA);
     c->pipeline_enabled = !(cfg->flags & PBK_F_NO_PIPELINE) && getenv("PBK_NO_PIPELINE") == nullptr;
+    if (getenv("PBK_UNKNOWN_AS_N") && atoi(getenv("PBK_UNKNOWN_AS_N")) != 0) c->flags |= PBK_F_UNKNOWN_AS_N;
     if (cudaMallocHost((void **)&c->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(PBK_E_NOMEM);
     memset(c->h_ctr, 0, sizeof(Counters));
     if (dev_alloc(c, (void **)&c->d_ctr, sizeof(Counters)) || dev_alloc(c, (void **)&c->d_len_hist, PBK_LEN_BINS * 8) ||
@@ -1247,7 +1248,7 @@ static int lookup_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_ba
             if (cudaMemcpyAsync(d_tmp_stage, h_bases + b0, nb, cudaMemcpyHostToDevice, c->s_compute) != cudaSuccess) rc = fail(c, PBK_E_CUDA, "H2D copy failed");
             c->h2d_bytes += nb;
         }
-        { Span sp(c, LC_PACK); launch_pack(src, nb, nw, encoding, stream, nflag, w0, c->d_ctr_scratch, c->s_compute); }
+        { Span sp(c, LC_PACK); launch_pack(src, nb, nw, encoding | ((c->flags & PBK_F_UNKNOWN_AS_N) ? 0x100 : 0), stream, nflag, w0, c->d_ctr_scratch, c->s_compute); }
     }
     if (rc == PBK_OK && encoding == PBK_ENC_PLATANUS) {
         if (!n_pos || !n_pos_offsets) rc = fail(c, PBK_E_ARG, "PBK_ENC_PLATANUS needs n_pos and n_pos_offsets");

@@ -11,8 +11,11 @@ namespace pbk {
 
 // four characters per 32-bit lane.  Char2Bin only looks at the low nibble: 1->A 3->C 7->G 4->T
 // 14->N 15->0(A); every other nibble has no defined code in the reference.
-__device__ __forceinline__ void pack4(u32 v, bool platanus, u32 &byte_out, u32 &nflag4, u32 &bad)
+// `platanus` carries the encoding (bit 0: PBK_ENC_PLATANUS code bytes) and bit 8: characters without a Char2Bin code are
+// treated as N instead of being reported (PBK_F_UNKNOWN_AS_N: IUPAC ambiguity codes occur in real FASTQ files)
+__device__ __forceinline__ void pack4(u32 v, int mode, u32 &byte_out, u32 &nflag4, u32 &bad)
 {
+    const bool platanus = (mode & 1) != 0;
     if (platanus) {
         u32 codes = v & 0x03030303u;
         byte_out = (codes * 0x40100401u) >> 24;
@@ -26,7 +29,9 @@ __device__ __forceinline__ void pack4(u32 v, bool platanus, u32 &byte_out, u32 &
     nflag4 = (((z >> 7) * 0x01020408u) >> 24) & 0xFu;        // bit i <=> byte i
     u32 b0 = v, b1 = v >> 1, b2 = v >> 2, b3 = v >> 3;
     u32 ok = (~b3 & ~b2 & b0) | (~b3 & b2 & ~(b1 ^ b0)) | (b3 & b2 & b1);
-    bad |= (~ok) & 0x01010101u;
+    const u32 notok = (~ok) & 0x01010101u;
+    if (mode & 0x100) nflag4 |= ((notok * 0x01020408u) >> 24) & 0xFu;
+    else bad |= notok;
 }
 
 template <bool ALIGNED>
@@ -54,7 +59,7 @@ pack_kernel(const uint8_t *__restrict__ bases, u64 n_valid, u64 n_words, int pla
                     u64 pos = b0 + 4 * j + b;
                     u32 c;
                     if (pos < n_valid) c = bases[pos];
-                    else { c = platanus ? 0u : (u32)'A'; tail_flags |= 1u << (4 * j + b); }
+                    else { c = (platanus & 1) ? 0u : (u32)'A'; tail_flags |= 1u << (4 * j + b); }
                     v |= c << (8 * b);
                 }
                 x[j] = v;
@@ -65,7 +70,7 @@ pack_kernel(const uint8_t *__restrict__ bases, u64 n_valid, u64 n_words, int pla
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             u32 byte, f4;
-            pack4(x[j], platanus != 0, byte, f4, bad);
+            pack4(x[j], platanus, byte, f4, bad);
             word |= (u64)byte << (56 - 8 * j);
             nf |= f4 << (4 * j);
         }

@@ -476,3 +476,28 @@ def test_pack_reads_rejects_characters_without_a_code():
     with pytest.raises(capi.PbkError) as e:
         capi.pack_reads(np.frombuffer(b"ACGTRACGT", dtype=np.uint8))
     assert e.value.status == -6
+
+
+def test_unknown_characters_can_count_as_n(oracle):
+    """PBK_F_UNKNOWN_AS_N: IUPAC ambiguity codes and other characters without a Char2Bin code behave like N (the default stays
+    PBK_E_BAD_BASE; the reference silently miscodes them)"""
+    O = oracle
+    rs = synth.make_reads(synth.config("C1", scale=1 / 200))
+    b, o = rs.flat()
+    b = b.copy()
+    iupac = np.frombuffer(b"RYKMBHVryk-", dtype=np.uint8)      # (S, W, D have the low nibbles of C, G, T: Char2Bin gives them a code)
+    idx = np.arange(17, len(b), 997)
+    b[idx] = iupac[np.arange(len(idx)) % len(iupac)]
+    as_n = b.copy()
+    as_n[idx] = ord("N")
+    want = O.count(_reads_from_arrays(O, as_n, o), 32)
+    with KmerCounter(32) as kc:
+        with pytest.raises(PbkError) as e:
+            kc.push_reads(b, o)
+        assert e.value.status == -6
+    with KmerCounter(32, unknown_as_n=True) as kc:
+        kc.push_reads(b, o)
+        kc.finalize()
+        keys, counts = kc.export(1, sorted=True)
+        assert kc.n_instances == want.n_instances
+    assert np.array_equal(keys, want.keys) and np.array_equal(counts, want.counts)
