@@ -62,7 +62,7 @@ def algorithmic_bytes_per_instance(read_len: int, k: int) -> float:
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of one step's Pass A + Pass B launches, from the committed
     `ncu --set full` capture of this workload (profiles/*_traffic.json); None when there is no capture."""
-    path = os.path.join(ROOT, "profiles", "r1c_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r2a_traffic.json")
     try:
         return float(json.load(open(path))["dram_bytes_per_step"])
     except Exception:
