@@ -49,6 +49,12 @@ struct pbk_ctx {
     u32 k = 0; int W = 0; u32 flags = 0;
     ShardInfo shard{1, 0};
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    // side streams (PBK_NO_OVERLAP=1 switches both uses off): s_clear zero-fills the tables at pbk_reset while the next batch's
+    // pack and Pass A -- which never touch a table -- already run on s_compute (table_ready() orders the first table access behind
+    // it); s_pack runs the pack kernel of chunk i + 1 (memory bound) next to Pass A of chunk i (issue bound) for device-resident input
+    cudaStream_t s_clear = nullptr, s_pack = nullptr;
+    cudaEvent_t ev_table_clear = nullptr, ev_pack[N_STAGE] = {}, ev_pack_may_start = nullptr;
+    bool table_clear_pending = false, overlap_enabled = true;
     u64 budget = 0, used = 0;
 
     // batch buffers (grow-only)
@@ -194,8 +200,18 @@ u64 round_slots(const pbk_ctx *c, u64 want)
     return std::max<u64>(MIN_SLOTS, (want + 1023) & ~1023ull);
 }
 
+// the tables may still be being zero-filled on the side stream (pbk_reset): everything that touches a table calls this first
+int table_ready(pbk_ctx *c)
+{
+    if (!c->table_clear_pending) return PBK_OK;
+    c->table_clear_pending = false;
+    CK(cudaStreamWaitEvent(c->s_compute, c->ev_table_clear, 0));
+    return PBK_OK;
+}
+
 int table_alloc(pbk_ctx *c, TableView *t, u64 slots)
 {
+    TRY(table_ready(c));
     t->words = c->W; t->cap = slots; t->slots = nullptr;
     TRY(dev_alloc(c, &t->slots, t->bytes()));
     { Span sp(c, LC_OTHER); launch_table_init(*t, c->s_compute); }
@@ -221,6 +237,7 @@ int read_counters(pbk_ctx *c)
 
 int grow_table(pbk_ctx *c, TableView *t, u64 occupied, u64 want_slots)
 {
+    TRY(table_ready(c));
     const u64 ns = round_slots(c, std::max<u64>(t->cap + t->cap / 2, want_slots));
     DBG("grow table %llu -> %llu slots (occupied %llu)", t->cap, ns, occupied);
     TableView nt{nullptr, ns, c->W};
@@ -286,6 +303,7 @@ int ensure_tables(pbk_ctx *c, u64 first_batch_windows, bool need_remote);
 
 int drain_overflow(pbk_ctx *c)
 {
+    if (c->h_ctr->overflow_n > 0) TRY(table_ready(c));
     if (c->h_ctr->overflow_n > 0) TRY(ensure_tables(c, 1024, c->shard.n_shards > 1));   // (key-exchange pushes create no table)
     for (int attempt = 0; c->h_ctr->overflow_n > 0; ++attempt) {
         const u64 n = std::min<u64>(c->h_ctr->overflow_n, c->ovf_cap);
@@ -318,6 +336,7 @@ int drain_overflow(pbk_ctx *c)
 // host's view of the table (occupancy, staged records, the overflow list) calls this first
 int settle(pbk_ctx *c)
 {
+    TRY(table_ready(c));
     if (!c->counters_pending) return PBK_OK;
     c->counters_pending = false;
     c->pending_new = 0;
@@ -328,6 +347,7 @@ int settle(pbk_ctx *c)
 int maybe_clamp(pbk_ctx *c, u64 upcoming)
 {
     if (c->inst_since_clamp + upcoming < U32_HEADROOM) return PBK_OK;
+    TRY(table_ready(c));
     { Span sp(c, LC_OTHER); launch_table_clamp(c->table, c->s_compute); }
     if (c->shard.n_shards > 1 && c->remote.slots) { Span sp(c, LC_OTHER); launch_table_clamp(c->remote, c->s_compute); }
     CK(cudaGetLastError());
@@ -378,6 +398,7 @@ int ensure_batch_buffers(pbk_ctx *c, u64 n_bases, u64 n_reads)
 int count_range(pbk_ctx *c, u64 w0, u64 w1)
 {
     if (w1 <= w0) return PBK_OK;
+    TRY(table_ready(c));
     const u64 windows = (w1 - w0) * 32;
     TRY(maybe_clamp(c, windows));
     TRY(ensure_room(c, (u64)(windows * std::min(1.0, c->new_ratio * 1.25))));
@@ -445,6 +466,7 @@ struct Pipe {
 int pipe_finish_subbatch(pbk_ctx *c, Pipe &p)
 {
     if (p.in_sb == 0) return PBK_OK;
+    TRY(table_ready(c));                             // Pass B is the first thing of a batch that touches the table
     { Span sp(c, LC_OTHER); launch_passb_desc(c->d_bkt_cursor, c->plan.seg_cap, c->plan.n_buckets, c->table, c->remote, c->shard, c->d_passb, c->s_compute); }
     CK(cudaGetLastError());
     {
@@ -474,6 +496,7 @@ int pipe_end(pbk_ctx *c, Pipe &p)
 // one Pass B launch over buckets [b0, b1)
 int passb_launch(pbk_ctx *c, u32 b0, u32 b1)
 {
+    TRY(table_ready(c));
     u64 total = 0;
     for (u32 b = b0; b < b1; ++b) total += c->h_bkt_cursor[b];
     DBG("pass B buckets [%u,%u) of %u: %llu keys, table %llu slots, occupied %llu", b0, b1, c->plan.n_buckets, total, c->table.cap, c->occupied);
@@ -530,9 +553,10 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
     if (c->finalized) return fail(c, PBK_E_STATE, "pbk_push_reads after pbk_finalize (call pbk_reset first)");
     if (n_reads == 0) return PBK_OK;
     CK(cudaSetDevice(c->device));
-    if (!c->keyx_send) TRY(settle(c));              // (a key-exchange partition only runs Pass A; its own read-back at the end settles)
+    if (!c->keyx_send && c->counters_pending) TRY(settle(c));   // (a key-exchange partition only runs Pass A; its own read-back at the end settles)
+    // (no table_ready() here: read marks, pack and Pass A do not touch the tables, which may still be being cleared on s_clear)
     c->stage_gen += 1;
-    if (c->remote_dirty) { Span sp(c, LC_OTHER); launch_table_init(c->remote, c->s_compute); c->remote_dirty = false; }
+    if (c->remote_dirty) { TRY(table_ready(c)); Span sp(c, LC_OTHER); launch_table_init(c->remote, c->s_compute); c->remote_dirty = false; }
     TRY(ensure_batch_buffers(c, n_bases, n_reads));
     const u64 windows_ub = n_bases > (u64)n_reads * (c->k - 1) ? n_bases - (u64)n_reads * (c->k - 1) : 0;
     const bool keyx = c->keyx_send != nullptr;       // Pass A only, into the caller's all-to-all send buffer
@@ -597,10 +621,27 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
         return PBK_OK;
     };
     if (d_bases_in) {
-        // inputs already in HBM: pack chunk by chunk so the chunk's stream words are still in L2 when counted
-        for (u64 b0 = 0; b0 < n_bases; b0 += CHUNK_BASES) {
+        // inputs already in HBM: pack chunk by chunk so the chunk's stream words are still in L2 when counted.  With Pass A behind
+        // it (partitioned batches) the pack kernel of a chunk runs on its own stream, so that it overlaps Pass A of the chunk before:
+        // one is bound by memory, the other by instruction issue.  (Not with per-launch timing: the spans bracket s_compute.)
+        const bool side = c->overlap_enabled && partitioned && !(c->flags & PBK_F_TIMING);
+        if (side) {
+            CK(cudaEventRecord(c->ev_pack_may_start, c->s_compute));       // whatever still reads the previous batch's stream comes first
+            CK(cudaStreamWaitEvent(c->s_pack, c->ev_pack_may_start, 0));
+        }
+        u64 ci = 0;
+        for (u64 b0 = 0; b0 < n_bases; b0 += CHUNK_BASES, ++ci) {
             const u64 nb = std::min(CHUNK_BASES, n_bases - b0), w0 = b0 / 32, nw = (nb + 31) / 32;
-            { Span sp(c, LC_PACK); launch_pack(d_bases_in + b0, nb, nw, encoding | ((c->flags & PBK_F_UNKNOWN_AS_N) ? 0x100 : 0), stream, nflag, w0, c->d_ctr, c->s_compute); }
+            const int mode = encoding | ((c->flags & PBK_F_UNKNOWN_AS_N) ? 0x100 : 0);
+            if (side) {
+                c->launches[LC_PACK] += 1;
+                launch_pack(d_bases_in + b0, nb, nw, mode, stream, nflag, w0, c->d_ctr, c->s_pack);
+                CK(cudaEventRecord(c->ev_pack[ci % N_STAGE], c->s_pack));
+                CK(cudaStreamWaitEvent(c->s_compute, c->ev_pack[ci % N_STAGE], 0));
+            } else {
+                Span sp(c, LC_PACK);
+                launch_pack(d_bases_in + b0, nb, nw, mode, stream, nflag, w0, c->d_ctr, c->s_compute);
+            }
             CK(cudaGetLastError());
             TRY(count_words(w0, w0 + nw));
         }
@@ -719,6 +760,11 @@ void release_all(pbk_ctx *c)
     cudaSetDevice(c->device);
     if (c->s_compute) cudaStreamSynchronize(c->s_compute);
     if (c->s_copy) cudaStreamSynchronize(c->s_copy);
+    if (c->s_clear) { cudaStreamSynchronize(c->s_clear); cudaStreamDestroy(c->s_clear); }
+    if (c->s_pack) { cudaStreamSynchronize(c->s_pack); cudaStreamDestroy(c->s_pack); }
+    if (c->ev_table_clear) cudaEventDestroy(c->ev_table_clear);
+    if (c->ev_pack_may_start) cudaEventDestroy(c->ev_pack_may_start);
+    for (int i = 0; i < N_STAGE; ++i) if (c->ev_pack[i]) cudaEventDestroy(c->ev_pack[i]);
     resolve_spans(c);
     cudaFree(c->d_stream_raw); cudaFree(c->d_nflag_raw); cudaFree(c->d_rflag_raw); cudaFree(c->d_offsets);
     for (int i = 0; i < N_STAGE; ++i) {
@@ -747,6 +793,7 @@ void release_all(pbk_ctx *c)
 // pbk_seed_entries: the seeded k-mers get their seeded value, whatever the reads added (see override_records_kernel)
 int apply_seeds(pbk_ctx *c)
 {
+    TRY(table_ready(c));
     const u64 n = c->seed_rec.size() / (c->W + 1);
     TRY(ensure_tables(c, std::max<u64>(n, 1024), false));
     if ((double)(c->occupied + n) > max_load(c) * (double)c->table.capacity())
@@ -832,6 +879,13 @@ int pbk_create(pbk_ctx **out, const pbk_config *cfg)
     auto bail = [&](int code) { release_all(c); delete c; return code; };
     if (cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking) != cudaSuccess) return bail(PBK_E_CUDA);
     if (cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking) != cudaSuccess) return bail(PBK_E_CUDA);
+    if (cudaStreamCreateWithFlags(&c->s_clear, cudaStreamNonBlocking) != cudaSuccess) return bail(PBK_E_CUDA);
+    if (cudaStreamCreateWithFlags(&c->s_pack, cudaStreamNonBlocking) != cudaSuccess) return bail(PBK_E_CUDA);
+    if (cudaEventCreateWithFlags(&c->ev_table_clear, cudaEventDisableTiming) != cudaSuccess) return bail(PBK_E_CUDA);
+    if (cudaEventCreateWithFlags(&c->ev_pack_may_start, cudaEventDisableTiming) != cudaSuccess) return bail(PBK_E_CUDA);
+    for (int i = 0; i < N_STAGE; ++i)
+        if (cudaEventCreateWithFlags(&c->ev_pack[i], cudaEventDisableTiming) != cudaSuccess) return bail(PBK_E_CUDA);
+    c->overlap_enabled = getenv("PBK_NO_OVERLAP") == nullptr;
     c->pipeline_enabled = !(cfg->flags & PBK_F_NO_PIPELINE) && getenv("PBK_NO_PIPELINE") == nullptr;
     if (getenv("PBK_UNKNOWN_AS_N") && atoi(getenv("PBK_UNKNOWN_AS_N")) != 0) c->flags |= PBK_F_UNKNOWN_AS_N;
     if (cudaMallocHost((void **)&c->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(PBK_E_NOMEM);
@@ -961,6 +1015,7 @@ int pbk_export(pbk_ctx *c, uint32_t min_count, int sorted, uint64_t *keys, uint1
     if (!c) return PBK_E_ARG;
     if (!c->finalized) return fail(c, PBK_E_STATE, "pbk_export before pbk_finalize");
     CK(cudaSetDevice(c->device));
+    TRY(table_ready(c));
     u64 n = 0;
     for (u64 i = std::max<u64>(min_count, 1); i < PBK_OCC_BINS; ++i) n += c->h_occ_hist[i];
     if (n_out) *n_out = n;
@@ -1059,12 +1114,20 @@ int pbk_reset(pbk_ctx *c, uint32_t k)
     c->counters_pending = false;                       // whatever was queued is about to be forgotten
     c->pending_new = 0;
     const int W = (int)((k + 31) / 32);
+    if (c->table_clear_pending) { CK(cudaStreamSynchronize(c->s_clear)); c->table_clear_pending = false; }
     if (W != c->W) {                                   // slot size changes: tables are re-created lazily
         if (c->table.slots) dev_free(c, c->table.slots, c->table.bytes());
         if (c->remote.slots) dev_free(c, c->remote.slots, c->remote.bytes());
         if (c->d_ovf) dev_free(c, c->d_ovf, c->ovf_cap * (c->W + 1) * 8);
         c->table = TableView{nullptr, 0, 0}; c->remote = TableView{nullptr, 0, 0}; c->d_ovf = nullptr; c->ovf_cap = 0;
+    } else if (c->overlap_enabled && !(c->flags & PBK_F_TIMING)) {
+        // zero-fill on the side stream (s_compute is idle: synchronised above); the first table access waits for it (table_ready)
+        if (c->table.slots) { c->launches[LC_OTHER] += 1; launch_table_init(c->table, c->s_clear); }
+        if (c->remote.slots) { c->launches[LC_OTHER] += 1; launch_table_init(c->remote, c->s_clear); }
+        CK(cudaEventRecord(c->ev_table_clear, c->s_clear));
+        c->table_clear_pending = true;
     } else {
+        TRY(table_ready(c));
         if (c->table.slots) { Span sp(c, LC_OTHER); launch_table_init(c->table, c->s_compute); }
         if (c->remote.slots) { Span sp(c, LC_OTHER); launch_table_init(c->remote, c->s_compute); }
     }
@@ -1549,6 +1612,7 @@ static int keyx_insert_common(pbk_ctx *c, const KeyxSources &srcs)
 {
     if (c->finalized) return fail(c, PBK_E_STATE, "insert after finalize");
     CK(cudaSetDevice(c->device));
+    TRY(table_ready(c));
     const u32 G = c->shard.n_shards, n_desc = c->keyx_plan.n_buckets, R = n_desc / G;
     const u64 seg_cap = c->keyx_plan.seg_cap;
     TRY(ensure_passb_buffers(c));
