@@ -313,7 +313,8 @@ int  pbk_group_neighbor_flags(pbk_group *g, uint32_t min_count, const uint64_t *
  *            the window starting at base i of read r; 0 if the k-mer is not in the table, if the
  *            window contains an N, and for the last k - 1 bases of every read (no window starts there).
  * With n_shards > 1 only keys this shard owns are found: summing occ_out over the shards gives the
- * global answer.  Other arguments as pbk_push_reads; at most 2^31 bases per call.                  */
+ * global answer.  Other arguments as pbk_push_reads; at most 2^31 bases per call; a sequence may be of any length
+ * (contigs: the 500000-base limit of reads does not apply).                                         */
 int  pbk_lookup(pbk_ctx *ctx, const uint8_t *bases, const uint64_t *read_offsets, uint64_t n_reads,
                 int encoding, const int32_t *n_pos, const uint64_t *n_pos_offsets, uint16_t *occ_out);
 /* same with inputs and output in device memory (d_occ_out: n_bases u16, 8-byte aligned)              */

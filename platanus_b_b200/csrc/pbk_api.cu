@@ -1349,8 +1349,9 @@ static int lookup_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_ba
         else {
             const u32 flags = c->h_ctr->error_flags;
             *c->h_ctr = c->last;                                      // h_ctr mirrors the counting counters between calls
-            if (flags & ERR_READ_TOO_LONG) rc = fail(c, PBK_E_READ_TOO_LONG, "a read has >= 500000 bases");
-            else if (flags & ERR_BAD_BASE) rc = fail(c, PBK_E_BAD_BASE, "input contains a character with no Char2Bin code (only ACGTN, any case)");
+            // (no length limit here: ContigDivider::getOccurrenceArray walks contigs of any length, kmer_divide.cpp:151-197; the
+            //  500000-base limit belongs to SEQ::convertFromString on the counting path)
+            if (flags & ERR_BAD_BASE) rc = fail(c, PBK_E_BAD_BASE, "input contains a character with no Char2Bin code (only ACGTN, any case)");
         }
     }
     cudaStreamSynchronize(c->s_compute);

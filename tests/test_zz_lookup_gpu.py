@@ -3,6 +3,7 @@ section 8f rows 1-2) against the reference's own getOccurrenceArray output (test
 First seen to pass on a B200 at the end of round 1 (GPUTEST_r01); the kernel's logic is also covered on CPU by
 tests/test_lookup_cpu.py through the host emulation."""
 import ctypes as C
+import dataclasses
 import os
 
 import numpy as np
@@ -216,3 +217,25 @@ def test_neighbor_flags_after_counting_match_the_oracle(oracle, k):
     assert np.array_equal(flags, O.neighbor_flags(k, want.keys, want.counts, cutoff)[sel])
     # a 100x genome: nearly all kept k-mers are interior nodes of a path (exactly one neighbour on each side)
     assert (flags != 0).mean() > 0.99
+
+
+def test_lookup_takes_contigs_longer_than_the_read_limit(oracle):
+    """ContigDivider::getOccurrenceArray (kmer_divide.cpp:151-197) walks contigs of any length: a 600 kb sequence (reads are
+    limited to 499 999 bases, contigs are not)"""
+    O = oracle
+    spec = synth.config("C1", scale=600_000 / 4_600_000)
+    genome = np.frombuffer(b"ACGT", dtype=np.uint8)[synth.make_genome(spec.genome_lengths[0], spec.gc[0], spec.genome_seeds[0])]
+    assert len(genome) >= 500_000
+    rs = synth.make_reads(dataclasses.replace(spec, coverage=6.0))
+    b, o = rs.flat()
+    rd = O.Reads()
+    rd.add_array(b, o)
+    want = O.count(rd, 32)
+    with KmerCounter(32) as kc:
+        kc.push_reads(b, o)
+        kc.finalize()
+        got = kc.lookup(genome, np.array([0, len(genome)], np.uint64))
+    seqs = O.Reads()
+    seqs.add_array(genome, np.array([0, len(genome)], np.uint64))
+    assert np.array_equal(got, O.occurrence_array(seqs, 32, want.keys, want.counts))
+    assert (got[: len(genome) - 31] > 0).mean() > 0.9
