@@ -143,6 +143,7 @@ PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words, siz
 {
     PartitionPlan p{};
     if (smem_budget == 0) smem_budget = getenv("PBK_PART_SMEM_KB") ? (size_t)atoi(getenv("PBK_PART_SMEM_KB")) * 1024 : PART_SMEM_BUDGET;
+    if (words > 1) smem_budget -= 8 * 1024;                  // partition_compact_kernel's queue of live work items (static shared memory)
     const u64 entries = smem_budget / (8 * (size_t)words);
     const u64 region_bytes = getenv("PBK_REGION_MB") ? (u64)atoi(getenv("PBK_REGION_MB")) << 20 : PART_REGION_BYTES;
     u64 P = (est_table_bytes + region_bytes - 1) / region_bytes;
@@ -207,6 +208,21 @@ void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64
         if (words == 1)
             partition_launch_w<1, true>(stream, nflag, rflag, word_begin, word_end, k, plan, bkt_keys, bkt_cursor, ctr,
                                         overflow_keys, overflow_cap, grid, keyx_dest, st);
+        return;
+    }
+    // multi-word keys: live work items compacted across the CTA (partition_compact_kernel) unless PBK_PART_COMPACT=0; its queue takes
+    // 8 KB of static shared memory, which plan_partition leaves free for these key widths
+    static const bool compact = !(getenv("PBK_PART_COMPACT") && atoi(getenv("PBK_PART_COMPACT")) == 0);
+    if (words > 1 && compact && plan.threads <= PARTC_MAX_THREADS) {
+        switch (words) {
+#define PBK_CASE_W(Wv) case Wv:                                                                                                        \
+            cudaFuncSetAttribute(partition_compact_kernel<Wv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);           \
+            partition_compact_kernel<Wv><<<grid, plan.threads, plan.smem, st>>>(stream, nflag, rflag, word_begin, word_end, k,          \
+                plan.n_buckets, plan.bin_cap, bkt_keys, plan.seg_cap, bkt_cursor, ctr, overflow_keys, overflow_cap); break;
+        PBK_CASE_W(2) PBK_CASE_W(3) PBK_CASE_W(4) PBK_CASE_W(5) PBK_CASE_W(6) PBK_CASE_W(7) PBK_CASE_W(8)
+#undef PBK_CASE_W
+        default: break;
+        }
         return;
     }
     PBK_DISPATCH_W(words,

@@ -799,6 +799,188 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
     if (lane == 0 && inst) atomicAdd(&ctr->instances, inst);
 }
 
+// Pass A for multi-word keys with the LIVE work items compacted across the CTA.  A work item (PART_WIN<W> consecutive window
+// ends of one stream word) can only produce keys if the run of usable bases reaching into it is long enough (run + WIN >= k):
+// with k = 75 on 150-base reads that excludes the first 74 positions of every read -- half of all items -- but a warp's 32
+// consecutive items span 256 positions, so every warp holds dead and live items and the early exit of partition_kernel saves
+// no issue slots.  Here the CTA first classifies candidate items (cheap: flag words and two clz) and queues the live ones
+// (item index + run, 8 bytes) in shared memory; as soon as blockDim are queued, every thread takes one and does the expensive
+// part -- rolling W-word forward / reverse keys, canonical minimum, hash, bin -- with all lanes busy; then the usual flush.
+// Same bins, same bucket store, same results as partition_kernel<W>; only which thread handles which item differs.
+constexpr int PARTC_MAX_THREADS = 512;
+struct PartcEntry { u32 item; int run; };
+
+template <int W>
+__global__ void __launch_bounds__(PARTC_MAX_THREADS)
+partition_compact_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, const u32 *__restrict__ rflag,
+                         u64 word_begin, u64 word_end, int k, u32 n_buckets, u32 bin_cap, u64 *bkt_keys, u64 seg_cap,
+                         u64 *bkt_cursor, Counters *ctr, u64 *ovf, u64 ovf_cap)
+{
+    PBK_DYN_SMEM(u64, bins);                          // n_buckets * bin_cap * W words
+    __shared__ u32 scount[PART_MAX_BUCKETS];
+    __shared__ u64 sbase[PART_MAX_BUCKETS];
+    __shared__ PartcEntry s_q[2 * PARTC_MAX_THREADS];
+    __shared__ u32 s_qn;
+    const int top_shift = 2 * ((k - 1) & 31);
+    const u64 top_mask = (k & 31) ? ((1ull << (2 * (k & 31))) - 1ull) : ~0ull;
+    const int s = 2 * (32 * W - k);
+    const int nb = (k + 30) >> 5;
+    const u32 nthreads = blockDim.x, tid = threadIdx.x;
+    const u32 wsize = nthreads < 32u ? nthreads : 32u, lane = tid % wsize;
+    constexpr int WIN = PART_WIN<W>::value, SUBS = 32 / WIN;
+    const u64 n_items = (word_end - word_begin) * SUBS;           // < 2^32: a batch has at most 2^31 bases
+    u64 inst = 0;
+    u64 cursor = (u64)blockIdx.x * nthreads;                       // first candidate item of this CTA's next batch
+    const u64 stride = (u64)gridDim.x * nthreads;
+    if (tid == 0) s_qn = 0;
+    __syncthreads();
+
+    for (;;) {
+        // ---- phase 1: classify candidates until a full round of live items is queued (or the input ends) ----------------
+        while (s_qn < nthreads && cursor < n_items) {              // (uniform: s_qn is only changed between barriers)
+            const u64 item = cursor + tid;
+            int run = 0;
+            bool live = item < n_items;
+            if (live) {
+                const u64 wi = word_begin + item / SUBS;
+                const int i0 = (int)(item % SUBS) * WIN;
+                run = k;
+                for (int j = 1; j <= nb; ++j) {
+                    const u32 a = nflag[wi - j], b = rflag[wi - j];
+                    if (a | b) {
+                        const int pn = a ? 32 - __clz(a) : 0;
+                        const int pr = b ? 31 - __clz(b) : 0;
+                        run = 32 * j - max(pn, pr);
+                        break;
+                    }
+                }
+                if (i0) {                                           // the positions of this word in front of the item
+                    const u32 nf = nflag[wi], rf = rflag[wi];
+                    const u32 a = nf & ((1u << i0) - 1u), b = rf & ((1u << i0) - 1u);
+                    if (a | b) {
+                        const int pn = a ? 32 - __clz(a) : 0;
+                        const int pr = b ? 31 - __clz(b) : 0;
+                        run = i0 - max(pn, pr);
+                    } else {
+                        run += i0;
+                    }
+                }
+                live = run + WIN >= k;                              // flags inside the item only shorten the run
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, live);
+            u32 base = 0;
+            if (lane == 0 && bal) base = atomicAdd(&s_qn, (u32)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (live) {
+                PartcEntry e;
+                e.item = (u32)item; e.run = run;
+                s_q[base + (u32)__popc(bal & ((1u << lane) - 1u))] = e;
+            }
+            cursor += stride;
+            __syncthreads();
+        }
+        const u32 qn = s_qn;
+        if (qn == 0) break;
+        const u32 take = qn < nthreads ? qn : nthreads;
+        for (u32 b = tid; b < n_buckets; b += nthreads) scount[b] = 0;
+        __syncthreads();
+
+        // ---- phase 2: one live item per thread, all lanes of the active warps busy -------------------------------------------
+        if (tid < take) {
+            const PartcEntry e = s_q[qn - 1 - tid];
+            const u64 wi = word_begin + e.item / SUBS;
+            const int i0 = (int)(e.item % SUBS) * WIN;
+            int run = e.run;
+            const u64 cur = stream[wi];
+            u64 fwd[W], rev[W];
+            if (i0 == 0) {
+#pragma unroll
+                for (int j = 0; j < W; ++j) fwd[j] = stream[wi - 1 - j];
+            } else {
+                u64 hi = cur;
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+                    const u64 lo = stream[wi - 1 - j];
+                    fwd[j] = (lo << (2 * i0)) | (hi >> (64 - 2 * i0));
+                    hi = lo;
+                }
+            }
+            {
+                u64 y[W + 1];
+#pragma unroll
+                for (int j = 0; j < W; ++j) y[j] = pair_reverse64(~fwd[W - 1 - j]);
+                y[W] = 0;
+#pragma unroll
+                for (int j = 0; j < W; ++j) rev[j] = s ? ((y[j] >> s) | (y[j + 1] << (64 - s))) : y[j];
+            }
+            u64 c = i0 ? cur << (2 * i0) : cur;
+            const u32 nfs = nflag[wi] >> i0, rfs = rflag[wi] >> i0;
+#pragma unroll 2
+            for (int i = 0; i < WIN; ++i) {
+                const u32 b = (u32)(c >> 62);
+                c <<= 2;
+                if ((rfs >> i) & 1u) run = 0;
+                run = ((nfs >> i) & 1u) ? 0 : run + 1;
+#pragma unroll
+                for (int j = W - 1; j > 0; --j) fwd[j] = (fwd[j] << 2) | (fwd[j - 1] >> 62);
+                fwd[0] = (fwd[0] << 2) | b;
+                fwd[W - 1] &= top_mask;
+#pragma unroll
+                for (int j = 0; j < W - 1; ++j) rev[j] = (rev[j] >> 2) | (rev[j + 1] << 62);
+                rev[W - 1] = (rev[W - 1] >> 2) | ((u64)(3u - b) << top_shift);
+                if (run >= k) {
+                    const bool use_rev = key_less<W>(rev, fwd);
+                    u64 key[W];
+#pragma unroll
+                    for (int j = 0; j < W; ++j) key[j] = use_rev ? rev[j] : fwd[j];
+                    const u64 hh = hash_key<W>(key);
+                    const u32 bkt = (u32)__umul64hi(hh, (u64)n_buckets);
+                    ++inst;
+                    const u32 pos = atomicAdd(&scount[bkt], 1u);
+                    if (pos < bin_cap) {
+                        u64 *dst = bins + (bkt * bin_cap + pos) * (u32)W;
+#pragma unroll
+                        for (int j = 0; j < W; ++j) dst[j] = key[j];
+                    } else {
+                        bucket_append_direct<W>(key, bkt, bkt_keys, seg_cap, bkt_cursor, ovf, ovf_cap, ctr);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- flush (as partition_kernel): reserve per bucket, then 16-lane groups copy the bins ------------------------------
+        for (u32 b = tid; b < n_buckets; b += nthreads) {
+            const u32 n = min(scount[b], bin_cap);
+            scount[b] = n;
+            sbase[b] = n ? atomicAdd(&bkt_cursor[b], (u64)n) : 0ull;
+        }
+        if (tid == 0) s_qn = qn - take;
+        __syncthreads();
+        {
+            const u32 gs = nthreads < 16u ? nthreads : 16u;
+            const u32 gl = tid % gs, n_groups = nthreads / gs;
+            for (u32 b = tid / gs; b < n_buckets; b += n_groups) {
+                const u32 n = scount[b];
+                if (n == 0) continue;
+                const u64 g = sbase[b];
+                const u64 *src = bins + (u64)b * bin_cap * W;
+                u64 *dst = bkt_keys + ((u64)b * seg_cap + g) * W;
+                if (g + n <= seg_cap) {
+                    for (u32 i = gl; i < n * W; i += gs) st_stream_u64(dst + i, src[i]);
+                } else {
+                    for (u32 i = gl; i < n * W; i += gs) {
+                        if (g + i / W < seg_cap) st_stream_u64(dst + i, src[i]);
+                        else if (i % W == 0) spill_stored<W>(src + i, ctr, ovf, ovf_cap);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    inst = warp_sum_u64(inst);
+    if (lane == 0 && inst) atomicAdd(&ctr->instances, inst);
+}
+
 // Pass B, ONE persistent launch for buckets [b_first, b_end).
 //  * Order: tiles of PASSB_TILE_KEYS keys are handed out in bucket order through an atomic ticket, so
 //    at any moment every CTA works inside the same one or two hash ranges and the table region they

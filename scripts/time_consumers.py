@@ -31,7 +31,16 @@ rs = synth.make_reads(spec)
 b, o = rs.flat()
 genome = np.frombuffer(b"ACGT", dtype=np.uint8)[synth.make_genome(spec.genome_lengths[0], spec.gc[0], spec.genome_seeds[0])]
 out = {"workload": f"C1, k={K}", "n_reads": int(rs.n_reads), "n_bases": int(len(b))}
-with KmerCounter(K) as kc:
+def kernel_ms(kc, f):
+    """device time of the call's own kernels (per-launch CUDA events, PBK_F_TIMING): pack + other classes"""
+    s0 = kc.stats()
+    f()
+    s1 = kc.stats()
+    return {"pack": round(s1["ms_pack"] - s0["ms_pack"], 3), "kernels": round(s1["ms_other"] - s0["ms_other"], 3)}
+
+
+with KmerCounter(K, timing=True) as kc:
+    kc.set_timing(False)
     kc.push_reads(b, o)
     kc.finalize()
     cutoff = kc.coverage_cutoff()
@@ -53,6 +62,14 @@ with KmerCounter(K) as kc:
     m = kc.match_reads(b, o)
     out["match_all_reads_ms"] = med(lambda: kc.match_reads(b, o))
     out["reads_matched_frac"] = float(m.mean())
+    # device time of the kernels alone (the wall-clock figures above are dominated by pageable H2D / D2H copies of the arguments)
+    kc.set_timing(True)
+    out["kernel_ms"] = {"neighbor_flags": kernel_ms(kc, lambda: kc.neighbor_flags(keys, cutoff)),
+                        "lookup_quarter_reads": kernel_ms(kc, lambda: kc.lookup(bq, oq)),
+                        "match_all_reads": kernel_ms(kc, lambda: kc.match_reads(b, o)),
+                        "export_sorted": kernel_ms(kc, lambda: kc.export(cutoff, sorted=True))}
+    out["lookup_kernel_Gwindows_per_s"] = (len(bq) - q * (K - 1)) / max(out["kernel_ms"]["lookup_quarter_reads"]["kernels"], 1e-9) / 1e6
+    kc.set_timing(False)
 with KmerCounter(K) as kc:
     def seeded():
         kc.reset()
