@@ -582,16 +582,19 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
 
     const bool deferred_count = (encoding == PBK_ENC_PLATANUS);     // N flags arrive after all packs
     const bool partitioned = keyx || (c->partition_enabled && (windows_ub >= PART_MIN_WINDOWS || (c->partition_forced && windows_ub > 0)));
-    // Chained (k <= 32, new-key ratio known from an earlier batch of this context, so the table can be sized up front;
+    // Chained (new-key ratio known from an earlier batch of this context, so the table can be sized up front;
     // the first large batch takes the other path with its pilot launch): Pass A per chunk, then a device-built tile map
     // and Pass B, all queued without a host round trip.  Host input is counted in up to four such groups of chunks so
     // that only the last group's Pass B is left when the last H2D copy lands; device-resident input in one group.
     const u64 n_chunks_total = (n_bases + CHUNK_BASES - 1) / CHUNK_BASES;
     Pipe pipe;
-    pipe.on = partitioned && !keyx && c->pipeline_enabled && c->W == 1 && c->ratio_known;
+    static const bool wide_pipe = !(getenv("PBK_WIDE_PIPE") && atoi(getenv("PBK_WIDE_PIPE")) == 0);
+    pipe.on = partitioned && !keyx && c->pipeline_enabled && (c->W == 1 || wide_pipe) && c->ratio_known;
     if (pipe.on) {
         const u32 max_sb = getenv("PBK_N_SB") ? (u32)std::min(8, std::max(1, atoi(getenv("PBK_N_SB")))) : 4u;
-        const u32 n_sb = (h_bases != nullptr && n_chunks_total >= 4) ? (u32)std::max<u64>(1, std::min<u64>(max_sb, n_chunks_total / 2)) : 1u;
+        // (multi-word keys: every group's Pass B sweeps a table of 32-byte slots once more, so at most two groups)
+        const u32 cap_sb = c->W == 1 ? max_sb : std::min<u32>(max_sb, 2u);
+        const u32 n_sb = (h_bases != nullptr && n_chunks_total >= 4) ? (u32)std::max<u64>(1, std::min<u64>(cap_sb, n_chunks_total / 2)) : 1u;
         // host input: groups of equal size (a schedule that ends with a single-chunk group was measured: 2 % slower)
         pipe.n_sb = n_sb;
         for (u32 i = 0; i < n_sb; ++i) pipe.sizes[i] = (u32)((n_chunks_total + n_sb - 1) / n_sb);

@@ -419,7 +419,8 @@ void launch_passb_desc(const u64 *d_cursor, u64 seg_cap, u32 n_buckets, TableVie
                        void *d_desc, cudaStream_t st)
 {
     const int pf_dist = getenv("PBK_PF_DIST") ? atoi(getenv("PBK_PF_DIST")) : 1;
-    passb_desc_kernel<<<1, PART_MAX_BUCKETS, 0, st>>>(d_cursor, seg_cap, n_buckets, (u32)PASSB1_TILE_KEYS, (const char *)table.slots,
+    const u32 tile_keys = table.words == 1 ? (u32)PASSB1_TILE_KEYS : (u32)PASSB_TILE_KEYS;
+    passb_desc_kernel<<<1, PART_MAX_BUCKETS, 0, st>>>(d_cursor, seg_cap, n_buckets, tile_keys, (const char *)table.slots,
         table.cap, shard.n_shards > 1 ? (const char *)remote.slots : nullptr, remote.cap, (u32)table.slot_bytes(), pf_dist,
         (u64 *)d_desc, (PassBBucket *)((char *)d_desc + 16));
 }
@@ -429,6 +430,18 @@ void launch_bucket_insert_chained(const u64 *bkt_keys, u64 seg_cap, const void *
                                   int sm_count, int ctas_per_sm, cudaStream_t st)
 {
     const PassBBucket *d_bk = (const PassBBucket *)((const char *)d_desc + 16);
+    if (table.words > 1) {                                      // multi-word keys: the same chaining, the wide kernel (its own streaming loads)
+        const int wgrid = sm_count * PBK_PASSBW_MINCTAS;
+        switch (table.words) {
+#define PBK_CASE_W(Wv) case Wv: bucket_insert_wide_kernel<Wv, false><<<wgrid, PASSB_THREADS, 0, st>>>(bkt_keys, seg_cap, d_bk, 0, n_buckets, \
+                (u64 *)d_desc, Table<Wv>(table.slots, table.cap), Table<Wv>(remote.slots, remote.cap), shard.n_shards, shard.rank, ctr,     \
+                overflow_keys, overflow_cap); break;
+        PBK_CASE_W(2) PBK_CASE_W(3) PBK_CASE_W(4) PBK_CASE_W(5) PBK_CASE_W(6) PBK_CASE_W(7) PBK_CASE_W(8)
+#undef PBK_CASE_W
+        default: break;
+        }
+        return;
+    }
     const u32 opts = getenv("PBK_PASSB_HINT") ? (u32)atoi(getenv("PBK_PASSB_HINT")) : 1u;
     if (getenv("PBK_PASSB_CTAS")) ctas_per_sm = atoi(getenv("PBK_PASSB_CTAS"));
     const int grid = sm_count * ctas_per_sm;                    // CTAs that find no tile left leave at once

@@ -1808,11 +1808,33 @@ export_kernel(Table<W> t, u32 min_count, u64 *keys_out, uint16_t *counts_out, u6
         __syncthreads();
         u64 key[PER_THREAD][W];
         u32 count[PER_THREAD], rank[PER_THREAD];
+        if constexpr (W == 1) {
+            // compact slots: all eight loads go out first (streaming, nothing depends on them yet); a slot is decoded -- the
+            // inverse of fmix64 -- only if it is occupied AND passes the count filter (1 % of the slots of a read set's table)
+            u64 v[PER_THREAD];
 #pragma unroll
-        for (int q = 0; q < PER_THREAD; ++q) {
-            const u64 i = c0 + (u64)q * blockDim.x + threadIdx.x;
-            rank[q] = 0xFFFFFFFFu; count[q] = 0;
-            if (i < t.cap && t.load(i, key[q], &count[q]) && count[q] >= min_count) rank[q] = atomicAdd(&s_n, 1u);
+            for (int q = 0; q < PER_THREAD; ++q) {
+                const u64 i = c0 + (u64)q * blockDim.x + threadIdx.x;
+                v[q] = i < t.cap ? ld_stream_u64(t.slots + i) : 0ull;
+            }
+#pragma unroll
+            for (int q = 0; q < PER_THREAD; ++q) {
+                rank[q] = 0xFFFFFFFFu; count[q] = 0;
+                if ((v[q] >> t.g.cbits) == 0) continue;
+                const u64 cc = v[q] & t.g.cmask;
+                count[q] = cc > COUNT_SAT ? COUNT_SAT : (u32)cc;
+                if (count[q] < min_count) continue;
+                u64 dummy;
+                ct_decode(v[q], c0 + (u64)q * blockDim.x + threadIdx.x, t.g, &key[q][0], &dummy);
+                rank[q] = atomicAdd(&s_n, 1u);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < PER_THREAD; ++q) {
+                const u64 i = c0 + (u64)q * blockDim.x + threadIdx.x;
+                rank[q] = 0xFFFFFFFFu; count[q] = 0;
+                if (i < t.cap && t.load(i, key[q], &count[q]) && count[q] >= min_count) rank[q] = atomicAdd(&s_n, 1u);
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) s_base = s_n ? atomicAdd(d_n_out, (u64)s_n) : 0ull;
