@@ -34,6 +34,7 @@ constexpr double MAX_LOAD = 0.5;                  // k > 32 (16+ byte slots, any
 constexpr double MAX_LOAD_COMPACT = 0.6;          // k <= 32: capacity is a power of two, real load ends up 0.3-0.6
 constexpr u64 U32_HEADROOM = (1ull << 32) - 65536 - 2;
 constexpr u64 PART_MIN_WINDOWS = 1ull << 22;    // smaller batches go straight to the table
+constexpr bool PASSB2_DEFAULT = false;            // second form of Pass B (split + shared-memory build): PBK_PASSB2=1 / 0 overrides
 constexpr u64 MAX_PUSH_BASES = 1ull << 31;       // larger pushes are cut into internal batches (2 Gi bases: 16 GiB of bucket store at k <= 32)
 
 enum LaunchClass { LC_PACK = 0, LC_COUNT = 1, LC_OTHER = 2, LC_PART = 3, LC_INSERT = 4, LC_N = 5 };
@@ -75,6 +76,13 @@ struct pbk_ctx {
     u64 *d_bkt_cursor = nullptr, *h_bkt_cursor = nullptr;
     void *d_passb = nullptr, *h_passb = nullptr;    // Pass B bucket descriptors
     bool partition_enabled = true, partition_forced = false;
+    // second form of Pass B (k <= 32, unsharded; split_kernel + region_build_kernel): the sub-region segments and their fill counts
+    bool passb2_enabled = false, passb2_fresh = true;
+    u64 *d_sub_keys = nullptr; size_t sub_bytes = 0;
+    u64 *d_sub_cursor = nullptr; u64 sub_cursor_cap = 0;
+    u64 store_windows_ub = 0;        // windows the current bucket store was planned for
+    u64 n_passb2 = 0;                // Pass B launches that took the second form
+    bool table_touched = true;       // something may have written the main table since it was last zero-filled
     // sub-batched counting of host input (k <= 32): Pass A + Pass B per group of chunks, chained on the GPU, so that
     // only the last group's Pass B is left to do when the last H2D copy lands
     bool pipeline_enabled = true, ratio_known = false;
@@ -203,6 +211,7 @@ u64 round_slots(const pbk_ctx *c, u64 want)
 // the tables may still be being zero-filled on the side stream (pbk_reset): everything that touches a table calls this first
 int table_ready(pbk_ctx *c)
 {
+    c->table_touched = true;                         // whoever asks is about to read or write it
     if (!c->table_clear_pending) return PBK_OK;
     c->table_clear_pending = false;
     CK(cudaStreamWaitEvent(c->s_compute, c->ev_table_clear, 0));
@@ -216,6 +225,7 @@ int table_alloc(pbk_ctx *c, TableView *t, u64 slots)
     TRY(dev_alloc(c, &t->slots, t->bytes()));
     { Span sp(c, LC_OTHER); launch_table_init(*t, c->s_compute); }
     CK(cudaGetLastError());
+    if (t == &c->table) c->table_touched = false;
     return PBK_OK;
 }
 
@@ -247,6 +257,7 @@ int grow_table(pbk_ctx *c, TableView *t, u64 occupied, u64 want_slots)
     CK(cudaStreamSynchronize(c->s_compute));
     dev_free(c, t->slots, t->bytes());
     *t = nt;
+    c->table_touched = true;
     c->n_grow += 1;
     (void)occupied;
     return PBK_OK;
@@ -272,7 +283,7 @@ int settle(pbk_ctx *c);
 int ensure_overflow(pbk_ctx *c, u64 records)
 {
     if (records <= c->ovf_cap) return PBK_OK;
-    TRY(settle(c));                                  // queued launches may still append to the list that is about to be replaced
+    if (c->counters_pending) TRY(settle(c));         // queued launches may still append to the list that is about to be replaced
     if (c->d_ovf) { CK(cudaStreamSynchronize(c->s_compute)); dev_free(c, c->d_ovf, c->ovf_cap * (c->W + 1) * 8); c->d_ovf = nullptr; c->ovf_cap = 0; }
     TRY(dev_alloc(c, (void **)&c->d_ovf, records * (c->W + 1) * 8));
     c->ovf_cap = records;
@@ -437,6 +448,7 @@ int prepare_partition(pbk_ctx *c, u64 windows_ub, u64 windows_total)
                                                        (u64)((c->occupied + windows_total * c->new_ratio) / max_load(c))));
     TableView tv{nullptr, est_slots, c->W};
     c->plan = plan_partition(tv.bytes(), windows_ub, c->W);
+    c->store_windows_ub = windows_ub;
     const size_t need = (size_t)c->plan.n_buckets * c->plan.seg_cap * c->W * 8;
     if (need > c->bkt_bytes) {
         CK(cudaStreamSynchronize(c->s_compute));
@@ -450,6 +462,50 @@ int prepare_partition(pbk_ctx *c, u64 windows_ub, u64 windows_total)
     // a spilled key (bucket segment or bin full) is rare; the list is also used by Pass B
     TRY(ensure_overflow_for_batch(c, windows_total));
     return PBK_OK;
+}
+
+// Pass B, second form (PBK_PASSB2; k <= 32, unsharded): buckets [b0, b1) of the context's bucket store go through split_kernel into
+// per-sub-region segments and region_build_kernel builds every sub-region of the table in shared memory.  `was_touched`: the
+// table may hold entries (the sub-regions are then read first).  Returns 1 if the launches were queued, 0 if this table / plan
+// cannot take the route (the caller runs the first form), a negative status on error.
+int passb2_run(pbk_ctx *c, u32 b0, u32 b1, bool was_touched)
+{
+    if (!c->passb2_enabled || c->W != 1 || c->shard.n_shards > 1 || b1 <= b0) return 0;
+    Passb2Geom geom;
+    if (!passb2_geom(c->table, c->plan.n_buckets, &geom)) return 0;
+    const u64 sub_cap = passb2_sub_cap(c->store_windows_ub, geom.n_sub);
+    const size_t need = (size_t)geom.n_sub * sub_cap * 8;
+    if (need > c->sub_bytes || geom.n_sub > c->sub_cursor_cap) {
+        CK(cudaStreamSynchronize(c->s_compute));
+        dev_free(c, c->d_sub_keys, c->sub_bytes); dev_free(c, c->d_sub_cursor, c->sub_cursor_cap * 8);
+        c->d_sub_keys = c->d_sub_cursor = nullptr; c->sub_bytes = 0; c->sub_cursor_cap = 0;
+        if (dev_alloc(c, (void **)&c->d_sub_keys, need) != PBK_OK || dev_alloc(c, (void **)&c->d_sub_cursor, geom.n_sub * 8) != PBK_OK) {
+            DBG("pass B second form: no room for %.1f MB of sub-region segments, first form from here on", need / 1e6);
+            dev_free(c, c->d_sub_keys, need);
+            c->d_sub_keys = nullptr; c->err.clear(); c->passb2_enabled = false;
+            return 0;
+        }
+        c->sub_bytes = need; c->sub_cursor_cap = geom.n_sub;
+    }
+    DBG("pass B second form: buckets [%u,%u) of %u, %u sub-regions per bucket, sub_cap %llu, %s", b0, b1, c->plan.n_buckets, geom.F,
+        (unsigned long long)sub_cap, was_touched ? "table read" : "table known empty");
+    CK(cudaMemsetAsync(c->d_sub_cursor, 0, geom.n_sub * 8, c->s_compute));
+    { Span sp(c, LC_OTHER); launch_passb2_desc(c->d_bkt_cursor, c->plan.seg_cap, b0, b1, c->d_passb, c->s_compute); }
+    CK(cudaGetLastError());
+    {
+        Span sp(c, LC_INSERT);
+        launch_passb2_split(c->d_bkt_keys, c->plan.seg_cap, c->d_passb, b0, b1, geom, c->d_sub_keys, sub_cap, c->d_sub_cursor, c->d_ctr,
+                            c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+    }
+    CK(cudaGetLastError());
+    {
+        Span sp(c, LC_INSERT);
+        launch_passb2_build(c->d_sub_keys, sub_cap, c->d_sub_cursor, b0, b1, geom, c->table, was_touched || !c->passb2_fresh, c->d_ctr,
+                            c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+    }
+    CK(cudaGetLastError());
+    c->n_passb2 += 1;
+    return 1;
 }
 
 // ---- sub-batched path (k <= 32, host input): the chunks of a batch are counted in groups -- Pass A per chunk, then
@@ -466,15 +522,20 @@ struct Pipe {
 int pipe_finish_subbatch(pbk_ctx *c, Pipe &p)
 {
     if (p.in_sb == 0) return PBK_OK;
+    const bool was_touched = c->table_touched;
     TRY(table_ready(c));                             // Pass B is the first thing of a batch that touches the table
-    { Span sp(c, LC_OTHER); launch_passb_desc(c->d_bkt_cursor, c->plan.seg_cap, c->plan.n_buckets, c->table, c->remote, c->shard, c->d_passb, c->s_compute); }
-    CK(cudaGetLastError());
-    {
-        Span sp(c, LC_INSERT);
-        launch_bucket_insert_chained(c->d_bkt_keys, c->plan.seg_cap, c->d_passb, c->plan.n_buckets, c->table, c->remote, c->shard, c->d_ctr,
-                                     c->d_ovf, c->ovf_cap, c->sm_count, 3, c->s_compute);
+    const int second = passb2_run(c, 0, c->plan.n_buckets, was_touched);
+    if (second < 0) return second;
+    if (second == 0) {
+        { Span sp(c, LC_OTHER); launch_passb_desc(c->d_bkt_cursor, c->plan.seg_cap, c->plan.n_buckets, c->table, c->remote, c->shard, c->d_passb, c->s_compute); }
+        CK(cudaGetLastError());
+        {
+            Span sp(c, LC_INSERT);
+            launch_bucket_insert_chained(c->d_bkt_keys, c->plan.seg_cap, c->d_passb, c->plan.n_buckets, c->table, c->remote, c->shard, c->d_ctr,
+                                         c->d_ovf, c->ovf_cap, c->sm_count, 3, c->s_compute);
+        }
+        CK(cudaGetLastError());
     }
-    CK(cudaGetLastError());
     CK(cudaMemsetAsync(c->d_bkt_cursor, 0, PART_MAX_BUCKETS * 8, c->s_compute));
     p.in_sb = 0;
     p.cur += 1;
@@ -496,11 +557,14 @@ int pipe_end(pbk_ctx *c, Pipe &p)
 // one Pass B launch over buckets [b0, b1)
 int passb_launch(pbk_ctx *c, u32 b0, u32 b1)
 {
+    const bool was_touched = c->table_touched;
     TRY(table_ready(c));
     u64 total = 0;
     for (u32 b = b0; b < b1; ++b) total += c->h_bkt_cursor[b];
     DBG("pass B buckets [%u,%u) of %u: %llu keys, table %llu slots, occupied %llu", b0, b1, c->plan.n_buckets, total, c->table.cap, c->occupied);
-    {
+    const int second = passb2_run(c, b0, b1, was_touched);
+    if (second < 0) return second;
+    if (second == 0) {
         Span sp(c, LC_INSERT);
         launch_bucket_insert(c->d_bkt_keys, c->plan.seg_cap, c->h_bkt_cursor, c->h_passb, c->d_passb, b0, b1, c->plan.n_buckets,
                              c->table, c->remote, c->shard, c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
@@ -776,6 +840,7 @@ void release_all(pbk_ctx *c)
         if (c->ev_stage_free[i]) cudaEventDestroy(c->ev_stage_free[i]);
     }
     cudaFree(c->d_bkt_keys); cudaFree(c->d_bkt_cursor); if (c->h_bkt_cursor) cudaFreeHost(c->h_bkt_cursor);
+    cudaFree(c->d_sub_keys); cudaFree(c->d_sub_cursor);
     cudaFree(c->d_passb); if (c->h_passb) cudaFreeHost(c->h_passb);
     cudaFree(c->table.slots); cudaFree(c->remote.slots); cudaFree(c->d_ctr); cudaFree(c->d_ovf);
     cudaFree(c->d_len_hist); cudaFree(c->d_occ_hist); cudaFree(c->d_shard_counts);
@@ -890,6 +955,8 @@ int pbk_create(pbk_ctx **out, const pbk_config *cfg)
         if (cudaEventCreateWithFlags(&c->ev_pack[i], cudaEventDisableTiming) != cudaSuccess) return bail(PBK_E_CUDA);
     c->overlap_enabled = getenv("PBK_NO_OVERLAP") == nullptr;
     c->pipeline_enabled = !(cfg->flags & PBK_F_NO_PIPELINE) && getenv("PBK_NO_PIPELINE") == nullptr;
+    c->passb2_enabled = getenv("PBK_PASSB2") ? atoi(getenv("PBK_PASSB2")) != 0 : PASSB2_DEFAULT;
+    c->passb2_fresh = !(getenv("PBK_PASSB2_FRESH") && atoi(getenv("PBK_PASSB2_FRESH")) == 0);
     if (getenv("PBK_UNKNOWN_AS_N") && atoi(getenv("PBK_UNKNOWN_AS_N")) != 0) c->flags |= PBK_F_UNKNOWN_AS_N;
     if (cudaMallocHost((void **)&c->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(PBK_E_NOMEM);
     memset(c->h_ctr, 0, sizeof(Counters));
@@ -1134,6 +1201,7 @@ int pbk_reset(pbk_ctx *c, uint32_t k)
         if (c->table.slots) { Span sp(c, LC_OTHER); launch_table_init(c->table, c->s_compute); }
         if (c->remote.slots) { Span sp(c, LC_OTHER); launch_table_init(c->remote, c->s_compute); }
     }
+    c->table_touched = false;                          // (zero-filled, or gone and zero-filled again when it is re-created)
     c->remote_dirty = false; c->stage_gen += 1;
     c->seed_rec.clear();
     c->k = k; c->W = W;

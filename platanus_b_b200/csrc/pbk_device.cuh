@@ -161,6 +161,10 @@ __device__ __forceinline__ void st_cg_u64(u64 *p, u64 v)
 {
     asm volatile("st.global.cg.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_cg_u64x2(u64 *p, u64 a, u64 b)
+{
+    asm volatile("st.global.cg.v2.u64 [%0], {%1,%2};" :: "l"(p), "l"(a), "l"(b) : "memory");
+}
 __device__ __forceinline__ void st_release_u32(u32 *p, u32 v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
@@ -235,6 +239,7 @@ inline void st_cg_256(void *p, u64 a, u64 b, u64 c, u64 d)
 inline void red_add_u32(u32 *p, u32 v) { *p += v; }
 inline void red_add_u64(u64 *p, u64 v) { *p += v; }
 inline void st_cg_u64(u64 *p, u64 v) { *p = v; }
+inline void st_cg_u64x2(u64 *p, u64 a, u64 b) { p[0] = a; p[1] = b; }
 inline void st_release_u32(u32 *p, u32 v) { *p = v; }
 inline u64 l2_keep_policy() { return 0; }
 inline u64 atom_add_keep_u64(u64 *p, u64 v, u64) { u64 o = *p; *p += v; return o; }

@@ -467,6 +467,59 @@ void launch_bucket_insert_chained(const u64 *bkt_keys, u64 seg_cap, const void *
             Table<1>(table.slots, table.cap), Table<1>(remote.slots, remote.cap), 1, 0, ctr, overflow_keys, overflow_cap, opts);
 }
 
+// ---- Pass B, second form (k <= 32, unsharded): split_kernel + region_build_kernel (see pbk_kernels_impl.cuh) ----------------
+// The route needs Pass A's buckets to be whole groups of sub-regions: a power-of-two bucket count (its bucket function is then
+// the top hash bits) and a table of at least one sub-region per bucket.
+bool passb2_geom(TableView table, u32 n_buckets, Passb2Geom *out)
+{
+    if (table.words != 1 || !table.slots || n_buckets == 0 || (n_buckets & (n_buckets - 1))) return false;
+    if (table.cap & (table.cap - 1)) return false;
+    const u64 n_sub = table.cap >> BUILD_LOG2_SLOTS;
+    if (n_sub < n_buckets || n_sub / n_buckets > (u64)SPLIT_MAX_F) return false;
+    out->n_sub = n_sub;
+    out->F = (u32)(n_sub / n_buckets);
+    out->sub_shift = ct_geom(table.cap).rbits + BUILD_LOG2_SLOTS;
+    return true;
+}
+
+// entries per sub-region segment for a bucket store of up to `windows_ub` keys: the mean plus a half (a sub-region holds a few
+// thousand distinct keys, so its share of a read set's instances varies by several per cent; keys beyond a full segment go
+// through the overflow list), even (16-byte aligned segments)
+u64 passb2_sub_cap(u64 windows_ub, u64 n_sub)
+{
+    const u64 mean = windows_ub / n_sub + 1;
+    return (mean + mean / 2 + 1024 + 1) & ~1ull;
+}
+
+void launch_passb2_desc(const u64 *d_cursor, u64 seg_cap, u32 b_first, u32 b_end, void *d_desc, cudaStream_t st)
+{
+    passb_desc_kernel<<<1, PART_MAX_BUCKETS, 0, st>>>(d_cursor + b_first, seg_cap, b_end - b_first, (u32)SPLIT_TILE_KEYS, nullptr, 0, nullptr, 0,
+        8u, 0, (u64 *)d_desc, (PassBBucket *)((char *)d_desc + 16));
+}
+
+void launch_passb2_split(const u64 *bkt_keys, u64 seg_cap, const void *d_desc, u32 b_first, u32 b_end, const Passb2Geom &geom,
+                         u64 *d_sub_keys, u64 sub_cap, u64 *d_sub_cursor, Counters *ctr, u64 *overflow_keys, u64 overflow_cap,
+                         int sm_count, cudaStream_t st)
+{
+    const PassBBucket *d_bk = (const PassBBucket *)((const char *)d_desc + 16);
+    const size_t smem = (size_t)SPLIT_TILE_KEYS * 8;
+    cudaFuncSetAttribute(split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int ctas = getenv("PBK_SPLIT_CTAS") ? std::max(1, atoi(getenv("PBK_SPLIT_CTAS"))) : 2;
+    split_kernel<<<sm_count * ctas, SPLIT_THREADS, smem, st>>>(bkt_keys, seg_cap, d_bk, b_first, b_end - b_first, geom.F, geom.sub_shift,
+        d_sub_keys, sub_cap, d_sub_cursor, ctr, overflow_keys, overflow_cap);
+}
+
+void launch_passb2_build(const u64 *d_sub_keys, u64 sub_cap, const u64 *d_sub_cursor, u32 b_first, u32 b_end, const Passb2Geom &geom,
+                         TableView table, bool load_existing, Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count,
+                         cudaStream_t st)
+{
+    const size_t smem = (size_t)BUILD_SLOTS * 8;
+    cudaFuncSetAttribute(region_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int ctas = getenv("PBK_BUILD_CTAS") ? std::max(1, atoi(getenv("PBK_BUILD_CTAS"))) : 3;
+    region_build_kernel<<<sm_count * ctas, BUILD_THREADS, smem, st>>>(d_sub_keys, sub_cap, d_sub_cursor, (u64)b_first * geom.F,
+        (u64)b_end * geom.F, Table<1>(table.slots, table.cap), load_existing ? 1 : 0, ctr, overflow_keys, overflow_cap);
+}
+
 void launch_table_init(TableView t, cudaStream_t st)
 {
     cudaMemsetAsync(t.slots, 0, t.bytes(), st);        // both slot formats use all-zero for "empty"

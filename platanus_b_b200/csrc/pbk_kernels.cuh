@@ -95,6 +95,26 @@ void launch_bucket_insert_chained(const u64 *bkt_keys, u64 seg_cap, const void *
                                   TableView remote, ShardInfo shard, Counters *ctr, u64 *overflow_keys, u64 overflow_cap,
                                   int sm_count, int ctas_per_sm, cudaStream_t st);
 
+// k <= 32, unsharded table, second form of Pass B (PBK_PASSB2): every bucket's keys are split once more by SUB-REGION of the
+// table (split_kernel), and a CTA then builds each 64 KB sub-region in shared memory (region_build_kernel) -- no L2 atomics.
+struct Passb2Geom {
+    u32 F;            // sub-regions per bucket
+    u64 n_sub;        // sub-regions of the whole table
+    int sub_shift;    // hash >> sub_shift = global sub-region
+};
+bool passb2_geom(TableView table, u32 n_buckets, Passb2Geom *out);        // false: this table / bucket count cannot take the route
+u64  passb2_sub_cap(u64 windows_ub, u64 n_sub);                            // entries per sub-region segment
+// tile map of buckets [b_first, b_end) for split_kernel, built on the device from the cursors
+void launch_passb2_desc(const u64 *d_cursor, u64 seg_cap, u32 b_first, u32 b_end, void *d_desc, cudaStream_t st);
+// d_sub_keys: geom.n_sub segments of sub_cap hashes, d_sub_cursor: geom.n_sub fill counts (zeroed by the caller)
+void launch_passb2_split(const u64 *bkt_keys, u64 seg_cap, const void *d_desc, u32 b_first, u32 b_end, const Passb2Geom &geom,
+                         u64 *d_sub_keys, u64 sub_cap, u64 *d_sub_cursor, Counters *ctr, u64 *overflow_keys, u64 overflow_cap,
+                         int sm_count, cudaStream_t st);
+// load_existing = false: nothing has been inserted since the table was zero-filled
+void launch_passb2_build(const u64 *d_sub_keys, u64 sub_cap, const u64 *d_sub_cursor, u32 b_first, u32 b_end, const Passb2Geom &geom,
+                         TableView table, bool load_existing, Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count,
+                         cudaStream_t st);
+
 // ---- table ------------------------------------------------------------------------------------
 void launch_table_init(TableView t, cudaStream_t st);
 // move every entry of `from` into `to` (capacity change)

@@ -1483,6 +1483,207 @@ bucket_insert_gather_staged_kernel(const __grid_constant__ KeyxSources srcs, u64
     bucket_insert_compact_body<2, true>(nullptr, seg_cap, bk, b_first, b_end, ticket, table, table, 1u, 0u, ctr, ovf, ovf_cap, opts, &srcs);
 }
 
+// =================================================================================================
+// Pass B, second form for one-word keys on an unsharded table: split + build (PBK_PASSB2).
+//
+// bucket_insert_compact_kernel above sits at the rate of the L2's 64-bit atomics (one per k-mer instance, ~100 G/s).  The only
+// way under that is not to send the increments to the L2 at all: here a CTA owns a SUB-REGION of the table -- BUILD_SLOTS
+// consecutive slots, 64 KB -- outright, holds it in shared memory while every key whose home slot lies in it is inserted
+// with shared-memory atomics, and writes it back with coalesced 16-byte stores.  Nothing is shared between CTAs, so there is
+// no claim/publish protocol across the chip: a slot word changes from 0 to (tag | 1) in ONE 64-bit shared-memory
+// compare-and-swap, and a hit is a 32-bit shared-memory add on its low half (the count field).
+// That needs the keys sorted by sub-region.  Pass A's P buckets (16 MB table regions) stay as they are; split_kernel takes a
+// bucket's keys tile by tile and scatters them into the F = region / sub-region segments of that bucket (second-level
+// partition on the next log2 F hash bits: counting sort of the tile in shared memory, one reservation per segment and tile,
+// coalesced copy-out), region_build_kernel then drains segment after segment.  DRAM sees the keys twice more (8 B written,
+// 8 B read per instance) -- sequential traffic the HBM has room for -- and the table once, written only when the table was
+// empty before (pbk_reset): `load_existing` = 0.
+// A probe sequence that would leave the sub-region (or pass CT_MAX_DISP) ends on the overflow list like every other key that
+// finds no slot; drain_overflow inserts those with the global protocol afterwards, which may place them in the next
+// sub-region's first slots -- to later launches just occupied slots with a foreign tag.
+// =================================================================================================
+constexpr int SPLIT_THREADS = 512;
+constexpr int SPLIT_KPT = 16;
+constexpr int SPLIT_MAX_F = 512;                     // sub-regions per bucket
+#ifndef PBK_CPU_EMUL
+constexpr int SPLIT_LAUNCH_THREADS = SPLIT_THREADS;
+#else
+constexpr int SPLIT_LAUNCH_THREADS = 1;
+#endif
+constexpr int SPLIT_TILE_KEYS = SPLIT_LAUNCH_THREADS * SPLIT_KPT;
+constexpr int BUILD_THREADS = 256;
+constexpr int BUILD_LOG2_SLOTS = 13;
+constexpr u32 BUILD_SLOTS = 1u << BUILD_LOG2_SLOTS;  // 64 KB of compact slots: three CTAs per SM
+constexpr int BUILD_ILP = 4;                         // 16-byte key loads a thread keeps in flight
+
+// bk: tile map of buckets [b_first, b_first + nb) with tiles of blockDim * SPLIT_KPT keys (passb_desc_kernel).
+// sub_shift = rbits + BUILD_LOG2_SLOTS: h >> sub_shift is the global sub-region of hash h, its low log2 F bits the
+// sub-region within the bucket.  sub_keys: [global sub-region][sub_cap] hashes, sub_cursor: their fill counts (zeroed).
+__global__ void __launch_bounds__(SPLIT_THREADS, 2)
+split_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, const PassBBucket *__restrict__ bk, u32 b_first, u32 nb,
+             u32 F, int sub_shift, u64 *__restrict__ sub_keys, u64 sub_cap, u64 *sub_cursor, Counters *ctr, u64 *ovf, u64 ovf_cap)
+{
+    PBK_DYN_SMEM(u64, s_sorted);                     // the tile's keys in sub-region order: blockDim * SPLIT_KPT entries
+    __shared__ u32 s_cnt[SPLIT_MAX_F], s_off[SPLIT_MAX_F];
+    __shared__ u64 s_base[SPLIT_MAX_F];
+    const u32 tid = threadIdx.x, nthreads = blockDim.x, tile_keys = nthreads * SPLIT_KPT;
+    const u32 wsize = nthreads < 32u ? nthreads : 32u;
+    const u64 n_tiles = bk[nb].tile_start;
+    u32 lb = 0;
+    for (u64 t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        while (bk[lb + 1].tile_start <= t) ++lb;
+        const u64 j = t - bk[lb].tile_start;
+        const u32 n = (u32)min((u64)tile_keys, bk[lb].n_keys - j * tile_keys);
+        const u64 *src = bkt_hash + (u64)(b_first + lb) * seg_cap + j * tile_keys;
+        for (u32 f = tid; f < F; f += nthreads) s_cnt[f] = 0;
+        __syncthreads();
+        // 1. keys into registers, each counted into its sub-region (the count's old value = the key's rank there)
+        u64 h[SPLIT_KPT];
+        u32 sp[SPLIT_KPT];                           // sub-region << 16 | rank (rank < tile_keys <= 8192)
+        if (n == tile_keys) {                        // full tile: 16-byte loads (tiles start 16-byte aligned: even seg_cap)
+#pragma unroll
+            for (int p = 0; p < SPLIT_KPT / 2; ++p) {
+                const ulonglong2 v = ld_stream_u64x2(src + 2 * ((u32)p * nthreads + tid));
+                h[2 * p] = v.x; h[2 * p + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < SPLIT_KPT / 2; ++p) {
+                const u32 i = 2 * ((u32)p * nthreads + tid);
+                h[2 * p] = i < n ? ld_stream_u64(src + i) : 0;
+                h[2 * p + 1] = i + 1 < n ? ld_stream_u64(src + i + 1) : 0;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < SPLIT_KPT; ++q) {
+            const u32 i = 2 * ((u32)(q >> 1) * nthreads + tid) + (u32)(q & 1);
+            sp[q] = 0;
+            if (i < n) {
+                const u32 sub = (u32)(h[q] >> sub_shift) & (F - 1u);
+                sp[q] = (sub << 16) | atomicAdd(&s_cnt[sub], 1u);
+            }
+        }
+        __syncthreads();
+        // 2. exclusive prefix of the counts (one warp, a run of consecutive sub-regions per lane)
+        if (tid < wsize) {
+            const u32 per = (F + wsize - 1) / wsize, f0 = tid * per;
+            u32 sum = 0;
+            for (u32 i = 0; i < per; ++i) if (f0 + i < F) sum += s_cnt[f0 + i];
+            u32 incl = sum;
+            for (u32 o = 1; o < wsize; o <<= 1) {
+                const u32 v = __shfl_up_sync(0xffffffffu, incl, (int)o);
+                if (tid >= o) incl += v;
+            }
+            u32 run = incl - sum;
+            for (u32 i = 0; i < per; ++i) if (f0 + i < F) { s_off[f0 + i] = run; run += s_cnt[f0 + i]; }
+        }
+        __syncthreads();
+        // 3. one reservation per non-empty sub-region (all in flight together), keys into sub-region order
+        for (u32 f = tid; f < F; f += nthreads) {
+            const u32 c = s_cnt[f];
+            s_base[f] = c ? atomicAdd(&sub_cursor[(u64)(b_first + lb) * F + f], (u64)c) : 0ull;
+        }
+#pragma unroll
+        for (int q = 0; q < SPLIT_KPT; ++q) {
+            const u32 i = 2 * ((u32)(q >> 1) * nthreads + tid) + (u32)(q & 1);
+            if (i < n) s_sorted[s_off[sp[q] >> 16] + (sp[q] & 0xFFFFu)] = h[q];
+        }
+        __syncthreads();
+        // 4. copy-out: a group of 16 lanes per sub-region (a full tile brings tile_keys / F keys for each: 256 B at F = 256)
+        {
+            const u32 gs = nthreads < 16u ? nthreads : 16u;
+            const u32 gl = tid % gs, n_groups = nthreads / gs;
+            for (u32 f = tid / gs; f < F; f += n_groups) {
+                const u32 c = s_cnt[f];
+                if (c == 0) continue;
+                const u64 g0 = s_base[f];
+                const u64 *from = s_sorted + s_off[f];
+                u64 *to = sub_keys + ((u64)(b_first + lb) * F + f) * sub_cap + g0;
+                if (g0 + c <= sub_cap) {
+                    for (u32 i = gl; i < c; i += gs) st_stream_u64(to + i, from[i]);
+                } else {
+                    for (u32 i = gl; i < c; i += gs) {
+                        if (g0 + i < sub_cap) st_stream_u64(to + i, from[i]);
+                        else spill_stored<1>(from + i, ctr, ovf, ovf_cap);        // segment full: through the overflow list
+                    }
+                }
+            }
+        }
+        __syncthreads();                             // s_cnt / s_off / s_sorted are rewritten by the next tile
+    }
+}
+
+// insert-or-increment of the key with hash h in the shared-memory copy of its sub-region
+__device__ __forceinline__ void build_insert(u64 *s_tab, const CtGeom &g, u64 h, u32 &newk, Counters *ctr, u64 *ovf, u64 ovf_cap)
+{
+    const u32 home = (u32)(h >> g.rbits) & (BUILD_SLOTS - 1u);
+    const u64 rem = h << (64 - g.rbits);             // remainder in the top bits, as in the slot word
+#pragma unroll 1
+    for (u32 d = 0; d <= (u32)CT_MAX_DISP && home + d < BUILD_SLOTS; ++d) {
+        u64 *s = s_tab + home + d;
+        const u64 tag = rem | ((u64)(d + 1) << g.cbits);
+        u64 cur = *reinterpret_cast<volatile u64 *>(s);
+        if (cur == 0) {
+            cur = atomicCAS(s, 0ull, tag | 1ull);
+            if (cur == 0) { ++newk; return; }        // the slot was empty and is ours, count 1
+        }
+        if (((cur ^ tag) >> g.cbits) == 0) {         // our key: +1 on the count field (low half of the word), unless saturated
+            if ((cur & g.cmask) < (u64)COUNT_SAT) atomicAdd(reinterpret_cast<u32 *>(s), 1u);
+            return;
+        }
+    }
+    const u64 k0 = fmix64_inverse(h);
+    spill_key<1>(&k0, ctr, ovf, ovf_cap);
+}
+
+// sub-regions [g_first, g_end) of the table, one CTA at a time each; load_existing = 0: the table is known to be all zero
+// (nothing has touched it since it was cleared), so the sub-region is not read
+__global__ void __launch_bounds__(BUILD_THREADS, 3)
+region_build_kernel(const u64 *__restrict__ sub_keys, u64 sub_cap, const u64 *__restrict__ sub_cursor, u64 g_first, u64 g_end,
+                    Table<1> table, int load_existing, Counters *ctr, u64 *ovf, u64 ovf_cap)
+{
+    PBK_DYN_SMEM(u64, s_tab);                        // BUILD_SLOTS slot words
+    const u32 tid = threadIdx.x, nthreads = blockDim.x;
+    const CtGeom g = table.g;
+    u32 newk = 0;
+    for (u64 r = g_first + blockIdx.x; r < g_end; r += gridDim.x) {
+        const u64 n = min(sub_cursor[r], sub_cap);
+        if (n == 0) continue;                        // (same for every thread) nothing to add: the sub-region stays as it is
+        u64 *region = table.slots + r * BUILD_SLOTS;
+        if (load_existing) {
+            for (u32 i = tid; i < BUILD_SLOTS / 2; i += nthreads) {
+                const ulonglong2 v = ld_stream_u64x2(region + 2 * i);
+                s_tab[2 * i] = v.x; s_tab[2 * i + 1] = v.y;
+            }
+        } else {
+            for (u32 i = tid; i < BUILD_SLOTS; i += nthreads) s_tab[i] = 0;
+        }
+        __syncthreads();
+        const u64 *src = sub_keys + r * sub_cap;     // 16-byte aligned: sub_cap is even
+        for (u64 i0 = 0; i0 < n; i0 += (u64)nthreads * 2 * BUILD_ILP) {
+            ulonglong2 v[BUILD_ILP];
+#pragma unroll
+            for (int j = 0; j < BUILD_ILP; ++j) {
+                const u64 i = i0 + 2 * ((u64)j * nthreads + tid);
+                if (i + 1 < n) v[j] = ld_stream_u64x2(src + i);
+                else v[j] = make_ulonglong2(i < n ? ld_stream_u64(src + i) : 0ull, 0ull);
+            }
+#pragma unroll
+            for (int j = 0; j < BUILD_ILP; ++j) {
+                const u64 i = i0 + 2 * ((u64)j * nthreads + tid);
+                if (i < n) build_insert(s_tab, g, v[j].x, newk, ctr, ovf, ovf_cap);
+                if (i + 1 < n) build_insert(s_tab, g, v[j].y, newk, ctr, ovf, ovf_cap);
+            }
+        }
+        __syncthreads();
+        for (u32 i = tid; i < BUILD_SLOTS / 2; i += nthreads)
+            st_cg_u64x2(region + 2 * i, s_tab[2 * i], s_tab[2 * i + 1]);
+        __syncthreads();                             // the next sub-region overwrites s_tab
+    }
+    newk = warp_sum_u32(newk);
+    if ((tid & 31) == 0 && newk) atomicAdd(&ctr->new_keys, (u64)newk);
+}
+
 // Pass B for multi-word keys (k > 32), batched like the one-word kernel: a thread works on PASSBW_KPT<W> new keys plus
 // one deferred key per round; the state words of all their slots are loaded together, then the claims (CAS) and the
 // key words of the occupied slots, then the matching keys get their reduction.  A slot that is locked by a claimer, a

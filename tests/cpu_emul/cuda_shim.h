@@ -54,5 +54,6 @@ static inline bool __any_sync(unsigned, bool p) { return p; }
 template <typename T> static inline unsigned __match_any_sync(unsigned, T) { return 1u; }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T, int) { return (T)0; }   // other lanes hold 0
+template <typename T> static inline T __shfl_up_sync(unsigned, T v, int) { return v; }    // lane 0 never uses the result
 using std::max;
 using std::min;
