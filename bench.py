@@ -59,10 +59,11 @@ def algorithmic_bytes_per_instance(read_len: int, k: int) -> float:
     return read_len / (read_len - k + 1.0) + 64.0
 
 
-def ncu_traffic_bytes():
+def ncu_traffic_bytes(split_build=False):
     """dram__bytes_read.sum + dram__bytes_write.sum of one step's Pass A + Pass B launches, from the committed
-    `ncu --set full` capture of this workload (profiles/*_traffic.json); None when there is no capture."""
-    path = os.path.join(ROOT, "profiles", "r2a_traffic.json")
+    `ncu --set full` capture of this workload (profiles/*_traffic.json); None when there is no capture of the form of
+    Pass B that ran."""
+    path = os.path.join(ROOT, "profiles", "r2k_traffic_split_build.json" if split_build else "r2a_traffic.json")
     try:
         return float(json.load(open(path))["dram_bytes_per_step"])
     except Exception:
@@ -509,22 +510,28 @@ def main_ours(args):
     ms_pair = d_res["ms_count_elapsed"] / args.steps
     direct = d_res["ms_count"] - d_res["ms_partition"] - d_res["ms_insert"]      # non-partitioned launches (small batches)
     achieved = bpi * n_inst_local / (ms_pair * 1e-3) / 1e9 if ms_pair > 0 else 0.0
+    # which form of Pass B ran (k <= 32, one GPU): the L2-atomic one, or split + shared-memory build (pbk_stats.n_split_build)
+    split_build = d_res.get("n_split_build", 0) > 0
+    insert_name = "split_kernel + region_build_kernel" if split_build else "bucket_insert_compact_kernel"
     roofline = {"bound": "hbm", "kernel": ("partition_kernel<1, KEYX> + bucket_insert_gather_kernel (Pass A into the rank's own owner-major store + Pass B "
                                           "reading every peer's store over NVLink: each instance goes through both exactly once)" if pull else
                                           "partition_kernel<1, KEYX> + bucket_insert_gather_kernel (Pass A into the all-to-all send "
                                           "buffer + Pass B over the received keys: each instance goes through both exactly once)" if keyx else
                                           f"partition_kernel<{W}> + bucket_insert_wide_kernel<{W}> (Pass A + Pass B, multi-word keys: "
                                           "each instance goes through both exactly once)" if W > 1 else
+                                          "partition_kernel<1> + split_kernel + region_build_kernel (Pass A, then Pass B in its second form: keys split by "
+                                          "64 KB sub-region of the table, every sub-region built in shared memory; each instance goes through all three "
+                                          "exactly once)" if split_build else
                                           "partition_kernel<1> + bucket_insert_compact_kernel<0> (Pass A + Pass B: "
                                           "each instance goes through both exactly once)"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic_bytes() if (W == 1 and world == 1 and args.workload == "C1" and args.scale == 1.0) else None,
+                "traffic": ncu_traffic_bytes(split_build) if (W == 1 and world == 1 and args.workload == "C1" and args.scale == 1.0) else None,
                 "traffic_source": "committed ncu --set full capture of this workload (profiles/), not measured in this run", "peak_source": peak_src, "algorithmic_bytes_per_instance": bpi,
                 "instances_per_launch": n_inst_local, "ms_per_launch": ms_pair,
                 "launches_per_step": {"partition_kernel": d_res["launches_partition"] / args.steps,
-                                      "bucket_insert_compact_kernel": d_res["launches_insert"] / args.steps},
+                                      insert_name: d_res["launches_insert"] / args.steps},
                 "ms_per_step": {"partition_kernel": d_res["ms_partition"] / args.steps,
-                                "bucket_insert_compact_kernel": d_res["ms_insert"] / args.steps,
+                                insert_name: d_res["ms_insert"] / args.steps,
                                 "direct_count_kernel": direct / args.steps},
                 "sub_batched_behind_h2d_copies": {"device_resident": bool(d_res["n_pipelined_batches"] > 0), "host_buffers": bool(d_e2e["n_pipelined_batches"] > 0)},
                 "kernel_share_of_step": ms_pair * args.steps / max(ms_inst, 1e-9),
@@ -532,7 +539,8 @@ def main_ours(args):
                 "frac_of_step": bpi * n_inst_local * args.steps / (ms_res * 1e-3) / 1e9 / peak,
                 "atomic_bound_note": "random 64-bit atomics with return: 125 G/s on an L2-resident table, 22 G/s on a table >> L2 "
                                      "(profiles/r1a_atomics_microbench.json, profiles/r1b_atomics_sweep.json, profiles/r1c_warp_ops_microbench.jsonl); Pass B alone "
-                                     "runs at instances / ms_per_step.bucket_insert_compact_kernel"}
+                                     "runs at instances / ms_per_step.bucket_insert_compact_kernel; its second form (split_kernel + region_build_kernel) "
+                                     "sends no atomics to the L2 at all"}
 
     line = None
     if rank == 0:

@@ -99,6 +99,8 @@ typedef struct pbk_stats {
     double   ms_insert;
     double   ms_count_elapsed;   /* counting phase, begin to end (= ms_count: the launches are serial)          */
     uint64_t n_pipelined_batches;/* pushes whose Pass A / tile map / Pass B were chained on the GPU (no host sync) */
+    uint64_t n_split_build;      /* Pass B runs that took the second form: keys split by 64 KB sub-region of the table, every
+                                    sub-region built in shared memory (split_kernel + region_build_kernel; k <= 32, unsharded)      */
 } pbk_stats;
 
 const char *pbk_strerror(int status);

@@ -64,7 +64,7 @@ class PbkStats(C.Structure):
                 ("ms_other", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("launches_partition", C.c_uint64), ("launches_insert", C.c_uint64),
                 ("ms_partition", C.c_double), ("ms_insert", C.c_double), ("ms_count_elapsed", C.c_double),
-                ("n_pipelined_batches", C.c_uint64)]
+                ("n_pipelined_batches", C.c_uint64), ("n_split_build", C.c_uint64)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -218,6 +218,16 @@ int table_ready(pbk_ctx *c)
     return PBK_OK;
 }
 
+// the same ordering for the three Pass B call sites, which decide themselves (at launch time) whether the table may hold
+// entries: the flag keeps its value here and is set once their launch is queued
+int table_ordered(pbk_ctx *c)
+{
+    const bool touched = c->table_touched;
+    const int rc = table_ready(c);
+    c->table_touched = touched;
+    return rc;
+}
+
 int table_alloc(pbk_ctx *c, TableView *t, u64 slots)
 {
     TRY(table_ready(c));
@@ -334,6 +344,7 @@ int drain_overflow(pbk_ctx *c)
         if (rc == PBK_OK) {
             Span sp(c, LC_COUNT);
             launch_insert_records(tmp, n, true, c->table, c->remote, c->shard, c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+            c->table_touched = true;                 // (the table may have been created after the table_ready() above)
         }
         if (rc == PBK_OK) rc = read_counters(c);
         else cudaStreamSynchronize(c->s_compute);
@@ -419,6 +430,7 @@ int count_range(pbk_ctx *c, u64 w0, u64 w1)
         Span sp(c, LC_COUNT);
         launch_count(c->d_stream_raw + STREAM_PAD_WORDS, c->d_nflag_raw + STREAM_PAD_WORDS, c->d_rflag_raw + STREAM_PAD_WORDS,
                      w0, w1, (int)c->k, c->table, c->remote, c->shard, c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+        c->table_touched = true;
     }
     CK(cudaGetLastError());
     TRY(read_counters(c));
@@ -464,16 +476,24 @@ int prepare_partition(pbk_ctx *c, u64 windows_ub, u64 windows_total)
     return PBK_OK;
 }
 
-// Pass B, second form (PBK_PASSB2; k <= 32, unsharded): buckets [b0, b1) of the context's bucket store go through split_kernel into
-// per-sub-region segments and region_build_kernel builds every sub-region of the table in shared memory.  `was_touched`: the
-// table may hold entries (the sub-regions are then read first).  Returns 1 if the launches were queued, 0 if this table / plan
-// cannot take the route (the caller runs the first form), a negative status on error.
-int passb2_run(pbk_ctx *c, u32 b0, u32 b1, bool was_touched)
+// Pass B, second form (PBK_PASSB2; k <= 32): the keys go through split_kernel into per-sub-region segments and
+// region_build_kernel builds every sub-region of the table in shared memory.
+//   srcs == nullptr  buckets [d0, d1) of the context's own bucket store (unsharded table)
+//   srcs             key exchange: descriptors [d0, d1) of the n_src x n_regions (region-major) sources -- the all-to-all
+//                    receive buffer, or the peers' stores read in place over NVLink (pull form); d0, d1 multiples of n_src
+// If nothing has touched the table since it was zero-filled (c->table_touched) the sub-regions are not read.  Returns 1 if the
+// launches were queued, 0 if this table / plan cannot take the route (the caller runs the first form), a negative status on error.
+int passb2_run(pbk_ctx *c, const KeyxSources *srcs, u32 d0, u32 d1)
 {
-    if (!c->passb2_enabled || c->W != 1 || c->shard.n_shards > 1 || b1 <= b0) return 0;
+    const bool was_touched = c->table_touched;
+    if (!c->passb2_enabled || c->W != 1 || d1 <= d0) return 0;
+    if (!srcs && c->shard.n_shards > 1) return 0;       // (record exchange: foreign keys go to the remote-staging table)
+    const u32 G = srcs ? c->shard.n_shards : 1u;
+    const u32 n_desc = srcs ? c->keyx_plan.n_buckets : c->plan.n_buckets, n_regions = n_desc / G;
+    const u64 seg_cap = srcs ? c->keyx_plan.seg_cap : c->plan.seg_cap;
     Passb2Geom geom;
-    if (!passb2_geom(c->table, c->plan.n_buckets, &geom)) return 0;
-    const u64 sub_cap = passb2_sub_cap(c->store_windows_ub, geom.n_sub);
+    if (!passb2_geom(c->table, n_regions, &geom) || d0 % G || d1 % G) return 0;
+    const u64 sub_cap = passb2_sub_cap(srcs ? c->keyx_max_windows : c->store_windows_ub, geom.n_sub);
     const size_t need = (size_t)geom.n_sub * sub_cap * 8;
     if (need > c->sub_bytes || geom.n_sub > c->sub_cursor_cap) {
         CK(cudaStreamSynchronize(c->s_compute));
@@ -487,20 +507,24 @@ int passb2_run(pbk_ctx *c, u32 b0, u32 b1, bool was_touched)
         }
         c->sub_bytes = need; c->sub_cursor_cap = geom.n_sub;
     }
-    DBG("pass B second form: buckets [%u,%u) of %u, %u sub-regions per bucket, sub_cap %llu, %s", b0, b1, c->plan.n_buckets, geom.F,
+    DBG("pass B second form: descriptors [%u,%u) of %u (%u sources), %u sub-regions per region, sub_cap %llu, %s", d0, d1, n_desc, G, geom.F,
         (unsigned long long)sub_cap, was_touched ? "table read" : "table known empty");
     CK(cudaMemsetAsync(c->d_sub_cursor, 0, geom.n_sub * 8, c->s_compute));
-    { Span sp(c, LC_OTHER); launch_passb2_desc(c->d_bkt_cursor, c->plan.seg_cap, b0, b1, c->d_passb, c->s_compute); }
+    {
+        Span sp(c, LC_OTHER);
+        if (srcs) launch_passb2_desc_gather(*srcs, seg_cap, G, n_regions, c->d_passb, c->s_compute);
+        else launch_passb2_desc(c->d_bkt_cursor, seg_cap, n_desc, c->d_passb, c->s_compute);
+    }
     CK(cudaGetLastError());
     {
         Span sp(c, LC_INSERT);
-        launch_passb2_split(c->d_bkt_keys, c->plan.seg_cap, c->d_passb, b0, b1, geom, c->d_sub_keys, sub_cap, c->d_sub_cursor, c->d_ctr,
+        launch_passb2_split(c->d_bkt_keys, srcs, G, seg_cap, c->d_passb, d0, d1, geom, c->d_sub_keys, sub_cap, c->d_sub_cursor, c->d_ctr,
                             c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
     }
     CK(cudaGetLastError());
     {
         Span sp(c, LC_INSERT);
-        launch_passb2_build(c->d_sub_keys, sub_cap, c->d_sub_cursor, b0, b1, geom, c->table, was_touched || !c->passb2_fresh, c->d_ctr,
+        launch_passb2_build(c->d_sub_keys, sub_cap, c->d_sub_cursor, d0 / G, d1 / G, geom, c->table, was_touched || !c->passb2_fresh, c->d_ctr,
                             c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
     }
     CK(cudaGetLastError());
@@ -522,10 +546,10 @@ struct Pipe {
 int pipe_finish_subbatch(pbk_ctx *c, Pipe &p)
 {
     if (p.in_sb == 0) return PBK_OK;
-    const bool was_touched = c->table_touched;
-    TRY(table_ready(c));                             // Pass B is the first thing of a batch that touches the table
-    const int second = passb2_run(c, 0, c->plan.n_buckets, was_touched);
+    TRY(table_ordered(c));                           // Pass B is the first thing of a batch that touches the table
+    const int second = passb2_run(c, nullptr, 0, c->plan.n_buckets);
     if (second < 0) return second;
+    c->table_touched = true;
     if (second == 0) {
         { Span sp(c, LC_OTHER); launch_passb_desc(c->d_bkt_cursor, c->plan.seg_cap, c->plan.n_buckets, c->table, c->remote, c->shard, c->d_passb, c->s_compute); }
         CK(cudaGetLastError());
@@ -557,13 +581,13 @@ int pipe_end(pbk_ctx *c, Pipe &p)
 // one Pass B launch over buckets [b0, b1)
 int passb_launch(pbk_ctx *c, u32 b0, u32 b1)
 {
-    const bool was_touched = c->table_touched;
-    TRY(table_ready(c));
+    TRY(table_ordered(c));
     u64 total = 0;
     for (u32 b = b0; b < b1; ++b) total += c->h_bkt_cursor[b];
     DBG("pass B buckets [%u,%u) of %u: %llu keys, table %llu slots, occupied %llu", b0, b1, c->plan.n_buckets, total, c->table.cap, c->occupied);
-    const int second = passb2_run(c, b0, b1, was_touched);
+    const int second = passb2_run(c, nullptr, b0, b1);
     if (second < 0) return second;
+    c->table_touched = true;
     if (second == 0) {
         Span sp(c, LC_INSERT);
         launch_bucket_insert(c->d_bkt_keys, c->plan.seg_cap, c->h_bkt_cursor, c->h_passb, c->d_passb, b0, b1, c->plan.n_buckets,
@@ -875,6 +899,7 @@ int apply_seeds(pbk_ctx *c)
     c->h2d_bytes += bytes;
     if (rc == PBK_OK) {
         { Span sp(c, LC_OTHER); launch_override_records(d_rec, n, c->table, c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute); }
+        c->table_touched = true;
         if (cudaGetLastError() != cudaSuccess) rc = fail(c, PBK_E_CUDA, "override launch failed");
     }
     if (rc == PBK_OK) rc = read_counters(c);
@@ -1145,6 +1170,7 @@ int pbk_get_stats(const pbk_ctx *cc, pbk_stats *out)
     out->h2d_bytes = c->h2d_bytes; out->d2h_bytes = c->d2h_bytes;
     out->ms_count_elapsed = out->ms_count;         // all counting launches are serial on one stream
     out->n_pipelined_batches = c->n_pipelined;
+    out->n_split_build = c->n_passb2;
     return PBK_OK;
 }
 
@@ -1292,6 +1318,7 @@ static int insert_records_device(pbk_ctx *c, const void *d_records, uint64_t n_r
             Span sp(c, LC_COUNT);
             launch_insert_records((const u64 *)d_records + at * (c->W + 1), n, true, c->table, c->remote, local, c->d_ctr,
                                   c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+            c->table_touched = true;
         }
         CK(cudaGetLastError());
         TRY(read_counters(c));
@@ -1508,6 +1535,7 @@ int pbk_push_contigs(pbk_ctx *c, const uint8_t *bases, const uint64_t *seq_offse
     }
     if (rc == PBK_OK) {
         { Span sp(c, LC_OTHER); launch_contig_max(stream, nflag, rflag, 0, words, (int)c->k, c->table, d_val, c->d_ctr, c->sm_count, c->s_compute); }
+        c->table_touched = true;
         if (cudaGetLastError() != cudaSuccess) rc = fail(c, PBK_E_CUDA, "contig_max launch failed");
     }
     if (rc == PBK_OK) rc = read_counters(c);
@@ -1684,7 +1712,7 @@ static int keyx_insert_common(pbk_ctx *c, const KeyxSources &srcs)
 {
     if (c->finalized) return fail(c, PBK_E_STATE, "insert after finalize");
     CK(cudaSetDevice(c->device));
-    TRY(table_ready(c));
+    TRY(table_ordered(c));
     const u32 G = c->shard.n_shards, n_desc = c->keyx_plan.n_buckets, R = n_desc / G;
     const u64 seg_cap = c->keyx_plan.seg_cap;
     TRY(ensure_passb_buffers(c));
@@ -1706,7 +1734,10 @@ static int keyx_insert_common(pbk_ctx *c, const KeyxSources &srcs)
             TRY(grow_table(c, &c->table, c->occupied, (u64)((c->occupied + expect) / max_load(c)) + 1));
         c->pending_new += expect;
         TRY(ensure_overflow_for_batch(c, c->keyx_last_total + c->keyx_last_total / 8));
-        {
+        const int second = passb2_run(c, &srcs, 0, n_desc);
+        if (second < 0) return second;
+        c->table_touched = true;
+        if (second == 0) {
             Span sp(c, LC_INSERT);
             launch_bucket_insert_gathered_chained(srcs, seg_cap, c->d_passb, G, R, c->table, c->d_ctr, c->d_ovf, c->ovf_cap,
                                                   c->sm_count, c->s_compute);
@@ -1739,7 +1770,10 @@ static int keyx_insert_common(pbk_ctx *c, const KeyxSources &srcs)
         return PBK_OK;
     };
     auto launch = [&](u32 d0, u32 d1) -> int {
-        {
+        const int second = passb2_run(c, &srcs, d0, d1);
+        if (second < 0) return second;
+        c->table_touched = true;
+        if (second == 0) {
             Span sp(c, LC_INSERT);
             launch_bucket_insert_gathered(srcs, seg_cap, cnt.data(), c->h_passb, c->d_passb, d0, d1, G, R, c->table,
                                           c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);

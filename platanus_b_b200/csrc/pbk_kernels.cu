@@ -491,24 +491,39 @@ u64 passb2_sub_cap(u64 windows_ub, u64 n_sub)
     return (mean + mean / 2 + 1024 + 1) & ~1ull;
 }
 
-void launch_passb2_desc(const u64 *d_cursor, u64 seg_cap, u32 b_first, u32 b_end, void *d_desc, cudaStream_t st)
+// tile map of ALL n_buckets buckets for split_kernel, built on the device from the cursors
+void launch_passb2_desc(const u64 *d_cursor, u64 seg_cap, u32 n_buckets, void *d_desc, cudaStream_t st)
 {
-    passb_desc_kernel<<<1, PART_MAX_BUCKETS, 0, st>>>(d_cursor + b_first, seg_cap, b_end - b_first, (u32)SPLIT_TILE_KEYS, nullptr, 0, nullptr, 0,
+    passb_desc_kernel<<<1, PART_MAX_BUCKETS, 0, st>>>(d_cursor, seg_cap, n_buckets, (u32)SPLIT_TILE_KEYS, nullptr, 0, nullptr, 0,
         8u, 0, (u64 *)d_desc, (PassBBucket *)((char *)d_desc + 16));
 }
+// the same for the key exchange: descriptor i = (table region i / n_src, source i % n_src), fill counts read from the sources
+void launch_passb2_desc_gather(const KeyxSources &srcs, u64 seg_cap, u32 n_src, u32 n_regions, void *d_desc, cudaStream_t st)
+{
+    passb_desc_gather_kernel<<<1, PART_MAX_BUCKETS, 0, st>>>(srcs, seg_cap, n_src, n_regions, (u32)SPLIT_TILE_KEYS, nullptr, 0, 8u, 0,
+        (u64 *)d_desc, (PassBBucket *)((char *)d_desc + 16));
+}
 
-void launch_passb2_split(const u64 *bkt_keys, u64 seg_cap, const void *d_desc, u32 b_first, u32 b_end, const Passb2Geom &geom,
-                         u64 *d_sub_keys, u64 sub_cap, u64 *d_sub_cursor, Counters *ctr, u64 *overflow_keys, u64 overflow_cap,
-                         int sm_count, cudaStream_t st)
+// descriptors [d_first, d_end) of the tile map; srcs == nullptr: the context's own bucket store (descriptor = bucket)
+void launch_passb2_split(const u64 *bkt_keys, const KeyxSources *srcs, u32 n_src, u64 seg_cap, const void *d_desc, u32 d_first, u32 d_end,
+                         const Passb2Geom &geom, u64 *d_sub_keys, u64 sub_cap, u64 *d_sub_cursor, Counters *ctr, u64 *overflow_keys,
+                         u64 overflow_cap, int sm_count, cudaStream_t st)
 {
     const PassBBucket *d_bk = (const PassBBucket *)((const char *)d_desc + 16);
     const size_t smem = (size_t)SPLIT_TILE_KEYS * 8;
-    cudaFuncSetAttribute(split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int ctas = getenv("PBK_SPLIT_CTAS") ? std::max(1, atoi(getenv("PBK_SPLIT_CTAS"))) : 2;
-    split_kernel<<<sm_count * ctas, SPLIT_THREADS, smem, st>>>(bkt_keys, seg_cap, d_bk, b_first, b_end - b_first, geom.F, geom.sub_shift,
+    if (srcs) {
+        cudaFuncSetAttribute(split_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        split_gather_kernel<<<sm_count * ctas, SPLIT_THREADS, smem, st>>>(*srcs, n_src, seg_cap, d_bk, d_first, d_end, geom.F, geom.sub_shift,
+            d_sub_keys, sub_cap, d_sub_cursor, ctr, overflow_keys, overflow_cap);
+        return;
+    }
+    cudaFuncSetAttribute(split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    split_kernel<<<sm_count * ctas, SPLIT_THREADS, smem, st>>>(bkt_keys, seg_cap, d_bk, d_first, d_end, geom.F, geom.sub_shift,
         d_sub_keys, sub_cap, d_sub_cursor, ctr, overflow_keys, overflow_cap);
 }
 
+// buckets (table regions) [b_first, b_end)
 void launch_passb2_build(const u64 *d_sub_keys, u64 sub_cap, const u64 *d_sub_cursor, u32 b_first, u32 b_end, const Passb2Geom &geom,
                          TableView table, bool load_existing, Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count,
                          cudaStream_t st)

@@ -104,12 +104,16 @@ struct Passb2Geom {
 };
 bool passb2_geom(TableView table, u32 n_buckets, Passb2Geom *out);        // false: this table / bucket count cannot take the route
 u64  passb2_sub_cap(u64 windows_ub, u64 n_sub);                            // entries per sub-region segment
-// tile map of buckets [b_first, b_end) for split_kernel, built on the device from the cursors
-void launch_passb2_desc(const u64 *d_cursor, u64 seg_cap, u32 b_first, u32 b_end, void *d_desc, cudaStream_t st);
+// tile map of all n_buckets buckets for split_kernel, built on the device from the cursors; _gather: of the n_src x n_regions
+// descriptors of a key exchange (descriptor i = table region i / n_src, source i % n_src)
+void launch_passb2_desc(const u64 *d_cursor, u64 seg_cap, u32 n_buckets, void *d_desc, cudaStream_t st);
+void launch_passb2_desc_gather(const KeyxSources &srcs, u64 seg_cap, u32 n_src, u32 n_regions, void *d_desc, cudaStream_t st);
+// descriptors [d_first, d_end); srcs == nullptr: the context's own bucket store (descriptor = bucket).
 // d_sub_keys: geom.n_sub segments of sub_cap hashes, d_sub_cursor: geom.n_sub fill counts (zeroed by the caller)
-void launch_passb2_split(const u64 *bkt_keys, u64 seg_cap, const void *d_desc, u32 b_first, u32 b_end, const Passb2Geom &geom,
-                         u64 *d_sub_keys, u64 sub_cap, u64 *d_sub_cursor, Counters *ctr, u64 *overflow_keys, u64 overflow_cap,
-                         int sm_count, cudaStream_t st);
+void launch_passb2_split(const u64 *bkt_keys, const KeyxSources *srcs, u32 n_src, u64 seg_cap, const void *d_desc, u32 d_first, u32 d_end,
+                         const Passb2Geom &geom, u64 *d_sub_keys, u64 sub_cap, u64 *d_sub_cursor, Counters *ctr, u64 *overflow_keys,
+                         u64 overflow_cap, int sm_count, cudaStream_t st);
+// buckets (table regions) [b_first, b_end).
 // load_existing = false: nothing has been inserted since the table was zero-filled
 void launch_passb2_build(const u64 *d_sub_keys, u64 sub_cap, const u64 *d_sub_cursor, u32 b_first, u32 b_end, const Passb2Geom &geom,
                          TableView table, bool load_existing, Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count,

@@ -1516,25 +1516,31 @@ constexpr int BUILD_LOG2_SLOTS = 13;
 constexpr u32 BUILD_SLOTS = 1u << BUILD_LOG2_SLOTS;  // 64 KB of compact slots: three CTAs per SM
 constexpr int BUILD_ILP = 4;                         // 16-byte key loads a thread keeps in flight
 
-// bk: tile map of buckets [b_first, b_first + nb) with tiles of blockDim * SPLIT_KPT keys (passb_desc_kernel).
+// bk: tile map (tiles of blockDim * SPLIT_KPT keys) of ALL descriptors, built by passb_desc_kernel / passb_desc_gather_kernel; this
+// launch splits descriptors [d_first, d_end).  Local form: descriptor = bucket, keys in bkt_hash.  GATHER (key exchange: the keys
+// every source rank holds for this shard, read in place -- out of the receive buffer, or out of the peers' HBM over NVLink in
+// the pull form): descriptor i = (table region i / n_src, source i % n_src), and "bucket" below is the table region.
 // sub_shift = rbits + BUILD_LOG2_SLOTS: h >> sub_shift is the global sub-region of hash h, its low log2 F bits the
 // sub-region within the bucket.  sub_keys: [global sub-region][sub_cap] hashes, sub_cursor: their fill counts (zeroed).
-__global__ void __launch_bounds__(SPLIT_THREADS, 2)
-split_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, const PassBBucket *__restrict__ bk, u32 b_first, u32 nb,
-             u32 F, int sub_shift, u64 *__restrict__ sub_keys, u64 sub_cap, u64 *sub_cursor, Counters *ctr, u64 *ovf, u64 ovf_cap)
+template <bool GATHER>
+__device__ __forceinline__ void
+split_body(const u64 *__restrict__ bkt_hash, const KeyxSources *srcs, u32 n_src, u64 seg_cap, const PassBBucket *__restrict__ bk,
+           u32 d_first, u32 d_end, u32 F, int sub_shift, u64 *__restrict__ sub_keys, u64 sub_cap, u64 *sub_cursor, Counters *ctr,
+           u64 *ovf, u64 ovf_cap)
 {
     PBK_DYN_SMEM(u64, s_sorted);                     // the tile's keys in sub-region order: blockDim * SPLIT_KPT entries
     __shared__ u32 s_cnt[SPLIT_MAX_F], s_off[SPLIT_MAX_F];
     __shared__ u64 s_base[SPLIT_MAX_F];
     const u32 tid = threadIdx.x, nthreads = blockDim.x, tile_keys = nthreads * SPLIT_KPT;
     const u32 wsize = nthreads < 32u ? nthreads : 32u;
-    const u64 n_tiles = bk[nb].tile_start;
-    u32 lb = 0;
-    for (u64 t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const u64 t_end = bk[d_end].tile_start;
+    u32 lb = d_first;
+    for (u64 t = bk[d_first].tile_start + blockIdx.x; t < t_end; t += gridDim.x) {
         while (bk[lb + 1].tile_start <= t) ++lb;
         const u64 j = t - bk[lb].tile_start;
         const u32 n = (u32)min((u64)tile_keys, bk[lb].n_keys - j * tile_keys);
-        const u64 *src = bkt_hash + (u64)(b_first + lb) * seg_cap + j * tile_keys;
+        const u32 bucket = GATHER ? lb / n_src : lb;
+        const u64 *src = (GATHER ? srcs->keys[lb % n_src] + (u64)bucket * seg_cap : bkt_hash + (u64)lb * seg_cap) + j * tile_keys;
         for (u32 f = tid; f < F; f += nthreads) s_cnt[f] = 0;
         __syncthreads();
         // 1. keys into registers, each counted into its sub-region (the count's old value = the key's rank there)
@@ -1581,7 +1587,7 @@ split_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, const PassBBucket *_
         // 3. one reservation per non-empty sub-region (all in flight together), keys into sub-region order
         for (u32 f = tid; f < F; f += nthreads) {
             const u32 c = s_cnt[f];
-            s_base[f] = c ? atomicAdd(&sub_cursor[(u64)(b_first + lb) * F + f], (u64)c) : 0ull;
+            s_base[f] = c ? atomicAdd(&sub_cursor[(u64)bucket * F + f], (u64)c) : 0ull;
         }
 #pragma unroll
         for (int q = 0; q < SPLIT_KPT; ++q) {
@@ -1598,7 +1604,7 @@ split_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, const PassBBucket *_
                 if (c == 0) continue;
                 const u64 g0 = s_base[f];
                 const u64 *from = s_sorted + s_off[f];
-                u64 *to = sub_keys + ((u64)(b_first + lb) * F + f) * sub_cap + g0;
+                u64 *to = sub_keys + ((u64)bucket * F + f) * sub_cap + g0;
                 if (g0 + c <= sub_cap) {
                     for (u32 i = gl; i < c; i += gs) st_stream_u64(to + i, from[i]);
                 } else {
@@ -1611,6 +1617,20 @@ split_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, const PassBBucket *_
         }
         __syncthreads();                             // s_cnt / s_off / s_sorted are rewritten by the next tile
     }
+}
+
+__global__ void __launch_bounds__(SPLIT_THREADS, 2)
+split_kernel(const u64 *__restrict__ bkt_hash, u64 seg_cap, const PassBBucket *__restrict__ bk, u32 d_first, u32 d_end,
+             u32 F, int sub_shift, u64 *__restrict__ sub_keys, u64 sub_cap, u64 *sub_cursor, Counters *ctr, u64 *ovf, u64 ovf_cap)
+{
+    split_body<false>(bkt_hash, nullptr, 1u, seg_cap, bk, d_first, d_end, F, sub_shift, sub_keys, sub_cap, sub_cursor, ctr, ovf, ovf_cap);
+}
+__global__ void __launch_bounds__(SPLIT_THREADS, 2)
+split_gather_kernel(const __grid_constant__ KeyxSources srcs, u32 n_src, u64 seg_cap, const PassBBucket *__restrict__ bk, u32 d_first,
+                    u32 d_end, u32 F, int sub_shift, u64 *__restrict__ sub_keys, u64 sub_cap, u64 *sub_cursor, Counters *ctr,
+                    u64 *ovf, u64 ovf_cap)
+{
+    split_body<true>(nullptr, &srcs, n_src, seg_cap, bk, d_first, d_end, F, sub_shift, sub_keys, sub_cap, sub_cursor, ctr, ovf, ovf_cap);
 }
 
 // insert-or-increment of the key with hash h in the shared-memory copy of its sub-region
