@@ -513,7 +513,10 @@ def main_ours(args):
     # which form of Pass B ran (k <= 32, one GPU): the L2-atomic one, or split + shared-memory build (pbk_stats.n_split_build)
     split_build = d_res.get("n_split_build", 0) > 0
     insert_name = "split_kernel + region_build_kernel" if split_build else "bucket_insert_compact_kernel"
-    roofline = {"bound": "hbm", "kernel": ("partition_kernel<1, KEYX> + bucket_insert_gather_kernel (Pass A into the rank's own owner-major store + Pass B "
+    roofline = {"bound": "hbm", "kernel": ("partition_kernel<1, KEYX> + split_gather_kernel + region_build_kernel (Pass A into the rank's own owner-major store; Pass B in its "
+                                          "second form: split_gather_kernel reads every peer's store over NVLink and scatters the keys by 64 KB sub-region of the "
+                                          "table, region_build_kernel builds every sub-region in shared memory)" if (pull and split_build) else
+                                          "partition_kernel<1, KEYX> + bucket_insert_gather_kernel (Pass A into the rank's own owner-major store + Pass B "
                                           "reading every peer's store over NVLink: each instance goes through both exactly once)" if pull else
                                           "partition_kernel<1, KEYX> + bucket_insert_gather_kernel (Pass A into the all-to-all send "
                                           "buffer + Pass B over the received keys: each instance goes through both exactly once)" if keyx else
