@@ -16,11 +16,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-def run_child(args, timeout):
+def run_child(args, timeout, **extra_env):
     import emul_helper
     emul_helper.abi_lib_path()                       # built here, once: the child's workers only find them up to date
     emul_helper.abi_cli_path()
-    env = dict(os.environ, PBK_TEST_EMULATED_ABI="1")
+    env = dict(os.environ, PBK_TEST_EMULATED_ABI="1", **extra_env)
     workers = ["-n", str(min(6, os.cpu_count() or 1))] if (os.cpu_count() or 1) >= 4 else []      # pytest-xdist: the cases are independent
     return subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "--runxfail", "-p", "no:cacheprovider", "-x", *workers, *args],
                           cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
@@ -49,6 +49,23 @@ def test_gpu_tests_pass_against_the_emulated_abi():
     """key exchange, lookup / read filter / seeded counting / contig tables, pbk_assemble against the reference program, a
     subset of the golden cases, table growth, error behaviour -- one child pytest, xdist workers"""
     p = run_child(SELECTION, timeout=2000)
+    tail = "\n".join(p.stdout.splitlines()[-25:])
+    assert p.returncode == 0, tail + "\n" + p.stderr[-2000:]
+    assert " passed" in tail and "failed" not in tail, tail
+
+
+BOTH_FORMS_SELECTION = (
+    ["tests/test_zz_keyx_gpu.py", "tests/test_zz_group_gpu.py", "tests/test_gpu_parity.py::test_forced_partition_path_on_golden_cases",
+     "tests/test_gpu_parity.py::test_direct_and_partitioned_paths_agree", "tests/test_gpu_parity.py::test_table_growth_from_a_tiny_hint",
+     "tests/test_gpu_parity.py::test_packed_two_bit_host_input_equals_ascii_input"])
+
+
+@pytest.mark.parametrize("form", ["0", "1"])
+def test_both_forms_of_pass_b_against_the_emulated_abi(form):
+    """Pass B for one-word keys has two forms (PBK_PASSB2: 0 = one L2 atomic per instance, 1 = split by sub-region + shared-memory
+    build); whichever is the default, the partitioned routes -- own bucket store, key exchange, pull exchange, the group -- are
+    checked through BOTH."""
+    p = run_child(BOTH_FORMS_SELECTION, timeout=1500, PBK_PASSB2=form)
     tail = "\n".join(p.stdout.splitlines()[-25:])
     assert p.returncode == 0, tail + "\n" + p.stderr[-2000:]
     assert " passed" in tail and "failed" not in tail, tail
