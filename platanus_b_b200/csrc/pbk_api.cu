@@ -34,7 +34,11 @@ constexpr double MAX_LOAD = 0.5;                  // k > 32 (16+ byte slots, any
 constexpr double MAX_LOAD_COMPACT = 0.6;          // k <= 32: capacity is a power of two, real load ends up 0.3-0.6
 constexpr u64 U32_HEADROOM = (1ull << 32) - 65536 - 2;
 constexpr u64 PART_MIN_WINDOWS = 1ull << 22;    // smaller batches go straight to the table
-constexpr bool PASSB2_DEFAULT = false;            // second form of Pass B (split + shared-memory build): PBK_PASSB2=1 / 0 overrides
+// Second form of Pass B for one-word keys (split_kernel + region_build_kernel: sub-regions of the table built in shared memory,
+// no L2 atomics): the default for a context's own bucket store; PBK_PASSB2=0 / 1 overrides.  For the key exchange it stays
+// opt-in (PBK_PASSB2_GATHER=1): there Pass B's time is the NVLink transfer of the keys, which the first form overlaps with its
+// atomics tile by tile, while split_gather_kernel would only move them.
+constexpr bool PASSB2_DEFAULT = true;
 constexpr u64 MAX_PUSH_BASES = 1ull << 31;       // larger pushes are cut into internal batches (2 Gi bases: 16 GiB of bucket store at k <= 32)
 
 enum LaunchClass { LC_PACK = 0, LC_COUNT = 1, LC_OTHER = 2, LC_PART = 3, LC_INSERT = 4, LC_N = 5 };
@@ -77,7 +81,7 @@ struct pbk_ctx {
     void *d_passb = nullptr, *h_passb = nullptr;    // Pass B bucket descriptors
     bool partition_enabled = true, partition_forced = false;
     // second form of Pass B (k <= 32, unsharded; split_kernel + region_build_kernel): the sub-region segments and their fill counts
-    bool passb2_enabled = false, passb2_fresh = true;
+    bool passb2_enabled = false, passb2_gather = false, passb2_fresh = true;
     u64 *d_sub_keys = nullptr; size_t sub_bytes = 0;
     u64 *d_sub_cursor = nullptr; u64 sub_cursor_cap = 0;
     u64 store_windows_ub = 0;        // windows the current bucket store was planned for
@@ -488,6 +492,7 @@ int passb2_run(pbk_ctx *c, const KeyxSources *srcs, u32 d0, u32 d1)
     const bool was_touched = c->table_touched;
     if (!c->passb2_enabled || c->W != 1 || d1 <= d0) return 0;
     if (!srcs && c->shard.n_shards > 1) return 0;       // (record exchange: foreign keys go to the remote-staging table)
+    if (srcs && !c->passb2_gather) return 0;
     const u32 G = srcs ? c->shard.n_shards : 1u;
     const u32 n_desc = srcs ? c->keyx_plan.n_buckets : c->plan.n_buckets, n_regions = n_desc / G;
     const u64 seg_cap = srcs ? c->keyx_plan.seg_cap : c->plan.seg_cap;
@@ -981,6 +986,7 @@ int pbk_create(pbk_ctx **out, const pbk_config *cfg)
     c->overlap_enabled = getenv("PBK_NO_OVERLAP") == nullptr;
     c->pipeline_enabled = !(cfg->flags & PBK_F_NO_PIPELINE) && getenv("PBK_NO_PIPELINE") == nullptr;
     c->passb2_enabled = getenv("PBK_PASSB2") ? atoi(getenv("PBK_PASSB2")) != 0 : PASSB2_DEFAULT;
+    c->passb2_gather = getenv("PBK_PASSB2_GATHER") && atoi(getenv("PBK_PASSB2_GATHER")) != 0;
     c->passb2_fresh = !(getenv("PBK_PASSB2_FRESH") && atoi(getenv("PBK_PASSB2_FRESH")) == 0);
     if (getenv("PBK_UNKNOWN_AS_N") && atoi(getenv("PBK_UNKNOWN_AS_N")) != 0) c->flags |= PBK_F_UNKNOWN_AS_N;
     if (cudaMallocHost((void **)&c->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(PBK_E_NOMEM);

@@ -528,11 +528,11 @@ void launch_passb2_build(const u64 *d_sub_keys, u64 sub_cap, const u64 *d_sub_cu
                          TableView table, bool load_existing, Counters *ctr, u64 *overflow_keys, u64 overflow_cap, int sm_count,
                          cudaStream_t st)
 {
-    const size_t smem = (size_t)BUILD_SLOTS * 8;
+    const size_t smem = BUILD_SMEM_BYTES;
     cudaFuncSetAttribute(region_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int ctas = getenv("PBK_BUILD_CTAS") ? std::max(1, atoi(getenv("PBK_BUILD_CTAS"))) : 3;
+    const int ctas = getenv("PBK_BUILD_CTAS") ? std::max(1, atoi(getenv("PBK_BUILD_CTAS"))) : 2;
     region_build_kernel<<<sm_count * ctas, BUILD_THREADS, smem, st>>>(d_sub_keys, sub_cap, d_sub_cursor, (u64)b_first * geom.F,
-        (u64)b_end * geom.F, Table<1>(table.slots, table.cap), load_existing ? 1 : 0, ctr, overflow_keys, overflow_cap);
+        (u64)b_end * geom.F, geom.sub_shift, Table<1>(table.slots, table.cap), load_existing ? 1 : 0, ctr, overflow_keys, overflow_cap);
 }
 
 void launch_table_init(TableView t, cudaStream_t st)

@@ -1511,10 +1511,12 @@ constexpr int SPLIT_LAUNCH_THREADS = SPLIT_THREADS;
 constexpr int SPLIT_LAUNCH_THREADS = 1;
 #endif
 constexpr int SPLIT_TILE_KEYS = SPLIT_LAUNCH_THREADS * SPLIT_KPT;
-constexpr int BUILD_THREADS = 256;
+constexpr int BUILD_THREADS = 512;
 constexpr int BUILD_LOG2_SLOTS = 13;
-constexpr u32 BUILD_SLOTS = 1u << BUILD_LOG2_SLOTS;  // 64 KB of compact slots: three CTAs per SM
-constexpr int BUILD_ILP = 4;                         // 16-byte key loads a thread keeps in flight
+constexpr u32 BUILD_SLOTS = 1u << BUILD_LOG2_SLOTS;  // 64 KB of compact slots
+constexpr int BUILD_KPT = 4;                         // new keys per lane and round (two 16-byte loads)
+constexpr int BUILD_DEF_CAP = 32 * (BUILD_KPT + 2);  // list entries per warp: what one round can add, plus one batch
+constexpr size_t BUILD_SMEM_BYTES = ((size_t)BUILD_SLOTS + (size_t)(BUILD_THREADS / 32) * BUILD_DEF_CAP) * 8;    // 88 KB: two CTAs per SM
 
 // bk: tile map (tiles of blockDim * SPLIT_KPT keys) of ALL descriptors, built by passb_desc_kernel / passb_desc_gather_kernel; this
 // launch splits descriptors [d_first, d_end).  Local form: descriptor = bucket, keys in bkt_hash.  GATHER (key exchange: the keys
@@ -1570,7 +1572,16 @@ split_body(const u64 *__restrict__ bkt_hash, const KeyxSources *srcs, u32 n_src,
             }
         }
         __syncthreads();
-        // 2. exclusive prefix of the counts (one warp, a run of consecutive sub-regions per lane)
+        // 2. one reservation per non-empty sub-region, issued first: the round trips of these global atomics (all in flight
+        //    together) are covered by the prefix scan and the sort below -- the result is only needed for the copy-out
+        const bool one_each = nthreads >= F;         // (the CPU emulation runs one thread: it reserves in a loop)
+        u64 my_base = 0;
+        if (one_each) {
+            if (tid < F && s_cnt[tid]) my_base = atomicAdd(&sub_cursor[(u64)bucket * F + tid], (u64)s_cnt[tid]);
+        } else {
+            for (u32 f = tid; f < F; f += nthreads) s_base[f] = s_cnt[f] ? atomicAdd(&sub_cursor[(u64)bucket * F + f], (u64)s_cnt[f]) : 0ull;
+        }
+        //    exclusive prefix of the counts (one warp, a run of consecutive sub-regions per lane)
         if (tid < wsize) {
             const u32 per = (F + wsize - 1) / wsize, f0 = tid * per;
             u32 sum = 0;
@@ -1584,16 +1595,13 @@ split_body(const u64 *__restrict__ bkt_hash, const KeyxSources *srcs, u32 n_src,
             for (u32 i = 0; i < per; ++i) if (f0 + i < F) { s_off[f0 + i] = run; run += s_cnt[f0 + i]; }
         }
         __syncthreads();
-        // 3. one reservation per non-empty sub-region (all in flight together), keys into sub-region order
-        for (u32 f = tid; f < F; f += nthreads) {
-            const u32 c = s_cnt[f];
-            s_base[f] = c ? atomicAdd(&sub_cursor[(u64)bucket * F + f], (u64)c) : 0ull;
-        }
+        // 3. keys into sub-region order
 #pragma unroll
         for (int q = 0; q < SPLIT_KPT; ++q) {
             const u32 i = 2 * ((u32)(q >> 1) * nthreads + tid) + (u32)(q & 1);
             if (i < n) s_sorted[s_off[sp[q] >> 16] + (sp[q] & 0xFFFFu)] = h[q];
         }
+        if (one_each && tid < F) s_base[tid] = my_base;
         __syncthreads();
         // 4. copy-out: a group of 16 lanes per sub-region (a full tile brings tile_keys / F keys for each: 256 B at F = 256)
         {
@@ -1633,38 +1641,53 @@ split_gather_kernel(const __grid_constant__ KeyxSources srcs, u32 n_src, u64 seg
     split_body<true>(nullptr, &srcs, n_src, seg_cap, bk, d_first, d_end, F, sub_shift, sub_keys, sub_cap, sub_cursor, ctr, ovf, ovf_cap);
 }
 
-// insert-or-increment of the key with hash h in the shared-memory copy of its sub-region
-__device__ __forceinline__ void build_insert(u64 *s_tab, const CtGeom &g, u64 h, u32 &newk, Counters *ctr, u64 *ovf, u64 ovf_cap)
+// One probe of the shared-memory copy of a sub-region: slot (home + d) for the key with hash h.  Returns BUILD_DONE when the
+// key is settled (counted, claimed, or -- probe sequence leaving the sub-region or passing CT_MAX_DISP -- handed to the
+// overflow list), else the displacement to try next.
+constexpr u32 BUILD_DONE = 0xFFFFFFFFu;
+__device__ __forceinline__ u32 build_probe(u64 *s_tab, const CtGeom &g, u64 h, u32 d, u32 &newk, Counters *ctr, u64 *ovf, u64 ovf_cap)
 {
-    const u32 home = (u32)(h >> g.rbits) & (BUILD_SLOTS - 1u);
-    const u64 rem = h << (64 - g.rbits);             // remainder in the top bits, as in the slot word
-#pragma unroll 1
-    for (u32 d = 0; d <= (u32)CT_MAX_DISP && home + d < BUILD_SLOTS; ++d) {
-        u64 *s = s_tab + home + d;
-        const u64 tag = rem | ((u64)(d + 1) << g.cbits);
-        u64 cur = *reinterpret_cast<volatile u64 *>(s);
-        if (cur == 0) {
-            cur = atomicCAS(s, 0ull, tag | 1ull);
-            if (cur == 0) { ++newk; return; }        // the slot was empty and is ours, count 1
-        }
-        if (((cur ^ tag) >> g.cbits) == 0) {         // our key: +1 on the count field (low half of the word), unless saturated
-            if ((cur & g.cmask) < (u64)COUNT_SAT) atomicAdd(reinterpret_cast<u32 *>(s), 1u);
-            return;
-        }
+    const u32 idx = ((u32)(h >> g.rbits) & (BUILD_SLOTS - 1u)) + d;
+    if (idx >= BUILD_SLOTS || d > (u32)CT_MAX_DISP) {
+        const u64 k0 = fmix64_inverse(h);
+        spill_key<1>(&k0, ctr, ovf, ovf_cap);
+        return BUILD_DONE;
     }
-    const u64 k0 = fmix64_inverse(h);
-    spill_key<1>(&k0, ctr, ovf, ovf_cap);
+    u64 *s = s_tab + idx;
+    const u64 tag = (h << (64 - g.rbits)) | ((u64)(d + 1) << g.cbits);
+    u64 cur = *reinterpret_cast<volatile u64 *>(s);
+    if (cur == 0) {
+        cur = atomicCAS(s, 0ull, tag | 1ull);
+        if (cur == 0) { ++newk; return BUILD_DONE; }             // the slot was empty and is ours, count 1
+    }
+    if (((cur ^ tag) >> g.cbits) == 0) {                         // our key: +1 on the count field (low half of the word), unless saturated
+        if ((cur & g.cmask) < (u64)COUNT_SAT) atomicAdd(reinterpret_cast<u32 *>(s), 1u);
+        return BUILD_DONE;
+    }
+    return d + 1;
 }
 
-// sub-regions [g_first, g_end) of the table, one CTA at a time each; load_existing = 0: the table is known to be all zero
-// (nothing has touched it since it was cleared), so the sub-region is not read
-__global__ void __launch_bounds__(BUILD_THREADS, 3)
+// Sub-regions [g_first, g_end) of the table, one CTA at a time each; load_existing = 0: the table is known to be all zero
+// (nothing has touched it since it was cleared), so the sub-region is not read.
+// The first version probed in a loop per key: linear probing has a long tail (a hot k-mer deep in a cluster is hit by every one of
+// its instances), and a warp runs as long as its slowest lane -- ncu counted 7.4 active lanes per instruction and 550 warp
+// instructions per 32 keys (profiles/r2k_split_build_v1_kernels.txt; 6.5 ms).  So, as in bucket_insert_compact_kernel: every key
+// gets ONE probe per round; what is not settled goes on a small per-warp list in shared memory (the key's hash with the
+// displacement to try next in its top seven bits -- those bits are the same for all keys of a sub-region) and rides with a
+// later round, one list entry per lane.  Warps never wait for each other between the CTA barriers around load and write-back.
+__global__ void __launch_bounds__(BUILD_THREADS, 2)
 region_build_kernel(const u64 *__restrict__ sub_keys, u64 sub_cap, const u64 *__restrict__ sub_cursor, u64 g_first, u64 g_end,
-                    Table<1> table, int load_existing, Counters *ctr, u64 *ovf, u64 ovf_cap)
+                    int sub_shift, Table<1> table, int load_existing, Counters *ctr, u64 *ovf, u64 ovf_cap)
 {
-    PBK_DYN_SMEM(u64, s_tab);                        // BUILD_SLOTS slot words
+    PBK_DYN_SMEM(u64, s_mem);                        // BUILD_SLOTS slot words, then BUILD_DEF_CAP list entries per warp
+    u64 *s_tab = s_mem;
     const u32 tid = threadIdx.x, nthreads = blockDim.x;
+    const u32 wsize = nthreads < 32u ? nthreads : 32u;
+    const u32 lane = tid % wsize, warp = tid / wsize;
+    u64 *def = s_mem + BUILD_SLOTS + (size_t)warp * BUILD_DEF_CAP;
+    const u32 warp_keys = wsize * BUILD_KPT, round_keys = nthreads * BUILD_KPT;
     const CtGeom g = table.g;
+    constexpr u64 DMASK = 0x7Full << 57;
     u32 newk = 0;
     for (u64 r = g_first + blockIdx.x; r < g_end; r += gridDim.x) {
         const u64 n = min(sub_cursor[r], sub_cap);
@@ -1680,21 +1703,54 @@ region_build_kernel(const u64 *__restrict__ sub_keys, u64 sub_cap, const u64 *__
         }
         __syncthreads();
         const u64 *src = sub_keys + r * sub_cap;     // 16-byte aligned: sub_cap is even
-        for (u64 i0 = 0; i0 < n; i0 += (u64)nthreads * 2 * BUILD_ILP) {
-            ulonglong2 v[BUILD_ILP];
+        const u64 top7 = (r << sub_shift) & DMASK;   // bits 57..63 of every hash of this sub-region
+        u32 n_def = 0;
+        // one round of this warp: up to BUILD_KPT new keys per lane starting at key index `first` (n_new = 0: list entries only)
+        // plus one list entry per lane
+        auto round = [&](u64 first, u32 n_new) {
+            const u32 take = n_def < wsize ? n_def : wsize;
+            u64 xe = 0;
+            __syncwarp();
+            if (lane < take) xe = def[n_def - 1 - lane];
+            __syncwarp();
+            n_def -= take;
+            u64 h[BUILD_KPT + 1];
+            u32 d[BUILD_KPT + 1];
+            u32 live = 0;
 #pragma unroll
-            for (int j = 0; j < BUILD_ILP; ++j) {
-                const u64 i = i0 + 2 * ((u64)j * nthreads + tid);
-                if (i + 1 < n) v[j] = ld_stream_u64x2(src + i);
-                else v[j] = make_ulonglong2(i < n ? ld_stream_u64(src + i) : 0ull, 0ull);
+            for (int p = 0; p < BUILD_KPT / 2; ++p) {
+                const u32 i = 2 * ((u32)p * wsize + lane);
+                h[2 * p] = h[2 * p + 1] = 0;
+                if (i + 1 < n_new) {
+                    const ulonglong2 v = ld_stream_u64x2(src + first + i);
+                    h[2 * p] = v.x; h[2 * p + 1] = v.y;
+                    live |= 3u << (2 * p);
+                } else if (i < n_new) {
+                    h[2 * p] = ld_stream_u64(src + first + i);
+                    live |= 1u << (2 * p);
+                }
+                d[2 * p] = d[2 * p + 1] = 0;
             }
+            h[BUILD_KPT] = (xe & ~DMASK) | top7;
+            d[BUILD_KPT] = (u32)(xe >> 57);
+            if (lane < take) live |= 1u << BUILD_KPT;
 #pragma unroll
-            for (int j = 0; j < BUILD_ILP; ++j) {
-                const u64 i = i0 + 2 * ((u64)j * nthreads + tid);
-                if (i < n) build_insert(s_tab, g, v[j].x, newk, ctr, ovf, ovf_cap);
-                if (i + 1 < n) build_insert(s_tab, g, v[j].y, newk, ctr, ovf, ovf_cap);
+            for (int q = 0; q <= BUILD_KPT; ++q) {
+                u32 m = BUILD_DONE;
+                if ((live >> q) & 1u) m = build_probe(s_tab, g, h[q], d[q], newk, ctr, ovf, ovf_cap);
+                const unsigned bal = __ballot_sync(0xffffffffu, m != BUILD_DONE);
+                if (bal == 0) continue;
+                if (m != BUILD_DONE) def[n_def + (u32)__popc(bal & ((1u << lane) - 1u))] = (h[q] & ~DMASK) | ((u64)m << 57);
+                n_def += (u32)__popc(bal);
             }
+        };
+        for (u64 o = (u64)warp * warp_keys; o < n; o += round_keys) {
+#pragma unroll 1
+            while (n_def > wsize) round(0, 0u);      // a round may only start with at most one batch listed
+            round(o, (u32)min((u64)warp_keys, n - o));
         }
+#pragma unroll 1
+        while (n_def) round(0, 0u);                  // nothing ever waits, so the list drains
         __syncthreads();
         for (u32 i = tid; i < BUILD_SLOTS / 2; i += nthreads)
             st_cg_u64x2(region + 2 * i, s_tab[2 * i], s_tab[2 * i + 1]);

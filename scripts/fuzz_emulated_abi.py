@@ -79,7 +79,7 @@ def one_case(rng, case_no):
     partition = rng.choice([True, "force", False])
     pipeline = rng.random() < 0.7
     if "PBK_FUZZ_FIXED_FORM" not in os.environ:      # which form of Pass B (k <= 32) the contexts of this case use: read by pbk_create
-        os.environ["PBK_PASSB2"] = rng.choice(["0", "1"])
+        os.environ["PBK_PASSB2"] = os.environ["PBK_PASSB2_GATHER"] = rng.choice(["0", "1"])
     desc = f"case {case_no}: k={k} mode={mode} partition={partition} pipeline={pipeline} passb2={os.environ.get('PBK_PASSB2')} reads={len(reads)}"
     if mode in ("plain", "multi_push"):
         with KmerCounter(k, partition=partition, pipeline=pipeline, table_slots_hint=rng.choice([0, 0, 64])) as kc:

@@ -62,10 +62,10 @@ BOTH_FORMS_SELECTION = (
 
 @pytest.mark.parametrize("form", ["0", "1"])
 def test_both_forms_of_pass_b_against_the_emulated_abi(form):
-    """Pass B for one-word keys has two forms (PBK_PASSB2: 0 = one L2 atomic per instance, 1 = split by sub-region + shared-memory
-    build); whichever is the default, the partitioned routes -- own bucket store, key exchange, pull exchange, the group -- are
-    checked through BOTH."""
-    p = run_child(BOTH_FORMS_SELECTION, timeout=1500, PBK_PASSB2=form)
+    """Pass B for one-word keys has two forms (PBK_PASSB2 for a context's own bucket store, PBK_PASSB2_GATHER for the key exchange:
+    0 = one L2 atomic per instance, 1 = split by sub-region + shared-memory build); whichever is the default, the partitioned
+    routes -- own bucket store, key exchange, pull exchange, the group -- are checked through BOTH."""
+    p = run_child(BOTH_FORMS_SELECTION, timeout=1500, PBK_PASSB2=form, PBK_PASSB2_GATHER=form)
     tail = "\n".join(p.stdout.splitlines()[-25:])
     assert p.returncode == 0, tail + "\n" + p.stderr[-2000:]
     assert " passed" in tail and "failed" not in tail, tail
