@@ -38,7 +38,7 @@ constexpr u64 PART_MIN_WINDOWS = 1ull << 22;    // smaller batches go straight t
 // no L2 atomics): the default for a context's own bucket store; PBK_PASSB2=0 / 1 overrides.  For the key exchange it stays
 // opt-in (PBK_PASSB2_GATHER=1): there Pass B's time is the NVLink transfer of the keys, which the first form overlaps with its
 // atomics tile by tile, while split_gather_kernel would only move them.
-constexpr bool PASSB2_DEFAULT = true;
+constexpr bool PASSB2_DEFAULT = false;
 constexpr u64 MAX_PUSH_BASES = 1ull << 31;       // larger pushes are cut into internal batches (2 Gi bases: 16 GiB of bucket store at k <= 32)
 
 enum LaunchClass { LC_PACK = 0, LC_COUNT = 1, LC_OTHER = 2, LC_PART = 3, LC_INSERT = 4, LC_N = 5 };

@@ -54,18 +54,19 @@ def test_gpu_tests_pass_against_the_emulated_abi():
     assert " passed" in tail and "failed" not in tail, tail
 
 
-BOTH_FORMS_SELECTION = (
-    ["tests/test_zz_keyx_gpu.py", "tests/test_zz_group_gpu.py", "tests/test_gpu_parity.py::test_forced_partition_path_on_golden_cases",
-     "tests/test_gpu_parity.py::test_direct_and_partitioned_paths_agree", "tests/test_gpu_parity.py::test_table_growth_from_a_tiny_hint",
-     "tests/test_gpu_parity.py::test_packed_two_bit_host_input_equals_ascii_input"])
+OWN_STORE_ROUTES = ["tests/test_gpu_parity.py::test_forced_partition_path_on_golden_cases", "tests/test_gpu_parity.py::test_direct_and_partitioned_paths_agree",
+                    "tests/test_gpu_parity.py::test_packed_two_bit_host_input_equals_ascii_input"]
+EXCHANGE_ROUTES = ["tests/test_zz_keyx_gpu.py", "tests/test_zz_group_gpu.py"]
 
 
-@pytest.mark.parametrize("form", ["0", "1"])
-def test_both_forms_of_pass_b_against_the_emulated_abi(form):
-    """Pass B for one-word keys has two forms (PBK_PASSB2 for a context's own bucket store, PBK_PASSB2_GATHER for the key exchange:
-    0 = one L2 atomic per instance, 1 = split by sub-region + shared-memory build); whichever is the default, the partitioned
-    routes -- own bucket store, key exchange, pull exchange, the group -- are checked through BOTH."""
-    p = run_child(BOTH_FORMS_SELECTION, timeout=1500, PBK_PASSB2=form, PBK_PASSB2_GATHER=form)
+@pytest.mark.parametrize("env,selection", [({"PBK_PASSB2": "0"}, OWN_STORE_ROUTES), ({"PBK_PASSB2_GATHER": "1"}, EXCHANGE_ROUTES)],
+                         ids=["own_store_first_form", "exchange_second_form"])
+def test_the_other_form_of_pass_b_against_the_emulated_abi(env, selection):
+    """Pass B for one-word keys has two forms: one L2 atomic per instance (bucket_insert_compact / _gather_kernel), or the keys split by
+    sub-region of the table and every sub-region built in shared memory (split_kernel + region_build_kernel).  The defaults -- second
+    form for a context's own bucket store, first form for the key / pull exchange -- run in the selection above; here the
+    partitioned routes go through the OTHER form of each."""
+    p = run_child(selection, timeout=1500, **env)
     tail = "\n".join(p.stdout.splitlines()[-25:])
     assert p.returncode == 0, tail + "\n" + p.stderr[-2000:]
     assert " passed" in tail and "failed" not in tail, tail
