@@ -473,7 +473,7 @@ void launch_bucket_insert_chained(const u64 *bkt_keys, u64 seg_cap, const void *
 bool passb2_geom(TableView table, u32 n_buckets, Passb2Geom *out)
 {
     if (table.words != 1 || !table.slots || n_buckets == 0 || (n_buckets & (n_buckets - 1))) return false;
-    if (table.cap & (table.cap - 1)) return false;
+    if ((table.cap & (table.cap - 1)) || table.cap > (1ull << 31)) return false;   // (region_build_kernel looks at 32-bit halves of a slot)
     const u64 n_sub = table.cap >> BUILD_LOG2_SLOTS;
     if (n_sub < n_buckets || n_sub / n_buckets > (u64)SPLIT_MAX_F) return false;
     out->n_sub = n_sub;
@@ -491,16 +491,29 @@ u64 passb2_sub_cap(u64 windows_ub, u64 n_sub)
     return (mean + mean / 2 + 1024 + 1) & ~1ull;
 }
 
+// CTA size of split_kernel: 512 threads (tiles of 8192 keys, two CTAs per SM) unless PBK_SPLIT_THREADS says 256 (tiles of 4096
+// keys, four CTAs per SM: smaller barrier domains, shorter runs per sub-region) -- a tuning switch
+static int split_threads()
+{
+#ifdef PBK_CPU_EMUL
+    return SPLIT_LAUNCH_THREADS;
+#else
+    static const int t = (getenv("PBK_SPLIT_THREADS") && atoi(getenv("PBK_SPLIT_THREADS")) == 256) ? 256 : SPLIT_THREADS;
+    return t;
+#endif
+}
+static u32 split_tile_keys() { return (u32)split_threads() * SPLIT_KPT; }
+
 // tile map of ALL n_buckets buckets for split_kernel, built on the device from the cursors
 void launch_passb2_desc(const u64 *d_cursor, u64 seg_cap, u32 n_buckets, void *d_desc, cudaStream_t st)
 {
-    passb_desc_kernel<<<1, PART_MAX_BUCKETS, 0, st>>>(d_cursor, seg_cap, n_buckets, (u32)SPLIT_TILE_KEYS, nullptr, 0, nullptr, 0,
+    passb_desc_kernel<<<1, PART_MAX_BUCKETS, 0, st>>>(d_cursor, seg_cap, n_buckets, split_tile_keys(), nullptr, 0, nullptr, 0,
         8u, 0, (u64 *)d_desc, (PassBBucket *)((char *)d_desc + 16));
 }
 // the same for the key exchange: descriptor i = (table region i / n_src, source i % n_src), fill counts read from the sources
 void launch_passb2_desc_gather(const KeyxSources &srcs, u64 seg_cap, u32 n_src, u32 n_regions, void *d_desc, cudaStream_t st)
 {
-    passb_desc_gather_kernel<<<1, PART_MAX_BUCKETS, 0, st>>>(srcs, seg_cap, n_src, n_regions, (u32)SPLIT_TILE_KEYS, nullptr, 0, 8u, 0,
+    passb_desc_gather_kernel<<<1, PART_MAX_BUCKETS, 0, st>>>(srcs, seg_cap, n_src, n_regions, split_tile_keys(), nullptr, 0, 8u, 0,
         (u64 *)d_desc, (PassBBucket *)((char *)d_desc + 16));
 }
 
@@ -510,16 +523,17 @@ void launch_passb2_split(const u64 *bkt_keys, const KeyxSources *srcs, u32 n_src
                          u64 overflow_cap, int sm_count, cudaStream_t st)
 {
     const PassBBucket *d_bk = (const PassBBucket *)((const char *)d_desc + 16);
-    const size_t smem = (size_t)SPLIT_TILE_KEYS * 8;
-    const int ctas = getenv("PBK_SPLIT_CTAS") ? std::max(1, atoi(getenv("PBK_SPLIT_CTAS"))) : 2;
+    const size_t smem = (size_t)split_tile_keys() * 8;
+    const int threads = split_threads();
+    const int ctas = getenv("PBK_SPLIT_CTAS") ? std::max(1, atoi(getenv("PBK_SPLIT_CTAS"))) : (threads == 256 ? 4 : 2);
     if (srcs) {
         cudaFuncSetAttribute(split_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        split_gather_kernel<<<sm_count * ctas, SPLIT_THREADS, smem, st>>>(*srcs, n_src, seg_cap, d_bk, d_first, d_end, geom.F, geom.sub_shift,
+        split_gather_kernel<<<sm_count * ctas, threads, smem, st>>>(*srcs, n_src, seg_cap, d_bk, d_first, d_end, geom.F, geom.sub_shift,
             d_sub_keys, sub_cap, d_sub_cursor, ctr, overflow_keys, overflow_cap);
         return;
     }
     cudaFuncSetAttribute(split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    split_kernel<<<sm_count * ctas, SPLIT_THREADS, smem, st>>>(bkt_keys, seg_cap, d_bk, d_first, d_end, geom.F, geom.sub_shift,
+    split_kernel<<<sm_count * ctas, threads, smem, st>>>(bkt_keys, seg_cap, d_bk, d_first, d_end, geom.F, geom.sub_shift,
         d_sub_keys, sub_cap, d_sub_cursor, ctr, overflow_keys, overflow_cap);
 }
 

@@ -1644,27 +1644,34 @@ split_gather_kernel(const __grid_constant__ KeyxSources srcs, u32 n_src, u64 seg
 // One probe of the shared-memory copy of a sub-region: slot (home + d) for the key with hash h.  Returns BUILD_DONE when the
 // key is settled (counted, claimed, or -- probe sequence leaving the sub-region or passing CT_MAX_DISP -- handed to the
 // overflow list), else the displacement to try next.
+// The slot word is read and claimed as 64 bits but LOOKED AT as two 32-bit halves (the pass is bound by instruction issue, and
+// 64-bit shifts / compares by a run-time amount cost two to three instructions each): with q = log2(capacity) <= 31 the low
+// half holds count (q - 7 bits), displacement + 1 (7 bits) and the low 32 - q bits of the remainder, the high half the rest.
 constexpr u32 BUILD_DONE = 0xFFFFFFFFu;
-__device__ __forceinline__ u32 build_probe(u64 *s_tab, const CtGeom &g, u64 h, u32 d, u32 &newk, Counters *ctr, u64 *ovf, u64 ovf_cap)
+struct BuildGeom { int rbits, q, cbits; u32 cmask; };
+__device__ __forceinline__ u32 build_probe(u64 *s_tab, const BuildGeom &bg, u64 h, u32 d, u32 &newk, Counters *ctr, u64 *ovf, u64 ovf_cap)
 {
-    const u32 idx = ((u32)(h >> g.rbits) & (BUILD_SLOTS - 1u)) + d;
+    const u32 idx = ((u32)(h >> bg.rbits) & (BUILD_SLOTS - 1u)) + d;
     if (idx >= BUILD_SLOTS || d > (u32)CT_MAX_DISP) {
         const u64 k0 = fmix64_inverse(h);
         spill_key<1>(&k0, ctr, ovf, ovf_cap);
         return BUILD_DONE;
     }
     u64 *s = s_tab + idx;
-    const u64 tag = (h << (64 - g.rbits)) | ((u64)(d + 1) << g.cbits);
-    u64 cur = *reinterpret_cast<volatile u64 *>(s);
-    if (cur == 0) {
-        cur = atomicCAS(s, 0ull, tag | 1ull);
-        if (cur == 0) { ++newk; return BUILD_DONE; }             // the slot was empty and is ours, count 1
+    const u32 tag_hi = (u32)(h >> (32 - bg.q));                   // bits 32..63 of h << q
+    const u32 tag_lo = ((u32)h << bg.q) | ((d + 1u) << bg.cbits);
+    const u64 cur = *reinterpret_cast<volatile u64 *>(s);         // ONE 64-bit read: a slot goes from 0 to (tag | 1) in one step
+    u32 lo = (u32)cur, hi = (u32)(cur >> 32);
+    if ((lo | hi) == 0u) {
+        const u64 old = atomicCAS(s, 0ull, ((u64)tag_hi << 32) | (u64)(tag_lo | 1u));
+        if (old == 0) { ++newk; return BUILD_DONE; }              // the slot was empty and is ours, count 1
+        lo = (u32)old; hi = (u32)(old >> 32);
     }
-    if (((cur ^ tag) >> g.cbits) == 0) {                         // our key: +1 on the count field (low half of the word), unless saturated
-        if ((cur & g.cmask) < (u64)COUNT_SAT) atomicAdd(reinterpret_cast<u32 *>(s), 1u);
+    if (hi == tag_hi && ((lo ^ tag_lo) >> bg.cbits) == 0u) {      // our key: +1 on the count field, unless saturated
+        if ((lo & bg.cmask) < COUNT_SAT) atomicAdd(reinterpret_cast<u32 *>(s), 1u);
         return BUILD_DONE;
     }
-    return d + 1;
+    return d + 1u;
 }
 
 // Sub-regions [g_first, g_end) of the table, one CTA at a time each; load_existing = 0: the table is known to be all zero
@@ -1675,6 +1682,9 @@ __device__ __forceinline__ u32 build_probe(u64 *s_tab, const CtGeom &g, u64 h, u
 // gets ONE probe per round; what is not settled goes on a small per-warp list in shared memory (the key's hash with the
 // displacement to try next in its top seven bits -- those bits are the same for all keys of a sub-region) and rides with a
 // later round, one list entry per lane.  Warps never wait for each other between the CTA barriers around load and write-back.
+// That version ran in 2.07 ms, bound by instruction issue (64 % issue-active, ~100 warp instructions per 32 probes) with 15 % of
+// the samples waiting for the round's own key loads (profiles/r2l_split_build_kernels.txt): hence the 32-bit slot arithmetic above
+// and the keys of the NEXT round being loaded before the current round's probes.
 __global__ void __launch_bounds__(BUILD_THREADS, 2)
 region_build_kernel(const u64 *__restrict__ sub_keys, u64 sub_cap, const u64 *__restrict__ sub_cursor, u64 g_first, u64 g_end,
                     int sub_shift, Table<1> table, int load_existing, Counters *ctr, u64 *ovf, u64 ovf_cap)
@@ -1684,15 +1694,40 @@ region_build_kernel(const u64 *__restrict__ sub_keys, u64 sub_cap, const u64 *__
     const u32 tid = threadIdx.x, nthreads = blockDim.x;
     const u32 wsize = nthreads < 32u ? nthreads : 32u;
     const u32 lane = tid % wsize, warp = tid / wsize;
+    const u32 lt_mask = (1u << lane) - 1u;
     u64 *def = s_mem + BUILD_SLOTS + (size_t)warp * BUILD_DEF_CAP;
     const u32 warp_keys = wsize * BUILD_KPT, round_keys = nthreads * BUILD_KPT;
-    const CtGeom g = table.g;
+    BuildGeom bg;
+    bg.rbits = table.g.rbits; bg.q = 64 - table.g.rbits; bg.cbits = table.g.cbits; bg.cmask = (u32)table.g.cmask;
     constexpr u64 DMASK = 0x7Full << 57;
     u32 newk = 0;
     for (u64 r = g_first + blockIdx.x; r < g_end; r += gridDim.x) {
         const u64 n = min(sub_cursor[r], sub_cap);
         if (n == 0) continue;                        // (same for every thread) nothing to add: the sub-region stays as it is
         u64 *region = table.slots + r * BUILD_SLOTS;
+        const u64 *src = sub_keys + r * sub_cap;     // 16-byte aligned: sub_cap is even
+        const u64 top7 = (r << sub_shift) & DMASK;   // bits 57..63 of every hash of this sub-region
+        // the warp's slice of a round: BUILD_KPT keys per lane from key index o (two 16-byte loads per lane); bit q of the
+        // returned mask = key q exists
+        auto fetch = [&](u64 o, u64 *k) -> u32 {
+            u32 live = 0;
+#pragma unroll
+            for (int p = 0; p < BUILD_KPT / 2; ++p) {
+                const u64 i = o + 2 * ((u64)p * wsize + lane);
+                k[2 * p] = k[2 * p + 1] = 0;
+                if (i + 1 < n) {
+                    const ulonglong2 v = ld_stream_u64x2(src + i);
+                    k[2 * p] = v.x; k[2 * p + 1] = v.y;
+                    live |= 3u << (2 * p);
+                } else if (i < n) {
+                    k[2 * p] = ld_stream_u64(src + i);
+                    live |= 1u << (2 * p);
+                }
+            }
+            return live;
+        };
+        u64 nx[BUILD_KPT];
+        u32 nx_live = fetch((u64)warp * warp_keys, nx);          // in flight while the sub-region is loaded / cleared
         if (load_existing) {
             for (u32 i = tid; i < BUILD_SLOTS / 2; i += nthreads) {
                 const ulonglong2 v = ld_stream_u64x2(region + 2 * i);
@@ -1702,55 +1737,40 @@ region_build_kernel(const u64 *__restrict__ sub_keys, u64 sub_cap, const u64 *__
             for (u32 i = tid; i < BUILD_SLOTS; i += nthreads) s_tab[i] = 0;
         }
         __syncthreads();
-        const u64 *src = sub_keys + r * sub_cap;     // 16-byte aligned: sub_cap is even
-        const u64 top7 = (r << sub_shift) & DMASK;   // bits 57..63 of every hash of this sub-region
         u32 n_def = 0;
-        // one round of this warp: up to BUILD_KPT new keys per lane starting at key index `first` (n_new = 0: list entries only)
-        // plus one list entry per lane
-        auto round = [&](u64 first, u32 n_new) {
+        // settle or re-list what one probe of (hq, dq) left
+        auto settle = [&](bool live, u64 hq, u32 dq) {
+            u32 m = BUILD_DONE;
+            if (live) m = build_probe(s_tab, bg, hq, dq, newk, ctr, ovf, ovf_cap);
+            const unsigned bal = __ballot_sync(0xffffffffu, m != BUILD_DONE);
+            if (bal == 0) return;
+            if (m != BUILD_DONE) def[n_def + (u32)__popc(bal & lt_mask)] = (hq & ~DMASK) | ((u64)m << 57);
+            n_def += (u32)__popc(bal);
+        };
+        // one list entry per lane (the top min(n_def, warp size) entries)
+        auto list_round = [&]() {
             const u32 take = n_def < wsize ? n_def : wsize;
             u64 xe = 0;
             __syncwarp();
             if (lane < take) xe = def[n_def - 1 - lane];
             __syncwarp();
             n_def -= take;
-            u64 h[BUILD_KPT + 1];
-            u32 d[BUILD_KPT + 1];
-            u32 live = 0;
-#pragma unroll
-            for (int p = 0; p < BUILD_KPT / 2; ++p) {
-                const u32 i = 2 * ((u32)p * wsize + lane);
-                h[2 * p] = h[2 * p + 1] = 0;
-                if (i + 1 < n_new) {
-                    const ulonglong2 v = ld_stream_u64x2(src + first + i);
-                    h[2 * p] = v.x; h[2 * p + 1] = v.y;
-                    live |= 3u << (2 * p);
-                } else if (i < n_new) {
-                    h[2 * p] = ld_stream_u64(src + first + i);
-                    live |= 1u << (2 * p);
-                }
-                d[2 * p] = d[2 * p + 1] = 0;
-            }
-            h[BUILD_KPT] = (xe & ~DMASK) | top7;
-            d[BUILD_KPT] = (u32)(xe >> 57);
-            if (lane < take) live |= 1u << BUILD_KPT;
-#pragma unroll
-            for (int q = 0; q <= BUILD_KPT; ++q) {
-                u32 m = BUILD_DONE;
-                if ((live >> q) & 1u) m = build_probe(s_tab, g, h[q], d[q], newk, ctr, ovf, ovf_cap);
-                const unsigned bal = __ballot_sync(0xffffffffu, m != BUILD_DONE);
-                if (bal == 0) continue;
-                if (m != BUILD_DONE) def[n_def + (u32)__popc(bal & ((1u << lane) - 1u))] = (h[q] & ~DMASK) | ((u64)m << 57);
-                n_def += (u32)__popc(bal);
-            }
+            settle(lane < take, (xe & ~DMASK) | top7, (u32)(xe >> 57));
         };
         for (u64 o = (u64)warp * warp_keys; o < n; o += round_keys) {
+            u64 h[BUILD_KPT];
+            const u32 live = nx_live;
+#pragma unroll
+            for (int q = 0; q < BUILD_KPT; ++q) h[q] = nx[q];
+            nx_live = fetch(o + round_keys, nx);                 // the next round's keys, in flight during this round's probes
 #pragma unroll 1
-            while (n_def > wsize) round(0, 0u);      // a round may only start with at most one batch listed
-            round(o, (u32)min((u64)warp_keys, n - o));
+            while (n_def > wsize) list_round();                  // a round may only start with at most one batch listed
+#pragma unroll
+            for (int q = 0; q < BUILD_KPT; ++q) settle((live >> q) & 1u, h[q], 0u);
+            list_round();
         }
 #pragma unroll 1
-        while (n_def) round(0, 0u);                  // nothing ever waits, so the list drains
+        while (n_def) list_round();                  // nothing ever waits, so the list drains
         __syncthreads();
         for (u32 i = tid; i < BUILD_SLOTS / 2; i += nthreads)
             st_cg_u64x2(region + 2 * i, s_tab[2 * i], s_tab[2 * i + 1]);
