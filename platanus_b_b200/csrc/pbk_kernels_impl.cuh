@@ -1531,8 +1531,8 @@ split_body(const u64 *__restrict__ bkt_hash, const KeyxSources *srcs, u32 n_src,
            u64 *ovf, u64 ovf_cap)
 {
     PBK_DYN_SMEM(u64, s_sorted);                     // the tile's keys in sub-region order: blockDim * SPLIT_KPT entries
-    __shared__ u32 s_cnt[SPLIT_MAX_F], s_off[SPLIT_MAX_F];
-    __shared__ u64 s_base[SPLIT_MAX_F];
+    __shared__ u32 s_cnt[SPLIT_MAX_F], s_off[SPLIT_MAX_F], s_lim[SPLIT_MAX_F];
+    __shared__ u64 s_dst[SPLIT_MAX_F];
     const u32 tid = threadIdx.x, nthreads = blockDim.x, tile_keys = nthreads * SPLIT_KPT;
     const u32 wsize = nthreads < 32u ? nthreads : 32u;
     const u64 t_end = bk[d_end].tile_start;
@@ -1574,13 +1574,9 @@ split_body(const u64 *__restrict__ bkt_hash, const KeyxSources *srcs, u32 n_src,
         __syncthreads();
         // 2. one reservation per non-empty sub-region, issued first: the round trips of these global atomics (all in flight
         //    together) are covered by the prefix scan and the sort below -- the result is only needed for the copy-out
-        const bool one_each = nthreads >= F;         // (the CPU emulation runs one thread: it reserves in a loop)
+        const bool one_each = nthreads >= F;         // (the CPU emulation runs one thread: it reserves in a loop, below)
         u64 my_base = 0;
-        if (one_each) {
-            if (tid < F && s_cnt[tid]) my_base = atomicAdd(&sub_cursor[(u64)bucket * F + tid], (u64)s_cnt[tid]);
-        } else {
-            for (u32 f = tid; f < F; f += nthreads) s_base[f] = s_cnt[f] ? atomicAdd(&sub_cursor[(u64)bucket * F + f], (u64)s_cnt[f]) : 0ull;
-        }
+        if (one_each && tid < F && s_cnt[tid]) my_base = atomicAdd(&sub_cursor[(u64)bucket * F + tid], (u64)s_cnt[tid]);
         //    exclusive prefix of the counts (one warp, a run of consecutive sub-regions per lane)
         if (tid < wsize) {
             const u32 per = (F + wsize - 1) / wsize, f0 = tid * per;
@@ -1595,33 +1591,30 @@ split_body(const u64 *__restrict__ bkt_hash, const KeyxSources *srcs, u32 n_src,
             for (u32 i = 0; i < per; ++i) if (f0 + i < F) { s_off[f0 + i] = run; run += s_cnt[f0 + i]; }
         }
         __syncthreads();
-        // 3. keys into sub-region order
+        // 3. keys into sub-region order; per sub-region: where sorted position p goes (s_dst[f] + p, an index into sub_keys) and the
+        //    first position that no longer fits the segment (s_lim[f])
 #pragma unroll
         for (int q = 0; q < SPLIT_KPT; ++q) {
             const u32 i = 2 * ((u32)(q >> 1) * nthreads + tid) + (u32)(q & 1);
             if (i < n) s_sorted[s_off[sp[q] >> 16] + (sp[q] & 0xFFFFu)] = h[q];
         }
-        if (one_each && tid < F) s_base[tid] = my_base;
+        for (u32 f = tid; f < F; f += nthreads) {
+            const u32 c = s_cnt[f], off = s_off[f];
+            const u64 g0 = one_each ? my_base : (c ? atomicAdd(&sub_cursor[(u64)bucket * F + f], (u64)c) : 0ull);
+            const u64 room = g0 < sub_cap ? sub_cap - g0 : 0ull;
+            s_dst[f] = ((u64)bucket * F + f) * sub_cap + g0 - off;
+            s_lim[f] = off + (u32)min((u64)c, room);
+        }
         __syncthreads();
-        // 4. copy-out: a group of 16 lanes per sub-region (a full tile brings tile_keys / F keys for each: 256 B at F = 256)
-        {
-            const u32 gs = nthreads < 16u ? nthreads : 16u;
-            const u32 gl = tid % gs, n_groups = nthreads / gs;
-            for (u32 f = tid / gs; f < F; f += n_groups) {
-                const u32 c = s_cnt[f];
-                if (c == 0) continue;
-                const u64 g0 = s_base[f];
-                const u64 *from = s_sorted + s_off[f];
-                u64 *to = sub_keys + ((u64)bucket * F + f) * sub_cap + g0;
-                if (g0 + c <= sub_cap) {
-                    for (u32 i = gl; i < c; i += gs) st_stream_u64(to + i, from[i]);
-                } else {
-                    for (u32 i = gl; i < c; i += gs) {
-                        if (g0 + i < sub_cap) st_stream_u64(to + i, from[i]);
-                        else spill_stored<1>(from + i, ctr, ovf, ovf_cap);        // segment full: through the overflow list
-                    }
-                }
-            }
+        // 4. copy-out in sorted order: consecutive positions of a sub-region are consecutive addresses of its segment (a full tile
+        //    brings tile_keys / F keys for each sub-region: 256 B at F = 256); the sub-region of a key is in its own hash bits.
+        //    (The first version gave every sub-region's run to a group of 16 lanes: 41 % of the kernel's instructions went
+        //    into the per-run address arithmetic, profiles/r2l_split_build_kernels.txt)
+        for (u32 p = tid; p < n; p += nthreads) {
+            const u64 hk = s_sorted[p];
+            const u32 f = (u32)(hk >> sub_shift) & (F - 1u);
+            if (p < s_lim[f]) st_stream_u64(sub_keys + (s_dst[f] + p), hk);
+            else spill_stored<1>(&hk, ctr, ovf, ovf_cap);            // segment full: through the overflow list
         }
         __syncthreads();                             // s_cnt / s_off / s_sorted are rewritten by the next tile
     }
