@@ -74,7 +74,18 @@ typedef struct pbk_config {
     uint32_t shard_rank;
     uint64_t table_slots_hint;   /* initial table capacity in slots, 0 = derive from the first push */
     uint64_t hbm_budget_bytes;   /* cap on device memory used by the context, 0 = 85% of free HBM   */
+    /* Hash-range passes on ONE GPU, for a table that does not fit the HBM budget -- the counterpart of the reference's
+     * memory-limited mode, where k-mers that find no room are written to temporary files and counted in further rounds
+     * (counter.h:340-364, 442-449): with n_passes >= 2 this context counts ONLY the k-mers whose hash falls into range
+     * pass_index of n_passes (the ownership function of the sharded forms, pbk_shard_of_key); the caller pushes the same
+     * reads once per pass (the reference re-reads its temp files, too) and adds up what pbk_finalize / pbk_export return:
+     * the passes' key sets are disjoint.  n_instances counts the windows of this pass only.  Not together with n_shards > 1;
+     * pbk_push_contigs is not available.  pbk::Counter (host/pbk_counter.hpp) drives the passes when a plain count ends
+     * with PBK_E_NOMEM.  A config of the earlier, shorter layout (struct_size 40) is accepted: no passes.             */
+    uint32_t n_passes;           /* 0/1 = everything in one pass                                    */
+    uint32_t pass_index;
 } pbk_config;
+#define PBK_CONFIG_SIZE_V1 40u   /* sizeof(pbk_config) before n_passes / pass_index were added */
 
 /* counters of the work done so far; durations are CUDA-event times on the context's own streams */
 typedef struct pbk_stats {

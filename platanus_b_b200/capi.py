@@ -53,7 +53,7 @@ SYMBOLS = [
 class PbkConfig(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("k", C.c_uint32), ("device", C.c_int32), ("flags", C.c_uint32),
                 ("n_shards", C.c_uint32), ("shard_rank", C.c_uint32), ("table_slots_hint", C.c_uint64),
-                ("hbm_budget_bytes", C.c_uint64)]
+                ("hbm_budget_bytes", C.c_uint64), ("n_passes", C.c_uint32), ("pass_index", C.c_uint32)]
 
 
 class PbkStats(C.Structure):
@@ -210,7 +210,7 @@ class KmerGroup:
         self._g = C.c_void_p()
         self.k, self.words = int(k), (int(k) + 31) // 32
         devs = np.ascontiguousarray(devices, dtype=np.int32)
-        cfg = PbkConfig(C.sizeof(PbkConfig), self.k, -1, F_FORCE_PARTITION if partition == "force" else 0 if partition else F_NO_PARTITION, 0, 0, 0, 0)
+        cfg = PbkConfig(C.sizeof(PbkConfig), self.k, -1, F_FORCE_PARTITION if partition == "force" else 0 if partition else F_NO_PARTITION, 0, 0, 0, 0, 0, 0)
         rc = self._L.pbk_group_create(C.byref(self._g), C.byref(cfg), _ptr(devs), len(devs))
         if rc:
             self._g = C.c_void_p()
@@ -283,14 +283,16 @@ class KmerCounter:
 
     def __init__(self, k: int, device: int = -1, n_shards: int = 1, shard_rank: int = 0, timing: bool = False,
                  table_slots_hint: int = 0, hbm_budget_bytes: int = 0, partition: bool | str = True,
-                 pipeline: bool = True, unknown_as_n: bool = False):
+                 pipeline: bool = True, unknown_as_n: bool = False, n_passes: int = 0, pass_index: int = 0):
+        """n_passes >= 2: a hash-range pass on one GPU (pbk_config.n_passes) -- this context counts only the k-mers of range
+        `pass_index`; push the same reads into one context per pass and add the results up."""
         self._L = load_library()
         self._ctx = C.c_void_p()
         self.k = int(k)
         self.words = (self.k + 31) // 32
         cfg = PbkConfig(C.sizeof(PbkConfig), self.k, device, (F_TIMING if timing else 0) | (F_FORCE_PARTITION if partition == "force" else 0 if partition else F_NO_PARTITION) | (0 if pipeline else F_NO_PIPELINE) | (F_UNKNOWN_AS_N if unknown_as_n else 0),
                         n_shards, shard_rank,
-                        table_slots_hint, hbm_budget_bytes)
+                        table_slots_hint, hbm_budget_bytes, n_passes, pass_index)
         rc = self._L.pbk_create(C.byref(self._ctx), C.byref(cfg))
         if rc:
             self._ctx = C.c_void_p()

@@ -80,6 +80,7 @@ struct pbk_ctx {
     u64 *d_bkt_cursor = nullptr, *h_bkt_cursor = nullptr;
     void *d_passb = nullptr, *h_passb = nullptr;    // Pass B bucket descriptors
     bool partition_enabled = true, partition_forced = false;
+    u32 pass = 0;                    // hash-range pass (pbk_config.n_passes >= 2): (n_passes << 16) | pass_index, else 0
     // second form of Pass B (k <= 32, unsharded; split_kernel + region_build_kernel): the sub-region segments and their fill counts
     bool passb2_enabled = false, passb2_gather = false, passb2_fresh = true;
     u64 *d_sub_keys = nullptr; size_t sub_bytes = 0;
@@ -433,7 +434,7 @@ int count_range(pbk_ctx *c, u64 w0, u64 w1)
     {
         Span sp(c, LC_COUNT);
         launch_count(c->d_stream_raw + STREAM_PAD_WORDS, c->d_nflag_raw + STREAM_PAD_WORDS, c->d_rflag_raw + STREAM_PAD_WORDS,
-                     w0, w1, (int)c->k, c->table, c->remote, c->shard, c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute);
+                     w0, w1, (int)c->k, c->table, c->remote, c->shard, c->d_ctr, c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute, c->pass);
         c->table_touched = true;
     }
     CK(cudaGetLastError());
@@ -711,7 +712,7 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
         {
             Span sp(c, LC_PART);
             launch_partition(stream, nflag, rflag, w0, w1, (int)c->k, c->W, c->plan, bkt_keys, bkt_cursor, c->d_ctr,
-                             c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute, keyx ? c->shard.n_shards : 1u);
+                             c->d_ovf, c->ovf_cap, c->sm_count, c->s_compute, keyx ? c->shard.n_shards : 1u, c->pass);
         }
         if (pipe.on && ++pipe.in_sb >= pipe.sb_chunks()) TRY(pipe_finish_subbatch(c, pipe));
         return PBK_OK;
@@ -948,10 +949,15 @@ const char *pbk_strerror(int s)
 
 const char *pbk_last_error(const pbk_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
 
-int pbk_create(pbk_ctx **out, const pbk_config *cfg)
+int pbk_create(pbk_ctx **out, const pbk_config *cfg_in)
 {
-    if (!out || !cfg || cfg->struct_size < sizeof(pbk_config)) return PBK_E_ARG;
+    if (!out || !cfg_in || cfg_in->struct_size < PBK_CONFIG_SIZE_V1) return PBK_E_ARG;
     *out = nullptr;
+    pbk_config cfg_full;
+    memset(&cfg_full, 0, sizeof cfg_full);
+    memcpy(&cfg_full, cfg_in, std::min<size_t>(cfg_in->struct_size, sizeof cfg_full));     // (a shorter, earlier layout: the new fields are 0)
+    const pbk_config *cfg = &cfg_full;
+    if (cfg->n_passes > 1 && (cfg->pass_index >= cfg->n_passes || cfg->n_passes > 0xFFFFu || cfg->n_shards > 1)) return PBK_E_ARG;
     if (cfg->k == 0 || cfg->k > PBK_MAX_K) return PBK_E_UNSUPPORTED_K;
     if (cfg->n_shards > 1 && cfg->shard_rank >= cfg->n_shards) return PBK_E_ARG;
     int n_dev = 0;
@@ -969,6 +975,7 @@ int pbk_create(pbk_ctx **out, const pbk_config *cfg)
     c->shard.n_shards = cfg->n_shards > 1 ? cfg->n_shards : 1;
     c->shard.rank = cfg->n_shards > 1 ? cfg->shard_rank : 0;
     c->table_hint = cfg->table_slots_hint;
+    c->pass = cfg->n_passes > 1 ? ((cfg->n_passes << 16) | cfg->pass_index) : 0u;
     c->partition_enabled = !(cfg->flags & PBK_F_NO_PARTITION) && getenv("PBK_NO_PARTITION") == nullptr;
     c->partition_forced = (cfg->flags & PBK_F_FORCE_PARTITION) != 0;
     size_t free_b = 0, total_b = 0;
@@ -1356,6 +1363,7 @@ int pbk_load_entries(pbk_ctx *c, const uint64_t *keys, const uint16_t *counts, u
         for (u64 i = at; i < at + m; ++i) {
             if (counts[i] == 0) continue;                            // an empty slot of the reference table
             if (c->shard.n_shards > 1 && pbk_shard_of_key(keys + i * W, c->k, c->shard.n_shards) != c->shard.rank) continue;
+            if (c->pass && pbk_shard_of_key(keys + i * W, c->k, c->pass >> 16) != (c->pass & 0xFFFFu)) continue;   // another pass's key
             for (int j = 0; j < W; ++j) rec.push_back(keys[i * W + j]);
             rec.push_back(counts[i]);
         }
@@ -1499,6 +1507,7 @@ int pbk_push_contigs(pbk_ctx *c, const uint8_t *bases, const uint64_t *seq_offse
     if (n_seqs == 0) return PBK_OK;
     if (!seq_offsets || !coverage || seq_offsets[0] != 0) return fail(c, PBK_E_ARG, "bad arguments");
     if (c->finalized) return fail(c, PBK_E_STATE, "pbk_push_contigs after pbk_finalize (call pbk_reset first)");
+    if (c->pass) return fail(c, PBK_E_STATE, "pbk_push_contigs is not available in a hash-range pass (pbk_config.n_passes)");
     const u64 n_bases = seq_offsets[n_seqs];
     if (n_bases == 0) return PBK_OK;
     if (!bases) return fail(c, PBK_E_ARG, "bases is NULL");
@@ -1572,6 +1581,7 @@ int pbk_seed_entries(pbk_ctx *c, const uint64_t *keys, const uint16_t *counts, u
     for (u64 i = 0; i < n; ++i) {
         if (counts[i] == 0) continue;                                // counter.h:700: only entries with a value are written
         if (c->shard.n_shards > 1 && pbk_shard_of_key(keys + i * W, c->k, c->shard.n_shards) != c->shard.rank) continue;
+        if (c->pass && pbk_shard_of_key(keys + i * W, c->k, c->pass >> 16) != (c->pass & 0xFFFFu)) continue;       // another pass's key
         for (int j = 0; j < W; ++j) c->seed_rec.push_back(keys[i * W + j]);
         c->seed_rec.push_back(counts[i]);
     }

@@ -82,6 +82,7 @@ struct KeyxSources {
 };
 
 enum : u32 { ERR_BAD_BASE = 1u, ERR_READ_TOO_LONG = 2u, ERR_OVERFLOW_LOST = 4u };
+constexpr u32 PASS_ONLY_BIT = 1u << 31;      // in a kernel's n_shards argument: hash-range pass, foreign keys are skipped (count_kernel)
 
 __host__ __device__ __forceinline__ u64 fmix64(u64 x)
 {

@@ -116,7 +116,12 @@ int pbk_device_count(void)
 
 int pbk_group_create(pbk_group **out, const pbk_config *cfg, const int32_t *devices, uint32_t n_devices)
 {
-    if (!out || !cfg || cfg->struct_size < sizeof(pbk_config) || n_devices == 0 || n_devices > 16) return PBK_E_ARG;
+    if (!out || !cfg || cfg->struct_size < PBK_CONFIG_SIZE_V1 || n_devices == 0 || n_devices > 16) return PBK_E_ARG;
+    pbk_config cfg_full;                                            // (a shorter, earlier layout: the new fields are 0)
+    memset(&cfg_full, 0, sizeof cfg_full);
+    memcpy(&cfg_full, cfg, std::min<size_t>(cfg->struct_size, sizeof cfg_full));
+    cfg_full.n_passes = cfg_full.pass_index = 0;                    // hash-range passes are a one-GPU mode
+    cfg = &cfg_full;
     *out = nullptr;
     pbk_group *g = new (std::nothrow) pbk_group();
     if (!g) return PBK_E_NOMEM;

@@ -71,14 +71,16 @@ void launch_npos_scatter(const u64 *offsets, const int32_t *n_pos, const u64 *n_
 
 void launch_count(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
                   TableView table, TableView remote, ShardInfo shard, Counters *ctr,
-                  u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st)
+                  u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st, u32 pass)
 {
     if (word_end <= word_begin) return;
     const int grid = grid_for(word_end - word_begin, 256, sm_count, 8);
+    // hash-range pass on an unsharded context: the ownership test of the sharded form, with foreign keys skipped
+    const u32 n_sh = pass ? ((pass >> 16) | PASS_ONLY_BIT) : shard.n_shards, rank = pass ? (pass & 0xFFFFu) : shard.rank;
     PBK_DISPATCH_W(table.words,
         (count_kernel<W><<<grid, 256, 0, st>>>(stream, nflag, rflag, word_begin, word_end, k,
             Table<W>(table.slots, table.cap), Table<W>(remote.slots, remote.cap),
-            shard.n_shards, shard.rank, ctr, overflow_keys, overflow_cap)));
+            n_sh, rank, ctr, overflow_keys, overflow_cap)));
 }
 
 void launch_lookup(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
@@ -185,19 +187,20 @@ PartitionPlan plan_partition_keyx(u32 n_dest, u64 max_windows_any_rank, int word
     return p;
 }
 
-template <int W, bool KEYX>
+template <int W, bool KEYX, bool PASSF = false>
 static void partition_launch_w(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
                                const PartitionPlan &plan, u64 *bkt_keys, u64 *bkt_cursor, Counters *ctr,
                                u64 *overflow_keys, u64 overflow_cap, int grid, u32 n_dest, cudaStream_t st)
 {
-    cudaFuncSetAttribute(partition_kernel<W, KEYX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
-    partition_kernel<W, KEYX><<<grid, plan.threads, plan.smem, st>>>(stream, nflag, rflag, word_begin, word_end, k,
+    cudaFuncSetAttribute(partition_kernel<W, KEYX, PASSF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    partition_kernel<W, KEYX, PASSF><<<grid, plan.threads, plan.smem, st>>>(stream, nflag, rflag, word_begin, word_end, k,
         plan.n_buckets, plan.bin_cap, bkt_keys, plan.seg_cap, bkt_cursor, ctr, overflow_keys, overflow_cap, n_dest);
 }
 
+// pass != 0: (n_passes << 16) | pass_index -- only the keys of that hash range are bucketed (pbk_config.n_passes; not with keyx_dest)
 void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
                       int words, const PartitionPlan &plan, u64 *bkt_keys, u64 *bkt_cursor, Counters *ctr,
-                      u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st, u32 keyx_dest)
+                      u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st, u32 keyx_dest, u32 pass)
 {
     if (word_end <= word_begin) return;
     const u64 subs = words == 1 ? 32 / PART_WIN1 : words == 2 ? 2 : 32 / PBK_PART_WIN3;       // 32 / PART_WIN<W>: work items per stream word
@@ -216,13 +219,25 @@ void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64
     if (words > 1 && compact && plan.threads <= PARTC_MAX_THREADS) {
         switch (words) {
 #define PBK_CASE_W(Wv) case Wv:                                                                                                        \
-            cudaFuncSetAttribute(partition_compact_kernel<Wv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);           \
-            partition_compact_kernel<Wv><<<grid, plan.threads, plan.smem, st>>>(stream, nflag, rflag, word_begin, word_end, k,          \
-                plan.n_buckets, plan.bin_cap, bkt_keys, plan.seg_cap, bkt_cursor, ctr, overflow_keys, overflow_cap); break;
+            if (pass) {                                                                                                                \
+                cudaFuncSetAttribute(partition_compact_kernel<Wv, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem); \
+                partition_compact_kernel<Wv, true><<<grid, plan.threads, plan.smem, st>>>(stream, nflag, rflag, word_begin, word_end, k, \
+                    plan.n_buckets, plan.bin_cap, bkt_keys, plan.seg_cap, bkt_cursor, ctr, overflow_keys, overflow_cap, pass);         \
+            } else {                                                                                                                   \
+                cudaFuncSetAttribute(partition_compact_kernel<Wv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);       \
+                partition_compact_kernel<Wv><<<grid, plan.threads, plan.smem, st>>>(stream, nflag, rflag, word_begin, word_end, k,      \
+                    plan.n_buckets, plan.bin_cap, bkt_keys, plan.seg_cap, bkt_cursor, ctr, overflow_keys, overflow_cap, 0u);           \
+            } break;
         PBK_CASE_W(2) PBK_CASE_W(3) PBK_CASE_W(4) PBK_CASE_W(5) PBK_CASE_W(6) PBK_CASE_W(7) PBK_CASE_W(8)
 #undef PBK_CASE_W
         default: break;
         }
+        return;
+    }
+    if (pass) {
+        PBK_DISPATCH_W(words,
+            (partition_launch_w<W, false, true>(stream, nflag, rflag, word_begin, word_end, k, plan, bkt_keys, bkt_cursor, ctr,
+                                                overflow_keys, overflow_cap, grid, pass, st)));
         return;
     }
     PBK_DISPATCH_W(words,

@@ -37,7 +37,7 @@ void launch_npos_abs_scatter(const u64 *n_positions, u64 n_n, u64 n_bases, u32 *
 // windows that END in stream words [word_begin, word_end) are canonicalised and inserted
 void launch_count(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
                   TableView table, TableView remote, ShardInfo shard, Counters *ctr,
-                  u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st);
+                  u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st, u32 pass = 0);
 // occ[p] (u16, one per stream position of words [word_begin, word_end); 8-byte aligned) = clamped count of the window
 // that ENDS at p, 0 if unusable or absent.  Read-only on the table.
 void launch_lookup(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
@@ -71,7 +71,9 @@ PartitionPlan plan_partition(u64 est_table_bytes, u64 windows_ub, int words, siz
 // Pass A over stream words [word_begin, word_end): keys go to bkt_keys (P segments of seg_cap entries)
 void launch_partition(const u64 *stream, const u32 *nflag, const u32 *rflag, u64 word_begin, u64 word_end, int k,
                       int words, const PartitionPlan &plan, u64 *bkt_keys, u64 *bkt_cursor, Counters *ctr,
-                      u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st, u32 keyx_dest = 1);
+                      u64 *overflow_keys, u64 overflow_cap, int sm_count, cudaStream_t st, u32 keyx_dest = 1, u32 pass = 0);
+// (pass != 0 in launch_count / launch_partition: (n_passes << 16) | pass_index -- a hash-range pass over the whole input on one
+//  GPU, pbk_config.n_passes: only the keys with shard_of_hash(hash, n_passes) == pass_index are counted, the others skipped)
 // Key exchange between GPUs (k <= 32, pbk_keyx_*): plan with n_dest x n_regions buckets in destination-major order
 // (launch_partition with keyx_dest = n_dest fills it), and Pass B over the all-to-all receive buffer.
 PartitionPlan plan_partition_keyx(u32 n_dest, u64 max_windows_any_rank, int words, size_t smem_budget = 0);

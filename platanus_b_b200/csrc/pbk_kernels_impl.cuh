@@ -178,8 +178,12 @@ template <int W>
 __global__ void __launch_bounds__(256)
 count_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, const u32 *__restrict__ rflag,
              u64 word_begin, u64 word_end, int k, Table<W> table, Table<W> remote,
-             u32 n_shards, u32 rank, Counters *ctr, u64 *ovf, u64 ovf_cap)
+             u32 n_shards_in, u32 rank, Counters *ctr, u64 *ovf, u64 ovf_cap)
 {
+    // PASS_ONLY_BIT: a hash-range pass over the whole input on one GPU (pbk_config.n_passes): keys of the other ranges are
+    // skipped -- neither counted nor staged -- because a later pass over the same reads picks them up
+    const bool pass_only = (n_shards_in & PASS_ONLY_BIT) != 0;
+    const u32 n_shards = n_shards_in & ~PASS_ONLY_BIT;
     const int top_shift = 2 * ((k - 1) & 31);
     const u64 top_mask = (k & 31) ? ((1ull << (2 * (k & 31))) - 1ull) : ~0ull;
     const int s = 2 * (32 * W - k);                   // 0..62
@@ -235,9 +239,11 @@ count_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, cons
 #pragma unroll
                 for (int j = 0; j < W; ++j) key[j] = use_rev ? rev[j] : fwd[j];
                 const u64 h = hash_key<W>(key);
+                const bool foreign = n_shards > 1 && shard_of_hash(h, n_shards) != rank;
+                if (foreign && pass_only) continue;
                 ++inst;
                 int r;
-                if (n_shards > 1 && shard_of_hash(h, n_shards) != rank) {
+                if (foreign) {
                     r = remote.insert(key, h, 1u, true);
                     newr += (r > 0);
                 } else {
@@ -609,7 +615,9 @@ __device__ __forceinline__ u64 smear_up(u64 x, int w)
 // KEYX (key exchange between GPUs, pbk_keyx_*): the n_buckets = n_dest x R buckets are ordered by owner shard first
 // (shard_of_hash, the low hash bits) and by table region second (the top hash bits, R a power of two), so that the
 // segments of one destination are contiguous -- the bucket store is the all-to-all send buffer as it stands.
-template <int W, bool KEYX = false>
+// PASSF (hash-range passes on one GPU, pbk_config.n_passes): n_dest carries (n_passes << 16) | pass_index and only the keys of
+// that range are bucketed (and counted as instances); the other instantiations are unchanged.
+template <int W, bool KEYX = false, bool PASSF = false>
 __global__ void __launch_bounds__(512)
 partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, const u32 *__restrict__ rflag,
                  u64 word_begin, u64 word_end, int k, u32 n_buckets, u32 bin_cap, u64 *bkt_keys, u64 seg_cap,
@@ -667,6 +675,7 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
                     r = (r >> 2) | ((u64)(3u - b) * topmul);
                     if ((valid >> i) & 1u) {
                         const u64 hh = fmix64(r < f ? r : f);        // key = min(forward, reverse), counter.h:429
+                        if constexpr (PASSF) { if (shard_of_hash(hh, n_dest >> 16) != (n_dest & 0xFFFFu)) continue; }
                         u32 bkt = (u32)(hh >> pshift);                // == mulhi(hh, n_buckets) for a power of two
                         if constexpr (KEYX) bkt += shard_of_hash(hh, n_dest) * n_part;
                         ++n_here;
@@ -748,6 +757,7 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
 #pragma unroll
                     for (int j = 0; j < W; ++j) key[j] = use_rev ? rev[j] : fwd[j];
                     const u64 hh = hash_key<W>(key);
+                    if constexpr (PASSF) { if (shard_of_hash(hh, n_dest >> 16) != (n_dest & 0xFFFFu)) continue; }
                     u32 bkt = (u32)__umul64hi(hh, (u64)n_part);
                     if constexpr (KEYX) bkt += shard_of_hash(hh, n_dest) * n_part;
                     if (W == 1) key[0] = hh;          // one-word keys travel as their (bijective) hash
@@ -810,11 +820,11 @@ partition_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, 
 constexpr int PARTC_MAX_THREADS = 512;
 struct PartcEntry { u32 item; int run; };
 
-template <int W>
+template <int W, bool PASSF = false>
 __global__ void __launch_bounds__(PARTC_MAX_THREADS)
 partition_compact_kernel(const u64 *__restrict__ stream, const u32 *__restrict__ nflag, const u32 *__restrict__ rflag,
                          u64 word_begin, u64 word_end, int k, u32 n_buckets, u32 bin_cap, u64 *bkt_keys, u64 seg_cap,
-                         u64 *bkt_cursor, Counters *ctr, u64 *ovf, u64 ovf_cap)
+                         u64 *bkt_cursor, Counters *ctr, u64 *ovf, u64 ovf_cap, u32 pass)     // pass: PASSF only, (n_passes << 16) | pass_index
 {
     PBK_DYN_SMEM(u64, bins);                          // n_buckets * bin_cap * W words
     __shared__ u32 scount[PART_MAX_BUCKETS];
@@ -934,6 +944,7 @@ partition_compact_kernel(const u64 *__restrict__ stream, const u32 *__restrict__
 #pragma unroll
                     for (int j = 0; j < W; ++j) key[j] = use_rev ? rev[j] : fwd[j];
                     const u64 hh = hash_key<W>(key);
+                    if constexpr (PASSF) { if (shard_of_hash(hh, pass >> 16) != (pass & 0xFFFFu)) continue; }
                     const u32 bkt = (u32)__umul64hi(hh, (u64)n_buckets);
                     ++inst;
                     const u32 pos = atomicAdd(&scount[bkt], 1u);
