@@ -64,10 +64,7 @@ BODY_PREV = r'''{
         std::vector<uint16_t> values;
         pbk::shim::tableEntries(kmer, occurrenceTable, true, words, values);
         if (!gpu) gpu.reset(new pbk::Counter(k));
-        gpu->beginCounting(k);
-        gpu->seedEntries(words.data(), values.data(), values.size());
-        gpu->pushSeqTempFiles(readFP, numThread);
-        gpu->endCounting(memory);
+        gpu->makeKmerReadDistributionSeeded(k, readFP, memory, numThread, words.data(), values.data(), values.size());
         pbk::shim::publish(*gpu, k, kmerFP, occurrenceDistribution, this->maxOccurrence);
     } catch (const pbk::ErrorBase &e) {
         pbk::shim::rethrow(e);

@@ -142,6 +142,14 @@ double max_load(const pbk_ctx *c)
     return c->W == 1 ? MAX_LOAD_COMPACT : wide;
 }
 
+// a hash-range pass (pbk_config.n_passes) keeps 1 / n_passes of a batch's windows: what tables and bucket stores are sized for
+u64 pass_share(const pbk_ctx *c, u64 windows)
+{
+    if (!c->pass) return windows;
+    const u64 n = c->pass >> 16;
+    return windows / n + windows / (8 * n) + 4096;
+}
+
 int fail(pbk_ctx *c, int code, const char *fmt, ...)
 {
     char buf[512];
@@ -428,8 +436,8 @@ int count_range(pbk_ctx *c, u64 w0, u64 w1)
     TRY(table_ready(c));
     const u64 windows = (w1 - w0) * 32;
     TRY(maybe_clamp(c, windows));
-    TRY(ensure_room(c, (u64)(windows * std::min(1.0, c->new_ratio * 1.25))));
-    TRY(ensure_overflow(c, windows));
+    TRY(ensure_room(c, (u64)(pass_share(c, windows) * std::min(1.0, c->new_ratio * 1.25))));
+    TRY(ensure_overflow(c, pass_share(c, windows)));   // (only keys that are counted can spill)
     const u64 before_new = c->occupied + c->occupied_remote, before_inst = c->last.instances;
     {
         Span sp(c, LC_COUNT);
@@ -657,7 +665,7 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
     if (keyx && windows_ub > c->keyx_max_windows)
         return fail(c, PBK_E_ARG, "batch has up to %llu windows, the key-exchange layout was planned for %llu",
                     (unsigned long long)windows_ub, (unsigned long long)c->keyx_max_windows);
-    if (!keyx) TRY(ensure_tables(c, std::max<u64>(windows_ub, 1024), true));
+    if (!keyx) TRY(ensure_tables(c, std::max<u64>(pass_share(c, windows_ub), 1024), true));
 
     u64 *stream = c->d_stream_raw + STREAM_PAD_WORDS;
     u32 *nflag = c->d_nflag_raw + STREAM_PAD_WORDS, *rflag = c->d_rflag_raw + STREAM_PAD_WORDS;
@@ -696,14 +704,14 @@ int push_common(pbk_ctx *c, const uint8_t *h_bases, const uint8_t *d_bases_in, c
         for (u32 i = 0; i < n_sb; ++i) largest = std::max(largest, pipe.sizes[i]);
         const u64 sb_windows = std::min<u64>(windows_ub, (u64)largest * CHUNK_BASES);
         TRY(maybe_clamp(c, windows_ub));
-        TRY(ensure_room(c, (u64)(windows_ub * std::min(1.0, c->new_ratio * 1.15)) + 65536));
-        TRY(prepare_partition(c, sb_windows, windows_ub));
+        TRY(ensure_room(c, (u64)(pass_share(c, windows_ub) * std::min(1.0, c->new_ratio * 1.15)) + 65536));
+        TRY(prepare_partition(c, pass_share(c, sb_windows), pass_share(c, windows_ub)));
     } else if (keyx) {
         c->plan = c->keyx_plan;
         CK(cudaMemsetAsync(c->keyx_cursors, 0, (size_t)c->plan.n_buckets * 8, c->s_compute));
         TRY(ensure_overflow_for_batch(c, windows_ub));
     } else if (partitioned) {
-        TRY(prepare_partition(c, windows_ub, windows_ub));
+        TRY(prepare_partition(c, pass_share(c, windows_ub), pass_share(c, windows_ub)));
     }
     u64 *const bkt_keys = keyx ? c->keyx_send : c->d_bkt_keys, *const bkt_cursor = keyx ? c->keyx_cursors : c->d_bkt_cursor;
     // large batches: Pass A per chunk (no host sync), Pass B once at the end.  Small ones: straight to the table.

@@ -275,6 +275,7 @@ void exec(Options &opt)
 
     PhaseTimer pt;
     pbk::Counter counter;
+    counter.setTmpDir(tmp_dir);
     // open (and, for gzip/bzip2 inputs, decompress: one `gzip -cd` per file, -t at a time) and sniff the inputs; the
     // first failure in file order is the one reported, as in the reference's serial loop (assemble.cpp:162-163)
     std::vector<int> types(files.size(), 0);
@@ -301,18 +302,22 @@ void exec(Options &opt)
         for (size_t i = 0; i < files.size(); ++i) if (open_err[i]) throw *open_err[i];
     }
     u64 double_hash_size = 0;
-    if (opt.flag["-seq_tmp"]) {
-        // narrow seam: exactly the reference's data flow up to Counter::makeKmerReadDistributionMT
+    // narrow seam: exactly the reference's data flow up to Counter::makeKmerReadDistributionMT -- the reads go through the SEQ
+    // temp files (-seq_tmp), which is also where the streaming path below falls back to when the table does not fit the HBM
+    // budget: the temp files can be read once per hash-range pass (pbk::Counter::countFed), a parsed stream cannot
+    auto count_through_temp_files = [&](bool announce) {
         std::vector<FILE *> read_fp;
         for (u64 i = 0; i < num_thread; ++i) read_fp.push_back(pbk::Counter::makeTemporaryFile(opt.single["-tmp"]));
         SeqTmpSink sink(read_fp);
-        for (size_t i = 0; i < files.size(); ++i) {
-            parse_whole_file(*maps[i], types[i] == 2, sink);
-            delete maps[i];
-        }
-        std::cerr << "K = " << k0 << ", saving kmers from reads..." << std::endl;
+        for (size_t i = 0; i < files.size(); ++i) parse_whole_file(*maps[i], types[i] == 2, sink);
+        if (announce) std::cerr << "K = " << k0 << ", saving kmers from reads..." << std::endl;
         double_hash_size = counter.makeKmerReadDistributionMT(k0, read_fp.data(), memory, num_thread);
         for (size_t i = 0; i < read_fp.size(); ++i) fclose(read_fp[i]);
+        if (counter.getNumPasses() > 1 && getenv("PBK_TIMING")) std::cerr << "[pbk] table beyond the HBM budget: counted in " << counter.getNumPasses() << " hash-range passes" << std::endl;
+    };
+    if (opt.flag["-seq_tmp"]) {
+        count_through_temp_files(true);
+        for (size_t i = 0; i < maps.size(); ++i) delete maps[i];
     } else {
     pt.mark("open + sniff inputs");
     std::cerr << "K = " << k0 << ", saving kmers from reads..." << std::endl;                   // assemble.cpp:306
@@ -391,12 +396,16 @@ void exec(Options &opt)
         q.put_free(b);
     }
     for (size_t w = 0; w < workers.size(); ++w) workers[w].join();
-    for (size_t i = 0; i < maps.size(); ++i) delete maps[i];
     if (!errors.empty()) throw errors[0];
-    if (push_error) throw *push_error;
+    bool beyond_budget = push_error && push_error->getID() == pbk::E_GPU_NOMEM && counter.getNumDevices() == 1;
+    if (push_error && !beyond_budget) throw *push_error;
     pt.mark("parse + push (overlapped)");
-
-    double_hash_size = counter.endCounting(memory);
+    if (!beyond_budget) {
+        try { double_hash_size = counter.endCounting(memory); }
+        catch (pbk::NoMemory &) { if (counter.getNumDevices() > 1) throw; beyond_budget = true; }
+    }
+    if (beyond_budget) count_through_temp_files(false);        // the table does not fit: hash-range passes over the SEQ temp files
+    for (size_t i = 0; i < maps.size(); ++i) delete maps[i];
     pt.mark("pbk_finalize");
     }
 

@@ -13,6 +13,7 @@
 
 #include "../../include/pbk.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -26,7 +27,7 @@
 namespace pbk {
 
 // platanus::ERROR ids (common.h:55-56): the process exit code of the reference's main (main.cpp:121-124)
-enum ErrorId { E_IO = 0, E_FOPEN = 1, E_TMP = 2, E_FORMAT = 3, E_READ = 4, E_KMERDIST = 6, E_GPU = 64 };
+enum ErrorId { E_IO = 0, E_FOPEN = 1, E_TMP = 2, E_FORMAT = 3, E_READ = 4, E_KMERDIST = 6, E_GPU = 64, E_GPU_NOMEM = 65 };
 
 class ErrorBase {
 public:
@@ -42,7 +43,11 @@ struct FILEError : ErrorBase { explicit FILEError(const std::string &f) : ErrorB
 struct TMPError : ErrorBase { TMPError() : ErrorBase(E_TMP, "Error, temporary file exception!!") {} };
 struct ReadError : ErrorBase { explicit ReadError(const std::string &m = "") : ErrorBase(E_READ, "Error, Read file exception!!" + (m.empty() ? m : "\n" + m)) {} };
 struct KmerDistError : ErrorBase { KmerDistError() : ErrorBase(E_KMERDIST, "Error, kmer distribution exception!!\nkmer distribution can't be calculated.") {} };
-struct GPUError : ErrorBase { explicit GPUError(const std::string &m) : ErrorBase(E_GPU, "Error, GPU k-mer counter exception!!\n" + m) {} };
+struct GPUError : ErrorBase {
+    explicit GPUError(const std::string &m, int id = E_GPU) : ErrorBase(id, "Error, GPU k-mer counter exception!!\n" + m) {}
+};
+// the table does not fit the HBM budget (PBK_E_NOMEM): what the counting members answer with hash-range passes
+struct NoMemory : GPUError { explicit NoMemory(const std::string &m) : GPUError(m, E_GPU_NOMEM) {} };
 
 class Counter {
 public:
@@ -54,7 +59,7 @@ public:
                 device_(-1), flags_(0), numDevices_(1) {}
     explicit Counter(u64_t k) : kmerFP(NULL), ctx_(NULL), group_(NULL), kmerLength_(k), maxOccurrence_(0), doubleHashSize_(0), nInstances_(0),
                                 nDistinct_(0), device_(-1), flags_(0), numDevices_(1) {}
-    ~Counter() { if (ctx_) pbk_destroy(ctx_); if (group_) pbk_group_destroy(group_); }
+    ~Counter() { if (ctx_) pbk_destroy(ctx_); if (group_) pbk_group_destroy(group_); if (passFP_) fclose(passFP_); }
     Counter(const Counter &) = delete;
     Counter &operator=(const Counter &) = delete;
 
@@ -69,6 +74,12 @@ public:
     unsigned getNumDevices() const { return numDevices_; }
     void setFlags(unsigned flags) { flags_ = flags; }
     pbk_ctx *context() { return ctx_; }
+    // cap on the device memory of a context (default: 85 % of the free HBM; PBK_HBM_BUDGET_MB overrides both) and the directory
+    // of the temporary file the hash-range passes collect their entries in (the reference's -tmp)
+    void setHbmBudget(u64_t bytes) { hbmBudget_ = bytes; }
+    void setTmpDir(const std::string &dir) { tmpDir_ = dir; }
+    // how many hash-range passes the last count took (1 = the table fitted)
+    unsigned getNumPasses() const { return passes_; }
 
     // ---- getters (counter.h:86-92) ------------------------------------------------------------
     u64_t getMaxOccurrence() const { return maxOccurrence_; }
@@ -91,15 +102,22 @@ public:
 
     // ---- the wide seam: reads straight from the parser (what Assemble::readInputFile hands to
     //      SEQ::convertFromString, assemble.cpp:790-986), no temp-file detour ----------------------
-    void beginCounting(u64_t kLength)
+    void beginCounting(u64_t kLength) { beginPass(kLength, 1, 0); multiPass_ = false; passes_ = 1; }
+    // a context that counts hash range `pass` of `passes` (pbk_config.n_passes); passes == 1: everything
+    void beginPass(u64_t kLength, unsigned passes, unsigned pass)
     {
         kmerLength_ = kLength;
         keptValid_ = false;
         if (group_) { check(pbk_group_reset(group_, (uint32_t)kLength), "pbk_group_reset"); return; }
-        if (ctx_) { check(pbk_reset(ctx_, (uint32_t)kLength), "pbk_reset"); return; }
+        if (ctx_ && passes == 1 && !ctxIsPass_) { check(pbk_reset(ctx_, (uint32_t)kLength), "pbk_reset"); return; }
+        dropContext();                                       // (a pass context is bound to its range: a new one per pass)
         pbk_config cfg;
         memset(&cfg, 0, sizeof cfg);
         cfg.struct_size = sizeof cfg; cfg.k = (uint32_t)kLength; cfg.device = device_; cfg.flags = flags_;
+        cfg.hbm_budget_bytes = hbmBudget_;
+        if (const char *e = getenv("PBK_HBM_BUDGET_MB")) { const long long mb = atoll(e); if (mb > 0) cfg.hbm_budget_bytes = (uint64_t)mb << 20; }
+        if (passes > 1) { cfg.n_passes = passes; cfg.pass_index = pass; }
+        ctxIsPass_ = passes > 1;
         if (numDevices_ > 1) {
             const int rc = pbk_group_create(&group_, &cfg, deviceList_.empty() ? NULL : deviceList_.data(), numDevices_);
             if (rc != PBK_OK) { group_ = NULL; throw GPUError(pbk_strerror(rc)); }
@@ -135,11 +153,45 @@ public:
     // ---- the narrow seam: counter.h:276-383 -------------------------------------------------------
     // readFP[0..numThread) are the per-thread SEQ temp files (common.h:426-448).  They are left
     // readable (counter.h:874 rewinds them again).  numThread only says how many files there are.
+    // If the table does not fit the HBM budget (PBK_E_NOMEM) the count is repeated in 2, 4, 8 ... hash-range passes over the
+    // same temp files -- the counterpart of the reference's own memory-limited mode, which writes the k-mers that found no
+    // room to temporary files and counts them in further rounds (counter.h:340-364, 442-449).
     u64_t makeKmerReadDistributionMT(u64_t kLength, FILE **readFP, u64_t memory, u64_t numThread)
     {
-        beginCounting(kLength);
-        pushSeqTempFiles(readFP, numThread);
-        return endCounting(memory);
+        const SeqTempFeed feed = {readFP, numThread};
+        return countFed(kLength, memory, feed, NULL, NULL, 0);
+    }
+    // feeder over the per-thread SEQ temp files (rewound and read once per pass)
+    struct SeqTempFeed { FILE **fp; u64_t n; void operator()(Counter &c) const { c.pushSeqTempFiles(fp, n); } };
+    // Counter::makeKmerReadDistributionConsideringPreviousGraph (counter.h:663-750) on the same files: the seeded k-mers keep
+    // their value, every other k-mer of the reads is counted -- in hash-range passes, too, if the table does not fit
+    u64_t makeKmerReadDistributionSeeded(u64_t kLength, FILE **readFP, u64_t memory, u64_t numThread, const uint64_t *seedKeys,
+                                         const uint16_t *seedValues, uint64_t nSeeds)
+    {
+        const SeqTempFeed feed = {readFP, numThread};
+        return countFed(kLength, memory, feed, seedKeys, seedValues, nSeeds);
+    }
+    // The general form: feed(*this) pushes ALL reads (pushReads / pushSeqTempFiles) and is called once per pass; seeds
+    // (makeKmerReadDistributionConsideringPreviousGraph) are handed to every pass, the library keeps those of its range.
+    template <typename Feed>
+    u64_t countFed(u64_t kLength, u64_t memory, const Feed &feed, const uint64_t *seedKeys, const uint16_t *seedValues, uint64_t nSeeds)
+    {
+        unsigned passes = 1;
+        if (const char *e = getenv("PBK_NUM_PASSES")) passes = (unsigned)std::max(1, atoi(e));       // (tests; a power of two is not required)
+        for (;; passes *= 2) {
+            try {
+                if (passes == 1) {
+                    beginCounting(kLength);
+                    if (nSeeds) seedEntries(seedKeys, seedValues, nSeeds);
+                    feed(*this);
+                    return endCounting(memory);
+                }
+                return countInPasses(kLength, memory, passes, feed, seedKeys, seedValues, nSeeds);
+            } catch (const NoMemory &) {
+                dropContext();
+                if (group_ || passes >= 4096) throw;
+            }
+        }
     }
     // the reads of numThread SEQ temp files (common.h:426-448), in batches of 256 MB, through PBK_ENC_PLATANUS
     void pushSeqTempFiles(FILE **readFP, u64_t numThread)
@@ -284,6 +336,7 @@ public:
             keptMin_ = minOccurrence; keptValid_ = true;
             return;
         }
+        if (multiPass_) { exportFromPassFile(minOccurrence, sorted); return; }
         check(pbk_export(ctx_, (uint32_t)minOccurrence, sorted ? 1 : 0, NULL, NULL, 0, &n), "pbk_export");
         keptKeys_.assign(n * W, 0);
         keptCounts_.assign(n, 0);
@@ -297,6 +350,14 @@ public:
         if (!keptValid_) throw GPUError("neighborFlags before sortedKeyFromKmerFile / exportKmers");
         std::vector<uint8_t> flags(keptCounts_.size(), 0);
         if (flags.empty()) return flags;
+        if (multiPass_ && !ctx_) {
+            // the passes' tables are gone; the kept entries (count >= the cutoff: what loadKmer puts into the host DoubleHash,
+            // counter.h:600-640) fit -- they are what the graph stage works on
+            beginPass(kmerLength_, 1, 0);
+            keptValid_ = true;
+            check(pbk_load_entries(ctx_, keptKeys_.data(), keptCounts_.data(), keptCounts_.size()), "pbk_load_entries");
+            check(pbk_finalize(ctx_, NULL, NULL, NULL, NULL, NULL), "pbk_finalize");
+        }
         if (group_) check(pbk_group_neighbor_flags(group_, (uint32_t)keptMin_, keptKeys_.data(), flags.size(), flags.data()), "pbk_group_neighbor_flags");
         else check(pbk_neighbor_flags(ctx_, (uint32_t)keptMin_, keptKeys_.data(), flags.size(), flags.data()), "pbk_neighbor_flags");
         return flags;
@@ -319,6 +380,85 @@ public:
     }
 
 private:
+    void dropContext()
+    {
+        if (ctx_) { pbk_destroy(ctx_); ctx_ = NULL; }
+        ctxIsPass_ = false;
+    }
+    // passes hash-range passes over everything feed pushes; every pass's entries go to an unlinked temporary file of
+    // (key words, u16 count) records -- the layout of the reference's kmerFP (counter.h:494-495)
+    template <typename Feed>
+    u64_t countInPasses(u64_t kLength, u64_t memory, unsigned passes, const Feed &feed, const uint64_t *seedKeys, const uint16_t *seedValues,
+                        uint64_t nSeeds)
+    {
+        const size_t W = (size_t)((kLength + 31) / 32);
+        if (passFP_) { fclose(passFP_); passFP_ = NULL; }
+        passFP_ = makeTemporaryFile(tmpDir_);
+        std::vector<u64_t> occTotal(PBK_OCC_BINS, 0), occ(PBK_OCC_BINS, 0);
+        lengthDistribution_.assign(PBK_LEN_BINS, 0);
+        uint64_t ndTotal = 0, niTotal = 0;
+        std::vector<uint64_t> keys;
+        std::vector<uint16_t> counts;
+        for (unsigned p = 0; p < passes; ++p) {
+            beginPass(kLength, passes, p);
+            if (nSeeds) seedEntries(seedKeys, seedValues, nSeeds);
+            feed(*this);
+            uint64_t nd = 0, ni = 0, mx = 0, n = 0;
+            // (every pass sees every read: the read-length distribution is the same each time, the first pass's is kept)
+            check(pbk_finalize(ctx_, (uint64_t *)occ.data(), p == 0 ? (uint64_t *)lengthDistribution_.data() : NULL, &nd, &ni, &mx), "pbk_finalize");
+            for (size_t i = 0; i < occ.size(); ++i) occTotal[i] += occ[i];
+            ndTotal += nd; niTotal += ni;
+            check(pbk_export(ctx_, 1, 0, NULL, NULL, 0, &n), "pbk_export");
+            keys.assign(n * W, 0); counts.assign(n, 0);
+            if (n) check(pbk_export(ctx_, 1, 0, keys.data(), counts.data(), n, &n), "pbk_export");
+            for (uint64_t i = 0; i < n; ++i)
+                if (fwrite(&keys[i * W], 8, W, passFP_) != W || fwrite(&counts[i], 2, 1, passFP_) != 1) throw TMPError();
+            dropContext();
+        }
+        occurrenceDistribution_.swap(occTotal);
+        nDistinct_ = ndTotal; nInstances_ = niTotal;
+        if (ndTotal) {
+            for (size_t i = PBK_OCC_BINS - 1; i > 0; --i) if (occurrenceDistribution_[i]) { maxOccurrence_ = i; break; }     // counter.h:371-376
+        }
+        multiPass_ = true; passes_ = passes; keptValid_ = false;
+        doubleHashSize_ = pbk_double_hash_size(memory, (uint32_t)kLength);
+        return doubleHashSize_;
+    }
+    // exportKmers after a multi-pass count: the records of the pass file with count >= minOccurrence; sorted = ascending in
+    // the reference's numeric order (top word first, binstr.h:460-466)
+    void exportFromPassFile(u64_t minOccurrence, bool sorted)
+    {
+        const size_t W = (size_t)((kmerLength_ + 31) / 32);
+        std::vector<uint64_t> keys;
+        std::vector<uint16_t> counts;
+        rewind(passFP_);
+        std::vector<uint64_t> key(W);
+        uint16_t c;
+        while (fread(key.data(), 8, W, passFP_) == W) {
+            if (fread(&c, 2, 1, passFP_) != 1) throw TMPError();
+            if (c < minOccurrence) continue;
+            keys.insert(keys.end(), key.begin(), key.end());
+            counts.push_back(c);
+        }
+        const size_t n = counts.size();
+        if (sorted && n > 1) {
+            std::vector<size_t> order(n);
+            for (size_t i = 0; i < n; ++i) order[i] = i;
+            const uint64_t *kp = keys.data();
+            std::sort(order.begin(), order.end(), [kp, W](size_t a, size_t b) {
+                for (size_t j = W; j-- > 0;) if (kp[a * W + j] != kp[b * W + j]) return kp[a * W + j] < kp[b * W + j];
+                return false;
+            });
+            keptKeys_.resize(n * W); keptCounts_.resize(n);
+            for (size_t i = 0; i < n; ++i) {
+                for (size_t j = 0; j < W; ++j) keptKeys_[i * W + j] = keys[order[i] * W + j];
+                keptCounts_[i] = counts[order[i]];
+            }
+        } else {
+            keptKeys_.swap(keys); keptCounts_.swap(counts);
+        }
+        keptMin_ = minOccurrence; keptValid_ = true;
+    }
     void check(int rc, const char *what)
     {
         if (rc == PBK_OK) return;
@@ -329,6 +469,7 @@ private:
         if (ctx_ && pbk_last_error(ctx_)[0]) m += std::string(" (") + pbk_last_error(ctx_) + ")";
         if (group_ && pbk_group_last_error(group_)[0]) m += std::string(" (") + pbk_group_last_error(group_) + ")";
         if (rc == PBK_E_BAD_BASE) throw ReadError(m);
+        if (rc == PBK_E_NOMEM) throw NoMemory(m);
         throw GPUError(m);
     }
     double average(const std::vector<u64_t> &dist, u64_t start, u64_t end) const
@@ -361,6 +502,12 @@ private:
     std::vector<uint16_t> keptCounts_;
     u64_t keptMin_ = 0, loadSize_ = 0;
     bool keptValid_ = false;
+    // hash-range passes (a table beyond the HBM budget)
+    u64_t hbmBudget_ = 0;
+    std::string tmpDir_ = ".";
+    FILE *passFP_ = NULL;           // (key words, u16 count) records of all passes
+    bool multiPass_ = false, ctxIsPass_ = false;
+    unsigned passes_ = 1;
 };
 
 }  // namespace pbk

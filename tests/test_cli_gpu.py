@@ -63,6 +63,37 @@ def test_pbk_assemble_matches_the_reference_program(oracle, cli, k, repeat, seq_
 
 
 @needs_ref
+@pytest.mark.parametrize("how", ["budget", "three_passes"])
+def test_pbk_assemble_counts_in_hash_range_passes_when_the_table_does_not_fit(oracle, cli, how, tmp_path):
+    """A table beyond the HBM budget (the reference's memory-limited mode writes the k-mers that found no room
+    to temporary files and counts them in further rounds, counter.h:340-364, 442-449): pbk_assemble falls back from the streaming
+    ingest to the SEQ temp files and pbk::Counter counts them in 2, 4, ... hash-range passes (pbk_config.n_passes), each pass's
+    entries collected in a temporary file -- same .tsv, same table, same markers as the reference program.
+    `budget`: PBK_HBM_BUDGET_MB leaves less room than the k = 40 table of this input needs next to the fixed buffers;
+    `three_passes`: the pass count given outright (PBK_NUM_PASSES), through -seq_tmp."""
+    O = oracle
+    k = 40
+    rs = synth.make_reads(synth.config("C1", scale=1 / 100))
+    files = synth.write_fastq(rs, str(tmp_path / "r_1.fq"), str(tmp_path / "r_2.fq"))
+    ref = O.run_reference(files, k, str(tmp_path), threads=min(8, os.cpu_count() or 1), mem_gb=1)
+    assert ref.returncode == 0, ref.stderr
+    if how == "budget":
+        p = run_ours(cli, files, k, str(tmp_path), env={"PBK_HBM_BUDGET_MB": "150", "PBK_TIMING": "1"})
+    else:
+        p = run_ours(cli, files, k, str(tmp_path), extra=("-seq_tmp",), env={"PBK_NUM_PASSES": "3", "PBK_TIMING": "1"})
+    assert p.returncode == 0, p.stderr
+    m = re.search(r"counted in (\d+) hash-range passes", p.stderr)
+    assert m and int(m.group(1)) >= 2, p.stderr[-1500:]
+    assert markers(p.stderr, k) == markers(ref.stderr, k)
+    assert open(tmp_path / f"gpu_{k}merFrq.tsv").read() == ref.tsv
+    t = O.read_bin(str(tmp_path / "gpu_kmer_occ.bin"))
+    assert t.reachable and t.k == k and t.index_size == ref.table.index_size
+    gk, gc = t.sorted_dump()
+    rk, rc = ref.table.sorted_dump()
+    assert np.array_equal(gk, rk) and np.array_equal(gc, rc)
+
+
+@needs_ref
 @pytest.mark.parametrize("k", [32, 75])
 def test_reference_kmer_divide_reads_our_bin(oracle, cli, k, tmp_path):
     """Consumer test: the reference's `kmer_divide -k <bin> -f contigs` (kmer_divide.cpp:71-197) must produce the

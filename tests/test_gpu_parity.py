@@ -336,6 +336,32 @@ def test_logical_shards_on_one_gpu_match_unsharded(oracle, k, n_shards):
             kc.close()
 
 
+@pytest.mark.parametrize("k,partition", [(21, True), (32, "force"), (40, "force"), (75, True), (75, "force")])
+def test_hash_range_passes_add_up_to_the_whole_count(oracle, k, partition):
+    """pbk_config.n_passes: three contexts, each counting one hash range of the same reads (pushed in two batches), hold disjoint
+    key sets whose union, histogram sum and instance sum are the unsharded count -- which is the oracle's."""
+    O = oracle
+    rs = synth.make_reads(synth.config("C1", scale=1 / 400))
+    want = O.count(_oracle_reads_from_set(O, rs), k)
+    b, o = rs.flat()
+    n = len(o) - 1
+    h = n // 2
+    keys, cts, hist, inst = [], [], np.zeros(65535, np.uint64), 0
+    for p in range(3):
+        with KmerCounter(k, partition=partition, n_passes=3, pass_index=p) as kc:
+            kc.push_reads(b[:int(o[h])], o[:h + 1])
+            kc.push_reads(b[int(o[h]):], o[h:] - o[h])
+            kc.finalize()
+            kk, cc = kc.export(1, sorted=True)
+            keys.append(kk); cts.append(cc); hist += kc.occ_hist; inst += kc.n_instances
+            assert len(kk) > 0
+    keys = np.concatenate(keys); cts = np.concatenate(cts)
+    order = np.lexsort(tuple(keys[:, w] for w in range(keys.shape[1])))
+    assert inst == want.n_instances
+    assert np.array_equal(hist, want.occ_hist)
+    assert np.array_equal(keys[order], want.keys) and np.array_equal(cts[order], want.counts)
+
+
 def test_table_growth_from_a_tiny_hint(oracle):
     O = oracle
     rs = synth.make_reads(synth.config("C3", scale=1 / 200))

@@ -62,6 +62,18 @@ def test_patched_reference_full_assemble_on_the_emulated_abi(tmp_path):
 
 
 @needs_bins
+def test_patched_reference_in_hash_range_passes_on_the_emulated_abi(tmp_path):
+    """The same full assemble with every count of the iterative schedule done in THREE hash-range passes over the SEQ temp files
+    (PBK_NUM_PASSES: what pbk::Counter does by itself when a table does not fit the HBM budget -- the counterpart of the
+    reference's temp-file rounds, counter.h:340-364): first-k counting, the seeded counts of the later k, the entries published
+    to kmerFP from the passes' temporary file -- byte-identical contigs, .tsv and log."""
+    import emul_helper
+    emul_helper.abi_cli_path()
+    env = {"LD_LIBRARY_PATH": os.path.join(ROOT, "tests", "cpu_emul", "_build", "cli"), "PBK_NUM_PASSES": "3"}
+    _full_assemble_is_identical(tmp_path, 30_000, 40.0, env)
+
+
+@needs_bins
 def test_patched_reference_long_reads_up_to_four_word_keys_on_the_emulated_abi(tmp_path):
     """2x250 bp reads (config C3 scaled down): the reference's own schedule runs k = 32, 42, ... 122, 125, i.e. Kmer31, Binstr63,
     Binstr95 and Binstr127 keys, with coverage cutoffs 3 -> 1 along the way."""
