@@ -70,6 +70,15 @@ def ncu_traffic_bytes(split_build=False):
         return None
 
 
+def atomic_peak_gops():
+    """Best measured rate of the operation Pass B consists of (profiles/r1b_atomics_sweep.json, mode "sweep 64 regions, atom64-ret")."""
+    try:
+        rows = json.load(open(os.path.join(ROOT, "profiles", "r1b_atomics_sweep.json")))["results"]
+        return max(r["gops"] for r in rows if r["mode"].startswith("sweep 64 regions") and r["mode"].endswith("atom64-ret") and "stream" not in r["mode"])
+    except Exception:
+        return 130.0
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -544,6 +553,16 @@ def main_ours(args):
                                      "(profiles/r1a_atomics_microbench.json, profiles/r1b_atomics_sweep.json, profiles/r1c_warp_ops_microbench.jsonl); Pass B alone "
                                      "runs at instances / ms_per_step.bucket_insert_compact_kernel; its second form (split_kernel + region_build_kernel) "
                                      "sends no atomics to the L2 at all"}
+
+    # north_star quotes the fraction of the "HBM/atomic roofline": next to the HBM figure above, Pass B (first form, one-word keys)
+    # against the measured rate of what it is made of -- one 64-bit atomic with return per instance on an L2-resident table region
+    if W == 1 and not split_build and d_res["ms_insert"] > 0:
+        peak_atomics = atomic_peak_gops()
+        ach = n_inst_local * args.steps / (d_res["ms_insert"] * 1e-3) / 1e9
+        roofline["atomic"] = {"bound": "l2_atomic", "kernel": "bucket_insert_gather_kernel" if (pull or keyx) else "bucket_insert_compact_kernel<0>",
+                              "achieved": ach, "peak": peak_atomics, "unit": "G atomics/s", "frac": ach / peak_atomics if peak_atomics else None,
+                              "peak_source": "profiles/r1b_atomics_sweep.json (pbk_microbench_atomics: uniform-random 64-bit atomicAdd with return, 1 GiB table swept "
+                                             "in 64 L2-resident regions; committed measurement on a B200 of this pool, not repeated in this run)"}
 
     line = None
     if rank == 0:
