@@ -35,9 +35,11 @@ constexpr double MAX_LOAD_COMPACT = 0.6;          // k <= 32: capacity is a powe
 constexpr u64 U32_HEADROOM = (1ull << 32) - 65536 - 2;
 constexpr u64 PART_MIN_WINDOWS = 1ull << 22;    // smaller batches go straight to the table
 // Second form of Pass B for one-word keys (split_kernel + region_build_kernel: sub-regions of the table built in shared memory,
-// no L2 atomics): the default for a context's own bucket store; PBK_PASSB2=0 / 1 overrides.  For the key exchange it stays
-// opt-in (PBK_PASSB2_GATHER=1): there Pass B's time is the NVLink transfer of the keys, which the first form overlaps with its
-// atomics tile by tile, while split_gather_kernel would only move them.
+// no L2 atomics): opt-in, PBK_PASSB2=1 for a context's own bucket store, PBK_PASSB2_GATHER=1 on top for the key / pull exchange.
+// Measured on a B200 (profiles/r2m_variants.jsonl): 3.50 ms against 3.72 ms for the first form on device-resident C1, but 13.2
+// against 12.5 ms from host buffers (every chunk group reads and rewrites the whole table), for 4.4 GB more store -- not the
+// default.  For the exchange, Pass B's time is the NVLink transfer of the keys, which the first form overlaps with its atomics
+// tile by tile, while split_gather_kernel would only move them.
 constexpr bool PASSB2_DEFAULT = false;
 constexpr u64 MAX_PUSH_BASES = 1ull << 31;       // larger pushes are cut into internal batches (2 Gi bases: 16 GiB of bucket store at k <= 32)
 
