@@ -73,7 +73,7 @@ def one_case(rng, case_no):
     rd = oracle_reads(reads)
     want = O.count(rd, k)
     b, o = as_arrays(reads)
-    mode = rng.choice(["plain", "multi_push", "seeded", "lookup", "records", "keys", "contigs"])
+    mode = rng.choice(["plain", "multi_push", "seeded", "lookup", "records", "keys", "contigs", "passes"])
     if mode == "keys" and W > 1:
         mode = "records"
     partition = rng.choice([True, "force", False])
@@ -94,6 +94,32 @@ def one_case(rng, case_no):
             kc.push_reads(b, o)
             kc.finalize()
             check_table(kc, want, desc + " (after reset)")
+    elif mode == "passes":
+        # hash-range passes on one GPU (pbk_config.n_passes): disjoint key sets that add up to the whole count; seeds are handed
+        # to every pass, the library keeps those of its range
+        P = rng.randint(2, 5)
+        seeded = rng.random() < 0.4 and len(want.counts) > 0
+        ref = want
+        if seeded:
+            sel = np.array([rng.random() < 0.3 for _ in range(len(want.counts))], bool)
+            sk, sc = np.ascontiguousarray(want.keys[sel]), np.array([rng.randint(1, 300) for _ in range(int(sel.sum()))], np.uint16)
+            ref = O.count(rd, k, sk, sc)
+        keys, cts, hist, inst = [], [], np.zeros(65535, np.uint64), 0
+        for p in range(P):
+            with KmerCounter(k, partition=partition, pipeline=pipeline, n_passes=P, pass_index=p) as kc:
+                h = rng.randint(0, len(reads))
+                if seeded:
+                    kc.seed_entries(sk, sc)
+                kc.push_reads(b[:int(o[h])], o[:h + 1]); kc.push_reads(b[int(o[h]):], o[h:] - o[h])
+                kc.finalize()
+                kk, cc = kc.export(1, sorted=True)
+                keys.append(kk); cts.append(cc); hist += kc.occ_hist; inst += kc.n_instances
+        keys = np.concatenate(keys); cts = np.concatenate(cts)
+        order = np.lexsort(tuple(keys[:, w] for w in range(W)))
+        assert np.array_equal(keys[order], ref.keys) and np.array_equal(cts[order], ref.counts), desc
+        assert np.array_equal(hist, ref.occ_hist), desc
+        if not seeded:
+            assert inst == want.n_instances, desc
     elif mode == "seeded":
         sel = np.array([rng.random() < 0.3 for _ in range(len(want.counts))], bool)
         sk, sc = want.keys[sel], np.array([rng.randint(0, 300) for _ in range(int(sel.sum()))], np.uint16)
