@@ -41,7 +41,7 @@ SELECTION = (
     + [f"tests/test_gpu_parity.py::test_golden_cases_bit_exact[{c}]"
        for c in ("kat_k4", "smallfq_k32", "smallfq_k75", "smallfa_k200", "cov_k21_auto", "multi_k32_n2", "sat_k32")]
     + ["tests/test_gpu_parity.py::test_table_growth_from_a_tiny_hint", "tests/test_gpu_parity.py::test_error_behaviour",
-       "tests/test_gpu_parity.py::test_hash_range_passes_add_up_to_the_whole_count"])
+       "tests/test_gpu_parity.py::test_hash_range_passes_add_up_to_the_whole_count", "tests/test_gpu_parity.py::test_config_layouts_and_pass_arguments"])
 # (tests/test_gpu_parity.py::test_pipelined_pass_overlap_gives_the_identical_table also passes this way, but its batch of > 4 M
 #  windows takes 80 s in the emulation: run by hand when the chained Pass A -> Pass B route of pbk_api.cu changes)
 

@@ -376,6 +376,36 @@ def test_table_growth_from_a_tiny_hint(oracle):
     assert np.array_equal(keys, want.keys) and np.array_equal(counts, want.counts)
 
 
+def test_config_layouts_and_pass_arguments():
+    """pbk_create takes the earlier, shorter pbk_config (struct_size 40: no n_passes / pass_index) as "no passes", refuses anything
+    shorter, and refuses pass arguments that make no sense (index >= count, passes together with shards)."""
+    import ctypes as C
+    from platanus_b_b200 import capi
+    L = capi.load_library()
+
+    class ConfigV1(C.Structure):
+        _fields_ = [("struct_size", C.c_uint32), ("k", C.c_uint32), ("device", C.c_int32), ("flags", C.c_uint32),
+                    ("n_shards", C.c_uint32), ("shard_rank", C.c_uint32), ("table_slots_hint", C.c_uint64), ("hbm_budget_bytes", C.c_uint64)]
+
+    assert C.sizeof(ConfigV1) == 40 and C.sizeof(capi.PbkConfig) == 48
+    create = L.pbk_create
+    ctx = C.c_void_p()
+    v1 = ConfigV1(40, 21, -1, 0, 0, 0, 0, 0)
+    rc = create(C.byref(ctx), C.cast(C.byref(v1), C.POINTER(capi.PbkConfig)))
+    assert rc == 0 and ctx.value
+    L.pbk_destroy(ctx)
+    v1.struct_size = 39
+    assert create(C.byref(ctx), C.cast(C.byref(v1), C.POINTER(capi.PbkConfig))) == -1           # PBK_E_ARG
+    for kw in (dict(n_passes=3, pass_index=3), dict(n_passes=2, pass_index=0, n_shards=2, shard_rank=1)):
+        with pytest.raises(PbkError) as e:
+            KmerCounter(21, **kw)
+        assert e.value.status == -1
+    with KmerCounter(21, n_passes=2, pass_index=1) as kc:                                             # contigs are not available in a pass
+        with pytest.raises(PbkError) as e:
+            kc.push_contigs(np.frombuffer(b"ACGTACGTACGTACGTACGTACGTACGT", np.uint8), np.array([0, 28], np.uint64), np.array([5], np.uint16), 1)
+        assert e.value.status == -8
+
+
 def test_error_behaviour():
     bad = np.frombuffer(b"ACGTACGTACGTACGTRYACGTACGTACGTACGTACGTACGTACGT", dtype=np.uint8)
     with KmerCounter(8) as kc:
